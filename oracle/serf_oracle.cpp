@@ -1,0 +1,898 @@
+// serf_oracle.cpp — CPU restatement of serf-core's membership state-merge path.
+//
+//   *** TEST INFRASTRUCTURE — NOT PART OF THE PRODUCT. ***
+//   Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+//   legs may load this library.  The product (serf_b200/csrc) never links or calls it.
+//
+// Parity status
+//   * serf half (LamportClock, intent buffer, handle_node_{join,leave}[_intent], push-pull
+//     ordering, reaper, queue cap): PINNED by the reference's own known-answer tests,
+//     replayed literally in tests/test_oracle_kat.py (list: SURVEY.md §8c).
+//   * SWIM half (alive/suspect/dead merge, incarnation, suspicion timer, retransmit limit,
+//     gossip fan-out): the algorithm lives in the un-vendored dependency
+//     memberlist-core = "0.8.1" (reference Cargo.toml:40, no Cargo.lock), a port of
+//     hashicorp/memberlist.  Restated here from the published SWIM + Lifeguard algorithm
+//     and upstream behaviour; the reference tree holds no test that pins it:
+//     PARITY UNPINNED for that half.
+//
+// Two models live here:
+//   Part A  RefNode   — ONE serf node, literal: HashMap-like tables keyed by id, the
+//                       recent-intent buffer, left/failed lists, a TransmitLimitedQueue.
+//                       This is what the reference KATs are replayed against.
+//   Part B  TickSim   — N virtual nodes × R tracked subjects, bulk-synchronous ticks, the
+//                       message set of every destination applied ONE MESSAGE AT A TIME in
+//                       the canonical order (DESIGN.md §"Tick semantics").  The CUDA path
+//                       must reproduce its records, clocks and per-tick trace bit-exactly.
+//
+// All `file:line` citations are relative to /root/reference/serf-core/src/.
+//
+// Build: see oracle/Makefile (g++ -O2 -shared -fPIC).  Plain C ABI at the bottom (ctypes).
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../include/serfsim.h"   // config / stats / trace-row struct layouts and constants only
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+// =====================================================================================
+// Shared primitives
+// =====================================================================================
+
+// MemberStatus — types/member.rs:54-58
+enum : u8 { ST_NONE = 0, ST_ALIVE = 1, ST_LEAVING = 2, ST_LEFT = 3, ST_FAILED = 4 };
+// MessageType tags — types/message.rs:17-18
+enum : u8 { TY_NONE = 0, TY_LEAVE = 1, TY_JOIN = 2 };
+// memberlist node states (external crate; restated)
+enum : u8 { ML_ALIVE = 0, ML_SUSPECT = 1, ML_DEAD = 2, ML_LEFT = 3 };
+// SerfState — serf.rs (Alive, Leaving, Left, Shutdown)
+enum : u8 { SS_ALIVE = 0, SS_LEAVING = 1, SS_LEFT = 2 };
+
+// LamportClock — types/clock.rs:121-173
+struct LamportClock {
+  u64 v = 0;
+  u64 time() const { return v; }                        // clock.rs:142-145
+  u64 increment() { v += 1; return v; }                 // clock.rs:148-151 (fetch_add(1) + 1)
+  void witness(u64 t) {                                 // clock.rs:155-172
+    if (t < v) return;                                  // "If the other value is old, we do not need to do anything"
+    v = t + 1;                                          // CAS(cur → t + 1)
+  }
+};
+
+// memberlist retransmit limit: retransmit_mult * ceil(log10(n + 1))   [external; SURVEY §8c]
+static u32 retransmit_limit(u32 mult, u64 n) {
+  u32 digits = 0;          // smallest k with 10^k >= n + 1  == ceil(log10(n+1)) in exact arithmetic
+  u64 p = 1;
+  while (p < n + 1) { p *= 10; ++digits; }
+  return mult * digits;
+}
+
+// memberlist suspicion timeouts in ticks [external; SURVEY §8c]:
+//   min = suspicion_mult * max(1, log10(max(1,n))) * probe_interval   (ms arithmetic as upstream:
+//         mult * int(node_scale*1000) * interval / 1000),  max = suspicion_max_timeout_mult * min,
+//   k   = suspicion_mult - 2 (0 when n - 2 < k),
+//   timeout(c) = max - log(c+1)/log(k+1) * (max - min), floored to ms, >= min;  k < 1 → min.
+// Returned table has k+1 entries, each ceil(ms / tick_ms), at least 1.
+static std::vector<u32> suspicion_table(u32 susp_mult, u32 max_mult, u32 probe_ticks, u32 tick_ms, u64 n) {
+  double node_scale = std::max(1.0, std::log10(std::max(1.0, (double)n)));
+  int64_t interval_ms = (int64_t)probe_ticks * tick_ms;
+  int64_t min_ms = (int64_t)susp_mult * (int64_t)(node_scale * 1000.0) * interval_ms / 1000;
+  int64_t max_ms = (int64_t)max_mult * min_ms;
+  int64_t k = (int64_t)susp_mult - 2;
+  if ((int64_t)n - 2 < k) k = 0;
+  if (k < 0) k = 0;
+  std::vector<u32> tab;
+  for (int64_t c = 0; c <= k; ++c) {
+    int64_t ms;
+    if (k < 1) ms = min_ms;
+    else {
+      double frac = std::log((double)c + 1.0) / std::log((double)k + 1.0);
+      double raw = (double)max_ms - frac * (double)(max_ms - min_ms);
+      ms = (int64_t)std::floor(raw);
+      if (ms < min_ms) ms = min_ms;
+    }
+    int64_t ticks = (ms + tick_ms - 1) / tick_ms;
+    if (ticks < 1) ticks = 1;
+    tab.push_back((u32)ticks);
+  }
+  return tab;
+}
+
+// Philox4x32-10 (Salmon et al., SC'11), the counter RNG both sides use.
+static inline void philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, u32 k0, u32 k1, u32 out[4]) {
+  const u32 M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  for (int r = 0; r < 10; ++r) {
+    u64 p0 = (u64)M0 * c0, p1 = (u64)M1 * c2;
+    u32 hi0 = (u32)(p0 >> 32), lo0 = (u32)p0, hi1 = (u32)(p1 >> 32), lo1 = (u32)p1;
+    u32 n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+static inline u32 mulhi32(u32 a, u32 b) { return (u32)(((u64)a * b) >> 32); }
+
+enum : u32 { DOMAIN_GOSSIP = 0, DOMAIN_PROBE = 1 };
+
+static inline u64 mix64(u64 x) {   // splitmix64 finaliser
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL;
+  x ^= x >> 27; x *= 0x94d049bb133111ebULL;
+  x ^= x >> 31; return x;
+}
+static inline u32 from_hash(u32 node) { return (node * 0x9E3779B1u) >> 28; }   // 4-bit confirmer bucket
+
+// =====================================================================================
+// Part A — RefNode: one serf node, literal tables
+// =====================================================================================
+
+struct MemberStateA { u8 status; u64 status_time; bool has_leave_time; int64_t leave_time_ms; };   // types/member.rs:20-26
+struct NodeIntentA { u8 ty; int64_t wall_ms; u64 ltime; };                                          // types/member.rs:30-34
+struct QueuedA { u8 ty; u64 ltime; u64 id; bool prune; u32 transmits; u64 seq; u32 len; bool notify; };
+
+struct RefNode {
+  u64 self_id;
+  u8 serf_state = SS_ALIVE;
+  LamportClock clock, event_clock, query_clock;                 // serf.rs:138-140
+  std::map<u64, MemberStateA> states;                           // Members.states          types/member.rs:37
+  std::map<u64, NodeIntentA> recent_intents;                    // Members.recent_intents  types/member.rs:38
+  std::vector<std::pair<u64, MemberStateA>> left_members, failed_members;   // types/member.rs:39-40
+  std::vector<QueuedA> broadcasts;                              // intent TransmitLimitedQueue, base.rs:179-190
+  u32 retransmit_mult = 4;
+  u64 seq = 0;
+  u32 refutes = 0;          // number of spawned broadcast_join refutations (base.rs:1470-1480)
+  std::vector<std::pair<u32, u64>> events;   // (MemberEventType, id) in emission order
+
+  explicit RefNode(u64 id) : self_id(id) {
+    // base.rs:198-200: all three clocks are incremented once at construction.
+    clock.increment(); event_clock.increment(); query_clock.increment();
+    // base.rs:269-272: notify_join(local) inserts self (Alive, status_time 0).
+    states[id] = MemberStateA{ST_ALIVE, 0, false, 0};
+  }
+
+  // base.rs:1817-1866 -----------------------------------------------------------------
+  bool upsert_intent(u64 id, u8 ty, u64 ltime, int64_t wall_ms) {
+    auto it = recent_intents.find(id);
+    if (it != recent_intents.end()) {                       // Entry::Occupied
+      if (ltime > it->second.ltime) {
+        it->second.ty = ty; it->second.ltime = ltime; it->second.wall_ms = wall_ms;
+        return true;
+      }
+      return false;
+    }
+    recent_intents[id] = NodeIntentA{ty, wall_ms, ltime};   // Entry::Vacant
+    return true;
+  }
+  bool recent_intent(u64 id, u8 ty, u64* ltime) const {
+    auto it = recent_intents.find(id);
+    if (it != recent_intents.end() && it->second.ty == ty) { *ltime = it->second.ltime; return true; }
+    return false;
+  }
+  void reap_intents(int64_t now_ms, int64_t timeout_ms) {   // retain (now - wall) <= timeout
+    for (auto it = recent_intents.begin(); it != recent_intents.end();) {
+      if ((now_ms - it->second.wall_ms) <= timeout_ms) ++it; else it = recent_intents.erase(it);
+    }
+  }
+  static void remove_old_member(std::vector<std::pair<u64, MemberStateA>>& old, u64 id) {   // base.rs:1813-1815
+    old.erase(std::remove_if(old.begin(), old.end(), [&](auto& m) { return m.first == id; }), old.end());
+  }
+
+  // base.rs:364-375 + the external TransmitLimitedQueue.queue_broadcast (SerfBroadcast never
+  // invalidates: broadcast.rs:24-30).
+  void queue(u8 ty, u64 ltime, u64 id, bool prune, bool notify) {
+    broadcasts.push_back(QueuedA{ty, ltime, id, prune, 0, seq++, 24, notify});
+  }
+
+  // base.rs:1338-1373 -----------------------------------------------------------------
+  bool handle_node_join_intent(u64 ltime, u64 id, int64_t now_ms = 0) {
+    clock.witness(ltime);                                   // :1340
+    auto it = states.find(id);
+    if (it != states.end()) {
+      MemberStateA& m = it->second;
+      if (ltime <= m.status_time) return false;             // :1346
+      m.status_time = ltime;                                // :1351
+      if (m.status == ST_LEAVING) m.status = ST_ALIVE;      // :1356-1358
+      return true;
+    }
+    return upsert_intent(id, TY_JOIN, ltime, now_ms);       // :1362-1370
+  }
+
+  // base.rs:381-397
+  void broadcast_join(u64 ltime) {
+    clock.witness(ltime);
+    handle_node_join_intent(ltime, self_id);
+    queue(TY_JOIN, ltime, self_id, false, false);
+  }
+
+  // base.rs:1442-1572 -----------------------------------------------------------------
+  // Returns rebroadcast.  A refutation (":1470-1480", spawn_detach(broadcast_join)) is
+  // recorded in `refute_pending`; run_detached() executes it (the reference runs it on
+  // another task "since we have the memberLock").
+  bool refute_pending = false;
+  bool handle_node_leave_intent(u64 ltime, u64 id, bool prune, int64_t now_ms = 0) {
+    u8 state = serf_state;                                  // :1443
+    clock.witness(ltime);                                   // :1446
+    auto it = states.find(id);
+    if (it == states.end())                                 // :1450-1458
+      return upsert_intent(id, TY_LEAVE, ltime, now_ms);
+    MemberStateA& m = it->second;
+    if (ltime <= m.status_time) return false;               // :1464
+    if (id == self_id && state == SS_ALIVE) {               // :1470-1480 refute
+      refute_pending = true; ++refutes;
+      return false;
+    }
+    m.status_time = ltime;                                  // :1497 — always, before the switch
+    switch (m.status) {
+      case ST_NONE: return false;                           // :1501
+      case ST_ALIVE:                                        // :1502-1511
+        m.status = ST_LEAVING;
+        if (prune) handle_prune(id);
+        return true;
+      case ST_LEAVING: case ST_LEFT:                        // :1512-1519
+        if (prune) handle_prune(id);
+        return true;
+      case ST_FAILED: {                                     // :1520-1559
+        m.status = ST_LEFT;
+        MemberStateA owned = m;
+        remove_old_member(failed_members, id);
+        left_members.push_back({id, owned});
+        events.push_back({SERFSIM_EVENT_LEAVE, id});
+        if (prune) handle_prune(id);
+        return true;
+      }
+      default:                                              // :1560-1570 unknown status
+        m.status = ST_LEAVING;
+        if (prune) handle_prune(id);
+        return true;
+    }
+  }
+  void run_detached() { if (refute_pending) { refute_pending = false; broadcast_join(clock.time()); } }
+
+  // base.rs:1628-1653 (the Leaving-state sleep is wall-clock only; erase is immediate here)
+  void handle_prune(u64 id) {
+    auto it = states.find(id);
+    if (it == states.end()) return;
+    u8 ms = it->second.status;
+    if (ms == ST_LEAVING || ms == ST_LEFT) remove_old_member(left_members, id);
+    states.erase(it);                                       // erase_node! :499-519
+    events.push_back({SERFSIM_EVENT_REAP, id});
+  }
+
+  // base.rs:1206-1334 -----------------------------------------------------------------
+  void handle_node_join(u64 id) {
+    auto it = states.find(id);
+    u8 old_status;
+    if (it != states.end()) {
+      old_status = it->second.status;
+      it->second.status = ST_ALIVE;                         // :1251-1263 (status_time kept, leave_time None)
+      it->second.has_leave_time = false;
+    } else {
+      u8 status = ST_ALIVE; u64 status_ltime = 0, t;        // :1276-1288
+      if (recent_intent(id, TY_JOIN, &t)) status_ltime = t;
+      if (recent_intent(id, TY_LEAVE, &t)) { status_ltime = t; status = ST_LEAVING; }
+      states[id] = MemberStateA{status, status_ltime, false, 0};
+      old_status = ST_NONE;
+    }
+    events.push_back({SERFSIM_EVENT_JOIN, id});
+    if (old_status == ST_FAILED || old_status == ST_LEFT) { // :1317-1320
+      remove_old_member(failed_members, id);
+      remove_old_member(left_members, id);
+    }
+  }
+
+  // base.rs:1375-1440 -----------------------------------------------------------------
+  void handle_node_leave(u64 id, int64_t now_ms) {
+    auto it = states.find(id);
+    if (it == states.end()) return;                         // :1378-1380
+    MemberStateA& m = it->second;
+    if (m.status == ST_LEAVING) {                           // :1384-1393
+      m.status = ST_LEFT; m.has_leave_time = true; m.leave_time_ms = now_ms;
+      left_members.push_back({id, m});
+      events.push_back({SERFSIM_EVENT_LEAVE, id});
+    } else if (m.status == ST_ALIVE) {                      // :1394-1402
+      m.status = ST_FAILED; m.has_leave_time = true; m.leave_time_ms = now_ms;
+      failed_members.push_back({id, m});
+      events.push_back({SERFSIM_EVENT_FAILED, id});
+    }                                                       // :1403-1406 anything else: warn + return
+  }
+
+  // serf/delegate.rs:427-554 (membership part) -----------------------------------------
+  void merge_remote_state(u64 pp_ltime, const u64* ids, const u64* ltimes, u32 n, const u64* left, u32 n_left,
+                          u64 event_ltime, u64 query_ltime) {
+    if (pp_ltime > 0) clock.witness(pp_ltime - 1);          // :466-468
+    if (event_ltime > 0) event_clock.witness(event_ltime - 1);
+    if (query_ltime > 0) query_clock.witness(query_ltime - 1);
+    auto find = [&](u64 id, u64* lt) { for (u32 i = 0; i < n; ++i) if (ids[i] == id) { *lt = ltimes[i]; return true; } return false; };
+    for (u32 i = 0; i < n_left; ++i) {                      // :495-510 left nodes first, ltime + 1
+      u64 lt;
+      if (find(left[i], &lt)) { handle_node_leave_intent(lt + 1, left[i], false); }
+    }
+    for (u32 i = 0; i < n; ++i) {                           // :513-523 then artificial joins
+      bool is_left = false;
+      for (u32 j = 0; j < n_left; ++j) if (left[j] == ids[i]) is_left = true;
+      if (is_left) continue;
+      handle_node_join_intent(ltimes[i], ids[i]);
+    }
+  }
+
+  // Local API — serf/api.rs:318-361 (join, after memberlist.join), :422-499 (leave),
+  // base.rs:454-480 (force_leave).  has_alive_members(): base.rs:346-359.
+  bool has_alive_members() const {
+    for (auto& kv : states) if (kv.first != self_id && kv.second.status == ST_ALIVE) return true;
+    return false;
+  }
+  void api_join() { broadcast_join(clock.time()); }
+  int api_leave() {
+    if (serf_state == SS_LEFT) return 0;
+    if (serf_state == SS_LEAVING) return -1;
+    serf_state = SS_LEAVING;
+    u64 t = clock.time();
+    clock.increment();
+    handle_node_leave_intent(t, self_id, false);
+    if (has_alive_members()) queue(TY_LEAVE, t, self_id, false, true);
+    return 0;
+  }
+  void api_force_leave(u64 id, bool prune) {
+    u64 t = clock.time();
+    handle_node_leave_intent(t, id, prune);
+    if (!has_alive_members()) return;
+    queue(TY_LEAVE, t, id, prune, true);
+  }
+
+  // External TransmitLimitedQueue.get_broadcasts restated: lowest transmit count first
+  // (ties: longer message, then newer), each pick increments transmits, entries reaching
+  // retransmit_limit(mult, NumMembers = states.len()) are dropped (finished()).
+  // serf.rs:109-131 (NumMembers), serf/delegate.rs:317-344.
+  u32 get_broadcasts(u32 byte_limit, u32 overhead, u8* ty_out, u64* lt_out, u64* id_out, u32 cap) {
+    u32 limit = retransmit_limit(retransmit_mult, states.size());
+    std::vector<size_t> order(broadcasts.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+      const QueuedA &x = broadcasts[a], &y = broadcasts[b];
+      if (x.transmits != y.transmits) return x.transmits < y.transmits;
+      if (x.len != y.len) return x.len > y.len;
+      return x.seq > y.seq;
+    });
+    u32 used = 0, n = 0;
+    std::vector<size_t> done;
+    for (size_t i : order) {
+      QueuedA& q = broadcasts[i];
+      if (used + overhead + q.len > byte_limit) continue;
+      used += overhead + q.len;
+      if (n < cap) { ty_out[n] = q.ty; lt_out[n] = q.ltime; id_out[n] = q.id; }
+      ++n;
+      if (++q.transmits >= limit) done.push_back(i);
+    }
+    std::sort(done.begin(), done.end());
+    for (size_t j = done.size(); j-- > 0;) broadcasts.erase(broadcasts.begin() + done[j]);
+    return n;
+  }
+
+  // Reaper — base.rs:483-610: reap!(failed, reconnect_timeout), reap!(left, tombstone_timeout),
+  // reap_intents(recent_intent_timeout).
+  void reap_list(std::vector<std::pair<u64, MemberStateA>>& list, int64_t now_ms, int64_t timeout_ms) {
+    size_t n = list.size(), i = 0;
+    while (i < n) {
+      auto m = list[i];
+      if (m.second.has_leave_time && (now_ms - m.second.leave_time_ms) <= timeout_ms) { ++i; continue; }   // :536-541
+      list[i] = list[n - 1]; list.pop_back(); --n;                                                        // swap_remove :544
+      states.erase(m.first);                                                                              // erase_node!
+      events.push_back({SERFSIM_EVENT_REAP, m.first});
+    }
+  }
+  void reap(int64_t now_ms, int64_t reconnect_timeout_ms, int64_t tombstone_timeout_ms, int64_t intent_timeout_ms) {
+    reap_list(failed_members, now_ms, reconnect_timeout_ms);
+    reap_list(left_members, now_ms, tombstone_timeout_ms);
+    reap_intents(now_ms, intent_timeout_ms);
+  }
+};
+
+// QueueChecker::get_queue_max — base.rs:728-739
+static u64 get_queue_max(u64 max_queue_depth, u64 min_queue_depth, u64 num_members) {
+  u64 max = max_queue_depth;
+  if (min_queue_depth > 0) {
+    max = num_members * 2;
+    if (max < min_queue_depth) max = min_queue_depth;
+  }
+  return max;
+}
+
+// =====================================================================================
+// Part B — TickSim: N nodes × R subject views, literal per-message application
+// =====================================================================================
+
+#pragma pack(push, 1)
+struct View {              // the 32-byte member record (DESIGN.md "Record layout")
+  u32 st;                  //  0 status_time, or buffered-intent ltime while !known
+  u32 qjoin;               //  4 ltime of the queued join intent
+  u32 qleave;              //  8 ltime of the queued leave intent
+  u32 inc;                 // 12 memberlist incarnation of the subject as seen
+  u32 deadline;            // 16 tick at which the suspicion timer fires (0 = none)
+  u32 leave_tick;          // 20 MemberState.leave_time as tick+1 (0 = None)
+  u8 status;               // 24 MemberStatus, or buffered-intent type while !known
+  u8 ml;                   // 25 bits 0-1 memberlist state, bits 2-5 from-hash of the queued suspect
+  u8 txj, txl, txm;        // 26-28 remaining transmits: join intent, leave intent, memberlist message
+  u8 flags;                // 29 bit0 = known (member present in Members.states)
+  u16 mask;                // 30 suspicion confirmer buckets
+};
+#pragma pack(pop)
+static_assert(sizeof(View) == 32, "record must be 32 bytes");
+
+static inline u8 ml_state(const View& r) { return r.ml & 3; }
+static inline void set_ml(View& r, u8 state, u8 fromh) { r.ml = (u8)((state & 3) | ((fromh & 15) << 2)); }
+static inline bool known(const View& r) { return r.flags & 1; }
+
+struct NodeB { u32 clock; u8 up; u8 sstate; };
+
+struct RuleCtx {            // per-run constants
+  u32 limit;                // retransmit limit
+  u32 k;                    // max confirmations
+  const u32* timeout;       // [k+1]
+};
+
+static inline void witness32(u32& c, u32 t) { if (t < c) return; c = t + 1; }   // clock.rs:155-172 on the device-width clock
+
+// --- serf-layer rules on a view (same statements as RefNode, on the packed record) ------
+static bool v_join_intent(View& r, u32 lt, const RuleCtx& cx) {            // base.rs:1338-1373 (witness done by caller)
+  bool acc;
+  if (known(r)) {
+    if (lt <= r.st) return false;
+    r.st = lt;
+    if (r.status == ST_LEAVING) r.status = ST_ALIVE;
+    acc = true;
+  } else {                                                                   // upsert_intent, base.rs:1838-1866
+    if (r.status == TY_NONE || lt > r.st) { r.status = TY_JOIN; r.st = lt; acc = true; } else acc = false;
+  }
+  if (acc) { r.qjoin = lt; r.txj = (u8)cx.limit; }                           // serf/delegate.rs:294-300 re-queue
+  return acc;
+}
+static bool v_leave_intent(View& r, u32 lt, bool self, u8 sstate, bool* refute, const RuleCtx& cx) {   // base.rs:1442-1572
+  bool acc;
+  if (!known(r)) {
+    if (r.status == TY_NONE || lt > r.st) { r.status = TY_LEAVE; r.st = lt; acc = true; } else acc = false;
+  } else {
+    if (lt <= r.st) return false;
+    if (self && sstate == SS_ALIVE) { *refute = true; return false; }
+    r.st = lt;
+    switch (r.status) {
+      case ST_NONE: acc = false; break;
+      case ST_ALIVE: r.status = ST_LEAVING; acc = true; break;
+      case ST_LEAVING: case ST_LEFT: acc = true; break;
+      case ST_FAILED: r.status = ST_LEFT; acc = true; break;
+      default: r.status = ST_LEAVING; acc = true; break;
+    }
+  }
+  if (acc) { r.qleave = lt; r.txl = (u8)cx.limit; }
+  return acc;
+}
+static void v_node_join(View& r) {                                           // base.rs:1206-1334
+  if (known(r)) { r.status = ST_ALIVE; r.leave_tick = 0; return; }
+  u8 status = ST_ALIVE; u32 st = 0;
+  if (r.status == TY_JOIN) st = r.st;
+  if (r.status == TY_LEAVE) { st = r.st; status = ST_LEAVING; }
+  r.status = status; r.st = st; r.flags |= 1; r.leave_tick = 0;
+}
+static void v_node_leave(View& r, u32 tick) {                                // base.rs:1375-1440
+  if (!known(r)) return;
+  if (r.status == ST_LEAVING) { r.status = ST_LEFT; r.leave_tick = tick + 1; }
+  else if (r.status == ST_ALIVE) { r.status = ST_FAILED; r.leave_tick = tick + 1; }
+}
+
+// --- memberlist rules on a view (external crate; restated from hashicorp/memberlist state.go
+//     aliveNode / suspectNode / deadNode / refute, which memberlist-core ports) -----------
+static void v_refute(View& r, u32 accused, const RuleCtx& cx) {
+  u32 inc = r.inc + 1;
+  if (accused >= inc) inc = accused + 1;
+  r.inc = inc;
+  set_ml(r, ML_ALIVE, 0);
+  r.txm = (u8)cx.limit;
+}
+static void v_ml_alive(View& r, u32 a, bool self, const RuleCtx& cx) {
+  if (a <= r.inc) return;                       // non-local: old incarnation; local: a < inc ignored, a == inc "same version"
+  if (self) { v_refute(r, a, cx); return; }
+  r.deadline = 0; r.mask = 0;                   // delete(nodeTimers)
+  u8 old = ml_state(r);
+  r.inc = a; set_ml(r, ML_ALIVE, 0); r.txm = (u8)cx.limit;
+  if (old == ML_DEAD || old == ML_LEFT) v_node_join(r);     // EventDelegate::notify_join, serf/delegate.rs:565
+}
+static void v_ml_suspect(View& r, u32 s, u32 fromh, u32 tick, bool self, const RuleCtx& cx) {
+  if (s < r.inc) return;
+  if (ml_state(r) == ML_SUSPECT) {              // timer exists → Confirm(from)
+    u32 n_old = (u32)__builtin_popcount(r.mask) - 1;
+    if (n_old >= cx.k) return;
+    if (r.mask & (1u << fromh)) return;
+    r.mask |= (u16)(1u << fromh);
+    r.deadline = r.deadline - cx.timeout[n_old] + cx.timeout[n_old + 1];
+    set_ml(r, ML_SUSPECT, (u8)fromh); r.txm = (u8)cx.limit;
+    return;
+  }
+  if (ml_state(r) != ML_ALIVE) return;
+  if (self) { v_refute(r, s, cx); return; }
+  r.inc = s; set_ml(r, ML_SUSPECT, (u8)fromh); r.mask = (u16)(1u << fromh);
+  r.deadline = tick + cx.timeout[0]; r.txm = (u8)cx.limit;
+}
+static void v_ml_dead(View& r, u32 d, bool left, u32 tick, bool self, const RuleCtx& cx) {
+  if (d < r.inc) return;
+  r.deadline = 0; r.mask = 0;                   // delete(nodeTimers)
+  u8 s = ml_state(r);
+  if (s == ML_DEAD || s == ML_LEFT) return;
+  if (self) { v_refute(r, d, cx); return; }     // a node that has left is already ML_LEFT (returned above)
+  r.inc = d; set_ml(r, left ? ML_LEFT : ML_DEAD, 0); r.txm = (u8)cx.limit;
+  v_node_leave(r, tick);                        // EventDelegate::notify_leave, serf/delegate.rs:571
+}
+static inline u32 ml_key(const View& r) { return (r.inc << 6) | ((u32)ml_state(r) << 4) | ((r.ml >> 2) & 15); }
+
+struct Msg { u32 dst, src, val; u8 slot, kind; };   // kind 0 leave, 1 join, 2 memberlist
+struct EventB { u32 tick, op, node, slot; };
+
+struct TickSim {
+  serfsim_config_t cfg;
+  u32 N, R, tick = 0;
+  std::vector<u64> row_ptr; std::vector<u32> col;
+  std::vector<u32> subj;
+  std::vector<View> rec;        // [R][N]
+  std::vector<NodeB> node;
+  std::vector<EventB> events;   // sorted by (tick, insertion)
+  std::vector<u32> timeout; RuleCtx cx;
+  std::vector<serfsim_tick_row_t> trace;
+  std::vector<u8> subj_up;      // ground truth per slot
+  std::vector<Msg> inflight;    // messages sent in the previous tick
+  u64 tot_events = 0;
+  int threads = 1;
+  std::string err;
+
+  View& at(u32 s, u32 v) { return rec[(size_t)s * N + v]; }
+
+  void init_tables() {
+    timeout = suspicion_table(cfg.suspicion_mult, cfg.suspicion_max_timeout_mult,
+                              cfg.probe_interval_ticks ? cfg.probe_interval_ticks : 1, cfg.gossip_interval_ms, N);
+    cx.limit = retransmit_limit(cfg.retransmit_mult, N);
+    cx.k = (u32)timeout.size() - 1;
+    cx.timeout = timeout.data();
+  }
+  void reset(u64 seed) {
+    cfg.seed = seed; tick = 0; events.clear(); trace.clear(); inflight.clear(); tot_events = 0;
+    rec.assign((size_t)R * N, View{});
+    node.assign(N, NodeB{cfg.init_clock, 1, SS_ALIVE});
+    for (u32 s = 0; s < R; ++s)
+      for (u32 v = 0; v < N; ++v) {
+        View& r = at(s, v);
+        r.st = cfg.init_status_ltime; r.inc = 1; r.status = ST_ALIVE; r.flags = 1; set_ml(r, ML_ALIVE, 0);
+      }
+    subj_up.assign(R, 1);
+  }
+  int slot_of(u32 nodeid) const { for (u32 s = 0; s < R; ++s) if (subj[s] == nodeid) return (int)s; return -1; }
+
+  u32 gossip_targets(u32 v, u32 t, u32* out) const {
+    u64 r0 = row_ptr[v]; u32 deg = (u32)(row_ptr[v + 1] - r0), nt = 0;
+    u32 w[4] = {0, 0, 0, 0};
+    for (u32 i = 0; i < 3 * deg && nt < cfg.fanout; ++i) {      // kRandomNodes: at most 3n tries (cf. query.rs:388-409)
+      if ((i & 3) == 0) philox4x32_10(t, v, i >> 2, DOMAIN_GOSSIP, (u32)cfg.seed, (u32)(cfg.seed >> 32), w);
+      u32 c = col[r0 + mulhi32(w[i & 3], deg)];
+      if (c == v) continue;
+      bool dup = false;
+      for (u32 j = 0; j < nt; ++j) dup |= (out[j] == c);
+      if (dup) continue;
+      out[nt++] = c;
+    }
+    return nt;
+  }
+  bool probe_target(u32 v, u32 t, u32* out) const {
+    u64 r0 = row_ptr[v]; u32 deg = (u32)(row_ptr[v + 1] - r0);
+    if (!deg) return false;
+    u32 w[4]; philox4x32_10(t, v, 0, DOMAIN_PROBE, (u32)cfg.seed, (u32)(cfg.seed >> 32), w);
+    *out = col[r0 + mulhi32(w[0], deg)];
+    return true;
+  }
+
+  void step_one() {
+    const u32 t = tick;
+    serfsim_tick_row_t row{};
+    // ---- bucket last tick's messages by destination (stable counting sort) ----
+    std::vector<u32> head(N + 1, 0);
+    for (auto& m : inflight) head[m.dst + 1]++;
+    for (u32 i = 0; i < N; ++i) head[i + 1] += head[i];
+    std::vector<Msg> byd(inflight.size());
+    { std::vector<u32> pos(head.begin(), head.end() - 1); for (auto& m : inflight) byd[pos[m.dst]++] = m; }
+    inflight.clear();
+    // events of this tick
+    std::vector<EventB> evs;
+    for (auto& e : events) if (e.tick == t) evs.push_back(e);
+    // ground truth after this tick's operations (what a failed probe observes)
+    for (auto& e : evs) {
+      int s = slot_of(e.node);
+      if (s >= 0) { if (e.op == SERFSIM_OP_FAIL) subj_up[s] = 0; if (e.op == SERFSIM_OP_REJOIN) subj_up[s] = 1; }
+    }
+    bool any_down = false; for (u32 s = 0; s < R; ++s) any_down |= !subj_up[s];
+
+    std::vector<Msg> out;
+    for (u32 v = 0; v < N; ++v) {
+      NodeB& nd = node[v];
+      const bool up_r = nd.up;
+      const EventB* ev = nullptr;
+      for (auto& e : evs) if (e.node == v) { ev = &e; break; }        // at most one op per (node, tick)
+      bool up_s = up_r;
+      if (ev && ev->op == SERFSIM_OP_FAIL) up_s = false;
+      if (ev && ev->op == SERFSIM_OP_REJOIN) up_s = true;
+      u32 targets[8], nt = 0; bool have_targets = false;
+      u32 ptarget = 0; bool have_probe = false;
+      if (up_s && cfg.probe_interval_ticks && any_down && ((t + v) % cfg.probe_interval_ticks) == 0)
+        have_probe = probe_target(v, t, &ptarget);
+      u32 max_tx = 0;
+      for (u32 s = 0; s < R; ++s) {
+        View& r = at(s, v);
+        const bool self = (subj[s] == v);
+        // ---------------- Phase R: receive / state merge ----------------
+        if (up_r) {
+          const View before = r;
+          std::vector<Msg> ml, lv, jn;
+          for (u32 i = head[v]; i < head[v + 1]; ++i) {
+            const Msg& m = byd[i];
+            if (m.slot != s) continue;
+            (m.kind == 2 ? ml : m.kind == 0 ? lv : jn).push_back(m);
+          }
+          // memberlist: only the greatest (incarnation, kind, from) message is delivered per tick (rule ML-1)
+          if (!ml.empty()) {
+            u32 key = 0; for (auto& m : ml) key = std::max(key, m.val);
+            u32 inc = key >> 6, kind = (key >> 4) & 3, fromh = key & 15;
+            if (kind == ML_ALIVE) v_ml_alive(r, inc, self, cx);
+            else if (kind == ML_SUSPECT) v_ml_suspect(r, inc, fromh, t, self, cx);
+            else v_ml_dead(r, inc, kind == ML_LEFT, t, self, cx);
+          }
+          // serf intents, one at a time: leaves ascending (ltime, src), then joins ascending
+          auto by_lt = [](const Msg& a, const Msg& b) { return a.val != b.val ? a.val < b.val : a.src < b.src; };
+          std::sort(lv.begin(), lv.end(), by_lt); std::sort(jn.begin(), jn.end(), by_lt);
+          bool refute = false;
+          for (auto& m : lv) { witness32(nd.clock, m.val); v_leave_intent(r, m.val, self, nd.sstate, &refute, cx); }
+          for (auto& m : jn) { witness32(nd.clock, m.val); v_join_intent(r, m.val, cx); }
+          if (refute) {                                   // base.rs:1470-1480 → broadcast_join(clock.time()), base.rs:381-397
+            u32 T = nd.clock; witness32(nd.clock, T);
+            v_join_intent(r, T, cx);
+            r.qjoin = T; r.txj = (u8)cx.limit;
+          }
+          if (memcmp(&before, &r, sizeof(View)) != 0) row.changed++;
+        }
+        // ---------------- Phase E: host operation ----------------
+        if (ev) {
+          const u32 op = ev->op;
+          if (op == SERFSIM_OP_FAIL && self) { /* state kept; node simply stops */ }
+          if (op == SERFSIM_OP_REJOIN && self && !up_r) {
+            r.inc += 1; set_ml(r, ML_ALIVE, 0); r.txm = (u8)cx.limit; r.deadline = 0; r.mask = 0;
+            nd.sstate = SS_ALIVE;
+            v_node_join(r);
+          }
+          if (((op == SERFSIM_OP_JOIN && up_r) || (op == SERFSIM_OP_REJOIN && !up_r)) && self) {   // api.rs:339-342 → base.rs:381-397
+            u32 T = nd.clock; witness32(nd.clock, T);
+            v_join_intent(r, T, cx);
+            r.qjoin = T; r.txj = (u8)cx.limit;
+          }
+          if (op == SERFSIM_OP_LEAVE && up_r && self && nd.sstate == SS_ALIVE) {                  // api.rs:422-449
+            nd.sstate = SS_LEAVING;
+            u32 T = nd.clock; nd.clock += 1;
+            bool refute = false;
+            v_leave_intent(r, T, true, nd.sstate, &refute, cx);
+            r.qleave = T; r.txl = (u8)cx.limit;
+          }
+          if (op == SERFSIM_OP_FORCE_LEAVE && up_r && ev->slot == s) {                            // base.rs:454-480
+            u32 T = nd.clock; witness32(nd.clock, T);
+            bool refute = false;
+            v_leave_intent(r, T, self, nd.sstate, &refute, cx);
+            r.qleave = T; r.txl = (u8)cx.limit;
+            if (refute) { u32 T2 = nd.clock; witness32(nd.clock, T2); v_join_intent(r, T2, cx); r.qjoin = T2; r.txj = (u8)cx.limit; }
+          }
+        }
+        if (up_s) {
+          // ---------------- Phase T: suspicion timer, probe ----------------
+          if (ml_state(r) == ML_SUSPECT && r.deadline != 0 && t >= r.deadline) v_ml_dead(r, r.inc, false, t, false, cx);
+          if (have_probe && !self && ptarget == subj[s] && !subj_up[s]) {
+            u8 st = ml_state(r);
+            if (st == ML_ALIVE || st == ML_SUSPECT) {
+              bool starts = (st == ML_ALIVE);
+              v_ml_suspect(r, r.inc, from_hash(v), t, false, cx);
+              if (starts) row.suspects++;
+            }
+          }
+          // ---------------- Phase S: gossip send ----------------
+          if (r.txl | r.txj | r.txm) {
+            if (!have_targets) { nt = gossip_targets(v, t, targets); have_targets = true; }
+            for (u32 k = 0; k < nt; ++k) {
+              u32 cnt = 0;
+              if (r.txl > k) { out.push_back(Msg{targets[k], v, r.qleave, (u8)s, 0}); ++cnt; }
+              if (r.txj > k) { out.push_back(Msg{targets[k], v, r.qjoin, (u8)s, 1}); ++cnt; }
+              if (r.txm > k) { out.push_back(Msg{targets[k], v, ml_key(r), (u8)s, 2}); ++cnt; }
+              if (cnt) { row.edge_updates++; row.messages += cnt; }
+            }
+            max_tx = std::max(max_tx, (u32)std::max(r.txl, std::max(r.txj, r.txm)));
+            r.txl -= (u8)std::min<u32>(r.txl, nt); r.txj -= (u8)std::min<u32>(r.txj, nt); r.txm -= (u8)std::min<u32>(r.txm, nt);
+          }
+          // Serf::leave: once our own leave intent is out, memberlist.leave() → dead{node == from}  (api.rs:451-476)
+          if (self && nd.sstate == SS_LEAVING && r.txl == 0 && ml_state(r) == ML_ALIVE) {
+            set_ml(r, ML_LEFT, 0); r.txm = (u8)cx.limit; nd.sstate = SS_LEFT;
+          }
+          // pending?
+          bool pend = (r.txl | r.txj | r.txm) || ml_state(r) == ML_SUSPECT ||
+                      (cfg.probe_interval_ticks && !subj_up[s] && !self && ml_state(r) == ML_ALIVE);
+          if (pend) row.pending++;
+        }
+      }
+      if (ev) { row.events++; }
+      nd.up = up_s;
+      row.packets += std::min(nt, max_tx);
+    }
+    inflight.swap(out);
+    if (cfg.trace) row.hash = state_hash();
+    trace.push_back(row);
+    tot_events += row.events;
+    ++tick;
+  }
+
+  u64 state_hash() const {
+    u64 h = 0;
+    for (u32 s = 0; s < R; ++s)
+      for (u32 v = 0; v < N; ++v) {
+        u64 w[4]; memcpy(w, &rec[(size_t)s * N + v], 32);
+        u64 idx = (u64)s * N + v;
+        h += mix64(w[0] ^ mix64(w[1] ^ mix64(w[2] ^ mix64(w[3] ^ mix64(idx + 0x9e3779b97f4a7c15ULL)))));
+      }
+    for (u32 v = 0; v < N; ++v) {
+      u64 w = (u64)node[v].clock | ((u64)node[v].up << 32) | ((u64)node[v].sstate << 40);
+      h += mix64(w ^ mix64((u64)R * N + v + 0x9e3779b97f4a7c15ULL));
+    }
+    return h;
+  }
+  bool future_events() const { for (auto& e : events) if (e.tick >= tick) return true; return false; }
+};
+
+// =====================================================================================
+// C ABI (ctypes)
+// =====================================================================================
+static thread_local std::string g_err;
+#define ORC extern "C" __attribute__((visibility("default")))
+
+// ---- Part A ----
+ORC void* ref_node_new(u64 self_id, u32 retransmit_mult) { auto* n = new RefNode(self_id); n->retransmit_mult = retransmit_mult; return n; }
+ORC void ref_node_free(void* p) { delete (RefNode*)p; }
+ORC u64 ref_clock_time(void* p, int which) { auto* n = (RefNode*)p; return (which == 0 ? n->clock : which == 1 ? n->event_clock : n->query_clock).time(); }
+ORC u64 ref_clock_increment(void* p) { return ((RefNode*)p)->clock.increment(); }
+ORC void ref_clock_witness(void* p, u64 t) { ((RefNode*)p)->clock.witness(t); }
+ORC u64 lamport_new_time(void) { LamportClock c; return c.time(); }
+ORC void ref_set_serf_state(void* p, int s) { ((RefNode*)p)->serf_state = (u8)s; }
+ORC int ref_get_serf_state(void* p) { return ((RefNode*)p)->serf_state; }
+ORC void ref_insert_member(void* p, u64 id, int status, u64 status_time) { ((RefNode*)p)->states[id] = MemberStateA{(u8)status, status_time, false, 0}; }
+ORC int ref_member_get(void* p, u64 id, u8* status, u64* status_time) {
+  auto* n = (RefNode*)p; auto it = n->states.find(id);
+  if (it == n->states.end()) return 0;
+  *status = it->second.status; *status_time = it->second.status_time; return 1;
+}
+ORC u64 ref_num_members(void* p) { return ((RefNode*)p)->states.size(); }
+ORC int ref_handle_node_join_intent(void* p, u64 ltime, u64 id) { return ((RefNode*)p)->handle_node_join_intent(ltime, id); }
+ORC int ref_handle_node_leave_intent(void* p, u64 ltime, u64 id, int prune) { return ((RefNode*)p)->handle_node_leave_intent(ltime, id, prune != 0); }
+ORC void ref_run_detached(void* p) { ((RefNode*)p)->run_detached(); }
+ORC u32 ref_refutes(void* p) { return ((RefNode*)p)->refutes; }
+ORC void ref_handle_node_join(void* p, u64 id) { ((RefNode*)p)->handle_node_join(id); }
+ORC void ref_handle_node_leave(void* p, u64 id, int64_t now_ms) { ((RefNode*)p)->handle_node_leave(id, now_ms); }
+ORC int ref_upsert_intent(void* p, u64 id, int ty, u64 ltime, int64_t wall_ms) { return ((RefNode*)p)->upsert_intent(id, (u8)ty, ltime, wall_ms); }
+ORC int ref_recent_intent(void* p, u64 id, int ty, u64* ltime) { return ((RefNode*)p)->recent_intent(id, (u8)ty, ltime); }
+ORC void ref_reap_intents(void* p, int64_t now_ms, int64_t timeout_ms) { ((RefNode*)p)->reap_intents(now_ms, timeout_ms); }
+ORC void ref_merge_remote_state(void* p, u64 pp_ltime, const u64* ids, const u64* ltimes, u32 n, const u64* left, u32 n_left, u64 event_ltime, u64 query_ltime) {
+  ((RefNode*)p)->merge_remote_state(pp_ltime, ids, ltimes, n, left, n_left, event_ltime, query_ltime);
+}
+ORC void ref_api_join(void* p) { ((RefNode*)p)->api_join(); }
+ORC int ref_api_leave(void* p) { return ((RefNode*)p)->api_leave(); }
+ORC void ref_api_force_leave(void* p, u64 id, int prune) { ((RefNode*)p)->api_force_leave(id, prune != 0); }
+ORC u32 ref_queue_len(void* p) { return (u32)((RefNode*)p)->broadcasts.size(); }
+ORC int ref_queue_get(void* p, u32 i, u8* ty, u64* ltime, u64* id, u32* transmits) {
+  auto* n = (RefNode*)p; if (i >= n->broadcasts.size()) return 0;
+  auto& q = n->broadcasts[i]; *ty = q.ty; *ltime = q.ltime; *id = q.id; *transmits = q.transmits; return 1;
+}
+ORC u32 ref_get_broadcasts(void* p, u32 byte_limit, u32 overhead, u8* ty, u64* lt, u64* id, u32 cap) { return ((RefNode*)p)->get_broadcasts(byte_limit, overhead, ty, lt, id, cap); }
+ORC u32 ref_left_count(void* p) { return (u32)((RefNode*)p)->left_members.size(); }
+ORC u32 ref_failed_count(void* p) { return (u32)((RefNode*)p)->failed_members.size(); }
+ORC void ref_push_left(void* p, u64 id, int status, u64 status_time, int64_t leave_time_ms) { ((RefNode*)p)->left_members.push_back({id, MemberStateA{(u8)status, status_time, true, leave_time_ms}}); }
+ORC void ref_push_failed(void* p, u64 id, int status, u64 status_time, int64_t leave_time_ms) { ((RefNode*)p)->failed_members.push_back({id, MemberStateA{(u8)status, status_time, true, leave_time_ms}}); }
+ORC void ref_reap(void* p, int64_t now_ms, int64_t reconnect_ms, int64_t tombstone_ms, int64_t intent_ms) { ((RefNode*)p)->reap(now_ms, reconnect_ms, tombstone_ms, intent_ms); }
+ORC u32 ref_event_count(void* p) { return (u32)((RefNode*)p)->events.size(); }
+ORC int ref_event_get(void* p, u32 i, u32* ty, u64* id) { auto* n = (RefNode*)p; if (i >= n->events.size()) return 0; *ty = n->events[i].first; *id = n->events[i].second; return 1; }
+ORC u64 ref_get_queue_max(u64 max_depth, u64 min_depth, u64 members) { return get_queue_max(max_depth, min_depth, members); }
+
+// ---- shared primitives ----
+ORC void oracle_philox4x32_10(const u32 ctr[4], const u32 key[2], u32 out[4]) { philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out); }
+ORC u32 oracle_retransmit_limit(u32 mult, u64 n) { return retransmit_limit(mult, n); }
+ORC u32 oracle_suspicion_table(u32 susp_mult, u32 max_mult, u32 probe_ticks, u32 tick_ms, u64 n, u32* out, u32 cap) {
+  auto t = suspicion_table(susp_mult, max_mult, probe_ticks, tick_ms, n);
+  for (u32 i = 0; i < t.size() && i < cap; ++i) out[i] = t[i];
+  return (u32)t.size();
+}
+ORC u64 oracle_mix64(u64 x) { return mix64(x); }
+ORC u32 oracle_from_hash(u32 node) { return from_hash(node); }
+
+// view-rule hooks: lets tests drive the packed-record rules against RefNode (Part A ≡ Part B)
+ORC void oracle_view_init(void* rec32, int known_, int status, u32 st) { View r{}; r.flags = known_ ? 1 : 0; r.status = (u8)status; r.st = st; r.inc = known_ ? 1 : 0; set_ml(r, known_ ? ML_ALIVE : ML_DEAD, 0); memcpy(rec32, &r, 32); }
+ORC int oracle_view_join_intent(void* rec32, u32 lt, u32 limit) { RuleCtx cx{limit, 0, nullptr}; View r; memcpy(&r, rec32, 32); bool a = v_join_intent(r, lt, cx); memcpy(rec32, &r, 32); return a; }
+ORC int oracle_view_leave_intent(void* rec32, u32 lt, int self, int sstate, int* refute, u32 limit) { RuleCtx cx{limit, 0, nullptr}; View r; memcpy(&r, rec32, 32); bool rf = false; bool a = v_leave_intent(r, lt, self != 0, (u8)sstate, &rf, cx); memcpy(rec32, &r, 32); *refute = rf; return a; }
+ORC void oracle_view_node_join(void* rec32) { View r; memcpy(&r, rec32, 32); v_node_join(r); memcpy(rec32, &r, 32); }
+ORC void oracle_view_node_leave(void* rec32, u32 tick) { View r; memcpy(&r, rec32, 32); v_node_leave(r, tick); memcpy(rec32, &r, 32); }
+
+// ---- Part B: same shapes as the serfsim_* ABI so one test driver serves both ----
+ORC int oracle_sim_create(const serfsim_config_t* cfg, void** out) {
+  if (!cfg || !out || cfg->n_nodes == 0 || cfg->slots == 0 || cfg->slots > 16 || cfg->fanout == 0 || cfg->fanout > 8) { g_err = "bad config"; return SERFSIM_E_INVAL; }
+  auto* s = new TickSim(); s->cfg = *cfg; s->N = cfg->n_nodes; s->R = cfg->slots;
+  s->subj.resize(s->R); for (u32 i = 0; i < s->R; ++i) s->subj[i] = i;
+  s->init_tables();
+  if (s->cx.limit > 255) { delete s; g_err = "retransmit limit > 255"; return SERFSIM_E_INVAL; }
+  s->reset(cfg->seed);
+  *out = s; return 0;
+}
+ORC void oracle_sim_destroy(void* p) { delete (TickSim*)p; }
+ORC const char* oracle_last_error(void) { return g_err.c_str(); }
+ORC int oracle_sim_set_topology_csr(void* p, const u64* row_ptr, const u32* col_idx) {
+  auto* s = (TickSim*)p; s->row_ptr.assign(row_ptr, row_ptr + s->N + 1); s->col.assign(col_idx, col_idx + row_ptr[s->N]);
+  for (u32 c : s->col) if (c >= s->N) { g_err = "col_idx out of range"; return SERFSIM_E_INVAL; }
+  return 0;
+}
+ORC int oracle_sim_set_subjects(void* p, const u32* subjects) {
+  auto* s = (TickSim*)p;
+  for (u32 i = 0; i < s->R; ++i) { if (subjects[i] >= s->N) return SERFSIM_E_INVAL; for (u32 j = 0; j < i; ++j) if (subjects[j] == subjects[i]) return SERFSIM_E_INVAL; }
+  s->subj.assign(subjects, subjects + s->R); return 0;
+}
+ORC int oracle_sim_reset(void* p, u64 seed) { ((TickSim*)p)->reset(seed); return 0; }
+ORC int oracle_sim_inject(void* p, u32 tick, u32 op, u32 node, u32 slot) {
+  auto* s = (TickSim*)p;
+  if (tick < s->tick || node >= s->N || op < 1 || op > 5) { g_err = "bad inject"; return SERFSIM_E_INVAL; }
+  if (op == SERFSIM_OP_FORCE_LEAVE) { if (slot >= s->R) return SERFSIM_E_INVAL; }
+  else if (s->slot_of(node) < 0) { g_err = "origin must be a tracked subject"; return SERFSIM_E_INVAL; }
+  for (auto& e : s->events) if (e.tick == tick && e.node == node) { g_err = "one operation per node per tick"; return SERFSIM_E_INVAL; }
+  s->events.push_back(EventB{tick, op, node, slot}); return 0;
+}
+ORC int oracle_sim_step(void* p, u32 n) { auto* s = (TickSim*)p; if (s->row_ptr.empty()) { g_err = "no topology"; return SERFSIM_E_INVAL; } for (u32 i = 0; i < n; ++i) s->step_one(); return 0; }
+ORC int oracle_sim_run_until_converged(void* p, u32 max_ticks, u32* ticks_out) {
+  auto* s = (TickSim*)p; if (s->row_ptr.empty()) return SERFSIM_E_INVAL;
+  for (u32 i = 0; i < max_ticks; ++i) {
+    s->step_one();
+    auto& r = s->trace.back();
+    if (r.pending == 0 && r.edge_updates == 0 && !s->future_events()) { if (ticks_out) *ticks_out = s->tick - 1; return 0; }
+  }
+  if (ticks_out) *ticks_out = s->tick;
+  return 1;
+}
+ORC int oracle_sim_member_status(void* p, u32 slot, u8* out) { auto* s = (TickSim*)p; if (slot >= s->R) return SERFSIM_E_INVAL; for (u32 v = 0; v < s->N; ++v) { View& r = s->at(slot, v); out[v] = known(r) ? r.status : (u8)ST_NONE; } return 0; }
+ORC int oracle_sim_status_ltime(void* p, u32 slot, u64* out) { auto* s = (TickSim*)p; if (slot >= s->R) return SERFSIM_E_INVAL; for (u32 v = 0; v < s->N; ++v) { View& r = s->at(slot, v); out[v] = known(r) ? r.st : 0; } return 0; }
+ORC int oracle_sim_lamport_time(void* p, u64* out) { auto* s = (TickSim*)p; for (u32 v = 0; v < s->N; ++v) out[v] = s->node[v].clock; return 0; }
+ORC int oracle_sim_incarnation(void* p, u32 slot, u32* out) { auto* s = (TickSim*)p; if (slot >= s->R) return SERFSIM_E_INVAL; for (u32 v = 0; v < s->N; ++v) out[v] = s->at(slot, v).inc; return 0; }
+ORC int oracle_sim_ml_state(void* p, u32 slot, u8* out) { auto* s = (TickSim*)p; if (slot >= s->R) return SERFSIM_E_INVAL; for (u32 v = 0; v < s->N; ++v) out[v] = ml_state(s->at(slot, v)); return 0; }
+ORC int oracle_sim_records(void* p, u32 slot, void* out) { auto* s = (TickSim*)p; if (slot >= s->R) return SERFSIM_E_INVAL; memcpy(out, &s->at(slot, 0), (size_t)s->N * 32); return 0; }
+ORC int oracle_sim_tick_trace(void* p, u32 first, u32 n, serfsim_tick_row_t* out) { auto* s = (TickSim*)p; if ((u64)first + n > s->trace.size()) return SERFSIM_E_INVAL; memcpy(out, s->trace.data() + first, (size_t)n * sizeof(serfsim_tick_row_t)); return 0; }
+ORC int oracle_sim_state_hash(void* p, u64* out) { *out = ((TickSim*)p)->state_hash(); return 0; }
+ORC int oracle_sim_stats(void* p, serfsim_stats_t* o) {
+  auto* s = (TickSim*)p; memset(o, 0, sizeof(*o));
+  o->tick = s->tick; o->members = s->N;
+  for (size_t i = 0; i < s->trace.size(); ++i) {
+    auto& r = s->trace[i];
+    o->packets += r.packets; o->edge_updates += r.edge_updates; o->messages += r.messages; o->changed += r.changed; o->events += r.events;
+    if (r.pending || r.edge_updates || r.events) o->last_active_tick = i;
+  }
+  if (!s->trace.empty()) o->pending = s->trace.back().pending;
+  for (u32 v = 0; v < s->N; ++v) o->member_time = std::max<u64>(o->member_time, s->node[v].clock);
+  for (auto& r : s->rec) o->intent_queue += (r.txj ? 1 : 0) + (r.txl ? 1 : 0);
+  for (u32 sl = 0; sl < s->R; ++sl) {
+    bool first = true, diff = false; u64 key0 = 0;
+    for (u32 v = 0; v < s->N; ++v) {
+      if (!s->node[v].up || s->subj[sl] == v) continue;
+      View& r = s->at(sl, v);
+      u64 key = ((u64)r.st << 32) ^ ((u64)r.inc << 8) ^ ((u64)(known(r) ? r.status : 0) << 4) ^ ml_state(r) ^ ((u64)known(r) << 63);
+      if (first) { key0 = key; first = false; } else if (key != key0) diff = true;
+    }
+    if (diff) o->disagree_slots++;
+  }
+  return 0;
+}
