@@ -850,7 +850,7 @@ ORC int oracle_sim_inject(void* p, u32 tick, u32 op, u32 node, u32 slot) {
   auto* s = (TickSim*)p;
   if (tick < s->tick || node >= s->N || op < 1 || op > 5) { g_err = "bad inject"; return SERFSIM_E_INVAL; }
   if (op == SERFSIM_OP_FORCE_LEAVE) { if (slot >= s->R) return SERFSIM_E_INVAL; }
-  else if (s->slot_of(node) < 0) { g_err = "origin must be a tracked subject"; return SERFSIM_E_INVAL; }
+  else if ((op == SERFSIM_OP_JOIN || op == SERFSIM_OP_LEAVE) && s->slot_of(node) < 0) { g_err = "join/leave origin must be a tracked subject"; return SERFSIM_E_INVAL; }
   for (auto& e : s->events) if (e.tick == tick && e.node == node) { g_err = "one operation per node per tick"; return SERFSIM_E_INVAL; }
   s->events.push_back(EventB{tick, op, node, slot}); return 0;
 }

@@ -1,0 +1,653 @@
+// serfsim.cu — host side of the simulator and its C ABI (include/serfsim.h).
+//
+// The reference's host code is Rust; Rust is not available in this build environment, so the
+// host layer above the C ABI is C++ and mirrors the reference's names: Options/MemberlistOptions
+// fields (serf-core/src/options.rs:495-530), Serf::{join,leave,remove_failed_node,members,stats}
+// (serf/api.rs), MemberStatus (types/member.rs:54-58), MemberEventType (event.rs:325-328).
+// Device memory, streams and the per-tick launch sequence live here; the kernels are in
+// tick_kernel.cu.  There is no CPU execution path: without a CUDA device every entry point fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/serfsim.h"
+#include "tick_kernel.cuh"
+
+using namespace sfs;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(SERFSIM_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
+
+struct HostOp { u32 tick, op, node, slot; u64 seq; };
+
+// memberlist retransmit limit: retransmit_mult * ceil(log10(n + 1))  [external crate, restated]
+u32 retransmit_limit(u32 mult, u64 n) {
+  u32 digits = 0;
+  u64 p = 1;
+  while (p < n + 1) { p *= 10; ++digits; }
+  return mult * digits;
+}
+
+// memberlist suspicion timeouts (Lifeguard), in ticks  [external crate, restated]:
+//   min = suspicion_mult · max(1, log10 n) · probe_interval, max = suspicion_max_timeout_mult · min,
+//   k = suspicion_mult − 2 (0 if n − 2 < k), timeout(c) = max − log(c+1)/log(k+1)·(max − min) ≥ min.
+// The only floating point on the whole path; it runs once on the host and yields integers.
+std::vector<u32> suspicion_table(u32 susp_mult, u32 max_mult, u32 probe_ticks, u32 tick_ms, u64 n) {
+  const double node_scale = std::max(1.0, std::log10(std::max(1.0, (double)n)));
+  const int64_t interval_ms = (int64_t)probe_ticks * tick_ms;
+  const int64_t min_ms = (int64_t)susp_mult * (int64_t)(node_scale * 1000.0) * interval_ms / 1000;
+  const int64_t max_ms = (int64_t)max_mult * min_ms;
+  int64_t k = (int64_t)susp_mult - 2;
+  if ((int64_t)n - 2 < k) k = 0;
+  if (k < 0) k = 0;
+  std::vector<u32> tab;
+  for (int64_t c = 0; c <= k; ++c) {
+    int64_t ms = min_ms;
+    if (k >= 1) {
+      const double frac = std::log((double)c + 1.0) / std::log((double)k + 1.0);
+      ms = (int64_t)std::floor((double)max_ms - frac * (double)(max_ms - min_ms));
+      if (ms < min_ms) ms = min_ms;
+    }
+    int64_t ticks = (ms + tick_ms - 1) / tick_ms;
+    if (ticks < 1) ticks = 1;
+    tab.push_back((u32)ticks);
+  }
+  return tab;
+}
+
+}  // namespace
+
+struct serfsim {
+  serfsim_config_t cfg{};
+  u32 N = 0, R = 0, first = 0, count = 0, shard_size = 0;
+  Rules rules{};
+  // device state
+  uint4* d_rec = nullptr;          // [R][count] × 32 B
+  u32* d_inbox[2] = {nullptr, nullptr};   // [3][R][count]
+  u64* d_node = nullptr;           // [count]
+  u32* d_rowptr = nullptr;         // [count+1]
+  u32* d_col = nullptr;
+  u32 *d_ev_node = nullptr, *d_ev_op = nullptr, *d_ev_slot = nullptr;
+  size_t ev_cap = 0;
+  u64* d_trace = nullptr;          // [trace_cap][8]
+  u32* d_kinds = nullptr;          // [trace_cap+1][4]; row t+1 = messages by kind sent in tick t
+  u32* d_ones = nullptr;           // [4] non-zero (multi-GPU: never skip an inbox plane)
+  u32 trace_cap = 0;
+  u32* d_overflow = nullptr;
+  u32* d_subj = nullptr;
+  u64* d_scratch = nullptr;        // summary / hash output
+  void* d_stage = nullptr;         // getter staging, count × 8 B
+  // host state
+  std::vector<HostOp> ops;         // sorted by (tick, seq)
+  bool ops_dirty = false;
+  u64 op_seq = 0;
+  std::vector<u32> subj;
+  u32 up_mask = 0;
+  u32 tick = 0;
+  bool has_topo = false;
+  std::vector<serfsim_tick_row_t> rows;   // rows pulled from the device so far
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timing_open = false;
+  double last_ms = 0.0;
+  u64 last_launches = 0, launches = 0;
+  serfsim_event_cb cb = nullptr;
+  void* cb_user = nullptr;
+  std::vector<u8> reported;        // last status reported per slot
+  int grid = 1;
+  // multi-GPU
+  std::vector<u64*> peer_win_data; std::vector<u32*> peer_win_count;
+  u64* d_win_data[2] = {nullptr, nullptr};     // my windows [parity][world][win_cap]
+  u32* d_win_count[2] = {nullptr, nullptr};    // [parity][world]
+  u64** d_peer_data[2] = {nullptr, nullptr};   // device arrays of peer pointers, per parity
+  u32** d_peer_count[2] = {nullptr, nullptr};
+  u32 win_cap = 0;
+  bool connected = false;
+  serfsim_barrier_fn barrier = nullptr; serfsim_allreduce_u64_fn allreduce = nullptr; void* comm_user = nullptr;
+  std::vector<void*> ipc_opened;
+};
+
+namespace {
+
+int slot_of(const serfsim* h, u32 node) {
+  for (u32 s = 0; s < h->R; ++s) if (h->subj[s] == node) return (int)s;
+  return -1;
+}
+
+int ensure_trace(serfsim* h, u32 need) {
+  if (need <= h->trace_cap) return 0;
+  u32 cap = std::max<u32>(1024, h->trace_cap);
+  while (cap < need) cap *= 2;
+  u64* nt = nullptr; u32* nk = nullptr;
+  CU(cudaMalloc(&nt, (size_t)cap * 8 * sizeof(u64)));
+  CU(cudaMalloc(&nk, ((size_t)cap + 1) * 4 * sizeof(u32)));
+  CU(cudaMemsetAsync(nt, 0, (size_t)cap * 8 * sizeof(u64), h->stream));
+  CU(cudaMemsetAsync(nk, 0, ((size_t)cap + 1) * 4 * sizeof(u32), h->stream));
+  if (h->d_trace) {
+    CU(cudaMemcpyAsync(nt, h->d_trace, (size_t)h->trace_cap * 8 * sizeof(u64), cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(nk, h->d_kinds, ((size_t)h->trace_cap + 1) * 4 * sizeof(u32), cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_trace); cudaFree(h->d_kinds);
+  }
+  h->d_trace = nt; h->d_kinds = nk; h->trace_cap = cap;
+  return 0;
+}
+
+int upload_ops(serfsim* h) {
+  if (!h->ops_dirty) return 0;
+  std::stable_sort(h->ops.begin(), h->ops.end(), [](const HostOp& a, const HostOp& b) { return a.tick != b.tick ? a.tick < b.tick : a.seq < b.seq; });
+  const size_t n = h->ops.size();
+  if (n > h->ev_cap) {
+    size_t cap = std::max<size_t>(1024, h->ev_cap);
+    while (cap < n) cap *= 2;
+    if (h->d_ev_node) { cudaFree(h->d_ev_node); cudaFree(h->d_ev_op); cudaFree(h->d_ev_slot); }
+    CU(cudaMalloc(&h->d_ev_node, cap * 4)); CU(cudaMalloc(&h->d_ev_op, cap * 4)); CU(cudaMalloc(&h->d_ev_slot, cap * 4));
+    h->ev_cap = cap;
+  }
+  if (n) {
+    std::vector<u32> a(n), b(n), c(n);
+    for (size_t i = 0; i < n; ++i) { a[i] = h->ops[i].node; b[i] = h->ops[i].op; c[i] = h->ops[i].slot; }
+    CU(cudaMemcpyAsync(h->d_ev_node, a.data(), n * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_ev_op, b.data(), n * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_ev_slot, c.data(), n * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));     // staging vectors die here
+  }
+  h->ops_dirty = false;
+  return 0;
+}
+
+bool future_ops(const serfsim* h, u32 after_tick) {       // any op scheduled at tick > after_tick
+  return !h->ops.empty() && h->ops.back().tick > after_tick;
+}
+
+// Launch n ticks on the stream (no synchronisation).
+int launch_ticks(serfsim* h, u32 n) {
+  if (!h->has_topo) return fail(SERFSIM_E_INVAL, "serfsim_step: no topology set");
+  if (h->cfg.world_size > 1 && !h->connected) return fail(SERFSIM_E_COMM, "serfsim_step: world_size > 1 but serfsim_comm_connect was not called");
+  int rc = upload_ops(h);
+  if (rc) return rc;
+  rc = ensure_trace(h, h->tick + n + 1);
+  if (rc) return rc;
+  if (!h->timing_open) { CU(cudaEventRecord(h->ev0, h->stream)); h->timing_open = true; h->last_launches = 0; }
+  for (u32 i = 0; i < n; ++i) {
+    const u32 t = h->tick;
+    auto lo = std::lower_bound(h->ops.begin(), h->ops.end(), t, [](const HostOp& o, u32 tt) { return o.tick < tt; });
+    auto hi = std::upper_bound(h->ops.begin(), h->ops.end(), t, [](u32 tt, const HostOp& o) { return tt < o.tick; });
+    const u32 eb = (u32)(lo - h->ops.begin()), ee = (u32)(hi - h->ops.begin());
+    for (auto it = lo; it != hi; ++it) {          // ground truth the SWIM probe observes (after this tick's ops)
+      const int s = slot_of(h, it->node);
+      if (s >= 0) { if (it->op == SERFSIM_OP_FAIL) h->up_mask &= ~(1u << s); if (it->op == SERFSIM_OP_REJOIN) h->up_mask |= (1u << s); }
+    }
+    if (ee > eb) { launch_mark_events(h->d_node, h->d_ev_node, eb, ee, h->first, h->count, h->stream); h->last_launches++; }
+    TickParams p{};
+    p.n_local = h->count; p.first = h->first; p.n_global = h->N; p.R = h->R;
+    p.fanout = h->cfg.fanout; p.probe_every = h->cfg.probe_interval_ticks; p.tick = t;
+    p.down_mask = (~h->up_mask) & ((1u << h->R) - 1);
+    p.seed_lo = (u32)h->cfg.seed; p.seed_hi = (u32)(h->cfg.seed >> 32); p.ev_begin = eb; p.ev_end = ee;
+    p.rules = h->rules;
+    for (u32 s = 0; s < h->R; ++s) p.subj[s] = h->subj[s];
+    p.rec = h->d_rec; p.inbox_rd = h->d_inbox[(t & 1) ^ 1]; p.inbox_wr = h->d_inbox[t & 1];
+    p.node_state = h->d_node; p.row_ptr = h->d_rowptr; p.col = h->d_col;
+    p.ev_node = h->d_ev_node; p.ev_op = h->d_ev_op; p.ev_slot = h->d_ev_slot;
+    p.row = h->d_trace + (size_t)t * 8;
+    p.kinds_prev = (h->cfg.world_size > 1) ? h->d_ones : h->d_kinds + (size_t)t * 4;
+    p.kinds_cur = h->d_kinds + ((size_t)t + 1) * 4;
+    p.overflow = h->d_overflow;
+    p.world = (u32)h->cfg.world_size; p.rank = (u32)h->cfg.rank; p.shard_size = h->shard_size; p.win_cap = h->win_cap;
+    p.win_data = h->d_peer_data[t & 1]; p.win_count = h->d_peer_count[t & 1];
+    launch_tick(p, h->cfg.trace != 0, h->grid, h->stream);
+    h->last_launches++;
+    if (h->cfg.world_size > 1) {
+      // all peers have finished writing into my window of this parity once the barrier returns
+      CU(cudaStreamSynchronize(h->stream));
+      h->barrier(h->comm_user);
+      DrainParams d{};
+      d.n_local = h->count; d.R = h->R; d.world = (u32)h->cfg.world_size; d.rank = (u32)h->cfg.rank; d.win_cap = h->win_cap;
+      d.win_data = h->d_win_data[t & 1]; d.win_count = h->d_win_count[t & 1]; d.inbox_wr = h->d_inbox[t & 1]; d.overflow = h->d_overflow;
+      launch_drain(d, h->stream);
+      CU(cudaMemsetAsync(h->d_win_count[t & 1], 0, sizeof(u32) * h->cfg.world_size, h->stream));
+      h->last_launches++;
+      CU(cudaStreamSynchronize(h->stream));
+      h->barrier(h->comm_user);      // windows of this parity are reusable two ticks from now; counters are reset
+    }
+    h->tick++;
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int finish_timing(serfsim* h) {
+  if (!h->timing_open) return 0;
+  CU(cudaEventRecord(h->ev1, h->stream));
+  CU(cudaEventSynchronize(h->ev1));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->last_ms = ms; h->timing_open = false; h->launches += h->last_launches;
+  return 0;
+}
+
+int check_overflow(serfsim* h) {
+  u32 ov = 0;
+  CU(cudaMemcpy(&ov, h->d_overflow, 4, cudaMemcpyDeviceToHost));
+  if (ov == 1) return fail(SERFSIM_E_OVERFLOW, "a Lamport time or incarnation left the 32-bit device range");
+  if (ov == 2) return fail(SERFSIM_E_COMM, "cross-shard window overflow (raise SERFSIM_WIN_FACTOR)");
+  if (ov) return fail(SERFSIM_E_COMM, "corrupt cross-shard window entry");
+  return 0;
+}
+
+int pull_rows(serfsim* h) {                     // bring rows [rows.size(), tick) to the host (global sums when sharded)
+  const u32 have = (u32)h->rows.size();
+  if (have >= h->tick) return 0;
+  const u32 n = h->tick - have;
+  h->rows.resize(h->tick);
+  CU(cudaMemcpy(h->rows.data() + have, h->d_trace + (size_t)have * 8, (size_t)n * sizeof(serfsim_tick_row_t), cudaMemcpyDeviceToHost));
+  if (h->cfg.world_size > 1) h->allreduce(h->comm_user, (uint64_t*)(h->rows.data() + have), n * 8);
+  return 0;
+}
+
+int fire_events(serfsim* h) {
+  if (!h->cb) return 0;
+  const u32 nout = 2 + 2 * h->R;
+  std::vector<u64> init(nout, 0), out(nout);
+  for (u32 s = 0; s < h->R; ++s) init[2 + 2 * s] = ~0ull;
+  CU(cudaMemcpyAsync(h->d_scratch, init.data(), nout * 8, cudaMemcpyHostToDevice, h->stream));
+  launch_summary(h->d_rec, h->d_node, h->count, h->first, h->R, h->d_subj, h->d_scratch, h->stream);
+  CU(cudaMemcpyAsync(out.data(), h->d_scratch, nout * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (u32 type = 0; type < 3; ++type) {
+    std::vector<u32> ids;
+    for (u32 s = 0; s < h->R; ++s) {
+      if (out[2 + 2 * s] != out[3 + 2 * s]) continue;                 // views still disagree
+      const u8 status = (u8)((out[2 + 2 * s] >> 4) & 0xf);
+      const u32 ty = status == ST_ALIVE ? SERFSIM_EVENT_JOIN : status == ST_FAILED ? SERFSIM_EVENT_FAILED : SERFSIM_EVENT_LEAVE;
+      if (ty == type && h->reported[s] != status) ids.push_back(h->subj[s]);
+    }
+    if (!ids.empty()) h->cb(h->cb_user, h->tick, type, ids.data(), (u32)ids.size());
+  }
+  for (u32 s = 0; s < h->R; ++s) if (out[2 + 2 * s] == out[3 + 2 * s]) h->reported[s] = (u8)((out[2 + 2 * s] >> 4) & 0xf);
+  return 0;
+}
+
+int do_reset(serfsim* h, u64 seed) {
+  h->cfg.seed = seed; h->tick = 0; h->ops.clear(); h->ops_dirty = false; h->rows.clear();
+  h->up_mask = (h->R >= 32) ? 0xffffffffu : ((1u << h->R) - 1);
+  h->reported.assign(h->R, (u8)ST_ALIVE);
+  const size_t inbox_bytes = (size_t)3 * h->R * h->count * sizeof(u32);
+  launch_init_state(h->d_rec, h->d_node, h->count, h->R, h->cfg.init_status_ltime, h->cfg.init_clock, h->stream);
+  CU(cudaMemsetAsync(h->d_inbox[0], 0, inbox_bytes, h->stream));
+  CU(cudaMemsetAsync(h->d_inbox[1], 0, inbox_bytes, h->stream));
+  CU(cudaMemsetAsync(h->d_overflow, 0, 4, h->stream));
+  if (h->d_trace) {
+    CU(cudaMemsetAsync(h->d_trace, 0, (size_t)h->trace_cap * 8 * sizeof(u64), h->stream));
+    CU(cudaMemsetAsync(h->d_kinds, 0, ((size_t)h->trace_cap + 1) * 4 * sizeof(u32), h->stream));
+  }
+  for (int par = 0; par < 2; ++par)
+    if (h->d_win_count[par]) CU(cudaMemsetAsync(h->d_win_count[par], 0, sizeof(u32) * h->cfg.world_size, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+void free_all(serfsim* h) {
+  for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+  cudaFree(h->d_rec); cudaFree(h->d_inbox[0]); cudaFree(h->d_inbox[1]); cudaFree(h->d_node); cudaFree(h->d_rowptr); cudaFree(h->d_col);
+  cudaFree(h->d_ev_node); cudaFree(h->d_ev_op); cudaFree(h->d_ev_slot); cudaFree(h->d_trace); cudaFree(h->d_kinds); cudaFree(h->d_ones);
+  cudaFree(h->d_overflow); cudaFree(h->d_subj); cudaFree(h->d_scratch); cudaFree(h->d_stage);
+  for (int par = 0; par < 2; ++par) { cudaFree(h->d_win_data[par]); cudaFree(h->d_win_count[par]); cudaFree(h->d_peer_data[par]); cudaFree(h->d_peer_count[par]); }
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+}
+
+int getter(serfsim* h, u32 slot, int what, void* out, size_t elem) {
+  if (!h || !out) return fail(SERFSIM_E_INVAL, "null argument");
+  if (what != EXTRACT_CLOCK && slot >= h->R) return fail(SERFSIM_E_INVAL, "slot out of range");
+  launch_extract(h->d_rec, h->d_node, h->count, slot, what, h->d_stage, h->stream);
+  CU(cudaMemcpyAsync(out, h->d_stage, (size_t)h->count * elem, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+}  // namespace
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+#pragma GCC visibility push(default)
+extern "C" {
+
+uint32_t serfsim_abi_version(void) { return SERFSIM_ABI_VERSION; }
+const char* serfsim_last_error(void) { return g_err.c_str(); }
+
+void serfsim_default_config(serfsim_config_t* c) {
+  if (!c) return;
+  memset(c, 0, sizeof(*c));
+  c->abi_version = SERFSIM_ABI_VERSION;
+  c->n_nodes = 0; c->slots = 1;
+  c->fanout = 3;                       // memberlist LAN gossip_nodes
+  c->retransmit_mult = 4; c->suspicion_mult = 4; c->suspicion_max_timeout_mult = 6;
+  c->probe_interval_ticks = 5;         // 1 s / 200 ms
+  c->gossip_interval_ms = 200;
+  c->init_status_ltime = 1; c->init_clock = 2;
+  c->trace = 0; c->seed = 1; c->device = -1; c->rank = 0; c->world_size = 1;
+}
+
+int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
+  if (!cfg || !out) return fail(SERFSIM_E_INVAL, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != SERFSIM_ABI_VERSION) return fail(SERFSIM_E_INVAL, "abi_version mismatch");
+  if (cfg->n_nodes < 2 || cfg->slots < 1 || cfg->slots > MAX_SLOTS || cfg->fanout < 1 || cfg->fanout > MAX_FANOUT)
+    return fail(SERFSIM_E_INVAL, "bad n_nodes / slots (1..16) / fanout (1..8)");
+  if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) return fail(SERFSIM_E_INVAL, "bad rank / world_size");
+  if (cfg->gossip_interval_ms == 0) return fail(SERFSIM_E_INVAL, "gossip_interval_ms must be > 0");
+  if (cfg->suspicion_mult >= 2 && cfg->suspicion_mult - 2 > MAX_K) return fail(SERFSIM_E_INVAL, "suspicion_mult too large");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(SERFSIM_E_NO_DEVICE, "no CUDA device: serfsim has no CPU execution path");
+  if (cfg->device >= 0) { if (cfg->device >= ndev) return fail(SERFSIM_E_NO_DEVICE, "device ordinal out of range"); CU(cudaSetDevice(cfg->device)); }
+  int dev = 0, major = 0;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return fail(SERFSIM_E_NO_DEVICE, "kernels are built for sm_100a only (B200)");
+
+  serfsim* h = new serfsim();
+  h->cfg = *cfg; h->N = cfg->n_nodes; h->R = cfg->slots;
+  h->shard_size = (h->N + cfg->world_size - 1) / cfg->world_size;
+  h->first = std::min<u64>((u64)h->shard_size * cfg->rank, h->N);
+  h->count = (u32)std::min<u64>(h->shard_size, (u64)h->N - h->first);
+  if (h->count == 0) { delete h; return fail(SERFSIM_E_INVAL, "empty shard"); }
+  if (h->shard_size >= (1u << 26)) { delete h; return fail(SERFSIM_E_INVAL, "shard larger than 2^26 nodes"); }
+  h->rules.limit = retransmit_limit(cfg->retransmit_mult, h->N);
+  if (h->rules.limit == 0 || h->rules.limit > 255) { delete h; return fail(SERFSIM_E_INVAL, "retransmit limit must be 1..255"); }
+  auto tab = suspicion_table(cfg->suspicion_mult, cfg->suspicion_max_timeout_mult, cfg->probe_interval_ticks ? cfg->probe_interval_ticks : 1, cfg->gossip_interval_ms, h->N);
+  h->rules.k = (u32)tab.size() - 1;
+  for (size_t i = 0; i < tab.size(); ++i) h->rules.timeout[i] = tab[i];
+  h->subj.resize(h->R);
+  for (u32 s = 0; s < h->R; ++s) h->subj[s] = s;
+
+  auto bail = [&](int rc) { free_all(h); delete h; return rc; };
+#define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(fail(e_ == cudaErrorMemoryAllocation ? SERFSIM_E_NOMEM : SERFSIM_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); } while (0)
+  CUB(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUB(cudaEventCreate(&h->ev0)); CUB(cudaEventCreate(&h->ev1));
+  const size_t inbox_bytes = (size_t)3 * h->R * h->count * sizeof(u32);
+  CUB(cudaMalloc(&h->d_rec, (size_t)h->R * h->count * 32));
+  CUB(cudaMalloc(&h->d_inbox[0], inbox_bytes)); CUB(cudaMalloc(&h->d_inbox[1], inbox_bytes));
+  CUB(cudaMalloc(&h->d_node, (size_t)h->count * 8));
+  CUB(cudaMalloc(&h->d_overflow, 4)); CUB(cudaMalloc(&h->d_subj, MAX_SLOTS * 4)); CUB(cudaMalloc(&h->d_scratch, 64 * 8));
+  CUB(cudaMalloc(&h->d_stage, (size_t)h->count * 8));
+  CUB(cudaMalloc(&h->d_ones, 16));
+  const u32 ones[4] = {1, 1, 1, 1};
+  CUB(cudaMemcpy(h->d_ones, ones, 16, cudaMemcpyHostToDevice));
+  CUB(cudaMemcpy(h->d_subj, h->subj.data(), h->R * 4, cudaMemcpyHostToDevice));
+  h->grid = tick_grid_size(h->count);
+  if (cfg->world_size > 1) {
+    // receive windows: expected cross-shard entries per tick ≈ count · fanout · R · 3 / world per peer; SERFSIM_WIN_FACTOR scales it
+    double factor = 1.5;
+    if (const char* e = getenv("SERFSIM_WIN_FACTOR")) factor = atof(e);
+    double cap = (double)h->shard_size * cfg->fanout * h->R * factor / cfg->world_size + 4096.0;
+    h->win_cap = (u32)std::min(cap, 4.0e9);
+    for (int par = 0; par < 2; ++par) {
+      CUB(cudaMalloc(&h->d_win_data[par], (size_t)cfg->world_size * h->win_cap * 8));
+      CUB(cudaMalloc(&h->d_win_count[par], sizeof(u32) * cfg->world_size));
+      CUB(cudaMalloc(&h->d_peer_data[par], sizeof(u64*) * cfg->world_size));
+      CUB(cudaMalloc(&h->d_peer_count[par], sizeof(u32*) * cfg->world_size));
+    }
+  }
+  {
+    int rc = ensure_trace(h, 1024);
+    if (rc) return bail(rc);
+    rc = do_reset(h, cfg->seed);
+    if (rc) return bail(rc);
+  }
+#undef CUB
+  *out = h;
+  return 0;
+}
+
+void serfsim_destroy(serfsim_t* h) {
+  if (!h) return;
+  cudaStreamSynchronize(h->stream);
+  free_all(h);
+  delete h;
+}
+
+int serfsim_set_topology_csr(serfsim_t* h, const uint64_t* row_ptr, const uint32_t* col_idx) {
+  if (!h || !row_ptr || !col_idx) return fail(SERFSIM_E_INVAL, "null argument");
+  if (row_ptr[0] != 0) return fail(SERFSIM_E_INVAL, "row_ptr[0] must be 0");
+  const u64 e0 = row_ptr[h->first], e1 = row_ptr[h->first + h->count];
+  if (e1 < e0 || e1 - e0 >= 0xffffffffull) return fail(SERFSIM_E_INVAL, "shard has too many edges (u32 offsets)");
+  std::vector<u32> rp(h->count + 1);
+  for (u32 i = 0; i <= h->count; ++i) {
+    const u64 r = row_ptr[h->first + i];
+    if (r < e0 || (i && r < row_ptr[h->first + i - 1])) return fail(SERFSIM_E_INVAL, "row_ptr not monotone");
+    rp[i] = (u32)(r - e0);
+  }
+  const u64 ne = e1 - e0;
+  for (u64 i = 0; i < ne; ++i) if (col_idx[e0 + i] >= h->N) return fail(SERFSIM_E_INVAL, "col_idx out of range");
+  cudaFree(h->d_rowptr); cudaFree(h->d_col); h->d_rowptr = nullptr; h->d_col = nullptr;
+  CU(cudaMalloc(&h->d_rowptr, ((size_t)h->count + 1) * 4));
+  CU(cudaMalloc(&h->d_col, std::max<u64>(ne, 1) * 4));
+  CU(cudaMemcpy(h->d_rowptr, rp.data(), ((size_t)h->count + 1) * 4, cudaMemcpyHostToDevice));
+  if (ne) CU(cudaMemcpy(h->d_col, col_idx + e0, ne * 4, cudaMemcpyHostToDevice));
+  h->has_topo = true;
+  return 0;
+}
+
+int serfsim_set_subjects(serfsim_t* h, const uint32_t* subjects) {
+  if (!h || !subjects) return fail(SERFSIM_E_INVAL, "null argument");
+  if (h->tick != 0) return fail(SERFSIM_E_INVAL, "subjects can only change at tick 0");
+  for (u32 i = 0; i < h->R; ++i) {
+    if (subjects[i] >= h->N) return fail(SERFSIM_E_INVAL, "subject id out of range");
+    for (u32 j = 0; j < i; ++j) if (subjects[j] == subjects[i]) return fail(SERFSIM_E_INVAL, "subjects must be distinct");
+  }
+  h->subj.assign(subjects, subjects + h->R);
+  CU(cudaMemcpy(h->d_subj, h->subj.data(), h->R * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int serfsim_reset(serfsim_t* h, uint64_t seed) {
+  if (!h) return fail(SERFSIM_E_INVAL, "null handle");
+  return do_reset(h, seed);
+}
+
+int serfsim_inject(serfsim_t* h, uint32_t tick, uint32_t op, uint32_t node, uint32_t slot) {
+  if (!h) return fail(SERFSIM_E_INVAL, "null handle");
+  if (tick < h->tick) return fail(SERFSIM_E_INVAL, "cannot schedule an operation in the past");
+  if (node >= h->N || op < SERFSIM_OP_JOIN || op > SERFSIM_OP_REJOIN) return fail(SERFSIM_E_INVAL, "bad node / op");
+  if (op == SERFSIM_OP_FORCE_LEAVE) { if (slot >= h->R) return fail(SERFSIM_E_INVAL, "slot out of range"); }
+  else if ((op == SERFSIM_OP_JOIN || op == SERFSIM_OP_LEAVE) && slot_of(h, node) < 0)
+    return fail(SERFSIM_E_INVAL, "join/leave origin must be a tracked subject");
+  for (const auto& o : h->ops) if (o.tick == tick && o.node == node) return fail(SERFSIM_E_INVAL, "one operation per node per tick");
+  h->ops.push_back(HostOp{tick, op, node, slot, h->op_seq++});
+  h->ops_dirty = true;
+  return 0;
+}
+
+int serfsim_step(serfsim_t* h, uint32_t n_ticks) {
+  if (!h) return fail(SERFSIM_E_INVAL, "null handle");
+  int rc = launch_ticks(h, n_ticks);
+  if (rc) return rc;
+  rc = finish_timing(h);
+  if (rc) return rc;
+  rc = check_overflow(h);
+  if (rc) return rc;
+  return fire_events(h);
+}
+
+int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* ticks_out) {
+  if (!h) return fail(SERFSIM_E_INVAL, "null handle");
+  u32 chunk = 4;
+  if (const char* e = getenv("SERFSIM_CHUNK")) chunk = std::max(1, atoi(e));
+  const u32 start = h->tick;
+  int rc = 0;
+  while (h->tick - start < max_ticks) {
+    const u32 n = std::min(chunk, max_ticks - (h->tick - start));
+    const u32 from = h->tick;
+    if ((rc = launch_ticks(h, n))) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    if ((rc = pull_rows(h))) return rc;
+    for (u32 t = from; t < h->tick; ++t) {
+      const serfsim_tick_row_t& r = h->rows[t];
+      if (r.pending == 0 && r.edge_updates == 0 && !future_ops(h, t)) {
+        // ticks after t were no-ops on a quiescent cluster: rewind the logical clock to t + 1
+        if (h->tick > t + 1) {
+          CU(cudaMemsetAsync(h->d_trace + (size_t)(t + 1) * 8, 0, (size_t)(h->tick - t - 1) * 8 * sizeof(u64), h->stream));
+          h->tick = t + 1; h->rows.resize(t + 1);
+        }
+        if ((rc = finish_timing(h))) return rc;
+        if ((rc = check_overflow(h))) return rc;
+        if (ticks_out) *ticks_out = t;
+        return fire_events(h);
+      }
+    }
+  }
+  if ((rc = finish_timing(h))) return rc;
+  if ((rc = check_overflow(h))) return rc;
+  if (ticks_out) *ticks_out = h->tick;
+  if ((rc = fire_events(h))) return rc;
+  return 1;
+}
+
+int serfsim_shard_range(serfsim_t* h, uint32_t* first, uint32_t* count) {
+  if (!h) return fail(SERFSIM_E_INVAL, "null handle");
+  if (first) *first = h->first;
+  if (count) *count = h->count;
+  return 0;
+}
+int serfsim_member_status(serfsim_t* h, uint32_t slot, uint8_t* out) { return getter(h, slot, EXTRACT_STATUS, out, 1); }
+int serfsim_status_ltime(serfsim_t* h, uint32_t slot, uint64_t* out) { return getter(h, slot, EXTRACT_STATUS_LTIME, out, 8); }
+int serfsim_lamport_time(serfsim_t* h, uint64_t* out) { return getter(h, 0, EXTRACT_CLOCK, out, 8); }
+int serfsim_incarnation(serfsim_t* h, uint32_t slot, uint32_t* out) { return getter(h, slot, EXTRACT_INC, out, 4); }
+int serfsim_ml_state(serfsim_t* h, uint32_t slot, uint8_t* out) { return getter(h, slot, EXTRACT_ML, out, 1); }
+
+int serfsim_records(serfsim_t* h, uint32_t slot, void* out) {
+  if (!h || !out) return fail(SERFSIM_E_INVAL, "null argument");
+  if (slot >= h->R) return fail(SERFSIM_E_INVAL, "slot out of range");
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpy(out, (const char*)h->d_rec + (size_t)slot * h->count * 32, (size_t)h->count * 32, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int serfsim_tick_trace(serfsim_t* h, uint32_t first_tick, uint32_t n, serfsim_tick_row_t* out) {
+  if (!h || !out) return fail(SERFSIM_E_INVAL, "null argument");
+  if ((u64)first_tick + n > h->tick) return fail(SERFSIM_E_INVAL, "trace range beyond the executed ticks");
+  CU(cudaStreamSynchronize(h->stream));
+  int rc = pull_rows(h);
+  if (rc) return rc;
+  memcpy(out, h->rows.data() + first_tick, (size_t)n * sizeof(serfsim_tick_row_t));
+  return 0;
+}
+
+int serfsim_state_hash(serfsim_t* h, uint64_t* out) {
+  if (!h || !out) return fail(SERFSIM_E_INVAL, "null argument");
+  CU(cudaMemsetAsync(h->d_scratch, 0, 8, h->stream));
+  launch_state_hash(h->d_rec, h->d_node, h->count, h->first, h->N, h->R, h->d_scratch, h->stream);
+  CU(cudaMemcpyAsync(out, h->d_scratch, 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (h->cfg.world_size > 1) h->allreduce(h->comm_user, out, 1);
+  return 0;
+}
+
+int serfsim_stats(serfsim_t* h, serfsim_stats_t* o) {
+  if (!h || !o) return fail(SERFSIM_E_INVAL, "null argument");
+  memset(o, 0, sizeof(*o));
+  CU(cudaStreamSynchronize(h->stream));
+  int rc = pull_rows(h);
+  if (rc) return rc;
+  o->tick = h->tick; o->members = h->N;
+  for (size_t i = 0; i < h->rows.size(); ++i) {
+    const auto& r = h->rows[i];
+    o->packets += r.packets; o->edge_updates += r.edge_updates; o->messages += r.messages; o->changed += r.changed; o->events += r.events;
+    if (r.pending || r.edge_updates || r.events) o->last_active_tick = i;
+  }
+  if (!h->rows.empty()) o->pending = h->rows.back().pending;
+  const u32 nout = 2 + 2 * h->R;
+  std::vector<u64> init(nout, 0), out(nout);
+  for (u32 s = 0; s < h->R; ++s) init[2 + 2 * s] = ~0ull;
+  CU(cudaMemcpyAsync(h->d_scratch, init.data(), nout * 8, cudaMemcpyHostToDevice, h->stream));
+  launch_summary(h->d_rec, h->d_node, h->count, h->first, h->R, h->d_subj, h->d_scratch, h->stream);
+  CU(cudaMemcpyAsync(out.data(), h->d_scratch, nout * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  o->member_time = out[0]; o->intent_queue = out[1];
+  for (u32 s = 0; s < h->R; ++s) if (out[2 + 2 * s] != ~0ull && out[2 + 2 * s] != out[3 + 2 * s]) o->disagree_slots++;
+  return 0;
+}
+
+int serfsim_set_event_cb(serfsim_t* h, serfsim_event_cb cb, void* user) {
+  if (!h) return fail(SERFSIM_E_INVAL, "null handle");
+  h->cb = cb; h->cb_user = user;
+  return 0;
+}
+
+int serfsim_last_step_device_ms(serfsim_t* h, double* ms, uint64_t* kernel_launches) {
+  if (!h) return fail(SERFSIM_E_INVAL, "null handle");
+  if (ms) *ms = h->last_ms;
+  if (kernel_launches) *kernel_launches = h->last_launches;
+  return 0;
+}
+
+// ---- multi-GPU: CUDA IPC windows ----------------------------------------------------------
+struct comm_blob { cudaIpcMemHandle_t data[2]; cudaIpcMemHandle_t count[2]; u32 win_cap; u32 rank; };
+
+size_t serfsim_comm_blob_size(void) { return sizeof(comm_blob); }
+
+int serfsim_comm_export(serfsim_t* h, void* blob) {
+  if (!h || !blob) return fail(SERFSIM_E_INVAL, "null argument");
+  if (h->cfg.world_size < 2) return fail(SERFSIM_E_INVAL, "world_size == 1: nothing to export");
+  comm_blob b{};
+  for (int par = 0; par < 2; ++par) {
+    CU(cudaIpcGetMemHandle(&b.data[par], h->d_win_data[par]));
+    CU(cudaIpcGetMemHandle(&b.count[par], h->d_win_count[par]));
+  }
+  b.win_cap = h->win_cap; b.rank = (u32)h->cfg.rank;
+  memcpy(blob, &b, sizeof(b));
+  return 0;
+}
+
+int serfsim_comm_connect(serfsim_t* h, const void* blobs) {
+  if (!h || !blobs) return fail(SERFSIM_E_INVAL, "null argument");
+  const int W = h->cfg.world_size;
+  if (W < 2) return fail(SERFSIM_E_INVAL, "world_size == 1");
+  if (!h->barrier || !h->allreduce) return fail(SERFSIM_E_COMM, "serfsim_comm_set_hooks must be called first");
+  const comm_blob* bs = (const comm_blob*)blobs;
+  for (int par = 0; par < 2; ++par) {
+    std::vector<u64*> pd(W); std::vector<u32*> pc(W);
+    for (int r = 0; r < W; ++r) {
+      if (bs[r].rank != (u32)r || bs[r].win_cap != h->win_cap) return fail(SERFSIM_E_COMM, "blob order / window size mismatch");
+      if (r == h->cfg.rank) { pd[r] = h->d_win_data[par]; pc[r] = h->d_win_count[par]; continue; }
+      void *p1 = nullptr, *p2 = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&p1, bs[r].data[par], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return fail(SERFSIM_E_COMM, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+      e = cudaIpcOpenMemHandle(&p2, bs[r].count[par], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return fail(SERFSIM_E_COMM, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+      h->ipc_opened.push_back(p1); h->ipc_opened.push_back(p2);
+      pd[r] = (u64*)p1; pc[r] = (u32*)p2;
+    }
+    CU(cudaMemcpy(h->d_peer_data[par], pd.data(), sizeof(u64*) * W, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_peer_count[par], pc.data(), sizeof(u32*) * W, cudaMemcpyHostToDevice));
+  }
+  h->connected = true;
+  return 0;
+}
+
+int serfsim_comm_set_hooks(serfsim_t* h, serfsim_barrier_fn barrier, serfsim_allreduce_u64_fn allreduce, void* user) {
+  if (!h || !barrier || !allreduce) return fail(SERFSIM_E_INVAL, "null argument");
+  h->barrier = barrier; h->allreduce = allreduce; h->comm_user = user;
+  return 0;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

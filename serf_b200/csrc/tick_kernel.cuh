@@ -1,0 +1,55 @@
+// tick_kernel.cuh — parameter block and launch interface of the device side.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "record.cuh"
+
+namespace sfs {
+
+struct TickParams {
+  // geometry / run constants
+  u32 n_local, first, n_global, R;
+  u32 fanout, probe_every, tick, down_mask;
+  u32 seed_lo, seed_hi, ev_begin, ev_end;
+  Rules rules;
+  u32 subj[MAX_SLOTS];
+  // state in HBM
+  uint4* rec;                 // [R][n_local] records, 2 × uint4 each
+  u32* inbox_rd;              // [3][R][n_local] reduced inbox filled by the previous tick (value+1, 0 = empty)
+  u32* inbox_wr;              // [3][R][n_local] inbox the sends of this tick reduce into
+  u64* node_state;            // [n_local]  clock | up | SerfState | op-pending
+  const u32* row_ptr;         // [n_local+1] CSR offsets into col (shard-local)
+  const u32* col;             // neighbour ids (global)
+  const u32* ev_node;         // host operations, sorted by tick
+  const u32* ev_op;
+  const u32* ev_slot;
+  u64* row;                   // this tick's trace row (8 × u64, zeroed)
+  const u32* kinds_prev;      // [4] messages of each kind sent in the previous tick (skip empty inbox planes)
+  u32* kinds_cur;             // [4] same, for this tick
+  u32* overflow;              // set when a Lamport time / incarnation nears the device width
+  // cross-shard exchange (world_size > 1): per-destination-shard message windows in peer memory
+  u32 world, rank, shard_size, win_cap;
+  u64* const* win_data;       // [world] peer window payloads for THIS tick parity (entry = dst_local | kind/slot<<.. , value)
+  u32* const* win_count;      // [world] peer window fill counters
+};
+
+struct DrainParams {
+  u32 n_local, R, world, rank, win_cap;
+  const u64* win_data;        // my window: [world][win_cap]
+  u32* win_count;             // [world]
+  u32* inbox_wr;
+  u32* overflow;
+};
+
+void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st);
+void launch_drain(const DrainParams& p, cudaStream_t st);
+void launch_init_state(uint4* rec, u64* node_state, u32 n_local, u32 R, u32 init_st, u32 init_clock, cudaStream_t st);
+void launch_mark_events(u64* node_state, const u32* ev_node, u32 ev_begin, u32 ev_end, u32 first, u32 n_local, cudaStream_t st);
+void launch_extract(const uint4* rec, const u64* node_state, u32 n_local, u32 slot, int what, void* out, cudaStream_t st);
+void launch_state_hash(const uint4* rec, const u64* node_state, u32 n_local, u32 first, u32 n_global, u32 R, u64* out, cudaStream_t st);
+void launch_summary(const uint4* rec, const u64* node_state, u32 n_local, u32 first, u32 R, const u32* subj_dev, u64* out /*[2 + 2*R + 2]*/, cudaStream_t st);
+int tick_grid_size(u32 n_local);
+
+enum { EXTRACT_STATUS = 0, EXTRACT_STATUS_LTIME = 1, EXTRACT_CLOCK = 2, EXTRACT_INC = 3, EXTRACT_ML = 4 };
+
+}  // namespace sfs

@@ -1,0 +1,122 @@
+"""Synthetic workloads: the BASELINE.json configs (and a seeded fuzzer) as concrete inputs.
+
+A scenario is plain data — topology (CSR), tracked subjects, config overrides and a schedule
+of host operations — that can be fed to any GossipSim-shaped driver.  Nothing here computes
+simulation results.
+"""
+import numpy as np
+
+from .sim import Op, full_mesh_graph, random_regular_graph, small_world_graph
+
+
+class Scenario:
+    def __init__(self, name, n, slots, topology, subjects, ops, cfg=None, max_ticks=2000):
+        self.name, self.n, self.slots = name, n, slots
+        self.row_ptr, self.col = topology
+        self.subjects = np.asarray(subjects, dtype=np.uint32)
+        self.ops = list(ops)              # (tick, op, node, slot)
+        self.cfg = dict(cfg or {})
+        self.max_ticks = max_ticks
+
+    def build(self, factory, **extra_cfg):
+        """factory(n, slots, **cfg) → GossipSim-shaped driver, configured and scheduled."""
+        cfg = dict(self.cfg)
+        cfg.update(extra_cfg)
+        sim = factory(self.n, self.slots, **cfg)
+        sim.set_topology(self.row_ptr, self.col)
+        sim.set_subjects(self.subjects)
+        self.schedule(sim)
+        return sim
+
+    def schedule(self, sim):
+        for (tick, op, node, slot) in self.ops:
+            sim.inject(tick, op, node, slot)
+
+
+def full_mesh_leave(n=256, fanout=3, seed=1):
+    """configs[0]: 256-node full mesh, fanout 3; node 0 leaves gracefully, node 1 re-announces its join."""
+    ops = [(0, Op.LEAVE, 0, 0), (0, Op.JOIN, 1, 0)]
+    return Scenario(f"full_mesh_{n}", n, 2, full_mesh_graph(n), [0, 1], ops, dict(fanout=fanout, seed=seed))
+
+
+def random_graph_leave(n=100_000, degree=16, fanout=3, seed=1, slots=1, graph_seed=7):
+    """configs[1]: random graph (each node draws `degree` out-neighbours), one leave intent at tick 0."""
+    subjects = np.arange(slots, dtype=np.uint32) * np.uint32(max(1, n // max(1, slots)))
+    ops = [(0, Op.LEAVE, int(subjects[s]), 0) for s in range(slots)]
+    return Scenario(f"random_{n}_d{degree}_f{fanout}_r{slots}", n, slots, random_regular_graph(n, degree, graph_seed), subjects, ops,
+                    dict(fanout=fanout, seed=seed))
+
+
+def random_graph_fail(n=100_000, degree=16, fanout=3, seed=1, graph_seed=7):
+    """Failure detection: subject 0 crashes at tick 0, subject 1 leaves; SWIM probe → suspect → dead → Failed."""
+    subjects = [5, n // 2]
+    ops = [(0, Op.FAIL, 5, 0), (0, Op.LEAVE, n // 2, 0)]
+    return Scenario(f"random_fail_{n}", n, 2, random_regular_graph(n, degree, graph_seed), subjects, ops,
+                    dict(fanout=fanout, seed=seed), max_ticks=5000)
+
+
+def small_world_churn(n=1_000_000, k=16, beta=0.1, churn_frac=0.05, slots=8, window=200, seed=1, graph_seed=11, fanout=3):
+    """configs[2]: Watts–Strogatz small world, `churn_frac` of the nodes fail / rejoin at random ticks in
+    [0, window); `slots` tracked subjects are sampled from the churn set."""
+    rng = np.random.Generator(np.random.Philox(seed + 1000))
+    n_churn = max(slots, int(n * churn_frac))
+    churn = rng.choice(n, size=n_churn, replace=False).astype(np.uint32)
+    subjects = churn[:slots]
+    ops = []
+    for node in churn:
+        t_fail = int(rng.integers(0, window))
+        t_back = t_fail + 1 + int(rng.integers(1, window))
+        ops.append((t_fail, Op.FAIL, int(node), 0))
+        if rng.random() < 0.5:
+            ops.append((t_back, Op.REJOIN, int(node), 0))
+    return Scenario(f"small_world_{n}_churn", n, slots, small_world_graph(n, k, beta, graph_seed), subjects, ops,
+                    dict(fanout=fanout, seed=seed), max_ticks=20000)
+
+
+def dissemination_storm(n=10_000_000, degree=16, fanout=4, slots=1, seed=1, graph_seed=7, waves=1, spacing=8):
+    """configs[3] on one GPU / sharded: 10 M-node random graph, fanout 4.  Every tracked subject leaves at tick
+    0; with `waves` > 1 further force-leave / join operations follow every `spacing` ticks so the gossip front
+    never drains (sustained activity for throughput measurements)."""
+    subjects = (np.arange(slots, dtype=np.uint64) * np.uint64(max(1, n // max(1, slots))) + np.uint64(3)).astype(np.uint32)
+    ops = [(0, Op.LEAVE, int(subjects[s]), 0) for s in range(slots)]
+    for w in range(1, waves):
+        for s in range(slots):
+            origin = int((int(subjects[s]) + 1 + 7919 * w) % n)
+            if origin in set(int(x) for x in subjects):
+                origin = (origin + 1) % n
+            ops.append((w * spacing, Op.FORCE_LEAVE, origin, s))
+    return Scenario(f"storm_{n}_d{degree}_f{fanout}_r{slots}_w{waves}", n, slots, random_regular_graph(n, degree, graph_seed), subjects, ops,
+                    dict(fanout=fanout, seed=seed), max_ticks=4000)
+
+
+def fuzz(seed, n=None, slots=None):
+    """Seeded random scenario for parity fuzzing: small random graph, every operation kind, random timing,
+    short suspicion timers so failures resolve within a few hundred ticks."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    n = n or int(rng.integers(8, 400))
+    slots = slots or int(rng.integers(1, 9))
+    slots = min(slots, n)
+    degree = int(rng.integers(2, min(n - 1, 12) + 1))
+    topo = random_regular_graph(n, degree, seed + 17) if rng.random() < 0.7 else small_world_graph(n, max(2, degree // 2 * 2), 0.2, seed + 17)
+    subjects = rng.choice(n, size=slots, replace=False).astype(np.uint32)
+    cfg = dict(fanout=int(rng.integers(1, 6)), seed=int(rng.integers(1, 2**40)),
+               retransmit_mult=int(rng.integers(1, 5)), suspicion_mult=int(rng.integers(1, 6)),
+               suspicion_max_timeout_mult=int(rng.integers(1, 4)), probe_interval_ticks=int(rng.integers(0, 4)),
+               gossip_interval_ms=200, init_status_ltime=int(rng.integers(0, 3)), init_clock=int(rng.integers(1, 5)))
+    ops, used = [], set()
+    horizon = int(rng.integers(5, 120))
+    for _ in range(int(rng.integers(1, 30))):
+        t = int(rng.integers(0, horizon))
+        kind = rng.choice([Op.JOIN, Op.LEAVE, Op.FORCE_LEAVE, Op.FAIL, Op.REJOIN], p=[0.15, 0.2, 0.3, 0.2, 0.15])
+        s = int(rng.integers(0, slots))
+        if kind == Op.FORCE_LEAVE:
+            node = int(rng.integers(0, n)) if rng.random() < 0.8 else int(subjects[int(rng.integers(0, slots))])
+        elif kind in (Op.FAIL, Op.REJOIN) and rng.random() < 0.3:
+            node = int(rng.integers(0, n))
+        else:
+            node = int(subjects[s])
+        if (t, node) in used:
+            continue
+        used.add((t, node))
+        ops.append((t, int(kind), node, s))
+    return Scenario(f"fuzz_{seed}", n, slots, topo, subjects, ops, cfg, max_ticks=6000)

@@ -124,3 +124,14 @@ class RefNode:
             self.L.ref_event_get(self.p, i, C.byref(ty), C.byref(idv))
             out.append((ty.value, idv.value))
         return out
+
+
+# ---- Part B: the tick oracle driven through the same Python driver as the product --------
+def oracle_sim(n_nodes, slots=1, **cfg_kw):
+    """A GossipSim-shaped object backed by the CPU oracle (oracle_sim_* entry points)."""
+    from serf_b200 import sim as _sim
+    L = lib()
+    for name, (res, args) in _sim.SIGNATURES.items():
+        f = getattr(L, "oracle_sim_" + name)
+        f.restype, f.argtypes = res, args
+    return _sim.GossipSim(n_nodes, slots, _lib=L, _prefix="oracle_sim_", _errfn="oracle_last_error", **cfg_kw)

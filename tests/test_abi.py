@@ -1,0 +1,54 @@
+"""CPU checks of the drop-in boundary: libserfsim.so builds, loads, exports exactly the symbols
+include/serfsim.h declares, and refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from serf_b200 import build as sb
+from serf_b200 import sim
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "serfsim.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(serfsim_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    so = sb.build()
+    out = subprocess.check_output(["nm", "-D", "--defined-only", so]).decode()
+    exported = sorted(l.split()[-1] for l in out.splitlines() if " T " in l)
+    declared = _declared()
+    assert declared, "header parse failed"
+    assert exported == declared, (set(declared) ^ set(exported))
+
+
+def test_library_is_sm100a_with_red_and_no_oracle_dependency():
+    so = sb.build()
+    sass = subprocess.check_output(["cuobjdump", "-sass", so]).decode()
+    assert "sm_100a" in sass
+    assert "RED.E.MAX" in sass or "REDG.E.MAX" in sass or "RED.MAX" in sass or ".MAX" in sass      # inbox reduction is a hardware RED.MAX
+    needed = subprocess.check_output(["readelf", "-d", so]).decode()
+    assert "oracle" not in needed.lower()
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(sim.Config) == 12 * 4 + 8 + 4 * 4
+    assert C.sizeof(sim.Stats) == 12 * 8 and C.sizeof(sim.TickRow) == 8 * 8
+    assert sim.RECORD_DTYPE.itemsize == 32
+
+
+def test_create_fails_loudly_without_gpu():
+    lib = sim.load_library()
+    assert lib.serfsim_abi_version() == 1
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu tests")
+    with pytest.raises(sim.SerfsimError) as e:
+        sim.GossipSim(100, 1)
+    assert e.value.code == -2 and "no CPU" in str(e.value)
