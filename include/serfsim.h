@@ -182,6 +182,10 @@ int serfsim_set_event_cb (serfsim_t* h, serfsim_event_cb cb, void* user);
  *      serfsim_step / run_until_converged call, measured with CUDA events on the launch
  *      stream, and the number of kernel launches issued by that call ------------------- */
 int serfsim_last_step_device_ms(serfsim_t* h, double* ms, uint64_t* kernel_launches);
+/* Optional per-tick device timing (one CUDA event pair per tick, profiling runs only): enable,
+ * step, then read the duration in milliseconds of ticks [first_tick, first_tick + n). */
+int serfsim_set_tick_timing(serfsim_t* h, int enabled);
+int serfsim_tick_times(serfsim_t* h, uint32_t first_tick, uint32_t n, float* ms_out);
 
 /* ---- multi-GPU (one process per GPU; ids sharded by contiguous range) ---------------- */
 /* Size of the opaque blob a rank publishes to its peers, and the exchange itself: every

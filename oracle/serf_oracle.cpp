@@ -546,7 +546,8 @@ struct TickSim {
   std::vector<u32> timeout; RuleCtx cx;
   std::vector<serfsim_tick_row_t> trace;
   std::vector<u8> subj_up;      // ground truth per slot
-  std::vector<Msg> inflight;    // messages sent in the previous tick
+  std::vector<std::vector<Msg>> mail;   // messages sent in the previous tick: [producer range][consumer range]
+  u32 chunk = 1;
   u64 tot_events = 0;
   int threads = 1;
   std::string err;
@@ -561,7 +562,8 @@ struct TickSim {
     cx.timeout = timeout.data();
   }
   void reset(u64 seed) {
-    cfg.seed = seed; tick = 0; events.clear(); trace.clear(); inflight.clear(); tot_events = 0;
+    cfg.seed = seed; tick = 0; events.clear(); trace.clear(); mail.clear(); tot_events = 0;
+    chunk = (N + threads - 1) / threads;
     rec.assign((size_t)R * N, View{});
     node.assign(N, NodeB{cfg.init_clock, 1, SS_ALIVE});
     for (u32 s = 0; s < R; ++s)
@@ -595,32 +597,44 @@ struct TickSim {
     return true;
   }
 
+  // One tick.  Nodes are independent within a tick (bulk-synchronous), so the node loop is split into
+  // `threads` contiguous id ranges; each range owner gathers its mail, applies it literally and posts the
+  // outgoing messages into per-(producer, consumer) boxes.  Results do not depend on `threads`.
+  u32 owner_of(u32 v) const { return v / chunk; }
   void step_one() {
     const u32 t = tick;
-    serfsim_tick_row_t row{};
-    // ---- bucket last tick's messages by destination (stable counting sort) ----
-    std::vector<u32> head(N + 1, 0);
-    for (auto& m : inflight) head[m.dst + 1]++;
-    for (u32 i = 0; i < N; ++i) head[i + 1] += head[i];
-    std::vector<Msg> byd(inflight.size());
-    { std::vector<u32> pos(head.begin(), head.end() - 1); for (auto& m : inflight) byd[pos[m.dst]++] = m; }
-    inflight.clear();
+    const u32 T = (u32)threads;
+    if (mail.size() != (size_t)T * T) { mail.assign((size_t)T * T, {}); }
+    std::vector<std::vector<Msg>> next((size_t)T * T);
     // events of this tick
     std::vector<EventB> evs;
-    for (auto& e : events) if (e.tick == t) evs.push_back(e);
+    std::unordered_map<u32, EventB> ev_of;
+    for (auto& e : events) if (e.tick == t) { evs.push_back(e); ev_of[e.node] = e; }
     // ground truth after this tick's operations (what a failed probe observes)
     for (auto& e : evs) {
       int s = slot_of(e.node);
       if (s >= 0) { if (e.op == SERFSIM_OP_FAIL) subj_up[s] = 0; if (e.op == SERFSIM_OP_REJOIN) subj_up[s] = 1; }
     }
     bool any_down = false; for (u32 s = 0; s < R; ++s) any_down |= !subj_up[s];
+    std::vector<serfsim_tick_row_t> rows(T);
 
-    std::vector<Msg> out;
-    for (u32 v = 0; v < N; ++v) {
+    auto work = [&](u32 c) {
+    serfsim_tick_row_t& row = rows[c];
+    const u32 v0 = c * chunk, v1 = std::min<u64>(N, (u64)(c + 1) * chunk);
+    if (v0 >= v1) return;
+    // ---- bucket last tick's messages for my id range by destination (stable counting sort) ----
+    std::vector<u32> head(v1 - v0 + 1, 0);
+    size_t total = 0;
+    for (u32 p = 0; p < T; ++p) { for (auto& m : mail[(size_t)p * T + c]) head[m.dst - v0 + 1]++; total += mail[(size_t)p * T + c].size(); }
+    for (u32 i = 0; i < v1 - v0; ++i) head[i + 1] += head[i];
+    std::vector<Msg> byd(total);
+    { std::vector<u32> pos(head.begin(), head.end() - 1); for (u32 p = 0; p < T; ++p) for (auto& m : mail[(size_t)p * T + c]) byd[pos[m.dst - v0]++] = m; }
+    auto post = [&](const Msg& m) { next[(size_t)c * T + owner_of(m.dst)].push_back(m); };
+    for (u32 v = v0; v < v1; ++v) {
       NodeB& nd = node[v];
       const bool up_r = nd.up;
       const EventB* ev = nullptr;
-      for (auto& e : evs) if (e.node == v) { ev = &e; break; }        // at most one op per (node, tick)
+      if (!ev_of.empty()) { auto it = ev_of.find(v); if (it != ev_of.end()) ev = &it->second; }   // at most one op per (node, tick)
       bool up_s = up_r;
       if (ev && ev->op == SERFSIM_OP_FAIL) up_s = false;
       if (ev && ev->op == SERFSIM_OP_REJOIN) up_s = true;
@@ -636,7 +650,7 @@ struct TickSim {
         if (up_r) {
           const View before = r;
           std::vector<Msg> ml, lv, jn;
-          for (u32 i = head[v]; i < head[v + 1]; ++i) {
+          for (u32 i = head[v - v0]; i < head[v - v0 + 1]; ++i) {
             const Msg& m = byd[i];
             if (m.slot != s) continue;
             (m.kind == 2 ? ml : m.kind == 0 ? lv : jn).push_back(m);
@@ -707,9 +721,9 @@ struct TickSim {
             if (!have_targets) { nt = gossip_targets(v, t, targets); have_targets = true; }
             for (u32 k = 0; k < nt; ++k) {
               u32 cnt = 0;
-              if (r.txl > k) { out.push_back(Msg{targets[k], v, r.qleave, (u8)s, 0}); ++cnt; }
-              if (r.txj > k) { out.push_back(Msg{targets[k], v, r.qjoin, (u8)s, 1}); ++cnt; }
-              if (r.txm > k) { out.push_back(Msg{targets[k], v, ml_key(r), (u8)s, 2}); ++cnt; }
+              if (r.txl > k) { post(Msg{targets[k], v, r.qleave, (u8)s, 0}); ++cnt; }
+              if (r.txj > k) { post(Msg{targets[k], v, r.qjoin, (u8)s, 1}); ++cnt; }
+              if (r.txm > k) { post(Msg{targets[k], v, ml_key(r), (u8)s, 2}); ++cnt; }
               if (cnt) { row.edge_updates++; row.messages += cnt; }
             }
             max_tx = std::max(max_tx, (u32)std::max(r.txl, std::max(r.txj, r.txm)));
@@ -729,7 +743,13 @@ struct TickSim {
       nd.up = up_s;
       row.packets += std::min(nt, max_tx);
     }
-    inflight.swap(out);
+    };
+    if (T == 1) work(0);
+    else { std::vector<std::thread> th; for (u32 c = 0; c < T; ++c) th.emplace_back(work, c); for (auto& x : th) x.join(); }
+    mail.swap(next);
+    serfsim_tick_row_t row{};
+    for (auto& r : rows) { row.packets += r.packets; row.edge_updates += r.edge_updates; row.messages += r.messages; row.changed += r.changed;
+                           row.pending += r.pending; row.events += r.events; row.suspects += r.suspects; }
     if (cfg.trace) row.hash = state_hash();
     trace.push_back(row);
     tot_events += row.events;
@@ -894,5 +914,12 @@ ORC int oracle_sim_stats(void* p, serfsim_stats_t* o) {
     }
     if (diff) o->disagree_slots++;
   }
+  return 0;
+}
+// Number of host threads the tick loop uses (results are independent of it).  Takes effect at the next reset.
+ORC int oracle_sim_set_threads(void* p, int n) {
+  auto* s = (TickSim*)p;
+  if (n < 1 || s->tick != 0) return SERFSIM_E_INVAL;
+  s->threads = n; s->chunk = (s->N + n - 1) / n; s->mail.clear();
   return 0;
 }

@@ -119,6 +119,8 @@ struct serfsim {
   bool connected = false;
   serfsim_barrier_fn barrier = nullptr; serfsim_allreduce_u64_fn allreduce = nullptr; void* comm_user = nullptr;
   std::vector<void*> ipc_opened;
+  bool tick_timing = false;
+  std::vector<cudaEvent_t> tick_ev;      // 2 per tick when tick_timing
 };
 
 namespace {
@@ -209,7 +211,12 @@ int launch_ticks(serfsim* h, u32 n) {
     p.overflow = h->d_overflow;
     p.world = (u32)h->cfg.world_size; p.rank = (u32)h->cfg.rank; p.shard_size = h->shard_size; p.win_cap = h->win_cap;
     p.win_data = h->d_peer_data[t & 1]; p.win_count = h->d_peer_count[t & 1];
+    if (h->tick_timing) {
+      while (h->tick_ev.size() < 2 * ((size_t)t + 1)) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->tick_ev.push_back(e); }
+      CU(cudaEventRecord(h->tick_ev[2 * (size_t)t], h->stream));
+    }
     launch_tick(p, h->cfg.trace != 0, h->grid, h->stream);
+    if (h->tick_timing) CU(cudaEventRecord(h->tick_ev[2 * (size_t)t + 1], h->stream));
     h->last_launches++;
     if (h->cfg.world_size > 1) {
       // all peers have finished writing into my window of this parity once the barrier returns
@@ -303,6 +310,7 @@ int do_reset(serfsim* h, u64 seed) {
 
 void free_all(serfsim* h) {
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+  for (cudaEvent_t e : h->tick_ev) cudaEventDestroy(e);
   cudaFree(h->d_rec); cudaFree(h->d_inbox[0]); cudaFree(h->d_inbox[1]); cudaFree(h->d_node); cudaFree(h->d_rowptr); cudaFree(h->d_col);
   cudaFree(h->d_ev_node); cudaFree(h->d_ev_op); cudaFree(h->d_ev_slot); cudaFree(h->d_trace); cudaFree(h->d_kinds); cudaFree(h->d_ones);
   cudaFree(h->d_overflow); cudaFree(h->d_subj); cudaFree(h->d_scratch); cudaFree(h->d_stage);
@@ -596,6 +604,20 @@ int serfsim_last_step_device_ms(serfsim_t* h, double* ms, uint64_t* kernel_launc
   if (!h) return fail(SERFSIM_E_INVAL, "null handle");
   if (ms) *ms = h->last_ms;
   if (kernel_launches) *kernel_launches = h->last_launches;
+  return 0;
+}
+
+int serfsim_set_tick_timing(serfsim_t* h, int enabled) {
+  if (!h) return fail(SERFSIM_E_INVAL, "null handle");
+  h->tick_timing = enabled != 0;
+  return 0;
+}
+
+int serfsim_tick_times(serfsim_t* h, uint32_t first_tick, uint32_t n, float* ms_out) {
+  if (!h || !ms_out) return fail(SERFSIM_E_INVAL, "null argument");
+  if (((size_t)first_tick + n) * 2 > h->tick_ev.size()) return fail(SERFSIM_E_INVAL, "tick timing was not enabled for that range");
+  CU(cudaStreamSynchronize(h->stream));
+  for (u32 i = 0; i < n; ++i) CU(cudaEventElapsedTime(ms_out + i, h->tick_ev[2 * ((size_t)first_tick + i)], h->tick_ev[2 * ((size_t)first_tick + i) + 1]));
   return 0;
 }
 

@@ -106,6 +106,8 @@ PRODUCT_ONLY = {
     "serfsim_shard_range": (C.c_int, [_vp, C.POINTER(_u32), C.POINTER(_u32)]),
     "serfsim_set_event_cb": (C.c_int, [_vp, EVENT_CB, _vp]),
     "serfsim_last_step_device_ms": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(_u64)]),
+    "serfsim_set_tick_timing": (C.c_int, [_vp, C.c_int]),
+    "serfsim_tick_times": (C.c_int, [_vp, _u32, _u32, _vp]),
     "serfsim_comm_blob_size": (C.c_size_t, []),
     "serfsim_comm_export": (C.c_int, [_vp, _vp]),
     "serfsim_comm_connect": (C.c_int, [_vp, _vp]),
@@ -275,6 +277,17 @@ class GossipSim:
         ms, n = C.c_double(), _u64()
         self._check(self._lib.serfsim_last_step_device_ms(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def set_tick_timing(self, enabled=True):
+        self._check(self._lib.serfsim_set_tick_timing(self._h, int(enabled)))
+
+    def tick_times_ms(self, first=0, n=None):
+        if n is None:
+            n = self.stats()["tick"] - first
+        out = np.zeros(n, dtype=np.float32)
+        if n:
+            self._check(self._lib.serfsim_tick_times(self._h, int(first), int(n), out.ctypes.data))
+        return out
 
     def set_event_callback(self, fn):
         """fn(tick, type, ids) — batched EventDelegate (serf/delegate.rs:557-582)."""
