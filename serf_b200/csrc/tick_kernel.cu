@@ -17,7 +17,7 @@
 // R 32-byte records with 128-bit loads (a warp covers 1 KB contiguous per plane), the three
 // inbox planes with coalesced 32-bit loads, and scatters 32-bit RED.MAX to random peers; the
 // inbox planes are the only randomly addressed data and are sized to stay L2-resident.
-#include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "tick_kernel.cuh"
 
@@ -27,11 +27,45 @@ namespace {
 
 constexpr int BLOCK = 256;
 
-__device__ __forceinline__ uint4 ld_rec(const uint4* p) { return __ldcg(p); }        // L2-only: records are streamed once per tick
-__device__ __forceinline__ void st_rec(uint4* p, const uint4& v) { __stcg(p, v); }
+// ---- cache-policy plumbing -------------------------------------------------------------------
+// The only randomly addressed data of a tick are the inbox planes the sends reduce into (RED.MAX,
+// 4 B at a random node).  They are kept L2-resident with an evict_last policy; everything that is
+// streamed exactly once per tick (records, node state, the inbox parity being consumed) goes
+// through evict_first / no-L1-allocate so it does not push the inbox out of the 126 MB L2.
+__device__ __forceinline__ u64 policy_evict_first() { u64 p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ u64 policy_evict_last() { u64 p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
 
-struct Counters {
-  u32 packets, edges, msgs, changed, pending, events, suspects, kL, kJ, kM;
+struct Words { u32 w[8]; };   // one 32-byte record
+
+__device__ __forceinline__ Words ld_rec256(const uint4* ptr, u64 pol) {   // one 256-bit load = one DRAM sector
+  Words r;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+               : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+               : "l"(ptr), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ void st_rec256(uint4* ptr, const Words& r, u64 pol) {
+  asm volatile("st.global.L2::cache_hint.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;"
+               :: "l"(ptr), "r"(r.w[0]), "r"(r.w[1]), "r"(r.w[2]), "r"(r.w[3]), "r"(r.w[4]), "r"(r.w[5]), "r"(r.w[6]), "r"(r.w[7]), "l"(pol) : "memory");
+}
+__device__ __forceinline__ u64 ld_u64_stream(const u64* ptr, u64 pol) {
+  u64 v; asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(ptr), "l"(pol)); return v;
+}
+__device__ __forceinline__ u32 ld_u32_stream(const u32* ptr, u64 pol) {
+  u32 v; asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol)); return v;
+}
+__device__ __forceinline__ void st_u32_stream(u32* ptr, u32 v, u64 pol) {
+  asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(ptr), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_u64_stream(u64* ptr, u64 v, u64 pol) {
+  asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" :: "l"(ptr), "l"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_max_resident(u32* ptr, u32 v, u64 pol) {   // RED.MAX, result unused, line kept in L2
+  asm volatile("red.relaxed.gpu.global.max.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(ptr), "r"(v), "l"(pol) : "memory");
+}
+
+struct Counters {          // per-thread, reduced once per CTA; rare counters (events, suspects) go straight to the trace row
+  u32 packets, edges, changed, pending, kL, kJ, kM;
   u64 hash;
 };
 
@@ -46,18 +80,18 @@ __device__ __forceinline__ u64 warp_sum64(u64 v) {
   return v;
 }
 
-// Deliver one entry to `dst` (global id): local → RED.MAX into this shard's inbox.
-__device__ __forceinline__ void deliver(const TickParams& p, u32 dst, u32 kind, u32 s, u32 val1) {
-  u32 dl = dst - p.first;
+// Deliver one entry to `dst` (global id): local → RED.MAX into this shard's inbox plane `plane`
+// (= inbox_wr + (kind·R + slot)·n_local); cross-shard → append to the peer's receive window over NVLink.
+__device__ __forceinline__ void deliver(const TickParams& p, u32* plane, u32 dst, u32 kind, u32 s, u32 val1, u64 pol_last) {
+  const u32 dl = dst - p.first;
   if (dl < p.n_local) {
-    atomicMax(p.inbox_wr + ((size_t)(kind * p.R + s)) * p.n_local + dl, val1);
+    red_max_resident(plane + dl, val1, pol_last);
   } else {
-    // cross-shard: append (dst_local, kind, slot, value) to the peer's receive window over NVLink
-    u32 shard = dst / p.shard_size;
-    u32 dloc = dst - shard * p.shard_size;
-    u32 pos = atomicAdd(p.win_count[shard] + p.rank, 1u);
+    const u32 shard = dst / p.shard_size;
+    const u32 dloc = dst - shard * p.shard_size;
+    const u32 pos = atomicAdd(p.win_count[shard] + p.rank, 1u);
     if (pos < p.win_cap) {
-      u64 e = ((u64)val1 << 32) | ((u64)s << 28) | ((u64)kind << 26) | dloc;
+      const u64 e = ((u64)val1 << 32) | ((u64)s << 28) | ((u64)kind << 26) | dloc;
       p.win_data[shard][(size_t)p.rank * p.win_cap + pos] = e;
     } else {
       *p.overflow = 2;
@@ -65,29 +99,51 @@ __device__ __forceinline__ void deliver(const TickParams& p, u32 dst, u32 kind, 
   }
 }
 
-template <bool TRACE>
-__device__ __forceinline__ void process_node(const TickParams& p, u32 vl, bool kL, bool kJ, bool kM, Counters& c) {
+__device__ __forceinline__ void unpack_words(const Words& x, Rec& r) {
+  r.st = x.w[0]; r.qjoin = x.w[1]; r.qleave = x.w[2]; r.inc = x.w[3]; r.deadline = x.w[4]; r.leave_tick = x.w[5];
+  r.status = x.w[6] & 0xff; r.mlstate = (x.w[6] >> 8) & 3; r.qfrom = (x.w[6] >> 10) & 15; r.txj = (x.w[6] >> 16) & 0xff; r.txl = x.w[6] >> 24;
+  r.txm = x.w[7] & 0xff; r.flags = (x.w[7] >> 8) & 0xff; r.mask = x.w[7] >> 16;
+}
+__device__ __forceinline__ void pack_words(const Rec& r, Words& x) {
+  x.w[0] = r.st; x.w[1] = r.qjoin; x.w[2] = r.qleave; x.w[3] = r.inc; x.w[4] = r.deadline; x.w[5] = r.leave_tick;
+  x.w[6] = r.status | (r.mlstate << 8) | (r.qfrom << 10) | (r.txj << 16) | (r.txl << 24);
+  x.w[7] = r.txm | (r.flags << 8) | (r.mask << 16);
+}
+__device__ __forceinline__ bool differs(const Words& a, const Words& b) {
+  return ((a.w[0] ^ b.w[0]) | (a.w[1] ^ b.w[1]) | (a.w[2] ^ b.w[2]) | (a.w[3] ^ b.w[3]) | (a.w[4] ^ b.w[4]) | (a.w[5] ^ b.w[5]) | (a.w[6] ^ b.w[6]) | (a.w[7] ^ b.w[7])) != 0;
+}
+
+template <bool TRACE, int FMAX>
+__device__ __forceinline__ void process_node(const TickParams& p, u32 vl, bool kL, bool kJ, bool kM, u64 pol_first, u64 pol_last, Counters& c) {
   const u32 v = p.first + vl;
   const u32 t = p.tick;
   const u32 limit = p.rules.limit;
-  const u64 ns = p.node_state[vl];
+  const u32 nl = p.n_local;
+
+  // ---- front-loaded, independent loads: node word, CSR row bounds, slot-0 record and inbox words ----
+  const u64 ns = ld_u64_stream(p.node_state + vl, pol_first);
+  const u32 row0 = __ldg(p.row_ptr + vl), row1 = __ldg(p.row_ptr + vl + 1);
+  Words cur = ld_rec256(p.rec + 2 * (size_t)vl, pol_first);
+  u32 mL = 0, mJ = 0, mM = 0;
+  if (kL) mL = ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * p.R) * nl + vl, pol_first);
+  if (kJ) mJ = ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * p.R) * nl + vl, pol_first);
+  if (kM) mM = ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * p.R) * nl + vl, pol_first);
+
   u32 clock = (u32)ns;
   const bool up_r = (ns & NS_UP) != 0;
   u32 sstate = (u32)(ns >> 40) & 3;
+  const u32 deg = row1 - row0;
 
   // host operation for this node (at most one per tick; the mark kernel set NS_EV)
   u32 op = 0, op_slot = 0;
   if (ns & NS_EV) {
     for (u32 e = p.ev_begin; e < p.ev_end; ++e)
       if (p.ev_node[e] == v) { op = p.ev_op[e]; op_slot = p.ev_slot[e]; break; }
-    c.events++;
+    atomicAdd((unsigned long long*)(p.row + 5), 1ull);
   }
   bool up_s = up_r;
   if (op == OP_FAIL) up_s = false;
   if (op == OP_REJOIN) up_s = true;
-
-  const u32 row0 = p.row_ptr[vl];
-  const u32 deg = p.row_ptr[vl + 1] - row0;
 
   // SWIM probe target of this round (only matters while some tracked subject is down)
   bool have_probe = false;
@@ -99,20 +155,25 @@ __device__ __forceinline__ void process_node(const TickParams& p, u32 vl, bool k
     have_probe = true;
   }
 
-  u32 targets[MAX_FANOUT];
+  u32 targets[FMAX];
   u32 nt = 0;
   bool have_targets = false;
   u32 max_tx = 0;
 
   for (u32 s = 0; s < p.R; ++s) {
-    const size_t idx = (size_t)s * p.n_local + vl;
-    const uint4 a0 = ld_rec(p.rec + 2 * idx), b0 = ld_rec(p.rec + 2 * idx + 1);
-    u32 mL = 0, mJ = 0, mM = 0;
-    if (kL) { u32* q = p.inbox_rd + ((size_t)(KIND_LEAVE * p.R + s)) * p.n_local + vl; mL = __ldcg(q); if (mL) __stcg(q, 0u); }
-    if (kJ) { u32* q = p.inbox_rd + ((size_t)(KIND_JOIN * p.R + s)) * p.n_local + vl; mJ = __ldcg(q); if (mJ) __stcg(q, 0u); }
-    if (kM) { u32* q = p.inbox_rd + ((size_t)(KIND_ML * p.R + s)) * p.n_local + vl; mM = __ldcg(q); if (mM) __stcg(q, 0u); }
+    const size_t idx = (size_t)s * nl + vl;
+    if (s) {                                               // slots > 0: load at the top of the iteration
+      cur = ld_rec256(p.rec + 2 * idx, pol_first);
+      mL = kL ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * p.R + s) * nl + vl, pol_first) : 0;
+      mJ = kJ ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * p.R + s) * nl + vl, pol_first) : 0;
+      mM = kM ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * p.R + s) * nl + vl, pol_first) : 0;
+    }
+    if (mL) st_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * p.R + s) * nl + vl, 0u, pol_first);   // consume: clear for reuse in two ticks
+    if (mJ) st_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * p.R + s) * nl + vl, 0u, pol_first);
+    if (mM) st_u32_stream(p.inbox_rd + (size_t)(KIND_ML * p.R + s) * nl + vl, 0u, pol_first);
+    const Words orig = cur;
     Rec r;
-    unpack(a0, b0, r);
+    unpack_words(cur, r);
     const bool self = (p.subj[s] == v);
 
     // ---------------- Phase R ----------------
@@ -131,10 +192,9 @@ __device__ __forceinline__ void process_node(const TickParams& p, u32 vl, bool k
         join_intent(r, T, limit);
         r.qjoin = T; r.txj = limit;
       }
-      uint4 a1, b1;
-      pack(r, a1, b1);
-      if (a1.x != a0.x || a1.y != a0.y || a1.z != a0.z || a1.w != a0.w || b1.x != b0.x || b1.y != b0.y || b1.z != b0.z || b1.w != b0.w)
-        c.changed++;
+      Words mid;
+      pack_words(r, mid);
+      c.changed += differs(mid, orig) ? 1 : 0;
     }
     // ---------------- Phase E ----------------
     if (op) {
@@ -168,42 +228,50 @@ __device__ __forceinline__ void process_node(const TickParams& p, u32 vl, bool k
       if (r.mlstate == ML_SUSPECT && r.deadline != 0 && t >= r.deadline) ml_dead(r, r.inc, false, t, false, limit);
       if (have_probe && !self && ptarget == p.subj[s] && ((p.down_mask >> s) & 1)) {
         if (r.mlstate == ML_ALIVE || r.mlstate == ML_SUSPECT) {
-          if (r.mlstate == ML_ALIVE) c.suspects++;
+          if (r.mlstate == ML_ALIVE) atomicAdd((unsigned long long*)(p.row + 6), 1ull);
           ml_suspect(r, r.inc, from_bucket(v), t, false, p.rules);
         }
       }
       // ---------------- Phase S ----------------
-      if (r.txl | r.txj | r.txm) {
+      const u32 mx = max(r.txl, max(r.txj, r.txm));
+      if (mx) {
         if (!have_targets) {
           // kRandomNodes: up to 3·deg draws for `fanout` distinct peers other than ourselves
           u32 w[4] = {0, 0, 0, 0};
-          for (u32 i = 0; i < 3 * deg && nt < p.fanout; ++i) {
+          const u32 tries = 3 * deg;
+          for (u32 i = 0; i < tries && nt < p.fanout; ++i) {
             if ((i & 3) == 0) philox4x32_10(t, v, i >> 2, DOMAIN_GOSSIP, p.seed_lo, p.seed_hi, w);
-            const u32 cnd = __ldg(p.col + row0 + mulhi32(w[i & 3], deg));
+            const u32 wi = (i & 3) == 0 ? w[0] : (i & 3) == 1 ? w[1] : (i & 3) == 2 ? w[2] : w[3];
+            const u32 cnd = __ldg(p.col + row0 + mulhi32(wi, deg));
             bool skip = (cnd == v);
 #pragma unroll
-            for (u32 j = 0; j < MAX_FANOUT; ++j) skip |= (j < nt && targets[j] == cnd);
+            for (int j = 0; j < FMAX; ++j) skip |= ((u32)j < nt && targets[j] == cnd);
             if (!skip) {
 #pragma unroll
-              for (u32 j = 0; j < MAX_FANOUT; ++j) if (j == nt) targets[j] = cnd;
+              for (int j = 0; j < FMAX; ++j) if ((u32)j == nt) targets[j] = cnd;
               ++nt;
             }
           }
           have_targets = true;
         }
-        const u32 key1 = ml_key(r) + 1;
+        u32* const planeL = p.inbox_wr + (size_t)(KIND_LEAVE * p.R + s) * nl;
+        u32* const planeJ = p.inbox_wr + (size_t)(KIND_JOIN * p.R + s) * nl;
+        u32* const planeM = p.inbox_wr + (size_t)(KIND_ML * p.R + s) * nl;
+        const u32 vL = r.qleave + 1, vJ = r.qjoin + 1, vM = ml_key(r) + 1;
 #pragma unroll
-        for (u32 k = 0; k < MAX_FANOUT; ++k) {
-          if (k < nt) {
-            u32 cnt = 0;
-            if (r.txl > k) { deliver(p, targets[k], KIND_LEAVE, s, r.qleave + 1); ++cnt; c.kL++; }
-            if (r.txj > k) { deliver(p, targets[k], KIND_JOIN, s, r.qjoin + 1); ++cnt; c.kJ++; }
-            if (r.txm > k) { deliver(p, targets[k], KIND_ML, s, key1); ++cnt; c.kM++; }
-            if (cnt) { c.edges++; c.msgs += cnt; }
+        for (int k = 0; k < FMAX; ++k) {
+          if ((u32)k < nt) {
+            const u32 dst = targets[k];
+            if (r.txl > (u32)k) deliver(p, planeL, dst, KIND_LEAVE, s, vL, pol_last);
+            if (r.txj > (u32)k) deliver(p, planeJ, dst, KIND_JOIN, s, vJ, pol_last);
+            if (r.txm > (u32)k) deliver(p, planeM, dst, KIND_ML, s, vM, pol_last);
           }
         }
-        max_tx = max(max_tx, max(r.txl, max(r.txj, r.txm)));
-        r.txl -= min(r.txl, nt); r.txj -= min(r.txj, nt); r.txm -= min(r.txm, nt);
+        const u32 sL = min(r.txl, nt), sJ = min(r.txj, nt), sM = min(r.txm, nt);
+        c.kL += sL; c.kJ += sJ; c.kM += sM;
+        c.edges += min(mx, nt);
+        max_tx = max(max_tx, mx);
+        r.txl -= sL; r.txj -= sJ; r.txm -= sM;
       }
       // Serf::leave: our own leave intent is out → memberlist.leave() → dead{node == from}  (serf/api.rs:451-476)
       if (self && sstate == SS_LEAVING && r.txl == 0 && r.mlstate == ML_ALIVE) {
@@ -213,47 +281,53 @@ __device__ __forceinline__ void process_node(const TickParams& p, u32 vl, bool k
                         (p.probe_every && ((p.down_mask >> s) & 1) && !self && r.mlstate == ML_ALIVE);
       c.pending += pend ? 1 : 0;
     }
-    uint4 a2, b2;
-    pack(r, a2, b2);
-    if (a2.x != a0.x || a2.y != a0.y || a2.z != a0.z || a2.w != a0.w) st_rec(p.rec + 2 * idx, a2);
-    if (b2.x != b0.x || b2.y != b0.y || b2.z != b0.z || b2.w != b0.w) st_rec(p.rec + 2 * idx + 1, b2);
-    if (TRACE) c.hash += rec_hash((u64)s * p.n_global + v, a2, b2);
+    pack_words(r, cur);
+    if (differs(cur, orig)) st_rec256(p.rec + 2 * idx, cur, pol_first);
+    if (TRACE) {
+      const uint4 a2 = make_uint4(cur.w[0], cur.w[1], cur.w[2], cur.w[3]), b2 = make_uint4(cur.w[4], cur.w[5], cur.w[6], cur.w[7]);
+      c.hash += rec_hash((u64)s * p.n_global + v, a2, b2);
+    }
     if (r.inc >= INC_LIMIT) *p.overflow = 1;
   }
   const u64 ns2 = (u64)clock | (up_s ? NS_UP : 0) | ((u64)sstate << 40);
-  if (ns2 != ns) p.node_state[vl] = ns2;
+  if (ns2 != ns) st_u64_stream(p.node_state + vl, ns2, pol_first);
   if (TRACE) c.hash += node_hash((u64)p.R * p.n_global + v, ns2);
   if (clock >= LTIME_LIMIT) *p.overflow = 1;
   c.packets += min(nt, max_tx);
 }
 
-template <bool TRACE>
-__global__ void __launch_bounds__(BLOCK) tick_kernel(const __grid_constant__ TickParams p) {
+template <bool TRACE, int FMAX, int MB>
+__global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__ TickParams p) {
   Counters c = {};
   const bool kL = p.kinds_prev[KIND_LEAVE] != 0, kJ = p.kinds_prev[KIND_JOIN] != 0, kM = p.kinds_prev[KIND_ML] != 0;
+  const u64 pol_first = policy_evict_first(), pol_last = policy_evict_last();
   for (u32 base = blockIdx.x * BLOCK; base < p.n_local; base += gridDim.x * BLOCK) {
     const u32 vl = base + threadIdx.x;
-    if (vl < p.n_local) process_node<TRACE>(p, vl, kL, kJ, kM, c);
+    if (vl < p.n_local) process_node<TRACE, FMAX>(p, vl, kL, kJ, kM, pol_first, pol_last, c);
   }
-  // block reduction → one atomic per counter per CTA
-  __shared__ u64 red[12][BLOCK / 32];
-  u64 vals[12] = {c.packets, c.edges, c.msgs, c.changed, c.pending, c.events, c.suspects, c.hash, c.kL, c.kJ, c.kM, 0};
+  // block reduction (warp shuffles, then shared memory) → one atomic per counter per CTA.
+  // trace row: 0 packets, 1 edge_updates, 2 messages, 3 changed, 4 pending, (5 events, 6 suspects: direct), 7 hash
+  __shared__ u64 red[8][BLOCK / 32];
+  const u64 vals[8] = {c.packets, c.edges, (u64)c.kL + c.kJ + c.kM, c.changed, c.pending, c.kL, c.kJ, c.kM};
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
-  for (int i = 0; i < 11; ++i) {
-    u64 s = (i == 7) ? warp_sum64(vals[i]) : (u64)warp_sum((u32)vals[i]);
+  for (int i = 0; i < 8; ++i) {
+    const u32 s = warp_sum((u32)vals[i]);
     if (lane == 0) red[i][wid] = s;
   }
+  u64 hs = 0;
+  if (TRACE) hs = warp_sum64(c.hash);
   __syncthreads();
-  if (threadIdx.x < 11) {
+  if (threadIdx.x < 8) {
     u64 s = 0;
 #pragma unroll
     for (int w = 0; w < BLOCK / 32; ++w) s += red[threadIdx.x][w];
     if (s) {
-      if (threadIdx.x < 8) atomicAdd((unsigned long long*)(p.row + threadIdx.x), (unsigned long long)s);
-      else atomicAdd(p.kinds_cur + (threadIdx.x - 8), (u32)min(s, (u64)0xffffffffu));
+      if (threadIdx.x < 5) atomicAdd((unsigned long long*)(p.row + threadIdx.x), (unsigned long long)s);
+      else atomicAdd(p.kinds_cur + (threadIdx.x - 5), (u32)min(s, (u64)0xffffffffu));
     }
   }
+  if (TRACE && lane == 0 && hs) atomicAdd((unsigned long long*)(p.row + 7), (unsigned long long)hs);
 }
 
 // Fold the cross-shard window (filled by the peers during their tick kernel) into the inbox.
@@ -362,6 +436,7 @@ __global__ void __launch_bounds__(BLOCK) summary_kernel(const uint4* rec, const 
 
 }  // namespace
 
+static int tick_min_blocks();
 int tick_grid_size(u32 n_local) {
   static int sms = 0;
   if (!sms) {
@@ -371,13 +446,24 @@ int tick_grid_size(u32 n_local) {
     if (sms <= 0) sms = 148;
   }
   const int tiles = (int)((n_local + BLOCK - 1) / BLOCK);
-  const int cap = sms * 8;                       // persistent: a multiple of the SM count (148 × 8 resident CTAs of 256)
+  const int cap = sms * tick_min_blocks() * 2;   // persistent: a multiple of SM count × resident CTAs (two waves for balance)
   return tiles < cap ? (tiles > 0 ? tiles : 1) : cap;
 }
 
+template <int FMAX, int MB>
+static void launch_tick_v(const TickParams& p, bool trace, int grid, cudaStream_t st) {
+  if (trace) tick_kernel<true, FMAX, MB><<<grid, BLOCK, 0, st>>>(p);
+  else tick_kernel<false, FMAX, MB><<<grid, BLOCK, 0, st>>>(p);
+}
+static int tick_min_blocks() {            // resident CTAs per SM the kernel is compiled for (register budget 85 vs 64)
+  static int mb = 0;
+  if (!mb) { const char* e = getenv("SERFSIM_MINB"); mb = (e && atoi(e) == 3) ? 3 : 4; }
+  return mb;
+}
 void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st) {
-  if (trace) tick_kernel<true><<<grid, BLOCK, 0, st>>>(p);
-  else tick_kernel<false><<<grid, BLOCK, 0, st>>>(p);
+  const bool small = p.fanout <= 4;          // the common fan-outs (3, 4) get the 4-wide target array
+  if (tick_min_blocks() == 3) { if (small) launch_tick_v<4, 3>(p, trace, grid, st); else launch_tick_v<8, 3>(p, trace, grid, st); }
+  else { if (small) launch_tick_v<4, 4>(p, trace, grid, st); else launch_tick_v<8, 4>(p, trace, grid, st); }
 }
 void launch_drain(const DrainParams& p, cudaStream_t st) { drain_kernel<<<148 * 4, BLOCK, 0, st>>>(p); }
 void launch_init_state(uint4* rec, u64* node_state, u32 n_local, u32 R, u32 init_st, u32 init_clock, cudaStream_t st) {

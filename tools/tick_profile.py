@@ -32,7 +32,7 @@ for t in range(len(ms)):
     eu, ch = int(tr["edge_updates"][t]), int(tr["changed"][t])
     be = 4 + 32 / a.fanout + 32 + 32 * (ch / eu if eu else 0)
     rows.append({"tick": t, "edge_updates": eu, "changed": ch, "pending": int(tr["pending"][t]), "ms": float(ms[t]),
-                 "alg_GBps": eu * be / (ms[t] * 1e-3) / 1e9 if ms[t] > 0 else 0.0})
+                 "alg_GBps": float(eu * be / (ms[t] * 1e-3) / 1e9) if ms[t] > 0 else 0.0})
     print(f"tick {t:3d}  eu {eu:10d}  changed {ch:9d}  pending {int(tr['pending'][t]):9d}  {ms[t]*1e3:9.1f} us  {rows[-1]['alg_GBps']:8.1f} GB/s(alg)")
 tot = float(ms.sum())
 print(f"total {tot:.3f} ms kernel time, {st['edge_updates']} edge-updates, {st['edge_updates'] / tot / 1e6:.2f} G edge-updates/s (kernel time only), p_dirty {p_dirty:.4f}")
