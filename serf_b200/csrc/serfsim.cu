@@ -79,6 +79,8 @@ struct serfsim {
   uint4* d_rec = nullptr;          // [R][count] × 32 B
   u32* d_inbox[2] = {nullptr, nullptr};   // [3][R][count]
   u64* d_node = nullptr;           // [count]
+  u8* d_hot[2] = {nullptr, nullptr};      // [n_tiles] per tick parity
+  u32 n_tiles = 0;
   u32* d_rowptr = nullptr;         // [count+1]
   u32* d_col = nullptr;
   u32 *d_ev_node = nullptr, *d_ev_op = nullptr, *d_ev_slot = nullptr;
@@ -120,6 +122,9 @@ struct serfsim {
   serfsim_barrier_fn barrier = nullptr; serfsim_allreduce_u64_fn allreduce = nullptr; void* comm_user = nullptr;
   std::vector<void*> ipc_opened;
   bool tick_timing = false;
+  size_t l2_persist_max = 0, l2_window_max = 0;
+  bool l2_window = false;           // SERFSIM_L2_WINDOW=1: stream access-policy window over the inbox being written
+  bool no_skip = false;             // SERFSIM_NO_SKIP=1: process every tile every tick (A/B measurements)
   std::vector<cudaEvent_t> tick_ev;      // 2 per tick when tick_timing
 };
 
@@ -194,7 +199,7 @@ int launch_ticks(serfsim* h, u32 n) {
       const int s = slot_of(h, it->node);
       if (s >= 0) { if (it->op == SERFSIM_OP_FAIL) h->up_mask &= ~(1u << s); if (it->op == SERFSIM_OP_REJOIN) h->up_mask |= (1u << s); }
     }
-    if (ee > eb) { launch_mark_events(h->d_node, h->d_ev_node, eb, ee, h->first, h->count, h->stream); h->last_launches++; }
+    if (ee > eb) { launch_mark_events(h->d_node, h->d_hot[(t & 1) ^ 1], h->d_ev_node, eb, ee, h->first, h->count, h->stream); h->last_launches++; }
     TickParams p{};
     p.n_local = h->count; p.first = h->first; p.n_global = h->N; p.R = h->R;
     p.fanout = h->cfg.fanout; p.probe_every = h->cfg.probe_interval_ticks; p.tick = t;
@@ -209,11 +214,24 @@ int launch_ticks(serfsim* h, u32 n) {
     p.kinds_prev = (h->cfg.world_size > 1) ? h->d_ones : h->d_kinds + (size_t)t * 4;
     p.kinds_cur = h->d_kinds + ((size_t)t + 1) * 4;
     p.overflow = h->d_overflow;
+    p.hot_rd = h->d_hot[(t & 1) ^ 1]; p.hot_wr = h->d_hot[t & 1];
+    p.n_tiles = h->n_tiles; p.tiles_per_cta = (h->n_tiles + h->grid - 1) / h->grid;
+    p.force_all = (h->cfg.trace != 0) || (h->cfg.probe_interval_ticks && p.down_mask) || h->no_skip;
     p.world = (u32)h->cfg.world_size; p.rank = (u32)h->cfg.rank; p.shard_size = h->shard_size; p.win_cap = h->win_cap;
     p.win_data = h->d_peer_data[t & 1]; p.win_count = h->d_peer_count[t & 1];
     if (h->tick_timing) {
       while (h->tick_ev.size() < 2 * ((size_t)t + 1)) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->tick_ev.push_back(e); }
       CU(cudaEventRecord(h->tick_ev[2 * (size_t)t], h->stream));
+    }
+    if (h->l2_window && h->l2_window_max) {
+      cudaStreamAttrValue av{};
+      const size_t bytes = (size_t)3 * h->R * h->count * sizeof(u32);
+      av.accessPolicyWindow.base_ptr = h->d_inbox[t & 1];
+      av.accessPolicyWindow.num_bytes = std::min(bytes, h->l2_window_max);
+      av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)h->l2_persist_max / (double)std::max<size_t>(1, av.accessPolicyWindow.num_bytes));
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      CU(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av));
     }
     launch_tick(p, h->cfg.trace != 0, h->grid, h->stream);
     if (h->tick_timing) CU(cudaEventRecord(h->tick_ev[2 * (size_t)t + 1], h->stream));
@@ -224,7 +242,7 @@ int launch_ticks(serfsim* h, u32 n) {
       h->barrier(h->comm_user);
       DrainParams d{};
       d.n_local = h->count; d.R = h->R; d.world = (u32)h->cfg.world_size; d.rank = (u32)h->cfg.rank; d.win_cap = h->win_cap;
-      d.win_data = h->d_win_data[t & 1]; d.win_count = h->d_win_count[t & 1]; d.inbox_wr = h->d_inbox[t & 1]; d.overflow = h->d_overflow;
+      d.win_data = h->d_win_data[t & 1]; d.win_count = h->d_win_count[t & 1]; d.inbox_wr = h->d_inbox[t & 1]; d.hot_wr = h->d_hot[t & 1]; d.overflow = h->d_overflow;
       launch_drain(d, h->stream);
       CU(cudaMemsetAsync(h->d_win_count[t & 1], 0, sizeof(u32) * h->cfg.world_size, h->stream));
       h->last_launches++;
@@ -298,6 +316,8 @@ int do_reset(serfsim* h, u64 seed) {
   CU(cudaMemsetAsync(h->d_inbox[0], 0, inbox_bytes, h->stream));
   CU(cudaMemsetAsync(h->d_inbox[1], 0, inbox_bytes, h->stream));
   CU(cudaMemsetAsync(h->d_overflow, 0, 4, h->stream));
+  CU(cudaMemsetAsync(h->d_hot[0], 0, h->n_tiles, h->stream));
+  CU(cudaMemsetAsync(h->d_hot[1], 0, h->n_tiles, h->stream));
   if (h->d_trace) {
     CU(cudaMemsetAsync(h->d_trace, 0, (size_t)h->trace_cap * 8 * sizeof(u64), h->stream));
     CU(cudaMemsetAsync(h->d_kinds, 0, ((size_t)h->trace_cap + 1) * 4 * sizeof(u32), h->stream));
@@ -311,6 +331,7 @@ int do_reset(serfsim* h, u64 seed) {
 void free_all(serfsim* h) {
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   for (cudaEvent_t e : h->tick_ev) cudaEventDestroy(e);
+  cudaFree(h->d_hot[0]); cudaFree(h->d_hot[1]);
   cudaFree(h->d_rec); cudaFree(h->d_inbox[0]); cudaFree(h->d_inbox[1]); cudaFree(h->d_node); cudaFree(h->d_rowptr); cudaFree(h->d_col);
   cudaFree(h->d_ev_node); cudaFree(h->d_ev_op); cudaFree(h->d_ev_slot); cudaFree(h->d_trace); cudaFree(h->d_kinds); cudaFree(h->d_ones);
   cudaFree(h->d_overflow); cudaFree(h->d_subj); cudaFree(h->d_scratch); cudaFree(h->d_stage);
@@ -394,13 +415,28 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
   CUB(cudaMalloc(&h->d_rec, (size_t)h->R * h->count * 32));
   CUB(cudaMalloc(&h->d_inbox[0], inbox_bytes)); CUB(cudaMalloc(&h->d_inbox[1], inbox_bytes));
   CUB(cudaMalloc(&h->d_node, (size_t)h->count * 8));
+  h->n_tiles = (h->count + 255) / 256;
+  CUB(cudaMalloc(&h->d_hot[0], h->n_tiles)); CUB(cudaMalloc(&h->d_hot[1], h->n_tiles));
   CUB(cudaMalloc(&h->d_overflow, 4)); CUB(cudaMalloc(&h->d_subj, MAX_SLOTS * 4)); CUB(cudaMalloc(&h->d_scratch, 64 * 8));
   CUB(cudaMalloc(&h->d_stage, (size_t)h->count * 8));
   CUB(cudaMalloc(&h->d_ones, 16));
-  const u32 ones[4] = {1, 1, 1, 1};
+  const u32 ones[4] = {0x40000000u, 0x40000000u, 0x40000000u, 1u};   // multi-GPU: every inbox plane may hold entries, every tick is dense
   CUB(cudaMemcpy(h->d_ones, ones, 16, cudaMemcpyHostToDevice));
   CUB(cudaMemcpy(h->d_subj, h->subj.data(), h->R * 4, cudaMemcpyHostToDevice));
   h->grid = tick_grid_size(h->count);
+  {
+    // L2 set-aside for persisting (evict_last) lines: the randomly addressed inbox planes live there
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    h->l2_persist_max = (size_t)max_persist; h->l2_window_max = (size_t)max_window;
+    int want = 0;        // measured: a 79 MB persisting carve-out makes the plateau tick 35 % slower (profiles/r1_notes.md)
+    if (const char* e = getenv("SERFSIM_L2_PERSIST")) want = atoi(e);
+    if (want && max_persist > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+    if (const char* e = getenv("SERFSIM_L2_WINDOW")) h->l2_window = atoi(e) != 0;
+    if (getenv("SERFSIM_VERBOSE")) fprintf(stderr, "serfsim: L2 persisting max %d B, window max %d B, persist %d window %d\n", max_persist, max_window, want, (int)h->l2_window);
+  }
+  if (const char* e = getenv("SERFSIM_NO_SKIP")) h->no_skip = atoi(e) != 0;
   if (cfg->world_size > 1) {
     // receive windows: expected cross-shard entries per tick ≈ count · fanout · R · 3 / world per peer; SERFSIM_WIN_FACTOR scales it
     double factor = 1.5;

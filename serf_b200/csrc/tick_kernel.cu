@@ -26,6 +26,9 @@ namespace sfs {
 namespace {
 
 constexpr int BLOCK = 256;
+constexpr u32 TILE_SHIFT = 8;              // one tile = one CTA pass = 256 nodes
+constexpr u32 MAX_TILES_PER_CTA = 1024;
+static_assert((1u << TILE_SHIFT) == BLOCK, "tile = block");
 
 // ---- cache-policy plumbing -------------------------------------------------------------------
 // The only randomly addressed data of a tick are the inbox planes the sends reduce into (RED.MAX,
@@ -81,11 +84,14 @@ __device__ __forceinline__ u64 warp_sum64(u64 v) {
 }
 
 // Deliver one entry to `dst` (global id): local → RED.MAX into this shard's inbox plane `plane`
-// (= inbox_wr + (kind·R + slot)·n_local); cross-shard → append to the peer's receive window over NVLink.
-__device__ __forceinline__ void deliver(const TickParams& p, u32* plane, u32 dst, u32 kind, u32 s, u32 val1, u64 pol_last) {
+// (= inbox_wr + (kind·R + slot)·n_local) and mark the destination tile hot for the next tick;
+// cross-shard → append to the peer's receive window over NVLink.
+template <bool SHARDED>
+__device__ __forceinline__ void deliver(const TickParams& p, u32* plane, u32 dst, u32 kind, u32 s, u32 val1, u64 pol_last, bool mark) {
   const u32 dl = dst - p.first;
-  if (dl < p.n_local) {
+  if (!SHARDED || dl < p.n_local) {
     red_max_resident(plane + dl, val1, pol_last);
+    if (mark) p.hot_wr[dl >> TILE_SHIFT] = 1;  // sparse ticks only: tell the next tick which tiles received something
   } else {
     const u32 shard = dst / p.shard_size;
     const u32 dloc = dst - shard * p.shard_size;
@@ -113,26 +119,73 @@ __device__ __forceinline__ bool differs(const Words& a, const Words& b) {
   return ((a.w[0] ^ b.w[0]) | (a.w[1] ^ b.w[1]) | (a.w[2] ^ b.w[2]) | (a.w[3] ^ b.w[3]) | (a.w[4] ^ b.w[4]) | (a.w[5] ^ b.w[5]) | (a.w[6] ^ b.w[6]) | (a.w[7] ^ b.w[7])) != 0;
 }
 
-template <bool TRACE, int FMAX>
-__device__ __forceinline__ void process_node(const TickParams& p, u32 vl, bool kL, bool kJ, bool kM, u64 pol_first, u64 pol_last, Counters& c) {
+// Gossip peers of one node for one tick — memberlist kRandomNodes: up to 3·deg draws for `fanout`
+// distinct neighbours other than the node itself; draw i uses word i&3 of Philox block i>>2.
+// Unfilled entries stay NO_TARGET, so the duplicate test needs no count.
+constexpr u32 NO_TARGET = 0xffffffffu;
+template <int FMAX>
+__device__ __forceinline__ u32 pick_targets(const TickParams& p, u32 v, u32 row0, u32 deg, u32 (&tg)[FMAX]) {
+#pragma unroll
+  for (int j = 0; j < FMAX; ++j) tg[j] = NO_TARGET;
+  u32 nt = 0;
+  const u32 tries = 3 * deg, fan = p.fanout;
+  for (u32 blk = 0; blk * 4 < tries && nt < fan; ++blk) {
+    u32 w[4];
+    philox4x32_10(p.tick, v, blk, DOMAIN_GOSSIP, p.seed_lo, p.seed_hi, w);
+    u32 cand[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cand[q] = __ldg(p.col + row0 + mulhi32(w[q], deg));     // four independent gathers in flight
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (blk * 4 + q < tries && nt < fan) {
+        const u32 cnd = cand[q];
+        bool dup = (cnd == v);
+#pragma unroll
+        for (int j = 0; j < FMAX; ++j) dup |= (tg[j] == cnd);
+        if (!dup) {
+#pragma unroll
+          for (int j = 0; j < FMAX; ++j) tg[j] = ((u32)j == nt) ? cnd : tg[j];
+          ++nt;
+        }
+      }
+    }
+  }
+  return nt;
+}
+
+// Returns true when the node still holds pending work (keeps its tile hot for the next tick).
+template <bool TRACE, int FMAX, bool SHARDED, bool R1>
+__device__ __forceinline__ bool process_node(const TickParams& p, const u32 vl, const bool kL, const bool kJ, const bool kM, const bool mark,
+                                             const u64 pol_first, const u64 pol_last, Counters& c) {
   const u32 v = p.first + vl;
   const u32 t = p.tick;
   const u32 limit = p.rules.limit;
   const u32 nl = p.n_local;
+  const u32 R = R1 ? 1u : p.R;
 
-  // ---- front-loaded, independent loads: node word, CSR row bounds, slot-0 record and inbox words ----
+  // ---- front-loaded, independent loads: node word, slot-0 record and inbox words ----
   const u64 ns = ld_u64_stream(p.node_state + vl, pol_first);
-  const u32 row0 = __ldg(p.row_ptr + vl), row1 = __ldg(p.row_ptr + vl + 1);
   Words cur = ld_rec256(p.rec + 2 * (size_t)vl, pol_first);
   u32 mL = 0, mJ = 0, mM = 0;
-  if (kL) mL = ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * p.R) * nl + vl, pol_first);
-  if (kJ) mJ = ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * p.R) * nl + vl, pol_first);
-  if (kM) mM = ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * p.R) * nl + vl, pol_first);
+  if (kL) mL = ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R) * nl + vl, pol_first);
+  if (kJ) mJ = ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R) * nl + vl, pol_first);
+  if (kM) mM = ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R) * nl + vl, pol_first);
+
+  // ---- idle fast exit (single-slot runs): nothing received, nothing queued, no timer, no operation ----
+  if (R1 && !(mL | mJ | mM) && !(ns & NS_EV) && ((cur.w[6] >> 16) | (cur.w[7] & 0xff)) == 0 && ((cur.w[6] >> 8) & 3) != ML_SUSPECT &&
+      !(p.probe_every && p.down_mask)) {
+    if (TRACE) {
+      c.hash += rec_hash((u64)v, make_uint4(cur.w[0], cur.w[1], cur.w[2], cur.w[3]), make_uint4(cur.w[4], cur.w[5], cur.w[6], cur.w[7]));
+      c.hash += node_hash((u64)p.n_global + v, ns);
+    }
+    return false;
+  }
 
   u32 clock = (u32)ns;
   const bool up_r = (ns & NS_UP) != 0;
   u32 sstate = (u32)(ns >> 40) & 3;
-  const u32 deg = row1 - row0;
+  const u32 row0 = __ldg(p.row_ptr + vl);
+  const u32 deg = __ldg(p.row_ptr + vl + 1) - row0;
 
   // host operation for this node (at most one per tick; the mark kernel set NS_EV)
   u32 op = 0, op_slot = 0;
@@ -155,22 +208,24 @@ __device__ __forceinline__ void process_node(const TickParams& p, u32 vl, bool k
     have_probe = true;
   }
 
-  u32 targets[FMAX];
+  u32 tg[FMAX];
   u32 nt = 0;
   bool have_targets = false;
   u32 max_tx = 0;
+  bool any_pending = false;
 
-  for (u32 s = 0; s < p.R; ++s) {
+#pragma unroll 1
+  for (u32 s = 0; s < R; ++s) {
     const size_t idx = (size_t)s * nl + vl;
-    if (s) {                                               // slots > 0: load at the top of the iteration
+    if (!R1 && s) {                                        // slots > 0: load at the top of the iteration
       cur = ld_rec256(p.rec + 2 * idx, pol_first);
-      mL = kL ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * p.R + s) * nl + vl, pol_first) : 0;
-      mJ = kJ ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * p.R + s) * nl + vl, pol_first) : 0;
-      mM = kM ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * p.R + s) * nl + vl, pol_first) : 0;
+      mL = kL ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R + s) * nl + vl, pol_first) : 0;
+      mJ = kJ ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R + s) * nl + vl, pol_first) : 0;
+      mM = kM ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R + s) * nl + vl, pol_first) : 0;
     }
-    if (mL) st_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * p.R + s) * nl + vl, 0u, pol_first);   // consume: clear for reuse in two ticks
-    if (mJ) st_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * p.R + s) * nl + vl, 0u, pol_first);
-    if (mM) st_u32_stream(p.inbox_rd + (size_t)(KIND_ML * p.R + s) * nl + vl, 0u, pol_first);
+    if (mL) st_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R + s) * nl + vl, 0u, pol_first);   // consume: clear for reuse in two ticks
+    if (mJ) st_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R + s) * nl + vl, 0u, pol_first);
+    if (mM) st_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R + s) * nl + vl, 0u, pol_first);
     const Words orig = cur;
     Rec r;
     unpack_words(cur, r);
@@ -235,39 +290,18 @@ __device__ __forceinline__ void process_node(const TickParams& p, u32 vl, bool k
       // ---------------- Phase S ----------------
       const u32 mx = max(r.txl, max(r.txj, r.txm));
       if (mx) {
-        if (!have_targets) {
-          // kRandomNodes: up to 3·deg draws for `fanout` distinct peers other than ourselves
-          u32 w[4] = {0, 0, 0, 0};
-          const u32 tries = 3 * deg;
-          for (u32 i = 0; i < tries && nt < p.fanout; ++i) {
-            if ((i & 3) == 0) philox4x32_10(t, v, i >> 2, DOMAIN_GOSSIP, p.seed_lo, p.seed_hi, w);
-            const u32 wi = (i & 3) == 0 ? w[0] : (i & 3) == 1 ? w[1] : (i & 3) == 2 ? w[2] : w[3];
-            const u32 cnd = __ldg(p.col + row0 + mulhi32(wi, deg));
-            bool skip = (cnd == v);
-#pragma unroll
-            for (int j = 0; j < FMAX; ++j) skip |= ((u32)j < nt && targets[j] == cnd);
-            if (!skip) {
-#pragma unroll
-              for (int j = 0; j < FMAX; ++j) if ((u32)j == nt) targets[j] = cnd;
-              ++nt;
-            }
-          }
-          have_targets = true;
-        }
-        u32* const planeL = p.inbox_wr + (size_t)(KIND_LEAVE * p.R + s) * nl;
-        u32* const planeJ = p.inbox_wr + (size_t)(KIND_JOIN * p.R + s) * nl;
-        u32* const planeM = p.inbox_wr + (size_t)(KIND_ML * p.R + s) * nl;
+        if (!have_targets) { nt = pick_targets<FMAX>(p, v, row0, deg, tg); have_targets = true; }
+        u32* const planeL = p.inbox_wr + (size_t)(KIND_LEAVE * R + s) * nl;
+        u32* const planeJ = p.inbox_wr + (size_t)(KIND_JOIN * R + s) * nl;
+        u32* const planeM = p.inbox_wr + (size_t)(KIND_ML * R + s) * nl;
         const u32 vL = r.qleave + 1, vJ = r.qjoin + 1, vM = ml_key(r) + 1;
+        const u32 sL = min(r.txl, nt), sJ = min(r.txj, nt), sM = min(r.txm, nt);     // entry e goes to targets 0 .. min(tx_e, nt)-1
 #pragma unroll
         for (int k = 0; k < FMAX; ++k) {
-          if ((u32)k < nt) {
-            const u32 dst = targets[k];
-            if (r.txl > (u32)k) deliver(p, planeL, dst, KIND_LEAVE, s, vL, pol_last);
-            if (r.txj > (u32)k) deliver(p, planeJ, dst, KIND_JOIN, s, vJ, pol_last);
-            if (r.txm > (u32)k) deliver(p, planeM, dst, KIND_ML, s, vM, pol_last);
-          }
+          if ((u32)k < sL) deliver<SHARDED>(p, planeL, tg[k], KIND_LEAVE, s, vL, pol_last, mark);
+          if ((u32)k < sJ) deliver<SHARDED>(p, planeJ, tg[k], KIND_JOIN, s, vJ, pol_last, mark);
+          if ((u32)k < sM) deliver<SHARDED>(p, planeM, tg[k], KIND_ML, s, vM, pol_last, mark);
         }
-        const u32 sL = min(r.txl, nt), sJ = min(r.txj, nt), sM = min(r.txm, nt);
         c.kL += sL; c.kJ += sJ; c.kM += sM;
         c.edges += min(mx, nt);
         max_tx = max(max_tx, mx);
@@ -280,36 +314,61 @@ __device__ __forceinline__ void process_node(const TickParams& p, u32 vl, bool k
       const bool pend = (r.txl | r.txj | r.txm) || r.mlstate == ML_SUSPECT ||
                         (p.probe_every && ((p.down_mask >> s) & 1) && !self && r.mlstate == ML_ALIVE);
       c.pending += pend ? 1 : 0;
+      any_pending |= pend;
     }
     pack_words(r, cur);
     if (differs(cur, orig)) st_rec256(p.rec + 2 * idx, cur, pol_first);
-    if (TRACE) {
-      const uint4 a2 = make_uint4(cur.w[0], cur.w[1], cur.w[2], cur.w[3]), b2 = make_uint4(cur.w[4], cur.w[5], cur.w[6], cur.w[7]);
-      c.hash += rec_hash((u64)s * p.n_global + v, a2, b2);
-    }
+    if (TRACE) c.hash += rec_hash((u64)s * p.n_global + v, make_uint4(cur.w[0], cur.w[1], cur.w[2], cur.w[3]), make_uint4(cur.w[4], cur.w[5], cur.w[6], cur.w[7]));
     if (r.inc >= INC_LIMIT) *p.overflow = 1;
   }
   const u64 ns2 = (u64)clock | (up_s ? NS_UP : 0) | ((u64)sstate << 40);
   if (ns2 != ns) st_u64_stream(p.node_state + vl, ns2, pol_first);
-  if (TRACE) c.hash += node_hash((u64)p.R * p.n_global + v, ns2);
+  if (TRACE) c.hash += node_hash((u64)R * p.n_global + v, ns2);
   if (clock >= LTIME_LIMIT) *p.overflow = 1;
   c.packets += min(nt, max_tx);
+  return any_pending;
 }
 
-template <bool TRACE, int FMAX, int MB>
-__global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__ TickParams p) {
+// Persistent CTAs; each owns a contiguous range of 256-node tiles.  A tile is processed only if it is
+// "hot": somebody delivered into it during the previous tick, it kept pending work (queued transmits,
+// suspicion timers), or a host operation targets it — otherwise not a single byte of it is touched.
+template <bool TRACE, int FMAX, bool SHARDED, bool R1>
+__global__ void __launch_bounds__(BLOCK, 4) tick_kernel(const __grid_constant__ TickParams p) {
+  __shared__ u8 hot_s[MAX_TILES_PER_CTA];
+  __shared__ u64 red[8][BLOCK / 32];
   Counters c = {};
   const bool kL = p.kinds_prev[KIND_LEAVE] != 0, kJ = p.kinds_prev[KIND_JOIN] != 0, kM = p.kinds_prev[KIND_ML] != 0;
   const u64 pol_first = policy_evict_first(), pol_last = policy_evict_last();
-  for (u32 base = blockIdx.x * BLOCK; base < p.n_local; base += gridDim.x * BLOCK) {
-    const u32 vl = base + threadIdx.x;
-    if (vl < p.n_local) process_node<TRACE, FMAX>(p, vl, kL, kJ, kM, pol_first, pol_last, c);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+  // Dense / sparse ticks.  While the gossip front is wide (the previous tick sent at least one message per
+  // two tiles) every tile will be hot anyway: senders skip the per-message tile marking and the next tick
+  // simply processes everything (kinds[3] of this tick's row records the decision).  In sparse ticks each
+  // delivery marks its destination tile, and tiles nobody touched are not read at all.
+  const u32 prev_msgs = p.kinds_prev[KIND_LEAVE] + p.kinds_prev[KIND_JOIN] + p.kinds_prev[KIND_ML];
+  const bool dense_now = prev_msgs >= (p.n_tiles >> 1) + 1;      // what this tick's sends will look like
+  const bool all_hot = p.force_all || p.kinds_prev[3] != 0;      // the previous tick was dense (or skipping is off)
+  const bool mark = !dense_now;
+  if (dense_now && blockIdx.x == 0 && threadIdx.x == 0) p.kinds_cur[3] = 1;
+
+  const u32 tile0 = blockIdx.x * p.tiles_per_cta;
+  const u32 ntile = tile0 < p.n_tiles ? min(p.tiles_per_cta, p.n_tiles - tile0) : 0;
+  for (u32 i = threadIdx.x; i < ntile; i += BLOCK) {
+    const u8 f = p.hot_rd[tile0 + i];
+    if (f) p.hot_rd[tile0 + i] = 0;                      // consumed; this parity is written again two ticks from now
+    hot_s[i] = (f || all_hot) ? 1 : 0;
+  }
+  __syncthreads();
+  for (u32 i = 0; i < ntile; ++i) {
+    if (!hot_s[i]) continue;
+    const u32 vl = ((tile0 + i) << TILE_SHIFT) + threadIdx.x;
+    bool pend = false;
+    if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, R1>(p, vl, kL, kJ, kM, mark, pol_first, pol_last, c);
+    if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + i] = 1;
   }
   // block reduction (warp shuffles, then shared memory) → one atomic per counter per CTA.
   // trace row: 0 packets, 1 edge_updates, 2 messages, 3 changed, 4 pending, (5 events, 6 suspects: direct), 7 hash
-  __shared__ u64 red[8][BLOCK / 32];
   const u64 vals[8] = {c.packets, c.edges, (u64)c.kL + c.kJ + c.kM, c.changed, c.pending, c.kL, c.kJ, c.kM};
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const u32 s = warp_sum((u32)vals[i]);
@@ -339,7 +398,10 @@ __global__ void __launch_bounds__(BLOCK) drain_kernel(const __grid_constant__ Dr
     for (u32 i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
       const u64 e = __ldcg(w + i);
       const u32 val1 = (u32)(e >> 32), s = (u32)(e >> 28) & 15, kind = (u32)(e >> 26) & 3, dl = (u32)e & ((1u << 26) - 1);
-      if (dl < p.n_local && s < p.R && kind < 3) atomicMax(p.inbox_wr + ((size_t)(kind * p.R + s)) * p.n_local + dl, val1);
+      if (dl < p.n_local && s < p.R && kind < 3) {
+        atomicMax(p.inbox_wr + ((size_t)(kind * p.R + s)) * p.n_local + dl, val1);
+        if (p.hot_wr[dl >> TILE_SHIFT] == 0) p.hot_wr[dl >> TILE_SHIFT] = 1;
+      }
       else *p.overflow = 3;
     }
   }
@@ -359,11 +421,14 @@ __global__ void init_state_kernel(uint4* rec, u64* node_state, u32 n_local, u32 
   node_state[vl] = (u64)init_clock | NS_UP;
 }
 
-__global__ void mark_events_kernel(u64* node_state, const u32* ev_node, u32 ev_begin, u32 ev_end, u32 first, u32 n_local) {
+__global__ void mark_events_kernel(u64* node_state, u8* hot_rd, const u32* ev_node, u32 ev_begin, u32 ev_end, u32 first, u32 n_local) {
   const u32 e = ev_begin + blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= ev_end) return;
   const u32 vl = ev_node[e] - first;
-  if (vl < n_local) node_state[vl] |= NS_EV;       // one op per (node, tick): no two threads touch the same word
+  if (vl < n_local) {
+    node_state[vl] |= NS_EV;                       // one op per (node, tick): no two threads touch the same word
+    hot_rd[vl >> TILE_SHIFT] = 1;                  // the tile must run this tick
+  }
 }
 
 __global__ void extract_kernel(const uint4* rec, const u64* node_state, u32 n_local, u32 slot, int what, void* out) {
@@ -436,7 +501,6 @@ __global__ void __launch_bounds__(BLOCK) summary_kernel(const uint4* rec, const 
 
 }  // namespace
 
-static int tick_min_blocks();
 int tick_grid_size(u32 n_local) {
   static int sms = 0;
   if (!sms) {
@@ -445,34 +509,32 @@ int tick_grid_size(u32 n_local) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
   }
-  const int tiles = (int)((n_local + BLOCK - 1) / BLOCK);
-  const int cap = sms * tick_min_blocks() * 2;   // persistent: a multiple of SM count × resident CTAs (two waves for balance)
-  return tiles < cap ? (tiles > 0 ? tiles : 1) : cap;
+  const u32 tiles = (n_local + BLOCK - 1) / BLOCK;
+  u32 grid = (u32)sms * 4 * 2;                   // persistent: SM count × 4 resident CTAs × 2 (two waves for balance)
+  if (tiles < grid) grid = tiles ? tiles : 1;
+  while ((tiles + grid - 1) / grid > MAX_TILES_PER_CTA) grid += (u32)sms * 4;
+  return (int)grid;
 }
 
-template <int FMAX, int MB>
-static void launch_tick_v(const TickParams& p, bool trace, int grid, cudaStream_t st) {
-  if (trace) tick_kernel<true, FMAX, MB><<<grid, BLOCK, 0, st>>>(p);
-  else tick_kernel<false, FMAX, MB><<<grid, BLOCK, 0, st>>>(p);
-}
-static int tick_min_blocks() {            // resident CTAs per SM the kernel is compiled for (register budget 85 vs 64)
-  static int mb = 0;
-  if (!mb) { const char* e = getenv("SERFSIM_MINB"); mb = (e && atoi(e) == 3) ? 3 : 4; }
-  return mb;
+template <bool TRACE, int FMAX>
+static void launch_tick_v(const TickParams& p, int grid, cudaStream_t st) {
+  const bool sharded = p.world > 1, r1 = p.R == 1;
+  if (sharded) { if (r1) tick_kernel<TRACE, FMAX, true, true><<<grid, BLOCK, 0, st>>>(p); else tick_kernel<TRACE, FMAX, true, false><<<grid, BLOCK, 0, st>>>(p); }
+  else { if (r1) tick_kernel<TRACE, FMAX, false, true><<<grid, BLOCK, 0, st>>>(p); else tick_kernel<TRACE, FMAX, false, false><<<grid, BLOCK, 0, st>>>(p); }
 }
 void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st) {
   const bool small = p.fanout <= 4;          // the common fan-outs (3, 4) get the 4-wide target array
-  if (tick_min_blocks() == 3) { if (small) launch_tick_v<4, 3>(p, trace, grid, st); else launch_tick_v<8, 3>(p, trace, grid, st); }
-  else { if (small) launch_tick_v<4, 4>(p, trace, grid, st); else launch_tick_v<8, 4>(p, trace, grid, st); }
+  if (trace) { if (small) launch_tick_v<true, 4>(p, grid, st); else launch_tick_v<true, 8>(p, grid, st); }
+  else { if (small) launch_tick_v<false, 4>(p, grid, st); else launch_tick_v<false, 8>(p, grid, st); }
 }
 void launch_drain(const DrainParams& p, cudaStream_t st) { drain_kernel<<<148 * 4, BLOCK, 0, st>>>(p); }
 void launch_init_state(uint4* rec, u64* node_state, u32 n_local, u32 R, u32 init_st, u32 init_clock, cudaStream_t st) {
   init_state_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(rec, node_state, n_local, R, init_st, init_clock);
 }
-void launch_mark_events(u64* node_state, const u32* ev_node, u32 ev_begin, u32 ev_end, u32 first, u32 n_local, cudaStream_t st) {
+void launch_mark_events(u64* node_state, u8* hot_rd, const u32* ev_node, u32 ev_begin, u32 ev_end, u32 first, u32 n_local, cudaStream_t st) {
   const u32 n = ev_end - ev_begin;
   if (!n) return;
-  mark_events_kernel<<<(n + 127) / 128, 128, 0, st>>>(node_state, ev_node, ev_begin, ev_end, first, n_local);
+  mark_events_kernel<<<(n + 127) / 128, 128, 0, st>>>(node_state, hot_rd, ev_node, ev_begin, ev_end, first, n_local);
 }
 void launch_extract(const uint4* rec, const u64* node_state, u32 n_local, u32 slot, int what, void* out, cudaStream_t st) {
   extract_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(rec, node_state, n_local, slot, what, out);

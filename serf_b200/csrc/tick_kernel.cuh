@@ -27,6 +27,9 @@ struct TickParams {
   const u32* kinds_prev;      // [4] messages of each kind sent in the previous tick (skip empty inbox planes)
   u32* kinds_cur;             // [4] same, for this tick
   u32* overflow;              // set when a Lamport time / incarnation nears the device width
+  u8* hot_rd;                 // [n_tiles] tile flags set during the previous tick (deliveries, pending work, host ops)
+  u8* hot_wr;                 // [n_tiles] tile flags for the next tick
+  u32 n_tiles, tiles_per_cta, force_all, pad0;
   // cross-shard exchange (world_size > 1): per-destination-shard message windows in peer memory
   u32 world, rank, shard_size, win_cap;
   u64* const* win_data;       // [world] peer window payloads for THIS tick parity (entry = dst_local | kind/slot<<.. , value)
@@ -38,13 +41,14 @@ struct DrainParams {
   const u64* win_data;        // my window: [world][win_cap]
   u32* win_count;             // [world]
   u32* inbox_wr;
+  u8* hot_wr;
   u32* overflow;
 };
 
 void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st);
 void launch_drain(const DrainParams& p, cudaStream_t st);
 void launch_init_state(uint4* rec, u64* node_state, u32 n_local, u32 R, u32 init_st, u32 init_clock, cudaStream_t st);
-void launch_mark_events(u64* node_state, const u32* ev_node, u32 ev_begin, u32 ev_end, u32 first, u32 n_local, cudaStream_t st);
+void launch_mark_events(u64* node_state, u8* hot_rd, const u32* ev_node, u32 ev_begin, u32 ev_end, u32 first, u32 n_local, cudaStream_t st);
 void launch_extract(const uint4* rec, const u64* node_state, u32 n_local, u32 slot, int what, void* out, cudaStream_t st);
 void launch_state_hash(const uint4* rec, const u64* node_state, u32 n_local, u32 first, u32 n_global, u32 R, u64* out, cudaStream_t st);
 void launch_summary(const uint4* rec, const u64* node_state, u32 n_local, u32 first, u32 R, const u32* subj_dev, u64* out /*[2 + 2*R + 2]*/, cudaStream_t st);
