@@ -74,6 +74,7 @@ std::vector<u32> suspicion_table(u32 susp_mult, u32 max_mult, u32 probe_ticks, u
 struct serfsim {
   serfsim_config_t cfg{};
   u32 N = 0, R = 0, first = 0, count = 0, shard_size = 0;
+  u32 stride = 0;                  // count rounded up to a whole 256-node tile: stride of every per-slot plane
   Rules rules{};
   // device state
   uint4* d_rec = nullptr;          // [R][count] × 32 B
@@ -101,6 +102,8 @@ struct serfsim {
   u32 up_mask = 0;
   u32 tick = 0;
   bool has_topo = false;
+  u32 stage_col_bytes = 0;         // 0: direct-load kernel; else bytes of CSR per TMA stage
+  u32 max_tile_edges = 0;          // largest 16-byte-aligned CSR span of one 256-node tile (sizes the TMA stage)
   std::vector<serfsim_tick_row_t> rows;   // rows pulled from the device so far
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -215,7 +218,8 @@ int launch_ticks(serfsim* h, u32 n) {
     p.kinds_cur = h->d_kinds + ((size_t)t + 1) * 4;
     p.overflow = h->d_overflow;
     p.hot_rd = h->d_hot[(t & 1) ^ 1]; p.hot_wr = h->d_hot[t & 1];
-    p.n_tiles = h->n_tiles; p.tiles_per_cta = (h->n_tiles + h->grid - 1) / h->grid;
+    p.stage_col_bytes = h->stage_col_bytes;
+    p.stride = h->stride; p.n_tiles = h->n_tiles; p.tiles_per_cta = (h->n_tiles + h->grid - 1) / h->grid;
     p.force_all = (h->cfg.trace != 0) || (h->cfg.probe_interval_ticks && p.down_mask) || h->no_skip;
     p.world = (u32)h->cfg.world_size; p.rank = (u32)h->cfg.rank; p.shard_size = h->shard_size; p.win_cap = h->win_cap;
     p.win_data = h->d_peer_data[t & 1]; p.win_count = h->d_peer_count[t & 1];
@@ -225,7 +229,7 @@ int launch_ticks(serfsim* h, u32 n) {
     }
     if (h->l2_window && h->l2_window_max) {
       cudaStreamAttrValue av{};
-      const size_t bytes = (size_t)3 * h->R * h->count * sizeof(u32);
+      const size_t bytes = (size_t)3 * h->R * h->stride * sizeof(u32);
       av.accessPolicyWindow.base_ptr = h->d_inbox[t & 1];
       av.accessPolicyWindow.num_bytes = std::min(bytes, h->l2_window_max);
       av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)h->l2_persist_max / (double)std::max<size_t>(1, av.accessPolicyWindow.num_bytes));
@@ -241,7 +245,7 @@ int launch_ticks(serfsim* h, u32 n) {
       CU(cudaStreamSynchronize(h->stream));
       h->barrier(h->comm_user);
       DrainParams d{};
-      d.n_local = h->count; d.R = h->R; d.world = (u32)h->cfg.world_size; d.rank = (u32)h->cfg.rank; d.win_cap = h->win_cap;
+      d.n_local = h->count; d.stride = h->stride; d.R = h->R; d.world = (u32)h->cfg.world_size; d.rank = (u32)h->cfg.rank; d.win_cap = h->win_cap;
       d.win_data = h->d_win_data[t & 1]; d.win_count = h->d_win_count[t & 1]; d.inbox_wr = h->d_inbox[t & 1]; d.hot_wr = h->d_hot[t & 1]; d.overflow = h->d_overflow;
       launch_drain(d, h->stream);
       CU(cudaMemsetAsync(h->d_win_count[t & 1], 0, sizeof(u32) * h->cfg.world_size, h->stream));
@@ -290,7 +294,7 @@ int fire_events(serfsim* h) {
   std::vector<u64> init(nout, 0), out(nout);
   for (u32 s = 0; s < h->R; ++s) init[2 + 2 * s] = ~0ull;
   CU(cudaMemcpyAsync(h->d_scratch, init.data(), nout * 8, cudaMemcpyHostToDevice, h->stream));
-  launch_summary(h->d_rec, h->d_node, h->count, h->first, h->R, h->d_subj, h->d_scratch, h->stream);
+  launch_summary(h->d_rec, h->d_node, h->count, h->stride, h->first, h->R, h->d_subj, h->d_scratch, h->stream);
   CU(cudaMemcpyAsync(out.data(), h->d_scratch, nout * 8, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   for (u32 type = 0; type < 3; ++type) {
@@ -311,8 +315,8 @@ int do_reset(serfsim* h, u64 seed) {
   h->cfg.seed = seed; h->tick = 0; h->ops.clear(); h->ops_dirty = false; h->rows.clear();
   h->up_mask = (h->R >= 32) ? 0xffffffffu : ((1u << h->R) - 1);
   h->reported.assign(h->R, (u8)ST_ALIVE);
-  const size_t inbox_bytes = (size_t)3 * h->R * h->count * sizeof(u32);
-  launch_init_state(h->d_rec, h->d_node, h->count, h->R, h->cfg.init_status_ltime, h->cfg.init_clock, h->stream);
+  const size_t inbox_bytes = (size_t)3 * h->R * h->stride * sizeof(u32);
+  launch_init_state(h->d_rec, h->d_node, h->count, h->stride, h->R, h->cfg.init_status_ltime, h->cfg.init_clock, h->stream);
   CU(cudaMemsetAsync(h->d_inbox[0], 0, inbox_bytes, h->stream));
   CU(cudaMemsetAsync(h->d_inbox[1], 0, inbox_bytes, h->stream));
   CU(cudaMemsetAsync(h->d_overflow, 0, 4, h->stream));
@@ -344,7 +348,7 @@ void free_all(serfsim* h) {
 int getter(serfsim* h, u32 slot, int what, void* out, size_t elem) {
   if (!h || !out) return fail(SERFSIM_E_INVAL, "null argument");
   if (what != EXTRACT_CLOCK && slot >= h->R) return fail(SERFSIM_E_INVAL, "slot out of range");
-  launch_extract(h->d_rec, h->d_node, h->count, slot, what, h->d_stage, h->stream);
+  launch_extract(h->d_rec, h->d_node, h->count, h->stride, slot, what, h->d_stage, h->stream);
   CU(cudaMemcpyAsync(out, h->d_stage, (size_t)h->count * elem, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return 0;
@@ -411,10 +415,13 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
 #define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(fail(e_ == cudaErrorMemoryAllocation ? SERFSIM_E_NOMEM : SERFSIM_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); } while (0)
   CUB(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CUB(cudaEventCreate(&h->ev0)); CUB(cudaEventCreate(&h->ev1));
-  const size_t inbox_bytes = (size_t)3 * h->R * h->count * sizeof(u32);
-  CUB(cudaMalloc(&h->d_rec, (size_t)h->R * h->count * 32));
+  h->stride = ((h->count + 255) / 256) * 256;
+  const size_t inbox_bytes = (size_t)3 * h->R * h->stride * sizeof(u32);
+  CUB(cudaMalloc(&h->d_rec, (size_t)h->R * h->stride * 32));
+  CUB(cudaMemset(h->d_rec, 0, (size_t)h->R * h->stride * 32));
   CUB(cudaMalloc(&h->d_inbox[0], inbox_bytes)); CUB(cudaMalloc(&h->d_inbox[1], inbox_bytes));
-  CUB(cudaMalloc(&h->d_node, (size_t)h->count * 8));
+  CUB(cudaMalloc(&h->d_node, (size_t)h->stride * 8));
+  CUB(cudaMemset(h->d_node, 0, (size_t)h->stride * 8));
   h->n_tiles = (h->count + 255) / 256;
   CUB(cudaMalloc(&h->d_hot[0], h->n_tiles)); CUB(cudaMalloc(&h->d_hot[1], h->n_tiles));
   CUB(cudaMalloc(&h->d_overflow, 4)); CUB(cudaMalloc(&h->d_subj, MAX_SLOTS * 4)); CUB(cudaMalloc(&h->d_scratch, 64 * 8));
@@ -423,7 +430,7 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
   const u32 ones[4] = {0x40000000u, 0x40000000u, 0x40000000u, 1u};   // multi-GPU: every inbox plane may hold entries, every tick is dense
   CUB(cudaMemcpy(h->d_ones, ones, 16, cudaMemcpyHostToDevice));
   CUB(cudaMemcpy(h->d_subj, h->subj.data(), h->R * 4, cudaMemcpyHostToDevice));
-  h->grid = tick_grid_size(h->count);
+  h->grid = tick_grid_size(h->count, 4);
   {
     // L2 set-aside for persisting (evict_last) lines: the randomly addressed inbox planes live there
     int max_persist = 0, max_window = 0;
@@ -473,19 +480,35 @@ int serfsim_set_topology_csr(serfsim_t* h, const uint64_t* row_ptr, const uint32
   if (row_ptr[0] != 0) return fail(SERFSIM_E_INVAL, "row_ptr[0] must be 0");
   const u64 e0 = row_ptr[h->first], e1 = row_ptr[h->first + h->count];
   if (e1 < e0 || e1 - e0 >= 0xffffffffull) return fail(SERFSIM_E_INVAL, "shard has too many edges (u32 offsets)");
-  std::vector<u32> rp(h->count + 1);
+  std::vector<u32> rp((size_t)h->stride + 8);
   for (u32 i = 0; i <= h->count; ++i) {
     const u64 r = row_ptr[h->first + i];
     if (r < e0 || (i && r < row_ptr[h->first + i - 1])) return fail(SERFSIM_E_INVAL, "row_ptr not monotone");
     rp[i] = (u32)(r - e0);
   }
   const u64 ne = e1 - e0;
+  for (size_t i = h->count + 1; i < rp.size(); ++i) rp[i] = (u32)ne;      // padding rows: degree 0
+  h->max_tile_edges = 0;
+  for (u32 b = 0; b < h->count; b += 256) {
+    const u32 lo = rp[b] & ~3u, hi = (rp[std::min<u32>(b + 256, h->count)] + 3u) & ~3u;
+    h->max_tile_edges = std::max(h->max_tile_edges, hi - lo);
+  }
   for (u64 i = 0; i < ne; ++i) if (col_idx[e0 + i] >= h->N) return fail(SERFSIM_E_INVAL, "col_idx out of range");
   cudaFree(h->d_rowptr); cudaFree(h->d_col); h->d_rowptr = nullptr; h->d_col = nullptr;
-  CU(cudaMalloc(&h->d_rowptr, ((size_t)h->count + 1) * 4));
-  CU(cudaMalloc(&h->d_col, std::max<u64>(ne, 1) * 4));
-  CU(cudaMemcpy(h->d_rowptr, rp.data(), ((size_t)h->count + 1) * 4, cudaMemcpyHostToDevice));
+  CU(cudaMalloc(&h->d_rowptr, rp.size() * 4));
+  CU(cudaMalloc(&h->d_col, (ne + 8) * 4));
+  CU(cudaMemset(h->d_col, 0, (ne + 8) * 4));
+  CU(cudaMemcpy(h->d_rowptr, rp.data(), rp.size() * 4, cudaMemcpyHostToDevice));
   if (ne) CU(cudaMemcpy(h->d_col, col_idx + e0, ne * 4, cudaMemcpyHostToDevice));
+  // TMA pipeline (single-slot runs): a stage holds the largest tile's CSR span if that is at most 48 KB
+  h->stage_col_bytes = 0;
+  {
+    int use = 1;
+    if (const char* e = getenv("SERFSIM_TMA")) use = atoi(e);
+    const u32 need = std::max<u32>(h->max_tile_edges * 4u, 16u);
+    if (use && h->R == 1 && need <= 48u * 1024u) h->stage_col_bytes = (need + 127u) & ~127u;
+  }
+  h->grid = tick_grid_size(h->count, h->stage_col_bytes ? 3 : 4);
   h->has_topo = true;
   return 0;
 }
@@ -581,7 +604,7 @@ int serfsim_records(serfsim_t* h, uint32_t slot, void* out) {
   if (!h || !out) return fail(SERFSIM_E_INVAL, "null argument");
   if (slot >= h->R) return fail(SERFSIM_E_INVAL, "slot out of range");
   CU(cudaStreamSynchronize(h->stream));
-  CU(cudaMemcpy(out, (const char*)h->d_rec + (size_t)slot * h->count * 32, (size_t)h->count * 32, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(out, (const char*)h->d_rec + (size_t)slot * h->stride * 32, (size_t)h->count * 32, cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -598,7 +621,7 @@ int serfsim_tick_trace(serfsim_t* h, uint32_t first_tick, uint32_t n, serfsim_ti
 int serfsim_state_hash(serfsim_t* h, uint64_t* out) {
   if (!h || !out) return fail(SERFSIM_E_INVAL, "null argument");
   CU(cudaMemsetAsync(h->d_scratch, 0, 8, h->stream));
-  launch_state_hash(h->d_rec, h->d_node, h->count, h->first, h->N, h->R, h->d_scratch, h->stream);
+  launch_state_hash(h->d_rec, h->d_node, h->count, h->stride, h->first, h->N, h->R, h->d_scratch, h->stream);
   CU(cudaMemcpyAsync(out, h->d_scratch, 8, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   if (h->cfg.world_size > 1) h->allreduce(h->comm_user, out, 1);
@@ -622,7 +645,7 @@ int serfsim_stats(serfsim_t* h, serfsim_stats_t* o) {
   std::vector<u64> init(nout, 0), out(nout);
   for (u32 s = 0; s < h->R; ++s) init[2 + 2 * s] = ~0ull;
   CU(cudaMemcpyAsync(h->d_scratch, init.data(), nout * 8, cudaMemcpyHostToDevice, h->stream));
-  launch_summary(h->d_rec, h->d_node, h->count, h->first, h->R, h->d_subj, h->d_scratch, h->stream);
+  launch_summary(h->d_rec, h->d_node, h->count, h->stride, h->first, h->R, h->d_subj, h->d_scratch, h->stream);
   CU(cudaMemcpyAsync(out.data(), h->d_scratch, nout * 8, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   o->member_time = out[0]; o->intent_queue = out[1];

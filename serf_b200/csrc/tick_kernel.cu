@@ -67,6 +67,35 @@ __device__ __forceinline__ void red_max_resident(u32* ptr, u32 v, u64 pol) {   /
   asm volatile("red.relaxed.gpu.global.max.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(ptr), "r"(v), "l"(pol) : "memory");
 }
 
+
+// ---- TMA (bulk async copy) + mbarrier plumbing: stages a whole 256-node tile into shared memory ----
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(u64* bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+  u32 ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// global → shared bulk copy (UBLKCP); completion is signalled on `bar` as transaction bytes
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, u64* bar, u64 pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+
+// Shared-memory image of one tile (single-slot runs): everything the 256 nodes of the tile read this tick.
+constexpr u32 ST_REC = 0, ST_NODE = 8192, ST_INL = 10240, ST_INJ = 11264, ST_INM = 12288, ST_RP = 13312, ST_COL = 14400;
+constexpr u32 RP_BYTES = 1040;             // 260 row offsets (257 needed, rounded to 16 B)
+struct StageView {
+  const Words* rec; const u64* node; const u32* inL; const u32* inJ; const u32* inM; const u32* rowptr; const u32* col;
+  u32 col_base;                            // first CSR element held in `col`
+  bool col_staged;                         // false: the tile's CSR span exceeds the stage; gather from global memory
+};
+
 struct Counters {          // per-thread, reduced once per CTA; rare counters (events, suspects) go straight to the trace row
   u32 packets, edges, changed, pending, kL, kJ, kM;
   u64 hash;
@@ -123,8 +152,8 @@ __device__ __forceinline__ bool differs(const Words& a, const Words& b) {
 // distinct neighbours other than the node itself; draw i uses word i&3 of Philox block i>>2.
 // Unfilled entries stay NO_TARGET, so the duplicate test needs no count.
 constexpr u32 NO_TARGET = 0xffffffffu;
-template <int FMAX>
-__device__ __forceinline__ u32 pick_targets(const TickParams& p, u32 v, u32 row0, u32 deg, u32 (&tg)[FMAX]) {
+template <int FMAX, bool STAGED>
+__device__ __forceinline__ u32 pick_targets(const TickParams& p, const StageView& sv, u32 v, u32 row0, u32 deg, u32 (&tg)[FMAX]) {
 #pragma unroll
   for (int j = 0; j < FMAX; ++j) tg[j] = NO_TARGET;
   u32 nt = 0;
@@ -134,7 +163,10 @@ __device__ __forceinline__ u32 pick_targets(const TickParams& p, u32 v, u32 row0
     philox4x32_10(p.tick, v, blk, DOMAIN_GOSSIP, p.seed_lo, p.seed_hi, w);
     u32 cand[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) cand[q] = __ldg(p.col + row0 + mulhi32(w[q], deg));     // four independent gathers in flight
+    for (int q = 0; q < 4; ++q) {                                                         // four independent gathers in flight
+      const u32 e = row0 + mulhi32(w[q], deg);
+      cand[q] = (STAGED && sv.col_staged) ? sv.col[e - sv.col_base] : __ldg(p.col + e);
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       if (blk * 4 + q < tries && nt < fan) {
@@ -154,22 +186,30 @@ __device__ __forceinline__ u32 pick_targets(const TickParams& p, u32 v, u32 row0
 }
 
 // Returns true when the node still holds pending work (keeps its tile hot for the next tick).
-template <bool TRACE, int FMAX, bool SHARDED, bool R1>
-__device__ __forceinline__ bool process_node(const TickParams& p, const u32 vl, const bool kL, const bool kJ, const bool kM, const bool mark,
+template <bool TRACE, int FMAX, bool SHARDED, bool R1, bool STAGED>
+__device__ __forceinline__ bool process_node(const TickParams& p, const StageView& sv, const u32 vl, const bool kL, const bool kJ, const bool kM, const bool mark,
                                              const u64 pol_first, const u64 pol_last, Counters& c) {
+  static_assert(!STAGED || R1, "the staged path is the single-slot path");
+  const u32 lt = threadIdx.x;              // index inside the staged tile
   const u32 v = p.first + vl;
   const u32 t = p.tick;
   const u32 limit = p.rules.limit;
-  const u32 nl = p.n_local;
+  const u32 nl = p.stride;               // plane stride (n_local rounded up to a whole tile)
   const u32 R = R1 ? 1u : p.R;
 
   // ---- front-loaded, independent loads: node word, slot-0 record and inbox words ----
-  const u64 ns = ld_u64_stream(p.node_state + vl, pol_first);
-  Words cur = ld_rec256(p.rec + 2 * (size_t)vl, pol_first);
+  const u64 ns = STAGED ? sv.node[lt] : ld_u64_stream(p.node_state + vl, pol_first);
+  Words cur;
+  if (STAGED) {
+    const uint4 a = reinterpret_cast<const uint4*>(sv.rec + lt)[0], b = reinterpret_cast<const uint4*>(sv.rec + lt)[1];
+    cur.w[0] = a.x; cur.w[1] = a.y; cur.w[2] = a.z; cur.w[3] = a.w; cur.w[4] = b.x; cur.w[5] = b.y; cur.w[6] = b.z; cur.w[7] = b.w;
+  } else {
+    cur = ld_rec256(p.rec + 2 * (size_t)vl, pol_first);
+  }
   u32 mL = 0, mJ = 0, mM = 0;
-  if (kL) mL = ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R) * nl + vl, pol_first);
-  if (kJ) mJ = ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R) * nl + vl, pol_first);
-  if (kM) mM = ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R) * nl + vl, pol_first);
+  if (kL) mL = STAGED ? sv.inL[lt] : ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R) * nl + vl, pol_first);
+  if (kJ) mJ = STAGED ? sv.inJ[lt] : ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R) * nl + vl, pol_first);
+  if (kM) mM = STAGED ? sv.inM[lt] : ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R) * nl + vl, pol_first);
 
   // ---- idle fast exit (single-slot runs): nothing received, nothing queued, no timer, no operation ----
   if (R1 && !(mL | mJ | mM) && !(ns & NS_EV) && ((cur.w[6] >> 16) | (cur.w[7] & 0xff)) == 0 && ((cur.w[6] >> 8) & 3) != ML_SUSPECT &&
@@ -184,8 +224,8 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const u32 vl, 
   u32 clock = (u32)ns;
   const bool up_r = (ns & NS_UP) != 0;
   u32 sstate = (u32)(ns >> 40) & 3;
-  const u32 row0 = __ldg(p.row_ptr + vl);
-  const u32 deg = __ldg(p.row_ptr + vl + 1) - row0;
+  const u32 row0 = STAGED ? sv.rowptr[lt] : __ldg(p.row_ptr + vl);
+  const u32 deg = (STAGED ? sv.rowptr[lt + 1] : __ldg(p.row_ptr + vl + 1)) - row0;
 
   // host operation for this node (at most one per tick; the mark kernel set NS_EV)
   u32 op = 0, op_slot = 0;
@@ -204,7 +244,8 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const u32 vl, 
   if (up_s && p.probe_every && p.down_mask && ((t + v) % p.probe_every) == 0 && deg) {
     u32 w[4];
     philox4x32_10(t, v, 0, DOMAIN_PROBE, p.seed_lo, p.seed_hi, w);
-    ptarget = __ldg(p.col + row0 + mulhi32(w[0], deg));
+    const u32 e = row0 + mulhi32(w[0], deg);
+    ptarget = (STAGED && sv.col_staged) ? sv.col[e - sv.col_base] : __ldg(p.col + e);
     have_probe = true;
   }
 
@@ -290,7 +331,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const u32 vl, 
       // ---------------- Phase S ----------------
       const u32 mx = max(r.txl, max(r.txj, r.txm));
       if (mx) {
-        if (!have_targets) { nt = pick_targets<FMAX>(p, v, row0, deg, tg); have_targets = true; }
+        if (!have_targets) { nt = pick_targets<FMAX, STAGED>(p, sv, v, row0, deg, tg); have_targets = true; }
         u32* const planeL = p.inbox_wr + (size_t)(KIND_LEAVE * R + s) * nl;
         u32* const planeJ = p.inbox_wr + (size_t)(KIND_JOIN * R + s) * nl;
         u32* const planeM = p.inbox_wr + (size_t)(KIND_ML * R + s) * nl;
@@ -363,11 +404,117 @@ __global__ void __launch_bounds__(BLOCK, 4) tick_kernel(const __grid_constant__ 
     if (!hot_s[i]) continue;
     const u32 vl = ((tile0 + i) << TILE_SHIFT) + threadIdx.x;
     bool pend = false;
-    if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, R1>(p, vl, kL, kJ, kM, mark, pol_first, pol_last, c);
+    if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, vl, kL, kJ, kM, mark, pol_first, pol_last, c);
     if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + i] = 1;
   }
   // block reduction (warp shuffles, then shared memory) → one atomic per counter per CTA.
   // trace row: 0 packets, 1 edge_updates, 2 messages, 3 changed, 4 pending, (5 events, 6 suspects: direct), 7 hash
+  const u64 vals[8] = {c.packets, c.edges, (u64)c.kL + c.kJ + c.kM, c.changed, c.pending, c.kL, c.kJ, c.kM};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const u32 s = warp_sum((u32)vals[i]);
+    if (lane == 0) red[i][wid] = s;
+  }
+  u64 hs = 0;
+  if (TRACE) hs = warp_sum64(c.hash);
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    u64 s = 0;
+#pragma unroll
+    for (int w = 0; w < BLOCK / 32; ++w) s += red[threadIdx.x][w];
+    if (s) {
+      if (threadIdx.x < 5) atomicAdd((unsigned long long*)(p.row + threadIdx.x), (unsigned long long)s);
+      else atomicAdd(p.kinds_cur + (threadIdx.x - 5), (u32)min(s, (u64)0xffffffffu));
+    }
+  }
+  if (TRACE && lane == 0 && hs) atomicAdd((unsigned long long*)(p.row + 7), (unsigned long long)hs);
+}
+
+// The same tick for single-slot runs with the whole working set of a tile staged through TMA: one elected
+// thread bulk-copies the tile's records (8 KB), node words (2 KB), live inbox planes (1 KB each), row offsets
+// (1 KB) and CSR span (the tile's neighbour lists, 16 KB at out-degree 16) into shared memory, one tile ahead
+// of the 256 consumers (2 stages, mbarrier transaction counts).  The node logic then runs out of shared memory;
+// only the RED.MAX sends, the record write-back and the inbox clears touch global memory from the LSU.
+template <bool TRACE, int FMAX, bool SHARDED>
+__global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constant__ TickParams p) {
+  extern __shared__ __align__(128) unsigned char stage_mem[];
+  __shared__ u8 hot_s[MAX_TILES_PER_CTA];
+  __shared__ u16 hot_list[MAX_TILES_PER_CTA];
+  __shared__ u32 n_hot_s;
+  __shared__ u64 red[8][BLOCK / 32];
+  __shared__ __align__(8) u64 full_bar[2];
+  __shared__ u32 col_base_s[2], col_ok_s[2];
+  Counters c = {};
+  const bool kL = p.kinds_prev[KIND_LEAVE] != 0, kJ = p.kinds_prev[KIND_JOIN] != 0, kM = p.kinds_prev[KIND_ML] != 0;
+  const u64 pol_first = policy_evict_first(), pol_last = policy_evict_last();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+  const u32 prev_msgs = p.kinds_prev[KIND_LEAVE] + p.kinds_prev[KIND_JOIN] + p.kinds_prev[KIND_ML];
+  const bool dense_now = prev_msgs >= (p.n_tiles >> 1) + 1;
+  const bool all_hot = p.force_all || p.kinds_prev[3] != 0;
+  const bool mark = !dense_now;
+  if (dense_now && blockIdx.x == 0 && threadIdx.x == 0) p.kinds_cur[3] = 1;
+
+  const u32 tile0 = blockIdx.x * p.tiles_per_cta;
+  const u32 ntile = tile0 < p.n_tiles ? min(p.tiles_per_cta, p.n_tiles - tile0) : 0;
+  for (u32 i = threadIdx.x; i < ntile; i += BLOCK) {
+    const u8 f = p.hot_rd[tile0 + i];
+    if (f) p.hot_rd[tile0 + i] = 0;
+    hot_s[i] = (f || all_hot) ? 1 : 0;
+  }
+  if (threadIdx.x == 0) { mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1); fence_proxy_async(); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 n = 0;
+    for (u32 i = 0; i < ntile; ++i) if (hot_s[i]) hot_list[n++] = (u16)i;
+    n_hot_s = n;
+  }
+  __syncthreads();
+  const u32 n_hot = n_hot_s;
+  const u32 stage_bytes = ST_COL + p.stage_col_bytes;
+
+  // producer: bulk-copy tile `j` of the hot list into stage j&1
+  auto issue = [&](u32 j) {
+    const u32 st = j & 1;
+    unsigned char* base = stage_mem + (size_t)st * stage_bytes;
+    const u32 tile = tile0 + hot_list[j];
+    const u32 v0 = tile << TILE_SHIFT;
+    const u32 e0 = __ldg(p.row_ptr + v0) & ~3u;
+    const u32 e1 = (__ldg(p.row_ptr + min(v0 + BLOCK, p.n_local)) + 3u) & ~3u;
+    const u32 col_bytes = (e1 - e0) * 4u;
+    const bool col_ok = col_bytes != 0 && col_bytes <= p.stage_col_bytes;
+    col_base_s[st] = e0; col_ok_s[st] = col_ok ? 1u : 0u;
+    const u32 tx = 8192u + 2048u + RP_BYTES + (kL ? 1024u : 0u) + (kJ ? 1024u : 0u) + (kM ? 1024u : 0u) + (col_ok ? col_bytes : 0u);
+    fence_proxy_async();                                   // earlier generic reads of this stage precede the async writes
+    mbar_arrive_expect_tx(&full_bar[st], tx);
+    bulk_g2s(base + ST_REC, p.rec + 2 * (size_t)v0, 8192u, &full_bar[st], pol_first);
+    bulk_g2s(base + ST_NODE, p.node_state + v0, 2048u, &full_bar[st], pol_first);
+    bulk_g2s(base + ST_RP, p.row_ptr + v0, RP_BYTES, &full_bar[st], pol_first);
+    if (kL) bulk_g2s(base + ST_INL, p.inbox_rd + (size_t)KIND_LEAVE * p.stride + v0, 1024u, &full_bar[st], pol_first);
+    if (kJ) bulk_g2s(base + ST_INJ, p.inbox_rd + (size_t)KIND_JOIN * p.stride + v0, 1024u, &full_bar[st], pol_first);
+    if (kM) bulk_g2s(base + ST_INM, p.inbox_rd + (size_t)KIND_ML * p.stride + v0, 1024u, &full_bar[st], pol_first);
+    if (col_ok) bulk_g2s(base + ST_COL, p.col + e0, col_bytes, &full_bar[st], pol_first);
+  };
+
+  if (threadIdx.x == 0 && n_hot) issue(0);
+  for (u32 j = 0; j < n_hot; ++j) {
+    if (threadIdx.x == 0 && j + 1 < n_hot) issue(j + 1);   // stage (j+1)&1 was released by the barrier ending iteration j-1
+    const u32 st = j & 1;
+    mbar_wait(&full_bar[st], (j >> 1) & 1);
+    unsigned char* base = stage_mem + (size_t)st * stage_bytes;
+    StageView sv;
+    sv.rec = reinterpret_cast<const Words*>(base + ST_REC); sv.node = reinterpret_cast<const u64*>(base + ST_NODE);
+    sv.inL = reinterpret_cast<const u32*>(base + ST_INL); sv.inJ = reinterpret_cast<const u32*>(base + ST_INJ); sv.inM = reinterpret_cast<const u32*>(base + ST_INM);
+    sv.rowptr = reinterpret_cast<const u32*>(base + ST_RP); sv.col = reinterpret_cast<const u32*>(base + ST_COL);
+    sv.col_base = col_base_s[st]; sv.col_staged = col_ok_s[st] != 0;
+    const u32 ti = hot_list[j];
+    const u32 vl = ((tile0 + ti) << TILE_SHIFT) + threadIdx.x;
+    bool pend = false;
+    if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, true, true>(p, sv, vl, kL, kJ, kM, mark, pol_first, pol_last, c);
+    if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + ti] = 1;
+    __syncthreads();                                       // every thread is done with stage `st` before it is refilled
+  }
+
   const u64 vals[8] = {c.packets, c.edges, (u64)c.kL + c.kJ + c.kM, c.changed, c.pending, c.kL, c.kJ, c.kM};
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -399,7 +546,7 @@ __global__ void __launch_bounds__(BLOCK) drain_kernel(const __grid_constant__ Dr
       const u64 e = __ldcg(w + i);
       const u32 val1 = (u32)(e >> 32), s = (u32)(e >> 28) & 15, kind = (u32)(e >> 26) & 3, dl = (u32)e & ((1u << 26) - 1);
       if (dl < p.n_local && s < p.R && kind < 3) {
-        atomicMax(p.inbox_wr + ((size_t)(kind * p.R + s)) * p.n_local + dl, val1);
+        atomicMax(p.inbox_wr + ((size_t)(kind * p.R + s)) * p.stride + dl, val1);
         if (p.hot_wr[dl >> TILE_SHIFT] == 0) p.hot_wr[dl >> TILE_SHIFT] = 1;
       }
       else *p.overflow = 3;
@@ -407,7 +554,7 @@ __global__ void __launch_bounds__(BLOCK) drain_kernel(const __grid_constant__ Dr
   }
 }
 
-__global__ void init_state_kernel(uint4* rec, u64* node_state, u32 n_local, u32 R, u32 init_st, u32 init_clock) {
+__global__ void init_state_kernel(uint4* rec, u64* node_state, u32 n_local, u32 stride, u32 R, u32 init_st, u32 init_clock) {
   const u32 vl = blockIdx.x * blockDim.x + threadIdx.x;
   if (vl >= n_local) return;
   Rec r = {};
@@ -415,7 +562,7 @@ __global__ void init_state_kernel(uint4* rec, u64* node_state, u32 n_local, u32 
   uint4 a, b;
   pack(r, a, b);
   for (u32 s = 0; s < R; ++s) {
-    const size_t idx = (size_t)s * n_local + vl;
+    const size_t idx = (size_t)s * stride + vl;
     rec[2 * idx] = a; rec[2 * idx + 1] = b;
   }
   node_state[vl] = (u64)init_clock | NS_UP;
@@ -431,11 +578,11 @@ __global__ void mark_events_kernel(u64* node_state, u8* hot_rd, const u32* ev_no
   }
 }
 
-__global__ void extract_kernel(const uint4* rec, const u64* node_state, u32 n_local, u32 slot, int what, void* out) {
+__global__ void extract_kernel(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 slot, int what, void* out) {
   const u32 vl = blockIdx.x * blockDim.x + threadIdx.x;
   if (vl >= n_local) return;
   if (what == EXTRACT_CLOCK) { ((u64*)out)[vl] = node_state[vl] & 0xffffffffull; return; }
-  const size_t idx = (size_t)slot * n_local + vl;
+  const size_t idx = (size_t)slot * stride + vl;
   Rec r;
   unpack(rec[2 * idx], rec[2 * idx + 1], r);
   const bool known = r.flags & 1;
@@ -447,11 +594,11 @@ __global__ void extract_kernel(const uint4* rec, const u64* node_state, u32 n_lo
   }
 }
 
-__global__ void __launch_bounds__(BLOCK) state_hash_kernel(const uint4* rec, const u64* node_state, u32 n_local, u32 first, u32 n_global, u32 R, u64* out) {
+__global__ void __launch_bounds__(BLOCK) state_hash_kernel(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 n_global, u32 R, u64* out) {
   u64 h = 0;
   for (u32 vl = blockIdx.x * BLOCK + threadIdx.x; vl < n_local; vl += gridDim.x * BLOCK) {
     for (u32 s = 0; s < R; ++s) {
-      const size_t idx = (size_t)s * n_local + vl;
+      const size_t idx = (size_t)s * stride + vl;
       h += rec_hash((u64)s * n_global + first + vl, rec[2 * idx], rec[2 * idx + 1]);
     }
     h += node_hash((u64)R * n_global + first + vl, node_state[vl]);
@@ -462,7 +609,7 @@ __global__ void __launch_bounds__(BLOCK) state_hash_kernel(const uint4* rec, con
 
 // out[0] = max clock, out[1] = queued intents, out[2+2s] = min key, out[3+2s] = max key of slot s over
 // up nodes other than the subject (agreement check for Stats / convergence studies).
-__global__ void __launch_bounds__(BLOCK) summary_kernel(const uint4* rec, const u64* node_state, u32 n_local, u32 first, u32 R, const u32* subj, u64* out) {
+__global__ void __launch_bounds__(BLOCK) summary_kernel(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 R, const u32* subj, u64* out) {
   u64 maxclock = 0, queued = 0;
   for (u32 s = 0; s < R; ++s) {
     u64 kmin = ~0ull, kmax = 0;
@@ -470,7 +617,7 @@ __global__ void __launch_bounds__(BLOCK) summary_kernel(const uint4* rec, const 
     for (u32 vl = blockIdx.x * BLOCK + threadIdx.x; vl < n_local; vl += gridDim.x * BLOCK) {
       const u64 ns = node_state[vl];
       if (s == 0) maxclock = max(maxclock, (u64)(ns & 0xffffffffull));
-      const size_t idx = (size_t)s * n_local + vl;
+      const size_t idx = (size_t)s * stride + vl;
       Rec r;
       unpack(rec[2 * idx], rec[2 * idx + 1], r);
       queued += (r.txj ? 1 : 0) + (r.txl ? 1 : 0);
@@ -501,7 +648,7 @@ __global__ void __launch_bounds__(BLOCK) summary_kernel(const uint4* rec, const 
 
 }  // namespace
 
-int tick_grid_size(u32 n_local) {
+int tick_grid_size(u32 n_local, int ctas_per_sm) {
   static int sms = 0;
   if (!sms) {
     int dev = 0;
@@ -510,15 +657,30 @@ int tick_grid_size(u32 n_local) {
     if (sms <= 0) sms = 148;
   }
   const u32 tiles = (n_local + BLOCK - 1) / BLOCK;
-  u32 grid = (u32)sms * 4 * 2;                   // persistent: SM count × 4 resident CTAs × 2 (two waves for balance)
+  u32 grid = (u32)sms * (u32)ctas_per_sm * 2;    // persistent: SM count × resident CTAs × 2 (two waves for balance)
   if (tiles < grid) grid = tiles ? tiles : 1;
-  while ((tiles + grid - 1) / grid > MAX_TILES_PER_CTA) grid += (u32)sms * 4;
+  while ((tiles + grid - 1) / grid > MAX_TILES_PER_CTA) grid += (u32)sms * (u32)ctas_per_sm;
   return (int)grid;
+}
+
+template <bool TRACE, int FMAX, bool SHARDED>
+static void launch_tick_tma(const TickParams& p, int grid, cudaStream_t st) {
+  const size_t smem = 2 * (size_t)(ST_COL + p.stage_col_bytes);
+  static size_t configured = 0;
+  if (configured < smem) {
+    cudaFuncSetAttribute(tick_kernel_tma<TRACE, FMAX, SHARDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = 200 * 1024;
+  }
+  tick_kernel_tma<TRACE, FMAX, SHARDED><<<grid, BLOCK, smem, st>>>(p);
 }
 
 template <bool TRACE, int FMAX>
 static void launch_tick_v(const TickParams& p, int grid, cudaStream_t st) {
   const bool sharded = p.world > 1, r1 = p.R == 1;
+  if (r1 && p.stage_col_bytes) {             // single-slot run whose tiles fit a shared-memory stage: TMA pipeline
+    if (sharded) launch_tick_tma<TRACE, FMAX, true>(p, grid, st); else launch_tick_tma<TRACE, FMAX, false>(p, grid, st);
+    return;
+  }
   if (sharded) { if (r1) tick_kernel<TRACE, FMAX, true, true><<<grid, BLOCK, 0, st>>>(p); else tick_kernel<TRACE, FMAX, true, false><<<grid, BLOCK, 0, st>>>(p); }
   else { if (r1) tick_kernel<TRACE, FMAX, false, true><<<grid, BLOCK, 0, st>>>(p); else tick_kernel<TRACE, FMAX, false, false><<<grid, BLOCK, 0, st>>>(p); }
 }
@@ -528,22 +690,22 @@ void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st) {
   else { if (small) launch_tick_v<false, 4>(p, grid, st); else launch_tick_v<false, 8>(p, grid, st); }
 }
 void launch_drain(const DrainParams& p, cudaStream_t st) { drain_kernel<<<148 * 4, BLOCK, 0, st>>>(p); }
-void launch_init_state(uint4* rec, u64* node_state, u32 n_local, u32 R, u32 init_st, u32 init_clock, cudaStream_t st) {
-  init_state_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(rec, node_state, n_local, R, init_st, init_clock);
+void launch_init_state(uint4* rec, u64* node_state, u32 n_local, u32 stride, u32 R, u32 init_st, u32 init_clock, cudaStream_t st) {
+  init_state_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(rec, node_state, n_local, stride, R, init_st, init_clock);
 }
 void launch_mark_events(u64* node_state, u8* hot_rd, const u32* ev_node, u32 ev_begin, u32 ev_end, u32 first, u32 n_local, cudaStream_t st) {
   const u32 n = ev_end - ev_begin;
   if (!n) return;
   mark_events_kernel<<<(n + 127) / 128, 128, 0, st>>>(node_state, hot_rd, ev_node, ev_begin, ev_end, first, n_local);
 }
-void launch_extract(const uint4* rec, const u64* node_state, u32 n_local, u32 slot, int what, void* out, cudaStream_t st) {
-  extract_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(rec, node_state, n_local, slot, what, out);
+void launch_extract(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 slot, int what, void* out, cudaStream_t st) {
+  extract_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(rec, node_state, n_local, stride, slot, what, out);
 }
-void launch_state_hash(const uint4* rec, const u64* node_state, u32 n_local, u32 first, u32 n_global, u32 R, u64* out, cudaStream_t st) {
-  state_hash_kernel<<<148 * 4, BLOCK, 0, st>>>(rec, node_state, n_local, first, n_global, R, out);
+void launch_state_hash(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 n_global, u32 R, u64* out, cudaStream_t st) {
+  state_hash_kernel<<<148 * 4, BLOCK, 0, st>>>(rec, node_state, n_local, stride, first, n_global, R, out);
 }
-void launch_summary(const uint4* rec, const u64* node_state, u32 n_local, u32 first, u32 R, const u32* subj_dev, u64* out, cudaStream_t st) {
-  summary_kernel<<<148 * 4, BLOCK, 0, st>>>(rec, node_state, n_local, first, R, subj_dev, out);
+void launch_summary(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 R, const u32* subj_dev, u64* out, cudaStream_t st) {
+  summary_kernel<<<148 * 4, BLOCK, 0, st>>>(rec, node_state, n_local, stride, first, R, subj_dev, out);
 }
 
 }  // namespace sfs

@@ -29,7 +29,8 @@ struct TickParams {
   u32* overflow;              // set when a Lamport time / incarnation nears the device width
   u8* hot_rd;                 // [n_tiles] tile flags set during the previous tick (deliveries, pending work, host ops)
   u8* hot_wr;                 // [n_tiles] tile flags for the next tick
-  u32 n_tiles, tiles_per_cta, force_all, pad0;
+  u32 stage_col_bytes, pad1, pad2, pad3;             // > 0: single-slot TMA pipeline with this many bytes of CSR per stage
+  u32 n_tiles, tiles_per_cta, force_all, stride;   // stride: plane stride in nodes = n_local rounded up to a whole tile
   // cross-shard exchange (world_size > 1): per-destination-shard message windows in peer memory
   u32 world, rank, shard_size, win_cap;
   u64* const* win_data;       // [world] peer window payloads for THIS tick parity (entry = dst_local | kind/slot<<.. , value)
@@ -37,7 +38,7 @@ struct TickParams {
 };
 
 struct DrainParams {
-  u32 n_local, R, world, rank, win_cap;
+  u32 n_local, stride, R, world, rank, win_cap;
   const u64* win_data;        // my window: [world][win_cap]
   u32* win_count;             // [world]
   u32* inbox_wr;
@@ -47,12 +48,12 @@ struct DrainParams {
 
 void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st);
 void launch_drain(const DrainParams& p, cudaStream_t st);
-void launch_init_state(uint4* rec, u64* node_state, u32 n_local, u32 R, u32 init_st, u32 init_clock, cudaStream_t st);
+void launch_init_state(uint4* rec, u64* node_state, u32 n_local, u32 stride, u32 R, u32 init_st, u32 init_clock, cudaStream_t st);
 void launch_mark_events(u64* node_state, u8* hot_rd, const u32* ev_node, u32 ev_begin, u32 ev_end, u32 first, u32 n_local, cudaStream_t st);
-void launch_extract(const uint4* rec, const u64* node_state, u32 n_local, u32 slot, int what, void* out, cudaStream_t st);
-void launch_state_hash(const uint4* rec, const u64* node_state, u32 n_local, u32 first, u32 n_global, u32 R, u64* out, cudaStream_t st);
-void launch_summary(const uint4* rec, const u64* node_state, u32 n_local, u32 first, u32 R, const u32* subj_dev, u64* out /*[2 + 2*R + 2]*/, cudaStream_t st);
-int tick_grid_size(u32 n_local);
+void launch_extract(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 slot, int what, void* out, cudaStream_t st);
+void launch_state_hash(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 n_global, u32 R, u64* out, cudaStream_t st);
+void launch_summary(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 R, const u32* subj_dev, u64* out /*[2 + 2*R + 2]*/, cudaStream_t st);
+int tick_grid_size(u32 n_local, int ctas_per_sm);
 
 enum { EXTRACT_STATUS = 0, EXTRACT_STATUS_LTIME = 1, EXTRACT_CLOCK = 2, EXTRACT_INC = 3, EXTRACT_ML = 4 };
 
