@@ -575,17 +575,28 @@ struct TickSim {
   }
   int slot_of(u32 nodeid) const { for (u32 s = 0; s < R; ++s) if (subj[s] == nodeid) return (int)s; return -1; }
 
+  // Peer draws: Philox block b yields eight 16-bit draws (low half, then high half of words 0..3);
+  // draw i picks neighbour index (h16 * deg) >> 16.  Degrees are limited to 65535 by set_topology.
+  static inline u32 draw16(const u32 w[4], u32 i) { const u32 x = w[(i >> 1) & 3]; return (i & 1) ? (x >> 16) : (x & 0xffffu); }
+  // Gossip peers (memberlist kRandomNodes: k uniformly random distinct members other than ourselves):
+  // m = min(fanout, deg) distinct SLOTS of the node's neighbour list, sampled without replacement by rank —
+  // draw k picks rank j = (h16_k * (deg - k)) >> 16 among the slots not chosen yet — then slots that point
+  // at the node itself are dropped.  Peers are used in draw order.
   u32 gossip_targets(u32 v, u32 t, u32* out) const {
     u64 r0 = row_ptr[v]; u32 deg = (u32)(row_ptr[v + 1] - r0), nt = 0;
-    u32 w[4] = {0, 0, 0, 0};
-    for (u32 i = 0; i < 3 * deg && nt < cfg.fanout; ++i) {      // kRandomNodes: at most 3n tries (cf. query.rs:388-409)
-      if ((i & 3) == 0) philox4x32_10(t, v, i >> 2, DOMAIN_GOSSIP, (u32)cfg.seed, (u32)(cfg.seed >> 32), w);
-      u32 c = col[r0 + mulhi32(w[i & 3], deg)];
-      if (c == v) continue;
-      bool dup = false;
-      for (u32 j = 0; j < nt; ++j) dup |= (out[j] == c);
-      if (dup) continue;
-      out[nt++] = c;
+    const u32 m = std::min(cfg.fanout, deg);
+    if (!m) return 0;
+    u32 w[4];
+    philox4x32_10(t, v, 0, DOMAIN_GOSSIP, (u32)cfg.seed, (u32)(cfg.seed >> 32), w);
+    u32 chosen[8], nc = 0;                                  // ascending
+    for (u32 k = 0; k < m; ++k) {
+      u32 j = (draw16(w, k) * (deg - k)) >> 16;
+      for (u32 i = 0; i < nc; ++i) if (j >= chosen[i]) ++j;
+      u32 pos = nc;                                          // insert keeping the list ascending
+      while (pos > 0 && chosen[pos - 1] > j) { chosen[pos] = chosen[pos - 1]; --pos; }
+      chosen[pos] = j; ++nc;
+      const u32 c = col[r0 + j];
+      if (c != v) out[nt++] = c;
     }
     return nt;
   }
@@ -593,7 +604,7 @@ struct TickSim {
     u64 r0 = row_ptr[v]; u32 deg = (u32)(row_ptr[v + 1] - r0);
     if (!deg) return false;
     u32 w[4]; philox4x32_10(t, v, 0, DOMAIN_PROBE, (u32)cfg.seed, (u32)(cfg.seed >> 32), w);
-    *out = col[r0 + mulhi32(w[0], deg)];
+    *out = col[r0 + ((draw16(w, 0) * deg) >> 16)];
     return true;
   }
 
@@ -858,6 +869,7 @@ ORC const char* oracle_last_error(void) { return g_err.c_str(); }
 ORC int oracle_sim_set_topology_csr(void* p, const u64* row_ptr, const u32* col_idx) {
   auto* s = (TickSim*)p; s->row_ptr.assign(row_ptr, row_ptr + s->N + 1); s->col.assign(col_idx, col_idx + row_ptr[s->N]);
   for (u32 c : s->col) if (c >= s->N) { g_err = "col_idx out of range"; return SERFSIM_E_INVAL; }
+  for (u32 v = 0; v < s->N; ++v) if (row_ptr[v + 1] - row_ptr[v] > 65535) { g_err = "node degree > 65535"; return SERFSIM_E_INVAL; }
   return 0;
 }
 ORC int oracle_sim_set_subjects(void* p, const u32* subjects) {

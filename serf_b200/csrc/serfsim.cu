@@ -484,6 +484,7 @@ int serfsim_set_topology_csr(serfsim_t* h, const uint64_t* row_ptr, const uint32
   for (u32 i = 0; i <= h->count; ++i) {
     const u64 r = row_ptr[h->first + i];
     if (r < e0 || (i && r < row_ptr[h->first + i - 1])) return fail(SERFSIM_E_INVAL, "row_ptr not monotone");
+    if (i && r - row_ptr[h->first + i - 1] > 65535) return fail(SERFSIM_E_INVAL, "node degree > 65535 (peer draws are 16-bit)");
     rp[i] = (u32)(r - e0);
   }
   const u64 ne = e1 - e0;

@@ -74,6 +74,7 @@ __device__ __forceinline__ void mbar_init(u64* bar, u32 count) { asm volatile("m
 __device__ __forceinline__ void mbar_arrive_expect_tx(u64* bar, u32 bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(u64* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory"); }
 __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
   u32 ok;
   do {
@@ -148,38 +149,45 @@ __device__ __forceinline__ bool differs(const Words& a, const Words& b) {
   return ((a.w[0] ^ b.w[0]) | (a.w[1] ^ b.w[1]) | (a.w[2] ^ b.w[2]) | (a.w[3] ^ b.w[3]) | (a.w[4] ^ b.w[4]) | (a.w[5] ^ b.w[5]) | (a.w[6] ^ b.w[6]) | (a.w[7] ^ b.w[7])) != 0;
 }
 
-// Gossip peers of one node for one tick — memberlist kRandomNodes: up to 3·deg draws for `fanout`
-// distinct neighbours other than the node itself; draw i uses word i&3 of Philox block i>>2.
-// Unfilled entries stay NO_TARGET, so the duplicate test needs no count.
+// Gossip peers of one node for one tick — memberlist kRandomNodes (k uniformly random distinct members
+// other than ourselves): m = min(fanout, deg) distinct slots of the node's CSR row, sampled without
+// replacement by rank from ONE Philox4x32-10 block (eight 16-bit draws: low half, then high half of words
+// 0..3): draw k picks rank j = (h16_k·(deg−k)) >> 16 among the slots not chosen yet; slots pointing at the
+// node itself are dropped; peers are used in draw order.  No rejection loop, no divergence, m gathers.
 constexpr u32 NO_TARGET = 0xffffffffu;
+__device__ __forceinline__ u32 draw16(const u32 (&w)[4], int i) { const u32 x = w[(i >> 1) & 3]; return (i & 1) ? (x >> 16) : (x & 0xffffu); }
 template <int FMAX, bool STAGED>
 __device__ __forceinline__ u32 pick_targets(const TickParams& p, const StageView& sv, u32 v, u32 row0, u32 deg, u32 (&tg)[FMAX]) {
+  const u32 m = min(p.fanout, deg);
+  u32 w[4];
+  philox4x32_10(p.tick, v, 0, DOMAIN_GOSSIP, p.seed_lo, p.seed_hi, w);
+  u32 srt[FMAX];                                           // chosen slots so far, ascending; unused entries = NO_TARGET (sort last)
+  u32 cand[FMAX];
 #pragma unroll
-  for (int j = 0; j < FMAX; ++j) tg[j] = NO_TARGET;
+  for (int k = 0; k < FMAX; ++k) srt[k] = NO_TARGET;
+#pragma unroll
+  for (int k = 0; k < FMAX; ++k) {
+    u32 j = (draw16(w, k) * (deg - min((u32)k, deg))) >> 16;
+#pragma unroll
+    for (int i = 0; i < k; ++i) j += (j >= srt[i]) ? 1u : 0u;         // rank → slot: skip the slots already taken
+    const bool use = (u32)k < m;
+    const u32 e = row0 + (use ? j : 0u);
+    cand[k] = use ? ((STAGED && sv.col_staged) ? sv.col[e - sv.col_base] : __ldg(p.col + e)) : v;
+    // insert j into the ascending list (only if used): bubble it down from position k
+    u32 x = use ? j : NO_TARGET;
+#pragma unroll
+    for (int i = 0; i < k; ++i) { const u32 lo = min(srt[i], x), hi = max(srt[i], x); srt[i] = lo; x = hi; }
+    srt[k] = x;
+  }
   u32 nt = 0;
-  const u32 tries = 3 * deg, fan = p.fanout;
-  for (u32 blk = 0; blk * 4 < tries && nt < fan; ++blk) {
-    u32 w[4];
-    philox4x32_10(p.tick, v, blk, DOMAIN_GOSSIP, p.seed_lo, p.seed_hi, w);
-    u32 cand[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {                                                         // four independent gathers in flight
-      const u32 e = row0 + mulhi32(w[q], deg);
-      cand[q] = (STAGED && sv.col_staged) ? sv.col[e - sv.col_base] : __ldg(p.col + e);
-    }
+  for (int k = 0; k < FMAX; ++k) tg[k] = NO_TARGET;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (blk * 4 + q < tries && nt < fan) {
-        const u32 cnd = cand[q];
-        bool dup = (cnd == v);
+  for (int k = 0; k < FMAX; ++k) {
+    if (cand[k] != v) {                                    // self slots (and the unused tail) are dropped
 #pragma unroll
-        for (int j = 0; j < FMAX; ++j) dup |= (tg[j] == cnd);
-        if (!dup) {
-#pragma unroll
-          for (int j = 0; j < FMAX; ++j) tg[j] = ((u32)j == nt) ? cnd : tg[j];
-          ++nt;
-        }
-      }
+      for (int j2 = 0; j2 <= k; ++j2) tg[j2] = ((u32)j2 == nt) ? cand[k] : tg[j2];
+      ++nt;
     }
   }
   return nt;
@@ -244,7 +252,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   if (up_s && p.probe_every && p.down_mask && ((t + v) % p.probe_every) == 0 && deg) {
     u32 w[4];
     philox4x32_10(t, v, 0, DOMAIN_PROBE, p.seed_lo, p.seed_hi, w);
-    const u32 e = row0 + mulhi32(w[0], deg);
+    const u32 e = row0 + (((w[0] & 0xffffu) * deg) >> 16);
     ptarget = (STAGED && sv.col_staged) ? sv.col[e - sv.col_base] : __ldg(p.col + e);
     have_probe = true;
   }
@@ -435,14 +443,14 @@ __global__ void __launch_bounds__(BLOCK, 4) tick_kernel(const __grid_constant__ 
 // (1 KB) and CSR span (the tile's neighbour lists, 16 KB at out-degree 16) into shared memory, one tile ahead
 // of the 256 consumers (2 stages, mbarrier transaction counts).  The node logic then runs out of shared memory;
 // only the RED.MAX sends, the record write-back and the inbox clears touch global memory from the LSU.
-template <bool TRACE, int FMAX, bool SHARDED>
+template <bool TRACE, int FMAX, bool SHARDED, bool BARSYNC>
 __global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constant__ TickParams p) {
   extern __shared__ __align__(128) unsigned char stage_mem[];
   __shared__ u8 hot_s[MAX_TILES_PER_CTA];
   __shared__ u16 hot_list[MAX_TILES_PER_CTA];
   __shared__ u32 n_hot_s;
   __shared__ u64 red[8][BLOCK / 32];
-  __shared__ __align__(8) u64 full_bar[2];
+  __shared__ __align__(8) u64 full_bar[2], empty_bar[2];
   __shared__ u32 col_base_s[2], col_ok_s[2];
   Counters c = {};
   const bool kL = p.kinds_prev[KIND_LEAVE] != 0, kJ = p.kinds_prev[KIND_JOIN] != 0, kM = p.kinds_prev[KIND_ML] != 0;
@@ -462,7 +470,11 @@ __global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constan
     if (f) p.hot_rd[tile0 + i] = 0;
     hot_s[i] = (f || all_hot) ? 1 : 0;
   }
-  if (threadIdx.x == 0) { mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1); fence_proxy_async(); }
+  if (threadIdx.x == 0) {
+    mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1);
+    mbar_init(&empty_bar[0], BLOCK / 32); mbar_init(&empty_bar[1], BLOCK / 32);     // one arrival per consumer warp
+    fence_proxy_async();
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     u32 n = 0;
@@ -496,9 +508,14 @@ __global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constan
     if (col_ok) bulk_g2s(base + ST_COL, p.col + e0, col_bytes, &full_bar[st], pol_first);
   };
 
+  // No CTA-wide barrier in the loop: a warp that finishes a tile arrives on the stage's `empty` barrier and
+  // moves on; only the producer (thread 0) waits for all eight warps to release a stage before refilling it.
   if (threadIdx.x == 0 && n_hot) issue(0);
   for (u32 j = 0; j < n_hot; ++j) {
-    if (threadIdx.x == 0 && j + 1 < n_hot) issue(j + 1);   // stage (j+1)&1 was released by the barrier ending iteration j-1
+    if (threadIdx.x == 0 && j + 1 < n_hot) {
+      if (!BARSYNC && j >= 1) mbar_wait(&empty_bar[(j + 1) & 1], ((j - 1) >> 1) & 1);   // tile j-1 (same stage) fully consumed
+      issue(j + 1);
+    }
     const u32 st = j & 1;
     mbar_wait(&full_bar[st], (j >> 1) & 1);
     unsigned char* base = stage_mem + (size_t)st * stage_bytes;
@@ -512,7 +529,8 @@ __global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constan
     bool pend = false;
     if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, true, true>(p, sv, vl, kL, kJ, kM, mark, pol_first, pol_last, c);
     if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + ti] = 1;
-    __syncthreads();                                       // every thread is done with stage `st` before it is refilled
+    if (BARSYNC) __syncthreads();
+    else { __syncwarp(); if (lane == 0) mbar_arrive(&empty_bar[st]); }     // this warp is done reading stage `st`
   }
 
   const u64 vals[8] = {c.packets, c.edges, (u64)c.kL + c.kJ + c.kM, c.changed, c.pending, c.kL, c.kJ, c.kM};
@@ -666,12 +684,16 @@ int tick_grid_size(u32 n_local, int ctas_per_sm) {
 template <bool TRACE, int FMAX, bool SHARDED>
 static void launch_tick_tma(const TickParams& p, int grid, cudaStream_t st) {
   const size_t smem = 2 * (size_t)(ST_COL + p.stage_col_bytes);
-  static size_t configured = 0;
-  if (configured < smem) {
-    cudaFuncSetAttribute(tick_kernel_tma<TRACE, FMAX, SHARDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = 200 * 1024;
+  static bool configured = false;
+  static int barsync = 0;
+  if (!configured) {
+    cudaFuncSetAttribute(tick_kernel_tma<TRACE, FMAX, SHARDED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(tick_kernel_tma<TRACE, FMAX, SHARDED, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (const char* e = getenv("SERFSIM_TMA_SYNC")) barsync = atoi(e);
+    configured = true;
   }
-  tick_kernel_tma<TRACE, FMAX, SHARDED><<<grid, BLOCK, smem, st>>>(p);
+  if (barsync) tick_kernel_tma<TRACE, FMAX, SHARDED, true><<<grid, BLOCK, smem, st>>>(p);
+  else tick_kernel_tma<TRACE, FMAX, SHARDED, false><<<grid, BLOCK, smem, st>>>(p);
 }
 
 template <bool TRACE, int FMAX>
