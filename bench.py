@@ -88,13 +88,20 @@ def b_edge(fanout, p_dirty):
     return 4.0 + 32.0 / fanout + 32.0 + 32.0 * p_dirty
 
 
-def time_oracle(args, nodes, threads=1):
-    """CPU baseline: the oracle (C++ port of the reference path) on a bounded sample of the workload."""
+def time_oracle(args, nodes, threads=None):
+    """CPU baseline: the oracle (C++ port of the reference path) on a bounded sample of the workload,
+    node ranges split over `threads` host threads (default: every core of the box)."""
+    import ctypes
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from oracle_lib import oracle_sim
+    from oracle_lib import lib, oracle_sim
     from serf_b200 import scenarios
+    threads = threads or (os.cpu_count() or 1)
     sc = scenarios.dissemination_storm(nodes, args.degree, args.fanout, slots=args.slots, seed=1, waves=args.waves)
-    o = sc.build(oracle_sim)
+    o = oracle_sim(sc.n, sc.slots, **sc.cfg)
+    L = lib()
+    L.oracle_sim_set_threads.restype, L.oracle_sim_set_threads.argtypes = ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]
+    assert L.oracle_sim_set_threads(o._h, threads) == 0
+    o.set_topology(sc.row_ptr, sc.col); o.set_subjects(sc.subjects); o.reset(sc.cfg.get("seed", 1)); sc.schedule(o)
     t0 = time.perf_counter()
     ticks, ok = o.run_until_converged(sc.max_ticks)
     dt = time.perf_counter() - t0
@@ -121,7 +128,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total_s / max(1, len(vals)), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic", "config": sc_cfg,
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": last["sample"]},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
@@ -172,25 +179,19 @@ def main():
     sc = workload(args)
     g = sc.build(lambda n, s, **kw: GossipSim(n, s, **kw), device=local_rank, rank=rank, world_size=world, trace=0)
     if world > 1:
-        def all_gather_bytes(b):
-            out = [None] * world
-            dist.all_gather_object(out, b)
-            return out
-
-        def barrier():
-            dist.barrier()
-
-        def allreduce_u64(arr):
-            t = torch.from_numpy(arr.view(np.int64)).cuda()
-            dist.all_reduce(t)
-            arr.view(np.int64)[:] = t.cpu().numpy()
-        g.connect(all_gather_bytes, barrier, allreduce_u64)
+        from serf_b200 import dist as sdist
+        sdist.connect(g, dist, torch.device("cuda", local_rank))
 
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    # pinned host buffers for the results a caller reads back (the C ABI copies into caller-owned memory)
+    pin_status = [torch.empty(g.count, dtype=torch.uint8).pin_memory() for _ in range(sc.slots)]
+    pin_ltime = [torch.empty(g.count, dtype=torch.int64).pin_memory() for _ in range(sc.slots)]
+    pin_clock = torch.empty(g.count, dtype=torch.int64).pin_memory()
 
     def one_step(read_back):
         g.reset(1)
@@ -200,8 +201,9 @@ def main():
         out_bytes = 0
         if read_back:                                  # device→host: the step's result vectors
             for s in range(sc.slots):
-                out_bytes += g.member_status(s).nbytes + g.status_ltime(s).nbytes
-            out_bytes += g.lamport_time().nbytes
+                out_bytes += g.member_status(s, out=pin_status[s].numpy()).nbytes
+                out_bytes += g.status_ltime(s, out=pin_ltime[s].numpy().view(np.uint64)).nbytes
+            out_bytes += g.lamport_time(out=pin_clock.numpy().view(np.uint64)).nbytes
         return ticks, ok, ms, launches, out_bytes
 
     for _ in range(args.warmup):
@@ -240,7 +242,7 @@ def main():
 
     if rank == 0:
         total_eu = eu_per_step * args.steps
-        value = total_eu / (dev_ms * 1e-3)
+        value = total_eu / wall_dev                    # K whole steps (reset + schedule + ticks), sync to sync
         p_dirty = changed / max(1, eu_per_step)
         be = b_edge(args.fanout, p_dirty)
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -253,10 +255,9 @@ def main():
         achieved = (total_eu / world) * be / (dev_ms * 1e-3) / 1e9
         h2d = len(sc.ops) * 12
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "ms_per_step": 1e3 * wall_dev / args.steps, "kernel_ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "u32", "data": "synthetic", "config": config_dict(args, sc),
                 "ticks_to_convergence": ticks_list[-1], "edge_updates_per_step": eu_per_step, "p_dirty": p_dirty,
-                "wall_s_per_step": wall_dev / args.steps,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_src, "kernel": "tick_kernel", "bytes_per_edge_update": be,
                              "launches": tick_launches, "avg_launch_us": 1e3 * dev_ms / max(1, tick_launches)},

@@ -115,11 +115,12 @@ struct serfsim {
   std::vector<u8> reported;        // last status reported per slot
   int grid = 1;
   // multi-GPU
-  std::vector<u64*> peer_win_data; std::vector<u32*> peer_win_count;
-  u64* d_win_data[2] = {nullptr, nullptr};     // my windows [parity][world][win_cap]
-  u32* d_win_count[2] = {nullptr, nullptr};    // [parity][world]
-  u64** d_peer_data[2] = {nullptr, nullptr};   // device arrays of peer pointers, per parity
-  u32** d_peer_count[2] = {nullptr, nullptr};
+  u64* d_win_data[2] = {nullptr, nullptr};     // my receive windows [parity][world][win_cap]  (IPC-exported)
+  u32* d_ctrl = nullptr;                       // my control block [parity][counts[8] | flags[8]] (IPC-exported)
+  u32* d_send_count = nullptr;                 // [world] entries written into each peer's window this tick
+  u64** d_peer_data[2] = {nullptr, nullptr};   // device arrays of peer window pointers, per parity
+  u32** d_peer_ctrl = nullptr;                 // device array of peer control-block pointers
+  u32 xepoch = 0;                              // executed-tick counter of the exchange (never rewinds): stamps and parity
   u32 win_cap = 0;
   bool connected = false;
   serfsim_barrier_fn barrier = nullptr; serfsim_allreduce_u64_fn allreduce = nullptr; void* comm_user = nullptr;
@@ -221,8 +222,9 @@ int launch_ticks(serfsim* h, u32 n) {
     p.stage_col_bytes = h->stage_col_bytes;
     p.stride = h->stride; p.n_tiles = h->n_tiles; p.tiles_per_cta = (h->n_tiles + h->grid - 1) / h->grid;
     p.force_all = (h->cfg.trace != 0) || (h->cfg.probe_interval_ticks && p.down_mask) || h->no_skip;
+    const u32 xpar = h->xepoch & 1;
     p.world = (u32)h->cfg.world_size; p.rank = (u32)h->cfg.rank; p.shard_size = h->shard_size; p.win_cap = h->win_cap;
-    p.win_data = h->d_peer_data[t & 1]; p.win_count = h->d_peer_count[t & 1];
+    p.win_data = h->d_peer_data[xpar]; p.send_count = h->d_send_count;
     if (h->tick_timing) {
       while (h->tick_ev.size() < 2 * ((size_t)t + 1)) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->tick_ev.push_back(e); }
       CU(cudaEventRecord(h->tick_ev[2 * (size_t)t], h->stream));
@@ -238,21 +240,22 @@ int launch_ticks(serfsim* h, u32 n) {
       CU(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av));
     }
     launch_tick(p, h->cfg.trace != 0, h->grid, h->stream);
-    if (h->tick_timing) CU(cudaEventRecord(h->tick_ev[2 * (size_t)t + 1], h->stream));
     h->last_launches++;
     if (h->cfg.world_size > 1) {
-      // all peers have finished writing into my window of this parity once the barrier returns
-      CU(cudaStreamSynchronize(h->stream));
-      h->barrier(h->comm_user);
+      // No host round trip: publish (counts + flag into every peer's control block) and drain (waits for the
+      // peers' flags of this exchange) are ordinary kernels on the same stream.
+      const u32 stamp = h->xepoch + 1;
+      PublishParams pb{};
+      pb.world = p.world; pb.rank = p.rank; pb.stamp = stamp; pb.xpar = xpar; pb.send_count = h->d_send_count; pb.peer_ctrl = h->d_peer_ctrl;
+      launch_publish(pb, h->stream);
       DrainParams d{};
-      d.n_local = h->count; d.stride = h->stride; d.R = h->R; d.world = (u32)h->cfg.world_size; d.rank = (u32)h->cfg.rank; d.win_cap = h->win_cap;
-      d.win_data = h->d_win_data[t & 1]; d.win_count = h->d_win_count[t & 1]; d.inbox_wr = h->d_inbox[t & 1]; d.hot_wr = h->d_hot[t & 1]; d.overflow = h->d_overflow;
+      d.n_local = h->count; d.stride = h->stride; d.R = h->R; d.world = p.world; d.rank = p.rank; d.win_cap = h->win_cap; d.stamp = stamp;
+      d.win_data = h->d_win_data[xpar]; d.ctrl = h->d_ctrl + xpar * 16; d.inbox_wr = h->d_inbox[t & 1]; d.hot_wr = h->d_hot[t & 1]; d.overflow = h->d_overflow;
       launch_drain(d, h->stream);
-      CU(cudaMemsetAsync(h->d_win_count[t & 1], 0, sizeof(u32) * h->cfg.world_size, h->stream));
-      h->last_launches++;
-      CU(cudaStreamSynchronize(h->stream));
-      h->barrier(h->comm_user);      // windows of this parity are reusable two ticks from now; counters are reset
+      h->last_launches += 2;
+      h->xepoch++;
     }
+    if (h->tick_timing) CU(cudaEventRecord(h->tick_ev[2 * (size_t)t + 1], h->stream));
     h->tick++;
   }
   CU(cudaGetLastError());
@@ -326,8 +329,7 @@ int do_reset(serfsim* h, u64 seed) {
     CU(cudaMemsetAsync(h->d_trace, 0, (size_t)h->trace_cap * 8 * sizeof(u64), h->stream));
     CU(cudaMemsetAsync(h->d_kinds, 0, ((size_t)h->trace_cap + 1) * 4 * sizeof(u32), h->stream));
   }
-  for (int par = 0; par < 2; ++par)
-    if (h->d_win_count[par]) CU(cudaMemsetAsync(h->d_win_count[par], 0, sizeof(u32) * h->cfg.world_size, h->stream));
+  if (h->d_send_count) CU(cudaMemsetAsync(h->d_send_count, 0, sizeof(u32) * 8, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -339,7 +341,8 @@ void free_all(serfsim* h) {
   cudaFree(h->d_rec); cudaFree(h->d_inbox[0]); cudaFree(h->d_inbox[1]); cudaFree(h->d_node); cudaFree(h->d_rowptr); cudaFree(h->d_col);
   cudaFree(h->d_ev_node); cudaFree(h->d_ev_op); cudaFree(h->d_ev_slot); cudaFree(h->d_trace); cudaFree(h->d_kinds); cudaFree(h->d_ones);
   cudaFree(h->d_overflow); cudaFree(h->d_subj); cudaFree(h->d_scratch); cudaFree(h->d_stage);
-  for (int par = 0; par < 2; ++par) { cudaFree(h->d_win_data[par]); cudaFree(h->d_win_count[par]); cudaFree(h->d_peer_data[par]); cudaFree(h->d_peer_count[par]); }
+  for (int par = 0; par < 2; ++par) { cudaFree(h->d_win_data[par]); cudaFree(h->d_peer_data[par]); }
+  cudaFree(h->d_ctrl); cudaFree(h->d_send_count); cudaFree(h->d_peer_ctrl);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -445,17 +448,21 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
   }
   if (const char* e = getenv("SERFSIM_NO_SKIP")) h->no_skip = atoi(e) != 0;
   if (cfg->world_size > 1) {
-    // receive windows: expected cross-shard entries per tick ≈ count · fanout · R · 3 / world per peer; SERFSIM_WIN_FACTOR scales it
-    double factor = 1.5;
+    // receive windows: one segment per peer; expected entries per tick and pair ≈ shard · fanout · R · kinds / world
+    if (cfg->world_size > 8) return bail(fail(SERFSIM_E_INVAL, "world_size > 8"));
+    double factor = 1.25;
     if (const char* e = getenv("SERFSIM_WIN_FACTOR")) factor = atof(e);
-    double cap = (double)h->shard_size * cfg->fanout * h->R * factor / cfg->world_size + 4096.0;
+    double cap = (double)h->shard_size * cfg->fanout * h->R * 3.0 * factor / cfg->world_size + 4096.0;
     h->win_cap = (u32)std::min(cap, 4.0e9);
     for (int par = 0; par < 2; ++par) {
       CUB(cudaMalloc(&h->d_win_data[par], (size_t)cfg->world_size * h->win_cap * 8));
-      CUB(cudaMalloc(&h->d_win_count[par], sizeof(u32) * cfg->world_size));
-      CUB(cudaMalloc(&h->d_peer_data[par], sizeof(u64*) * cfg->world_size));
-      CUB(cudaMalloc(&h->d_peer_count[par], sizeof(u32*) * cfg->world_size));
+      CUB(cudaMalloc(&h->d_peer_data[par], sizeof(u64*) * 8));
     }
+    CUB(cudaMalloc(&h->d_ctrl, 2 * 16 * sizeof(u32)));
+    CUB(cudaMemset(h->d_ctrl, 0, 2 * 16 * sizeof(u32)));
+    CUB(cudaMalloc(&h->d_send_count, 8 * sizeof(u32)));
+    CUB(cudaMemset(h->d_send_count, 0, 8 * sizeof(u32)));
+    CUB(cudaMalloc(&h->d_peer_ctrl, sizeof(u32*) * 8));
   }
   {
     int rc = ensure_trace(h, 1024);
@@ -504,7 +511,7 @@ int serfsim_set_topology_csr(serfsim_t* h, const uint64_t* row_ptr, const uint32
   // TMA pipeline (single-slot runs): a stage holds the largest tile's CSR span if that is at most 48 KB
   h->stage_col_bytes = 0;
   {
-    int use = 1;
+    int use = 0;   // measured (profiles/): the direct-load kernel is 3 % faster over a whole run; SERFSIM_TMA=1 selects the TMA pipeline
     if (const char* e = getenv("SERFSIM_TMA")) use = atoi(e);
     const u32 need = std::max<u32>(h->max_tile_edges * 4u, 16u);
     if (use && h->R == 1 && need <= 48u * 1024u) h->stage_col_bytes = (need + 127u) & ~127u;
@@ -682,7 +689,7 @@ int serfsim_tick_times(serfsim_t* h, uint32_t first_tick, uint32_t n, float* ms_
 }
 
 // ---- multi-GPU: CUDA IPC windows ----------------------------------------------------------
-struct comm_blob { cudaIpcMemHandle_t data[2]; cudaIpcMemHandle_t count[2]; u32 win_cap; u32 rank; };
+struct comm_blob { cudaIpcMemHandle_t data[2]; cudaIpcMemHandle_t ctrl; u32 win_cap; u32 rank; };
 
 size_t serfsim_comm_blob_size(void) { return sizeof(comm_blob); }
 
@@ -690,10 +697,8 @@ int serfsim_comm_export(serfsim_t* h, void* blob) {
   if (!h || !blob) return fail(SERFSIM_E_INVAL, "null argument");
   if (h->cfg.world_size < 2) return fail(SERFSIM_E_INVAL, "world_size == 1: nothing to export");
   comm_blob b{};
-  for (int par = 0; par < 2; ++par) {
-    CU(cudaIpcGetMemHandle(&b.data[par], h->d_win_data[par]));
-    CU(cudaIpcGetMemHandle(&b.count[par], h->d_win_count[par]));
-  }
+  for (int par = 0; par < 2; ++par) CU(cudaIpcGetMemHandle(&b.data[par], h->d_win_data[par]));
+  CU(cudaIpcGetMemHandle(&b.ctrl, h->d_ctrl));
   b.win_cap = h->win_cap; b.rank = (u32)h->cfg.rank;
   memcpy(blob, &b, sizeof(b));
   return 0;
@@ -705,22 +710,24 @@ int serfsim_comm_connect(serfsim_t* h, const void* blobs) {
   if (W < 2) return fail(SERFSIM_E_INVAL, "world_size == 1");
   if (!h->barrier || !h->allreduce) return fail(SERFSIM_E_COMM, "serfsim_comm_set_hooks must be called first");
   const comm_blob* bs = (const comm_blob*)blobs;
-  for (int par = 0; par < 2; ++par) {
-    std::vector<u64*> pd(W); std::vector<u32*> pc(W);
-    for (int r = 0; r < W; ++r) {
-      if (bs[r].rank != (u32)r || bs[r].win_cap != h->win_cap) return fail(SERFSIM_E_COMM, "blob order / window size mismatch");
-      if (r == h->cfg.rank) { pd[r] = h->d_win_data[par]; pc[r] = h->d_win_count[par]; continue; }
-      void *p1 = nullptr, *p2 = nullptr;
-      cudaError_t e = cudaIpcOpenMemHandle(&p1, bs[r].data[par], cudaIpcMemLazyEnablePeerAccess);
-      if (e != cudaSuccess) return fail(SERFSIM_E_COMM, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
-      e = cudaIpcOpenMemHandle(&p2, bs[r].count[par], cudaIpcMemLazyEnablePeerAccess);
-      if (e != cudaSuccess) return fail(SERFSIM_E_COMM, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
-      h->ipc_opened.push_back(p1); h->ipc_opened.push_back(p2);
-      pd[r] = (u64*)p1; pc[r] = (u32*)p2;
+  std::vector<u32*> pc(8, nullptr);
+  std::vector<std::vector<u64*>> pd(2, std::vector<u64*>(8, nullptr));
+  for (int r = 0; r < W; ++r) {
+    if (bs[r].rank != (u32)r || bs[r].win_cap != h->win_cap) return fail(SERFSIM_E_COMM, "blob order / window size mismatch");
+    if (r == h->cfg.rank) { pd[0][r] = h->d_win_data[0]; pd[1][r] = h->d_win_data[1]; pc[r] = h->d_ctrl; continue; }
+    void* ptr = nullptr;
+    for (int par = 0; par < 2; ++par) {
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, bs[r].data[par], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return fail(SERFSIM_E_COMM, std::string("cudaIpcOpenMemHandle(window): ") + cudaGetErrorString(e));
+      h->ipc_opened.push_back(ptr); pd[par][r] = (u64*)ptr;
     }
-    CU(cudaMemcpy(h->d_peer_data[par], pd.data(), sizeof(u64*) * W, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(h->d_peer_count[par], pc.data(), sizeof(u32*) * W, cudaMemcpyHostToDevice));
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, bs[r].ctrl, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(SERFSIM_E_COMM, std::string("cudaIpcOpenMemHandle(ctrl): ") + cudaGetErrorString(e));
+    h->ipc_opened.push_back(ptr); pc[r] = (u32*)ptr;
   }
+  for (int par = 0; par < 2; ++par) CU(cudaMemcpy(h->d_peer_data[par], pd[par].data(), sizeof(u64*) * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_peer_ctrl, pc.data(), sizeof(u32*) * 8, cudaMemcpyHostToDevice));
+  h->barrier(h->comm_user);          // every rank has mapped every window before the first tick writes into one
   h->connected = true;
   return 0;
 }

@@ -116,8 +116,14 @@ __device__ __forceinline__ u64 warp_sum64(u64 v) {
 // Deliver one entry to `dst` (global id): local → RED.MAX into this shard's inbox plane `plane`
 // (= inbox_wr + (kind·R + slot)·n_local) and mark the destination tile hot for the next tick;
 // cross-shard → append to the peer's receive window over NVLink.
+// Cross-shard staging area of a CTA: entries are grouped by destination shard in shared memory and flushed
+// once per tile with coalesced 8-byte stores into the peer's window (one counter atomic per shard per tile).
+constexpr u32 XCAP = 384;                  // entries per destination shard per tile
+constexpr u32 MAX_WORLD = 8;
+struct XStage { u64 buf[MAX_WORLD][XCAP]; u32 cnt[MAX_WORLD]; u32 base[MAX_WORLD]; };
+
 template <bool SHARDED>
-__device__ __forceinline__ void deliver(const TickParams& p, u32* plane, u32 dst, u32 kind, u32 s, u32 val1, u64 pol_last, bool mark) {
+__device__ __forceinline__ void deliver(const TickParams& p, XStage* xs, u32* plane, u32 dst, u32 kind, u32 s, u32 val1, u64 pol_last, bool mark) {
   const u32 dl = dst - p.first;
   if (!SHARDED || dl < p.n_local) {
     red_max_resident(plane + dl, val1, pol_last);
@@ -125,14 +131,39 @@ __device__ __forceinline__ void deliver(const TickParams& p, u32* plane, u32 dst
   } else {
     const u32 shard = dst / p.shard_size;
     const u32 dloc = dst - shard * p.shard_size;
-    const u32 pos = atomicAdd(p.win_count[shard] + p.rank, 1u);
-    if (pos < p.win_cap) {
-      const u64 e = ((u64)val1 << 32) | ((u64)s << 28) | ((u64)kind << 26) | dloc;
-      p.win_data[shard][(size_t)p.rank * p.win_cap + pos] = e;
-    } else {
-      *p.overflow = 2;
+    const u64 e = ((u64)val1 << 32) | ((u64)s << 28) | ((u64)kind << 26) | dloc;
+    const u32 pos = atomicAdd(&xs->cnt[shard], 1u);
+    if (pos < XCAP) {
+      xs->buf[shard][pos] = e;
+    } else {                                   // stage full: write this one straight through
+      const u32 g = atomicAdd(p.send_count + shard, 1u);
+      if (g < p.win_cap) p.win_data[shard][(size_t)p.rank * p.win_cap + g] = e;
+      else *p.overflow = 2;
     }
   }
+}
+
+// Flush the staged cross-shard entries of a tile (whole CTA).
+__device__ __forceinline__ void flush_xstage(const TickParams& p, XStage* xs) {
+  __syncthreads();
+  if (threadIdx.x < p.world) {
+    const u32 n = min(xs->cnt[threadIdx.x], XCAP);
+    xs->base[threadIdx.x] = n ? atomicAdd(p.send_count + threadIdx.x, n) : 0u;
+  }
+  __syncthreads();
+  bool wrote = false;
+  for (u32 sh = 0; sh < p.world; ++sh) {
+    const u32 n = min(xs->cnt[sh], XCAP), base = xs->base[sh];
+    u64* dst = p.win_data[sh] + (size_t)p.rank * p.win_cap;
+    for (u32 i = threadIdx.x; i < n; i += BLOCK) {
+      if (base + i < p.win_cap) { dst[base + i] = xs->buf[sh][i]; wrote = true; }
+      else *p.overflow = 2;
+    }
+  }
+  if (wrote) __threadfence_system();           // the entries are visible to the peer before the publish kernel raises the flag
+  __syncthreads();
+  if (threadIdx.x < MAX_WORLD) xs->cnt[threadIdx.x] = 0;
+  __syncthreads();
 }
 
 __device__ __forceinline__ void unpack_words(const Words& x, Rec& r) {
@@ -195,7 +226,7 @@ __device__ __forceinline__ u32 pick_targets(const TickParams& p, const StageView
 
 // Returns true when the node still holds pending work (keeps its tile hot for the next tick).
 template <bool TRACE, int FMAX, bool SHARDED, bool R1, bool STAGED>
-__device__ __forceinline__ bool process_node(const TickParams& p, const StageView& sv, const u32 vl, const bool kL, const bool kJ, const bool kM, const bool mark,
+__device__ __forceinline__ bool process_node(const TickParams& p, const StageView& sv, XStage* xs, const u32 vl, const bool kL, const bool kJ, const bool kM, const bool mark,
                                              const u64 pol_first, const u64 pol_last, Counters& c) {
   static_assert(!STAGED || R1, "the staged path is the single-slot path");
   const u32 lt = threadIdx.x;              // index inside the staged tile
@@ -347,9 +378,9 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
         const u32 sL = min(r.txl, nt), sJ = min(r.txj, nt), sM = min(r.txm, nt);     // entry e goes to targets 0 .. min(tx_e, nt)-1
 #pragma unroll
         for (int k = 0; k < FMAX; ++k) {
-          if ((u32)k < sL) deliver<SHARDED>(p, planeL, tg[k], KIND_LEAVE, s, vL, pol_last, mark);
-          if ((u32)k < sJ) deliver<SHARDED>(p, planeJ, tg[k], KIND_JOIN, s, vJ, pol_last, mark);
-          if ((u32)k < sM) deliver<SHARDED>(p, planeM, tg[k], KIND_ML, s, vM, pol_last, mark);
+          if ((u32)k < sL) deliver<SHARDED>(p, xs, planeL, tg[k], KIND_LEAVE, s, vL, pol_last, mark);
+          if ((u32)k < sJ) deliver<SHARDED>(p, xs, planeJ, tg[k], KIND_JOIN, s, vJ, pol_last, mark);
+          if ((u32)k < sM) deliver<SHARDED>(p, xs, planeM, tg[k], KIND_ML, s, vM, pol_last, mark);
         }
         c.kL += sL; c.kJ += sJ; c.kM += sM;
         c.edges += min(mx, nt);
@@ -385,10 +416,13 @@ template <bool TRACE, int FMAX, bool SHARDED, bool R1>
 __global__ void __launch_bounds__(BLOCK, 4) tick_kernel(const __grid_constant__ TickParams p) {
   __shared__ u8 hot_s[MAX_TILES_PER_CTA];
   __shared__ u64 red[8][BLOCK / 32];
+  __shared__ __align__(16) unsigned char xs_mem[SHARDED ? sizeof(XStage) : 16];
+  XStage* xs = reinterpret_cast<XStage*>(xs_mem);
   Counters c = {};
   const bool kL = p.kinds_prev[KIND_LEAVE] != 0, kJ = p.kinds_prev[KIND_JOIN] != 0, kM = p.kinds_prev[KIND_ML] != 0;
   const u64 pol_first = policy_evict_first(), pol_last = policy_evict_last();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (SHARDED && threadIdx.x < MAX_WORLD) xs->cnt[threadIdx.x] = 0;
 
   // Dense / sparse ticks.  While the gossip front is wide (the previous tick sent at least one message per
   // two tiles) every tile will be hot anyway: senders skip the per-message tile marking and the next tick
@@ -412,8 +446,9 @@ __global__ void __launch_bounds__(BLOCK, 4) tick_kernel(const __grid_constant__ 
     if (!hot_s[i]) continue;
     const u32 vl = ((tile0 + i) << TILE_SHIFT) + threadIdx.x;
     bool pend = false;
-    if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, vl, kL, kJ, kM, mark, pol_first, pol_last, c);
+    if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, kL, kJ, kM, mark, pol_first, pol_last, c);
     if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + i] = 1;
+    if (SHARDED) flush_xstage(p, xs);
   }
   // block reduction (warp shuffles, then shared memory) → one atomic per counter per CTA.
   // trace row: 0 packets, 1 edge_updates, 2 messages, 3 changed, 4 pending, (5 events, 6 suspects: direct), 7 hash
@@ -527,7 +562,7 @@ __global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constan
     const u32 ti = hot_list[j];
     const u32 vl = ((tile0 + ti) << TILE_SHIFT) + threadIdx.x;
     bool pend = false;
-    if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, true, true>(p, sv, vl, kL, kJ, kM, mark, pol_first, pol_last, c);
+    if (vl < p.n_local) pend = process_node<TRACE, FMAX, false, true, true>(p, sv, nullptr, vl, kL, kJ, kM, mark, pol_first, pol_last, c);
     if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + ti] = 1;
     if (BARSYNC) __syncthreads();
     else { __syncwarp(); if (lane == 0) mbar_arrive(&empty_bar[st]); }     // this warp is done reading stage `st`
@@ -554,11 +589,31 @@ __global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constan
   if (TRACE && lane == 0 && hs) atomicAdd((unsigned long long*)(p.row + 7), (unsigned long long)hs);
 }
 
-// Fold the cross-shard window (filled by the peers during their tick kernel) into the inbox.
+// After the tick kernel: publish, to every peer, how many entries this rank wrote into its window, then raise
+// the peer's flag for this exchange (system-scope release).  One warp.
+__global__ void publish_kernel(const __grid_constant__ PublishParams p) {
+  const u32 r = threadIdx.x;
+  if (r < p.world && r != p.rank) {
+    u32* ctrl = p.peer_ctrl[r] + p.xpar * 16;
+    ctrl[p.rank] = p.send_count[r];
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(ctrl + 8 + p.rank), "r"(p.stamp) : "memory");
+    p.send_count[r] = 0;
+  }
+}
+
+// Fold the cross-shard windows into the inbox.  Waits (system-scope acquire) until every peer has raised
+// this exchange's flag — the peers' publish kernels precede their own drains in stream order, so the wait
+// cannot deadlock — then reduces the entries exactly like local deliveries.
 __global__ void __launch_bounds__(BLOCK) drain_kernel(const __grid_constant__ DrainParams p) {
+  if (threadIdx.x < p.world && threadIdx.x != p.rank) {
+    u32 f;
+    do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(p.ctrl + 8 + threadIdx.x) : "memory"); } while (f != p.stamp);
+  }
+  __syncthreads();
   for (u32 src = 0; src < p.world; ++src) {
     if (src == p.rank) continue;
-    const u32 n = min(p.win_count[src], p.win_cap);
+    const u32 n = min(p.ctrl[src], p.win_cap);
     const u64* w = p.win_data + (size_t)src * p.win_cap;
     for (u32 i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
       const u64 e = __ldcg(w + i);
@@ -699,8 +754,8 @@ static void launch_tick_tma(const TickParams& p, int grid, cudaStream_t st) {
 template <bool TRACE, int FMAX>
 static void launch_tick_v(const TickParams& p, int grid, cudaStream_t st) {
   const bool sharded = p.world > 1, r1 = p.R == 1;
-  if (r1 && p.stage_col_bytes) {             // single-slot run whose tiles fit a shared-memory stage: TMA pipeline
-    if (sharded) launch_tick_tma<TRACE, FMAX, true>(p, grid, st); else launch_tick_tma<TRACE, FMAX, false>(p, grid, st);
+  if (r1 && p.stage_col_bytes && !sharded) { // single-slot, single-GPU run whose tiles fit a shared-memory stage: TMA pipeline
+    launch_tick_tma<TRACE, FMAX, false>(p, grid, st);
     return;
   }
   if (sharded) { if (r1) tick_kernel<TRACE, FMAX, true, true><<<grid, BLOCK, 0, st>>>(p); else tick_kernel<TRACE, FMAX, true, false><<<grid, BLOCK, 0, st>>>(p); }
@@ -711,7 +766,8 @@ void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st) {
   if (trace) { if (small) launch_tick_v<true, 4>(p, grid, st); else launch_tick_v<true, 8>(p, grid, st); }
   else { if (small) launch_tick_v<false, 4>(p, grid, st); else launch_tick_v<false, 8>(p, grid, st); }
 }
-void launch_drain(const DrainParams& p, cudaStream_t st) { drain_kernel<<<148 * 4, BLOCK, 0, st>>>(p); }
+void launch_drain(const DrainParams& p, cudaStream_t st) { drain_kernel<<<148 * 2, BLOCK, 0, st>>>(p); }
+void launch_publish(const PublishParams& p, cudaStream_t st) { publish_kernel<<<1, 32, 0, st>>>(p); }
 void launch_init_state(uint4* rec, u64* node_state, u32 n_local, u32 stride, u32 R, u32 init_st, u32 init_clock, cudaStream_t st) {
   init_state_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(rec, node_state, n_local, stride, R, init_st, init_clock);
 }

@@ -31,16 +31,24 @@ struct TickParams {
   u8* hot_wr;                 // [n_tiles] tile flags for the next tick
   u32 stage_col_bytes, pad1, pad2, pad3;             // > 0: single-slot TMA pipeline with this many bytes of CSR per stage
   u32 n_tiles, tiles_per_cta, force_all, stride;   // stride: plane stride in nodes = n_local rounded up to a whole tile
-  // cross-shard exchange (world_size > 1): per-destination-shard message windows in peer memory
+  // cross-shard exchange (world_size > 1): every rank owns one receive window per peer (mapped into the
+  // peers with CUDA IPC); the tick kernel stages cross-shard entries per destination shard in shared memory
+  // and writes them into the peer's window with coalesced stores over NVLink.
   u32 world, rank, shard_size, win_cap;
-  u64* const* win_data;       // [world] peer window payloads for THIS tick parity (entry = dst_local | kind/slot<<.. , value)
-  u32* const* win_count;      // [world] peer window fill counters
+  u64* const* win_data;       // [world] peer windows of this exchange parity; my segment starts at rank·win_cap
+  u32* send_count;            // [world] entries written so far into each peer's window (local counters)
+};
+
+struct PublishParams {        // after the tick kernel: tell every peer how much was written, then raise its flag
+  u32 world, rank, stamp, xpar;
+  u32* send_count;            // [world] local, reset here
+  u32* const* peer_ctrl;      // [world] peers' control blocks: [parity][ counts[8] | flags[8] ]
 };
 
 struct DrainParams {
-  u32 n_local, stride, R, world, rank, win_cap;
-  const u64* win_data;        // my window: [world][win_cap]
-  u32* win_count;             // [world]
+  u32 n_local, stride, R, world, rank, win_cap, stamp, pad;
+  const u64* win_data;        // my window of this exchange parity: [world][win_cap]
+  const u32* ctrl;            // my control block of this parity: counts[8] | flags[8], written by the peers
   u32* inbox_wr;
   u8* hot_wr;
   u32* overflow;
@@ -48,6 +56,7 @@ struct DrainParams {
 
 void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st);
 void launch_drain(const DrainParams& p, cudaStream_t st);
+void launch_publish(const PublishParams& p, cudaStream_t st);
 void launch_init_state(uint4* rec, u64* node_state, u32 n_local, u32 stride, u32 R, u32 init_st, u32 init_clock, cudaStream_t st);
 void launch_mark_events(u64* node_state, u8* hot_rd, const u32* ev_node, u32 ev_begin, u32 ev_end, u32 first, u32 n_local, cudaStream_t st);
 void launch_extract(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 slot, int what, void* out, cudaStream_t st);

@@ -239,17 +239,19 @@ class GossipSim:
         return t.value, rc == 0
 
     # -- outputs ----------------------------------------------------------------------
-    def _get(self, name, dtype, slot=None):
-        out = np.empty(self.count, dtype=dtype)
+    def _get(self, name, dtype, slot=None, out=None):
+        if out is None:
+            out = np.empty(self.count, dtype=dtype)
+        assert out.dtype == np.dtype(dtype) and out.shape == (self.count,) and out.flags.c_contiguous
         if slot is None:
             self._check(self._fn(name)(self._h, out.ctypes.data))
         else:
             self._check(self._fn(name)(self._h, int(slot), out.ctypes.data))
         return out
 
-    def member_status(self, slot=0): return self._get("member_status", np.uint8, slot)        # Serf::members
-    def status_ltime(self, slot=0): return self._get("status_ltime", np.uint64, slot)
-    def lamport_time(self): return self._get("lamport_time", np.uint64)
+    def member_status(self, slot=0, out=None): return self._get("member_status", np.uint8, slot, out)        # Serf::members
+    def status_ltime(self, slot=0, out=None): return self._get("status_ltime", np.uint64, slot, out)
+    def lamport_time(self, out=None): return self._get("lamport_time", np.uint64, None, out)
     def incarnation(self, slot=0): return self._get("incarnation", np.uint32, slot)
     def ml_state(self, slot=0): return self._get("ml_state", np.uint8, slot)
     def records(self, slot=0): return self._get("records", RECORD_DTYPE, slot)
