@@ -130,6 +130,7 @@ struct serfsim {
   bool l2_window = false;           // SERFSIM_L2_WINDOW=1: stream access-policy window over the inbox being written
   bool no_skip = false;             // SERFSIM_NO_SKIP=1: process every tile every tick (A/B measurements)
   std::vector<cudaEvent_t> tick_ev;      // 2 per tick when tick_timing
+  std::vector<cudaEvent_t> mid_ev;       // after the tick kernel (multi-GPU breakdown, SERFSIM_XTIMING=1)
 };
 
 namespace {
@@ -215,7 +216,7 @@ int launch_ticks(serfsim* h, u32 n) {
     p.node_state = h->d_node; p.row_ptr = h->d_rowptr; p.col = h->d_col;
     p.ev_node = h->d_ev_node; p.ev_op = h->d_ev_op; p.ev_slot = h->d_ev_slot;
     p.row = h->d_trace + (size_t)t * 8;
-    p.kinds_prev = (h->cfg.world_size > 1) ? h->d_ones : h->d_kinds + (size_t)t * 4;
+    p.kinds_prev = h->d_kinds + (size_t)t * 4;
     p.kinds_cur = h->d_kinds + ((size_t)t + 1) * 4;
     p.overflow = h->d_overflow;
     p.hot_rd = h->d_hot[(t & 1) ^ 1]; p.hot_wr = h->d_hot[t & 1];
@@ -241,6 +242,10 @@ int launch_ticks(serfsim* h, u32 n) {
     }
     launch_tick(p, h->cfg.trace != 0, h->grid, h->stream);
     h->last_launches++;
+    if (h->tick_timing && h->cfg.world_size > 1) {
+      while (h->mid_ev.size() < (size_t)t + 1) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->mid_ev.push_back(e); }
+      CU(cudaEventRecord(h->mid_ev[t], h->stream));
+    }
     if (h->cfg.world_size > 1) {
       // No host round trip: publish (counts + flag into every peer's control block) and drain (waits for the
       // peers' flags of this exchange) are ordinary kernels on the same stream.
@@ -249,8 +254,8 @@ int launch_ticks(serfsim* h, u32 n) {
       pb.world = p.world; pb.rank = p.rank; pb.stamp = stamp; pb.xpar = xpar; pb.send_count = h->d_send_count; pb.peer_ctrl = h->d_peer_ctrl;
       launch_publish(pb, h->stream);
       DrainParams d{};
-      d.n_local = h->count; d.stride = h->stride; d.R = h->R; d.world = p.world; d.rank = p.rank; d.win_cap = h->win_cap; d.stamp = stamp;
-      d.win_data = h->d_win_data[xpar]; d.ctrl = h->d_ctrl + xpar * 16; d.inbox_wr = h->d_inbox[t & 1]; d.hot_wr = h->d_hot[t & 1]; d.overflow = h->d_overflow;
+      d.n_local = h->count; d.stride = h->stride; d.R = h->R; d.world = p.world; d.rank = p.rank; d.win_cap = h->win_cap; d.stamp = stamp; d.n_tiles = h->n_tiles; d.kinds_prev = p.kinds_prev;
+      d.win_data = h->d_win_data[xpar]; d.ctrl = h->d_ctrl + xpar * 16; d.inbox_wr = h->d_inbox[t & 1]; d.hot_wr = h->d_hot[t & 1]; d.kinds_cur = h->d_kinds + ((size_t)t + 1) * 4; d.overflow = h->d_overflow;
       launch_drain(d, h->stream);
       h->last_launches += 2;
       h->xepoch++;
@@ -478,6 +483,17 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
 void serfsim_destroy(serfsim_t* h) {
   if (!h) return;
   cudaStreamSynchronize(h->stream);
+  if (getenv("SERFSIM_XTIMING") && !h->mid_ev.empty()) {
+    double a = 0, b = 0; size_t n = std::min(h->mid_ev.size(), h->tick_ev.size() / 2);
+    for (size_t t = 0; t < n; ++t) {
+      float x = 0, y = 0;
+      if (cudaEventElapsedTime(&x, h->tick_ev[2 * t], h->mid_ev[t]) == cudaSuccess && cudaEventElapsedTime(&y, h->mid_ev[t], h->tick_ev[2 * t + 1]) == cudaSuccess) {
+        a += x; b += y;
+        if (t >= 12 && t <= 15) fprintf(stderr, "rank %d tick %zu: tick kernel %.1f us, publish+drain %.1f us\n", h->cfg.rank, t, x * 1e3, y * 1e3);
+      }
+    }
+    fprintf(stderr, "rank %d: tick kernels %.3f ms, publish+drain %.3f ms over %zu ticks\n", h->cfg.rank, a, b, n);
+  }
   free_all(h);
   delete h;
 }

@@ -118,9 +118,11 @@ __device__ __forceinline__ u64 warp_sum64(u64 v) {
 // cross-shard → append to the peer's receive window over NVLink.
 // Cross-shard staging area of a CTA: entries are grouped by destination shard in shared memory and flushed
 // once per tile with coalesced 8-byte stores into the peer's window (one counter atomic per shard per tile).
-constexpr u32 XCAP = 384;                  // entries per destination shard per tile
+constexpr u32 XTOTAL = 3072;               // staged entries per CTA (24 KB), split evenly over the world-1 peers
 constexpr u32 MAX_WORLD = 8;
-struct XStage { u64 buf[MAX_WORLD][XCAP]; u32 cnt[MAX_WORLD]; u32 base[MAX_WORLD]; };
+struct XStage { u64 buf[XTOTAL]; u32 cnt[MAX_WORLD]; u32 base[MAX_WORLD]; };
+__device__ __forceinline__ u32 xcap(const TickParams& p) { return XTOTAL / (p.world - 1); }
+__device__ __forceinline__ u32 xseg(const TickParams& p, u32 shard) { return (shard < p.rank ? shard : shard - 1) * xcap(p); }
 
 template <bool SHARDED>
 __device__ __forceinline__ void deliver(const TickParams& p, XStage* xs, u32* plane, u32 dst, u32 kind, u32 s, u32 val1, u64 pol_last, bool mark) {
@@ -132,9 +134,16 @@ __device__ __forceinline__ void deliver(const TickParams& p, XStage* xs, u32* pl
     const u32 shard = dst / p.shard_size;
     const u32 dloc = dst - shard * p.shard_size;
     const u64 e = ((u64)val1 << 32) | ((u64)s << 28) | ((u64)kind << 26) | dloc;
-    const u32 pos = atomicAdd(&xs->cnt[shard], 1u);
-    if (pos < XCAP) {
-      xs->buf[shard][pos] = e;
+    // warp-aggregated append: the lanes of this call that target the same shard reserve their slots with ONE
+    // shared-memory atomic (a per-message atomic on the same counter serialises the whole tile)
+    const u32 peers = __match_any_sync(__activemask(), shard);
+    const u32 lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    u32 base = 0;
+    if (lane == leader) base = atomicAdd(&xs->cnt[shard], (u32)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const u32 pos = base + (u32)__popc(peers & ((1u << lane) - 1u));
+    if (pos < xcap(p)) {
+      xs->buf[xseg(p, shard) + pos] = e;
     } else {                                   // stage full: write this one straight through
       const u32 g = atomicAdd(p.send_count + shard, 1u);
       if (g < p.win_cap) p.win_data[shard][(size_t)p.rank * p.win_cap + g] = e;
@@ -144,26 +153,28 @@ __device__ __forceinline__ void deliver(const TickParams& p, XStage* xs, u32* pl
 }
 
 // Flush the staged cross-shard entries of a tile (whole CTA).
-__device__ __forceinline__ void flush_xstage(const TickParams& p, XStage* xs) {
+__device__ __forceinline__ bool flush_xstage(const TickParams& p, XStage* xs) {
   __syncthreads();
-  if (threadIdx.x < p.world) {
-    const u32 n = min(xs->cnt[threadIdx.x], XCAP);
+  if (threadIdx.x < p.world && threadIdx.x != p.rank) {
+    const u32 n = min(xs->cnt[threadIdx.x], xcap(p));
     xs->base[threadIdx.x] = n ? atomicAdd(p.send_count + threadIdx.x, n) : 0u;
   }
   __syncthreads();
   bool wrote = false;
   for (u32 sh = 0; sh < p.world; ++sh) {
-    const u32 n = min(xs->cnt[sh], XCAP), base = xs->base[sh];
+    if (sh == p.rank) continue;
+    const u32 n = min(xs->cnt[sh], xcap(p)), base = xs->base[sh];
+    const u64* src = xs->buf + xseg(p, sh);
     u64* dst = p.win_data[sh] + (size_t)p.rank * p.win_cap;
     for (u32 i = threadIdx.x; i < n; i += BLOCK) {
-      if (base + i < p.win_cap) { dst[base + i] = xs->buf[sh][i]; wrote = true; }
+      if (base + i < p.win_cap) { dst[base + i] = src[i]; wrote = true; }
       else *p.overflow = 2;
     }
   }
-  if (wrote) __threadfence_system();           // the entries are visible to the peer before the publish kernel raises the flag
   __syncthreads();
   if (threadIdx.x < MAX_WORLD) xs->cnt[threadIdx.x] = 0;
   __syncthreads();
+  return wrote;
 }
 
 __device__ __forceinline__ void unpack_words(const Words& x, Rec& r) {
@@ -423,6 +434,7 @@ __global__ void __launch_bounds__(BLOCK, 4) tick_kernel(const __grid_constant__ 
   const u64 pol_first = policy_evict_first(), pol_last = policy_evict_last();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (SHARDED && threadIdx.x < MAX_WORLD) xs->cnt[threadIdx.x] = 0;
+  bool wrote_remote = false;
 
   // Dense / sparse ticks.  While the gossip front is wide (the previous tick sent at least one message per
   // two tiles) every tile will be hot anyway: senders skip the per-message tile marking and the next tick
@@ -448,8 +460,9 @@ __global__ void __launch_bounds__(BLOCK, 4) tick_kernel(const __grid_constant__ 
     bool pend = false;
     if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, kL, kJ, kM, mark, pol_first, pol_last, c);
     if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + i] = 1;
-    if (SHARDED) flush_xstage(p, xs);
+    if (SHARDED) wrote_remote |= flush_xstage(p, xs);
   }
+  if (SHARDED && wrote_remote) __threadfence_system();   // peer-window stores are performed before the publish kernel raises the flags
   // block reduction (warp shuffles, then shared memory) → one atomic per counter per CTA.
   // trace row: 0 packets, 1 edge_updates, 2 messages, 3 changed, 4 pending, (5 events, 6 suspects: direct), 7 hash
   const u64 vals[8] = {c.packets, c.edges, (u64)c.kL + c.kJ + c.kM, c.changed, c.pending, c.kL, c.kJ, c.kM};
@@ -611,6 +624,11 @@ __global__ void __launch_bounds__(BLOCK) drain_kernel(const __grid_constant__ Dr
     do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(p.ctrl + 8 + threadIdx.x) : "memory"); } while (f != p.stamp);
   }
   __syncthreads();
+  // same dense / sparse decision as the tick kernel of this tick: in a dense tick the next tick processes every
+  // tile anyway, so per-entry tile marking (millions of byte stores onto a few thousand flags) is skipped
+  const u32 prev_msgs = p.kinds_prev[KIND_LEAVE] + p.kinds_prev[KIND_JOIN] + p.kinds_prev[KIND_ML];
+  const bool mark = prev_msgs < (p.n_tiles >> 1) + 1;
+  u32 seen = 0;                                 // kinds this thread folded (bit per kind)
   for (u32 src = 0; src < p.world; ++src) {
     if (src == p.rank) continue;
     const u32 n = min(p.ctrl[src], p.win_cap);
@@ -620,10 +638,16 @@ __global__ void __launch_bounds__(BLOCK) drain_kernel(const __grid_constant__ Dr
       const u32 val1 = (u32)(e >> 32), s = (u32)(e >> 28) & 15, kind = (u32)(e >> 26) & 3, dl = (u32)e & ((1u << 26) - 1);
       if (dl < p.n_local && s < p.R && kind < 3) {
         atomicMax(p.inbox_wr + ((size_t)(kind * p.R + s)) * p.stride + dl, val1);
-        if (p.hot_wr[dl >> TILE_SHIFT] == 0) p.hot_wr[dl >> TILE_SHIFT] = 1;
+        if (mark) p.hot_wr[dl >> TILE_SHIFT] = 1;
+        seen |= 1u << kind;
       }
       else *p.overflow = 3;
     }
+  }
+  // received kinds count as "in flight" for the next tick's plane skipping; the received volume feeds its dense/sparse decision
+  seen = __reduce_or_sync(0xffffffffu, seen);
+  if ((threadIdx.x & 31) == 0 && seen) {
+    for (u32 k = 0; k < 3; ++k) if ((seen >> k) & 1) atomicAdd(p.kinds_cur + k, 1u);
   }
 }
 
@@ -766,7 +790,7 @@ void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st) {
   if (trace) { if (small) launch_tick_v<true, 4>(p, grid, st); else launch_tick_v<true, 8>(p, grid, st); }
   else { if (small) launch_tick_v<false, 4>(p, grid, st); else launch_tick_v<false, 8>(p, grid, st); }
 }
-void launch_drain(const DrainParams& p, cudaStream_t st) { drain_kernel<<<148 * 2, BLOCK, 0, st>>>(p); }
+void launch_drain(const DrainParams& p, cudaStream_t st) { drain_kernel<<<148 * 8, BLOCK, 0, st>>>(p); }
 void launch_publish(const PublishParams& p, cudaStream_t st) { publish_kernel<<<1, 32, 0, st>>>(p); }
 void launch_init_state(uint4* rec, u64* node_state, u32 n_local, u32 stride, u32 R, u32 init_st, u32 init_clock, cudaStream_t st) {
   init_state_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(rec, node_state, n_local, stride, R, init_st, init_clock);

@@ -45,7 +45,10 @@ def _run(world, scen_args, tmp_path):
     return [np.load(os.path.join(str(tmp_path), f"r{r}.npz")) for r in range(world)]
 
 
-@pytest.mark.parametrize("world", [2, 4])
+WORLDS = [int(x) for x in os.environ.get("SERFSIM_TEST_WORLDS", "2,4").split(",")]
+
+
+@pytest.mark.parametrize("world", WORLDS)
 @pytest.mark.parametrize("scen", [
     ("random_graph_leave", dict(n=50_000, degree=16, fanout=3, seed=2, slots=1), {}),
     ("random_graph_leave", dict(n=30_001, degree=12, fanout=4, seed=3, slots=3), {}),
