@@ -45,16 +45,20 @@ def config_dict(args, sc):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md recipe).  nvidia-smi needs ~1 s to start, so it is
+    launched before the warm-up; samples are time-stamped and only those inside [mark_begin, mark_end] — the timed
+    regions — are summarised (all samples under load if the window caught none)."""
+
+    QUERY = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -62,24 +66,38 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+
+        def summarise(rows):
+            sm, mx, reasons = [], [], set()
+            for _, r in rows:
+                try:
+                    sm.append(float(r[1])); mx.append(float(r[2]))
+                except (ValueError, IndexError):
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+        inside = [x for x in self.rows if self.t0 is not None and self.t0 <= x[0] <= (self.t1 or 1e30)]
+        window = "timed regions"
+        if not inside:
+            inside, window = self.rows, "warm-up + timed regions (no sample fell inside the timed window)"
+        sm, mx, reasons = summarise(inside)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def b_edge(fanout, p_dirty):
@@ -115,7 +133,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    nodes = args.ref_nodes
+    nodes = args.ref_nodes or (args.nodes if (os.cpu_count() or 1) >= 32 else 1_000_000)
     vals, last = [], None
     for i in range(args.warmup + args.steps):
         r = time_oracle(args, nodes)
@@ -146,7 +164,7 @@ def workload_stub(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nodes", type=int, default=10_000_000)
@@ -154,7 +172,7 @@ def main():
     ap.add_argument("--fanout", type=int, default=4)
     ap.add_argument("--slots", type=int, default=1)
     ap.add_argument("--waves", type=int, default=1)
-    ap.add_argument("--ref-nodes", type=int, default=1_000_000, help="size of the bounded CPU sample")
+    ap.add_argument("--ref-nodes", type=int, default=0, help="size of the bounded CPU sample (0: 1 M nodes inside the b200 arm; the reference arm uses the full workload on hosts with >= 32 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -206,14 +224,18 @@ def main():
             out_bytes += g.lamport_time(out=pin_clock.numpy().view(np.uint64)).nbytes
         return ticks, ok, ms, launches, out_bytes
 
-    for _ in range(args.warmup):
-        one_step(False)
-
-    # ---- device-timed region: K steps ----
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        one_step(False)
+    time.sleep(1.2)                                      # let nvidia-smi come up before the timed regions (all ranks: steps are collective)
+    for _ in range(2):
+        one_step(False)
+
+    # ---- device-timed region: K steps ----
     sync_all()
+    sampler.mark_begin()
     dev_ms, launches, ticks_list = 0.0, 0, []
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -221,7 +243,6 @@ def main():
         dev_ms += ms; launches += nl; ticks_list.append(ticks)
     sync_all()
     wall_dev = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
     st = g.stats()                                       # global sums (all ranks) of the LAST step
     eu_per_step, changed = st["edge_updates"], st["changed"]
 
@@ -234,6 +255,8 @@ def main():
         d2h = ob
     sync_all()
     wall_e2e = time.perf_counter() - t0
+    sampler.mark_end()
+    clocks = sampler.stop() if rank == 0 else None
 
     t = torch.tensor([dev_ms, wall_e2e, wall_dev], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -250,7 +273,11 @@ def main():
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
-        tick_launches = sum(t + 1 for t in ticks_list)
+        tick_launches = launches                       # every kernel this library launched in the timed region (tick kernels ≥ 98 % of them)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if world == 1 and os.path.exists(tpath):       # DRAM bytes per tick launch of this workload from the committed ncu capture
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         # per-GPU: each GPU runs its own tick kernel over its shard; algorithmic bytes split evenly
         achieved = (total_eu / world) * be / (dev_ms * 1e-3) / 1e9
         h2d = len(sc.ops) * 12
@@ -259,13 +286,14 @@ def main():
                 "dtype": "u32", "data": "synthetic", "config": config_dict(args, sc),
                 "ticks_to_convergence": ticks_list[-1], "edge_updates_per_step": eu_per_step, "p_dirty": p_dirty,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "kernel": "tick_kernel", "bytes_per_edge_update": be,
+                             "traffic": traffic, "traffic_source": "profiles/r1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per tick launch)" if traffic else None,
+                             "algorithmic_bytes_per_launch": total_eu * be / world / max(1, tick_launches), "peak_source": peak_src, "kernel": "tick_kernel", "bytes_per_edge_update": be,
                              "launches": tick_launches, "avg_launch_us": 1e3 * dev_ms / max(1, tick_launches)},
                 "e2e": {"value": total_eu / wall_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": 1e3 * wall_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clocks}
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = {k: v for k, v in time_oracle(args, args.ref_nodes).items() if k not in ("seconds", "ticks")}
+            line["cpu_baseline"] = {k: v for k, v in time_oracle(args, args.ref_nodes or 1_000_000).items() if k not in ("seconds", "ticks")}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -660,26 +660,33 @@ struct TickSim {
         // ---------------- Phase R: receive / state merge ----------------
         if (up_r) {
           const View before = r;
-          std::vector<Msg> ml, lv, jn;
-          for (u32 i = head[v - v0]; i < head[v - v0 + 1]; ++i) {
-            const Msg& m = byd[i];
-            if (m.slot != s) continue;
-            (m.kind == 2 ? ml : m.kind == 0 ? lv : jn).push_back(m);
-          }
+          // this node's mail for slot s, in canonical order: memberlist messages, then leave intents ascending
+          // (ltime, src), then join intents ascending — sorted once per node (first slot), then walked per slot
+          if (s == 0 && head[v - v0 + 1] - head[v - v0] > 1)
+            std::sort(byd.begin() + head[v - v0], byd.begin() + head[v - v0 + 1], [](const Msg& a, const Msg& b) {
+              if (a.slot != b.slot) return a.slot < b.slot;
+              const int ka = a.kind == 2 ? 0 : a.kind == 0 ? 1 : 2, kb = b.kind == 2 ? 0 : b.kind == 0 ? 1 : 2;
+              if (ka != kb) return ka < kb;
+              return a.val != b.val ? a.val < b.val : a.src < b.src;
+            });
+          u32 i0 = head[v - v0];
+          const u32 i1 = head[v - v0 + 1];
+          while (i0 < i1 && byd[i0].slot < s) ++i0;
           // memberlist: only the greatest (incarnation, kind, from) message is delivered per tick (rule ML-1)
-          if (!ml.empty()) {
-            u32 key = 0; for (auto& m : ml) key = std::max(key, m.val);
-            u32 inc = key >> 6, kind = (key >> 4) & 3, fromh = key & 15;
-            if (kind == ML_ALIVE) v_ml_alive(r, inc, self, cx);
-            else if (kind == ML_SUSPECT) v_ml_suspect(r, inc, fromh, t, self, cx);
-            else v_ml_dead(r, inc, kind == ML_LEFT, t, self, cx);
+          {
+            u32 key = 0; bool any = false;
+            for (; i0 < i1 && byd[i0].slot == s && byd[i0].kind == 2; ++i0) { key = std::max(key, byd[i0].val); any = true; }
+            if (any) {
+              u32 inc = key >> 6, kind = (key >> 4) & 3, fromh = key & 15;
+              if (kind == ML_ALIVE) v_ml_alive(r, inc, self, cx);
+              else if (kind == ML_SUSPECT) v_ml_suspect(r, inc, fromh, t, self, cx);
+              else v_ml_dead(r, inc, kind == ML_LEFT, t, self, cx);
+            }
           }
-          // serf intents, one at a time: leaves ascending (ltime, src), then joins ascending
-          auto by_lt = [](const Msg& a, const Msg& b) { return a.val != b.val ? a.val < b.val : a.src < b.src; };
-          std::sort(lv.begin(), lv.end(), by_lt); std::sort(jn.begin(), jn.end(), by_lt);
+          // serf intents, one message at a time
           bool refute = false;
-          for (auto& m : lv) { witness32(nd.clock, m.val); v_leave_intent(r, m.val, self, nd.sstate, &refute, cx); }
-          for (auto& m : jn) { witness32(nd.clock, m.val); v_join_intent(r, m.val, cx); }
+          for (; i0 < i1 && byd[i0].slot == s && byd[i0].kind == 0; ++i0) { witness32(nd.clock, byd[i0].val); v_leave_intent(r, byd[i0].val, self, nd.sstate, &refute, cx); }
+          for (; i0 < i1 && byd[i0].slot == s && byd[i0].kind == 1; ++i0) { witness32(nd.clock, byd[i0].val); v_join_intent(r, byd[i0].val, cx); }
           if (refute) {                                   // base.rs:1470-1480 → broadcast_join(clock.time()), base.rs:381-397
             u32 T = nd.clock; witness32(nd.clock, T);
             v_join_intent(r, T, cx);
