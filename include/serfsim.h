@@ -93,7 +93,7 @@ typedef struct serfsim_config {
   int32_t  device;                    /* CUDA ordinal (-1 = current)                                 */
   int32_t  rank;                      /* shard index of this process (0 when world_size == 1)        */
   int32_t  world_size;                /* number of shards (one process per GPU)                      */
-  int32_t  reserved;
+  int32_t  push_pull_interval_ticks;  /* memberlist push_pull_interval in ticks (LAN 30 s = 150, times pushPullScale(n)); 0 = no anti-entropy rounds */
 } serfsim_config_t;
 
 /* ---- Stats — mirrors `serf/api.rs:588-602` (members/failed/left/member_time/intent_queue)

@@ -37,6 +37,7 @@
 #include <string>
 #include <thread>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "../include/serfsim.h"   // config / stats / trace-row struct layouts and constants only
@@ -123,7 +124,7 @@ static inline void philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, u32 k0, u32 k1,
 }
 static inline u32 mulhi32(u32 a, u32 b) { return (u32)(((u64)a * b) >> 32); }
 
-enum : u32 { DOMAIN_GOSSIP = 0, DOMAIN_PROBE = 1 };
+enum : u32 { DOMAIN_GOSSIP = 0, DOMAIN_PROBE = 1, DOMAIN_PUSHPULL = 2 };
 
 static inline u64 mix64(u64 x) {   // splitmix64 finaliser
   x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL;
@@ -443,7 +444,7 @@ struct RuleCtx {            // per-run constants
 static inline void witness32(u32& c, u32 t) { if (t < c) return; c = t + 1; }   // clock.rs:155-172 on the device-width clock
 
 // --- serf-layer rules on a view (same statements as RefNode, on the packed record) ------
-static bool v_join_intent(View& r, u32 lt, const RuleCtx& cx) {            // base.rs:1338-1373 (witness done by caller)
+static bool v_join_intent(View& r, u32 lt, const RuleCtx& cx, bool requeue = true) {            // base.rs:1338-1373 (witness done by caller)
   bool acc;
   if (known(r)) {
     if (lt <= r.st) return false;
@@ -453,10 +454,10 @@ static bool v_join_intent(View& r, u32 lt, const RuleCtx& cx) {            // ba
   } else {                                                                   // upsert_intent, base.rs:1838-1866
     if (r.status == TY_NONE || lt > r.st) { r.status = TY_JOIN; r.st = lt; acc = true; } else acc = false;
   }
-  if (acc) { r.qjoin = lt; r.txj = (u8)cx.limit; }                           // serf/delegate.rs:294-300 re-queue
+  if (acc && requeue) { r.qjoin = lt; r.txj = (u8)cx.limit; }                // serf/delegate.rs:294-300 re-queue (push-pull discards the result, :495-523)
   return acc;
 }
-static bool v_leave_intent(View& r, u32 lt, bool self, u8 sstate, bool* refute, const RuleCtx& cx) {   // base.rs:1442-1572
+static bool v_leave_intent(View& r, u32 lt, bool self, u8 sstate, bool* refute, const RuleCtx& cx, bool requeue = true) {   // base.rs:1442-1572
   bool acc;
   if (!known(r)) {
     if (r.status == TY_NONE || lt > r.st) { r.status = TY_LEAVE; r.st = lt; acc = true; } else acc = false;
@@ -472,7 +473,7 @@ static bool v_leave_intent(View& r, u32 lt, bool self, u8 sstate, bool* refute, 
       default: r.status = ST_LEAVING; acc = true; break;
     }
   }
-  if (acc) { r.qleave = lt; r.txl = (u8)cx.limit; }
+  if (acc && requeue) { r.qleave = lt; r.txl = (u8)cx.limit; }
   return acc;
 }
 static void v_node_join(View& r) {                                           // base.rs:1206-1334
@@ -543,6 +544,9 @@ struct TickSim {
   std::vector<View> rec;        // [R][N]
   std::vector<NodeB> node;
   std::vector<EventB> events;   // sorted by (tick, insertion)
+  std::unordered_set<u64> event_keys;
+  std::unordered_map<u32, std::vector<EventB>> ev_by_tick;
+  u32 max_event_tick = 0; bool any_event = false;
   std::vector<u32> timeout; RuleCtx cx;
   std::vector<serfsim_tick_row_t> trace;
   std::vector<u8> subj_up;      // ground truth per slot
@@ -562,7 +566,7 @@ struct TickSim {
     cx.timeout = timeout.data();
   }
   void reset(u64 seed) {
-    cfg.seed = seed; tick = 0; events.clear(); trace.clear(); mail.clear(); tot_events = 0;
+    cfg.seed = seed; tick = 0; events.clear(); event_keys.clear(); ev_by_tick.clear(); any_event = false; max_event_tick = 0; trace.clear(); mail.clear(); tot_events = 0;
     chunk = (N + threads - 1) / threads;
     rec.assign((size_t)R * N, View{});
     node.assign(N, NodeB{cfg.init_clock, 1, SS_ALIVE});
@@ -620,7 +624,7 @@ struct TickSim {
     // events of this tick
     std::vector<EventB> evs;
     std::unordered_map<u32, EventB> ev_of;
-    for (auto& e : events) if (e.tick == t) { evs.push_back(e); ev_of[e.node] = e; }
+    { auto it = ev_by_tick.find(t); if (it != ev_by_tick.end()) for (auto& e : it->second) { evs.push_back(e); ev_of[e.node] = e; } }
     // ground truth after this tick's operations (what a failed probe observes)
     for (auto& e : evs) {
       int s = slot_of(e.node);
@@ -765,6 +769,57 @@ struct TickSim {
     if (T == 1) work(0);
     else { std::vector<std::thread> th; for (u32 c = 0; c < T; ++c) th.emplace_back(work, c); for (auto& x : th) x.join(); }
     mail.swap(next);
+    // ---------------- anti-entropy round: memberlist push-pull + SerfDelegate::merge_remote_state ----------------
+    // (serf/delegate.rs:386-554; memberlist mergeState [external]).  Every push_pull_interval ticks each up node
+    // pulls the end-of-tick state of ONE random neighbour and merges it: clock witness(ltime-1); per subject the
+    // memberlist state (alive → aliveNode, suspect/dead → suspectNode{from = self}, left → deadNode{from = node}),
+    // then serf's view: a Left member → leave intent at status_ltime + 1, any other known member → join intent
+    // at status_ltime — results discarded, i.e. nothing is re-queued (delegate.rs:495-523).
+    const u32 pp = (u32)std::max(0, cfg.push_pull_interval_ticks);
+    if (pp && (t + 1) % pp == 0) {
+      const std::vector<View> srec = rec;
+      const std::vector<NodeB> snode = node;
+      auto ppwork = [&](u32 c) {
+        serfsim_tick_row_t& row = rows[c];
+        const u32 v0 = c * chunk, v1 = std::min<u64>(N, (u64)(c + 1) * chunk);
+        for (u32 v = v0; v < v1; ++v) {
+          NodeB& nd = node[v];
+          if (!snode[v].up) continue;
+          const u64 r0 = row_ptr[v]; const u32 deg = (u32)(row_ptr[v + 1] - r0);
+          if (!deg) continue;
+          u32 w[4]; philox4x32_10(t, v, 0, DOMAIN_PUSHPULL, (u32)cfg.seed, (u32)(cfg.seed >> 32), w);
+          const u32 u = col[r0 + ((draw16(w, 0) * deg) >> 16)];
+          if (u == v || !snode[u].up) continue;
+          if (snode[u].clock > 0) witness32(nd.clock, snode[u].clock - 1);            // delegate.rs:466-468
+          for (u32 s = 0; s < R; ++s) {
+            View& r = at(s, v);
+            const View before = r;
+            const View& q = srec[(size_t)s * N + u];
+            const bool self = (subj[s] == v);
+            const bool was_pending = (r.txl | r.txj | r.txm) || ml_state(r) == ML_SUSPECT ||
+                                     (cfg.probe_interval_ticks && !subj_up[s] && !self && ml_state(r) == ML_ALIVE);
+            if (known(q)) {
+              const u8 qs = ml_state(q);
+              if (qs == ML_ALIVE) v_ml_alive(r, q.inc, self, cx);
+              else if (qs == ML_LEFT) v_ml_dead(r, q.inc, true, t, self, cx);
+              else v_ml_suspect(r, q.inc, from_hash(v), t, self, cx);
+              bool refute = false;
+              if (q.status == ST_LEFT) { witness32(nd.clock, q.st + 1); v_leave_intent(r, q.st + 1, self, nd.sstate, &refute, cx, false); }
+              else { witness32(nd.clock, q.st); v_join_intent(r, q.st, cx, false); }
+              if (refute) { u32 T2 = nd.clock; witness32(nd.clock, T2); v_join_intent(r, T2, cx); r.qjoin = T2; r.txj = (u8)cx.limit; }
+            }
+            { View a = before, b = r; a.st = b.st = 0;       // status_time creeps by design (leave at status_ltime + 1): not a change
+              if (memcmp(&a, &b, sizeof(View)) != 0) row.changed++; }
+            const bool now_pending = (r.txl | r.txj | r.txm) || ml_state(r) == ML_SUSPECT ||
+                                     (cfg.probe_interval_ticks && !subj_up[s] && !self && ml_state(r) == ML_ALIVE);
+            if (now_pending && !was_pending) row.pending++;
+            if (!now_pending && was_pending) row.pending--;
+          }
+        }
+      };
+      if (T == 1) ppwork(0);
+      else { std::vector<std::thread> th; for (u32 c = 0; c < T; ++c) th.emplace_back(ppwork, c); for (auto& x : th) x.join(); }
+    }
     serfsim_tick_row_t row{};
     for (auto& r : rows) { row.packets += r.packets; row.edge_updates += r.edge_updates; row.messages += r.messages; row.changed += r.changed;
                            row.pending += r.pending; row.events += r.events; row.suspects += r.suspects; }
@@ -788,7 +843,7 @@ struct TickSim {
     }
     return h;
   }
-  bool future_events() const { for (auto& e : events) if (e.tick >= tick) return true; return false; }
+  bool future_events() const { return any_event && max_event_tick >= tick; }
 };
 
 // =====================================================================================
@@ -890,8 +945,10 @@ ORC int oracle_sim_inject(void* p, u32 tick, u32 op, u32 node, u32 slot) {
   if (tick < s->tick || node >= s->N || op < 1 || op > 5) { g_err = "bad inject"; return SERFSIM_E_INVAL; }
   if (op == SERFSIM_OP_FORCE_LEAVE) { if (slot >= s->R) return SERFSIM_E_INVAL; }
   else if ((op == SERFSIM_OP_JOIN || op == SERFSIM_OP_LEAVE) && s->slot_of(node) < 0) { g_err = "join/leave origin must be a tracked subject"; return SERFSIM_E_INVAL; }
-  for (auto& e : s->events) if (e.tick == tick && e.node == node) { g_err = "one operation per node per tick"; return SERFSIM_E_INVAL; }
-  s->events.push_back(EventB{tick, op, node, slot}); return 0;
+  if (!s->event_keys.insert(((u64)tick << 32) | node).second) { g_err = "one operation per node per tick"; return SERFSIM_E_INVAL; }
+  s->events.push_back(EventB{tick, op, node, slot}); s->ev_by_tick[tick].push_back(EventB{tick, op, node, slot});
+  s->max_event_tick = s->any_event ? std::max(s->max_event_tick, tick) : tick; s->any_event = true;
+  return 0;
 }
 ORC int oracle_sim_step(void* p, u32 n) { auto* s = (TickSim*)p; if (s->row_ptr.empty()) { g_err = "no topology"; return SERFSIM_E_INVAL; } for (u32 i = 0; i < n; ++i) s->step_one(); return 0; }
 ORC int oracle_sim_run_until_converged(void* p, u32 max_ticks, u32* ticks_out) {
@@ -899,7 +956,12 @@ ORC int oracle_sim_run_until_converged(void* p, u32 max_ticks, u32* ticks_out) {
   for (u32 i = 0; i < max_ticks; ++i) {
     s->step_one();
     auto& r = s->trace.back();
-    if (r.pending == 0 && r.edge_updates == 0 && !s->future_events()) { if (ticks_out) *ticks_out = s->tick - 1; return 0; }
+    const u32 pp = (u32)std::max(0, s->cfg.push_pull_interval_ticks);
+    // with anti-entropy on, convergence additionally needs a push-pull round that changed nothing but Lamport
+    // times (status_time keeps creeping: the reference re-sends a Left member as "leave at status_ltime + 1",
+    // serf/delegate.rs:495-510, so the round's `changed` counter ignores status_time)
+    const bool pp_ok = !pp || ((s->tick % pp) == 0 && r.changed == 0);
+    if (r.pending == 0 && r.edge_updates == 0 && !s->future_events() && pp_ok) { if (ticks_out) *ticks_out = s->tick - 1; return 0; }
   }
   if (ticks_out) *ticks_out = s->tick;
   return 1;

@@ -38,7 +38,7 @@ enum : u32 { TY_NONE = 0, TY_LEAVE = 1, TY_JOIN = 2 };                          
 enum : u32 { ML_ALIVE = 0, ML_SUSPECT = 1, ML_DEAD = 2, ML_LEFT = 3 };
 enum : u32 { SS_ALIVE = 0, SS_LEAVING = 1, SS_LEFT = 2 };                                // SerfState
 enum : u32 { OP_JOIN = 1, OP_LEAVE = 2, OP_FORCE_LEAVE = 3, OP_FAIL = 4, OP_REJOIN = 5 };
-enum : u32 { DOMAIN_GOSSIP = 0, DOMAIN_PROBE = 1 };
+enum : u32 { DOMAIN_GOSSIP = 0, DOMAIN_PROBE = 1, DOMAIN_PUSHPULL = 2 };
 enum : u32 { KIND_LEAVE = 0, KIND_JOIN = 1, KIND_ML = 2 };
 
 constexpr u32 MAX_SLOTS = 16;
@@ -47,9 +47,8 @@ constexpr u32 MAX_K = 7;            // suspicion_mult - 2
 constexpr u32 LTIME_LIMIT = 0xFFFFFFF0u;
 constexpr u32 INC_LIMIT = (1u << 26) - 16;
 
-// node_state word: bits 0-31 LamportClock (types/clock.rs:125), 32 up, 40-41 SerfState, 48 op-pending
+// node_state word: bits 0-31 LamportClock (types/clock.rs:125), 32 up, 40-41 SerfState
 constexpr u64 NS_UP = 1ull << 32;
-constexpr u64 NS_EV = 1ull << 48;
 
 struct Rec {
   u32 st, qjoin, qleave, inc, deadline, leave_tick;
@@ -82,7 +81,7 @@ __host__ __device__ inline void witness(u32& c, u32 t) { if (t >= c) c = t + 1; 
 __host__ __device__ inline u32 from_bucket(u32 node) { return (node * 0x9E3779B1u) >> 28; }
 
 // handle_node_join_intent — serf/base.rs:1338-1373 (witness by the caller); re-queue = serf/delegate.rs:294-300
-__host__ __device__ inline void join_intent(Rec& r, u32 lt, u32 limit) {
+__host__ __device__ inline void join_intent(Rec& r, u32 lt, u32 limit, bool requeue = true) {
   bool acc;
   if (r.flags & 1) {
     if (lt <= r.st) return;                               // :1346
@@ -93,11 +92,11 @@ __host__ __device__ inline void join_intent(Rec& r, u32 lt, u32 limit) {
     acc = (r.status == TY_NONE) || (lt > r.st);
     if (acc) { r.status = TY_JOIN; r.st = lt; }
   }
-  if (acc) { r.qjoin = lt; r.txj = limit; }
+  if (acc && requeue) { r.qjoin = lt; r.txj = limit; }   // push-pull discards the handler's result (serf/delegate.rs:495-523)
 }
 
 // handle_node_leave_intent — serf/base.rs:1442-1572
-__host__ __device__ inline void leave_intent(Rec& r, u32 lt, bool self, u32 sstate, bool& refute, u32 limit) {
+__host__ __device__ inline void leave_intent(Rec& r, u32 lt, bool self, u32 sstate, bool& refute, u32 limit, bool requeue = true) {
   bool acc;
   if (!(r.flags & 1)) {                                   // :1450-1458
     acc = (r.status == TY_NONE) || (lt > r.st);
@@ -114,7 +113,7 @@ __host__ __device__ inline void leave_intent(Rec& r, u32 lt, bool self, u32 ssta
       default: r.status = ST_LEAVING; acc = true; break;          // :1560-1570
     }
   }
-  if (acc) { r.qleave = lt; r.txl = limit; }
+  if (acc && requeue) { r.qleave = lt; r.txl = limit; }
 }
 
 // handle_node_join — serf/base.rs:1206-1334

@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/serfsim.h"
@@ -80,6 +81,9 @@ struct serfsim {
   uint4* d_rec = nullptr;          // [R][count] × 32 B
   u32* d_inbox[2] = {nullptr, nullptr};   // [3][R][count]
   u64* d_node = nullptr;           // [count]
+  u8* d_busy = nullptr;            // [stride] per-node busy byte
+  uint4* d_snap_rec = nullptr;     // push-pull rounds: end-of-tick snapshot of the records …
+  u64* d_snap_node = nullptr;      // … and of the node words
   u8* d_hot[2] = {nullptr, nullptr};      // [n_tiles] per tick parity
   u32 n_tiles = 0;
   u32* d_rowptr = nullptr;         // [count+1]
@@ -96,6 +100,7 @@ struct serfsim {
   void* d_stage = nullptr;         // getter staging, count × 8 B
   // host state
   std::vector<HostOp> ops;         // sorted by (tick, seq)
+  std::unordered_set<u64> op_keys; // (tick << 32 | node): at most one operation per node per tick
   bool ops_dirty = false;
   u64 op_seq = 0;
   std::vector<u32> subj;
@@ -204,7 +209,7 @@ int launch_ticks(serfsim* h, u32 n) {
       const int s = slot_of(h, it->node);
       if (s >= 0) { if (it->op == SERFSIM_OP_FAIL) h->up_mask &= ~(1u << s); if (it->op == SERFSIM_OP_REJOIN) h->up_mask |= (1u << s); }
     }
-    if (ee > eb) { launch_mark_events(h->d_node, h->d_hot[(t & 1) ^ 1], h->d_ev_node, eb, ee, h->first, h->count, h->stream); h->last_launches++; }
+    if (ee > eb) { launch_mark_events(h->d_busy, h->d_hot[(t & 1) ^ 1], h->d_ev_node, eb, ee, h->first, h->count, h->stream); h->last_launches++; }
     TickParams p{};
     p.n_local = h->count; p.first = h->first; p.n_global = h->N; p.R = h->R;
     p.fanout = h->cfg.fanout; p.probe_every = h->cfg.probe_interval_ticks; p.tick = t;
@@ -213,7 +218,7 @@ int launch_ticks(serfsim* h, u32 n) {
     p.rules = h->rules;
     for (u32 s = 0; s < h->R; ++s) p.subj[s] = h->subj[s];
     p.rec = h->d_rec; p.inbox_rd = h->d_inbox[(t & 1) ^ 1]; p.inbox_wr = h->d_inbox[t & 1];
-    p.node_state = h->d_node; p.row_ptr = h->d_rowptr; p.col = h->d_col;
+    p.node_state = h->d_node; p.busy = h->d_busy; p.row_ptr = h->d_rowptr; p.col = h->d_col;
     p.ev_node = h->d_ev_node; p.ev_op = h->d_ev_op; p.ev_slot = h->d_ev_slot;
     p.row = h->d_trace + (size_t)t * 8;
     p.kinds_prev = h->d_kinds + (size_t)t * 4;
@@ -259,6 +264,16 @@ int launch_ticks(serfsim* h, u32 n) {
       launch_drain(d, h->stream);
       h->last_launches += 2;
       h->xepoch++;
+    }
+    const u32 pp = (u32)std::max(0, h->cfg.push_pull_interval_ticks);
+    if (pp && (t + 1) % pp == 0) {
+      // anti-entropy round on a snapshot of the end-of-tick state (only this node's own records are written)
+      const size_t rb = (size_t)h->R * h->stride * 32, nb = (size_t)h->stride * 8;
+      if (!h->d_snap_rec) { CU(cudaMalloc(&h->d_snap_rec, rb)); CU(cudaMalloc(&h->d_snap_node, nb)); }
+      CU(cudaMemcpyAsync(h->d_snap_rec, h->d_rec, rb, cudaMemcpyDeviceToDevice, h->stream));
+      CU(cudaMemcpyAsync(h->d_snap_node, h->d_node, nb, cudaMemcpyDeviceToDevice, h->stream));
+      launch_pushpull(p, h->d_snap_rec, h->d_snap_node, h->cfg.trace != 0, h->stream);
+      h->last_launches++;
     }
     if (h->tick_timing) CU(cudaEventRecord(h->tick_ev[2 * (size_t)t + 1], h->stream));
     h->tick++;
@@ -320,7 +335,7 @@ int fire_events(serfsim* h) {
 }
 
 int do_reset(serfsim* h, u64 seed) {
-  h->cfg.seed = seed; h->tick = 0; h->ops.clear(); h->ops_dirty = false; h->rows.clear();
+  h->cfg.seed = seed; h->tick = 0; h->ops.clear(); h->op_keys.clear(); h->ops_dirty = false; h->rows.clear();
   h->up_mask = (h->R >= 32) ? 0xffffffffu : ((1u << h->R) - 1);
   h->reported.assign(h->R, (u8)ST_ALIVE);
   const size_t inbox_bytes = (size_t)3 * h->R * h->stride * sizeof(u32);
@@ -328,6 +343,7 @@ int do_reset(serfsim* h, u64 seed) {
   CU(cudaMemsetAsync(h->d_inbox[0], 0, inbox_bytes, h->stream));
   CU(cudaMemsetAsync(h->d_inbox[1], 0, inbox_bytes, h->stream));
   CU(cudaMemsetAsync(h->d_overflow, 0, 4, h->stream));
+  CU(cudaMemsetAsync(h->d_busy, 0, h->stride, h->stream));
   CU(cudaMemsetAsync(h->d_hot[0], 0, h->n_tiles, h->stream));
   CU(cudaMemsetAsync(h->d_hot[1], 0, h->n_tiles, h->stream));
   if (h->d_trace) {
@@ -342,7 +358,7 @@ int do_reset(serfsim* h, u64 seed) {
 void free_all(serfsim* h) {
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   for (cudaEvent_t e : h->tick_ev) cudaEventDestroy(e);
-  cudaFree(h->d_hot[0]); cudaFree(h->d_hot[1]);
+  cudaFree(h->d_hot[0]); cudaFree(h->d_hot[1]); cudaFree(h->d_busy); cudaFree(h->d_snap_rec); cudaFree(h->d_snap_node);
   cudaFree(h->d_rec); cudaFree(h->d_inbox[0]); cudaFree(h->d_inbox[1]); cudaFree(h->d_node); cudaFree(h->d_rowptr); cudaFree(h->d_col);
   cudaFree(h->d_ev_node); cudaFree(h->d_ev_op); cudaFree(h->d_ev_slot); cudaFree(h->d_trace); cudaFree(h->d_kinds); cudaFree(h->d_ones);
   cudaFree(h->d_overflow); cudaFree(h->d_subj); cudaFree(h->d_scratch); cudaFree(h->d_stage);
@@ -384,6 +400,7 @@ void serfsim_default_config(serfsim_config_t* c) {
   c->gossip_interval_ms = 200;
   c->init_status_ltime = 1; c->init_clock = 2;
   c->trace = 0; c->seed = 1; c->device = -1; c->rank = 0; c->world_size = 1;
+  c->push_pull_interval_ticks = 0;     // LAN: 30 s = 150 ticks × pushPullScale(n); off unless asked for
 }
 
 int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
@@ -394,6 +411,8 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
     return fail(SERFSIM_E_INVAL, "bad n_nodes / slots (1..16) / fanout (1..8)");
   if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) return fail(SERFSIM_E_INVAL, "bad rank / world_size");
   if (cfg->gossip_interval_ms == 0) return fail(SERFSIM_E_INVAL, "gossip_interval_ms must be > 0");
+  if (cfg->push_pull_interval_ticks < 0) return fail(SERFSIM_E_INVAL, "push_pull_interval_ticks must be >= 0");
+  if (cfg->push_pull_interval_ticks > 0 && cfg->world_size > 1) return fail(SERFSIM_E_INVAL, "push-pull rounds are single-GPU in this version (world_size must be 1)");
   if (cfg->suspicion_mult >= 2 && cfg->suspicion_mult - 2 > MAX_K) return fail(SERFSIM_E_INVAL, "suspicion_mult too large");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -431,6 +450,7 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
   CUB(cudaMalloc(&h->d_node, (size_t)h->stride * 8));
   CUB(cudaMemset(h->d_node, 0, (size_t)h->stride * 8));
   h->n_tiles = (h->count + 255) / 256;
+  CUB(cudaMalloc(&h->d_busy, h->stride));
   CUB(cudaMalloc(&h->d_hot[0], h->n_tiles)); CUB(cudaMalloc(&h->d_hot[1], h->n_tiles));
   CUB(cudaMalloc(&h->d_overflow, 4)); CUB(cudaMalloc(&h->d_subj, MAX_SLOTS * 4)); CUB(cudaMalloc(&h->d_scratch, 64 * 8));
   CUB(cudaMalloc(&h->d_stage, (size_t)h->count * 8));
@@ -561,7 +581,7 @@ int serfsim_inject(serfsim_t* h, uint32_t tick, uint32_t op, uint32_t node, uint
   if (op == SERFSIM_OP_FORCE_LEAVE) { if (slot >= h->R) return fail(SERFSIM_E_INVAL, "slot out of range"); }
   else if ((op == SERFSIM_OP_JOIN || op == SERFSIM_OP_LEAVE) && slot_of(h, node) < 0)
     return fail(SERFSIM_E_INVAL, "join/leave origin must be a tracked subject");
-  for (const auto& o : h->ops) if (o.tick == tick && o.node == node) return fail(SERFSIM_E_INVAL, "one operation per node per tick");
+  if (!h->op_keys.insert(((u64)tick << 32) | node).second) return fail(SERFSIM_E_INVAL, "one operation per node per tick");
   h->ops.push_back(HostOp{tick, op, node, slot, h->op_seq++});
   h->ops_dirty = true;
   return 0;
@@ -582,6 +602,8 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
   if (!h) return fail(SERFSIM_E_INVAL, "null handle");
   u32 chunk = 4;
   if (const char* e = getenv("SERFSIM_CHUNK")) chunk = std::max(1, atoi(e));
+  const u32 pp = (u32)std::max(0, h->cfg.push_pull_interval_ticks);
+  if (pp) chunk = std::min(chunk, pp);             // never run past the next anti-entropy round after a candidate tick
   const u32 start = h->tick;
   int rc = 0;
   while (h->tick - start < max_ticks) {
@@ -592,7 +614,10 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
     if ((rc = pull_rows(h))) return rc;
     for (u32 t = from; t < h->tick; ++t) {
       const serfsim_tick_row_t& r = h->rows[t];
-      if (r.pending == 0 && r.edge_updates == 0 && !future_ops(h, t)) {
+      // with anti-entropy on, convergence additionally needs a push-pull round that changed nothing but Lamport times
+      // (a Left member is re-sent as "leave at status_ltime + 1", serf/delegate.rs:495-510: status_time creeps by design)
+      const bool pp_ok = !pp || (((t + 1) % pp) == 0 && r.changed == 0);
+      if (r.pending == 0 && r.edge_updates == 0 && !future_ops(h, t) && pp_ok) {
         // ticks after t were no-ops on a quiescent cluster: rewind the logical clock to t + 1
         if (h->tick > t + 1) {
           CU(cudaMemsetAsync(h->d_trace + (size_t)(t + 1) * 8, 0, (size_t)(h->tick - t - 1) * 8 * sizeof(u64), h->stream));

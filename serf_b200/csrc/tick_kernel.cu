@@ -235,9 +235,31 @@ __device__ __forceinline__ u32 pick_targets(const TickParams& p, const StageView
   return nt;
 }
 
+// What decides whether a node has anything to do this tick: its busy byte (pending work / host op) and the inbox
+// words of the previous tick (slot 0 kept, the other slots OR-ed).  13 bytes per node instead of 45.
+struct Pre { u32 busy, mL, mJ, mM, any; };
+template <bool R1>
+__device__ __forceinline__ Pre prefetch_node(const TickParams& p, u32 vl, bool kL, bool kJ, bool kM, u64 pol_first) {
+  const u32 nl = p.stride, R = R1 ? 1u : p.R;
+  Pre x;
+  x.busy = p.busy[vl];
+  x.mL = kL ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R) * nl + vl, pol_first) : 0u;
+  x.mJ = kJ ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R) * nl + vl, pol_first) : 0u;
+  x.mM = kM ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R) * nl + vl, pol_first) : 0u;
+  x.any = x.mL | x.mJ | x.mM;
+  if (!R1) {
+    for (u32 s2 = 1; s2 < R; ++s2) {
+      if (kL) x.any |= ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R + s2) * nl + vl, pol_first);
+      if (kJ) x.any |= ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R + s2) * nl + vl, pol_first);
+      if (kM) x.any |= ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R + s2) * nl + vl, pol_first);
+    }
+  }
+  return x;
+}
+
 // Returns true when the node still holds pending work (keeps its tile hot for the next tick).
 template <bool TRACE, int FMAX, bool SHARDED, bool R1, bool STAGED>
-__device__ __forceinline__ bool process_node(const TickParams& p, const StageView& sv, XStage* xs, const u32 vl, const bool kL, const bool kJ, const bool kM, const bool mark,
+__device__ __forceinline__ bool process_node(const TickParams& p, const StageView& sv, XStage* xs, const u32 vl, const Pre& pre, const bool kL, const bool kJ, const bool kM, const bool mark, const bool saturated,
                                              const u64 pol_first, const u64 pol_last, Counters& c) {
   static_assert(!STAGED || R1, "the staged path is the single-slot path");
   const u32 lt = threadIdx.x;              // index inside the staged tile
@@ -247,29 +269,30 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   const u32 nl = p.stride;               // plane stride (n_local rounded up to a whole tile)
   const u32 R = R1 ? 1u : p.R;
 
-  // ---- front-loaded, independent loads: node word, slot-0 record and inbox words ----
-  const u64 ns = STAGED ? sv.node[lt] : ld_u64_stream(p.node_state + vl, pol_first);
+  // ---- loads.  Saturated ticks (the previous tick delivered to at least half of the nodes): everything a node
+  // needs is requested up front, independent loads in flight together.  Otherwise most nodes are idle: read only
+  // the busy byte (pending work / host op) and the inbox words, and fetch the 8-byte node word and the 32-byte
+  // record just for the nodes that have something to do. ----
+  const bool upfront = saturated || TRACE || STAGED;
+  u64 ns = 0;
   Words cur;
-  if (STAGED) {
-    const uint4 a = reinterpret_cast<const uint4*>(sv.rec + lt)[0], b = reinterpret_cast<const uint4*>(sv.rec + lt)[1];
-    cur.w[0] = a.x; cur.w[1] = a.y; cur.w[2] = a.z; cur.w[3] = a.w; cur.w[4] = b.x; cur.w[5] = b.y; cur.w[6] = b.z; cur.w[7] = b.w;
-  } else {
-    cur = ld_rec256(p.rec + 2 * (size_t)vl, pol_first);
-  }
-  u32 mL = 0, mJ = 0, mM = 0;
-  if (kL) mL = STAGED ? sv.inL[lt] : ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R) * nl + vl, pol_first);
-  if (kJ) mJ = STAGED ? sv.inJ[lt] : ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R) * nl + vl, pol_first);
-  if (kM) mM = STAGED ? sv.inM[lt] : ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R) * nl + vl, pol_first);
-
-  // ---- idle fast exit (single-slot runs): nothing received, nothing queued, no timer, no operation ----
-  if (R1 && !(mL | mJ | mM) && !(ns & NS_EV) && ((cur.w[6] >> 16) | (cur.w[7] & 0xff)) == 0 && ((cur.w[6] >> 8) & 3) != ML_SUSPECT &&
-      !(p.probe_every && p.down_mask)) {
-    if (TRACE) {
-      c.hash += rec_hash((u64)v, make_uint4(cur.w[0], cur.w[1], cur.w[2], cur.w[3]), make_uint4(cur.w[4], cur.w[5], cur.w[6], cur.w[7]));
-      c.hash += node_hash((u64)p.n_global + v, ns);
+  auto load_state = [&]() {
+    ns = STAGED ? sv.node[lt] : ld_u64_stream(p.node_state + vl, pol_first);
+    if (STAGED) {
+      const uint4 a = reinterpret_cast<const uint4*>(sv.rec + lt)[0], b = reinterpret_cast<const uint4*>(sv.rec + lt)[1];
+      cur.w[0] = a.x; cur.w[1] = a.y; cur.w[2] = a.z; cur.w[3] = a.w; cur.w[4] = b.x; cur.w[5] = b.y; cur.w[6] = b.z; cur.w[7] = b.w;
+    } else {
+      cur = ld_rec256(p.rec + 2 * (size_t)vl, pol_first);
     }
-    return false;
-  }
+  };
+  if (upfront) load_state();
+  const u32 busy = pre.busy;
+  u32 mL = pre.mL, mJ = pre.mJ, mM = pre.mM;
+  if (STAGED) { mL = kL ? sv.inL[lt] : 0u; mJ = kJ ? sv.inJ[lt] : 0u; mM = kM ? sv.inM[lt] : 0u; }
+
+  // ---- idle exit: nothing received (any slot), nothing queued, no timer, no host operation, no probe duty ----
+  if (!TRACE && !STAGED && busy == 0 && !pre.any && !(p.probe_every && p.down_mask)) return false;
+  if (!upfront) load_state();
 
   u32 clock = (u32)ns;
   const bool up_r = (ns & NS_UP) != 0;
@@ -277,9 +300,9 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   const u32 row0 = STAGED ? sv.rowptr[lt] : __ldg(p.row_ptr + vl);
   const u32 deg = (STAGED ? sv.rowptr[lt + 1] : __ldg(p.row_ptr + vl + 1)) - row0;
 
-  // host operation for this node (at most one per tick; the mark kernel set NS_EV)
+  // host operation for this node (at most one per tick; the mark kernel set bit 1 of the busy byte)
   u32 op = 0, op_slot = 0;
-  if (ns & NS_EV) {
+  if (busy & 2) {
     for (u32 e = p.ev_begin; e < p.ev_end; ++e)
       if (p.ev_node[e] == v) { op = p.ev_op[e]; op_slot = p.ev_slot[e]; break; }
     atomicAdd((unsigned long long*)(p.row + 5), 1ull);
@@ -417,6 +440,8 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   if (TRACE) c.hash += node_hash((u64)R * p.n_global + v, ns2);
   if (clock >= LTIME_LIMIT) *p.overflow = 1;
   c.packets += min(nt, max_tx);
+  const u32 busy2 = any_pending ? 1u : 0u;                 // the op bit is consumed
+  if (busy2 != busy) p.busy[vl] = (u8)busy2;
   return any_pending;
 }
 
@@ -427,6 +452,9 @@ template <bool TRACE, int FMAX, bool SHARDED, bool R1>
 __global__ void __launch_bounds__(BLOCK, 4) tick_kernel(const __grid_constant__ TickParams p) {
   __shared__ u8 hot_s[MAX_TILES_PER_CTA];
   __shared__ u64 red[8][BLOCK / 32];
+  __shared__ u32 warp_cnt[BLOCK / 32];
+  __shared__ u16 act_list[BLOCK];
+  __shared__ Pre pre_s[BLOCK];
   __shared__ __align__(16) unsigned char xs_mem[SHARDED ? sizeof(XStage) : 16];
   XStage* xs = reinterpret_cast<XStage*>(xs_mem);
   Counters c = {};
@@ -444,6 +472,7 @@ __global__ void __launch_bounds__(BLOCK, 4) tick_kernel(const __grid_constant__ 
   const bool dense_now = prev_msgs >= (p.n_tiles >> 1) + 1;      // what this tick's sends will look like
   const bool all_hot = p.force_all || p.kinds_prev[3] != 0;      // the previous tick was dense (or skipping is off)
   const bool mark = !dense_now;
+  const bool saturated = prev_msgs >= (p.n_local >> 1);          // most nodes have mail: request record + node word up front
   if (dense_now && blockIdx.x == 0 && threadIdx.x == 0) p.kinds_cur[3] = 1;
 
   const u32 tile0 = blockIdx.x * p.tiles_per_cta;
@@ -456,9 +485,39 @@ __global__ void __launch_bounds__(BLOCK, 4) tick_kernel(const __grid_constant__ 
   __syncthreads();
   for (u32 i = 0; i < ntile; ++i) {
     if (!hot_s[i]) continue;
-    const u32 vl = ((tile0 + i) << TILE_SHIFT) + threadIdx.x;
+    const u32 vbase = (tile0 + i) << TILE_SHIFT;
+    const u32 vl = vbase + threadIdx.x;
     bool pend = false;
-    if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, kL, kJ, kM, mark, pol_first, pol_last, c);
+    if (saturated || TRACE) {
+      // most nodes have mail: thread t handles node t of the tile
+      if (vl < p.n_local) {
+        const Pre pre = prefetch_node<R1>(p, vl, kL, kJ, kM, pol_first);
+        pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, true, pol_first, pol_last, c);
+      }
+    } else {
+      // few nodes have anything to do: find them (13 bytes per node), compact their indices in shared memory and
+      // run the node logic with FULL warps — the per-warp instruction cost of the logic does not depend on how
+      // many lanes are active, so scattered activity would otherwise cost as much as a saturated tick
+      Pre pre = {};
+      bool active = false;
+      if (vl < p.n_local) {
+        pre = prefetch_node<R1>(p, vl, kL, kJ, kM, pol_first);
+        active = pre.busy || pre.any || (p.probe_every && p.down_mask);
+      }
+      const u32 bal = __ballot_sync(0xffffffffu, active);
+      if (lane == 0) warp_cnt[wid] = __popc(bal);
+      __syncthreads();
+      u32 base = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < BLOCK / 32; ++w) { const u32 cw = warp_cnt[w]; base += (w < wid) ? cw : 0u; total += cw; }
+      if (active) { const u32 pos = base + __popc(bal & ((1u << lane) - 1u)); act_list[pos] = (u16)threadIdx.x; pre_s[threadIdx.x] = pre; }
+      __syncthreads();
+      if (threadIdx.x < total) {
+        const u32 tsel = act_list[threadIdx.x];
+        pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vbase + tsel, pre_s[tsel], kL, kJ, kM, mark, false, pol_first, pol_last, c);
+      }
+      __syncthreads();                         // the lists are reused by the next tile
+    }
     if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + i] = 1;
     if (SHARDED) wrote_remote |= flush_xstage(p, xs);
   }
@@ -575,7 +634,11 @@ __global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constan
     const u32 ti = hot_list[j];
     const u32 vl = ((tile0 + ti) << TILE_SHIFT) + threadIdx.x;
     bool pend = false;
-    if (vl < p.n_local) pend = process_node<TRACE, FMAX, false, true, true>(p, sv, nullptr, vl, kL, kJ, kM, mark, pol_first, pol_last, c);
+    if (vl < p.n_local) {
+      Pre pre = {};
+      pre.busy = p.busy[vl];
+      pend = process_node<TRACE, FMAX, false, true, true>(p, sv, nullptr, vl, pre, kL, kJ, kM, mark, true, pol_first, pol_last, c);
+    }
     if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + ti] = 1;
     if (BARSYNC) __syncthreads();
     else { __syncwarp(); if (lane == 0) mbar_arrive(&empty_bar[st]); }     // this warp is done reading stage `st`
@@ -600,6 +663,78 @@ __global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constan
     }
   }
   if (TRACE && lane == 0 && hs) atomicAdd((unsigned long long*)(p.row + 7), (unsigned long long)hs);
+}
+
+// Anti-entropy round — memberlist push-pull + SerfDelegate::merge_remote_state (serf/delegate.rs:386-554; "next"
+// row 1 of SURVEY §8f).  Runs after the tick kernel every push_pull_interval ticks on a SNAPSHOT of the end-of-tick
+// state: each up node pulls the state of one random neighbour and merges it — clock witness(ltime−1), per subject
+// the memberlist state (alive → aliveNode, suspect/dead → suspectNode{from = self}, left → deadNode{from = node}),
+// then serf's view (Left member → leave intent at status_ltime+1, any other → join intent at status_ltime) with the
+// handlers' results discarded: nothing is re-queued (delegate.rs:495-523).  A node writes only its own records.
+template <bool TRACE>
+__global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__ TickParams p, const uint4* __restrict__ snap_rec, const u64* __restrict__ snap_node) {
+  long long d_changed = 0, d_pending = 0;
+  u64 d_hash = 0;
+  for (u32 vl = blockIdx.x * BLOCK + threadIdx.x; vl < p.n_local; vl += gridDim.x * BLOCK) {
+    const u32 v = p.first + vl;
+    const u64 ns = snap_node[vl];
+    if (!(ns & NS_UP)) continue;
+    const u32 row0 = p.row_ptr[vl], deg = p.row_ptr[vl + 1] - row0;
+    if (!deg) continue;
+    u32 w[4];
+    philox4x32_10(p.tick, v, 0, DOMAIN_PUSHPULL, p.seed_lo, p.seed_hi, w);
+    const u32 u = p.col[row0 + (((w[0] & 0xffffu) * deg) >> 16)];
+    if (u == v) continue;
+    const u32 ul = u - p.first;                               // single-GPU only (checked by the host)
+    const u64 nu = snap_node[ul];
+    if (!(nu & NS_UP)) continue;
+    u32 clock = (u32)ns;
+    const u32 sstate = (u32)(ns >> 40) & 3;
+    const u32 cu = (u32)nu;
+    if (cu > 0) witness(clock, cu - 1);
+    bool any_pending = false;
+    for (u32 s = 0; s < p.R; ++s) {
+      const size_t iv = (size_t)s * p.stride + vl, iu = (size_t)s * p.stride + ul;
+      const uint4 a0 = p.rec[2 * iv], b0 = p.rec[2 * iv + 1];
+      Rec r, q;
+      unpack(a0, b0, r);
+      unpack(snap_rec[2 * iu], snap_rec[2 * iu + 1], q);
+      const bool self = (p.subj[s] == v);
+      const bool was = (r.txl | r.txj | r.txm) || r.mlstate == ML_SUSPECT || (p.probe_every && ((p.down_mask >> s) & 1) && !self && r.mlstate == ML_ALIVE);
+      if (q.flags & 1) {
+        if (q.mlstate == ML_ALIVE) ml_alive(r, q.inc, self, p.rules.limit);
+        else if (q.mlstate == ML_LEFT) ml_dead(r, q.inc, true, p.tick, self, p.rules.limit);
+        else ml_suspect(r, q.inc, from_bucket(v), p.tick, self, p.rules);
+        bool refute = false;
+        if (q.status == ST_LEFT) { witness(clock, q.st + 1); leave_intent(r, q.st + 1, self, sstate, refute, p.rules.limit, false); }
+        else { witness(clock, q.st); join_intent(r, q.st, p.rules.limit, false); }
+        if (refute) { const u32 T = clock; witness(clock, T); join_intent(r, T, p.rules.limit); r.qjoin = T; r.txj = p.rules.limit; }
+      }
+      uint4 a1, b1;
+      pack(r, a1, b1);
+      const bool ch = (a1.x ^ a0.x) | (a1.y ^ a0.y) | (a1.z ^ a0.z) | (a1.w ^ a0.w) | (b1.x ^ b0.x) | (b1.y ^ b0.y) | (b1.z ^ b0.z) | (b1.w ^ b0.w);
+      if (ch) { p.rec[2 * iv] = a1; p.rec[2 * iv + 1] = b1; }
+      if ((a1.y ^ a0.y) | (a1.z ^ a0.z) | (a1.w ^ a0.w) | (b1.x ^ b0.x) | (b1.y ^ b0.y) | (b1.z ^ b0.z) | (b1.w ^ b0.w)) d_changed++;   // status_time creep is not a change
+      if (TRACE && ch) d_hash += rec_hash((u64)s * p.n_global + v, a1, b1) - rec_hash((u64)s * p.n_global + v, a0, b0);
+      const bool now = (r.txl | r.txj | r.txm) || r.mlstate == ML_SUSPECT || (p.probe_every && ((p.down_mask >> s) & 1) && !self && r.mlstate == ML_ALIVE);
+      d_pending += (now ? 1 : 0) - (was ? 1 : 0);
+      any_pending |= now;
+      if (r.inc >= INC_LIMIT) *p.overflow = 1;
+    }
+    const u64 ns2 = (ns & ~0xffffffffull) | clock;
+    if (ns2 != ns) {
+      p.node_state[vl] = ns2;
+      if (TRACE) d_hash += node_hash((u64)p.R * p.n_global + v, ns2) - node_hash((u64)p.R * p.n_global + v, ns);
+    }
+    if (clock >= LTIME_LIMIT) *p.overflow = 1;
+    if (any_pending) { p.busy[vl] = 1; p.hot_wr[vl >> TILE_SHIFT] = 1; }
+  }
+  const u64 c = warp_sum64((u64)d_changed), q = warp_sum64((u64)d_pending), h = TRACE ? warp_sum64(d_hash) : 0;
+  if ((threadIdx.x & 31) == 0) {
+    if (c) atomicAdd((unsigned long long*)(p.row + 3), (unsigned long long)c);
+    if (q) atomicAdd((unsigned long long*)(p.row + 4), (unsigned long long)q);
+    if (TRACE && h) atomicAdd((unsigned long long*)(p.row + 7), (unsigned long long)h);
+  }
 }
 
 // After the tick kernel: publish, to every peer, how many entries this rank wrote into its window, then raise
@@ -665,12 +800,12 @@ __global__ void init_state_kernel(uint4* rec, u64* node_state, u32 n_local, u32 
   node_state[vl] = (u64)init_clock | NS_UP;
 }
 
-__global__ void mark_events_kernel(u64* node_state, u8* hot_rd, const u32* ev_node, u32 ev_begin, u32 ev_end, u32 first, u32 n_local) {
+__global__ void mark_events_kernel(u8* busy, u8* hot_rd, const u32* ev_node, u32 ev_begin, u32 ev_end, u32 first, u32 n_local) {
   const u32 e = ev_begin + blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= ev_end) return;
   const u32 vl = ev_node[e] - first;
   if (vl < n_local) {
-    node_state[vl] |= NS_EV;                       // one op per (node, tick): no two threads touch the same word
+    busy[vl] |= 2;                                 // one op per (node, tick): no two threads touch the same byte
     hot_rd[vl >> TILE_SHIFT] = 1;                  // the tile must run this tick
   }
 }
@@ -790,15 +925,19 @@ void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st) {
   if (trace) { if (small) launch_tick_v<true, 4>(p, grid, st); else launch_tick_v<true, 8>(p, grid, st); }
   else { if (small) launch_tick_v<false, 4>(p, grid, st); else launch_tick_v<false, 8>(p, grid, st); }
 }
+void launch_pushpull(const TickParams& p, const uint4* snap_rec, const u64* snap_node, bool trace, cudaStream_t st) {
+  if (trace) pushpull_kernel<true><<<148 * 8, BLOCK, 0, st>>>(p, snap_rec, snap_node);
+  else pushpull_kernel<false><<<148 * 8, BLOCK, 0, st>>>(p, snap_rec, snap_node);
+}
 void launch_drain(const DrainParams& p, cudaStream_t st) { drain_kernel<<<148 * 8, BLOCK, 0, st>>>(p); }
 void launch_publish(const PublishParams& p, cudaStream_t st) { publish_kernel<<<1, 32, 0, st>>>(p); }
 void launch_init_state(uint4* rec, u64* node_state, u32 n_local, u32 stride, u32 R, u32 init_st, u32 init_clock, cudaStream_t st) {
   init_state_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(rec, node_state, n_local, stride, R, init_st, init_clock);
 }
-void launch_mark_events(u64* node_state, u8* hot_rd, const u32* ev_node, u32 ev_begin, u32 ev_end, u32 first, u32 n_local, cudaStream_t st) {
+void launch_mark_events(u8* busy, u8* hot_rd, const u32* ev_node, u32 ev_begin, u32 ev_end, u32 first, u32 n_local, cudaStream_t st) {
   const u32 n = ev_end - ev_begin;
   if (!n) return;
-  mark_events_kernel<<<(n + 127) / 128, 128, 0, st>>>(node_state, hot_rd, ev_node, ev_begin, ev_end, first, n_local);
+  mark_events_kernel<<<(n + 127) / 128, 128, 0, st>>>(busy, hot_rd, ev_node, ev_begin, ev_end, first, n_local);
 }
 void launch_extract(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 slot, int what, void* out, cudaStream_t st) {
   extract_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(rec, node_state, n_local, stride, slot, what, out);

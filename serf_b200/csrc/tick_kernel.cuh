@@ -17,7 +17,8 @@ struct TickParams {
   uint4* rec;                 // [R][n_local] records, 2 × uint4 each
   u32* inbox_rd;              // [3][R][n_local] reduced inbox filled by the previous tick (value+1, 0 = empty)
   u32* inbox_wr;              // [3][R][n_local] inbox the sends of this tick reduce into
-  u64* node_state;            // [n_local]  clock | up | SerfState | op-pending
+  u64* node_state;            // [n_local]  clock | up | SerfState
+  u8* busy;                   // [n_local]  bit 0: the node holds pending work (queued transmits, suspicion timer); bit 1: host op this tick
   const u32* row_ptr;         // [n_local+1] CSR offsets into col (shard-local)
   const u32* col;             // neighbour ids (global)
   const u32* ev_node;         // host operations, sorted by tick
@@ -57,10 +58,11 @@ struct DrainParams {
 };
 
 void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st);
+void launch_pushpull(const TickParams& p, const uint4* snap_rec, const u64* snap_node, bool trace, cudaStream_t st);
 void launch_drain(const DrainParams& p, cudaStream_t st);
 void launch_publish(const PublishParams& p, cudaStream_t st);
 void launch_init_state(uint4* rec, u64* node_state, u32 n_local, u32 stride, u32 R, u32 init_st, u32 init_clock, cudaStream_t st);
-void launch_mark_events(u64* node_state, u8* hot_rd, const u32* ev_node, u32 ev_begin, u32 ev_end, u32 first, u32 n_local, cudaStream_t st);
+void launch_mark_events(u8* busy, u8* hot_rd, const u32* ev_node, u32 ev_begin, u32 ev_end, u32 first, u32 n_local, cudaStream_t st);
 void launch_extract(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 slot, int what, void* out, cudaStream_t st);
 void launch_state_hash(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 n_global, u32 R, u64* out, cudaStream_t st);
 void launch_summary(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 R, const u32* subj_dev, u64* out /*[2 + 2*R + 2]*/, cudaStream_t st);

@@ -102,7 +102,8 @@ def fuzz(seed, n=None, slots=None):
     cfg = dict(fanout=int(rng.integers(1, 6)), seed=int(rng.integers(1, 2**40)),
                retransmit_mult=int(rng.integers(1, 5)), suspicion_mult=int(rng.integers(1, 6)),
                suspicion_max_timeout_mult=int(rng.integers(1, 4)), probe_interval_ticks=int(rng.integers(0, 4)),
-               gossip_interval_ms=200, init_status_ltime=int(rng.integers(0, 3)), init_clock=int(rng.integers(1, 5)))
+               gossip_interval_ms=200, init_status_ltime=int(rng.integers(0, 3)), init_clock=int(rng.integers(1, 5)),
+               push_pull_interval_ticks=int(rng.choice([0, 0, 5, 11, 30])))
     ops, used = [], set()
     horizon = int(rng.integers(5, 120))
     for _ in range(int(rng.integers(1, 30))):

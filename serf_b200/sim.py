@@ -46,7 +46,7 @@ class Config(C.Structure):             # serfsim_config_t
                 ("retransmit_mult", C.c_uint32), ("suspicion_mult", C.c_uint32), ("suspicion_max_timeout_mult", C.c_uint32),
                 ("probe_interval_ticks", C.c_uint32), ("gossip_interval_ms", C.c_uint32), ("init_status_ltime", C.c_uint32),
                 ("init_clock", C.c_uint32), ("trace", C.c_uint32), ("seed", C.c_uint64), ("device", C.c_int32),
-                ("rank", C.c_int32), ("world_size", C.c_int32), ("reserved", C.c_int32)]
+                ("rank", C.c_int32), ("world_size", C.c_int32), ("push_pull_interval_ticks", C.c_int32)]
 
 
 class Stats(C.Structure):              # serfsim_stats_t
@@ -147,7 +147,7 @@ def default_config(**kw):
     """memberlist LAN profile (serf-core/src/options.rs:521) in ticks; override by keyword."""
     cfg = Config(abi_version=ABI_VERSION, n_nodes=0, slots=1, fanout=3, retransmit_mult=4, suspicion_mult=4,
                  suspicion_max_timeout_mult=6, probe_interval_ticks=5, gossip_interval_ms=200, init_status_ltime=1,
-                 init_clock=2, trace=0, seed=1, device=-1, rank=0, world_size=1, reserved=0)
+                 init_clock=2, trace=0, seed=1, device=-1, rank=0, world_size=1, push_pull_interval_ticks=0)
     for k, v in kw.items():
         if not hasattr(cfg, k):
             raise TypeError(f"unknown config field {k}")

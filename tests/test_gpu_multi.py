@@ -53,7 +53,7 @@ WORLDS = [int(x) for x in os.environ.get("SERFSIM_TEST_WORLDS", "2,4").split(","
     ("random_graph_leave", dict(n=50_000, degree=16, fanout=3, seed=2, slots=1), {}),
     ("random_graph_leave", dict(n=30_001, degree=12, fanout=4, seed=3, slots=3), {}),
     ("random_graph_fail", dict(n=20_000, degree=16, fanout=3, seed=2), dict(suspicion_mult=2, suspicion_max_timeout_mult=2, probe_interval_ticks=2)),
-    ("fuzz", dict(seed=7, n=3000, slots=4), {}),
+    ("fuzz", dict(seed=7, n=3000, slots=4), dict(push_pull_interval_ticks=0)),
 ])
 def test_sharded_equals_oracle(world, scen, tmp_path):
     if torch.cuda.device_count() < world:

@@ -95,6 +95,19 @@ def test_config2_small_world_churn():
     run_both(sc, suspicion_mult=2, suspicion_max_timeout_mult=2, probe_interval_ticks=2)
 
 
+@pytest.mark.parametrize("pp", [7, 16])
+def test_push_pull_anti_entropy(pp):
+    from serf_b200 import small_world_graph
+    from serf_b200.scenarios import Scenario
+    from serf_b200 import Op
+    n = 20_000
+    sc = Scenario("pushpull", n, 3, small_world_graph(n, 4, 0.05, 5), [7, 900, 15000],
+                  [(0, Op.LEAVE, 7, 0), (3, Op.FAIL, 900, 0), (40, Op.FORCE_LEAVE, 11, 1), (5, Op.JOIN, 15000, 0)],
+                  dict(fanout=2, retransmit_mult=1, seed=5, push_pull_interval_ticks=pp, probe_interval_ticks=2, suspicion_mult=2, suspicion_max_timeout_mult=2), max_ticks=3000)
+    g, o, ticks = run_both(sc)
+    assert (ticks + 1) % pp == 0
+
+
 @pytest.mark.parametrize("seed", range(40))
 def test_fuzz(seed):
     sc = scenarios.fuzz(seed)

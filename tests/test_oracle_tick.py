@@ -192,3 +192,22 @@ def test_fuzz_scenarios_run_and_are_reproducible(seed):
     b.step(n)
     assert a.state_hash() == b.state_hash()
     assert (a.tick_trace(0, n) == b.tick_trace(0, n)).all()
+
+
+def test_push_pull_backstop_converges_what_gossip_strands():
+    """serf/delegate.rs:386-554: with tiny retransmit budgets on a sparse graph plain gossip strands members in
+    Alive / Leaving / Failed; periodic push-pull (anti-entropy) brings every view to Left."""
+    from serf_b200 import small_world_graph
+    n = 3000
+    res = {}
+    for pp in (0, 15):
+        o = oracle_sim(n, 1, seed=3, fanout=2, retransmit_mult=1, push_pull_interval_ticks=pp, probe_interval_ticks=0)
+        o.set_topology(*small_world_graph(n, 4, 0.05, 5))
+        o.set_subjects([7])
+        o.leave(7, tick=0)
+        ticks, ok = o.run_until_converged(3000)
+        assert ok
+        res[pp] = (np.bincount(np.delete(o.member_status(0), 7), minlength=5), ticks)
+    assert res[0][0][MemberStatus.LEFT] < n - 1                       # gossip alone leaves stragglers
+    assert res[15][0][MemberStatus.LEFT] == n - 1                     # anti-entropy finishes the job
+    assert (res[15][1] + 1) % 15 == 0                                 # convergence is declared on a push-pull round after a gossip-free interval
