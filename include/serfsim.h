@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SERFSIM_ABI_VERSION 1u
+#define SERFSIM_ABI_VERSION 2u
 
 /* ---- error codes ------------------------------------------------------------------ */
 #define SERFSIM_OK            0
@@ -94,6 +94,11 @@ typedef struct serfsim_config {
   int32_t  rank;                      /* shard index of this process (0 when world_size == 1)        */
   int32_t  world_size;                /* number of shards (one process per GPU)                      */
   int32_t  push_pull_interval_ticks;  /* memberlist push_pull_interval in ticks (LAN 30 s = 150, times pushPullScale(n)); 0 = no anti-entropy rounds */
+  /* Reaper — `serf/base.rs:483-610`, defaults `options.rs:506-515` (reap 15 s = 75 ticks, timeouts 24 h, intents 5 min = 1500 ticks) */
+  uint32_t reap_interval_ticks;       /* 0 = the reaper never runs                                                         */
+  uint32_t tombstone_timeout_ticks;   /* Left members older than this are erased from the view (Options.tombstone_timeout) */
+  uint32_t reconnect_timeout_ticks;   /* Failed members older than this are erased (Options.reconnect_timeout)             */
+  uint32_t recent_intent_timeout_ticks; /* buffered intents older than this are dropped (Options.recent_intent_timeout)    */
 } serfsim_config_t;
 
 /* ---- Stats — mirrors `serf/api.rs:588-602` (members/failed/left/member_time/intent_queue)

@@ -631,6 +631,7 @@ struct TickSim {
       if (s >= 0) { if (e.op == SERFSIM_OP_FAIL) subj_up[s] = 0; if (e.op == SERFSIM_OP_REJOIN) subj_up[s] = 1; }
     }
     bool any_down = false; for (u32 s = 0; s < R; ++s) any_down |= !subj_up[s];
+    const bool reap_now = cfg.reap_interval_ticks && ((t + 1) % cfg.reap_interval_ticks) == 0;
     std::vector<serfsim_tick_row_t> rows(T);
 
     auto work = [&](u32 c) {
@@ -696,6 +697,7 @@ struct TickSim {
             v_join_intent(r, T, cx);
             r.qjoin = T; r.txj = (u8)cx.limit;
           }
+          if (!known(r) && r.status != TY_NONE && (r.status != before.status || r.st != before.st)) r.leave_tick = t + 1;   // NodeIntent.wall_time (types/member.rs:32)
           if (memcmp(&before, &r, sizeof(View)) != 0) row.changed++;
         }
         // ---------------- Phase E: host operation ----------------
@@ -727,8 +729,18 @@ struct TickSim {
             if (refute) { u32 T2 = nd.clock; witness32(nd.clock, T2); v_join_intent(r, T2, cx); r.qjoin = T2; r.txj = (u8)cx.limit; }
           }
         }
+        if (ev && !known(r) && r.status != TY_NONE && r.leave_tick == 0) r.leave_tick = t + 1;
         if (up_s) {
-          // ---------------- Phase T: suspicion timer, probe ----------------
+          // ---------------- Phase T: reaper (serf/base.rs:483-610), suspicion timer, probe ----------------
+          if (reap_now) {
+            const u32 age = r.leave_tick ? (t + 1 - r.leave_tick) : 0;
+            if (known(r) && r.leave_tick &&
+                ((r.status == ST_LEFT && age > cfg.tombstone_timeout_ticks) || (r.status == ST_FAILED && age > cfg.reconnect_timeout_ticks))) {
+              r.flags &= ~1; r.status = TY_NONE; r.st = 0; r.leave_tick = 0;          // erase_node! :499-519 (the view forgets the member)
+            } else if (!known(r) && r.status != TY_NONE && r.leave_tick && age > cfg.recent_intent_timeout_ticks) {
+              r.status = TY_NONE; r.st = 0; r.leave_tick = 0;                          // reap_intents :1817-1822
+            }
+          }
           if (ml_state(r) == ML_SUSPECT && r.deadline != 0 && t >= r.deadline) v_ml_dead(r, r.inc, false, t, false, cx);
           if (have_probe && !self && ptarget == subj[s] && !subj_up[s]) {
             u8 st = ml_state(r);
@@ -807,6 +819,7 @@ struct TickSim {
               if (q.status == ST_LEFT) { witness32(nd.clock, q.st + 1); v_leave_intent(r, q.st + 1, self, nd.sstate, &refute, cx, false); }
               else { witness32(nd.clock, q.st); v_join_intent(r, q.st, cx, false); }
               if (refute) { u32 T2 = nd.clock; witness32(nd.clock, T2); v_join_intent(r, T2, cx); r.qjoin = T2; r.txj = (u8)cx.limit; }
+              if (!known(r) && r.status != TY_NONE && (r.status != before.status || r.st != before.st)) r.leave_tick = t + 1;
             }
             { View a = before, b = r; a.st = b.st = 0;       // status_time creeps by design (leave at status_ltime + 1): not a change
               if (memcmp(&a, &b, sizeof(View)) != 0) row.changed++; }

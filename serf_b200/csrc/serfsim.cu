@@ -226,8 +226,10 @@ int launch_ticks(serfsim* h, u32 n) {
     p.overflow = h->d_overflow;
     p.hot_rd = h->d_hot[(t & 1) ^ 1]; p.hot_wr = h->d_hot[t & 1];
     p.stage_col_bytes = h->stage_col_bytes;
+    p.reap_now = (h->cfg.reap_interval_ticks && ((t + 1) % h->cfg.reap_interval_ticks) == 0) ? 1u : 0u;
+    p.tombstone_ticks = h->cfg.tombstone_timeout_ticks; p.reconnect_ticks = h->cfg.reconnect_timeout_ticks; p.intent_ticks = h->cfg.recent_intent_timeout_ticks;
     p.stride = h->stride; p.n_tiles = h->n_tiles; p.tiles_per_cta = (h->n_tiles + h->grid - 1) / h->grid;
-    p.force_all = (h->cfg.trace != 0) || (h->cfg.probe_interval_ticks && p.down_mask) || h->no_skip;
+    p.force_all = (h->cfg.trace != 0) || (h->cfg.probe_interval_ticks && p.down_mask) || h->no_skip || p.reap_now;
     const u32 xpar = h->xepoch & 1;
     p.world = (u32)h->cfg.world_size; p.rank = (u32)h->cfg.rank; p.shard_size = h->shard_size; p.win_cap = h->win_cap;
     p.win_data = h->d_peer_data[xpar]; p.send_count = h->d_send_count;
@@ -401,6 +403,9 @@ void serfsim_default_config(serfsim_config_t* c) {
   c->init_status_ltime = 1; c->init_clock = 2;
   c->trace = 0; c->seed = 1; c->device = -1; c->rank = 0; c->world_size = 1;
   c->push_pull_interval_ticks = 0;     // LAN: 30 s = 150 ticks × pushPullScale(n); off unless asked for
+  c->reap_interval_ticks = 0;          // options.rs:506: 15 s = 75 ticks; off unless asked for
+  c->tombstone_timeout_ticks = 432000; c->reconnect_timeout_ticks = 432000;   // 24 h (options.rs:508-509)
+  c->recent_intent_timeout_ticks = 1500;                                     // 5 min (options.rs:515)
 }
 
 int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {

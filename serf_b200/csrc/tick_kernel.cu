@@ -291,7 +291,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   if (STAGED) { mL = kL ? sv.inL[lt] : 0u; mJ = kJ ? sv.inJ[lt] : 0u; mM = kM ? sv.inM[lt] : 0u; }
 
   // ---- idle exit: nothing received (any slot), nothing queued, no timer, no host operation, no probe duty ----
-  if (!TRACE && !STAGED && busy == 0 && !pre.any && !(p.probe_every && p.down_mask)) return false;
+  if (!TRACE && !STAGED && busy == 0 && !pre.any && !(p.probe_every && p.down_mask) && !p.reap_now) return false;
   if (!upfront) load_state();
 
   u32 clock = (u32)ns;
@@ -328,14 +328,21 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   u32 max_tx = 0;
   bool any_pending = false;
 
+  // multi-slot runs: the record and inbox words of slot s+1 are requested while slot s is being processed
+  Words nxt = {};
+  u32 nL = 0, nJ = 0, nM = 0;
 #pragma unroll 1
   for (u32 s = 0; s < R; ++s) {
     const size_t idx = (size_t)s * nl + vl;
-    if (!R1 && s) {                                        // slots > 0: load at the top of the iteration
-      cur = ld_rec256(p.rec + 2 * idx, pol_first);
-      mL = kL ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R + s) * nl + vl, pol_first) : 0;
-      mJ = kJ ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R + s) * nl + vl, pol_first) : 0;
-      mM = kM ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R + s) * nl + vl, pol_first) : 0;
+    if (!R1) {
+      if (s) { cur = nxt; mL = nL; mJ = nJ; mM = nM; }
+      if (s + 1 < R) {
+        const size_t idn = idx + nl;
+        nxt = ld_rec256(p.rec + 2 * idn, pol_first);
+        nL = kL ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R + s + 1) * nl + vl, pol_first) : 0;
+        nJ = kJ ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R + s + 1) * nl + vl, pol_first) : 0;
+        nM = kM ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R + s + 1) * nl + vl, pol_first) : 0;
+      }
     }
     if (mL) st_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R + s) * nl + vl, 0u, pol_first);   // consume: clear for reuse in two ticks
     if (mJ) st_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R + s) * nl + vl, 0u, pol_first);
@@ -361,6 +368,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
         join_intent(r, T, limit);
         r.qjoin = T; r.txj = limit;
       }
+      if (!(r.flags & 1) && r.status != TY_NONE && (r.status != (orig.w[6] & 0xff) || r.st != orig.w[0])) r.leave_tick = t + 1;   // NodeIntent.wall_time (types/member.rs:32)
       Words mid;
       pack_words(r, mid);
       c.changed += differs(mid, orig) ? 1 : 0;
@@ -392,8 +400,18 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
         if (rf) { const u32 T2 = clock; witness(clock, T2); join_intent(r, T2, limit); r.qjoin = T2; r.txj = limit; }
       }
     }
+    if (op && !(r.flags & 1) && r.status != TY_NONE && r.leave_tick == 0) r.leave_tick = t + 1;
     if (up_s) {
-      // ---------------- Phase T ----------------
+      // ---------------- Phase T: reaper (serf/base.rs:483-610), suspicion timer, probe ----------------
+      if (p.reap_now) {
+        const u32 age = r.leave_tick ? (t + 1 - r.leave_tick) : 0;
+        if ((r.flags & 1) && r.leave_tick &&
+            ((r.status == ST_LEFT && age > p.tombstone_ticks) || (r.status == ST_FAILED && age > p.reconnect_ticks))) {
+          r.flags &= ~1u; r.status = TY_NONE; r.st = 0; r.leave_tick = 0;           // erase_node! :499-519
+        } else if (!(r.flags & 1) && r.status != TY_NONE && r.leave_tick && age > p.intent_ticks) {
+          r.status = TY_NONE; r.st = 0; r.leave_tick = 0;                           // reap_intents :1817-1822
+        }
+      }
       if (r.mlstate == ML_SUSPECT && r.deadline != 0 && t >= r.deadline) ml_dead(r, r.inc, false, t, false, limit);
       if (have_probe && !self && ptarget == p.subj[s] && ((p.down_mask >> s) & 1)) {
         if (r.mlstate == ML_ALIVE || r.mlstate == ML_SUSPECT) {
@@ -502,7 +520,7 @@ __global__ void __launch_bounds__(BLOCK, 4) tick_kernel(const __grid_constant__ 
       bool active = false;
       if (vl < p.n_local) {
         pre = prefetch_node<R1>(p, vl, kL, kJ, kM, pol_first);
-        active = pre.busy || pre.any || (p.probe_every && p.down_mask);
+        active = pre.busy || pre.any || (p.probe_every && p.down_mask) || p.reap_now;
       }
       const u32 bal = __ballot_sync(0xffffffffu, active);
       if (lane == 0) warp_cnt[wid] = __popc(bal);
@@ -709,6 +727,7 @@ __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__
         if (q.status == ST_LEFT) { witness(clock, q.st + 1); leave_intent(r, q.st + 1, self, sstate, refute, p.rules.limit, false); }
         else { witness(clock, q.st); join_intent(r, q.st, p.rules.limit, false); }
         if (refute) { const u32 T = clock; witness(clock, T); join_intent(r, T, p.rules.limit); r.qjoin = T; r.txj = p.rules.limit; }
+        if (!(r.flags & 1) && r.status != TY_NONE && (r.status != (b0.z & 0xff) || r.st != a0.x)) r.leave_tick = p.tick + 1;
       }
       uint4 a1, b1;
       pack(r, a1, b1);

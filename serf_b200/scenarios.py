@@ -103,7 +103,9 @@ def fuzz(seed, n=None, slots=None):
                retransmit_mult=int(rng.integers(1, 5)), suspicion_mult=int(rng.integers(1, 6)),
                suspicion_max_timeout_mult=int(rng.integers(1, 4)), probe_interval_ticks=int(rng.integers(0, 4)),
                gossip_interval_ms=200, init_status_ltime=int(rng.integers(0, 3)), init_clock=int(rng.integers(1, 5)),
-               push_pull_interval_ticks=int(rng.choice([0, 0, 5, 11, 30])))
+               push_pull_interval_ticks=int(rng.choice([0, 0, 5, 11, 30])),
+               reap_interval_ticks=int(rng.choice([0, 0, 7, 25])), tombstone_timeout_ticks=int(rng.integers(5, 80)),
+               reconnect_timeout_ticks=int(rng.integers(5, 80)), recent_intent_timeout_ticks=int(rng.integers(5, 80)))
     ops, used = [], set()
     horizon = int(rng.integers(5, 120))
     for _ in range(int(rng.integers(1, 30))):

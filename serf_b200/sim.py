@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class MemberStatus(enum.IntEnum):      # types/member.rs:54-58
@@ -46,7 +46,9 @@ class Config(C.Structure):             # serfsim_config_t
                 ("retransmit_mult", C.c_uint32), ("suspicion_mult", C.c_uint32), ("suspicion_max_timeout_mult", C.c_uint32),
                 ("probe_interval_ticks", C.c_uint32), ("gossip_interval_ms", C.c_uint32), ("init_status_ltime", C.c_uint32),
                 ("init_clock", C.c_uint32), ("trace", C.c_uint32), ("seed", C.c_uint64), ("device", C.c_int32),
-                ("rank", C.c_int32), ("world_size", C.c_int32), ("push_pull_interval_ticks", C.c_int32)]
+                ("rank", C.c_int32), ("world_size", C.c_int32), ("push_pull_interval_ticks", C.c_int32),
+                ("reap_interval_ticks", C.c_uint32), ("tombstone_timeout_ticks", C.c_uint32), ("reconnect_timeout_ticks", C.c_uint32),
+                ("recent_intent_timeout_ticks", C.c_uint32)]
 
 
 class Stats(C.Structure):              # serfsim_stats_t
@@ -147,7 +149,8 @@ def default_config(**kw):
     """memberlist LAN profile (serf-core/src/options.rs:521) in ticks; override by keyword."""
     cfg = Config(abi_version=ABI_VERSION, n_nodes=0, slots=1, fanout=3, retransmit_mult=4, suspicion_mult=4,
                  suspicion_max_timeout_mult=6, probe_interval_ticks=5, gossip_interval_ms=200, init_status_ltime=1,
-                 init_clock=2, trace=0, seed=1, device=-1, rank=0, world_size=1, push_pull_interval_ticks=0)
+                 init_clock=2, trace=0, seed=1, device=-1, rank=0, world_size=1, push_pull_interval_ticks=0,
+                 reap_interval_ticks=0, tombstone_timeout_ticks=432000, reconnect_timeout_ticks=432000, recent_intent_timeout_ticks=1500)
     for k, v in kw.items():
         if not hasattr(cfg, k):
             raise TypeError(f"unknown config field {k}")

@@ -38,14 +38,14 @@ def test_library_is_sm100a_with_red_and_no_oracle_dependency():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(sim.Config) == 12 * 4 + 8 + 4 * 4
+    assert C.sizeof(sim.Config) == 12 * 4 + 8 + 4 * 4 + 4 * 4
     assert C.sizeof(sim.Stats) == 12 * 8 and C.sizeof(sim.TickRow) == 8 * 8
     assert sim.RECORD_DTYPE.itemsize == 32
 
 
 def test_create_fails_loudly_without_gpu():
     lib = sim.load_library()
-    assert lib.serfsim_abi_version() == 1
+    assert lib.serfsim_abi_version() == 2
     import torch
     if torch.cuda.is_available():
         pytest.skip("GPU present: covered by the gpu tests")

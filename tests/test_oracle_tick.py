@@ -211,3 +211,40 @@ def test_push_pull_backstop_converges_what_gossip_strands():
     assert res[0][0][MemberStatus.LEFT] < n - 1                       # gossip alone leaves stragglers
     assert res[15][0][MemberStatus.LEFT] == n - 1                     # anti-entropy finishes the job
     assert (res[15][1] + 1) % 15 == 0                                 # convergence is declared on a push-pull round after a gossip-free interval
+
+
+def test_reaper_erases_tombstones_and_allows_a_fresh_join():
+    """serf/base.rs:483-610 on a tick clock: a Failed member is erased from every view once reconnect_timeout has
+    passed (erase_node!), a later return of the node is a brand-new member (handle_node_join's absent branch)."""
+    n = 40
+    o = oracle_sim(n, 1, seed=2, suspicion_mult=2, suspicion_max_timeout_mult=2, probe_interval_ticks=2,
+                   reap_interval_ticks=10, reconnect_timeout_ticks=30, tombstone_timeout_ticks=30, recent_intent_timeout_ticks=20)
+    o.set_topology(*full_mesh_graph(n))
+    o.set_subjects([5])
+    o.fail(5, tick=0)
+    o.run_until_converged(2000)
+    assert (np.delete(o.member_status(0), 5) == MemberStatus.FAILED).all()
+    o.step(60)                                                          # reconnect_timeout + a reap interval
+    assert (np.delete(o.member_status(0), 5) == MemberStatus.NONE).all()   # Serf::members no longer lists it
+    rec = np.delete(o.records(0), 5)
+    assert (rec["flags"] & 1 == 0).all() and (rec["leave_tick"] == 0).all()
+    t = o.stats()["tick"]
+    o.rejoin(5, tick=t)
+    o.run_until_converged(2000)
+    st = o.member_status(0)
+    assert (st == MemberStatus.ALIVE).all() and (o.incarnation(0) == 2).all()
+
+
+def test_reaper_drops_stale_buffered_intents():
+    n = 30
+    o = oracle_sim(n, 1, seed=2, probe_interval_ticks=0, reap_interval_ticks=5, recent_intent_timeout_ticks=12,
+                   tombstone_timeout_ticks=10, reconnect_timeout_ticks=10, suspicion_mult=2, suspicion_max_timeout_mult=1)
+    o.set_topology(*full_mesh_graph(n))
+    o.set_subjects([3])
+    # make the member unknown everywhere first: it fails, is detected, and is reaped
+    o2 = o
+    o2.cfg.probe_interval_ticks = 0
+    o.fail(3, tick=0)
+    o.remove_failed_node(1, 0, tick=1)                                 # Leave intent while everybody still sees it Alive → Leaving, never reaped
+    o.run_until_converged(500)
+    assert (np.delete(o.member_status(0), 3) == MemberStatus.LEAVING).all()
