@@ -467,7 +467,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
 // "hot": somebody delivered into it during the previous tick, it kept pending work (queued transmits,
 // suspicion timers), or a host operation targets it — otherwise not a single byte of it is touched.
 template <bool TRACE, int FMAX, bool SHARDED, bool R1>
-__global__ void __launch_bounds__(BLOCK, 4) tick_kernel(const __grid_constant__ TickParams p) {
+__global__ void __launch_bounds__(BLOCK, R1 ? 4 : 3) tick_kernel(const __grid_constant__ TickParams p) {
   __shared__ u8 hot_s[MAX_TILES_PER_CTA];
   __shared__ u64 red[8][BLOCK / 32];
   __shared__ u32 warp_cnt[BLOCK / 32];
