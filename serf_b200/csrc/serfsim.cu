@@ -608,11 +608,15 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
   u32 chunk = 4;
   if (const char* e = getenv("SERFSIM_CHUNK")) chunk = std::max(1, atoi(e));
   const u32 pp = (u32)std::max(0, h->cfg.push_pull_interval_ticks);
-  if (pp) chunk = std::min(chunk, pp);             // never run past the next anti-entropy round after a candidate tick
+  const u32 reap = h->cfg.reap_interval_ticks;
+  // Ticks launched beyond the first quiescent one must be no-ops (they are rewound).  Anti-entropy rounds and reaper
+  // ticks are not — they act on a quiescent cluster too — so such a tick is only ever the FIRST tick of a chunk.
+  auto boundary = [&](u32 t) { return (pp && (t + 1) % pp == 0) || (reap && (t + 1) % reap == 0); };
   const u32 start = h->tick;
   int rc = 0;
   while (h->tick - start < max_ticks) {
-    const u32 n = std::min(chunk, max_ticks - (h->tick - start));
+    u32 n = std::min(chunk, max_ticks - (h->tick - start));
+    for (u32 k = 1; k < n; ++k) if (boundary(h->tick + k)) { n = k; break; }
     const u32 from = h->tick;
     if ((rc = launch_ticks(h, n))) return rc;
     CU(cudaStreamSynchronize(h->stream));

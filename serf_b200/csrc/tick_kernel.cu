@@ -275,9 +275,12 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   // record just for the nodes that have something to do. ----
   const bool upfront = saturated || TRACE || STAGED;
   u64 ns = 0;
+  u32 row0 = 0, row1 = 0;
   Words cur;
   auto load_state = [&]() {
     ns = STAGED ? sv.node[lt] : ld_u64_stream(p.node_state + vl, pol_first);
+    row0 = STAGED ? sv.rowptr[lt] : __ldg(p.row_ptr + vl);
+    row1 = STAGED ? sv.rowptr[lt + 1] : __ldg(p.row_ptr + vl + 1);
     if (STAGED) {
       const uint4 a = reinterpret_cast<const uint4*>(sv.rec + lt)[0], b = reinterpret_cast<const uint4*>(sv.rec + lt)[1];
       cur.w[0] = a.x; cur.w[1] = a.y; cur.w[2] = a.z; cur.w[3] = a.w; cur.w[4] = b.x; cur.w[5] = b.y; cur.w[6] = b.z; cur.w[7] = b.w;
@@ -297,8 +300,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   u32 clock = (u32)ns;
   const bool up_r = (ns & NS_UP) != 0;
   u32 sstate = (u32)(ns >> 40) & 3;
-  const u32 row0 = STAGED ? sv.rowptr[lt] : __ldg(p.row_ptr + vl);
-  const u32 deg = (STAGED ? sv.rowptr[lt + 1] : __ldg(p.row_ptr + vl + 1)) - row0;
+  const u32 deg = row1 - row0;
 
   // host operation for this node (at most one per tick; the mark kernel set bit 1 of the busy byte)
   u32 op = 0, op_slot = 0;
@@ -470,9 +472,6 @@ template <bool TRACE, int FMAX, bool SHARDED, bool R1>
 __global__ void __launch_bounds__(BLOCK, R1 ? 4 : 3) tick_kernel(const __grid_constant__ TickParams p) {
   __shared__ u8 hot_s[MAX_TILES_PER_CTA];
   __shared__ u64 red[8][BLOCK / 32];
-  __shared__ u32 warp_cnt[BLOCK / 32];
-  __shared__ u16 act_list[BLOCK];
-  __shared__ Pre pre_s[BLOCK];
   __shared__ __align__(16) unsigned char xs_mem[SHARDED ? sizeof(XStage) : 16];
   XStage* xs = reinterpret_cast<XStage*>(xs_mem);
   Counters c = {};
@@ -506,35 +505,9 @@ __global__ void __launch_bounds__(BLOCK, R1 ? 4 : 3) tick_kernel(const __grid_co
     const u32 vbase = (tile0 + i) << TILE_SHIFT;
     const u32 vl = vbase + threadIdx.x;
     bool pend = false;
-    if (saturated || TRACE) {
-      // most nodes have mail: thread t handles node t of the tile
-      if (vl < p.n_local) {
-        const Pre pre = prefetch_node<R1>(p, vl, kL, kJ, kM, pol_first);
-        pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, true, pol_first, pol_last, c);
-      }
-    } else {
-      // few nodes have anything to do: find them (13 bytes per node), compact their indices in shared memory and
-      // run the node logic with FULL warps — the per-warp instruction cost of the logic does not depend on how
-      // many lanes are active, so scattered activity would otherwise cost as much as a saturated tick
-      Pre pre = {};
-      bool active = false;
-      if (vl < p.n_local) {
-        pre = prefetch_node<R1>(p, vl, kL, kJ, kM, pol_first);
-        active = pre.busy || pre.any || (p.probe_every && p.down_mask) || p.reap_now;
-      }
-      const u32 bal = __ballot_sync(0xffffffffu, active);
-      if (lane == 0) warp_cnt[wid] = __popc(bal);
-      __syncthreads();
-      u32 base = 0, total = 0;
-#pragma unroll
-      for (int w = 0; w < BLOCK / 32; ++w) { const u32 cw = warp_cnt[w]; base += (w < wid) ? cw : 0u; total += cw; }
-      if (active) { const u32 pos = base + __popc(bal & ((1u << lane) - 1u)); act_list[pos] = (u16)threadIdx.x; pre_s[threadIdx.x] = pre; }
-      __syncthreads();
-      if (threadIdx.x < total) {
-        const u32 tsel = act_list[threadIdx.x];
-        pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vbase + tsel, pre_s[tsel], kL, kJ, kM, mark, false, pol_first, pol_last, c);
-      }
-      __syncthreads();                         // the lists are reused by the next tile
+    if (vl < p.n_local) {
+      const Pre pre = prefetch_node<R1>(p, vl, kL, kJ, kM, pol_first);
+      pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, saturated, pol_first, pol_last, c);
     }
     if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + i] = 1;
     if (SHARDED) wrote_remote |= flush_xstage(p, xs);
