@@ -119,6 +119,7 @@ struct serfsim {
   void* cb_user = nullptr;
   std::vector<u8> reported;        // last status reported per slot
   int grid = 1;
+  int ctas_per_sm = 4;
   // multi-GPU
   u64* d_win_data[2] = {nullptr, nullptr};     // my receive windows [parity][world][win_cap]  (IPC-exported)
   u32* d_ctrl = nullptr;                       // my control block [parity][counts[8] | flags[8]] (IPC-exported)
@@ -463,7 +464,11 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
   const u32 ones[4] = {0x40000000u, 0x40000000u, 0x40000000u, 1u};   // multi-GPU: every inbox plane may hold entries, every tick is dense
   CUB(cudaMemcpy(h->d_ones, ones, 16, cudaMemcpyHostToDevice));
   CUB(cudaMemcpy(h->d_subj, h->subj.data(), h->R * 4, cudaMemcpyHostToDevice));
-  h->grid = tick_grid_size(h->count, h->R == 1 ? 4 : 3);
+  {
+    const char* e = getenv("SERFSIM_MINB");
+    h->ctas_per_sm = (h->R == 1) ? ((e && atoi(e) == 5) ? 5 : 4) : 3;
+  }
+  h->grid = tick_grid_size(h->count, h->ctas_per_sm);
   {
     // L2 set-aside for persisting (evict_last) lines: the randomly addressed inbox planes live there
     int max_persist = 0, max_window = 0;
@@ -557,7 +562,7 @@ int serfsim_set_topology_csr(serfsim_t* h, const uint64_t* row_ptr, const uint32
     const u32 need = std::max<u32>(h->max_tile_edges * 4u, 16u);
     if (use && h->R == 1 && need <= 48u * 1024u) h->stage_col_bytes = (need + 127u) & ~127u;
   }
-  h->grid = tick_grid_size(h->count, (h->stage_col_bytes || h->R > 1) ? 3 : 4);
+  h->grid = tick_grid_size(h->count, h->stage_col_bytes ? 3 : h->ctas_per_sm);
   h->has_topo = true;
   return 0;
 }

@@ -468,8 +468,8 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
 // Persistent CTAs; each owns a contiguous range of 256-node tiles.  A tile is processed only if it is
 // "hot": somebody delivered into it during the previous tick, it kept pending work (queued transmits,
 // suspicion timers), or a host operation targets it — otherwise not a single byte of it is touched.
-template <bool TRACE, int FMAX, bool SHARDED, bool R1>
-__global__ void __launch_bounds__(BLOCK, R1 ? 4 : 3) tick_kernel(const __grid_constant__ TickParams p) {
+template <bool TRACE, int FMAX, bool SHARDED, bool R1, int MB>
+__global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__ TickParams p) {
   __shared__ u8 hot_s[MAX_TILES_PER_CTA];
   __shared__ u64 red[8][BLOCK / 32];
   __shared__ __align__(16) unsigned char xs_mem[SHARDED ? sizeof(XStage) : 16];
@@ -909,8 +909,11 @@ static void launch_tick_v(const TickParams& p, int grid, cudaStream_t st) {
     launch_tick_tma<TRACE, FMAX, false>(p, grid, st);
     return;
   }
-  if (sharded) { if (r1) tick_kernel<TRACE, FMAX, true, true><<<grid, BLOCK, 0, st>>>(p); else tick_kernel<TRACE, FMAX, true, false><<<grid, BLOCK, 0, st>>>(p); }
-  else { if (r1) tick_kernel<TRACE, FMAX, false, true><<<grid, BLOCK, 0, st>>>(p); else tick_kernel<TRACE, FMAX, false, false><<<grid, BLOCK, 0, st>>>(p); }
+  static int mb5 = -1;
+  if (mb5 < 0) { const char* e = getenv("SERFSIM_MINB"); mb5 = (e && atoi(e) == 5) ? 1 : 0; }
+  if (sharded) { if (r1) tick_kernel<TRACE, FMAX, true, true, 4><<<grid, BLOCK, 0, st>>>(p); else tick_kernel<TRACE, FMAX, true, false, 3><<<grid, BLOCK, 0, st>>>(p); }
+  else if (r1) { if (mb5) tick_kernel<TRACE, FMAX, false, true, 5><<<grid, BLOCK, 0, st>>>(p); else tick_kernel<TRACE, FMAX, false, true, 4><<<grid, BLOCK, 0, st>>>(p); }
+  else tick_kernel<TRACE, FMAX, false, false, 3><<<grid, BLOCK, 0, st>>>(p);
 }
 void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st) {
   const bool small = p.fanout <= 4;          // the common fan-outs (3, 4) get the 4-wide target array

@@ -17,9 +17,15 @@ ap.add_argument("--degree", type=int, default=16)
 ap.add_argument("--waves", type=int, default=1)
 ap.add_argument("--runs", type=int, default=2)
 ap.add_argument("--out", default=None)
+ap.add_argument("--scenario", default="storm", choices=["storm", "churn"])
 a = ap.parse_args()
-sc = scenarios.dissemination_storm(a.nodes, a.degree, a.fanout, slots=a.slots, seed=1, waves=a.waves)
-g = sc.build(lambda n, s, **kw: GossipSim(n, s, **kw))
+if a.scenario == "churn":      # BASELINE configs[2]: small-world graph, 5 % of the nodes fail / rejoin, 8 tracked subjects
+    sc = scenarios.small_world_churn(a.nodes, a.degree, 0.1, 0.05, slots=a.slots, window=200, seed=1, fanout=a.fanout)
+    extra = dict(suspicion_mult=2, suspicion_max_timeout_mult=2, probe_interval_ticks=2)
+else:
+    sc = scenarios.dissemination_storm(a.nodes, a.degree, a.fanout, slots=a.slots, seed=1, waves=a.waves)
+    extra = {}
+g = sc.build(lambda n, s, **kw: GossipSim(n, s, **kw), **extra)
 for run in range(a.runs):
     g.reset(1); sc.schedule(g)
     g.set_tick_timing(run == a.runs - 1)
