@@ -106,21 +106,30 @@ def b_edge(fanout, p_dirty):
     return 4.0 + 32.0 / fanout + 32.0 + 32.0 * p_dirty
 
 
+_ORACLE_CACHE = {}
+
+
 def time_oracle(args, nodes, threads=None):
     """CPU baseline: the oracle (C++ port of the reference path) on a bounded sample of the workload,
-    node ranges split over `threads` host threads (default: every core of the box)."""
+    node ranges split over `threads` host threads (default: every core of the box).  The cluster (topology,
+    oracle handle) is built once and reused; a call times one reset + schedule + run to quiescence."""
     import ctypes
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_lib import lib, oracle_sim
     from serf_b200 import scenarios
     threads = threads or (os.cpu_count() or 1)
-    sc = scenarios.dissemination_storm(nodes, args.degree, args.fanout, slots=args.slots, seed=1, waves=args.waves)
-    o = oracle_sim(sc.n, sc.slots, **sc.cfg)
-    L = lib()
-    L.oracle_sim_set_threads.restype, L.oracle_sim_set_threads.argtypes = ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]
-    assert L.oracle_sim_set_threads(o._h, threads) == 0
-    o.set_topology(sc.row_ptr, sc.col); o.set_subjects(sc.subjects); o.reset(sc.cfg.get("seed", 1)); sc.schedule(o)
+    key = (nodes, threads)
+    if key not in _ORACLE_CACHE:
+        sc = scenarios.dissemination_storm(nodes, args.degree, args.fanout, slots=args.slots, seed=1, waves=args.waves)
+        o = oracle_sim(sc.n, sc.slots, **sc.cfg)
+        L = lib()
+        L.oracle_sim_set_threads.restype, L.oracle_sim_set_threads.argtypes = ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]
+        assert L.oracle_sim_set_threads(o._h, threads) == 0
+        o.set_topology(sc.row_ptr, sc.col); o.set_subjects(sc.subjects)
+        _ORACLE_CACHE[key] = (sc, o)
+    sc, o = _ORACLE_CACHE[key]
     t0 = time.perf_counter()
+    o.reset(sc.cfg.get("seed", 1)); sc.schedule(o)
     ticks, ok = o.run_until_converged(sc.max_ticks)
     dt = time.perf_counter() - t0
     st = o.stats()

@@ -13,10 +13,14 @@
 // Sends of tick t land in inbox parity t&1 and are consumed by Phase R of tick t+1, so a launch
 // never reads what it writes: bulk-synchronous, order-independent, bit-reproducible.
 //
-// Memory behaviour (HBM-bound integer work, no tensor cores): one thread per node streams its
-// R 32-byte records with 128-bit loads (a warp covers 1 KB contiguous per plane), the three
-// inbox planes with coalesced 32-bit loads, and scatters 32-bit RED.MAX to random peers; the
-// inbox planes are the only randomly addressed data and are sized to stay L2-resident.
+// Memory behaviour (HBM-bound integer work, no tensor cores): one thread per node; a node's 32-byte record is one
+// 256-bit load (LDG.E.256 = one DRAM sector, a warp covers 1 KB contiguous) and, if changed, one 256-bit store; node
+// word, busy byte, inbox words and row offsets are coalesced streams with an evict_first / no-L1-allocate policy; the
+// four neighbour gathers stay inside the node's own 64-byte CSR row; the sends are 32-bit RED.MAX to random peers with
+// an evict_last policy — the inbox planes are the only randomly addressed data and are sized to stay L2-resident.
+// Tiles (256 nodes) nobody delivered to and that hold no pending work are skipped outright in sparse ticks.
+// A TMA variant (tick_kernel_tma) stages whole tiles through cp.async.bulk + mbarrier; the multi-GPU variant stages
+// cross-shard entries in shared memory and stores them into the peer GPU's window over NVLink.
 #include <cstdlib>
 
 #include "tick_kernel.cuh"
