@@ -550,6 +550,7 @@ struct TickSim {
   std::vector<u32> timeout; RuleCtx cx;
   std::vector<serfsim_tick_row_t> trace;
   std::vector<u8> subj_up;      // ground truth per slot
+  std::vector<u16> watch;       // per node: bit s set iff subject s is in the node's neighbour list (only those nodes can probe it)
   std::vector<std::vector<Msg>> mail;   // messages sent in the previous tick: [producer range][consumer range]
   u32 chunk = 1;
   u64 tot_events = 0;
@@ -576,6 +577,13 @@ struct TickSim {
         r.st = cfg.init_status_ltime; r.inc = 1; r.status = ST_ALIVE; r.flags = 1; set_ml(r, ML_ALIVE, 0);
       }
     subj_up.assign(R, 1);
+  }
+  void compute_watch() {
+    watch.assign(N, 0);
+    if (row_ptr.empty()) return;
+    std::unordered_map<u32, u32> sl; for (u32 s = 0; s < R; ++s) sl[subj[s]] = s;
+    for (u32 v = 0; v < N; ++v)
+      for (u64 e = row_ptr[v]; e < row_ptr[v + 1]; ++e) { auto it = sl.find(col[e]); if (it != sl.end() && col[e] != v) watch[v] |= (u16)(1u << it->second); }
   }
   int slot_of(u32 nodeid) const { for (u32 s = 0; s < R; ++s) if (subj[s] == nodeid) return (int)s; return -1; }
 
@@ -656,7 +664,8 @@ struct TickSim {
       if (ev && ev->op == SERFSIM_OP_REJOIN) up_s = true;
       u32 targets[8], nt = 0; bool have_targets = false;
       u32 ptarget = 0; bool have_probe = false;
-      if (up_s && cfg.probe_interval_ticks && any_down && ((t + v) % cfg.probe_interval_ticks) == 0)
+      const u32 wmask = watch.empty() ? 0u : watch[v];
+      if (up_s && wmask && cfg.probe_interval_ticks && any_down && ((t + v) % cfg.probe_interval_ticks) == 0)
         have_probe = probe_target(v, t, &ptarget);
       u32 max_tx = 0;
       for (u32 s = 0; s < R; ++s) {
@@ -769,7 +778,7 @@ struct TickSim {
           }
           // pending?
           bool pend = (r.txl | r.txj | r.txm) || ml_state(r) == ML_SUSPECT ||
-                      (cfg.probe_interval_ticks && !subj_up[s] && !self && ml_state(r) == ML_ALIVE);
+                      (cfg.probe_interval_ticks && !subj_up[s] && !self && ((wmask >> s) & 1) && ml_state(r) == ML_ALIVE);   // a watcher that has not noticed yet
           if (pend) row.pending++;
         }
       }
@@ -808,8 +817,9 @@ struct TickSim {
             const View before = r;
             const View& q = srec[(size_t)s * N + u];
             const bool self = (subj[s] == v);
+            const u32 wmask = watch.empty() ? 0u : watch[v];
             const bool was_pending = (r.txl | r.txj | r.txm) || ml_state(r) == ML_SUSPECT ||
-                                     (cfg.probe_interval_ticks && !subj_up[s] && !self && ml_state(r) == ML_ALIVE);
+                                     (cfg.probe_interval_ticks && !subj_up[s] && !self && ((wmask >> s) & 1) && ml_state(r) == ML_ALIVE);
             if (known(q)) {
               const u8 qs = ml_state(q);
               if (qs == ML_ALIVE) v_ml_alive(r, q.inc, self, cx);
@@ -824,7 +834,7 @@ struct TickSim {
             { View a = before, b = r; a.st = b.st = 0;       // status_time creeps by design (leave at status_ltime + 1): not a change
               if (memcmp(&a, &b, sizeof(View)) != 0) row.changed++; }
             const bool now_pending = (r.txl | r.txj | r.txm) || ml_state(r) == ML_SUSPECT ||
-                                     (cfg.probe_interval_ticks && !subj_up[s] && !self && ml_state(r) == ML_ALIVE);
+                                     (cfg.probe_interval_ticks && !subj_up[s] && !self && ((wmask >> s) & 1) && ml_state(r) == ML_ALIVE);
             if (now_pending && !was_pending) row.pending++;
             if (!now_pending && was_pending) row.pending--;
           }
@@ -945,12 +955,13 @@ ORC int oracle_sim_set_topology_csr(void* p, const u64* row_ptr, const u32* col_
   auto* s = (TickSim*)p; s->row_ptr.assign(row_ptr, row_ptr + s->N + 1); s->col.assign(col_idx, col_idx + row_ptr[s->N]);
   for (u32 c : s->col) if (c >= s->N) { g_err = "col_idx out of range"; return SERFSIM_E_INVAL; }
   for (u32 v = 0; v < s->N; ++v) if (row_ptr[v + 1] - row_ptr[v] > 65535) { g_err = "node degree > 65535"; return SERFSIM_E_INVAL; }
+  s->compute_watch();
   return 0;
 }
 ORC int oracle_sim_set_subjects(void* p, const u32* subjects) {
   auto* s = (TickSim*)p;
   for (u32 i = 0; i < s->R; ++i) { if (subjects[i] >= s->N) return SERFSIM_E_INVAL; for (u32 j = 0; j < i; ++j) if (subjects[j] == subjects[i]) return SERFSIM_E_INVAL; }
-  s->subj.assign(subjects, subjects + s->R); return 0;
+  s->subj.assign(subjects, subjects + s->R); s->compute_watch(); return 0;
 }
 ORC int oracle_sim_reset(void* p, u64 seed) { ((TickSim*)p)->reset(seed); return 0; }
 ORC int oracle_sim_inject(void* p, u32 tick, u32 op, u32 node, u32 slot) {

@@ -82,6 +82,8 @@ struct serfsim {
   u32* d_inbox[2] = {nullptr, nullptr};   // [3][R][count]
   u64* d_node = nullptr;           // [count]
   u8* d_busy = nullptr;            // [stride] per-node busy byte
+  u16* d_watch = nullptr;          // [stride] per-node watcher mask (subjects among the node's neighbours)
+  bool watch_dirty = true;
   uint4* d_snap_rec = nullptr;     // push-pull rounds: end-of-tick snapshot of the records …
   u64* d_snap_node = nullptr;      // … and of the node words
   u8* d_hot[2] = {nullptr, nullptr};      // [n_tiles] per tick parity
@@ -219,7 +221,7 @@ int launch_ticks(serfsim* h, u32 n) {
     p.rules = h->rules;
     for (u32 s = 0; s < h->R; ++s) p.subj[s] = h->subj[s];
     p.rec = h->d_rec; p.inbox_rd = h->d_inbox[(t & 1) ^ 1]; p.inbox_wr = h->d_inbox[t & 1];
-    p.node_state = h->d_node; p.busy = h->d_busy; p.row_ptr = h->d_rowptr; p.col = h->d_col;
+    p.node_state = h->d_node; p.busy = h->d_busy; p.watch = h->d_watch; p.row_ptr = h->d_rowptr; p.col = h->d_col;
     p.ev_node = h->d_ev_node; p.ev_op = h->d_ev_op; p.ev_slot = h->d_ev_slot;
     p.row = h->d_trace + (size_t)t * 8;
     p.kinds_prev = h->d_kinds + (size_t)t * 4;
@@ -230,7 +232,7 @@ int launch_ticks(serfsim* h, u32 n) {
     p.reap_now = (h->cfg.reap_interval_ticks && ((t + 1) % h->cfg.reap_interval_ticks) == 0) ? 1u : 0u;
     p.tombstone_ticks = h->cfg.tombstone_timeout_ticks; p.reconnect_ticks = h->cfg.reconnect_timeout_ticks; p.intent_ticks = h->cfg.recent_intent_timeout_ticks;
     p.stride = h->stride; p.n_tiles = h->n_tiles; p.tiles_per_cta = (h->n_tiles + h->grid - 1) / h->grid;
-    p.force_all = (h->cfg.trace != 0) || (h->cfg.probe_interval_ticks && p.down_mask) || h->no_skip || p.reap_now;
+    p.force_all = (h->cfg.trace != 0) || h->no_skip || p.reap_now;
     const u32 xpar = h->xepoch & 1;
     p.world = (u32)h->cfg.world_size; p.rank = (u32)h->cfg.rank; p.shard_size = h->shard_size; p.win_cap = h->win_cap;
     p.win_data = h->d_peer_data[xpar]; p.send_count = h->d_send_count;
@@ -337,6 +339,18 @@ int fire_events(serfsim* h) {
   return 0;
 }
 
+// Watcher masks depend on topology and subjects; the busy bit / hot tiles of the watchers are re-applied after every reset.
+int refresh_watchers(serfsim* h) {
+  if (!h->has_topo) return 0;
+  if (h->watch_dirty) {
+    launch_compute_watch(h->d_rowptr, h->d_col, h->d_subj, h->R, h->first, h->count, h->d_watch, h->stream);
+    h->watch_dirty = false;
+  }
+  launch_apply_watch(h->d_watch, h->count, h->d_busy, h->d_hot[0], h->d_hot[1], h->stream);
+  CU(cudaGetLastError());
+  return 0;
+}
+
 int do_reset(serfsim* h, u64 seed) {
   h->cfg.seed = seed; h->tick = 0; h->ops.clear(); h->op_keys.clear(); h->ops_dirty = false; h->rows.clear();
   h->up_mask = (h->R >= 32) ? 0xffffffffu : ((1u << h->R) - 1);
@@ -354,6 +368,7 @@ int do_reset(serfsim* h, u64 seed) {
     CU(cudaMemsetAsync(h->d_kinds, 0, ((size_t)h->trace_cap + 1) * 4 * sizeof(u32), h->stream));
   }
   if (h->d_send_count) CU(cudaMemsetAsync(h->d_send_count, 0, sizeof(u32) * 8, h->stream));
+  { int rc = refresh_watchers(h); if (rc) return rc; }
   CU(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -361,7 +376,7 @@ int do_reset(serfsim* h, u64 seed) {
 void free_all(serfsim* h) {
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   for (cudaEvent_t e : h->tick_ev) cudaEventDestroy(e);
-  cudaFree(h->d_hot[0]); cudaFree(h->d_hot[1]); cudaFree(h->d_busy); cudaFree(h->d_snap_rec); cudaFree(h->d_snap_node);
+  cudaFree(h->d_hot[0]); cudaFree(h->d_hot[1]); cudaFree(h->d_busy); cudaFree(h->d_watch); cudaFree(h->d_snap_rec); cudaFree(h->d_snap_node);
   cudaFree(h->d_rec); cudaFree(h->d_inbox[0]); cudaFree(h->d_inbox[1]); cudaFree(h->d_node); cudaFree(h->d_rowptr); cudaFree(h->d_col);
   cudaFree(h->d_ev_node); cudaFree(h->d_ev_op); cudaFree(h->d_ev_slot); cudaFree(h->d_trace); cudaFree(h->d_kinds); cudaFree(h->d_ones);
   cudaFree(h->d_overflow); cudaFree(h->d_subj); cudaFree(h->d_scratch); cudaFree(h->d_stage);
@@ -457,6 +472,8 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
   CUB(cudaMemset(h->d_node, 0, (size_t)h->stride * 8));
   h->n_tiles = (h->count + 255) / 256;
   CUB(cudaMalloc(&h->d_busy, h->stride));
+  CUB(cudaMalloc(&h->d_watch, (size_t)h->stride * 2));
+  CUB(cudaMemset(h->d_watch, 0, (size_t)h->stride * 2));
   CUB(cudaMalloc(&h->d_hot[0], h->n_tiles)); CUB(cudaMalloc(&h->d_hot[1], h->n_tiles));
   CUB(cudaMalloc(&h->d_overflow, 4)); CUB(cudaMalloc(&h->d_subj, MAX_SLOTS * 4)); CUB(cudaMalloc(&h->d_scratch, 64 * 8));
   CUB(cudaMalloc(&h->d_stage, (size_t)h->count * 8));
@@ -564,7 +581,8 @@ int serfsim_set_topology_csr(serfsim_t* h, const uint64_t* row_ptr, const uint32
   }
   h->grid = tick_grid_size(h->count, h->stage_col_bytes ? 3 : h->ctas_per_sm);
   h->has_topo = true;
-  return 0;
+  h->watch_dirty = true;
+  return refresh_watchers(h);
 }
 
 int serfsim_set_subjects(serfsim_t* h, const uint32_t* subjects) {
@@ -576,7 +594,12 @@ int serfsim_set_subjects(serfsim_t* h, const uint32_t* subjects) {
   }
   h->subj.assign(subjects, subjects + h->R);
   CU(cudaMemcpy(h->d_subj, h->subj.data(), h->R * 4, cudaMemcpyHostToDevice));
-  return 0;
+  h->watch_dirty = true;
+  // tick 0 with a clean state: re-derive the watchers' busy bits / hot tiles for the new subjects
+  CU(cudaMemsetAsync(h->d_busy, 0, h->stride, h->stream));
+  CU(cudaMemsetAsync(h->d_hot[0], 0, h->n_tiles, h->stream));
+  CU(cudaMemsetAsync(h->d_hot[1], 0, h->n_tiles, h->stream));
+  return refresh_watchers(h);
 }
 
 int serfsim_reset(serfsim_t* h, uint64_t seed) {

@@ -298,7 +298,8 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   if (STAGED) { mL = kL ? sv.inL[lt] : 0u; mJ = kJ ? sv.inJ[lt] : 0u; mM = kM ? sv.inM[lt] : 0u; }
 
   // ---- idle exit: nothing received (any slot), nothing queued, no timer, no host operation, no probe duty ----
-  if (!TRACE && !STAGED && busy == 0 && !pre.any && !(p.probe_every && p.down_mask) && !p.reap_now) return false;
+  if (!TRACE && !STAGED && busy == 0 && !pre.any && !p.reap_now) return false;
+  const u32 wmask = (busy & 4) ? (u32)p.watch[vl] : 0u;     // subjects this node can probe (it has them as neighbours)
   if (!upfront) load_state();
 
   u32 clock = (u32)ns;
@@ -320,7 +321,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   // SWIM probe target of this round (only matters while some tracked subject is down)
   bool have_probe = false;
   u32 ptarget = 0;
-  if (up_s && p.probe_every && p.down_mask && ((t + v) % p.probe_every) == 0 && deg) {
+  if (up_s && wmask && p.probe_every && p.down_mask && ((t + v) % p.probe_every) == 0 && deg) {
     u32 w[4];
     philox4x32_10(t, v, 0, DOMAIN_PROBE, p.seed_lo, p.seed_hi, w);
     const u32 e = row0 + (((w[0] & 0xffffu) * deg) >> 16);
@@ -450,7 +451,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
         r.mlstate = ML_LEFT; r.qfrom = 0; r.txm = limit; sstate = SS_LEFT;
       }
       const bool pend = (r.txl | r.txj | r.txm) || r.mlstate == ML_SUSPECT ||
-                        (p.probe_every && ((p.down_mask >> s) & 1) && !self && r.mlstate == ML_ALIVE);
+                        (p.probe_every && ((p.down_mask >> s) & 1) && !self && ((wmask >> s) & 1) && r.mlstate == ML_ALIVE);   // a watcher that has not noticed yet
       c.pending += pend ? 1 : 0;
       any_pending |= pend;
     }
@@ -464,9 +465,9 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   if (TRACE) c.hash += node_hash((u64)R * p.n_global + v, ns2);
   if (clock >= LTIME_LIMIT) *p.overflow = 1;
   c.packets += min(nt, max_tx);
-  const u32 busy2 = any_pending ? 1u : 0u;                 // the op bit is consumed
+  const u32 busy2 = (any_pending ? 1u : 0u) | (busy & 4u);   // the op bit is consumed, the watcher bit is static
   if (busy2 != busy) p.busy[vl] = (u8)busy2;
-  return any_pending;
+  return any_pending || (busy & 4u);                        // watchers keep their tile hot
 }
 
 // Persistent CTAs; each owns a contiguous range of 256-node tiles.  A tile is processed only if it is
@@ -688,6 +689,7 @@ __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__
     const u32 cu = (u32)nu;
     if (cu > 0) witness(clock, cu - 1);
     bool any_pending = false;
+    const u32 wmask = p.watch[vl];
     for (u32 s = 0; s < p.R; ++s) {
       const size_t iv = (size_t)s * p.stride + vl, iu = (size_t)s * p.stride + ul;
       const uint4 a0 = p.rec[2 * iv], b0 = p.rec[2 * iv + 1];
@@ -695,7 +697,7 @@ __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__
       unpack(a0, b0, r);
       unpack(snap_rec[2 * iu], snap_rec[2 * iu + 1], q);
       const bool self = (p.subj[s] == v);
-      const bool was = (r.txl | r.txj | r.txm) || r.mlstate == ML_SUSPECT || (p.probe_every && ((p.down_mask >> s) & 1) && !self && r.mlstate == ML_ALIVE);
+      const bool was = (r.txl | r.txj | r.txm) || r.mlstate == ML_SUSPECT || (p.probe_every && ((p.down_mask >> s) & 1) && !self && ((wmask >> s) & 1) && r.mlstate == ML_ALIVE);
       if (q.flags & 1) {
         if (q.mlstate == ML_ALIVE) ml_alive(r, q.inc, self, p.rules.limit);
         else if (q.mlstate == ML_LEFT) ml_dead(r, q.inc, true, p.tick, self, p.rules.limit);
@@ -712,7 +714,7 @@ __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__
       if (ch) { p.rec[2 * iv] = a1; p.rec[2 * iv + 1] = b1; }
       if ((a1.y ^ a0.y) | (a1.z ^ a0.z) | (a1.w ^ a0.w) | (b1.x ^ b0.x) | (b1.y ^ b0.y) | (b1.z ^ b0.z) | (b1.w ^ b0.w)) d_changed++;   // status_time creep is not a change
       if (TRACE && ch) d_hash += rec_hash((u64)s * p.n_global + v, a1, b1) - rec_hash((u64)s * p.n_global + v, a0, b0);
-      const bool now = (r.txl | r.txj | r.txm) || r.mlstate == ML_SUSPECT || (p.probe_every && ((p.down_mask >> s) & 1) && !self && r.mlstate == ML_ALIVE);
+      const bool now = (r.txl | r.txj | r.txm) || r.mlstate == ML_SUSPECT || (p.probe_every && ((p.down_mask >> s) & 1) && !self && ((wmask >> s) & 1) && r.mlstate == ML_ALIVE);
       d_pending += (now ? 1 : 0) - (was ? 1 : 0);
       any_pending |= now;
       if (r.inc >= INC_LIMIT) *p.overflow = 1;
@@ -723,7 +725,7 @@ __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__
       if (TRACE) d_hash += node_hash((u64)p.R * p.n_global + v, ns2) - node_hash((u64)p.R * p.n_global + v, ns);
     }
     if (clock >= LTIME_LIMIT) *p.overflow = 1;
-    if (any_pending) { p.busy[vl] = 1; p.hot_wr[vl >> TILE_SHIFT] = 1; }
+    if (any_pending) { p.busy[vl] = (u8)(1u | (wmask ? 4u : 0u)); p.hot_wr[vl >> TILE_SHIFT] = 1; }
   }
   const u64 c = warp_sum64((u64)d_changed), q = warp_sum64((u64)d_pending), h = TRACE ? warp_sum64(d_hash) : 0;
   if ((threadIdx.x & 31) == 0) {
@@ -780,6 +782,27 @@ __global__ void __launch_bounds__(BLOCK) drain_kernel(const __grid_constant__ Dr
   if ((threadIdx.x & 31) == 0 && seen) {
     for (u32 k = 0; k < 3; ++k) if ((seen >> k) & 1) atomicAdd(p.kinds_cur + k, 1u);
   }
+}
+
+// watch[v]: bit s set iff subject s appears in node v's neighbour list — only such nodes can ever pick it as a probe
+// target, so they alone evaluate the SWIM probe (and stay scheduled while it is down).
+__global__ void compute_watch_kernel(const u32* __restrict__ row_ptr, const u32* __restrict__ col, const u32* __restrict__ subj, u32 R, u32 first, u32 n_local, u16* watch) {
+  const u32 vl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (vl >= n_local) return;
+  u32 m = 0;
+  const u32 v = first + vl;
+  for (u32 e = row_ptr[vl]; e < row_ptr[vl + 1]; ++e) {
+    const u32 c = col[e];
+    if (c == v) continue;
+    for (u32 s = 0; s < R; ++s) m |= (c == subj[s]) ? (1u << s) : 0u;
+  }
+  watch[vl] = (u16)m;
+}
+__global__ void apply_watch_kernel(const u16* __restrict__ watch, u32 n_local, u8* busy, u8* hot0, u8* hot1) {
+  const u32 vl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (vl >= n_local || watch[vl] == 0) return;
+  busy[vl] |= 4;
+  hot0[vl >> TILE_SHIFT] = 1; hot1[vl >> TILE_SHIFT] = 1;
 }
 
 __global__ void init_state_kernel(uint4* rec, u64* node_state, u32 n_local, u32 stride, u32 R, u32 init_st, u32 init_clock) {
@@ -927,6 +950,12 @@ void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st) {
 void launch_pushpull(const TickParams& p, const uint4* snap_rec, const u64* snap_node, bool trace, cudaStream_t st) {
   if (trace) pushpull_kernel<true><<<148 * 8, BLOCK, 0, st>>>(p, snap_rec, snap_node);
   else pushpull_kernel<false><<<148 * 8, BLOCK, 0, st>>>(p, snap_rec, snap_node);
+}
+void launch_compute_watch(const u32* row_ptr, const u32* col, const u32* subj_dev, u32 R, u32 first, u32 n_local, u16* watch, cudaStream_t st) {
+  compute_watch_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(row_ptr, col, subj_dev, R, first, n_local, watch);
+}
+void launch_apply_watch(const u16* watch, u32 n_local, u8* busy, u8* hot0, u8* hot1, cudaStream_t st) {
+  apply_watch_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(watch, n_local, busy, hot0, hot1);
 }
 void launch_drain(const DrainParams& p, cudaStream_t st) { drain_kernel<<<148 * 8, BLOCK, 0, st>>>(p); }
 void launch_publish(const PublishParams& p, cudaStream_t st) { publish_kernel<<<1, 32, 0, st>>>(p); }

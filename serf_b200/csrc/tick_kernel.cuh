@@ -18,7 +18,8 @@ struct TickParams {
   u32* inbox_rd;              // [3][R][n_local] reduced inbox filled by the previous tick (value+1, 0 = empty)
   u32* inbox_wr;              // [3][R][n_local] inbox the sends of this tick reduce into
   u64* node_state;            // [n_local]  clock | up | SerfState
-  u8* busy;                   // [n_local]  bit 0: the node holds pending work (queued transmits, suspicion timer); bit 1: host op this tick
+  u8* busy;                   // [n_local]  bit 0: pending work (queued transmits, suspicion timer); bit 1: host op this tick; bit 2: watcher (static)
+  const u16* watch;           // [n_local]  bit s: subject s is in the node's neighbour list (only such nodes can probe it)
   const u32* row_ptr;         // [n_local+1] CSR offsets into col (shard-local)
   const u32* col;             // neighbour ids (global)
   const u32* ev_node;         // host operations, sorted by tick
@@ -68,6 +69,8 @@ void launch_extract(const uint4* rec, const u64* node_state, u32 n_local, u32 st
 void launch_state_hash(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 n_global, u32 R, u64* out, cudaStream_t st);
 void launch_summary(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 R, const u32* subj_dev, u64* out /*[2 + 2*R + 2]*/, cudaStream_t st);
 int tick_grid_size(u32 n_local, int ctas_per_sm);
+void launch_compute_watch(const u32* row_ptr, const u32* col, const u32* subj_dev, u32 R, u32 first, u32 n_local, u16* watch, cudaStream_t st);
+void launch_apply_watch(const u16* watch, u32 n_local, u8* busy, u8* hot0, u8* hot1, cudaStream_t st);
 
 enum { EXTRACT_STATUS = 0, EXTRACT_STATUS_LTIME = 1, EXTRACT_CLOCK = 2, EXTRACT_INC = 3, EXTRACT_ML = 4 };
 
