@@ -552,6 +552,9 @@ struct TickSim {
   std::vector<u8> subj_up;      // ground truth per slot
   std::vector<u16> watch;       // per node: bit s set iff subject s is in the node's neighbour list (only those nodes can probe it)
   std::vector<std::vector<Msg>> mail;   // messages sent in the previous tick: [producer range][consumer range]
+  std::vector<std::vector<Msg>> mail_next;                       // the boxes being filled this tick (capacity is reused)
+  struct Scratch { std::vector<u32> head, pos; std::vector<Msg> byd; };
+  std::vector<Scratch> scratch;                                  // per-thread buffers, reused across ticks
   u32 chunk = 1;
   u64 tot_events = 0;
   int threads = 1;
@@ -567,7 +570,7 @@ struct TickSim {
     cx.timeout = timeout.data();
   }
   void reset(u64 seed) {
-    cfg.seed = seed; tick = 0; events.clear(); event_keys.clear(); ev_by_tick.clear(); any_event = false; max_event_tick = 0; trace.clear(); mail.clear(); tot_events = 0;
+    cfg.seed = seed; tick = 0; events.clear(); event_keys.clear(); ev_by_tick.clear(); any_event = false; max_event_tick = 0; mail_next.clear(); trace.clear(); mail.clear(); tot_events = 0;
     chunk = (N + threads - 1) / threads;
     rec.assign((size_t)R * N, View{});
     node.assign(N, NodeB{cfg.init_clock, 1, SS_ALIVE});
@@ -628,7 +631,10 @@ struct TickSim {
     const u32 t = tick;
     const u32 T = (u32)threads;
     if (mail.size() != (size_t)T * T) { mail.assign((size_t)T * T, {}); }
-    std::vector<std::vector<Msg>> next((size_t)T * T);
+    if (mail_next.size() != (size_t)T * T) { mail_next.assign((size_t)T * T, {}); }
+    for (auto& b : mail_next) b.clear();
+    if (scratch.size() != T) scratch.assign(T, Scratch{});
+    std::vector<std::vector<Msg>>& next = mail_next;
     // events of this tick
     std::vector<EventB> evs;
     std::unordered_map<u32, EventB> ev_of;
@@ -647,12 +653,15 @@ struct TickSim {
     const u32 v0 = c * chunk, v1 = std::min<u64>(N, (u64)(c + 1) * chunk);
     if (v0 >= v1) return;
     // ---- bucket last tick's messages for my id range by destination (stable counting sort) ----
-    std::vector<u32> head(v1 - v0 + 1, 0);
+    Scratch& sx = scratch[c];
+    std::vector<u32>& head = sx.head;
+    head.assign(v1 - v0 + 1, 0);
     size_t total = 0;
     for (u32 p = 0; p < T; ++p) { for (auto& m : mail[(size_t)p * T + c]) head[m.dst - v0 + 1]++; total += mail[(size_t)p * T + c].size(); }
     for (u32 i = 0; i < v1 - v0; ++i) head[i + 1] += head[i];
-    std::vector<Msg> byd(total);
-    { std::vector<u32> pos(head.begin(), head.end() - 1); for (u32 p = 0; p < T; ++p) for (auto& m : mail[(size_t)p * T + c]) byd[pos[m.dst - v0]++] = m; }
+    std::vector<Msg>& byd = sx.byd;
+    byd.resize(total);
+    { std::vector<u32>& pos = sx.pos; pos.assign(head.begin(), head.end() - 1); for (u32 p = 0; p < T; ++p) for (auto& m : mail[(size_t)p * T + c]) byd[pos[m.dst - v0]++] = m; }
     auto post = [&](const Msg& m) { next[(size_t)c * T + owner_of(m.dst)].push_back(m); };
     for (u32 v = v0; v < v1; ++v) {
       NodeB& nd = node[v];
@@ -789,7 +798,7 @@ struct TickSim {
     };
     if (T == 1) work(0);
     else { std::vector<std::thread> th; for (u32 c = 0; c < T; ++c) th.emplace_back(work, c); for (auto& x : th) x.join(); }
-    mail.swap(next);
+    mail.swap(mail_next);
     // ---------------- anti-entropy round: memberlist push-pull + SerfDelegate::merge_remote_state ----------------
     // (serf/delegate.rs:386-554; memberlist mergeState [external]).  Every push_pull_interval ticks each up node
     // pulls the end-of-tick state of ONE random neighbour and merges it: clock witness(ltime-1); per subject the
@@ -1025,6 +1034,6 @@ ORC int oracle_sim_stats(void* p, serfsim_stats_t* o) {
 ORC int oracle_sim_set_threads(void* p, int n) {
   auto* s = (TickSim*)p;
   if (n < 1 || s->tick != 0) return SERFSIM_E_INVAL;
-  s->threads = n; s->chunk = (s->N + n - 1) / n; s->mail.clear();
+  s->threads = n; s->chunk = (s->N + n - 1) / n; s->mail.clear(); s->mail_next.clear(); s->scratch.clear();
   return 0;
 }
