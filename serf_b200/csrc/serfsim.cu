@@ -112,6 +112,8 @@ struct serfsim {
   u32 stage_col_bytes = 0;         // 0: direct-load kernel; else bytes of CSR per TMA stage
   u32 max_tile_edges = 0;          // largest 16-byte-aligned CSR span of one 256-node tile (sizes the TMA stage)
   std::vector<serfsim_tick_row_t> rows;   // rows pulled from the device so far
+  serfsim_tick_row_t* pin_rows = nullptr;  // pinned staging for the convergence loop (2 chunks)
+  cudaEvent_t chunk_ev[2] = {nullptr, nullptr};
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timing_open = false;
@@ -312,7 +314,10 @@ int pull_rows(serfsim* h) {                     // bring rows [rows.size(), tick
   const u32 n = h->tick - have;
   h->rows.resize(h->tick);
   CU(cudaMemcpy(h->rows.data() + have, h->d_trace + (size_t)have * 8, (size_t)n * sizeof(serfsim_tick_row_t), cudaMemcpyDeviceToHost));
-  if (h->cfg.world_size > 1) h->allreduce(h->comm_user, (uint64_t*)(h->rows.data() + have), n * 8);
+  if (h->cfg.world_size > 1) {
+    if (!h->allreduce) return fail(SERFSIM_E_COMM, "world_size > 1: serfsim_comm_set_hooks was not called");
+    h->allreduce(h->comm_user, (uint64_t*)(h->rows.data() + have), n * 8);
+  }
   return 0;
 }
 
@@ -382,6 +387,8 @@ void free_all(serfsim* h) {
   cudaFree(h->d_overflow); cudaFree(h->d_subj); cudaFree(h->d_scratch); cudaFree(h->d_stage);
   for (int par = 0; par < 2; ++par) { cudaFree(h->d_win_data[par]); cudaFree(h->d_peer_data[par]); }
   cudaFree(h->d_ctrl); cudaFree(h->d_send_count); cudaFree(h->d_peer_ctrl);
+  if (h->pin_rows) cudaFreeHost(h->pin_rows);
+  for (int i = 0; i < 2; ++i) if (h->chunk_ev[i]) cudaEventDestroy(h->chunk_ev[i]);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -642,6 +649,54 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
   auto boundary = [&](u32 t) { return (pp && (t + 1) % pp == 0) || (reap && (t + 1) % reap == 0); };
   const u32 start = h->tick;
   int rc = 0;
+  if (h->cfg.world_size == 1 && !pp && !reap && !getenv("SERFSIM_NO_SPECULATE")) {
+    // Pipelined convergence check (single GPU, no anti-entropy / reaper ticks): chunk k+1 is launched before the rows
+    // of chunk k are inspected, so the GPU never waits for the host.  Ticks past the first quiescent one are no-ops on
+    // a quiescent cluster and are rewound, exactly as in the synchronous loop below.
+    constexpr u32 MAXC = 16;
+    chunk = std::min(chunk, MAXC);
+    if (!h->pin_rows) { CU(cudaMallocHost(&h->pin_rows, 2 * MAXC * sizeof(serfsim_tick_row_t))); CU(cudaEventCreate(&h->chunk_ev[0])); CU(cudaEventCreate(&h->chunk_ev[1])); }
+    if ((rc = pull_rows(h))) return rc;                       // rows of earlier steps
+    struct Chunk { u32 from, n; };
+    Chunk cur{0, 0}, nxt{0, 0};
+    int slot = 0;
+    auto launch = [&](Chunk& c, int sl) -> int {
+      c.from = h->tick; c.n = std::min(chunk, max_ticks - (h->tick - start));
+      if (!c.n) return 0;
+      int r = launch_ticks(h, c.n);
+      if (r) return r;
+      CU(cudaMemcpyAsync(h->pin_rows + (size_t)sl * MAXC, h->d_trace + (size_t)c.from * 8, (size_t)c.n * sizeof(serfsim_tick_row_t), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaEventRecord(h->chunk_ev[sl], h->stream));
+      return 0;
+    };
+    if ((rc = launch(cur, slot))) return rc;
+    while (cur.n) {
+      if ((rc = launch(nxt, slot ^ 1))) return rc;              // speculative: may turn out to be all no-ops
+      CU(cudaEventSynchronize(h->chunk_ev[slot]));
+      h->rows.resize(cur.from + cur.n);
+      memcpy(h->rows.data() + cur.from, h->pin_rows + (size_t)slot * MAXC, (size_t)cur.n * sizeof(serfsim_tick_row_t));
+      for (u32 t = cur.from; t < cur.from + cur.n; ++t) {
+        const serfsim_tick_row_t& r = h->rows[t];
+        if (r.pending == 0 && r.edge_updates == 0 && !future_ops(h, t)) {
+          CU(cudaStreamSynchronize(h->stream));                 // the speculative chunk (no-ops) has drained
+          if (h->tick > t + 1) {
+            CU(cudaMemsetAsync(h->d_trace + (size_t)(t + 1) * 8, 0, (size_t)(h->tick - t - 1) * 8 * sizeof(u64), h->stream));
+            h->tick = t + 1; h->rows.resize(t + 1);
+          }
+          if ((rc = finish_timing(h))) return rc;
+          if ((rc = check_overflow(h))) return rc;
+          if (ticks_out) *ticks_out = t;
+          return fire_events(h);
+        }
+      }
+      cur = nxt; nxt = Chunk{0, 0}; slot ^= 1;
+    }
+    if ((rc = finish_timing(h))) return rc;
+    if ((rc = check_overflow(h))) return rc;
+    if (ticks_out) *ticks_out = h->tick;
+    if ((rc = fire_events(h))) return rc;
+    return 1;
+  }
   while (h->tick - start < max_ticks) {
     u32 n = std::min(chunk, max_ticks - (h->tick - start));
     for (u32 k = 1; k < n; ++k) if (boundary(h->tick + k)) { n = k; break; }
@@ -710,7 +765,10 @@ int serfsim_state_hash(serfsim_t* h, uint64_t* out) {
   launch_state_hash(h->d_rec, h->d_node, h->count, h->stride, h->first, h->N, h->R, h->d_scratch, h->stream);
   CU(cudaMemcpyAsync(out, h->d_scratch, 8, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  if (h->cfg.world_size > 1) h->allreduce(h->comm_user, out, 1);
+  if (h->cfg.world_size > 1) {
+    if (!h->allreduce) return fail(SERFSIM_E_COMM, "world_size > 1: serfsim_comm_set_hooks was not called");
+    h->allreduce(h->comm_user, out, 1);
+  }
   return 0;
 }
 
