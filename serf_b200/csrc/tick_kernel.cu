@@ -505,17 +505,27 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
     hot_s[i] = (f || all_hot) ? 1 : 0;
   }
   __syncthreads();
-  for (u32 i = 0; i < ntile; ++i) {
-    if (!hot_s[i]) continue;
-    const u32 vbase = (tile0 + i) << TILE_SHIFT;
-    const u32 vl = vbase + threadIdx.x;
+  // Walk the hot tiles of this CTA.  The 13 "is there anything to do" bytes of the NEXT hot tile (busy byte, inbox
+  // words) are requested before the current tile is processed, so an idle tile costs no exposed round trip.
+  auto prefetch_tile = [&](u32 ti) -> Pre {
+    const u32 vn = ((tile0 + ti) << TILE_SHIFT) + threadIdx.x;
+    return vn < p.n_local ? prefetch_node<R1>(p, vn, kL, kJ, kM, pol_first) : Pre{};
+  };
+  u32 i = 0;
+  while (i < ntile && !hot_s[i]) ++i;
+  Pre pre_next = {};
+  if (i < ntile) pre_next = prefetch_tile(i);
+  while (i < ntile) {
+    const Pre pre = pre_next;
+    u32 j = i + 1;
+    while (j < ntile && !hot_s[j]) ++j;
+    if (j < ntile) pre_next = prefetch_tile(j);
+    const u32 vl = ((tile0 + i) << TILE_SHIFT) + threadIdx.x;
     bool pend = false;
-    if (vl < p.n_local) {
-      const Pre pre = prefetch_node<R1>(p, vl, kL, kJ, kM, pol_first);
-      pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, saturated, pol_first, pol_last, c);
-    }
+    if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, saturated, pol_first, pol_last, c);
     if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + i] = 1;
     if (SHARDED) wrote_remote |= flush_xstage(p, xs);
+    i = j;
   }
   if (SHARDED && wrote_remote) __threadfence_system();   // peer-window stores are performed before the publish kernel raises the flags
   // block reduction (warp shuffles, then shared memory) → one atomic per counter per CTA.
