@@ -326,6 +326,18 @@ struct RefNode {
     }
   }
 
+  // serf/delegate.rs:386-425 local_state: {ltime: clock.time(), status_ltimes: every member's status_time, left_members: ids of
+  // the left list, event_ltime, query_ltime} (the event ring itself is out of scope)
+  u32 local_state(u64* pp_ltime, u64* ids, u64* ltimes, u32 cap, u64* left, u32 cap_left, u32* n_left, u64* event_ltime, u64* query_ltime) const {
+    *pp_ltime = clock.time(); *event_ltime = event_clock.time(); *query_ltime = query_clock.time();
+    u32 n = 0;
+    for (auto& kv : states) { if (n < cap) { ids[n] = kv.first; ltimes[n] = kv.second.status_time; } ++n; }
+    u32 nl = 0;
+    for (auto& m : left_members) { if (nl < cap_left) left[nl] = m.first; ++nl; }
+    *n_left = nl;
+    return n;
+  }
+
   // Local API — serf/api.rs:318-361 (join, after memberlist.join), :422-499 (leave),
   // base.rs:454-480 (force_leave).  has_alive_members(): base.rs:346-359.
   bool has_alive_members() const {
@@ -911,6 +923,9 @@ ORC int ref_recent_intent(void* p, u64 id, int ty, u64* ltime) { return ((RefNod
 ORC void ref_reap_intents(void* p, int64_t now_ms, int64_t timeout_ms) { ((RefNode*)p)->reap_intents(now_ms, timeout_ms); }
 ORC void ref_merge_remote_state(void* p, u64 pp_ltime, const u64* ids, const u64* ltimes, u32 n, const u64* left, u32 n_left, u64 event_ltime, u64 query_ltime) {
   ((RefNode*)p)->merge_remote_state(pp_ltime, ids, ltimes, n, left, n_left, event_ltime, query_ltime);
+}
+ORC u32 ref_local_state(void* p, u64* pp_ltime, u64* ids, u64* ltimes, u32 cap, u64* left, u32 cap_left, u32* n_left, u64* event_ltime, u64* query_ltime) {
+  return ((RefNode*)p)->local_state(pp_ltime, ids, ltimes, cap, left, cap_left, n_left, event_ltime, query_ltime);
 }
 ORC void ref_api_join(void* p) { ((RefNode*)p)->api_join(); }
 ORC int ref_api_leave(void* p) { return ((RefNode*)p)->api_leave(); }

@@ -162,6 +162,27 @@ def test_delegate_merge_remote_state():
     assert n.clock(2) == 100, "bad query clock"
 
 
+# ---- serf/base/tests/serf/delegate.rs:40-114  delegate_local_state (membership part) ------------
+def test_delegate_local_state_round_trip():
+    """local_state carries clock.time(), every member's status_time and the ids of the left list; feeding it to another
+    node's merge_remote_state reproduces the intents the reference KAT above pins (Left member → Leave at ltime + 1)."""
+    a = RefNode(1)
+    a.node_join(2); a.node_join(3)
+    assert a.join_intent(7, 2)                                   # member 2 joined at ltime 7
+    assert a.leave_intent(9, 3); a.node_leave(3, 0)             # member 3 left gracefully: Leaving → Left, on the left list
+    cap = 8
+    ids = (C.c_uint64 * cap)(); lts = (C.c_uint64 * cap)(); left = (C.c_uint64 * cap)()
+    ppl, evl, ql, nleft = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint32()
+    n = a.L.ref_local_state(a.p, C.byref(ppl), ids, lts, cap, left, cap, C.byref(nleft), C.byref(evl), C.byref(ql))
+    assert ppl.value == a.clock() == 10 and evl.value == a.clock(1) and ql.value == a.clock(2)
+    assert n == 3 and dict(zip(list(ids)[:n], list(lts)[:n])) == {1: 0, 2: 7, 3: 9}
+    assert nleft.value == 1 and left[0] == 3
+    b = RefNode(50)
+    b.L.ref_merge_remote_state(b.p, ppl.value, ids, lts, n, left, nleft.value, evl.value, ql.value)
+    assert b.clock() == 11                                       # witness(10-1) → 10, then the leave intent 9+1 = 10 → 11
+    assert b.recent_intent(2, JOIN) == 7 and b.recent_intent(3, LEAVE) == 10 and b.recent_intent(1, JOIN) == 0
+
+
 # ---- serf/base/tests/serf.rs:772-788  serf_stats (fresh node) -----------------------------
 def test_serf_stats_fresh_node():
     n = RefNode()
