@@ -1045,6 +1045,117 @@ ORC int oracle_sim_stats(void* p, serfsim_stats_t* o) {
   }
   return 0;
 }
+
+// =====================================================================================
+// Part C — FaithfulSim: N literal serf nodes (Part A), each with its own full member table and a
+// multi-entry TransmitLimitedQueue, driven tick by tick with the SAME peer selection as Part B.
+// Used only by tests to check that the packed-record tick model (two queue entries per view, inbox
+// reduction semantics) agrees with a literal multi-node execution on serf-only scenarios (join /
+// force-leave operations; the memberlist layer is not part of this model).
+// =====================================================================================
+struct FaithfulSim {
+  u32 N, fanout, retransmit_mult; u64 seed; u32 tick = 0;
+  std::vector<RefNode> nodes;
+  std::vector<u64> row_ptr; std::vector<u32> col;
+  struct Op { u32 tick, op, node; u64 subject; };
+  std::vector<Op> ops;
+  struct M { u32 dst, src; u8 ty; u64 ltime, id; };
+  std::vector<M> inflight;
+  std::vector<u64> subjects;      // processing order of subjects at a receiver (slot order of Part B)
+
+  FaithfulSim(u32 n, u32 f, u32 rm, u64 sd, u64 init_st, u64 init_clock) : N(n), fanout(f), retransmit_mult(rm), seed(sd) {
+    nodes.reserve(n);
+    for (u32 v = 0; v < n; ++v) {
+      nodes.emplace_back((u64)v);
+      RefNode& nd = nodes.back();
+      nd.retransmit_mult = rm;
+      nd.clock.v = init_clock;
+      for (u32 w = 0; w < n; ++w) nd.states[w] = MemberStateA{ST_ALIVE, init_st, false, 0};
+    }
+  }
+  u32 targets(u32 v, u32 t, u32* out) const {      // identical to TickSim::gossip_targets
+    u64 r0 = row_ptr[v]; u32 deg = (u32)(row_ptr[v + 1] - r0), nt = 0;
+    const u32 m = std::min(fanout, deg);
+    if (!m) return 0;
+    u32 w[4];
+    philox4x32_10(t, v, 0, DOMAIN_GOSSIP, (u32)seed, (u32)(seed >> 32), w);
+    u32 chosen[8], nc = 0;
+    for (u32 k = 0; k < m; ++k) {
+      const u32 x = w[(k >> 1) & 3];
+      u32 j = (((k & 1) ? (x >> 16) : (x & 0xffffu)) * (deg - k)) >> 16;
+      for (u32 i = 0; i < nc; ++i) if (j >= chosen[i]) ++j;
+      u32 pos = nc;
+      while (pos > 0 && chosen[pos - 1] > j) { chosen[pos] = chosen[pos - 1]; --pos; }
+      chosen[pos] = j; ++nc;
+      const u32 c = col[r0 + j];
+      if (c != v) out[nt++] = c;
+    }
+    return nt;
+  }
+  int order_of(u64 id) const { for (size_t i = 0; i < subjects.size(); ++i) if (subjects[i] == id) return (int)i; return (int)subjects.size(); }
+  void step_one() {
+    const u32 t = tick;
+    // Phase R: canonical order per receiver: subjects in slot order, leaves ascending, then joins ascending
+    std::stable_sort(inflight.begin(), inflight.end(), [&](const M& a, const M& b) {
+      if (a.dst != b.dst) return a.dst < b.dst;
+      const int oa = order_of(a.id), ob = order_of(b.id);
+      if (oa != ob) return oa < ob;
+      if (a.ty != b.ty) return a.ty < b.ty;            // TY_LEAVE (1) before TY_JOIN (2)
+      if (a.ltime != b.ltime) return a.ltime < b.ltime;
+      return a.src < b.src;
+    });
+    // Per node, per subject in slot order: Phase R (that subject's messages, leaves then joins), the refutation task,
+    // then Phase E (a host operation of this tick that concerns that subject) — the interleaving Part B uses.
+    size_t i = 0;
+    for (u32 d = 0; d < N; ++d) {
+      RefNode& nd = nodes[d];
+      const Op* op = nullptr;
+      for (auto& o : ops) if (o.tick == t && o.node == d) { op = &o; break; }
+      const size_t end0 = i;
+      size_t end = end0;
+      while (end < inflight.size() && inflight[end].dst == d) ++end;
+      if (end == end0 && !op) continue;
+      for (size_t sl = 0; sl <= subjects.size(); ++sl) {           // the last round takes untracked subjects (none in the tests)
+        while (i < end && order_of(inflight[i].id) == (int)sl) {
+          const M& m = inflight[i++];
+          const bool rb = (m.ty == TY_JOIN) ? nd.handle_node_join_intent(m.ltime, m.id) : nd.handle_node_leave_intent(m.ltime, m.id, false);
+          if (rb) nd.queue(m.ty, m.ltime, m.id, false, false);           // serf/delegate.rs:294-300
+        }
+        nd.run_detached();                                               // the refutation task of this subject, if any
+        if (op && sl < subjects.size()) {
+          if (op->op == SERFSIM_OP_JOIN && subjects[sl] == d) nd.api_join();
+          else if (op->op == SERFSIM_OP_FORCE_LEAVE && subjects[sl] == op->subject) { nd.api_force_leave(op->subject, false); nd.run_detached(); }
+        }
+      }
+      i = end;
+    }
+    inflight.clear();
+    // Phase S: every node with queued broadcasts sends one packet (all entries that fit) to each gossip peer
+    for (u32 v = 0; v < N; ++v) {
+      RefNode& nd = nodes[v];
+      if (nd.broadcasts.empty()) continue;
+      u32 tg[8]; const u32 nt = targets(v, t, tg);
+      for (u32 k = 0; k < nt && !nd.broadcasts.empty(); ++k) {
+        u8 ty[64]; u64 lt[64], id[64];
+        const u32 n = nd.get_broadcasts(1u << 20, 2, ty, lt, id, 64);
+        for (u32 q = 0; q < n && q < 64; ++q) inflight.push_back(M{tg[k], v, ty[q], lt[q], id[q]});
+      }
+    }
+    ++tick;
+  }
+};
+
+ORC void* faithful_new(u32 n, u32 fanout, u32 retransmit_mult, u64 seed, u64 init_st, u64 init_clock) { return new FaithfulSim(n, fanout, retransmit_mult, seed, init_st, init_clock); }
+ORC void faithful_free(void* p) { delete (FaithfulSim*)p; }
+ORC void faithful_set_topology(void* p, const u64* row_ptr, const u32* col) { auto* s = (FaithfulSim*)p; s->row_ptr.assign(row_ptr, row_ptr + s->N + 1); s->col.assign(col, col + row_ptr[s->N]); }
+ORC void faithful_set_subjects(void* p, const u64* subj, u32 n) { ((FaithfulSim*)p)->subjects.assign(subj, subj + n); }
+ORC void faithful_inject(void* p, u32 tick, u32 op, u32 node, u64 subject) { ((FaithfulSim*)p)->ops.push_back(FaithfulSim::Op{tick, op, node, subject}); }
+ORC void faithful_step(void* p, u32 n) { for (u32 i = 0; i < n; ++i) ((FaithfulSim*)p)->step_one(); }
+ORC int faithful_view(void* p, u32 node, u64 subject, u8* status, u64* st) { auto& nd = ((FaithfulSim*)p)->nodes[node]; auto it = nd.states.find(subject); if (it == nd.states.end()) return 0; *status = it->second.status; *st = it->second.status_time; return 1; }
+ORC u64 faithful_clock(void* p, u32 node) { return ((FaithfulSim*)p)->nodes[node].clock.time(); }
+ORC u32 faithful_queue_len(void* p, u32 node) { return (u32)((FaithfulSim*)p)->nodes[node].broadcasts.size(); }
+ORC u32 faithful_inflight(void* p) { return (u32)((FaithfulSim*)p)->inflight.size(); }
+
 // Number of host threads the tick loop uses (results are independent of it).  Takes effect at the next reset.
 ORC int oracle_sim_set_threads(void* p, int n) {
   auto* s = (TickSim*)p;
