@@ -565,6 +565,8 @@ struct TickSim {
   std::vector<u16> watch;       // per node: bit s set iff subject s is in the node's neighbour list (only those nodes can probe it)
   std::vector<std::vector<Msg>> mail;   // messages sent in the previous tick: [producer range][consumer range]
   std::vector<std::vector<Msg>> mail_next;                       // the boxes being filled this tick (capacity is reused)
+  u32 own_first = 0, own_count = 0;                              // id range this instance owns (sharded runs; default: everything)
+  std::vector<std::vector<Msg>> exported;                        // per thread: messages of the last tick for nodes owned elsewhere
   struct Scratch { std::vector<u32> head, pos; std::vector<Msg> byd; };
   std::vector<Scratch> scratch;                                  // per-thread buffers, reused across ticks
   u32 chunk = 1;
@@ -584,6 +586,7 @@ struct TickSim {
   void reset(u64 seed) {
     cfg.seed = seed; tick = 0; events.clear(); event_keys.clear(); ev_by_tick.clear(); any_event = false; max_event_tick = 0; mail_next.clear(); trace.clear(); mail.clear(); tot_events = 0;
     chunk = (N + threads - 1) / threads;
+    if (own_count == 0) { own_first = 0; own_count = N; }
     rec.assign((size_t)R * N, View{});
     node.assign(N, NodeB{cfg.init_clock, 1, SS_ALIVE});
     for (u32 s = 0; s < R; ++s)
@@ -646,6 +649,8 @@ struct TickSim {
     if (mail_next.size() != (size_t)T * T) { mail_next.assign((size_t)T * T, {}); }
     for (auto& b : mail_next) b.clear();
     if (scratch.size() != T) scratch.assign(T, Scratch{});
+    if (exported.size() != T) exported.assign(T, {});
+    for (auto& e : exported) e.clear();
     std::vector<std::vector<Msg>>& next = mail_next;
     // events of this tick
     std::vector<EventB> evs;
@@ -674,8 +679,11 @@ struct TickSim {
     std::vector<Msg>& byd = sx.byd;
     byd.resize(total);
     { std::vector<u32>& pos = sx.pos; pos.assign(head.begin(), head.end() - 1); for (u32 p = 0; p < T; ++p) for (auto& m : mail[(size_t)p * T + c]) byd[pos[m.dst - v0]++] = m; }
-    auto post = [&](const Msg& m) { next[(size_t)c * T + owner_of(m.dst)].push_back(m); };
-    for (u32 v = v0; v < v1; ++v) {
+    auto post = [&](const Msg& m) {
+      if (m.dst - own_first < own_count) next[(size_t)c * T + owner_of(m.dst)].push_back(m);
+      else exported[c].push_back(m);                      // destination lives in another shard
+    };
+    for (u32 v = std::max(v0, own_first); v < std::min<u64>(v1, (u64)own_first + own_count); ++v) {
       NodeB& nd = node[v];
       const bool up_r = nd.up;
       const EventB* ev = nullptr;
@@ -818,7 +826,7 @@ struct TickSim {
     // then serf's view: a Left member → leave intent at status_ltime + 1, any other known member → join intent
     // at status_ltime — results discarded, i.e. nothing is re-queued (delegate.rs:495-523).
     const u32 pp = (u32)std::max(0, cfg.push_pull_interval_ticks);
-    if (pp && (t + 1) % pp == 0) {
+    if (pp && (t + 1) % pp == 0 && own_count == N) {
       const std::vector<View> srec = rec;
       const std::vector<NodeB> snode = node;
       auto ppwork = [&](u32 c) {
@@ -873,15 +881,16 @@ struct TickSim {
     ++tick;
   }
 
-  u64 state_hash() const {
+  u64 state_hash() const {                    // additive over nodes: shard hashes sum to the global hash
     u64 h = 0;
+    const u32 a = own_first, b = own_first + own_count;
     for (u32 s = 0; s < R; ++s)
-      for (u32 v = 0; v < N; ++v) {
+      for (u32 v = a; v < b; ++v) {
         u64 w[4]; memcpy(w, &rec[(size_t)s * N + v], 32);
         u64 idx = (u64)s * N + v;
         h += mix64(w[0] ^ mix64(w[1] ^ mix64(w[2] ^ mix64(w[3] ^ mix64(idx + 0x9e3779b97f4a7c15ULL)))));
       }
-    for (u32 v = 0; v < N; ++v) {
+    for (u32 v = a; v < b; ++v) {
       u64 w = (u64)node[v].clock | ((u64)node[v].up << 32) | ((u64)node[v].sstate << 40);
       h += mix64(w ^ mix64((u64)R * N + v + 0x9e3779b97f4a7c15ULL));
     }
@@ -1155,6 +1164,30 @@ ORC int faithful_view(void* p, u32 node, u64 subject, u8* status, u64* st) { aut
 ORC u64 faithful_clock(void* p, u32 node) { return ((FaithfulSim*)p)->nodes[node].clock.time(); }
 ORC u32 faithful_queue_len(void* p, u32 node) { return (u32)((FaithfulSim*)p)->nodes[node].broadcasts.size(); }
 ORC u32 faithful_inflight(void* p) { return (u32)((FaithfulSim*)p)->inflight.size(); }
+
+// Sharded runs of the tick oracle (tests of the N > 1 host logic): an instance owns a contiguous id range, processes only
+// those nodes, and hands the messages for foreign nodes to the caller, who delivers them to the owning instance.
+ORC int oracle_sim_set_ownership(void* p, u32 first, u32 count) {
+  auto* s = (TickSim*)p;
+  if (s->tick != 0 || (u64)first + count > s->N || count == 0) return SERFSIM_E_INVAL;
+  s->own_first = first; s->own_count = count; return 0;
+}
+ORC u32 oracle_sim_export(void* p, void* out, u32 cap) {          // 16-byte entries {dst, src, val, slot u8, kind u8, pad}
+  auto* s = (TickSim*)p; u32 n = 0;
+  for (auto& e : s->exported) for (auto& m : e) { if (n < cap) memcpy((char*)out + (size_t)n * sizeof(Msg), &m, sizeof(Msg)); ++n; }
+  return n;
+}
+ORC int oracle_sim_import(void* p, const void* in, u32 n) {
+  auto* s = (TickSim*)p; const u32 T = (u32)s->threads;
+  if (s->mail.size() != (size_t)T * T) s->mail.assign((size_t)T * T, {});
+  for (u32 i = 0; i < n; ++i) {
+    Msg m; memcpy(&m, (const char*)in + (size_t)i * sizeof(Msg), sizeof(Msg));
+    if (m.dst - s->own_first >= s->own_count) return SERFSIM_E_INVAL;
+    s->mail[(size_t)0 * T + s->owner_of(m.dst)].push_back(m);
+  }
+  return 0;
+}
+ORC u32 oracle_msg_size(void) { return (u32)sizeof(Msg); }
 
 // Number of host threads the tick loop uses (results are independent of it).  Takes effect at the next reset.
 ORC int oracle_sim_set_threads(void* p, int n) {
