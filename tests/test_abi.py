@@ -52,3 +52,18 @@ def test_create_fails_loudly_without_gpu():
     with pytest.raises(sim.SerfsimError) as e:
         sim.GossipSim(100, 1)
     assert e.value.code == -2 and "no CPU" in str(e.value)
+
+
+def test_cpp_host_layer_compiles_links_and_fails_loudly_without_gpu(tmp_path):
+    """include/serfsim.hpp (the C++ host layer with the reference's names) builds against libserfsim.so; without a GPU
+    creating a cluster throws SERFSIM_E_NO_DEVICE (exit code 10 of the check program), with one it runs configs[0]."""
+    so = sb.build()
+    exe = str(tmp_path / "host_layer_check")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "host_layer_check.cpp"),
+                           "-o", exe, so, "-Wl,-rpath," + os.path.dirname(so)])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    import torch
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout + r.stderr
+    else:
+        assert r.returncode == 10 and "no CPU execution path" in r.stdout, r.stdout + r.stderr
