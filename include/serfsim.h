@@ -201,8 +201,11 @@ int serfsim_tick_times(serfsim_t* h, uint32_t first_tick, uint32_t n, float* ms_
 size_t serfsim_comm_blob_size(void);
 int    serfsim_comm_export (serfsim_t* h, void* blob);
 int    serfsim_comm_connect(serfsim_t* h, const void* blobs /*[world_size][blob_size]*/);
-/* Collective hooks the host must provide when world_size > 1 (a barrier and a u64 sum
- * all-reduce across ranks, e.g. torch.distributed / NCCL); called between ticks. */
+/* Collective hooks the host must provide when world_size > 1 (a barrier and a u64 sum all-reduce across ranks,
+ * e.g. torch.distributed / NCCL).  They are NOT on the per-tick data path (that is device-side: peer-window stores,
+ * release/acquire flags): the barrier runs once in serfsim_comm_connect, the all-reduce whenever the host looks at
+ * trace rows or the state hash (once per convergence-check chunk).  Every rank must make the same sequence of calls.
+ * In sharded runs serfsim_stats reports member_time / intent_queue / disagree_slots for the local shard only. */
 typedef void (*serfsim_barrier_fn)(void* user);
 typedef void (*serfsim_allreduce_u64_fn)(void* user, uint64_t* buf, uint32_t n);
 int    serfsim_comm_set_hooks(serfsim_t* h, serfsim_barrier_fn barrier, serfsim_allreduce_u64_fn allreduce, void* user);
