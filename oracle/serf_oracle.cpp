@@ -945,6 +945,7 @@ ORC int ref_queue_get(void* p, u32 i, u8* ty, u64* ltime, u64* id, u32* transmit
   auto& q = n->broadcasts[i]; *ty = q.ty; *ltime = q.ltime; *id = q.id; *transmits = q.transmits; return 1;
 }
 ORC u32 ref_get_broadcasts(void* p, u32 byte_limit, u32 overhead, u8* ty, u64* lt, u64* id, u32 cap) { return ((RefNode*)p)->get_broadcasts(byte_limit, overhead, ty, lt, id, cap); }
+ORC void ref_remove_old_member(void* p, int failed_list, u64 id) { auto* n = (RefNode*)p; RefNode::remove_old_member(failed_list ? n->failed_members : n->left_members, id); }
 ORC u32 ref_left_count(void* p) { return (u32)((RefNode*)p)->left_members.size(); }
 ORC u32 ref_failed_count(void* p) { return (u32)((RefNode*)p)->failed_members.size(); }
 ORC void ref_push_left(void* p, u64 id, int status, u64 status_time, int64_t leave_time_ms) { ((RefNode*)p)->left_members.push_back({id, MemberStateA{(u8)status, status_time, true, leave_time_ms}}); }

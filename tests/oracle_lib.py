@@ -46,6 +46,7 @@ def lib():
         "ref_api_join": (None, [vp]), "ref_api_leave": (i32, [vp]), "ref_api_force_leave": (None, [vp, u64, i32]),
         "ref_queue_len": (u32, [vp]), "ref_queue_get": (i32, [vp, u32, u8p, u64p, u64p, u32p]),
         "ref_get_broadcasts": (u32, [vp, u32, u32, u8p, u64p, u64p, u32]),
+        "ref_remove_old_member": (None, [vp, i32, u64]),
         "ref_left_count": (u32, [vp]), "ref_failed_count": (u32, [vp]),
         "ref_push_left": (None, [vp, u64, i32, u64, i64]), "ref_push_failed": (None, [vp, u64, i32, u64, i64]),
         "ref_reap": (None, [vp, i64, i64, i64, i64]),

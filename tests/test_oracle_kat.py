@@ -219,6 +219,17 @@ def test_reap_handler():
     assert n.recent_intent("doug", LEAVE) is None
 
 
+# ---- serf/base/tests/serf/remove.rs:187-222  test_remove_old_member ----------------------------
+def test_remove_old_member():
+    n = RefNode()
+    now = 1_000_000
+    n.L.ref_push_left(n.p, n.id("foo"), NONE, 0, now)
+    n.L.ref_push_left(n.p, n.id("bar"), NONE, 0, now - 5000)
+    n.L.ref_push_left(n.p, n.id("baz"), NONE, 0, now - 5000)
+    n.L.ref_remove_old_member(n.p, 0, n.id("bar"))
+    assert n.L.ref_left_count(n.p) == 2
+
+
 # ---- handle_node_leave transitions (base.rs:1375-1440) + event order scenarios
 #      serf/base/tests/serf/event.rs:88-232, 405-467; reconnect.rs:10-72 ---------------------
 def test_event_order_join_failed_leave_forced():
