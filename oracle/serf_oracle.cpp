@@ -153,6 +153,11 @@ struct RefNode {
   u64 seq = 0;
   u32 refutes = 0;          // number of spawned broadcast_join refutations (base.rs:1470-1480)
   std::vector<std::pair<u32, u64>> events;   // (MemberEventType, id) in emission order
+  // user-event ring ("next" row 3; restated for the KATs only): buffer[ltime % len] = {ltime, [(name, payload)…]}
+  struct UserEvents { u64 ltime; std::vector<std::pair<std::string, std::string>> events; };
+  std::vector<std::pair<bool, UserEvents>> event_buffer = std::vector<std::pair<bool, UserEvents>>(512);   // options.rs:517 event_buffer_size
+  u64 event_min_time = 0;
+  std::vector<std::pair<std::string, std::string>> user_events_out;          // delivered to the application, in order
 
   explicit RefNode(u64 id) : self_id(id) {
     // base.rs:198-200: all three clocks are incremented once at construction.
@@ -324,6 +329,25 @@ struct RefNode {
       if (is_left) continue;
       handle_node_join_intent(ltimes[i], ids[i]);
     }
+  }
+
+  // base.rs:750-837 handle_user_event → rebroadcast?  (quirk kept: an occupied ring slot is reused without checking
+  // or refreshing its ltime, base.rs:801-813)
+  bool handle_user_event(u64 ltime, const std::string& name, const std::string& payload) {
+    event_clock.witness(ltime);                                       // :763
+    if (ltime < event_min_time) return false;                         // :768-770
+    const u64 bltime = event_buffer.size();
+    const u64 cur = event_clock.time();
+    if (cur > bltime && ltime < cur - bltime) return false;           // :773-783 too old
+    auto& slot = event_buffer[(size_t)(ltime % bltime)];
+    if (slot.first) {
+      for (auto& prev : slot.second.events) if (prev.first == name && prev.second == payload) return false;   // :803-808 already seen
+      slot.second.events.push_back({name, payload});
+    } else {
+      slot.first = true; slot.second.ltime = ltime; slot.second.events = {{name, payload}};
+    }
+    user_events_out.push_back({name, payload});
+    return true;
   }
 
   // serf/delegate.rs:386-425 local_state: {ltime: clock.time(), status_ltimes: every member's status_time, left_members: ids of
@@ -936,6 +960,11 @@ ORC void ref_merge_remote_state(void* p, u64 pp_ltime, const u64* ids, const u64
 ORC u32 ref_local_state(void* p, u64* pp_ltime, u64* ids, u64* ltimes, u32 cap, u64* left, u32 cap_left, u32* n_left, u64* event_ltime, u64* query_ltime) {
   return ((RefNode*)p)->local_state(pp_ltime, ids, ltimes, cap, left, cap_left, n_left, event_ltime, query_ltime);
 }
+ORC int ref_handle_user_event(void* p, u64 ltime, const char* name, const char* payload) { return ((RefNode*)p)->handle_user_event(ltime, name, payload); }
+ORC void ref_event_clock_witness(void* p, u64 t) { ((RefNode*)p)->event_clock.witness(t); }
+ORC u32 ref_user_event_count(void* p) { return (u32)((RefNode*)p)->user_events_out.size(); }
+ORC const char* ref_user_event_get(void* p, u32 i, int payload) { auto& e = ((RefNode*)p)->user_events_out[i]; return payload ? e.second.c_str() : e.first.c_str(); }
+ORC int ref_event_buffer_has(void* p, u64 ltime) { auto* n = (RefNode*)p; auto& sl = n->event_buffer[(size_t)(ltime % n->event_buffer.size())]; return sl.first && sl.second.ltime == ltime; }
 ORC void ref_api_join(void* p) { ((RefNode*)p)->api_join(); }
 ORC int ref_api_leave(void* p) { return ((RefNode*)p)->api_leave(); }
 ORC void ref_api_force_leave(void* p, u64 id, int prune) { ((RefNode*)p)->api_force_leave(id, prune != 0); }

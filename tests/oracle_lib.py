@@ -43,6 +43,8 @@ def lib():
         "ref_reap_intents": (None, [vp, i64, i64]),
         "ref_merge_remote_state": (None, [vp, u64, u64p, u64p, u32, u64p, u32, u64, u64]),
         "ref_local_state": (u32, [vp, u64p, u64p, u64p, u32, u64p, u32, u32p, u64p, u64p]),
+        "ref_handle_user_event": (i32, [vp, u64, C.c_char_p, C.c_char_p]), "ref_event_clock_witness": (None, [vp, u64]),
+        "ref_user_event_count": (u32, [vp]), "ref_user_event_get": (C.c_char_p, [vp, u32, i32]), "ref_event_buffer_has": (i32, [vp, u64]),
         "ref_api_join": (None, [vp]), "ref_api_leave": (i32, [vp]), "ref_api_force_leave": (None, [vp, u64, i32]),
         "ref_queue_len": (u32, [vp]), "ref_queue_get": (i32, [vp, u32, u8p, u64p, u64p, u32p]),
         "ref_get_broadcasts": (u32, [vp, u32, u32, u8p, u64p, u64p, u32]),

@@ -319,6 +319,24 @@ def test_force_leave():                                         # base.rs:454-48
     assert n.queue() == [(LEAVE, 1, 3, 0)]
 
 
+# ---- adjacent row (user events): serf/base/tests/serf/event.rs:8-85 ---------------------------
+def test_user_event_old_message():           # event.rs:8-33
+    n = RefNode()
+    n.L.ref_event_clock_witness(n.p, 512 + 1000)                # event_buffer_size + 1000
+    assert not n.L.ref_handle_user_event(n.p, 1, b"old", b""), "should not rebroadcast"
+
+
+def test_user_event_same_clock():            # event.rs:36-85
+    n = RefNode()
+    assert n.L.ref_handle_user_event(n.p, 1, b"first", b"test"), "should rebroadcast"
+    assert n.L.ref_handle_user_event(n.p, 1, b"first", b"newpayload"), "should rebroadcast"
+    assert n.L.ref_handle_user_event(n.p, 1, b"second", b"other"), "should rebroadcast"
+    got = [(n.L.ref_user_event_get(n.p, i, 0), n.L.ref_user_event_get(n.p, i, 1)) for i in range(n.L.ref_user_event_count(n.p))]
+    assert got == [(b"first", b"test"), (b"first", b"newpayload"), (b"second", b"other")]
+    assert not n.L.ref_handle_user_event(n.p, 1, b"first", b"test")        # exact duplicate: already seen (base.rs:803-808)
+    assert n.L.ref_event_buffer_has(n.p, 1) and n.clock(1) == 2
+
+
 # ---- external TransmitLimitedQueue restated (parity unpinned; documents the restatement) ---
 def test_transmit_limited_queue_restated():
     L = lib()
