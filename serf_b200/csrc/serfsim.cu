@@ -100,6 +100,13 @@ struct serfsim {
   u32* d_subj = nullptr;
   u64* d_scratch = nullptr;        // summary / hash output
   void* d_stage = nullptr;         // getter staging, count × 8 B
+  // user events: allocated by serfsim_set_user_events
+  UeTable ue_table{};              // n = 0: user events off
+  uint4* d_ue_state = nullptr;     // [stride] 16-byte event records
+  u32* d_ue_inbox[2] = {nullptr, nullptr};   // [stride] arrived-event masks per tick parity
+  u32* d_ue_ltime = nullptr;       // [MAX_UEVENTS]
+  u64* d_ue_totals = nullptr;      // [8]
+  u32 ue_injected = 0;             // tracked events already scheduled (each may be injected once)
   // host state
   std::vector<HostOp> ops;         // sorted by (tick, seq)
   std::unordered_set<u64> op_keys; // (tick << 32 | node): at most one operation per node per tick
@@ -252,6 +259,17 @@ int launch_ticks(serfsim* h, u32 n) {
       av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
       CU(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av));
     }
+    if (h->ue_table.n) {                       // user-event tick: needs the pre-operation up flags and op bits, so it runs first
+      UeParams u{};
+      u.n_local = h->count; u.first = h->first; u.n_global = h->N; u.R = h->R; u.fanout = h->cfg.fanout; u.tick = t;
+      u.seed_lo = p.seed_lo; u.seed_hi = p.seed_hi; u.limit = h->rules.limit; u.ev_begin = eb; u.ev_end = ee;
+      u.table = h->ue_table; u.state = h->d_ue_state; u.inbox_rd = h->d_ue_inbox[(t & 1) ^ 1]; u.inbox_wr = h->d_ue_inbox[t & 1];
+      u.ltime = h->d_ue_ltime; u.node_state = h->d_node; u.busy = h->d_busy; u.row_ptr = h->d_rowptr; u.col = h->d_col;
+      u.ev_node = h->d_ev_node; u.ev_op = h->d_ev_op; u.ev_slot = h->d_ev_slot;
+      u.row = p.row; u.totals = h->d_ue_totals; u.overflow = h->d_overflow;
+      launch_uevent(u, h->cfg.trace != 0, h->stream);
+      h->last_launches++;
+    }
     launch_tick(p, h->cfg.trace != 0, h->grid, h->stream);
     h->last_launches++;
     if (h->tick_timing && h->cfg.world_size > 1) {
@@ -356,6 +374,18 @@ int refresh_watchers(serfsim* h) {
   return 0;
 }
 
+int ue_reset(serfsim* h) {                      // bootstrap event state: clock 1, nothing seen, nothing queued
+  h->ue_injected = 0;
+  if (!h->ue_table.n) return 0;
+  launch_ue_init(h->d_ue_state, h->count, h->stream);
+  CU(cudaMemsetAsync(h->d_ue_inbox[0], 0, (size_t)h->stride * 4, h->stream));
+  CU(cudaMemsetAsync(h->d_ue_inbox[1], 0, (size_t)h->stride * 4, h->stream));
+  CU(cudaMemsetAsync(h->d_ue_ltime, 0, MAX_UEVENTS * 4, h->stream));
+  CU(cudaMemsetAsync(h->d_ue_totals, 0, 8 * 8, h->stream));
+  CU(cudaGetLastError());
+  return 0;
+}
+
 int do_reset(serfsim* h, u64 seed) {
   h->cfg.seed = seed; h->tick = 0; h->ops.clear(); h->op_keys.clear(); h->ops_dirty = false; h->rows.clear();
   h->up_mask = (h->R >= 32) ? 0xffffffffu : ((1u << h->R) - 1);
@@ -373,6 +403,7 @@ int do_reset(serfsim* h, u64 seed) {
     CU(cudaMemsetAsync(h->d_kinds, 0, ((size_t)h->trace_cap + 1) * 4 * sizeof(u32), h->stream));
   }
   if (h->d_send_count) CU(cudaMemsetAsync(h->d_send_count, 0, sizeof(u32) * 8, h->stream));
+  { int rc = ue_reset(h); if (rc) return rc; }
   { int rc = refresh_watchers(h); if (rc) return rc; }
   CU(cudaStreamSynchronize(h->stream));
   return 0;
@@ -385,6 +416,7 @@ void free_all(serfsim* h) {
   cudaFree(h->d_rec); cudaFree(h->d_inbox[0]); cudaFree(h->d_inbox[1]); cudaFree(h->d_node); cudaFree(h->d_rowptr); cudaFree(h->d_col);
   cudaFree(h->d_ev_node); cudaFree(h->d_ev_op); cudaFree(h->d_ev_slot); cudaFree(h->d_trace); cudaFree(h->d_kinds); cudaFree(h->d_ones);
   cudaFree(h->d_overflow); cudaFree(h->d_subj); cudaFree(h->d_scratch); cudaFree(h->d_stage);
+  cudaFree(h->d_ue_state); cudaFree(h->d_ue_inbox[0]); cudaFree(h->d_ue_inbox[1]); cudaFree(h->d_ue_ltime); cudaFree(h->d_ue_totals);
   for (int par = 0; par < 2; ++par) { cudaFree(h->d_win_data[par]); cudaFree(h->d_peer_data[par]); }
   cudaFree(h->d_ctrl); cudaFree(h->d_send_count); cudaFree(h->d_peer_ctrl);
   if (h->pin_rows) cudaFreeHost(h->pin_rows);
@@ -617,11 +649,16 @@ int serfsim_reset(serfsim_t* h, uint64_t seed) {
 int serfsim_inject(serfsim_t* h, uint32_t tick, uint32_t op, uint32_t node, uint32_t slot) {
   if (!h) return fail(SERFSIM_E_INVAL, "null handle");
   if (tick < h->tick) return fail(SERFSIM_E_INVAL, "cannot schedule an operation in the past");
-  if (node >= h->N || op < SERFSIM_OP_JOIN || op > SERFSIM_OP_REJOIN) return fail(SERFSIM_E_INVAL, "bad node / op");
+  if (node >= h->N || op < SERFSIM_OP_JOIN || op > SERFSIM_OP_USER_EVENT) return fail(SERFSIM_E_INVAL, "bad node / op");
+  if (op == SERFSIM_OP_USER_EVENT) {
+    if (slot >= h->ue_table.n) return fail(SERFSIM_E_INVAL, "user event index out of range (serfsim_set_user_events)");
+    if ((h->ue_injected >> slot) & 1u) return fail(SERFSIM_E_INVAL, "a tracked user event can be injected once");
+  }
   if (op == SERFSIM_OP_FORCE_LEAVE) { if (slot >= h->R) return fail(SERFSIM_E_INVAL, "slot out of range"); }
   else if ((op == SERFSIM_OP_JOIN || op == SERFSIM_OP_LEAVE) && slot_of(h, node) < 0)
     return fail(SERFSIM_E_INVAL, "join/leave origin must be a tracked subject");
   if (!h->op_keys.insert(((u64)tick << 32) | node).second) return fail(SERFSIM_E_INVAL, "one operation per node per tick");
+  if (op == SERFSIM_OP_USER_EVENT) h->ue_injected |= 1u << slot;
   h->ops.push_back(HostOp{tick, op, node, slot, h->op_seq++});
   h->ops_dirty = true;
   return 0;
@@ -761,10 +798,13 @@ int serfsim_tick_trace(serfsim_t* h, uint32_t first_tick, uint32_t n, serfsim_ti
 
 int serfsim_state_hash(serfsim_t* h, uint64_t* out) {
   if (!h || !out) return fail(SERFSIM_E_INVAL, "null argument");
-  CU(cudaMemsetAsync(h->d_scratch, 0, 8, h->stream));
+  CU(cudaMemsetAsync(h->d_scratch, 0, 4 * 8, h->stream));
   launch_state_hash(h->d_rec, h->d_node, h->count, h->stride, h->first, h->N, h->R, h->d_scratch, h->stream);
-  CU(cudaMemcpyAsync(out, h->d_scratch, 8, cudaMemcpyDeviceToHost, h->stream));
+  if (h->ue_table.n) launch_ue_summary(h->d_ue_state, h->count, h->first, h->N, h->R, h->ue_table.n, h->d_scratch + 1, h->stream);
+  u64 parts[4] = {0, 0, 0, 0};
+  CU(cudaMemcpyAsync(parts, h->d_scratch, 4 * 8, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  *out = parts[0] + parts[3];                    // records + node words, plus the event records when user events are on
   if (h->cfg.world_size > 1) {
     if (!h->allreduce) return fail(SERFSIM_E_COMM, "world_size > 1: serfsim_comm_set_hooks was not called");
     h->allreduce(h->comm_user, out, 1);
@@ -794,6 +834,81 @@ int serfsim_stats(serfsim_t* h, serfsim_stats_t* o) {
   CU(cudaStreamSynchronize(h->stream));
   o->member_time = out[0]; o->intent_queue = out[1];
   for (u32 s = 0; s < h->R; ++s) if (out[2 + 2 * s] != ~0ull && out[2 + 2 * s] != out[3 + 2 * s]) o->disagree_slots++;
+  return 0;
+}
+
+// ---- user events (rules in uevent.cuh) ----
+int serfsim_set_user_events(serfsim_t* h, uint32_t n_events, const uint32_t* content_ids) {
+  if (!h) return fail(SERFSIM_E_INVAL, "null handle");
+  if (n_events > MAX_UEVENTS) return fail(SERFSIM_E_INVAL, "at most SERFSIM_MAX_USER_EVENTS tracked user events");
+  if (n_events && !content_ids) return fail(SERFSIM_E_INVAL, "null content ids");
+  if (h->tick != 0 || !h->ops.empty()) return fail(SERFSIM_E_INVAL, "serfsim_set_user_events: call before any operation is scheduled (or after serfsim_reset)");
+  if (n_events && h->cfg.world_size > 1) return fail(SERFSIM_E_INVAL, "user events are single-GPU in this version");
+  if (n_events && h->cfg.push_pull_interval_ticks > 0) return fail(SERFSIM_E_INVAL, "user events cannot be combined with push-pull rounds in this version");
+  if (n_events && !h->d_ue_state) {
+    CU(cudaMalloc(&h->d_ue_state, (size_t)h->stride * 16));
+    CU(cudaMalloc(&h->d_ue_inbox[0], (size_t)h->stride * 4));
+    CU(cudaMalloc(&h->d_ue_inbox[1], (size_t)h->stride * 4));
+    CU(cudaMalloc(&h->d_ue_ltime, MAX_UEVENTS * 4));
+    CU(cudaMalloc(&h->d_ue_totals, 8 * 8));
+  }
+  h->ue_table = UeTable{};
+  h->ue_table.n = n_events;
+  for (u32 e = 0; e < n_events; ++e) h->ue_table.content[e] = content_ids[e];
+  int rc = ue_reset(h);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int serfsim_event_time(serfsim_t* h, uint64_t* out) {
+  if (!h || !out) return fail(SERFSIM_E_INVAL, "null argument");
+  if (!h->ue_table.n) return fail(SERFSIM_E_INVAL, "user events are off (serfsim_set_user_events)");
+  launch_ue_extract(h->d_ue_state, h->count, 0, 0, h->d_stage, h->stream);
+  CU(cudaMemcpyAsync(out, h->d_stage, (size_t)h->count * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int serfsim_user_event_seen(serfsim_t* h, uint32_t event, uint8_t* out) {
+  if (!h || !out) return fail(SERFSIM_E_INVAL, "null argument");
+  if (event >= h->ue_table.n) return fail(SERFSIM_E_INVAL, "user event index out of range");
+  launch_ue_extract(h->d_ue_state, h->count, 1, event, h->d_stage, h->stream);
+  CU(cudaMemcpyAsync(out, h->d_stage, (size_t)h->count, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int serfsim_user_event_ltime(serfsim_t* h, uint32_t event, uint64_t* ltime) {
+  if (!h || !ltime) return fail(SERFSIM_E_INVAL, "null argument");
+  if (event >= h->ue_table.n) return fail(SERFSIM_E_INVAL, "user event index out of range");
+  u32 v = 0;
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpy(&v, h->d_ue_ltime + event, 4, cudaMemcpyDeviceToHost));
+  *ltime = v;
+  return 0;
+}
+
+int serfsim_user_event_records(serfsim_t* h, void* out) {
+  if (!h || !out) return fail(SERFSIM_E_INVAL, "null argument");
+  if (!h->ue_table.n) return fail(SERFSIM_E_INVAL, "user events are off (serfsim_set_user_events)");
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpy(out, h->d_ue_state, (size_t)h->count * 16, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int serfsim_user_event_stats(serfsim_t* h, serfsim_uevent_stats_t* o) {
+  if (!h || !o) return fail(SERFSIM_E_INVAL, "null argument");
+  memset(o, 0, sizeof(*o));
+  if (!h->ue_table.n) return fail(SERFSIM_E_INVAL, "user events are off (serfsim_set_user_events)");
+  u64 tot[8] = {0}, sum[3] = {0, 0, 0};
+  CU(cudaMemsetAsync(h->d_scratch, 0, 3 * 8, h->stream));
+  launch_ue_summary(h->d_ue_state, h->count, h->first, h->N, h->R, h->ue_table.n, h->d_scratch, h->stream);
+  CU(cudaMemcpyAsync(sum, h->d_scratch, 3 * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(tot, h->d_ue_totals, 8 * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  o->messages = tot[0]; o->edge_updates = tot[1]; o->delivered = tot[2]; o->duplicates = tot[3]; o->too_old = tot[4];
+  o->event_queue = sum[0]; o->event_time = sum[1];
   return 0;
 }
 

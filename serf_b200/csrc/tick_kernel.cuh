@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "record.cuh"
+#include "uevent.cuh"
 
 namespace sfs {
 
@@ -71,6 +72,28 @@ void launch_summary(const uint4* rec, const u64* node_state, u32 n_local, u32 st
 int tick_grid_size(u32 n_local, int ctas_per_sm);
 void launch_compute_watch(const u32* row_ptr, const u32* col, const u32* subj_dev, u32 R, u32 first, u32 n_local, u16* watch, cudaStream_t st);
 void launch_apply_watch(const u16* watch, u32 n_local, u8* busy, u8* hot0, u8* hot1, cudaStream_t st);
+
+// User-event tick (uevent_kernel.cu; rules in uevent.cuh)
+struct UeParams {
+  u32 n_local, first, n_global, R, fanout, tick, seed_lo, seed_hi, limit;
+  u32 ev_begin, ev_end;
+  UeTable table;
+  uint4* state;               // [n_local] 16-byte event records
+  u32* inbox_rd;              // [n_local] arrived-event masks written during the previous tick (consumed and cleared)
+  u32* inbox_wr;              // [n_local] masks being filled by this tick's sends
+  u32* ltime;                 // [MAX_UEVENTS] Lamport time of each tracked event, stamped by its origin
+  const u64* node_state;      // membership node words (up flag), pre-operation
+  const u8* busy;             // bit 1: a host operation targets the node this tick
+  const u32* row_ptr; const u32* col;
+  const u32* ev_node; const u32* ev_op; const u32* ev_slot;
+  u64* row;                   // this tick's trace row (shared with the membership kernel)
+  u64* totals;                // run totals: 0 messages, 1 edges, 2 delivered, 3 duplicates, 4 too_old
+  u32* overflow;
+};
+void launch_uevent(const UeParams& p, bool trace, cudaStream_t st);
+void launch_ue_init(uint4* state, u32 n_local, cudaStream_t st);
+void launch_ue_extract(const uint4* state, u32 n_local, int what, u32 e, void* out, cudaStream_t st);
+void launch_ue_summary(const uint4* state, u32 n_local, u32 first, u32 n_global, u32 R, u32 n_events, u64* out, cudaStream_t st);
 
 enum { EXTRACT_STATUS = 0, EXTRACT_STATUS_LTIME = 1, EXTRACT_CLOCK = 2, EXTRACT_INC = 3, EXTRACT_ML = 4 };
 
