@@ -139,6 +139,14 @@ typedef struct serfsim_uevent_stats {
   uint64_t event_time;    /* Stats.event_time: max event LamportClock over nodes                               */
 } serfsim_uevent_stats_t;
 
+/* Byzantine stale-record injectors (BASELINE configs[4]).  No reference semantics exist: serf ignores stale intents
+ * silently (`serf/base.rs:1346-1348, 1464-1466`); the model is defined by this repository's oracle. */
+typedef struct serfsim_byz_stats {
+  uint64_t messages;      /* stale entries injected (one serf + one memberlist entry per peer and subject) */
+  uint64_t edge_updates;  /* injected (peer, subject) pairs — NOT part of the tick rows' edge_updates       */
+  uint64_t flagged;       /* injectors whose anomaly flag is set                                            */
+} serfsim_byz_stats_t;
+
 typedef struct serfsim serfsim_t;   /* opaque; owned by the caller; freed by serfsim_destroy */
 
 /* Batched EventDelegate (`serf/delegate.rs:557-582` notify_join/leave/update → MemberEvent
@@ -211,6 +219,16 @@ int serfsim_user_event_seen  (serfsim_t* h, uint32_t event, uint8_t* out /*[coun
 int serfsim_user_event_ltime (serfsim_t* h, uint32_t event, uint64_t* ltime);            /* UserEventMessage.ltime stamped by the origin (0: not fired yet) */
 int serfsim_user_event_records(serfsim_t* h, void* out /*[count][16]*/);                 /* raw 16-byte event records (layout: DESIGN.md)          */
 int serfsim_user_event_stats (serfsim_t* h, serfsim_uevent_stats_t* out);
+
+/* ---- byzantine stale-record injectors (BASELINE configs[4]) --------------------------------------------
+ * ids[] re-inject, every tick, a copy of their own view aged by `delta` (status_time − delta, incarnation − delta,
+ * saturating) to that tick's gossip peers.  anomaly[u] = 1 once a receiver that was up held a view newer than
+ * u's injected entry by ≥ delta.  Call before scheduling operations; n = 0 switches injectors off.  With
+ * injectors on, serfsim_run_until_converged stops at the first tick with no honest traffic, nothing pending
+ * and nothing merged.  Single-GPU, and not together with push-pull rounds, in this version. */
+int serfsim_set_byzantine  (serfsim_t* h, uint32_t n, const uint32_t* ids /*[n]*/, uint32_t delta);
+int serfsim_anomaly_flags  (serfsim_t* h, uint8_t* out /*[count]*/);
+int serfsim_byzantine_stats(serfsim_t* h, serfsim_byz_stats_t* out);
 
 /* ---- measurement hooks (bench.py): device time of the tick kernels inside the last
  *      serfsim_step / run_until_converged call, measured with CUDA events on the launch

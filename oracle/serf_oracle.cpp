@@ -570,7 +570,18 @@ static void v_ml_dead(View& r, u32 d, bool left, u32 tick, bool self, const Rule
 }
 static inline u32 ml_key(const View& r) { return (r.inc << 6) | ((u32)ml_state(r) << 4) | ((r.ml >> 2) & 15); }
 
-struct Msg { u32 dst, src, val; u8 slot, kind; };   // kind 0 leave, 1 join, 2 memberlist
+// byzantine injector rules (BASELINE configs[4]; defined here, there is no reference behaviour to follow)
+static void byz_stale(const View& r, u32 delta, u8* kind, u32* lt, u32* key) {        // the aged copy of a view an injector re-sends
+  *lt = r.st > delta ? r.st - delta : 0;
+  const u32 inc = r.inc > delta ? r.inc - delta : 0;
+  *kind = (r.status == ST_LEAVING || r.status == ST_LEFT) ? 0 : 1;
+  *key = (inc << 6) | ((u32)ml_state(r) << 4) | ((r.ml >> 2) & 15);
+}
+static bool byz_judge(const View& q, u8 kind, u32 val, u32 delta) {                    // receiver's verdict on ONE arriving stale entry
+  return (kind == 2) ? (q.inc >= (val >> 6) + delta) : (known(q) && q.st >= val + delta);
+}
+
+struct Msg { u32 dst, src, val; u8 slot, kind, byz = 0; };   // kind 0 leave, 1 join, 2 memberlist; byz: a stale entry injected by a byzantine node
 
 // ---- user events: literal per-node state ----
 // EventCore.buffer is `Vec<Option<UserEvents>>` of event_buffer_size = 512 entries (serf/base.rs:193, options.rs:516);
@@ -612,6 +623,11 @@ struct TickSim {
   std::vector<UeNodeB> uen;
   std::vector<std::vector<UeMsg>> ue_mail, ue_mail_next;       // [producer range][consumer range], like `mail`
   u64 ue_tot[5] = {0, 0, 0, 0, 0};                             // messages, edge_updates, delivered, duplicates, too_old
+  // byzantine stale-record injectors (BASELINE configs[4]; no reference semantics — this block IS the definition)
+  std::vector<u8> byz;                                         // per node: 1 = injector
+  u32 byz_n = 0, byz_delta = 2;
+  std::vector<u8> anomaly;                                     // per node: sender flag
+  u64 byz_tot[3] = {0, 0, 0};                                  // injected entries, injected (peer, subject) pairs, senders flagged
   int threads = 1;
   std::string err;
 
@@ -637,6 +653,7 @@ struct TickSim {
       }
     subj_up.assign(R, 1);
     ue_reset();
+    anomaly.assign(byz_n ? N : 0, 0); for (auto& x : byz_tot) x = 0;
   }
   void ue_reset() {
     uen.assign(ue_n ? N : 0, UeNodeB{}); ue_mail.clear(); ue_mail_next.clear(); ue_injected = 0;
@@ -729,6 +746,8 @@ struct TickSim {
       for (auto& b : ue_mail_next) b.clear();
     }
     std::vector<u64> ue_rows((size_t)T * 5, 0);
+    std::vector<std::vector<u32>> byz_flagged(T);               // senders judged anomalous by the receivers of each range
+    std::vector<u64> byz_rows((size_t)T * 2, 0);
     std::vector<std::pair<u32, u32>> ue_stamps;                 // (event, ltime) stamped this tick; published after the node loop
     std::mutex ue_stamp_mx;
     std::vector<std::vector<Msg>>& next = mail_next;
@@ -780,6 +799,14 @@ struct TickSim {
       if (up_s && wmask && cfg.probe_interval_ticks && any_down && ((t + v) % cfg.probe_interval_ticks) == 0)
         have_probe = probe_target(v, t, &ptarget);
       u32 max_tx = 0;
+      // byzantine entries that arrive now are judged against this node's views as they stand, before anything is merged
+      if (byz_n && up_r)
+        for (u32 i = head[v - v0]; i < head[v - v0 + 1]; ++i) {
+          const Msg& m = byd[i];
+          if (!m.byz) continue;
+          const View& q = at(m.slot, v);
+          if (byz_judge(q, m.kind, m.val, byz_delta)) byz_flagged[c].push_back(m.src);
+        }
       for (u32 s = 0; s < R; ++s) {
         View& r = at(s, v);
         const bool self = (subj[s] == v);
@@ -892,6 +919,17 @@ struct TickSim {
           bool pend = (r.txl | r.txj | r.txm) || ml_state(r) == ML_SUSPECT ||
                       (cfg.probe_interval_ticks && !subj_up[s] && !self && ((wmask >> s) & 1) && ml_state(r) == ML_ALIVE);   // a watcher that has not noticed yet
           if (pend) row.pending++;
+          // byzantine injector: a stale copy of the END-of-tick view goes to this tick's gossip peers, budgets or not
+          if (byz_n && byz[v] && known(r)) {
+            if (!have_targets) { nt = gossip_targets(v, t, targets); have_targets = true; }
+            u8 kind; u32 lt, key;
+            byz_stale(r, byz_delta, &kind, &lt, &key);
+            for (u32 k = 0; k < nt; ++k) {
+              post(Msg{targets[k], v, lt, (u8)s, kind, 1});
+              post(Msg{targets[k], v, key, (u8)s, 2, 1});
+              byz_rows[(size_t)c * 2] += 2; byz_rows[(size_t)c * 2 + 1] += 1;
+            }
+          }
         }
       }
       // ---------------- user events: receive, originate, send (serf/base.rs:750-837, serf/api.rs:241-299) ----------------
@@ -945,6 +983,12 @@ struct TickSim {
     if (T == 1) work(0);
     else { std::vector<std::thread> th; for (u32 c = 0; c < T; ++c) th.emplace_back(work, c); for (auto& x : th) x.join(); }
     mail.swap(mail_next);
+    if (byz_n) {
+      for (u32 c = 0; c < T; ++c) {
+        for (u32 src : byz_flagged[c]) if (!anomaly[src]) { anomaly[src] = 1; byz_tot[2]++; }
+        byz_tot[0] += byz_rows[(size_t)c * 2]; byz_tot[1] += byz_rows[(size_t)c * 2 + 1];
+      }
+    }
     if (ue_n) {
       ue_mail.swap(ue_mail_next);
       for (auto& st : ue_stamps) ue_ltime[st.first] = st.second;        // visible to receivers from the next tick on
@@ -1164,7 +1208,9 @@ ORC int oracle_sim_run_until_converged(void* p, u32 max_ticks, u32* ticks_out) {
     // times (status_time keeps creeping: the reference re-sends a Left member as "leave at status_ltime + 1",
     // serf/delegate.rs:495-510, so the round's `changed` counter ignores status_time)
     const bool pp_ok = !pp || ((s->tick % pp) == 0 && r.changed == 0);
-    if (r.pending == 0 && r.edge_updates == 0 && !s->future_events() && pp_ok) { if (ticks_out) *ticks_out = s->tick - 1; return 0; }
+    // with byzantine injectors stale entries are in flight forever: quiescent = no honest traffic AND nothing merged this tick
+    const bool byz_ok = !s->byz_n || r.changed == 0;
+    if (r.pending == 0 && r.edge_updates == 0 && !s->future_events() && pp_ok && byz_ok) { if (ticks_out) *ticks_out = s->tick - 1; return 0; }
   }
   if (ticks_out) *ticks_out = s->tick;
   return 1;
@@ -1198,6 +1244,25 @@ ORC int oracle_sim_stats(void* p, serfsim_stats_t* o) {
     }
     if (diff) o->disagree_slots++;
   }
+  return 0;
+}
+
+ORC void oracle_byz_stale(const void* rec32, u32 delta, u32* out /*kind, lt, key*/) { View r; memcpy(&r, rec32, 32); u8 k; byz_stale(r, delta, &k, &out[1], &out[2]); out[0] = k; }
+ORC int oracle_byz_judge(const void* rec32, u32 kind, u32 val, u32 delta) { View q; memcpy(&q, rec32, 32); return byz_judge(q, (u8)kind, val, delta); }
+// ---- byzantine injectors: same shapes as serfsim_set_byzantine / serfsim_anomaly_flags / serfsim_byzantine_stats ----
+ORC int oracle_sim_set_byzantine(void* p, u32 n, const u32* ids, u32 delta) {
+  auto* s = (TickSim*)p;
+  if ((n && !ids) || s->tick != 0 || !s->events.empty()) { g_err = "bad set_byzantine"; return SERFSIM_E_INVAL; }
+  if (n && (s->own_count != s->N || s->cfg.push_pull_interval_ticks > 0)) { g_err = "byzantine injectors: single shard, no push-pull"; return SERFSIM_E_INVAL; }
+  s->byz.assign(n ? s->N : 0, 0); s->byz_n = 0;
+  for (u32 i = 0; i < n; ++i) { if (ids[i] >= s->N || s->byz[ids[i]]) { g_err = "bad byzantine id"; return SERFSIM_E_INVAL; } s->byz[ids[i]] = 1; s->byz_n++; }
+  s->byz_delta = delta; s->anomaly.assign(n ? s->N : 0, 0); for (auto& x : s->byz_tot) x = 0;
+  return 0;
+}
+ORC int oracle_sim_anomaly_flags(void* p, u8* out) { auto* s = (TickSim*)p; if (!s->byz_n) return SERFSIM_E_INVAL; memcpy(out, s->anomaly.data(), s->N); return 0; }
+ORC int oracle_sim_byzantine_stats(void* p, serfsim_byz_stats_t* o) {
+  auto* s = (TickSim*)p; if (!s->byz_n) return SERFSIM_E_INVAL;
+  o->messages = s->byz_tot[0]; o->edge_updates = s->byz_tot[1]; o->flagged = s->byz_tot[2];
   return 0;
 }
 

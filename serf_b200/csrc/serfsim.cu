@@ -107,6 +107,11 @@ struct serfsim {
   u32* d_ue_ltime = nullptr;       // [MAX_UEVENTS]
   u64* d_ue_totals = nullptr;      // [8]
   u32 ue_injected = 0;             // tracked events already scheduled (each may be injected once)
+  // byzantine injectors (BASELINE configs[4]): allocated by serfsim_set_byzantine
+  u32 byz_n = 0, byz_delta = 2;
+  u32* d_byz_ids = nullptr;        // [byz_n] ascending
+  u8* d_anomaly = nullptr;         // [stride] sender flags
+  u64* d_byz_totals = nullptr;     // [4]
   // host state
   std::vector<HostOp> ops;         // sorted by (tick, seq)
   std::unordered_set<u64> op_keys; // (tick << 32 | node): at most one operation per node per tick
@@ -290,6 +295,15 @@ int launch_ticks(serfsim* h, u32 n) {
       h->last_launches += 2;
       h->xepoch++;
     }
+    if (h->byz_n) {                            // stale entries of the injectors, judged against the receivers' end-of-tick views
+      ByzParams b{};
+      b.n_byz = h->byz_n; b.first = h->first; b.R = h->R; b.stride = h->stride; b.fanout = h->cfg.fanout; b.tick = t;
+      b.seed_lo = p.seed_lo; b.seed_hi = p.seed_hi; b.delta = h->byz_delta; b.ids = h->d_byz_ids; b.rec = h->d_rec; b.node_state = h->d_node;
+      b.row_ptr = h->d_rowptr; b.col = h->d_col; b.inbox_wr = h->d_inbox[t & 1]; b.hot_wr = h->d_hot[t & 1]; b.kinds_cur = p.kinds_cur;
+      b.anomaly = h->d_anomaly; b.totals = h->d_byz_totals;
+      launch_byz(b, h->stream);
+      h->last_launches++;
+    }
     const u32 pp = (u32)std::max(0, h->cfg.push_pull_interval_ticks);
     if (pp && (t + 1) % pp == 0) {
       // anti-entropy round on a snapshot of the end-of-tick state (only this node's own records are written)
@@ -404,6 +418,7 @@ int do_reset(serfsim* h, u64 seed) {
   }
   if (h->d_send_count) CU(cudaMemsetAsync(h->d_send_count, 0, sizeof(u32) * 8, h->stream));
   { int rc = ue_reset(h); if (rc) return rc; }
+  if (h->byz_n) { CU(cudaMemsetAsync(h->d_anomaly, 0, h->stride, h->stream)); CU(cudaMemsetAsync(h->d_byz_totals, 0, 4 * 8, h->stream)); }
   { int rc = refresh_watchers(h); if (rc) return rc; }
   CU(cudaStreamSynchronize(h->stream));
   return 0;
@@ -416,6 +431,7 @@ void free_all(serfsim* h) {
   cudaFree(h->d_rec); cudaFree(h->d_inbox[0]); cudaFree(h->d_inbox[1]); cudaFree(h->d_node); cudaFree(h->d_rowptr); cudaFree(h->d_col);
   cudaFree(h->d_ev_node); cudaFree(h->d_ev_op); cudaFree(h->d_ev_slot); cudaFree(h->d_trace); cudaFree(h->d_kinds); cudaFree(h->d_ones);
   cudaFree(h->d_overflow); cudaFree(h->d_subj); cudaFree(h->d_scratch); cudaFree(h->d_stage);
+  cudaFree(h->d_byz_ids); cudaFree(h->d_anomaly); cudaFree(h->d_byz_totals);
   cudaFree(h->d_ue_state); cudaFree(h->d_ue_inbox[0]); cudaFree(h->d_ue_inbox[1]); cudaFree(h->d_ue_ltime); cudaFree(h->d_ue_totals);
   for (int par = 0; par < 2; ++par) { cudaFree(h->d_win_data[par]); cudaFree(h->d_peer_data[par]); }
   cudaFree(h->d_ctrl); cudaFree(h->d_send_count); cudaFree(h->d_peer_ctrl);
@@ -679,6 +695,7 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
   if (!h) return fail(SERFSIM_E_INVAL, "null handle");
   u32 chunk = 4;
   if (const char* e = getenv("SERFSIM_CHUNK")) chunk = std::max(1, atoi(e));
+  if (h->byz_n) chunk = 1;     // injector ticks are never no-ops, so no tick may be launched past the quiescent one
   const u32 pp = (u32)std::max(0, h->cfg.push_pull_interval_ticks);
   const u32 reap = h->cfg.reap_interval_ticks;
   // Ticks launched beyond the first quiescent one must be no-ops (they are rewound).  Anti-entropy rounds and reaper
@@ -686,7 +703,7 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
   auto boundary = [&](u32 t) { return (pp && (t + 1) % pp == 0) || (reap && (t + 1) % reap == 0); };
   const u32 start = h->tick;
   int rc = 0;
-  if (h->cfg.world_size == 1 && !pp && !reap && getenv("SERFSIM_SPECULATE")) {   // measured: no gain over the synchronous loop (the 8 extra no-op ticks cost what the gaps saved); off by default
+  if (h->cfg.world_size == 1 && !pp && !reap && !h->byz_n && getenv("SERFSIM_SPECULATE")) {   // measured: no gain over the synchronous loop (the 8 extra no-op ticks cost what the gaps saved); off by default
     // Pipelined convergence check (single GPU, no anti-entropy / reaper ticks): chunk k+1 is launched before the rows
     // of chunk k are inspected, so the GPU never waits for the host.  Ticks past the first quiescent one are no-ops on
     // a quiescent cluster and are rewound, exactly as in the synchronous loop below.
@@ -746,7 +763,8 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
       // with anti-entropy on, convergence additionally needs a push-pull round that changed nothing but Lamport times
       // (a Left member is re-sent as "leave at status_ltime + 1", serf/delegate.rs:495-510: status_time creeps by design)
       const bool pp_ok = !pp || (((t + 1) % pp) == 0 && r.changed == 0);
-      if (r.pending == 0 && r.edge_updates == 0 && !future_ops(h, t) && pp_ok) {
+      const bool byz_ok = !h->byz_n || r.changed == 0;       // stale entries stay in flight forever: quiescent = no honest traffic and nothing merged
+      if (r.pending == 0 && r.edge_updates == 0 && !future_ops(h, t) && pp_ok && byz_ok) {
         // ticks after t were no-ops on a quiescent cluster: rewind the logical clock to t + 1
         if (h->tick > t + 1) {
           CU(cudaMemsetAsync(h->d_trace + (size_t)(t + 1) * 8, 0, (size_t)(h->tick - t - 1) * 8 * sizeof(u64), h->stream));
@@ -834,6 +852,47 @@ int serfsim_stats(serfsim_t* h, serfsim_stats_t* o) {
   CU(cudaStreamSynchronize(h->stream));
   o->member_time = out[0]; o->intent_queue = out[1];
   for (u32 s = 0; s < h->R; ++s) if (out[2 + 2 * s] != ~0ull && out[2 + 2 * s] != out[3 + 2 * s]) o->disagree_slots++;
+  return 0;
+}
+
+// ---- byzantine injectors (BASELINE configs[4]; model in byz.cuh) ----
+int serfsim_set_byzantine(serfsim_t* h, uint32_t n, const uint32_t* ids, uint32_t delta) {
+  if (!h) return fail(SERFSIM_E_INVAL, "null handle");
+  if (n && !ids) return fail(SERFSIM_E_INVAL, "null ids");
+  if (h->tick != 0 || !h->ops.empty()) return fail(SERFSIM_E_INVAL, "serfsim_set_byzantine: call before any operation is scheduled (or after serfsim_reset)");
+  if (n && h->cfg.world_size > 1) return fail(SERFSIM_E_INVAL, "byzantine injectors are single-GPU in this version");
+  if (n && h->cfg.push_pull_interval_ticks > 0) return fail(SERFSIM_E_INVAL, "byzantine injectors cannot be combined with push-pull rounds in this version");
+  std::vector<u32> v(ids, ids + n);
+  std::sort(v.begin(), v.end());
+  for (u32 i = 0; i < n; ++i) if (v[i] >= h->N || (i && v[i] == v[i - 1])) return fail(SERFSIM_E_INVAL, "byzantine ids must be distinct node ids");
+  cudaFree(h->d_byz_ids); h->d_byz_ids = nullptr;
+  h->byz_n = 0; h->byz_delta = delta;
+  if (n) {
+    if (!h->d_anomaly) { CU(cudaMalloc(&h->d_anomaly, h->stride)); CU(cudaMalloc(&h->d_byz_totals, 4 * 8)); }
+    CU(cudaMalloc(&h->d_byz_ids, (size_t)n * 4));
+    CU(cudaMemcpy(h->d_byz_ids, v.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemset(h->d_anomaly, 0, h->stride));
+    CU(cudaMemset(h->d_byz_totals, 0, 4 * 8));
+    h->byz_n = n;
+  }
+  return 0;
+}
+
+int serfsim_anomaly_flags(serfsim_t* h, uint8_t* out) {
+  if (!h || !out) return fail(SERFSIM_E_INVAL, "null argument");
+  if (!h->byz_n) return fail(SERFSIM_E_INVAL, "no byzantine injectors set (serfsim_set_byzantine)");
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpy(out, h->d_anomaly, h->count, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int serfsim_byzantine_stats(serfsim_t* h, serfsim_byz_stats_t* o) {
+  if (!h || !o) return fail(SERFSIM_E_INVAL, "null argument");
+  if (!h->byz_n) return fail(SERFSIM_E_INVAL, "no byzantine injectors set (serfsim_set_byzantine)");
+  u64 t[4] = {0, 0, 0, 0};
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpy(t, h->d_byz_totals, 4 * 8, cudaMemcpyDeviceToHost));
+  o->messages = t[0]; o->edge_updates = t[1]; o->flagged = t[2];
   return 0;
 }
 

@@ -95,6 +95,21 @@ void launch_ue_init(uint4* state, u32 n_local, cudaStream_t st);
 void launch_ue_extract(const uint4* state, u32 n_local, int what, u32 e, void* out, cudaStream_t st);
 void launch_ue_summary(const uint4* state, u32 n_local, u32 first, u32 n_global, u32 R, u32 n_events, u64* out, cudaStream_t st);
 
+// Byzantine injectors (byz_kernel.cu; model in byz.cuh)
+struct ByzParams {
+  u32 n_byz, first, R, stride, fanout, tick, seed_lo, seed_hi, delta;
+  const u32* ids;             // [n_byz] byzantine node ids (ascending)
+  const uint4* rec;           // end-of-tick records
+  const u64* node_state;
+  const u32* row_ptr; const u32* col;
+  u32* inbox_wr;              // the planes this tick's membership kernel filled
+  u8* hot_wr;
+  u32* kinds_cur;
+  u8* anomaly;                // [n_local] sender flags
+  u64* totals;                // 0 injected entries, 1 injected (peer, subject) pairs, 2 senders flagged
+};
+void launch_byz(const ByzParams& p, cudaStream_t st);
+
 enum { EXTRACT_STATUS = 0, EXTRACT_STATUS_LTIME = 1, EXTRACT_CLOCK = 2, EXTRACT_INC = 3, EXTRACT_ML = 4 };
 
 }  // namespace sfs

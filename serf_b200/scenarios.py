@@ -10,8 +10,10 @@ from .sim import Op, full_mesh_graph, random_regular_graph, small_world_graph
 
 
 class Scenario:
-    def __init__(self, name, n, slots, topology, subjects, ops, cfg=None, max_ticks=2000, user_events=None):
+    def __init__(self, name, n, slots, topology, subjects, ops, cfg=None, max_ticks=2000, user_events=None, byzantine=None, delta=2):
         self.name, self.n, self.slots = name, n, slots
+        self.byzantine = None if byzantine is None else np.asarray(byzantine, dtype=np.uint32)   # stale-record injector ids
+        self.delta = delta
         self.user_events = None if user_events is None else np.asarray(user_events, dtype=np.uint32)   # content id per tracked user event
         self.row_ptr, self.col = topology
         self.subjects = np.asarray(subjects, dtype=np.uint32)
@@ -28,6 +30,8 @@ class Scenario:
         sim.set_subjects(self.subjects)
         if self.user_events is not None:
             sim.set_user_events(self.user_events)
+        if self.byzantine is not None:
+            sim.set_byzantine(self.byzantine, self.delta)
         self.schedule(sim)
         return sim
 
@@ -157,3 +161,21 @@ def user_event_storm(n=100_000, degree=16, fanout=3, seed=1, graph_seed=7, n_eve
         ops.append((1, Op.LEAVE, 0, 0))
     return Scenario(f"user_events_{n}_e{n_events}", n, 1, random_regular_graph(n, degree, graph_seed), subjects, ops,
                     dict(fanout=fanout, seed=seed), max_ticks=3000, user_events=content)
+
+
+def byzantine_injectors(n=100_000, degree=16, fanout=4, frac=0.01, delta=2, seed=1, graph_seed=7, slots=2, churn=True):
+    """BASELINE configs[4] shape: random graph, `frac` of the nodes re-inject stale (status_time - delta,
+    incarnation - delta) copies of their views every tick; the run carries a leave, a crash with probing (so
+    incarnations and Lamport times actually move) and a rejoin."""
+    rng = np.random.Generator(np.random.Philox(seed + 777))
+    subjects = [3, n // 2][:slots]
+    byz = rng.choice(np.arange(8, n), size=max(1, int(n * frac)), replace=False)
+    byz = byz[~np.isin(byz, subjects)]
+    ops = [(0, Op.LEAVE, subjects[0], 0)]
+    if slots > 1 and churn:
+        ops += [(2, Op.FAIL, subjects[1], 0), (30, Op.REJOIN, subjects[1], 0)]
+    cfg = dict(fanout=fanout, seed=seed, init_clock=12)      # Lamport times well above delta, so stale copies beat the bootstrap views
+    if churn:
+        cfg.update(suspicion_mult=2, suspicion_max_timeout_mult=2, probe_interval_ticks=2)
+    return Scenario(f"byzantine_{n}_f{frac}", n, slots, random_regular_graph(n, degree, graph_seed), subjects, ops, cfg,
+                    max_ticks=4000, byzantine=byz, delta=delta)

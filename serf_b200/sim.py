@@ -60,6 +60,13 @@ class Stats(C.Structure):              # serfsim_stats_t
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+class ByzantineStats(C.Structure):     # serfsim_byz_stats_t
+    _fields_ = [(n, C.c_uint64) for n in ("messages", "edge_updates", "flagged")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 class UserEventStats(C.Structure):     # serfsim_uevent_stats_t
     _fields_ = [(n, C.c_uint64) for n in ("messages", "edge_updates", "delivered", "duplicates", "too_old", "event_queue", "event_time")]
 
@@ -112,6 +119,9 @@ SIGNATURES = {
     "stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "tick_trace": (C.c_int, [_vp, _u32, _u32, _vp]),
     "state_hash": (C.c_int, [_vp, C.POINTER(_u64)]),
+    "set_byzantine": (C.c_int, [_vp, _u32, _vp, _u32]),
+    "anomaly_flags": (C.c_int, [_vp, _vp]),
+    "byzantine_stats": (C.c_int, [_vp, C.POINTER(ByzantineStats)]),
     "set_user_events": (C.c_int, [_vp, _u32, _vp]),
     "event_time": (C.c_int, [_vp, _vp]),
     "user_event_seen": (C.c_int, [_vp, _u32, _vp]),
@@ -276,6 +286,18 @@ class GossipSim:
     def incarnation(self, slot=0): return self._get("incarnation", np.uint32, slot)
     def ml_state(self, slot=0): return self._get("ml_state", np.uint8, slot)
     def records(self, slot=0): return self._get("records", RECORD_DTYPE, slot)
+
+    # -- byzantine stale-record injectors (BASELINE configs[4]) ------------------------------
+    def set_byzantine(self, ids, delta=2):
+        a = np.ascontiguousarray(ids, dtype=np.uint32)
+        self._check(self._fn("set_byzantine")(self._h, int(a.size), a.ctypes.data if a.size else None, int(delta)))
+
+    def anomaly_flags(self): return self._get("anomaly_flags", np.uint8)
+
+    def byzantine_stats(self):
+        s = ByzantineStats()
+        self._check(self._fn("byzantine_stats")(self._h, C.byref(s)))
+        return s.as_dict()
 
     # -- user events (Serf::user_event, serf/api.rs:241-299) ------------------------------
     def set_user_events(self, content_ids):
