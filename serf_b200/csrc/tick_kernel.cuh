@@ -12,6 +12,12 @@ constexpr int SFS_SMS = 148;                 // B200: grid-stride helper kernels
 #else
 constexpr int SFS_SMS = 1;
 #endif
+// Coverage probes of the host build (tests assert that a code path was actually taken); nothing under nvcc.
+#ifdef SERFSIM_EMU
+#define SFS_PROBE(i) (emu::probes[i]++)
+#else
+#define SFS_PROBE(i) ((void)0)
+#endif
 
 namespace sfs {
 

@@ -12,6 +12,7 @@
 namespace emu {
 
 LaneCtx* cur = nullptr;
+unsigned long probes[32] = {0};
 
 namespace {
 constexpr int MAX_THREADS = 1024;
@@ -141,3 +142,6 @@ void run_grid(unsigned grid, unsigned block, const std::function<void()>& fn) {
 }
 
 }  // namespace emu
+
+extern "C" __attribute__((visibility("default"))) unsigned long emu_probe(int i) { return emu::probes[i & 31]; }
+extern "C" __attribute__((visibility("default"))) void emu_probe_reset() { for (auto& p : emu::probes) p = 0; }
