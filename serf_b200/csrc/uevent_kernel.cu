@@ -6,8 +6,8 @@
 // queued and no host operation stops after those 20 bytes.  Sends are one RED.OR per (target, tick) into the other
 // parity's inbox plane.  Counters go to the same trace row the membership kernel fills (edge_updates, messages,
 // changed, pending, hash), so the convergence logic sees user events with no extra host code, plus run totals.
+#include "tick_kernel.cuh"   // first: brings in <cuda_runtime.h> (nvcc's own, or the host shim of tests/emu)
 #include "uevent.cuh"
-#include "tick_kernel.cuh"
 
 namespace sfs {
 namespace {
@@ -131,16 +131,16 @@ __global__ void __launch_bounds__(UE_BLOCK) ue_summary_kernel(const uint4* state
 }  // namespace
 
 void launch_uevent(const UeParams& p, bool trace, cudaStream_t st) {
-  const int grid = 148 * 8;
-  if (trace) uevent_kernel<true><<<grid, UE_BLOCK, 0, st>>>(p);
-  else uevent_kernel<false><<<grid, UE_BLOCK, 0, st>>>(p);
+  const int grid = SFS_SMS * 8;
+  if (trace) SFS_LAUNCH(grid, UE_BLOCK, 0, st, uevent_kernel<true>)(p);
+  else SFS_LAUNCH(grid, UE_BLOCK, 0, st, uevent_kernel<false>)(p);
 }
-void launch_ue_init(uint4* state, u32 n_local, cudaStream_t st) { ue_init_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(state, n_local); }
+void launch_ue_init(uint4* state, u32 n_local, cudaStream_t st) { SFS_LAUNCH((n_local + 255) / 256, 256, 0, st, ue_init_kernel)(state, n_local); }
 void launch_ue_extract(const uint4* state, u32 n_local, int what, u32 e, void* out, cudaStream_t st) {
-  ue_extract_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(state, n_local, what, e, out);
+  SFS_LAUNCH((n_local + 255) / 256, 256, 0, st, ue_extract_kernel)(state, n_local, what, e, out);
 }
 void launch_ue_summary(const uint4* state, u32 n_local, u32 first, u32 n_global, u32 R, u32 n_events, u64* out, cudaStream_t st) {
-  ue_summary_kernel<<<148 * 4, UE_BLOCK, 0, st>>>(state, n_local, first, n_global, R, n_events, out);
+  SFS_LAUNCH(SFS_SMS * 4, UE_BLOCK, 0, st, ue_summary_kernel)(state, n_local, first, n_global, R, n_events, out);
 }
 
 }  // namespace sfs
