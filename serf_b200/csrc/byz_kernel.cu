@@ -6,9 +6,9 @@
 // destination tile hot, and judges the entry against the receiver's end-of-tick record (one 32-byte gather per
 // (peer, subject)) to raise its OWN anomaly flag — a thread writes only its own flag, no atomics on that path.
 // At 1 % injectors and fan-out 4 this is ≈ 4 % of a plateau tick's gathers.
+#include "tick_kernel.cuh"   // first: brings in <cuda_runtime.h> (nvcc's own, or the host shim of tests/emu)
 #include "byz.cuh"
 #include "uevent.cuh"
-#include "tick_kernel.cuh"
 
 namespace sfs {
 namespace {
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(128) byz_kernel(const __grid_constant__ ByzPar
 
 void launch_byz(const ByzParams& p, cudaStream_t st) {
   if (!p.n_byz) return;
-  byz_kernel<<<(p.n_byz + 127) / 128, 128, 0, st>>>(p);
+  SFS_LAUNCH((p.n_byz + 127) / 128, 128, 0, st, byz_kernel)(p);
 }
 
 }  // namespace sfs
