@@ -3,7 +3,7 @@
 No reference semantics exist for this configuration: serf ignores stale intents silently.  The model is
 defined by the oracle (oracle/serf_oracle.cpp, "byzantine" block); these tests pin its properties and check that the
 host/device rules the CUDA kernel runs (serf_b200/csrc/byz.cuh, compiled for the host) agree with the oracle's on
-random records.  GPU parity: tests/test_gpu_byzantine.py.
+random records.  GPU parity: tests/test_gpu_z_byzantine.py.
 """
 import ctypes as C
 import os

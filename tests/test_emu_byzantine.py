@@ -1,5 +1,5 @@
 """Byzantine-injector kernel logic on the CPU: byz_kernel.cu (and the host code around it) compiled for the host by
-tests/emu, against the oracle's definition — the comparisons of tests/test_gpu_byzantine.py at small sizes."""
+tests/emu, against the oracle's definition — the comparisons of tests/test_gpu_z_byzantine.py at small sizes."""
 import numpy as np
 import pytest
 

@@ -1,5 +1,5 @@
 """User-event kernel logic on the CPU: uevent_kernel.cu (and the host code around it) compiled for the host by
-tests/emu, against the oracle's literal ring-buffer model — the comparisons of tests/test_gpu_uevent.py at sizes a
+tests/emu, against the oracle's literal ring-buffer model — the comparisons of tests/test_gpu_z_uevent.py at sizes a
 fiber scheduler finishes in seconds."""
 import numpy as np
 import pytest

@@ -6,7 +6,7 @@ Three layers are pinned against each other without a GPU:
   TickSim user events         N literal nodes (map-backed ring) driven tick by tick (oracle Part B)
   uevent.cuh                  the packed 16-byte / mask rules the CUDA kernel runs, compiled for the host by
                               tests/cpp/uevent_rules_check.cpp and wrapped in the kernel's data flow
-The GPU parity proper is tests/test_gpu_uevent.py.
+The GPU parity proper is tests/test_gpu_z_uevent.py.
 """
 import ctypes as C
 import os
