@@ -83,8 +83,8 @@ inline u32 ld_u32_stream(const u32* ptr, u64) { return *ptr; }
 inline void st_u32_stream(u32* ptr, u32 v, u64) { *ptr = v; }
 inline void st_u64_stream(u64* ptr, u64 v, u64) { *ptr = v; }
 inline void red_max_resident(u32* ptr, u32 v, u64) { if (v > *ptr) *ptr = v; }
-inline void st_release_sys(u32* ptr, u32 v) { *ptr = v; }
-inline u32 ld_acquire_sys(const u32* ptr) { return *ptr; }
+inline void st_release_sys(u32* ptr, u32 v) { __atomic_store_n(ptr, v, __ATOMIC_RELEASE); }     // peers are other threads of the test process
+inline u32 ld_acquire_sys(const u32* ptr) { return __atomic_load_n(ptr, __ATOMIC_ACQUIRE); }
 #endif
 
 #ifndef SERFSIM_EMU

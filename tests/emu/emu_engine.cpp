@@ -11,7 +11,7 @@
 
 namespace emu {
 
-LaneCtx* cur = nullptr;
+thread_local LaneCtx* cur = nullptr;
 unsigned long probes[32] = {0};
 
 namespace {
@@ -31,13 +31,18 @@ struct Warp {
   unsigned long long buf[2][32];
   unsigned votes[2];
 };
-Lane lanes[MAX_THREADS];
-Warp warps[MAX_THREADS / 32];
-int cta_live = 0, cta_arrived = 0;
-unsigned cta_gen = 0;
-ucontext_t sched_ctx;
-Lane* cur_lane = nullptr;
-const std::function<void()>* body = nullptr;
+struct Engine {                     // everything a rank thread needs to run kernels; created on first use
+  Lane lanes[MAX_THREADS];
+  Warp warps[MAX_THREADS / 32];
+};
+thread_local Engine* eng = nullptr;
+#define lanes (eng->lanes)
+#define warps (eng->warps)
+thread_local int cta_live = 0, cta_arrived = 0;
+thread_local unsigned cta_gen = 0;
+thread_local ucontext_t sched_ctx;
+thread_local Lane* cur_lane = nullptr;
+thread_local const std::function<void()>* body = nullptr;
 
 void release_check(Warp& w) { if (w.live > 0 && w.arrived >= w.live) { w.arrived = 0; w.gen++; } }
 void cta_release_check() { if (cta_live > 0 && cta_arrived >= cta_live) { cta_arrived = 0; cta_gen++; } }
@@ -101,6 +106,7 @@ unsigned warp_reduce_or(unsigned v) {
 void run_grid(unsigned grid, unsigned block, const std::function<void()>& fn) {
   if (block == 0 || block > (unsigned)MAX_THREADS) { fprintf(stderr, "emu: bad block size %u\n", block); abort(); }
   if (cur_lane) { fprintf(stderr, "emu: nested kernel launch\n"); abort(); }
+  if (!eng) eng = new Engine();
   body = &fn;
   for (unsigned t = 0; t < block; ++t)
     if (!lanes[t].stack) {
