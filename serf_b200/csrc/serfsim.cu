@@ -86,6 +86,8 @@ struct serfsim {
   bool watch_dirty = true;
   uint4* d_snap_rec = nullptr;     // push-pull rounds: end-of-tick snapshot of the records …
   u64* d_snap_node = nullptr;      // … and of the node words
+  const uint4** d_peer_snap_rec = nullptr;   // sharded push-pull: device arrays of every rank's snapshot pointers
+  const u64** d_peer_snap_node = nullptr;
   u8* d_hot[2] = {nullptr, nullptr};      // [n_tiles] per tick parity
   u32 n_tiles = 0;
   u32* d_rowptr = nullptr;         // [count+1]
@@ -107,6 +109,7 @@ struct serfsim {
   u32* d_ue_ltime = nullptr;       // [MAX_UEVENTS]
   u64* d_ue_totals = nullptr;      // [8]
   u32 ue_injected = 0;             // tracked events already scheduled (each may be injected once)
+  u32 ue_origin[MAX_UEVENTS] = {0};  // origin node of each scheduled event (its shard is the one that stamps the Lamport time)
   // byzantine injectors (BASELINE configs[4]): allocated by serfsim_set_byzantine
   u32 byz_n = 0, byz_delta = 2;
   u32* d_byz_ids = nullptr;        // [byz_n] ascending
@@ -272,6 +275,8 @@ int launch_ticks(serfsim* h, u32 n) {
       u.ltime = h->d_ue_ltime; u.node_state = h->d_node; u.busy = h->d_busy; u.row_ptr = h->d_rowptr; u.col = h->d_col;
       u.ev_node = h->d_ev_node; u.ev_op = h->d_ev_op; u.ev_slot = h->d_ev_slot;
       u.row = p.row; u.totals = h->d_ue_totals; u.overflow = h->d_overflow;
+      u.world = (u32)h->cfg.world_size; u.rank = (u32)h->cfg.rank; u.shard_size = h->shard_size; u.win_cap = h->win_cap;
+      u.win_data = h->d_peer_data[h->xepoch & 1]; u.send_count = h->d_send_count;
       launch_uevent(u, h->cfg.trace != 0, h->stream);
       h->last_launches++;
     }
@@ -291,6 +296,7 @@ int launch_ticks(serfsim* h, u32 n) {
       DrainParams d{};
       d.n_local = h->count; d.stride = h->stride; d.R = h->R; d.world = p.world; d.rank = p.rank; d.win_cap = h->win_cap; d.stamp = stamp; d.n_tiles = h->n_tiles; d.kinds_prev = p.kinds_prev;
       d.win_data = h->d_win_data[xpar]; d.ctrl = h->d_ctrl + xpar * 16; d.inbox_wr = h->d_inbox[t & 1]; d.hot_wr = h->d_hot[t & 1]; d.kinds_cur = h->d_kinds + ((size_t)t + 1) * 4; d.overflow = h->d_overflow;
+      d.ue_n = h->ue_table.n; d.ue_inbox_wr = h->ue_table.n ? h->d_ue_inbox[t & 1] : nullptr; d.ue_ltime = h->d_ue_ltime;
       launch_drain(d, h->stream);
       h->last_launches += 2;
       h->xepoch++;
@@ -311,7 +317,19 @@ int launch_ticks(serfsim* h, u32 n) {
       if (!h->d_snap_rec) { CU(cudaMalloc(&h->d_snap_rec, rb)); CU(cudaMalloc(&h->d_snap_node, nb)); }
       CU(cudaMemcpyAsync(h->d_snap_rec, h->d_rec, rb, cudaMemcpyDeviceToDevice, h->stream));
       CU(cudaMemcpyAsync(h->d_snap_node, h->d_node, nb, cudaMemcpyDeviceToDevice, h->stream));
-      launch_pushpull(p, h->d_snap_rec, h->d_snap_node, h->cfg.trace != 0, h->stream);
+      if (h->cfg.world_size > 1) {
+        // partners may live on other GPUs: their snapshots are read through the peer mappings.  Rounds are rare (every
+        // push_pull_interval ticks) and always the first tick of a convergence chunk, so two host barriers are affordable:
+        // every rank has taken its snapshot before anyone reads, everyone has read before anyone moves on.
+        p.snap_rec_peer = h->d_peer_snap_rec; p.snap_node_peer = h->d_peer_snap_node;
+        CU(cudaStreamSynchronize(h->stream));
+        h->barrier(h->comm_user);
+        launch_pushpull(p, h->d_snap_rec, h->d_snap_node, h->cfg.trace != 0, h->stream);
+        CU(cudaStreamSynchronize(h->stream));
+        h->barrier(h->comm_user);
+      } else {
+        launch_pushpull(p, h->d_snap_rec, h->d_snap_node, h->cfg.trace != 0, h->stream);
+      }
       h->last_launches++;
     }
     if (h->tick_timing) CU(cudaEventRecord(h->tick_ev[2 * (size_t)t + 1], h->stream));
@@ -427,7 +445,7 @@ int do_reset(serfsim* h, u64 seed) {
 void free_all(serfsim* h) {
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   for (cudaEvent_t e : h->tick_ev) cudaEventDestroy(e);
-  cudaFree(h->d_hot[0]); cudaFree(h->d_hot[1]); cudaFree(h->d_busy); cudaFree(h->d_watch); cudaFree(h->d_snap_rec); cudaFree(h->d_snap_node);
+  cudaFree(h->d_hot[0]); cudaFree(h->d_hot[1]); cudaFree(h->d_busy); cudaFree(h->d_watch); cudaFree(h->d_snap_rec); cudaFree(h->d_snap_node); cudaFree(h->d_peer_snap_rec); cudaFree(h->d_peer_snap_node);
   cudaFree(h->d_rec); cudaFree(h->d_inbox[0]); cudaFree(h->d_inbox[1]); cudaFree(h->d_node); cudaFree(h->d_rowptr); cudaFree(h->d_col);
   cudaFree(h->d_ev_node); cudaFree(h->d_ev_op); cudaFree(h->d_ev_slot); cudaFree(h->d_trace); cudaFree(h->d_kinds); cudaFree(h->d_ones);
   cudaFree(h->d_overflow); cudaFree(h->d_subj); cudaFree(h->d_scratch); cudaFree(h->d_stage);
@@ -488,7 +506,6 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
   if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) return fail(SERFSIM_E_INVAL, "bad rank / world_size");
   if (cfg->gossip_interval_ms == 0) return fail(SERFSIM_E_INVAL, "gossip_interval_ms must be > 0");
   if (cfg->push_pull_interval_ticks < 0) return fail(SERFSIM_E_INVAL, "push_pull_interval_ticks must be >= 0");
-  if (cfg->push_pull_interval_ticks > 0 && cfg->world_size > 1) return fail(SERFSIM_E_INVAL, "push-pull rounds are single-GPU in this version (world_size must be 1)");
   if (cfg->suspicion_mult >= 2 && cfg->suspicion_mult - 2 > MAX_K) return fail(SERFSIM_E_INVAL, "suspicion_mult too large");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -570,6 +587,12 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
     CUB(cudaMalloc(&h->d_send_count, 8 * sizeof(u32)));
     CUB(cudaMemset(h->d_send_count, 0, 8 * sizeof(u32)));
     CUB(cudaMalloc(&h->d_peer_ctrl, sizeof(u32*) * 8));
+    if (cfg->push_pull_interval_ticks > 0) {      // the snapshots partners on other GPUs read: allocated now so that they can be exported
+      CUB(cudaMalloc(&h->d_snap_rec, (size_t)h->R * h->stride * 32));
+      CUB(cudaMalloc(&h->d_snap_node, (size_t)h->stride * 8));
+      CUB(cudaMalloc(&h->d_peer_snap_rec, sizeof(void*) * 8));
+      CUB(cudaMalloc(&h->d_peer_snap_node, sizeof(void*) * 8));
+    }
   }
   {
     int rc = ensure_trace(h, 1024);
@@ -674,7 +697,7 @@ int serfsim_inject(serfsim_t* h, uint32_t tick, uint32_t op, uint32_t node, uint
   else if ((op == SERFSIM_OP_JOIN || op == SERFSIM_OP_LEAVE) && slot_of(h, node) < 0)
     return fail(SERFSIM_E_INVAL, "join/leave origin must be a tracked subject");
   if (!h->op_keys.insert(((u64)tick << 32) | node).second) return fail(SERFSIM_E_INVAL, "one operation per node per tick");
-  if (op == SERFSIM_OP_USER_EVENT) h->ue_injected |= 1u << slot;
+  if (op == SERFSIM_OP_USER_EVENT) { h->ue_injected |= 1u << slot; h->ue_origin[slot] = node; }
   h->ops.push_back(HostOp{tick, op, node, slot, h->op_seq++});
   h->ops_dirty = true;
   return 0;
@@ -902,7 +925,6 @@ int serfsim_set_user_events(serfsim_t* h, uint32_t n_events, const uint32_t* con
   if (n_events > MAX_UEVENTS) return fail(SERFSIM_E_INVAL, "at most SERFSIM_MAX_USER_EVENTS tracked user events");
   if (n_events && !content_ids) return fail(SERFSIM_E_INVAL, "null content ids");
   if (h->tick != 0 || !h->ops.empty()) return fail(SERFSIM_E_INVAL, "serfsim_set_user_events: call before any operation is scheduled (or after serfsim_reset)");
-  if (n_events && h->cfg.world_size > 1) return fail(SERFSIM_E_INVAL, "user events are single-GPU in this version");
   if (n_events && h->cfg.push_pull_interval_ticks > 0) return fail(SERFSIM_E_INVAL, "user events cannot be combined with push-pull rounds in this version");
   if (n_events && !h->d_ue_state) {
     CU(cudaMalloc(&h->d_ue_state, (size_t)h->stride * 16));
@@ -945,6 +967,12 @@ int serfsim_user_event_ltime(serfsim_t* h, uint32_t event, uint64_t* ltime) {
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaMemcpy(&v, h->d_ue_ltime + event, 4, cudaMemcpyDeviceToHost));
   *ltime = v;
+  if (h->cfg.world_size > 1) {                      // the origin's shard stamped it; the others contribute 0 to the sum
+    if (!h->allreduce) return fail(SERFSIM_E_COMM, "world_size > 1: serfsim_comm_set_hooks was not called");
+    const bool scheduled = (h->ue_injected >> event) & 1u;
+    if (!scheduled || h->ue_origin[event] - h->first >= h->count) *ltime = 0;
+    h->allreduce(h->comm_user, ltime, 1);
+  }
   return 0;
 }
 
@@ -966,8 +994,13 @@ int serfsim_user_event_stats(serfsim_t* h, serfsim_uevent_stats_t* o) {
   CU(cudaMemcpyAsync(sum, h->d_scratch, 3 * 8, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaMemcpyAsync(tot, h->d_ue_totals, 8 * 8, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  o->messages = tot[0]; o->edge_updates = tot[1]; o->delivered = tot[2]; o->duplicates = tot[3]; o->too_old = tot[4];
-  o->event_queue = sum[0]; o->event_time = sum[1];
+  u64 v[6] = {tot[0], tot[1], tot[2], tot[3], tot[4], sum[0]};
+  if (h->cfg.world_size > 1) {                      // counters are sums over shards; event_time (a maximum) stays shard-local
+    if (!h->allreduce) return fail(SERFSIM_E_COMM, "world_size > 1: serfsim_comm_set_hooks was not called");
+    h->allreduce(h->comm_user, v, 6);
+  }
+  o->messages = v[0]; o->edge_updates = v[1]; o->delivered = v[2]; o->duplicates = v[3]; o->too_old = v[4];
+  o->event_queue = v[5]; o->event_time = sum[1];
   return 0;
 }
 
@@ -999,7 +1032,7 @@ int serfsim_tick_times(serfsim_t* h, uint32_t first_tick, uint32_t n, float* ms_
 }
 
 // ---- multi-GPU: CUDA IPC windows ----------------------------------------------------------
-struct comm_blob { cudaIpcMemHandle_t data[2]; cudaIpcMemHandle_t ctrl; u32 win_cap; u32 rank; };
+struct comm_blob { cudaIpcMemHandle_t data[2]; cudaIpcMemHandle_t ctrl; cudaIpcMemHandle_t snap_rec, snap_node; u32 win_cap; u32 rank; u32 has_snap; u32 pad; };
 
 size_t serfsim_comm_blob_size(void) { return sizeof(comm_blob); }
 
@@ -1010,6 +1043,10 @@ int serfsim_comm_export(serfsim_t* h, void* blob) {
   for (int par = 0; par < 2; ++par) CU(cudaIpcGetMemHandle(&b.data[par], h->d_win_data[par]));
   CU(cudaIpcGetMemHandle(&b.ctrl, h->d_ctrl));
   b.win_cap = h->win_cap; b.rank = (u32)h->cfg.rank;
+  if (h->d_snap_rec) {                              // push-pull rounds are on: partners on other GPUs read these
+    CU(cudaIpcGetMemHandle(&b.snap_rec, h->d_snap_rec)); CU(cudaIpcGetMemHandle(&b.snap_node, h->d_snap_node));
+    b.has_snap = 1;
+  }
   memcpy(blob, &b, sizeof(b));
   return 0;
 }
@@ -1022,10 +1059,21 @@ int serfsim_comm_connect(serfsim_t* h, const void* blobs) {
   const comm_blob* bs = (const comm_blob*)blobs;
   std::vector<u32*> pc(8, nullptr);
   std::vector<std::vector<u64*>> pd(2, std::vector<u64*>(8, nullptr));
+  std::vector<const uint4*> psr(8, nullptr);
+  std::vector<const u64*> psn(8, nullptr);
   for (int r = 0; r < W; ++r) {
     if (bs[r].rank != (u32)r || bs[r].win_cap != h->win_cap) return fail(SERFSIM_E_COMM, "blob order / window size mismatch");
-    if (r == h->cfg.rank) { pd[0][r] = h->d_win_data[0]; pd[1][r] = h->d_win_data[1]; pc[r] = h->d_ctrl; continue; }
+    if ((bs[r].has_snap != 0) != (h->d_snap_rec != nullptr)) return fail(SERFSIM_E_COMM, "push_pull_interval_ticks differs between ranks");
+    if (r == h->cfg.rank) { pd[0][r] = h->d_win_data[0]; pd[1][r] = h->d_win_data[1]; pc[r] = h->d_ctrl; psr[r] = h->d_snap_rec; psn[r] = h->d_snap_node; continue; }
     void* ptr = nullptr;
+    if (bs[r].has_snap) {
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, bs[r].snap_rec, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return fail(SERFSIM_E_COMM, std::string("cudaIpcOpenMemHandle(snapshot): ") + cudaGetErrorString(e));
+      h->ipc_opened.push_back(ptr); psr[r] = (const uint4*)ptr;
+      e = cudaIpcOpenMemHandle(&ptr, bs[r].snap_node, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return fail(SERFSIM_E_COMM, std::string("cudaIpcOpenMemHandle(snapshot): ") + cudaGetErrorString(e));
+      h->ipc_opened.push_back(ptr); psn[r] = (const u64*)ptr;
+    }
     for (int par = 0; par < 2; ++par) {
       cudaError_t e = cudaIpcOpenMemHandle(&ptr, bs[r].data[par], cudaIpcMemLazyEnablePeerAccess);
       if (e != cudaSuccess) return fail(SERFSIM_E_COMM, std::string("cudaIpcOpenMemHandle(window): ") + cudaGetErrorString(e));
@@ -1037,6 +1085,10 @@ int serfsim_comm_connect(serfsim_t* h, const void* blobs) {
   }
   for (int par = 0; par < 2; ++par) CU(cudaMemcpy(h->d_peer_data[par], pd[par].data(), sizeof(u64*) * 8, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(h->d_peer_ctrl, pc.data(), sizeof(u32*) * 8, cudaMemcpyHostToDevice));
+  if (h->d_snap_rec) {
+    CU(cudaMemcpy(h->d_peer_snap_rec, psr.data(), sizeof(void*) * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_peer_snap_node, psn.data(), sizeof(void*) * 8, cudaMemcpyHostToDevice));
+  }
   h->barrier(h->comm_user);          // every rank has mapped every window before the first tick writes into one
   h->connected = true;
   return 0;

@@ -710,8 +710,20 @@ __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__
     philox4x32_10(p.tick, v, 0, DOMAIN_PUSHPULL, p.seed_lo, p.seed_hi, w);
     const u32 u = p.col[row0 + (((w[0] & 0xffffu) * deg) >> 16)];
     if (u == v) continue;
-    const u32 ul = u - p.first;                               // single-GPU only (checked by the host)
-    const u64 nu = snap_node[ul];
+    // the partner may live in another shard: its rank's snapshot is read through the peer mapping (the host
+    // separates "every rank has taken its snapshot" and "every rank has finished reading" with barriers)
+    u32 ul = u - p.first;
+    const u64* part_node = snap_node;
+    const uint4* part_rec = snap_rec;
+    u32 part_stride = p.stride;
+    if (p.world > 1) {
+      const u32 shard = u / p.shard_size;
+      ul = u - shard * p.shard_size;
+      part_node = p.snap_node_peer[shard]; part_rec = p.snap_rec_peer[shard];
+      const u32 cnt = min(p.shard_size, p.n_global - shard * p.shard_size);
+      part_stride = ((cnt + BLOCK - 1) / BLOCK) * BLOCK;
+    }
+    const u64 nu = part_node[ul];
     if (!(nu & NS_UP)) continue;
     u32 clock = (u32)ns;
     const u32 sstate = (u32)(ns >> 40) & 3;
@@ -720,11 +732,11 @@ __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__
     bool any_pending = false;
     const u32 wmask = p.watch[vl];
     for (u32 s = 0; s < p.R; ++s) {
-      const size_t iv = (size_t)s * p.stride + vl, iu = (size_t)s * p.stride + ul;
+      const size_t iv = (size_t)s * p.stride + vl, iu = (size_t)s * part_stride + ul;
       const uint4 a0 = p.rec[2 * iv], b0 = p.rec[2 * iv + 1];
       Rec r, q;
       unpack(a0, b0, r);
-      unpack(snap_rec[2 * iu], snap_rec[2 * iu + 1], q);
+      unpack(part_rec[2 * iu], part_rec[2 * iu + 1], q);
       const bool self = (p.subj[s] == v);
       const bool was = (r.txl | r.txj | r.txm) || r.mlstate == ML_SUSPECT || (p.probe_every && ((p.down_mask >> s) & 1) && !self && ((wmask >> s) & 1) && r.mlstate == ML_ALIVE);
       if (q.flags & 1) {
@@ -802,6 +814,9 @@ __global__ void __launch_bounds__(BLOCK) drain_kernel(const __grid_constant__ Dr
         atomicMax(p.inbox_wr + ((size_t)(kind * p.R + s)) * p.stride + dl, val1);
         if (mark) p.hot_wr[dl >> TILE_SHIFT] = 1;
         seen |= 1u << kind;
+      } else if (dl < p.n_local && kind == 3 && s < p.ue_n && val1) {   // user event s arrived: one bit, and the time its origin stamped
+        atomicOr(p.ue_inbox_wr + dl, 1u << s);
+        p.ue_ltime[s] = val1 - 1;                      // every copy carries the same value; this shard learns it no later than the event itself
       }
       else *p.overflow = 3;
     }

@@ -49,6 +49,8 @@ struct TickParams {
   u8* hot_wr;                 // [n_tiles] tile flags for the next tick
   u32 stage_col_bytes, reap_now, pad2, pad3;         // reap_now: this tick the reaper runs (every view is visited)
   u32 tombstone_ticks, reconnect_ticks, intent_ticks, pad4;             // > 0: single-slot TMA pipeline with this many bytes of CSR per stage
+  // sharded push-pull rounds: every rank's end-of-tick snapshot, indexed by shard (null when world == 1)
+  const uint4* const* snap_rec_peer; const u64* const* snap_node_peer;
   u32 n_tiles, tiles_per_cta, force_all, stride;   // stride: plane stride in nodes = n_local rounded up to a whole tile
   // cross-shard exchange (world_size > 1): every rank owns one receive window per peer (mapped into the
   // peers with CUDA IPC); the tick kernel stages cross-shard entries per destination shard in shared memory
@@ -73,6 +75,10 @@ struct DrainParams {
   u8* hot_wr;
   u32* kinds_cur;             // [4] kind counters of this tick (received kinds are added so the next tick reads their planes)
   u32* overflow;
+  // user-event entries (kind 3: slot = tracked event, value = its Lamport time + 1); null / 0 when user events are off
+  u32 ue_n;
+  u32* ue_inbox_wr;
+  u32* ue_ltime;
 };
 
 void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st);
@@ -104,6 +110,10 @@ struct UeParams {
   u64* row;                   // this tick's trace row (shared with the membership kernel)
   u64* totals;                // run totals: 0 messages, 1 edges, 2 delivered, 3 duplicates, 4 too_old
   u32* overflow;
+  // sharded runs: a target outside [first, first + n_local) gets one window entry per event (kind 3) over NVLink
+  u32 world, rank, shard_size, win_cap;
+  u64* const* win_data;       // [world] peers' receive windows of this exchange parity
+  u32* send_count;            // [world] entries written into each peer's window this tick (shared with the tick kernel)
 };
 void launch_uevent(const UeParams& p, bool trace, cudaStream_t st);
 void launch_ue_init(uint4* state, u32 n_local, cudaStream_t st);

@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(UE_BLOCK) uevent_kernel(const __grid_constant_
   UeCounts c = {};
   u32 changed = 0;
   u64 hash = 0;
+  bool wrote_remote = false;
   for (u32 vl = blockIdx.x * UE_BLOCK + threadIdx.x; vl < p.n_local; vl += gridDim.x * UE_BLOCK) {
     const u32 v = p.first + vl;
     const u32 arrived = p.inbox_rd[vl];
@@ -63,8 +64,23 @@ __global__ void __launch_bounds__(UE_BLOCK) uevent_kernel(const __grid_constant_
       const u32 nt = ue_pick_targets(p.tick, v, row0, deg, p.fanout, p.seed_lo, p.seed_hi, p.col, tg);
       u32 bits[MAX_FANOUT];
       c.messages += ue_plan_send<(int)MAX_FANOUT>(r, p.table.n, nt, bits);
-      for (u32 k = 0; k < nt; ++k)
-        if (bits[k]) { atomicOr(p.inbox_wr + (tg[k] - p.first), bits[k]); c.edges++; }
+      for (u32 k = 0; k < nt; ++k) {
+        if (!bits[k]) continue;
+        c.edges++;
+        const u32 dl = tg[k] - p.first;
+        if (p.world == 1 || dl < p.n_local) { atomicOr(p.inbox_wr + dl, bits[k]); continue; }
+        // another shard owns the target: one 8-byte entry per event into its window (kind 3, slot = event, value = ltime + 1)
+        const u32 shard = tg[k] / p.shard_size, dloc = tg[k] - shard * p.shard_size;
+        for (u32 e = 0; e < p.table.n; ++e) {
+          if (!((bits[k] >> e) & 1u)) continue;
+          const u32 Le = (stamped && e == op_slot) ? L : p.ltime[e];
+          const u64 entry = ((u64)(Le + 1u) << 32) | ((u64)e << 28) | (3ull << 26) | dloc;
+          const u32 g = atomicAdd(p.send_count + shard, 1u);
+          if (g < p.win_cap) p.win_data[shard][(size_t)p.rank * p.win_cap + g] = entry;
+          else *p.overflow = 2;
+          wrote_remote = true;
+        }
+      }
     }
     if (up_s) c.pending += ue_queued(r, p.table.n);           // a crashed node's queue is frozen, not pending
     const uint4 w1 = ue_pack(r);
@@ -72,6 +88,7 @@ __global__ void __launch_bounds__(UE_BLOCK) uevent_kernel(const __grid_constant_
     if (TRACE) hash += ue_hash((u64)(p.R + 1) * p.n_global + v, w1);
     if (r.clock >= LTIME_LIMIT) *p.overflow = 1;
   }
+  if (wrote_remote) __threadfence_system();   // peer-window stores are performed before the publish kernel raises the flags
   // warp sums, one atomic per warp and counter (this kernel is not the hot path; the row is shared with the tick kernel)
   const u32 lane = threadIdx.x & 31;
   const u32 s_msgs = ue_warp_sum(c.messages), s_edges = ue_warp_sum(c.edges), s_deliv = ue_warp_sum(c.delivered),
