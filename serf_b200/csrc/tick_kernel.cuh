@@ -49,8 +49,6 @@ struct TickParams {
   u8* hot_wr;                 // [n_tiles] tile flags for the next tick
   u32 stage_col_bytes, reap_now, pad2, pad3;         // reap_now: this tick the reaper runs (every view is visited)
   u32 tombstone_ticks, reconnect_ticks, intent_ticks, pad4;             // > 0: single-slot TMA pipeline with this many bytes of CSR per stage
-  // sharded push-pull rounds: every rank's end-of-tick snapshot, indexed by shard (null when world == 1)
-  const uint4* const* snap_rec_peer; const u64* const* snap_node_peer;
   u32 n_tiles, tiles_per_cta, force_all, stride;   // stride: plane stride in nodes = n_local rounded up to a whole tile
   // cross-shard exchange (world_size > 1): every rank owns one receive window per peer (mapped into the
   // peers with CUDA IPC); the tick kernel stages cross-shard entries per destination shard in shared memory
@@ -58,6 +56,9 @@ struct TickParams {
   u32 world, rank, shard_size, win_cap;
   u64* const* win_data;       // [world] peer windows of this exchange parity; my segment starts at rank·win_cap
   u32* send_count;            // [world] entries written so far into each peer's window (local counters)
+  // sharded push-pull rounds: every rank's end-of-tick snapshot, indexed by shard (null when world == 1).  New members go
+  // at the end: the tick kernels do not read them and keep their parameter offsets (and their SASS) unchanged.
+  const uint4* const* snap_rec_peer; const u64* const* snap_node_peer;
 };
 
 struct PublishParams {        // after the tick kernel: tell every peer how much was written, then raise its flag
