@@ -227,7 +227,9 @@ int serfsim_user_event_stats (serfsim_t* h, serfsim_uevent_stats_t* out);
  * saturating) to that tick's gossip peers.  anomaly[u] = 1 once a receiver that was up held a view newer than
  * u's injected entry by ≥ delta.  Call before scheduling operations; n = 0 switches injectors off.  With
  * injectors on, serfsim_run_until_converged stops at the first tick with no honest traffic, nothing pending
- * and nothing merged.  Single-GPU, and not together with push-pull rounds, in this version. */
+ * and nothing merged.  Works sharded: every rank passes the GLOBAL id list and keeps the injectors of its shard; an
+ * entry bound for another shard is judged by that shard against its own record and the flag is raised in the
+ * sender's shard over NVLink.  Not together with push-pull rounds in this version. */
 int serfsim_set_byzantine  (serfsim_t* h, uint32_t n, const uint32_t* ids /*[n]*/, uint32_t delta);
 int serfsim_anomaly_flags  (serfsim_t* h, uint8_t* out /*[count]*/);
 int serfsim_byzantine_stats(serfsim_t* h, serfsim_byz_stats_t* out);

@@ -15,7 +15,8 @@ namespace {
 
 __global__ void __launch_bounds__(128) byz_kernel(const __grid_constant__ ByzParams p) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  u32 n_msgs = 0, n_edges = 0, kL = 0, kJ = 0, kM = 0, newly = 0;
+  u32 n_msgs = 0, n_edges = 0, kL = 0, kJ = 0, kM = 0;
+  bool wrote_remote = false;
   if (i < p.n_byz) {
     const u32 u = p.ids[i];
     const u32 ul = u - p.first;
@@ -35,10 +36,24 @@ __global__ void __launch_bounds__(128) byz_kernel(const __grid_constant__ ByzPar
         u32* const planeM = p.inbox_wr + (size_t)(KIND_ML * p.R + s) * p.stride;
         for (u32 k = 0; k < nt; ++k) {
           const u32 dl = tg[k] - p.first;
+          n_msgs += 2; n_edges += 1;
+          if (p.world > 1 && dl >= p.n_local) {                // the peer lives in another shard: triple into its window
+            const u32 shard = tg[k] / p.shard_size, dloc = (tg[k] - shard * p.shard_size) | BYZ_FLAG;
+            const u32 g = atomicAdd(p.send_count + shard, 3u);
+            if (g + 3 <= p.win_cap) {
+              u64* w = p.win_data[shard] + (size_t)p.rank * p.win_cap + g;
+              w[0] = ((u64)(e.serf_lt + 1u) << 32) | ((u64)s << 28) | ((u64)e.serf_kind << 26) | dloc;
+              w[1] = ((u64)(e.ml_key + 1u) << 32) | ((u64)s << 28) | ((u64)KIND_ML << 26) | dloc;
+              w[2] = ((u64)(u + 1u) << 32) | ((u64)BYZ_ANNOT_SLOT << 28) | (3ull << 26) | dloc;
+            } else {
+              *p.overflow = 2;
+            }
+            wrote_remote = true;
+            continue;                                          // kinds / tile flags / verdict are the receiving shard's business
+          }
           atomicMax(planeS + dl, e.serf_lt + 1u);
           atomicMax(planeM + dl, e.ml_key + 1u);
           p.hot_wr[dl >> 8] = 1;                               // TILE_SHIFT = 8: the destination tile must run next tick
-          n_msgs += 2; n_edges += 1;
           if (e.serf_kind == KIND_LEAVE) ++kL; else ++kJ;
           ++kM;
           if (p.node_state[dl] & NS_UP) {                      // the receiver is up when the packet arrives
@@ -49,21 +64,20 @@ __global__ void __launch_bounds__(128) byz_kernel(const __grid_constant__ ByzPar
           }
         }
       }
-      if (flag && !p.anomaly[ul]) { p.anomaly[ul] = 1; newly = 1; }
+      if (flag) p.anomaly[ul] = 1;
     }
   }
+  if (wrote_remote) __threadfence_system();   // peer-window stores are performed before the publish kernel raises the flags
   // warp sums → a few atomics per warp
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     n_msgs += __shfl_xor_sync(0xffffffffu, n_msgs, o); n_edges += __shfl_xor_sync(0xffffffffu, n_edges, o);
     kL += __shfl_xor_sync(0xffffffffu, kL, o); kJ += __shfl_xor_sync(0xffffffffu, kJ, o); kM += __shfl_xor_sync(0xffffffffu, kM, o);
-    newly += __shfl_xor_sync(0xffffffffu, newly, o);
   }
   if ((threadIdx.x & 31) == 0) {
     typedef unsigned long long ull;
     if (n_msgs) atomicAdd((ull*)(p.totals + 0), (ull)n_msgs);
     if (n_edges) atomicAdd((ull*)(p.totals + 1), (ull)n_edges);
-    if (newly) atomicAdd((ull*)(p.totals + 2), (ull)newly);
     if (kL) atomicAdd(p.kinds_cur + KIND_LEAVE, kL);
     if (kJ) atomicAdd(p.kinds_cur + KIND_JOIN, kJ);
     if (kM) atomicAdd(p.kinds_cur + KIND_ML, kM);

@@ -111,7 +111,9 @@ struct serfsim {
   u32 ue_injected = 0;             // tracked events already scheduled (each may be injected once)
   u32 ue_origin[MAX_UEVENTS] = {0};  // origin node of each scheduled event (its shard is the one that stamps the Lamport time)
   // byzantine injectors (BASELINE configs[4]): allocated by serfsim_set_byzantine
-  u32 byz_n = 0, byz_delta = 2;
+  u32 byz_n = 0, byz_delta = 2;    // byz_n: injectors of THIS shard
+  bool byz_on = false;             // any injector anywhere (all ranks agree): changes the convergence rule and the drain kernel
+  u8** d_peer_anomaly = nullptr;   // sharded runs: device array of every rank's flag array
   u32* d_byz_ids = nullptr;        // [byz_n] ascending
   u8* d_anomaly = nullptr;         // [stride] sender flags
   u64* d_byz_totals = nullptr;     // [4]
@@ -282,6 +284,17 @@ int launch_ticks(serfsim* h, u32 n) {
     }
     launch_tick(p, h->cfg.trace != 0, h->grid, h->stream);
     h->last_launches++;
+    if (h->byz_n) {                            // stale entries of this shard's injectors (before the exchange: peers in other shards get window entries)
+      ByzParams b{};
+      b.n_byz = h->byz_n; b.first = h->first; b.R = h->R; b.stride = h->stride; b.fanout = h->cfg.fanout; b.tick = t;
+      b.seed_lo = p.seed_lo; b.seed_hi = p.seed_hi; b.delta = h->byz_delta; b.ids = h->d_byz_ids; b.rec = h->d_rec; b.node_state = h->d_node;
+      b.row_ptr = h->d_rowptr; b.col = h->d_col; b.inbox_wr = h->d_inbox[t & 1]; b.hot_wr = h->d_hot[t & 1]; b.kinds_cur = p.kinds_cur;
+      b.anomaly = h->d_anomaly; b.totals = h->d_byz_totals;
+      b.n_local = h->count; b.world = p.world; b.rank = p.rank; b.shard_size = h->shard_size; b.win_cap = h->win_cap;
+      b.win_data = p.win_data; b.send_count = h->d_send_count; b.overflow = h->d_overflow;
+      launch_byz(b, h->stream);
+      h->last_launches++;
+    }
     if (h->tick_timing && h->cfg.world_size > 1) {
       while (h->mid_ev.size() < (size_t)t + 1) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->mid_ev.push_back(e); }
       CU(cudaEventRecord(h->mid_ev[t], h->stream));
@@ -296,19 +309,11 @@ int launch_ticks(serfsim* h, u32 n) {
       DrainParams d{};
       d.n_local = h->count; d.stride = h->stride; d.R = h->R; d.world = p.world; d.rank = p.rank; d.win_cap = h->win_cap; d.stamp = stamp; d.n_tiles = h->n_tiles; d.kinds_prev = p.kinds_prev;
       d.win_data = h->d_win_data[xpar]; d.ctrl = h->d_ctrl + xpar * 16; d.inbox_wr = h->d_inbox[t & 1]; d.hot_wr = h->d_hot[t & 1]; d.kinds_cur = h->d_kinds + ((size_t)t + 1) * 4; d.overflow = h->d_overflow;
+      d.byz_on = h->byz_on ? 1u : 0u; d.byz_delta = h->byz_delta; d.shard_size = h->shard_size; d.rec = h->d_rec; d.node_state = h->d_node; d.peer_anomaly = h->d_peer_anomaly;
       d.ue_n = h->ue_table.n; d.ue_inbox_wr = h->ue_table.n ? h->d_ue_inbox[t & 1] : nullptr; d.ue_ltime = h->d_ue_ltime;
       launch_drain(d, h->stream);
       h->last_launches += 2;
       h->xepoch++;
-    }
-    if (h->byz_n) {                            // stale entries of the injectors, judged against the receivers' end-of-tick views
-      ByzParams b{};
-      b.n_byz = h->byz_n; b.first = h->first; b.R = h->R; b.stride = h->stride; b.fanout = h->cfg.fanout; b.tick = t;
-      b.seed_lo = p.seed_lo; b.seed_hi = p.seed_hi; b.delta = h->byz_delta; b.ids = h->d_byz_ids; b.rec = h->d_rec; b.node_state = h->d_node;
-      b.row_ptr = h->d_rowptr; b.col = h->d_col; b.inbox_wr = h->d_inbox[t & 1]; b.hot_wr = h->d_hot[t & 1]; b.kinds_cur = p.kinds_cur;
-      b.anomaly = h->d_anomaly; b.totals = h->d_byz_totals;
-      launch_byz(b, h->stream);
-      h->last_launches++;
     }
     const u32 pp = (u32)std::max(0, h->cfg.push_pull_interval_ticks);
     if (pp && (t + 1) % pp == 0) {
@@ -436,7 +441,7 @@ int do_reset(serfsim* h, u64 seed) {
   }
   if (h->d_send_count) CU(cudaMemsetAsync(h->d_send_count, 0, sizeof(u32) * 8, h->stream));
   { int rc = ue_reset(h); if (rc) return rc; }
-  if (h->byz_n) { CU(cudaMemsetAsync(h->d_anomaly, 0, h->stride, h->stream)); CU(cudaMemsetAsync(h->d_byz_totals, 0, 4 * 8, h->stream)); }
+  if (h->d_anomaly) { CU(cudaMemsetAsync(h->d_anomaly, 0, h->stride, h->stream)); CU(cudaMemsetAsync(h->d_byz_totals, 0, 4 * 8, h->stream)); }
   { int rc = refresh_watchers(h); if (rc) return rc; }
   CU(cudaStreamSynchronize(h->stream));
   return 0;
@@ -449,7 +454,7 @@ void free_all(serfsim* h) {
   cudaFree(h->d_rec); cudaFree(h->d_inbox[0]); cudaFree(h->d_inbox[1]); cudaFree(h->d_node); cudaFree(h->d_rowptr); cudaFree(h->d_col);
   cudaFree(h->d_ev_node); cudaFree(h->d_ev_op); cudaFree(h->d_ev_slot); cudaFree(h->d_trace); cudaFree(h->d_kinds); cudaFree(h->d_ones);
   cudaFree(h->d_overflow); cudaFree(h->d_subj); cudaFree(h->d_scratch); cudaFree(h->d_stage);
-  cudaFree(h->d_byz_ids); cudaFree(h->d_anomaly); cudaFree(h->d_byz_totals);
+  cudaFree(h->d_byz_ids); cudaFree(h->d_anomaly); cudaFree(h->d_byz_totals); cudaFree(h->d_peer_anomaly);
   cudaFree(h->d_ue_state); cudaFree(h->d_ue_inbox[0]); cudaFree(h->d_ue_inbox[1]); cudaFree(h->d_ue_ltime); cudaFree(h->d_ue_totals);
   for (int par = 0; par < 2; ++par) { cudaFree(h->d_win_data[par]); cudaFree(h->d_peer_data[par]); }
   cudaFree(h->d_ctrl); cudaFree(h->d_send_count); cudaFree(h->d_peer_ctrl);
@@ -587,6 +592,9 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
     CUB(cudaMalloc(&h->d_send_count, 8 * sizeof(u32)));
     CUB(cudaMemset(h->d_send_count, 0, 8 * sizeof(u32)));
     CUB(cudaMalloc(&h->d_peer_ctrl, sizeof(u32*) * 8));
+    CUB(cudaMalloc(&h->d_anomaly, h->stride)); CUB(cudaMemset(h->d_anomaly, 0, h->stride));   // byzantine sender flags: peers' drain kernels raise them
+    CUB(cudaMalloc(&h->d_byz_totals, 4 * 8)); CUB(cudaMemset(h->d_byz_totals, 0, 4 * 8));
+    CUB(cudaMalloc(&h->d_peer_anomaly, sizeof(void*) * 8));
     if (cfg->push_pull_interval_ticks > 0) {      // the snapshots partners on other GPUs read: allocated now so that they can be exported
       CUB(cudaMalloc(&h->d_snap_rec, (size_t)h->R * h->stride * 32));
       CUB(cudaMalloc(&h->d_snap_node, (size_t)h->stride * 8));
@@ -718,7 +726,7 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
   if (!h) return fail(SERFSIM_E_INVAL, "null handle");
   u32 chunk = 4;
   if (const char* e = getenv("SERFSIM_CHUNK")) chunk = std::max(1, atoi(e));
-  if (h->byz_n) chunk = 1;     // injector ticks are never no-ops, so no tick may be launched past the quiescent one
+  if (h->byz_on) chunk = 1;     // injector ticks are never no-ops, so no tick may be launched past the quiescent one
   const u32 pp = (u32)std::max(0, h->cfg.push_pull_interval_ticks);
   const u32 reap = h->cfg.reap_interval_ticks;
   // Ticks launched beyond the first quiescent one must be no-ops (they are rewound).  Anti-entropy rounds and reaper
@@ -726,7 +734,7 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
   auto boundary = [&](u32 t) { return (pp && (t + 1) % pp == 0) || (reap && (t + 1) % reap == 0); };
   const u32 start = h->tick;
   int rc = 0;
-  if (h->cfg.world_size == 1 && !pp && !reap && !h->byz_n && getenv("SERFSIM_SPECULATE")) {   // measured: no gain over the synchronous loop (the 8 extra no-op ticks cost what the gaps saved); off by default
+  if (h->cfg.world_size == 1 && !pp && !reap && !h->byz_on && getenv("SERFSIM_SPECULATE")) {   // measured: no gain over the synchronous loop (the 8 extra no-op ticks cost what the gaps saved); off by default
     // Pipelined convergence check (single GPU, no anti-entropy / reaper ticks): chunk k+1 is launched before the rows
     // of chunk k are inspected, so the GPU never waits for the host.  Ticks past the first quiescent one are no-ops on
     // a quiescent cluster and are rewound, exactly as in the synchronous loop below.
@@ -786,7 +794,7 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
       // with anti-entropy on, convergence additionally needs a push-pull round that changed nothing but Lamport times
       // (a Left member is re-sent as "leave at status_ltime + 1", serf/delegate.rs:495-510: status_time creeps by design)
       const bool pp_ok = !pp || (((t + 1) % pp) == 0 && r.changed == 0);
-      const bool byz_ok = !h->byz_n || r.changed == 0;       // stale entries stay in flight forever: quiescent = no honest traffic and nothing merged
+      const bool byz_ok = !h->byz_on || r.changed == 0;       // stale entries stay in flight forever: quiescent = no honest traffic and nothing merged
       if (r.pending == 0 && r.edge_updates == 0 && !future_ops(h, t) && pp_ok && byz_ok) {
         // ticks after t were no-ops on a quiescent cluster: rewind the logical clock to t + 1
         if (h->tick > t + 1) {
@@ -883,39 +891,56 @@ int serfsim_set_byzantine(serfsim_t* h, uint32_t n, const uint32_t* ids, uint32_
   if (!h) return fail(SERFSIM_E_INVAL, "null handle");
   if (n && !ids) return fail(SERFSIM_E_INVAL, "null ids");
   if (h->tick != 0 || !h->ops.empty()) return fail(SERFSIM_E_INVAL, "serfsim_set_byzantine: call before any operation is scheduled (or after serfsim_reset)");
-  if (n && h->cfg.world_size > 1) return fail(SERFSIM_E_INVAL, "byzantine injectors are single-GPU in this version");
   if (n && h->cfg.push_pull_interval_ticks > 0) return fail(SERFSIM_E_INVAL, "byzantine injectors cannot be combined with push-pull rounds in this version");
+  if (n && h->cfg.world_size > 1 && h->shard_size >= BYZ_FLAG) return fail(SERFSIM_E_INVAL, "byzantine injectors: shards must hold fewer than 2^25 nodes");
   std::vector<u32> v(ids, ids + n);
   std::sort(v.begin(), v.end());
   for (u32 i = 0; i < n; ++i) if (v[i] >= h->N || (i && v[i] == v[i - 1])) return fail(SERFSIM_E_INVAL, "byzantine ids must be distinct node ids");
+  std::vector<u32> mine;                           // every rank is given the global list and keeps the injectors of its shard
+  for (u32 id : v) if (id - h->first < h->count) mine.push_back(id);
   cudaFree(h->d_byz_ids); h->d_byz_ids = nullptr;
-  h->byz_n = 0; h->byz_delta = delta;
+  h->byz_n = 0; h->byz_delta = delta; h->byz_on = n != 0;
   if (n) {
     if (!h->d_anomaly) { CU(cudaMalloc(&h->d_anomaly, h->stride)); CU(cudaMalloc(&h->d_byz_totals, 4 * 8)); }
-    CU(cudaMalloc(&h->d_byz_ids, (size_t)n * 4));
-    CU(cudaMemcpy(h->d_byz_ids, v.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    if (!mine.empty()) {
+      CU(cudaMalloc(&h->d_byz_ids, mine.size() * 4));
+      CU(cudaMemcpy(h->d_byz_ids, mine.data(), mine.size() * 4, cudaMemcpyHostToDevice));
+    }
     CU(cudaMemset(h->d_anomaly, 0, h->stride));
     CU(cudaMemset(h->d_byz_totals, 0, 4 * 8));
-    h->byz_n = n;
+    h->byz_n = (u32)mine.size();
   }
   return 0;
 }
 
 int serfsim_anomaly_flags(serfsim_t* h, uint8_t* out) {
   if (!h || !out) return fail(SERFSIM_E_INVAL, "null argument");
-  if (!h->byz_n) return fail(SERFSIM_E_INVAL, "no byzantine injectors set (serfsim_set_byzantine)");
+  if (!h->byz_on) return fail(SERFSIM_E_INVAL, "no byzantine injectors set (serfsim_set_byzantine)");
   CU(cudaStreamSynchronize(h->stream));
+  if (h->cfg.world_size > 1) {                     // peers' drain kernels raise flags in this array: wait until every rank has drained
+    if (!h->barrier) return fail(SERFSIM_E_COMM, "world_size > 1: serfsim_comm_set_hooks was not called");
+    h->barrier(h->comm_user);
+  }
   CU(cudaMemcpy(out, h->d_anomaly, h->count, cudaMemcpyDeviceToHost));
   return 0;
 }
 
 int serfsim_byzantine_stats(serfsim_t* h, serfsim_byz_stats_t* o) {
   if (!h || !o) return fail(SERFSIM_E_INVAL, "null argument");
-  if (!h->byz_n) return fail(SERFSIM_E_INVAL, "no byzantine injectors set (serfsim_set_byzantine)");
+  if (!h->byz_on) return fail(SERFSIM_E_INVAL, "no byzantine injectors set (serfsim_set_byzantine)");
   u64 t[4] = {0, 0, 0, 0};
   CU(cudaStreamSynchronize(h->stream));
+  if (h->cfg.world_size > 1) {
+    if (!h->barrier || !h->allreduce) return fail(SERFSIM_E_COMM, "world_size > 1: serfsim_comm_set_hooks was not called");
+    h->barrier(h->comm_user);                      // see serfsim_anomaly_flags
+  }
   CU(cudaMemcpy(t, h->d_byz_totals, 4 * 8, cudaMemcpyDeviceToHost));
-  o->messages = t[0]; o->edge_updates = t[1]; o->flagged = t[2];
+  std::vector<u8> flags(h->count);
+  CU(cudaMemcpy(flags.data(), h->d_anomaly, h->count, cudaMemcpyDeviceToHost));
+  u64 v[3] = {t[0], t[1], 0};
+  for (u8 f : flags) v[2] += f ? 1 : 0;
+  if (h->cfg.world_size > 1) h->allreduce(h->comm_user, v, 3);
+  o->messages = v[0]; o->edge_updates = v[1]; o->flagged = v[2];
   return 0;
 }
 
@@ -1032,7 +1057,7 @@ int serfsim_tick_times(serfsim_t* h, uint32_t first_tick, uint32_t n, float* ms_
 }
 
 // ---- multi-GPU: CUDA IPC windows ----------------------------------------------------------
-struct comm_blob { cudaIpcMemHandle_t data[2]; cudaIpcMemHandle_t ctrl; cudaIpcMemHandle_t snap_rec, snap_node; u32 win_cap; u32 rank; u32 has_snap; u32 pad; };
+struct comm_blob { cudaIpcMemHandle_t data[2]; cudaIpcMemHandle_t ctrl; cudaIpcMemHandle_t snap_rec, snap_node, anomaly; u32 win_cap; u32 rank; u32 has_snap; u32 pad; };
 
 size_t serfsim_comm_blob_size(void) { return sizeof(comm_blob); }
 
@@ -1042,6 +1067,7 @@ int serfsim_comm_export(serfsim_t* h, void* blob) {
   comm_blob b{};
   for (int par = 0; par < 2; ++par) CU(cudaIpcGetMemHandle(&b.data[par], h->d_win_data[par]));
   CU(cudaIpcGetMemHandle(&b.ctrl, h->d_ctrl));
+  CU(cudaIpcGetMemHandle(&b.anomaly, h->d_anomaly));
   b.win_cap = h->win_cap; b.rank = (u32)h->cfg.rank;
   if (h->d_snap_rec) {                              // push-pull rounds are on: partners on other GPUs read these
     CU(cudaIpcGetMemHandle(&b.snap_rec, h->d_snap_rec)); CU(cudaIpcGetMemHandle(&b.snap_node, h->d_snap_node));
@@ -1061,11 +1087,17 @@ int serfsim_comm_connect(serfsim_t* h, const void* blobs) {
   std::vector<std::vector<u64*>> pd(2, std::vector<u64*>(8, nullptr));
   std::vector<const uint4*> psr(8, nullptr);
   std::vector<const u64*> psn(8, nullptr);
+  std::vector<u8*> pan(8, nullptr);
   for (int r = 0; r < W; ++r) {
     if (bs[r].rank != (u32)r || bs[r].win_cap != h->win_cap) return fail(SERFSIM_E_COMM, "blob order / window size mismatch");
     if ((bs[r].has_snap != 0) != (h->d_snap_rec != nullptr)) return fail(SERFSIM_E_COMM, "push_pull_interval_ticks differs between ranks");
-    if (r == h->cfg.rank) { pd[0][r] = h->d_win_data[0]; pd[1][r] = h->d_win_data[1]; pc[r] = h->d_ctrl; psr[r] = h->d_snap_rec; psn[r] = h->d_snap_node; continue; }
+    if (r == h->cfg.rank) { pd[0][r] = h->d_win_data[0]; pd[1][r] = h->d_win_data[1]; pc[r] = h->d_ctrl; psr[r] = h->d_snap_rec; psn[r] = h->d_snap_node; pan[r] = h->d_anomaly; continue; }
     void* ptr = nullptr;
+    {
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, bs[r].anomaly, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return fail(SERFSIM_E_COMM, std::string("cudaIpcOpenMemHandle(flags): ") + cudaGetErrorString(e));
+      h->ipc_opened.push_back(ptr); pan[r] = (u8*)ptr;
+    }
     if (bs[r].has_snap) {
       cudaError_t e = cudaIpcOpenMemHandle(&ptr, bs[r].snap_rec, cudaIpcMemLazyEnablePeerAccess);
       if (e != cudaSuccess) return fail(SERFSIM_E_COMM, std::string("cudaIpcOpenMemHandle(snapshot): ") + cudaGetErrorString(e));
@@ -1085,6 +1117,7 @@ int serfsim_comm_connect(serfsim_t* h, const void* blobs) {
   }
   for (int par = 0; par < 2; ++par) CU(cudaMemcpy(h->d_peer_data[par], pd[par].data(), sizeof(u64*) * 8, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(h->d_peer_ctrl, pc.data(), sizeof(u32*) * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_peer_anomaly, pan.data(), sizeof(void*) * 8, cudaMemcpyHostToDevice));
   if (h->d_snap_rec) {
     CU(cudaMemcpy(h->d_peer_snap_rec, psr.data(), sizeof(void*) * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->d_peer_snap_node, psn.data(), sizeof(void*) * 8, cudaMemcpyHostToDevice));

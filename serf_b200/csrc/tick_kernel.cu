@@ -24,6 +24,7 @@
 #include <cstdlib>
 
 #include "tick_kernel.cuh"
+#include "byz.cuh"
 
 namespace sfs {
 
@@ -809,11 +810,27 @@ __global__ void __launch_bounds__(BLOCK) drain_kernel(const __grid_constant__ Dr
     const u64* w = p.win_data + (size_t)src * p.win_cap;
     for (u32 i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
       const u64 e = __ldcg(w + i);
-      const u32 val1 = (u32)(e >> 32), s = (u32)(e >> 28) & 15, kind = (u32)(e >> 26) & 3, dl = (u32)e & ((1u << 26) - 1);
+      const u32 val1 = (u32)(e >> 32), s = (u32)(e >> 28) & 15, kind = (u32)(e >> 26) & 3;
+      u32 dl = (u32)e & ((1u << 26) - 1);
+      const bool byz = p.byz_on && (dl & BYZ_FLAG);
+      if (byz) dl &= ~BYZ_FLAG;
+      if (byz && kind == 3 && s == BYZ_ANNOT_SLOT) continue;           // third entry of a triple: read by the thread holding the first
       if (dl < p.n_local && s < p.R && kind < 3) {
         atomicMax(p.inbox_wr + ((size_t)(kind * p.R + s)) * p.stride + dl, val1);
         if (mark) p.hot_wr[dl >> TILE_SHIFT] = 1;
         seen |= 1u << kind;
+        if (byz && kind < 2 && i + 2 < n) {                            // first entry of a triple: judge it against MY record, flag the sender in ITS shard
+          const u64 e1 = __ldcg(w + i + 1), e2 = __ldcg(w + i + 2);
+          const u32 src = (u32)(e2 >> 32) - 1u;
+          ByzEntries be{};
+          be.serf_lt = val1 - 1u; be.ml_inc = ((u32)(e1 >> 32) - 1u) >> 6;
+          if (p.node_state[dl] & NS_UP) {
+            const size_t iv = (size_t)s * p.stride + dl;
+            Rec q;
+            unpack(p.rec[2 * iv], p.rec[2 * iv + 1], q);
+            if (byz_anomalous(q, be, p.byz_delta)) { const u32 sh = src / p.shard_size; p.peer_anomaly[sh][src - sh * p.shard_size] = 1; }
+          }
+        }
       } else if (dl < p.n_local && kind == 3 && s < p.ue_n && val1) {   // user event s arrived: one bit, and the time its origin stamped
         atomicOr(p.ue_inbox_wr + dl, 1u << s);
         p.ue_ltime[s] = val1 - 1;                      // every copy carries the same value; this shard learns it no later than the event itself

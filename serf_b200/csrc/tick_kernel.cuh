@@ -76,6 +76,10 @@ struct DrainParams {
   u8* hot_wr;
   u32* kinds_cur;             // [4] kind counters of this tick (received kinds are added so the next tick reads their planes)
   u32* overflow;
+  // byzantine triples (see ByzParams): judged here against the receiver's end-of-tick record
+  u32 byz_on, byz_delta, shard_size;
+  const uint4* rec; const u64* node_state;
+  u8* const* peer_anomaly;    // [world] every rank's sender-flag array
   // user-event entries (kind 3: slot = tracked event, value = its Lamport time + 1); null / 0 when user events are off
   u32 ue_n;
   u32* ue_inbox_wr;
@@ -132,8 +136,17 @@ struct ByzParams {
   u8* hot_wr;
   u32* kinds_cur;
   u8* anomaly;                // [n_local] sender flags
-  u64* totals;                // 0 injected entries, 1 injected (peer, subject) pairs, 2 senders flagged
+  u64* totals;                // 0 injected entries, 1 injected (peer, subject) pairs
+  // sharded runs: a peer in another shard gets a TRIPLE of window entries — serf entry and memberlist entry, both with
+  // BYZ_FLAG set in the destination field, then an annotation (kind 3, slot 15) carrying the sender's global id + 1 —
+  // and the receiving shard's drain kernel judges it against ITS record and raises the flag in the sender's shard.
+  u32 n_local, world, rank, shard_size, win_cap;
+  u64* const* win_data;
+  u32* send_count;
+  u32* overflow;
 };
+constexpr u32 BYZ_FLAG = 1u << 25;          // in the 26-bit destination field of a window entry (shards hold < 2^25 nodes when injectors are on)
+constexpr u32 BYZ_ANNOT_SLOT = 15;
 void launch_byz(const ByzParams& p, cudaStream_t st);
 
 enum { EXTRACT_STATUS = 0, EXTRACT_STATUS_LTIME = 1, EXTRACT_CLOCK = 2, EXTRACT_INC = 3, EXTRACT_ML = 4 };

@@ -197,3 +197,56 @@ def test_sharded_push_pull(world, pp):
 @pytest.mark.parametrize("seed", [3, 5, 11])
 def test_sharded_fuzz_with_push_pull_and_reaper(seed):
     check(scenarios.fuzz(seed, n=500, slots=3), 2)
+
+
+# ---- byzantine injectors across shards: triples in the peer's window, verdict by the receiving shard's drain kernel ----
+def check_byzantine(sc, world, **cfg):
+    o = sc.build(oracle_sim, trace=1, **cfg)
+    to, oko = o.run_until_converged(sc.max_ticks)
+    n = o.stats()["tick"]
+    tro = o.tick_trace(0, n)
+    for trace in (1, 0):
+        comm = ThreadComm(world)
+        res, errs = [None] * world, []
+
+        def worker(rank):
+            try:
+                g = sc.build(emu_sim, rank=rank, world_size=world, trace=trace, **cfg)
+                g.connect(*comm.hooks(rank))
+                ticks, ok = g.run_until_converged(sc.max_ticks)
+                res[rank] = dict(ticks=ticks, ok=ok, trace=g.tick_trace(), hash=g.state_hash(), flags=g.anomaly_flags(), stats=g.byzantine_stats(),
+                                 rec=[g.records(s) for s in range(sc.slots)], clock=g.lamport_time())
+                comm.bar.wait()
+            except BaseException as e:                              # noqa: BLE001
+                errs.append(e)
+                comm.bar.abort()
+        th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join(600)
+        if errs:
+            raise errs[0]
+        for r in res:
+            assert (r["ticks"], r["ok"]) == (to, oko)
+            for f in tro.dtype.names:
+                if f == "hash" and not trace:
+                    continue
+                bad = np.nonzero(r["trace"][f] != tro[f])[0]
+                assert bad.size == 0, f"world {world} trace={trace}: field {f} first differs at tick {bad[0]}"
+            assert r["hash"] == o.state_hash()
+            assert r["stats"] == o.byzantine_stats(), (r["stats"], o.byzantine_stats())
+        flags = np.concatenate([r["flags"] for r in res])
+        bad = np.nonzero(flags != o.anomaly_flags())[0]
+        assert bad.size == 0, f"world {world} trace={trace}: anomaly flag of node {bad[0]}"
+        for s in range(sc.slots):
+            assert (np.concatenate([r["rec"][s] for r in res]) == o.records(s)).all()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_byzantine(world):
+    check_byzantine(scenarios.byzantine_injectors(2400, 16, 4, 0.02, seed=1), world)
+
+
+def test_sharded_byzantine_heavy_three_ranks():
+    check_byzantine(scenarios.byzantine_injectors(1501, 12, 3, 0.2, seed=3), 3)
