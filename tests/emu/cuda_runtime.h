@@ -8,7 +8,7 @@
 // fails with SERFSIM_E_NO_DEVICE without a GPU.
 //
 // Execution model (per rank; multi-rank runs give every rank its own OS thread and the engine state is thread-local,
-// peer windows are plain shared host memory with real acquire/release on the flags): one CTA at a time; every CUDA thread of the CTA is a fiber (ucontext) on one OS thread; fibers
+// peer windows are plain shared host memory with real acquire/release on the flags): one CTA at a time; every CUDA thread of the CTA is a fiber on one OS thread; fibers
 // switch only at collectives (__syncthreads, warp shuffles / votes), where they wait for the other lanes exactly like
 // the hardware does.  __shared__ becomes `static` (CTAs run one after another).  Atomics are plain read-modify-writes.
 #pragma once
