@@ -79,6 +79,23 @@ def test_fuzz(seed):
     run_both(scenarios.fuzz(seed))
 
 
+def test_compaction_path_is_taken_and_exact():
+    """Unsaturated ticks of a trace-off run gather the active nodes of several tiles (SFS_PROBE 0..2 count the groups,
+    the multi-tile groups and the groups needing more than one dense pass)."""
+    import ctypes as C
+    from emu_lib import lib
+    L = lib()
+    L.emu_probe.restype = C.c_ulong
+    L.emu_probe_reset()
+    sc = scenarios.random_graph_leave(6000, 16, 3, seed=1)
+    o = sc.build(oracle_sim, trace=1)
+    to = o.run_until_converged(sc.max_ticks)
+    f = sc.build(emu_sim, trace=0)
+    assert f.run_until_converged(sc.max_ticks) == to
+    assert L.emu_probe(0) > 0 and L.emu_probe(1) > 0 and L.emu_probe(2) > 0
+    assert_same(f, o, sc.slots, with_hash=False)
+
+
 def test_config1_shape_100k_nodes():
     """BASELINE configs[1] at full size (100 K-node random graph, fan-out 3) through the host-compiled kernels:
     391 tiles over 4 CTAs, dense and sparse ticks, production mode (trace off)."""
