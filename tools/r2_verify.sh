@@ -29,4 +29,9 @@ if [ $rc -eq 0 ]; then
   SERFSIM_LIB=$PWD/serf_b200/ab/libserfsim_queue-word.so timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_golden.py -m gpu -q -x > gpurun_out/r2_tests_queueword.log 2>&1
   tail -3 gpurun_out/r2_tests_queueword.log
 fi
+# the new features at BASELINE scale (only if their parity passed)
+if [ $rc -eq 0 ]; then
+  timeout 600 python tools/feature_profile.py --what events --out gpurun_out/r2_events.json > gpurun_out/r2_events.log 2>&1; tail -1 gpurun_out/r2_events.log
+  timeout 600 python tools/feature_profile.py --what byzantine --out gpurun_out/r2_byzantine.json > gpurun_out/r2_byzantine.log 2>&1; tail -1 gpurun_out/r2_byzantine.log
+fi
 exit $rc
