@@ -117,3 +117,25 @@ def test_config2_shape_small_world_churn_100k():
     f = sc.build(emu_sim, trace=0, **cfg)
     assert f.run_until_converged(sc.max_ticks) == to
     assert_same(f, o, sc.slots, with_hash=False)
+
+
+def _feature_checks(g, o, sc):
+    if sc.user_events is not None:
+        assert g.user_event_stats() == o.user_event_stats()
+        assert (g.user_event_records() == o.user_event_records()).all()
+    if sc.byzantine is not None:
+        assert g.byzantine_stats() == o.byzantine_stats()
+        assert (g.anomaly_flags() == o.anomaly_flags()).all()
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_fuzz_with_user_events_and_injectors(seed):
+    """Every operation kind, reaper, probing, tracked user events (with aliases) and byzantine injectors at once."""
+    sc = scenarios.fuzz_features(seed)
+    o = sc.build(oracle_sim, trace=1)
+    to = o.run_until_converged(sc.max_ticks)
+    for trace in (1, 0):
+        g = sc.build(emu_sim, trace=trace)
+        assert g.run_until_converged(sc.max_ticks) == to
+        assert_same(g, o, sc.slots, with_hash=bool(trace))
+        _feature_checks(g, o, sc)
