@@ -212,7 +212,8 @@ int serfsim_set_event_cb (serfsim_t* h, serfsim_event_cb cb, void* user);
  * are equal for the receiver's de-duplication.  Event e is fired with
  * serfsim_inject(tick, SERFSIM_OP_USER_EVENT, origin, e), once; its Lamport time is the origin's event
  * clock at that tick.  Call before scheduling operations; n_events = 0 switches user events off.
- * Works sharded (an event crossing shards is one 8-byte window entry carrying its Lamport time; counters of
+ * Works sharded (an event crossing shards is one 8-byte window entry carrying its Lamport time; call this BEFORE
+ * serfsim_comm_export, it resizes the receive windows; counters of
  * serfsim_user_event_stats are global sums, event_time is the local shard's maximum); not together with
  * push-pull rounds in this version. */
 int serfsim_set_user_events(serfsim_t* h, uint32_t n_events, const uint32_t* content_ids /*[n_events]*/);

@@ -149,6 +149,7 @@ struct serfsim {
   u32** d_peer_ctrl = nullptr;                 // device array of peer control-block pointers
   u32 xepoch = 0;                              // executed-tick counter of the exchange (never rewinds): stamps and parity
   u32 win_cap = 0;
+  u32 win_cap_base = 0;                        // capacity sized for the membership entries alone (serfsim_create)
   bool connected = false;
   serfsim_barrier_fn barrier = nullptr; serfsim_allreduce_u64_fn allreduce = nullptr; void* comm_user = nullptr;
   std::vector<void*> ipc_opened;
@@ -586,6 +587,7 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
     if (const char* e = getenv("SERFSIM_WIN_FACTOR")) factor = atof(e);
     double cap = (double)h->shard_size * cfg->fanout * h->R * 3.0 * factor / cfg->world_size + 4096.0;
     h->win_cap = (u32)std::min(cap, 4.0e9);
+    h->win_cap_base = h->win_cap;
     for (int par = 0; par < 2; ++par) {
       CUB(cudaMalloc(&h->d_win_data[par], (size_t)cfg->world_size * h->win_cap * 8));
       CUB(cudaMalloc(&h->d_peer_data[par], sizeof(u64*) * 8));
@@ -954,6 +956,22 @@ int serfsim_set_user_events(serfsim_t* h, uint32_t n_events, const uint32_t* con
   if (n_events && !content_ids) return fail(SERFSIM_E_INVAL, "null content ids");
   if (h->tick != 0 || !h->ops.empty()) return fail(SERFSIM_E_INVAL, "serfsim_set_user_events: call before any operation is scheduled (or after serfsim_reset)");
   if (n_events && h->cfg.push_pull_interval_ticks > 0) return fail(SERFSIM_E_INVAL, "user events cannot be combined with push-pull rounds in this version");
+  if (h->cfg.world_size > 1) {
+    // every event bit bound for another shard is one window entry: up to fanout · n_events per node and tick on top of the
+    // membership entries the windows were sized for.  The windows are exported by serfsim_comm_export, so this must come first.
+    double factor = 1.25;
+    if (const char* e = getenv("SERFSIM_WIN_FACTOR")) factor = atof(e);
+    const double cap = (double)h->win_cap_base + (double)h->shard_size * h->cfg.fanout * n_events * factor / h->cfg.world_size;
+    const u32 want = (u32)std::min(cap, 4.0e9);
+    if (want != h->win_cap) {
+      if (h->connected) return fail(SERFSIM_E_INVAL, "serfsim_set_user_events: in sharded runs call it before serfsim_comm_export / serfsim_comm_connect (it resizes the receive windows)");
+      for (int par = 0; par < 2; ++par) {
+        cudaFree(h->d_win_data[par]); h->d_win_data[par] = nullptr;
+        CU(cudaMalloc(&h->d_win_data[par], (size_t)h->cfg.world_size * want * 8));
+      }
+      h->win_cap = want;
+    }
+  }
   if (n_events && !h->d_ue_state) {
     CU(cudaMalloc(&h->d_ue_state, (size_t)h->stride * 16));
     CU(cudaMalloc(&h->d_ue_inbox[0], (size_t)h->stride * 4));

@@ -321,3 +321,9 @@ def test_sharded_fuzz_with_user_events_and_injectors(seed):
         if sc.byzantine is not None:
             assert (np.concatenate([r["flags"] for r in res]) == o.anomaly_flags()).all()
             assert all(r["byz_stats"] == o.byzantine_stats() for r in res)
+
+
+def test_sharded_user_events_need_bigger_windows():
+    """5 events × fan-out 3 from every node: more cross-shard entries per tick than the windows serfsim_create sizes for
+    membership traffic alone — serfsim_set_user_events must have resized them (it used to overflow at this size)."""
+    check_events(scenarios.user_event_storm(20_000, 16, 3, seed=3, n_events=5, spacing=2, churn=50, with_leave=True), 2)

@@ -26,8 +26,16 @@ def _worker(rank, world, port, scen_args, outdir):
     sdist.connect(g, dist, torch.device("cuda", rank))
     ticks, ok = g.run_until_converged(sc.max_ticks)
     tr = g.tick_trace()
+    extra = {}
+    if sc.user_events is not None:                 # collective getters: every rank makes the same calls in the same order
+        st = g.user_event_stats()
+        extra.update(ue=g.user_event_records(), ue_stats=np.array([st[k] for k in sorted(st)], dtype=np.uint64),
+                     ue_ltime=np.array([g.user_event_ltime(e) for e in range(len(sc.user_events))], dtype=np.uint64))
+    if sc.byzantine is not None:
+        bz = g.byzantine_stats()
+        extra.update(flags=g.anomaly_flags(), byz_stats=np.array([bz[k] for k in sorted(bz)], dtype=np.uint64))
     np.savez(os.path.join(outdir, f"r{rank}.npz"), ticks=ticks, ok=ok, trace=tr, first=g.first, count=g.count, hash=np.uint64(g.state_hash()),
-             clock=g.lamport_time(), **{f"rec{s}": g.records(s) for s in range(sc.slots)})
+             clock=g.lamport_time(), **{f"rec{s}": g.records(s) for s in range(sc.slots)}, **extra)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -54,6 +62,11 @@ WORLDS = [int(x) for x in os.environ.get("SERFSIM_TEST_WORLDS", "2,4").split(","
     ("random_graph_leave", dict(n=30_001, degree=12, fanout=4, seed=3, slots=3), {}),
     ("random_graph_fail", dict(n=20_000, degree=16, fanout=3, seed=2), dict(suspicion_mult=2, suspicion_max_timeout_mult=2, probe_interval_ticks=2)),
     ("fuzz", dict(seed=7, n=3000, slots=4), dict(push_pull_interval_ticks=0)),
+    # cross-shard traffic added after the last multi-GPU run (checked with the host-compiled kernels, tests/test_emu_multi.py)
+    ("user_event_storm", dict(n=40_000, degree=16, fanout=3, seed=3, n_events=5, spacing=2, churn=100, with_leave=True), {}),
+    ("byzantine_injectors", dict(n=40_000, degree=16, fanout=4, frac=0.02, seed=1), {}),
+    ("fuzz", dict(seed=11, n=3000, slots=3), {}),                                   # push-pull rounds across shards (fuzz 11 has them on)
+    ("fuzz_features", dict(seed=6, n=3000, slots=3), {}),
 ])
 def test_sharded_equals_oracle(world, scen, tmp_path):
     if torch.cuda.device_count() < world:
@@ -76,3 +89,17 @@ def test_sharded_equals_oracle(world, scen, tmp_path):
     assert (np.concatenate([r["clock"] for r in res]) == o.lamport_time()).all()
     for s in range(sc.slots):
         assert (np.concatenate([r[f"rec{s}"] for r in res]) == o.records(s)).all()
+    if sc.user_events is not None:
+        assert (np.concatenate([r["ue"] for r in res]) == o.user_event_records()).all()
+        so = o.user_event_stats()
+        keys = sorted(so)
+        for r in res:
+            got = dict(zip(keys, (int(x) for x in r["ue_stats"])))
+            assert {k: v for k, v in got.items() if k != "event_time"} == {k: v for k, v in so.items() if k != "event_time"}
+            assert [int(x) for x in r["ue_ltime"]] == [o.user_event_ltime(e) for e in range(len(sc.user_events))]
+        assert max(int(dict(zip(keys, r["ue_stats"]))["event_time"]) for r in res) == so["event_time"]
+    if sc.byzantine is not None:
+        assert (np.concatenate([r["flags"] for r in res]) == o.anomaly_flags()).all()
+        bo = o.byzantine_stats()
+        for r in res:
+            assert dict(zip(sorted(bo), (int(x) for x in r["byz_stats"]))) == bo
