@@ -67,3 +67,13 @@ def test_cpp_host_layer_compiles_links_and_fails_loudly_without_gpu(tmp_path):
         assert r.returncode == 0, r.stdout + r.stderr
     else:
         assert r.returncode == 10 and "no CPU execution path" in r.stdout, r.stdout + r.stderr
+
+
+def test_product_loader_refuses_the_host_compiled_test_build():
+    """SERFSIM_LIB may point at another nvcc build of the library (A/B runs) but never at tests/emu's host build."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import emu_lib
+    env = dict(os.environ, SERFSIM_LIB=emu_lib.build())
+    r = subprocess.run([sys.executable, "-c", "from serf_b200 import sim; sim.load_library()"], cwd=ROOT, env=env, capture_output=True, text=True)
+    assert r.returncode != 0 and "refusing to use it as the product" in r.stderr
