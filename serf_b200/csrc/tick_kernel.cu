@@ -39,10 +39,11 @@ static_assert((1u << TILE_SHIFT) == BLOCK, "tile = block");
 // 4 B at a random node).  They are kept L2-resident with an evict_last policy; everything that is
 // streamed exactly once per tick (records, node state, the inbox parity being consumed) goes
 // through evict_first / no-L1-allocate so it does not push the inbox out of the 126 MB L2.
+struct Words { u32 w[8]; };   // one 32-byte record
+
+#ifndef SERFSIM_EMU
 __device__ __forceinline__ u64 policy_evict_first() { u64 p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
 __device__ __forceinline__ u64 policy_evict_last() { u64 p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
-
-struct Words { u32 w[8]; };   // one 32-byte record
 
 __device__ __forceinline__ Words ld_rec256(const uint4* ptr, u64 pol) {   // one 256-bit load = one DRAM sector
   Words r;
@@ -70,8 +71,23 @@ __device__ __forceinline__ void st_u64_stream(u64* ptr, u64 v, u64 pol) {
 __device__ __forceinline__ void red_max_resident(u32* ptr, u32 v, u64 pol) {   // RED.MAX, result unused, line kept in L2
   asm volatile("red.relaxed.gpu.global.max.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(ptr), "r"(v), "l"(pol) : "memory");
 }
+__device__ __forceinline__ void st_release_sys(u32* ptr, u32 v) { asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(ptr), "r"(v) : "memory"); }
+__device__ __forceinline__ u32 ld_acquire_sys(const u32* ptr) { u32 f; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(ptr) : "memory"); return f; }
+#else   // SERFSIM_EMU: the same accessors as plain C++ (tests/emu compiles this file for the host; cache hints have no meaning there)
+inline u64 policy_evict_first() { return 0; }
+inline u64 policy_evict_last() { return 0; }
+inline Words ld_rec256(const uint4* ptr, u64) { Words r; const u32* q = reinterpret_cast<const u32*>(ptr); for (int i = 0; i < 8; ++i) r.w[i] = q[i]; return r; }
+inline void st_rec256(uint4* ptr, const Words& r, u64) { u32* q = reinterpret_cast<u32*>(ptr); for (int i = 0; i < 8; ++i) q[i] = r.w[i]; }
+inline u64 ld_u64_stream(const u64* ptr, u64) { return *ptr; }
+inline u32 ld_u32_stream(const u32* ptr, u64) { return *ptr; }
+inline void st_u32_stream(u32* ptr, u32 v, u64) { *ptr = v; }
+inline void st_u64_stream(u64* ptr, u64 v, u64) { *ptr = v; }
+inline void red_max_resident(u32* ptr, u32 v, u64) { if (v > *ptr) *ptr = v; }
+inline void st_release_sys(u32* ptr, u32 v) { *ptr = v; }
+inline u32 ld_acquire_sys(const u32* ptr) { return *ptr; }
+#endif
 
-
+#ifndef SERFSIM_EMU
 // ---- TMA (bulk async copy) + mbarrier plumbing: stages a whole 256-node tile into shared memory ----
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(u64* bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
@@ -91,6 +107,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, 
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
+#endif
 
 // Shared-memory image of one tile (single-slot runs): everything the 256 nodes of the tile read this tick.
 constexpr u32 ST_REC = 0, ST_NODE = 8192, ST_INL = 10240, ST_INJ = 11264, ST_INM = 12288, ST_RP = 13312, ST_COL = 14400;
@@ -565,6 +582,7 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
   if (TRACE && lane == 0 && hs) atomicAdd((unsigned long long*)(p.row + 7), (unsigned long long)hs);
 }
 
+#ifndef SERFSIM_EMU   // the TMA pipeline is device-only (bulk copies, mbarriers); the host build of tests/emu uses the direct-load kernel
 // The same tick for single-slot runs with the whole working set of a tile staged through TMA: one elected
 // thread bulk-copies the tile's records (8 KB), node words (2 KB), live inbox planes (1 KB each), row offsets
 // (1 KB) and CSR span (the tile's neighbour lists, 16 KB at out-degree 16) into shared memory, one tile ahead
@@ -685,6 +703,7 @@ __global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constan
   }
   if (TRACE && lane == 0 && hs) atomicAdd((unsigned long long*)(p.row + 7), (unsigned long long)hs);
 }
+#endif
 
 // Anti-entropy round — memberlist push-pull + SerfDelegate::merge_remote_state (serf/delegate.rs:386-554; "next"
 // row 1 of SURVEY §8f).  Runs after the tick kernel every push_pull_interval ticks on a SNAPSHOT of the end-of-tick
@@ -776,7 +795,7 @@ __global__ void publish_kernel(const __grid_constant__ PublishParams p) {
     u32* ctrl = p.peer_ctrl[r] + p.xpar * 16;
     ctrl[p.rank] = p.send_count[r];
     __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(ctrl + 8 + p.rank), "r"(p.stamp) : "memory");
+    st_release_sys(ctrl + 8 + p.rank, p.stamp);
     p.send_count[r] = 0;
   }
 }
@@ -787,7 +806,7 @@ __global__ void publish_kernel(const __grid_constant__ PublishParams p) {
 __global__ void __launch_bounds__(BLOCK) drain_kernel(const __grid_constant__ DrainParams p) {
   if (threadIdx.x < p.world && threadIdx.x != p.rank) {
     u32 f;
-    do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(p.ctrl + 8 + threadIdx.x) : "memory"); } while (f != p.stamp);
+    do { f = ld_acquire_sys(p.ctrl + 8 + threadIdx.x); } while (f != p.stamp);
   }
   __syncthreads();
   // same dense / sparse decision as the tick kernel of this tick: in a dense tick the next tick processes every
@@ -958,6 +977,7 @@ int tick_grid_size(u32 n_local, int ctas_per_sm) {
   return (int)grid;
 }
 
+#ifndef SERFSIM_EMU
 template <bool TRACE, int FMAX, bool SHARDED>
 static void launch_tick_tma(const TickParams& p, int grid, cudaStream_t st) {
   const size_t smem = 2 * (size_t)(ST_COL + p.stage_col_bytes);
@@ -969,22 +989,25 @@ static void launch_tick_tma(const TickParams& p, int grid, cudaStream_t st) {
     if (const char* e = getenv("SERFSIM_TMA_SYNC")) barsync = atoi(e);
     configured = true;
   }
-  if (barsync) tick_kernel_tma<TRACE, FMAX, SHARDED, true><<<grid, BLOCK, smem, st>>>(p);
-  else tick_kernel_tma<TRACE, FMAX, SHARDED, false><<<grid, BLOCK, smem, st>>>(p);
+  if (barsync) SFS_LAUNCH(grid, BLOCK, smem, st, tick_kernel_tma<TRACE, FMAX, SHARDED, true>)(p);
+  else SFS_LAUNCH(grid, BLOCK, smem, st, tick_kernel_tma<TRACE, FMAX, SHARDED, false>)(p);
 }
+#endif
 
 template <bool TRACE, int FMAX>
 static void launch_tick_v(const TickParams& p, int grid, cudaStream_t st) {
   const bool sharded = p.world > 1, r1 = p.R == 1;
+#ifndef SERFSIM_EMU
   if (r1 && p.stage_col_bytes && !sharded) { // single-slot, single-GPU run whose tiles fit a shared-memory stage: TMA pipeline
     launch_tick_tma<TRACE, FMAX, false>(p, grid, st);
     return;
   }
+#endif
   static int mb5 = -1;
   if (mb5 < 0) { const char* e = getenv("SERFSIM_MINB"); mb5 = (e && atoi(e) == 5) ? 1 : 0; }
-  if (sharded) { if (r1) tick_kernel<TRACE, FMAX, true, true, 4><<<grid, BLOCK, 0, st>>>(p); else tick_kernel<TRACE, FMAX, true, false, 3><<<grid, BLOCK, 0, st>>>(p); }
-  else if (r1) { if (mb5) tick_kernel<TRACE, FMAX, false, true, 5><<<grid, BLOCK, 0, st>>>(p); else tick_kernel<TRACE, FMAX, false, true, 4><<<grid, BLOCK, 0, st>>>(p); }
-  else tick_kernel<TRACE, FMAX, false, false, 3><<<grid, BLOCK, 0, st>>>(p);
+  if (sharded) { if (r1) SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, true, true, 4>)(p); else SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, true, false, 3>)(p); }
+  else if (r1) { if (mb5) SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, false, true, 5>)(p); else SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, false, true, 4>)(p); }
+  else SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, false, false, 3>)(p);
 }
 void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st) {
   const bool small = p.fanout <= 4;          // the common fan-outs (3, 4) get the 4-wide target array
@@ -992,36 +1015,36 @@ void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st) {
   else { if (small) launch_tick_v<false, 4>(p, grid, st); else launch_tick_v<false, 8>(p, grid, st); }
 }
 void launch_pushpull(const TickParams& p, const uint4* snap_rec, const u64* snap_node, bool trace, cudaStream_t st) {
-  if (trace) pushpull_kernel<true><<<148 * 8, BLOCK, 0, st>>>(p, snap_rec, snap_node);
-  else pushpull_kernel<false><<<148 * 8, BLOCK, 0, st>>>(p, snap_rec, snap_node);
+  if (trace) SFS_LAUNCH(SFS_SMS * 8, BLOCK, 0, st, pushpull_kernel<true>)(p, snap_rec, snap_node);
+  else SFS_LAUNCH(SFS_SMS * 8, BLOCK, 0, st, pushpull_kernel<false>)(p, snap_rec, snap_node);
 }
 void launch_compute_watch(const u32* row_ptr, const u32* col, const u32* subj_dev, u32 R, u32 first, u32 n_local, u16* watch, cudaStream_t st) {
-  compute_watch_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(row_ptr, col, subj_dev, R, first, n_local, watch);
+  SFS_LAUNCH((n_local + 255) / 256, 256, 0, st, compute_watch_kernel)(row_ptr, col, subj_dev, R, first, n_local, watch);
 }
 void launch_apply_watch(const u16* watch, u32 n_local, u8* busy, u8* hot0, u8* hot1, cudaStream_t st) {
-  apply_watch_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(watch, n_local, busy, hot0, hot1);
+  SFS_LAUNCH((n_local + 255) / 256, 256, 0, st, apply_watch_kernel)(watch, n_local, busy, hot0, hot1);
 }
-void launch_drain(const DrainParams& p, cudaStream_t st) { drain_kernel<<<148 * 8, BLOCK, 0, st>>>(p); }
-void launch_publish(const PublishParams& p, cudaStream_t st) { publish_kernel<<<1, 32, 0, st>>>(p); }
+void launch_drain(const DrainParams& p, cudaStream_t st) { SFS_LAUNCH(SFS_SMS * 8, BLOCK, 0, st, drain_kernel)(p); }
+void launch_publish(const PublishParams& p, cudaStream_t st) { SFS_LAUNCH(1, 32, 0, st, publish_kernel)(p); }
 void launch_init_state(uint4* rec, u64* node_state, u32 n_local, u32 stride, u32 R, u32 init_st, u32 init_clock, cudaStream_t st) {
-  init_state_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(rec, node_state, n_local, stride, R, init_st, init_clock);
+  SFS_LAUNCH((n_local + 255) / 256, 256, 0, st, init_state_kernel)(rec, node_state, n_local, stride, R, init_st, init_clock);
 }
 void launch_mark_events(u8* busy, u8* hot_rd, const u32* ev_node, u32 ev_begin, u32 ev_end, u32 first, u32 n_local, cudaStream_t st) {
   const u32 n = ev_end - ev_begin;
   if (!n) return;
-  mark_events_kernel<<<(n + 127) / 128, 128, 0, st>>>(busy, hot_rd, ev_node, ev_begin, ev_end, first, n_local);
+  SFS_LAUNCH((n + 127) / 128, 128, 0, st, mark_events_kernel)(busy, hot_rd, ev_node, ev_begin, ev_end, first, n_local);
 }
 void launch_extract(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 slot, int what, void* out, cudaStream_t st) {
-  extract_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(rec, node_state, n_local, stride, slot, what, out);
+  SFS_LAUNCH((n_local + 255) / 256, 256, 0, st, extract_kernel)(rec, node_state, n_local, stride, slot, what, out);
 }
 void launch_compose_records(const uint4* rec, const u32* qword, u32 n_local, u32 stride, u32 slot, uint4* out, cudaStream_t st) {
-  compose_records_kernel<<<(n_local + 255) / 256, 256, 0, st>>>(rec, qword, n_local, stride, slot, out);
+  SFS_LAUNCH((n_local + 255) / 256, 256, 0, st, compose_records_kernel)(rec, qword, n_local, stride, slot, out);
 }
 void launch_state_hash(const uint4* rec, const u32* qword, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 n_global, u32 R, u64* out, cudaStream_t st) {
-  state_hash_kernel<<<148 * 4, BLOCK, 0, st>>>(rec, qword, node_state, n_local, stride, first, n_global, R, out);
+  SFS_LAUNCH(SFS_SMS * 4, BLOCK, 0, st, state_hash_kernel)(rec, qword, node_state, n_local, stride, first, n_global, R, out);
 }
 void launch_summary(const uint4* rec, const u32* qword, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 R, const u32* subj_dev, u64* out, cudaStream_t st) {
-  summary_kernel<<<148 * 4, BLOCK, 0, st>>>(rec, qword, node_state, n_local, stride, first, R, subj_dev, out);
+  SFS_LAUNCH(SFS_SMS * 4, BLOCK, 0, st, summary_kernel)(rec, qword, node_state, n_local, stride, first, R, subj_dev, out);
 }
 
 }  // namespace sfs

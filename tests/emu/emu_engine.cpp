@@ -1,0 +1,143 @@
+// tests/emu/emu_engine.cpp — fiber scheduler of the CUDA-on-CPU shim (see cuda_runtime.h).  Test infrastructure only.
+#include <ucontext.h>
+#include <sys/mman.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#define SERFSIM_EMU 1
+#include "cuda_runtime.h"
+
+namespace emu {
+
+LaneCtx* cur = nullptr;
+
+namespace {
+constexpr int MAX_THREADS = 1024;
+constexpr size_t STACK = 256 * 1024;
+struct Lane {
+  ucontext_t ctx;
+  LaneCtx lc;
+  bool done = false;
+  int wait = 0;              // 0 runnable, 1 warp rendezvous, 2 CTA barrier
+  unsigned wait_gen = 0;
+  char* stack = nullptr;
+};
+struct Warp {
+  int live = 0, arrived = 0;
+  unsigned gen = 0;
+  unsigned long long buf[2][32];
+  unsigned votes[2];
+};
+Lane lanes[MAX_THREADS];
+Warp warps[MAX_THREADS / 32];
+int cta_live = 0, cta_arrived = 0;
+unsigned cta_gen = 0;
+ucontext_t sched_ctx;
+Lane* cur_lane = nullptr;
+const std::function<void()>* body = nullptr;
+
+void release_check(Warp& w) { if (w.live > 0 && w.arrived >= w.live) { w.arrived = 0; w.gen++; } }
+void cta_release_check() { if (cta_live > 0 && cta_arrived >= cta_live) { cta_arrived = 0; cta_gen++; } }
+
+void lane_entry() {
+  (*body)();
+  Lane* l = cur_lane;
+  l->done = true;
+  Warp& w = warps[l->lc.tid.x / 32];
+  w.live--; cta_live--;                       // an exited thread no longer takes part in collectives
+  release_check(w); cta_release_check();
+  swapcontext(&l->ctx, &sched_ctx);
+}
+
+void warp_rendezvous(Warp& w) {
+  Lane* l = cur_lane;
+  const unsigned g = w.gen;
+  if (++w.arrived >= w.live) { w.arrived = 0; w.gen++; return; }
+  l->wait = 1; l->wait_gen = g;
+  swapcontext(&l->ctx, &sched_ctx);           // resumed by the scheduler once w.gen has moved on
+}
+}  // namespace
+
+unsigned lane_id() { return cur_lane->lc.tid.x & 31u; }
+
+void cta_barrier() {
+  Lane* l = cur_lane;
+  const unsigned g = cta_gen;
+  if (++cta_arrived >= cta_live) { cta_arrived = 0; cta_gen++; return; }
+  l->wait = 2; l->wait_gen = g;
+  swapcontext(&l->ctx, &sched_ctx);
+}
+
+// Double-buffered by rendezvous generation: a lane can be at most one collective ahead of the slowest lane of its warp.
+unsigned long long warp_exchange(unsigned long long v, int x, int abs_lane) {
+  Warp& w = warps[cur_lane->lc.tid.x / 32];
+  const unsigned lane = lane_id(), par = w.gen & 1u;
+  w.buf[par][lane] = v;
+  warp_rendezvous(w);
+  return w.buf[par][abs_lane >= 0 ? (unsigned)abs_lane : (lane ^ (unsigned)x) & 31u];
+}
+
+unsigned warp_ballot(bool pred) {
+  Warp& w = warps[cur_lane->lc.tid.x / 32];
+  const unsigned lane = lane_id(), par = w.gen & 1u;
+  if (w.arrived == 0) w.votes[par] = 0;       // first lane of this collective
+  if (pred) w.votes[par] |= 1u << lane;
+  warp_rendezvous(w);
+  return w.votes[par];
+}
+
+unsigned warp_reduce_or(unsigned v) {
+  Warp& w = warps[cur_lane->lc.tid.x / 32];
+  const unsigned par = w.gen & 1u;
+  if (w.arrived == 0) w.votes[par] = 0;
+  w.votes[par] |= v;
+  warp_rendezvous(w);
+  return w.votes[par];
+}
+
+void run_grid(unsigned grid, unsigned block, const std::function<void()>& fn) {
+  if (block == 0 || block > (unsigned)MAX_THREADS) { fprintf(stderr, "emu: bad block size %u\n", block); abort(); }
+  if (cur_lane) { fprintf(stderr, "emu: nested kernel launch\n"); abort(); }
+  body = &fn;
+  for (unsigned t = 0; t < block; ++t)
+    if (!lanes[t].stack) {
+      void* s = mmap(nullptr, STACK, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+      if (s == MAP_FAILED) { perror("emu: mmap"); abort(); }
+      lanes[t].stack = (char*)s;
+    }
+  for (unsigned b = 0; b < grid; ++b) {
+    const unsigned nw = (block + 31) / 32;
+    for (unsigned w = 0; w < nw; ++w) { warps[w].live = 0; warps[w].arrived = 0; warps[w].gen = 0; }
+    cta_live = (int)block; cta_arrived = 0; cta_gen = 0;
+    for (unsigned t = 0; t < block; ++t) {
+      Lane& l = lanes[t];
+      l.done = false; l.wait = 0;
+      l.lc.tid = uint3{t, 0, 0}; l.lc.bid = uint3{b, 0, 0}; l.lc.bdim = uint3{block, 1, 1}; l.lc.gdim = uint3{grid, 1, 1};
+      warps[t / 32].live++;
+      getcontext(&l.ctx);
+      l.ctx.uc_stack.ss_sp = l.stack; l.ctx.uc_stack.ss_size = STACK; l.ctx.uc_link = nullptr;
+      makecontext(&l.ctx, lane_entry, 0);
+    }
+    unsigned remaining = block;
+    while (remaining) {
+      bool progressed = false;
+      for (unsigned t = 0; t < block; ++t) {
+        Lane& l = lanes[t];
+        if (l.done) continue;
+        if (l.wait == 1 && warps[t / 32].gen == l.wait_gen) continue;
+        if (l.wait == 2 && cta_gen == l.wait_gen) continue;
+        l.wait = 0;
+        cur_lane = &l; cur = &l.lc;
+        swapcontext(&sched_ctx, &l.ctx);
+        progressed = true;
+        if (l.done) --remaining;
+      }
+      if (!progressed) { fprintf(stderr, "emu: deadlock — a collective is waiting for threads that never arrive (block %u)\n", b); abort(); }
+    }
+  }
+  cur_lane = nullptr; cur = nullptr; body = nullptr;
+}
+
+}  // namespace emu

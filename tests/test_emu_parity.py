@@ -1,0 +1,79 @@
+"""Kernel logic on the CPU: the product's kernel sources, compiled for the host by tests/emu (every CUDA thread a fiber,
+collectives honoured), against the oracle — the same comparisons as tests/test_gpu_parity.py at sizes a fiber
+scheduler finishes in seconds.  This does not replace the GPU parity run (it cannot see memory-ordering, cache or
+PTX-level behaviour); it catches indexing / control-flow / host-logic mistakes before GPU time is spent.
+"""
+import numpy as np
+import pytest
+
+from emu_lib import emu_sim
+from oracle_lib import oracle_sim
+from serf_b200 import MemberStatus, scenarios
+
+
+def assert_same(g, o, slots, with_hash=True):
+    sg, so = g.stats(), o.stats()
+    assert sg == so, (sg, so)
+    n = sg["tick"]
+    tg, to = g.tick_trace(0, n), o.tick_trace(0, n)
+    for f in tg.dtype.names:
+        if f == "hash" and not with_hash:
+            continue
+        bad = np.nonzero(tg[f] != to[f])[0]
+        assert bad.size == 0, f"trace field {f} first differs at tick {bad[0]}: emu {tg[f][bad[0]]} oracle {to[f][bad[0]]}"
+    assert (g.lamport_time() == o.lamport_time()).all()
+    for s in range(slots):
+        rg, ro = g.records(s), o.records(s)
+        bad = np.nonzero(rg != ro)[0]
+        assert bad.size == 0, f"slot {s}: record of node {bad[0]} differs: emu {rg[bad[0]]} oracle {ro[bad[0]]}"
+        assert (g.member_status(s) == o.member_status(s)).all()
+        assert (g.status_ltime(s) == o.status_ltime(s)).all()
+        assert (g.incarnation(s) == o.incarnation(s)).all()
+        assert (g.ml_state(s) == o.ml_state(s)).all()
+    assert g.state_hash() == o.state_hash()
+
+
+def run_both(sc, **cfg):
+    o = sc.build(oracle_sim, trace=1, **cfg)
+    to = o.run_until_converged(sc.max_ticks)
+    g = sc.build(emu_sim, trace=1, **cfg)
+    assert g.run_until_converged(sc.max_ticks) == to
+    assert_same(g, o, sc.slots)
+    f = sc.build(emu_sim, trace=0, **cfg)                 # production mode: tile skipping, lazy loads, no per-tick hash
+    assert f.run_until_converged(sc.max_ticks) == to
+    assert_same(f, o, sc.slots, with_hash=False)
+    return g, o
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_config0_full_mesh_256(seed):
+    g, o = run_both(scenarios.full_mesh_leave(256, 3, seed))
+    assert (g.member_status(0)[1:] == MemberStatus.LEFT).all()
+
+
+def test_random_graph_single_slot():
+    run_both(scenarios.random_graph_leave(6000, 16, 3, seed=1))
+
+
+def test_random_graph_multi_slot_fanout4():
+    run_both(scenarios.random_graph_leave(3000, 12, 4, seed=5, slots=4))
+
+
+def test_fanout_eight():
+    run_both(scenarios.random_graph_leave(2000, 12, 8, seed=3, slots=2))
+
+
+def test_failure_detection():
+    sc = scenarios.random_graph_fail(2500, 16, 3, seed=2)
+    g, o = run_both(sc, suspicion_mult=2, suspicion_max_timeout_mult=2, probe_interval_ticks=2)
+    assert (np.delete(g.member_status(0), 5) == MemberStatus.FAILED).all()
+
+
+def test_small_world_churn():
+    sc = scenarios.small_world_churn(3000, 12, 0.1, 0.05, slots=4, window=30, seed=3)
+    run_both(sc, suspicion_mult=2, suspicion_max_timeout_mult=2, probe_interval_ticks=2)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_fuzz(seed):
+    run_both(scenarios.fuzz(seed))
