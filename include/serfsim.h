@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SERFSIM_ABI_VERSION 2u
+#define SERFSIM_ABI_VERSION 3u
 
 /* ---- error codes ------------------------------------------------------------------ */
 #define SERFSIM_OK            0
@@ -73,6 +73,9 @@ extern "C" {
 #define SERFSIM_OP_FORCE_LEAVE  3u  /* Serf::remove_failed_node           `serf/base.rs:454-480`                         */
 #define SERFSIM_OP_FAIL         4u  /* process crash: node stops sending/receiving (fault injection, cf. MessageDropper `serf/delegate.rs:42-45`) */
 #define SERFSIM_OP_REJOIN       5u  /* crashed node returns: memberlist alive(inc+1) + Serf::join                        */
+#define SERFSIM_OP_USER_EVENT   6u  /* Serf::user_event                   `serf/api.rs:241-299`; `slot` = tracked user event */
+
+#define SERFSIM_MAX_USER_EVENTS 8u
 
 /* ---- configuration: serf `Options` (`options.rs:495-530`) + the memberlist LAN knobs it
  *      embeds (`options.rs:521`), expressed in gossip ticks ----------------------------- */
@@ -123,6 +126,26 @@ typedef struct serfsim_stats {
 typedef struct serfsim_tick_row {
   uint64_t packets, edge_updates, messages, changed, pending, events, suspects, hash;
 } serfsim_tick_row_t;
+
+/* User-event dissemination counters — Stats.event_time / Stats.event_queue of `serf/api.rs:588-602`
+ * plus delivery counters.  Deliveries are also part of the tick rows (edge_updates, messages, changed, pending). */
+typedef struct serfsim_uevent_stats {
+  uint64_t messages;      /* event messages sent (one per event per target)                                  */
+  uint64_t edge_updates;  /* sender→target pairs that carried ≥ 1 event message                               */
+  uint64_t delivered;     /* events handed to the application: handle_user_event → true, `serf/base.rs:829-836` */
+  uint64_t duplicates;    /* (node, tick, event) arrivals dropped as already seen, `serf/base.rs:801-806`      */
+  uint64_t too_old;       /* arrivals outside the event_buffer_size window, `serf/base.rs:771-781`             */
+  uint64_t event_queue;   /* Stats.event_queue: event broadcasts still queued, over all nodes                  */
+  uint64_t event_time;    /* Stats.event_time: max event LamportClock over nodes                               */
+} serfsim_uevent_stats_t;
+
+/* Byzantine stale-record injectors (BASELINE configs[4]).  No reference semantics exist: serf ignores stale intents
+ * silently (`serf/base.rs:1346-1348, 1464-1466`); the model is defined by this repository's oracle. */
+typedef struct serfsim_byz_stats {
+  uint64_t messages;      /* stale entries injected (one serf + one memberlist entry per peer and subject) */
+  uint64_t edge_updates;  /* injected (peer, subject) pairs — NOT part of the tick rows' edge_updates       */
+  uint64_t flagged;       /* injectors whose anomaly flag is set                                            */
+} serfsim_byz_stats_t;
 
 typedef struct serfsim serfsim_t;   /* opaque; owned by the caller; freed by serfsim_destroy */
 
@@ -182,6 +205,34 @@ int serfsim_stats        (serfsim_t* h, serfsim_stats_t* out);                  
 int serfsim_tick_trace   (serfsim_t* h, uint32_t first_tick, uint32_t n, serfsim_tick_row_t* out);
 int serfsim_state_hash   (serfsim_t* h, uint64_t* out);                              /* hash of all records + clocks, any time                */
 int serfsim_set_event_cb (serfsim_t* h, serfsim_event_cb cb, void* user);
+
+/* ---- user events (`Serf::user_event` `serf/api.rs:241-299`, `handle_user_event` `serf/base.rs:750-837`,
+ *      re-broadcast `serf/delegate.rs:219-221, 293-300`) ------------------------------------------------
+ * Declare the tracked user events: content_ids[e] identifies (name, payload) — two events with equal ids
+ * are equal for the receiver's de-duplication.  Event e is fired with
+ * serfsim_inject(tick, SERFSIM_OP_USER_EVENT, origin, e), once; its Lamport time is the origin's event
+ * clock at that tick.  Call before scheduling operations; n_events = 0 switches user events off.
+ * Works sharded (an event crossing shards is one 8-byte window entry carrying its Lamport time; counters of
+ * serfsim_user_event_stats are global sums, event_time is the local shard's maximum); not together with
+ * push-pull rounds in this version. */
+int serfsim_set_user_events(serfsim_t* h, uint32_t n_events, const uint32_t* content_ids /*[n_events]*/);
+int serfsim_event_time       (serfsim_t* h, uint64_t* out /*[count]*/);                  /* event_clock.time() per node, `serf.rs:139`              */
+int serfsim_user_event_seen  (serfsim_t* h, uint32_t event, uint8_t* out /*[count]*/);   /* 1: the node delivered the event to its EventSubscriber */
+int serfsim_user_event_ltime (serfsim_t* h, uint32_t event, uint64_t* ltime);            /* UserEventMessage.ltime stamped by the origin (0: not fired yet) */
+int serfsim_user_event_records(serfsim_t* h, void* out /*[count][16]*/);                 /* raw 16-byte event records (layout: DESIGN.md)          */
+int serfsim_user_event_stats (serfsim_t* h, serfsim_uevent_stats_t* out);
+
+/* ---- byzantine stale-record injectors (BASELINE configs[4]) --------------------------------------------
+ * ids[] re-inject, every tick, a copy of their own view aged by `delta` (status_time − delta, incarnation − delta,
+ * saturating) to that tick's gossip peers.  anomaly[u] = 1 once a receiver that was up held a view newer than
+ * u's injected entry by ≥ delta.  Call before scheduling operations; n = 0 switches injectors off.  With
+ * injectors on, serfsim_run_until_converged stops at the first tick with no honest traffic, nothing pending
+ * and nothing merged.  Works sharded: every rank passes the GLOBAL id list and keeps the injectors of its shard; an
+ * entry bound for another shard is judged by that shard against its own record and the flag is raised in the
+ * sender's shard over NVLink.  Not together with push-pull rounds in this version. */
+int serfsim_set_byzantine  (serfsim_t* h, uint32_t n, const uint32_t* ids /*[n]*/, uint32_t delta);
+int serfsim_anomaly_flags  (serfsim_t* h, uint8_t* out /*[count]*/);
+int serfsim_byzantine_stats(serfsim_t* h, serfsim_byz_stats_t* out);
 
 /* ---- measurement hooks (bench.py): device time of the tick kernels inside the last
  *      serfsim_step / run_until_converged call, measured with CUDA events on the launch

@@ -8,6 +8,7 @@
 //   serf::Options                 ↔ serf-core/src/options.rs (the memberlist LAN profile it embeds, :521)
 //   serf::Serf::join/leave/remove_failed_node/members/stats/shutdown
 //                                    ↔ serf-core/src/serf/api.rs:318-361, 422-499, 505-515, 136-146, 150-183
+//   serf::Serf::user_event         ↔ serf-core/src/serf/api.rs:241-299
 //   serf::MemberEventType, EventSubscriber-style callback
 //                                    ↔ serf-core/src/event.rs:325-328, serf/delegate.rs:557-582
 //
@@ -106,6 +107,14 @@ class Serf {
   // fault injection (cf. MessageDropper, serf/delegate.rs:42-45)
   void fail(uint32_t node, uint32_t tick = 0) { check(serfsim_inject(h_, tick, SERFSIM_OP_FAIL, node, 0)); }
   void rejoin(uint32_t node, uint32_t tick = 0) { check(serfsim_inject(h_, tick, SERFSIM_OP_REJOIN, node, 0)); }
+
+  // Serf::user_event (serf/api.rs:241-299): declare the tracked events once, then fire event `event` at `origin`
+  void track_user_events(const std::vector<uint32_t>& content_ids) { check(serfsim_set_user_events(h_, (uint32_t)content_ids.size(), content_ids.data())); }
+  void user_event(uint32_t origin, uint32_t event, uint32_t tick = 0) { check(serfsim_inject(h_, tick, SERFSIM_OP_USER_EVENT, origin, event)); }
+  // which nodes handed the event to their EventSubscriber (event.rs:396-512)
+  std::vector<uint8_t> user_event_seen(uint32_t event) const { std::vector<uint8_t> v(n_); check(serfsim_user_event_seen(h_, event, v.data())); return v; }
+  std::vector<LamportTime> event_time() const { std::vector<LamportTime> v(n_); check(serfsim_event_time(h_, v.data())); return v; }
+  serfsim_uevent_stats_t user_event_stats() const { serfsim_uevent_stats_t s; check(serfsim_user_event_stats(h_, &s)); return s; }
 
   // the hot path
   void step(uint32_t ticks = 1) { check(serfsim_step(h_, ticks)); }

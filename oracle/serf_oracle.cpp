@@ -34,6 +34,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -569,7 +570,29 @@ static void v_ml_dead(View& r, u32 d, bool left, u32 tick, bool self, const Rule
 }
 static inline u32 ml_key(const View& r) { return (r.inc << 6) | ((u32)ml_state(r) << 4) | ((r.ml >> 2) & 15); }
 
-struct Msg { u32 dst, src, val; u8 slot, kind; };   // kind 0 leave, 1 join, 2 memberlist
+// byzantine injector rules (BASELINE configs[4]; defined here, there is no reference behaviour to follow)
+static void byz_stale(const View& r, u32 delta, u8* kind, u32* lt, u32* key) {        // the aged copy of a view an injector re-sends
+  *lt = r.st > delta ? r.st - delta : 0;
+  const u32 inc = r.inc > delta ? r.inc - delta : 0;
+  *kind = (r.status == ST_LEAVING || r.status == ST_LEFT) ? 0 : 1;
+  *key = (inc << 6) | ((u32)ml_state(r) << 4) | ((r.ml >> 2) & 15);
+}
+static bool byz_judge(const View& q, u8 kind, u32 val, u32 delta) {                    // receiver's verdict on ONE arriving stale entry
+  return (kind == 2) ? (q.inc >= (val >> 6) + delta) : (known(q) && q.st >= val + delta);
+}
+
+struct Msg { u32 dst, src, val; u8 slot, kind, byz = 0; };   // kind 0 leave, 1 join, 2 memberlist; byz: a stale entry injected by a byzantine node
+
+// ---- user events: literal per-node state ----
+// EventCore.buffer is `Vec<Option<UserEvents>>` of event_buffer_size = 512 entries (serf/base.rs:193, options.rs:516);
+// kept here as a map ring-index → slot, which is the same thing without the 512 × N empty entries.
+struct UeSlotB { u32 ltime; std::vector<u32> events; };      // UserEvents { ltime, events } — events hold tracked-event indices
+struct UeNodeB {
+  u32 clock = 1;                                             // event_clock after Serf::new (serf/base.rs:198-200)
+  std::map<u32, UeSlotB> ring;
+  u8 tx[8] = {0, 0, 0, 0, 0, 0, 0, 0};                       // remaining transmits of the queued broadcast of tracked event e
+};
+struct UeMsg { u32 dst, e; };
 struct EventB { u32 tick, op, node, slot; };
 
 struct TickSim {
@@ -595,6 +618,16 @@ struct TickSim {
   std::vector<Scratch> scratch;                                  // per-thread buffers, reused across ticks
   u32 chunk = 1;
   u64 tot_events = 0;
+  // user events
+  u32 ue_n = 0; u32 ue_content[8] = {0}; u32 ue_ltime[8] = {0}; u32 ue_injected = 0;
+  std::vector<UeNodeB> uen;
+  std::vector<std::vector<UeMsg>> ue_mail, ue_mail_next;       // [producer range][consumer range], like `mail`
+  u64 ue_tot[5] = {0, 0, 0, 0, 0};                             // messages, edge_updates, delivered, duplicates, too_old
+  // byzantine stale-record injectors (BASELINE configs[4]; no reference semantics — this block IS the definition)
+  std::vector<u8> byz;                                         // per node: 1 = injector
+  u32 byz_n = 0, byz_delta = 2;
+  std::vector<u8> anomaly;                                     // per node: sender flag
+  u64 byz_tot[3] = {0, 0, 0};                                  // injected entries, injected (peer, subject) pairs, senders flagged
   int threads = 1;
   std::string err;
 
@@ -619,6 +652,38 @@ struct TickSim {
         r.st = cfg.init_status_ltime; r.inc = 1; r.status = ST_ALIVE; r.flags = 1; set_ml(r, ML_ALIVE, 0);
       }
     subj_up.assign(R, 1);
+    ue_reset();
+    anomaly.assign(byz_n ? N : 0, 0); for (auto& x : byz_tot) x = 0;
+  }
+  void ue_reset() {
+    uen.assign(ue_n ? N : 0, UeNodeB{}); ue_mail.clear(); ue_mail_next.clear(); ue_injected = 0;
+    for (auto& x : ue_ltime) x = 0;
+    for (auto& x : ue_tot) x = 0;
+  }
+  // Serf::handle_user_event (serf/base.rs:750-837) for tracked event e carrying Lamport time L.
+  // 0 accepted (→ rebroadcast), 1 duplicate, 2 too old.
+  int ue_handle(UeNodeB& nd, u32 e, u32 L) {
+    witness32(nd.clock, L);                                                    // :763
+    const u32 min_time = 0;                                                    // EventCore.min_time: only moved by a join with event_join_ignore (delegate.rs:531-537)
+    if (L < min_time) return 2;                                                // :766-768
+    const u32 bltime = 512, cur = nd.clock;                                    // :771-772
+    if (cur > bltime && L < cur - bltime) return 2;                            // :773-781
+    const u32 idx = L % bltime;                                                // :784
+    auto it = nd.ring.find(idx);
+    if (it != nd.ring.end()) {                                                 // occupied: the slot's own ltime is not looked at (quirk ii)
+      for (u32 prev : it->second.events) if (ue_content[prev] == ue_content[e]) return 1;   // :801-806 user_event.eq(prev): name and payload
+      it->second.events.push_back(e);                                          // :807
+    } else {
+      nd.ring[idx] = UeSlotB{L, {e}};                                          // :809-813
+    }
+    return 0;                                                                  // :836 true
+  }
+  void ue_record(u32 v, u32 out[4]) const {                    // the 16-byte event record the CUDA path keeps
+    const UeNodeB& nd = uen[v];
+    u32 seen = 0, first = 0;
+    for (auto& kv : nd.ring) { for (u32 e : kv.second.events) seen |= 1u << e; first |= 1u << kv.second.events[0]; }
+    out[0] = nd.clock; out[1] = seen | (first << 8); out[2] = 0; out[3] = 0;
+    for (u32 e = 0; e < 4; ++e) { out[2] |= (u32)nd.tx[e] << (8 * e); out[3] |= (u32)nd.tx[4 + e] << (8 * e); }
   }
   void compute_watch() {
     watch.assign(N, 0);
@@ -675,6 +740,16 @@ struct TickSim {
     if (scratch.size() != T) scratch.assign(T, Scratch{});
     if (exported.size() != T) exported.assign(T, {});
     for (auto& e : exported) e.clear();
+    if (ue_n) {
+      if (ue_mail.size() != (size_t)T * T) ue_mail.assign((size_t)T * T, {});
+      if (ue_mail_next.size() != (size_t)T * T) ue_mail_next.assign((size_t)T * T, {});
+      for (auto& b : ue_mail_next) b.clear();
+    }
+    std::vector<u64> ue_rows((size_t)T * 5, 0);
+    std::vector<std::vector<u32>> byz_flagged(T);               // senders judged anomalous by the receivers of each range
+    std::vector<u64> byz_rows((size_t)T * 2, 0);
+    std::vector<std::pair<u32, u32>> ue_stamps;                 // (event, ltime) stamped this tick; published after the node loop
+    std::mutex ue_stamp_mx;
     std::vector<std::vector<Msg>>& next = mail_next;
     // events of this tick
     std::vector<EventB> evs;
@@ -703,6 +778,9 @@ struct TickSim {
     std::vector<Msg>& byd = sx.byd;
     byd.resize(total);
     { std::vector<u32>& pos = sx.pos; pos.assign(head.begin(), head.end() - 1); for (u32 p = 0; p < T; ++p) for (auto& m : mail[(size_t)p * T + c]) byd[pos[m.dst - v0]++] = m; }
+    // user-event mail for my id range: destination → arrived tracked events (every copy kept: literal delivery)
+    std::unordered_map<u32, std::vector<u32>> ue_in;
+    if (ue_n) for (u32 p = 0; p < T; ++p) for (auto& m : ue_mail[(size_t)p * T + c]) ue_in[m.dst].push_back(m.e);
     auto post = [&](const Msg& m) {
       if (m.dst - own_first < own_count) next[(size_t)c * T + owner_of(m.dst)].push_back(m);
       else exported[c].push_back(m);                      // destination lives in another shard
@@ -721,6 +799,14 @@ struct TickSim {
       if (up_s && wmask && cfg.probe_interval_ticks && any_down && ((t + v) % cfg.probe_interval_ticks) == 0)
         have_probe = probe_target(v, t, &ptarget);
       u32 max_tx = 0;
+      // byzantine entries that arrive now are judged against this node's views as they stand, before anything is merged
+      if (byz_n && up_r)
+        for (u32 i = head[v - v0]; i < head[v - v0 + 1]; ++i) {
+          const Msg& m = byd[i];
+          if (!m.byz) continue;
+          const View& q = at(m.slot, v);
+          if (byz_judge(q, m.kind, m.val, byz_delta)) byz_flagged[c].push_back(m.src);
+        }
       for (u32 s = 0; s < R; ++s) {
         View& r = at(s, v);
         const bool self = (subj[s] == v);
@@ -833,7 +919,61 @@ struct TickSim {
           bool pend = (r.txl | r.txj | r.txm) || ml_state(r) == ML_SUSPECT ||
                       (cfg.probe_interval_ticks && !subj_up[s] && !self && ((wmask >> s) & 1) && ml_state(r) == ML_ALIVE);   // a watcher that has not noticed yet
           if (pend) row.pending++;
+          // byzantine injector: a stale copy of the END-of-tick view goes to this tick's gossip peers, budgets or not
+          if (byz_n && byz[v] && known(r)) {
+            if (!have_targets) { nt = gossip_targets(v, t, targets); have_targets = true; }
+            u8 kind; u32 lt, key;
+            byz_stale(r, byz_delta, &kind, &lt, &key);
+            for (u32 k = 0; k < nt; ++k) {
+              post(Msg{targets[k], v, lt, (u8)s, kind, 1});
+              post(Msg{targets[k], v, key, (u8)s, 2, 1});
+              byz_rows[(size_t)c * 2] += 2; byz_rows[(size_t)c * 2 + 1] += 1;
+            }
+          }
         }
+      }
+      // ---------------- user events: receive, originate, send (serf/base.rs:750-837, serf/api.rs:241-299) ----------------
+      if (ue_n) {
+        UeNodeB& un = uen[v];
+        u64* ur = &ue_rows[(size_t)c * 5];
+        auto itin = ue_in.empty() ? ue_in.end() : ue_in.find(v);
+        if (up_r) {
+          if (itin != ue_in.end()) {
+            std::vector<u32>& arr = itin->second;
+            std::sort(arr.begin(), arr.end());                                  // canonical order: ascending tracked-event index
+            for (size_t i = 0; i < arr.size(); ++i) {
+              const u32 e = arr[i];
+              const int oc = ue_handle(un, e, ue_ltime[e]);
+              if (oc == 0) un.tx[e] = (u8)cx.limit;                             // true → re-queued with a fresh budget (delegate.rs:293-300)
+              if (i == 0 || arr[i - 1] != e) {                                  // counters per (node, tick, event): copies 2..k are always duplicates
+                if (oc == 0) { ur[2]++; row.changed++; } else if (oc == 1) ur[3]++; else ur[4]++;
+              }
+            }
+          }
+          if (ev && ev->op == SERFSIM_OP_USER_EVENT) {                          // Serf::user_event, serf/api.rs:241-299
+            const u32 e = ev->slot;
+            const u32 L = un.clock;                                             // :264 ltime = event_clock.time()
+            un.clock += 1;                                                      // :285 increment
+            const int oc = ue_handle(un, e, L);                                 // :288 handled locally, result ignored
+            un.tx[e] = (u8)cx.limit;                                            // :290-297 queued unconditionally
+            if (oc == 0) { ur[2]++; row.changed++; } else if (oc == 1) ur[3]++; else ur[4]++;
+            std::lock_guard<std::mutex> g(ue_stamp_mx);
+            ue_stamps.push_back({e, L});
+          }
+        }
+        if (up_s) {
+          bool any = false; for (u32 e = 0; e < ue_n; ++e) any |= un.tx[e] != 0;
+          if (any) {
+            u32 utg[8]; const u32 unt = gossip_targets(v, t, utg);              // same packet, same peers as the intents
+            for (u32 k = 0; k < unt; ++k) {
+              u32 cnt = 0;
+              for (u32 e = 0; e < ue_n; ++e) if (un.tx[e] > k) { ue_mail_next[(size_t)c * T + owner_of(utg[k])].push_back(UeMsg{utg[k], e}); ++cnt; }
+              if (cnt) { row.edge_updates++; row.messages += cnt; ur[0] += cnt; ur[1]++; }
+            }
+            for (u32 e = 0; e < ue_n; ++e) un.tx[e] -= (u8)std::min<u32>(un.tx[e], unt);
+          }
+        }
+        if (up_s) for (u32 e = 0; e < ue_n; ++e) if (un.tx[e]) row.pending++;      // a crashed node's queue is frozen, not pending
       }
       if (ev) { row.events++; }
       nd.up = up_s;
@@ -843,6 +983,17 @@ struct TickSim {
     if (T == 1) work(0);
     else { std::vector<std::thread> th; for (u32 c = 0; c < T; ++c) th.emplace_back(work, c); for (auto& x : th) x.join(); }
     mail.swap(mail_next);
+    if (byz_n) {
+      for (u32 c = 0; c < T; ++c) {
+        for (u32 src : byz_flagged[c]) if (!anomaly[src]) { anomaly[src] = 1; byz_tot[2]++; }
+        byz_tot[0] += byz_rows[(size_t)c * 2]; byz_tot[1] += byz_rows[(size_t)c * 2 + 1];
+      }
+    }
+    if (ue_n) {
+      ue_mail.swap(ue_mail_next);
+      for (auto& st : ue_stamps) ue_ltime[st.first] = st.second;        // visible to receivers from the next tick on
+      for (u32 c = 0; c < T; ++c) for (int i = 0; i < 5; ++i) ue_tot[i] += ue_rows[(size_t)c * 5 + i];
+    }
     // ---------------- anti-entropy round: memberlist push-pull + SerfDelegate::merge_remote_state ----------------
     // (serf/delegate.rs:386-554; memberlist mergeState [external]).  Every push_pull_interval ticks each up node
     // pulls the end-of-tick state of ONE random neighbour and merges it: clock witness(ltime-1); per subject the
@@ -917,6 +1068,10 @@ struct TickSim {
     for (u32 v = a; v < b; ++v) {
       u64 w = (u64)node[v].clock | ((u64)node[v].up << 32) | ((u64)node[v].sstate << 40);
       h += mix64(w ^ mix64((u64)R * N + v + 0x9e3779b97f4a7c15ULL));
+    }
+    if (ue_n) for (u32 v = a; v < b; ++v) {
+      u32 w[4]; ue_record(v, w);
+      h += mix64((((u64)w[1] << 32) | w[0]) ^ mix64((((u64)w[3] << 32) | w[2]) ^ mix64((u64)(R + 1) * N + v + 0x9e3779b97f4a7c15ULL)));
     }
     return h;
   }
@@ -1029,10 +1184,15 @@ ORC int oracle_sim_set_subjects(void* p, const u32* subjects) {
 ORC int oracle_sim_reset(void* p, u64 seed) { ((TickSim*)p)->reset(seed); return 0; }
 ORC int oracle_sim_inject(void* p, u32 tick, u32 op, u32 node, u32 slot) {
   auto* s = (TickSim*)p;
-  if (tick < s->tick || node >= s->N || op < 1 || op > 5) { g_err = "bad inject"; return SERFSIM_E_INVAL; }
+  if (tick < s->tick || node >= s->N || op < 1 || op > 6) { g_err = "bad inject"; return SERFSIM_E_INVAL; }
+  if (op == SERFSIM_OP_USER_EVENT) {
+    if (slot >= s->ue_n) { g_err = "user event index out of range"; return SERFSIM_E_INVAL; }
+    if ((s->ue_injected >> slot) & 1u) { g_err = "a tracked user event can be injected once"; return SERFSIM_E_INVAL; }
+  }
   if (op == SERFSIM_OP_FORCE_LEAVE) { if (slot >= s->R) return SERFSIM_E_INVAL; }
   else if ((op == SERFSIM_OP_JOIN || op == SERFSIM_OP_LEAVE) && s->slot_of(node) < 0) { g_err = "join/leave origin must be a tracked subject"; return SERFSIM_E_INVAL; }
   if (!s->event_keys.insert(((u64)tick << 32) | node).second) { g_err = "one operation per node per tick"; return SERFSIM_E_INVAL; }
+  if (op == SERFSIM_OP_USER_EVENT) s->ue_injected |= 1u << slot;
   s->events.push_back(EventB{tick, op, node, slot}); s->ev_by_tick[tick].push_back(EventB{tick, op, node, slot});
   s->max_event_tick = s->any_event ? std::max(s->max_event_tick, tick) : tick; s->any_event = true;
   return 0;
@@ -1048,7 +1208,9 @@ ORC int oracle_sim_run_until_converged(void* p, u32 max_ticks, u32* ticks_out) {
     // times (status_time keeps creeping: the reference re-sends a Left member as "leave at status_ltime + 1",
     // serf/delegate.rs:495-510, so the round's `changed` counter ignores status_time)
     const bool pp_ok = !pp || ((s->tick % pp) == 0 && r.changed == 0);
-    if (r.pending == 0 && r.edge_updates == 0 && !s->future_events() && pp_ok) { if (ticks_out) *ticks_out = s->tick - 1; return 0; }
+    // with byzantine injectors stale entries are in flight forever: quiescent = no honest traffic AND nothing merged this tick
+    const bool byz_ok = !s->byz_n || r.changed == 0;
+    if (r.pending == 0 && r.edge_updates == 0 && !s->future_events() && pp_ok && byz_ok) { if (ticks_out) *ticks_out = s->tick - 1; return 0; }
   }
   if (ticks_out) *ticks_out = s->tick;
   return 1;
@@ -1083,6 +1245,59 @@ ORC int oracle_sim_stats(void* p, serfsim_stats_t* o) {
     if (diff) o->disagree_slots++;
   }
   return 0;
+}
+
+ORC void oracle_byz_stale(const void* rec32, u32 delta, u32* out /*kind, lt, key*/) { View r; memcpy(&r, rec32, 32); u8 k; byz_stale(r, delta, &k, &out[1], &out[2]); out[0] = k; }
+ORC int oracle_byz_judge(const void* rec32, u32 kind, u32 val, u32 delta) { View q; memcpy(&q, rec32, 32); return byz_judge(q, (u8)kind, val, delta); }
+// ---- byzantine injectors: same shapes as serfsim_set_byzantine / serfsim_anomaly_flags / serfsim_byzantine_stats ----
+ORC int oracle_sim_set_byzantine(void* p, u32 n, const u32* ids, u32 delta) {
+  auto* s = (TickSim*)p;
+  if ((n && !ids) || s->tick != 0 || !s->events.empty()) { g_err = "bad set_byzantine"; return SERFSIM_E_INVAL; }
+  if (n && (s->own_count != s->N || s->cfg.push_pull_interval_ticks > 0)) { g_err = "byzantine injectors: single shard, no push-pull"; return SERFSIM_E_INVAL; }
+  s->byz.assign(n ? s->N : 0, 0); s->byz_n = 0;
+  for (u32 i = 0; i < n; ++i) { if (ids[i] >= s->N || s->byz[ids[i]]) { g_err = "bad byzantine id"; return SERFSIM_E_INVAL; } s->byz[ids[i]] = 1; s->byz_n++; }
+  s->byz_delta = delta; s->anomaly.assign(n ? s->N : 0, 0); for (auto& x : s->byz_tot) x = 0;
+  return 0;
+}
+ORC int oracle_sim_anomaly_flags(void* p, u8* out) { auto* s = (TickSim*)p; if (!s->byz_n) return SERFSIM_E_INVAL; memcpy(out, s->anomaly.data(), s->N); return 0; }
+ORC int oracle_sim_byzantine_stats(void* p, serfsim_byz_stats_t* o) {
+  auto* s = (TickSim*)p; if (!s->byz_n) return SERFSIM_E_INVAL;
+  o->messages = s->byz_tot[0]; o->edge_updates = s->byz_tot[1]; o->flagged = s->byz_tot[2];
+  return 0;
+}
+
+// ---- user events: same shapes as serfsim_set_user_events / serfsim_user_event_* ----
+ORC int oracle_sim_set_user_events(void* p, u32 n, const u32* content) {
+  auto* s = (TickSim*)p;
+  if (n > 8 || (n && !content) || s->tick != 0 || !s->events.empty()) { g_err = "bad set_user_events"; return SERFSIM_E_INVAL; }
+  if (n && (s->own_count != s->N || s->cfg.push_pull_interval_ticks > 0)) { g_err = "user events: single shard, no push-pull"; return SERFSIM_E_INVAL; }
+  s->ue_n = n; for (u32 e = 0; e < n; ++e) s->ue_content[e] = content[e];
+  s->ue_reset();
+  return 0;
+}
+ORC int oracle_sim_event_time(void* p, u64* out) { auto* s = (TickSim*)p; if (!s->ue_n) return SERFSIM_E_INVAL; for (u32 v = 0; v < s->N; ++v) out[v] = s->uen[v].clock; return 0; }
+ORC int oracle_sim_user_event_seen(void* p, u32 e, u8* out) {
+  auto* s = (TickSim*)p; if (e >= s->ue_n) return SERFSIM_E_INVAL;
+  for (u32 v = 0; v < s->N; ++v) { u32 w[4]; s->ue_record(v, w); out[v] = (u8)((w[1] >> e) & 1u); }
+  return 0;
+}
+ORC int oracle_sim_user_event_ltime(void* p, u32 e, u64* out) { auto* s = (TickSim*)p; if (e >= s->ue_n) return SERFSIM_E_INVAL; *out = s->ue_ltime[e]; return 0; }
+ORC int oracle_sim_user_event_records(void* p, void* out) { auto* s = (TickSim*)p; if (!s->ue_n) return SERFSIM_E_INVAL; for (u32 v = 0; v < s->N; ++v) s->ue_record(v, (u32*)out + 4 * (size_t)v); return 0; }
+ORC int oracle_sim_user_event_stats(void* p, serfsim_uevent_stats_t* o) {
+  auto* s = (TickSim*)p; if (!s->ue_n) return SERFSIM_E_INVAL;
+  memset(o, 0, sizeof(*o));
+  o->messages = s->ue_tot[0]; o->edge_updates = s->ue_tot[1]; o->delivered = s->ue_tot[2]; o->duplicates = s->ue_tot[3]; o->too_old = s->ue_tot[4];
+  for (auto& nd : s->uen) { for (u32 e = 0; e < s->ue_n; ++e) o->event_queue += nd.tx[e] ? 1 : 0; o->event_time = std::max<u64>(o->event_time, nd.clock); }
+  return 0;
+}
+
+// single-node probe: a sequence of (tracked event, its ltime) arrivals through TickSim::ue_handle; reports the outcomes and the record
+ORC void oracle_ue_handle_seq(u32 n_events, const u32* content, const u32* ltime_tab, u32 limit, u32 n, const u32* ev, int* outcomes, u32* record) {
+  TickSim s; s.N = 1; s.R = 1; s.ue_n = n_events;
+  for (u32 e = 0; e < n_events; ++e) { s.ue_content[e] = content[e]; s.ue_ltime[e] = ltime_tab[e]; }
+  s.uen.assign(1, UeNodeB{});
+  for (u32 i = 0; i < n; ++i) { outcomes[i] = s.ue_handle(s.uen[0], ev[i], ltime_tab[ev[i]]); if (outcomes[i] == 0) s.uen[0].tx[ev[i]] = (u8)limit; }
+  s.ue_record(0, record);
 }
 
 // =====================================================================================

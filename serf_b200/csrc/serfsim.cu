@@ -87,6 +87,8 @@ struct serfsim {
   bool watch_dirty = true;
   uint4* d_snap_rec = nullptr;     // push-pull rounds: end-of-tick snapshot of the records …
   u64* d_snap_node = nullptr;      // … and of the node words
+  const uint4** d_peer_snap_rec = nullptr;   // sharded push-pull: device arrays of every rank's snapshot pointers
+  const u64** d_peer_snap_node = nullptr;
   u8* d_hot[2] = {nullptr, nullptr};      // [n_tiles] per tick parity
   u32 n_tiles = 0;
   u32* d_rowptr = nullptr;         // [count+1]
@@ -101,6 +103,21 @@ struct serfsim {
   u32* d_subj = nullptr;
   u64* d_scratch = nullptr;        // summary / hash output
   void* d_stage = nullptr;         // getter staging, count × 8 B
+  // user events: allocated by serfsim_set_user_events
+  UeTable ue_table{};              // n = 0: user events off
+  uint4* d_ue_state = nullptr;     // [stride] 16-byte event records
+  u32* d_ue_inbox[2] = {nullptr, nullptr};   // [stride] arrived-event masks per tick parity
+  u32* d_ue_ltime = nullptr;       // [MAX_UEVENTS]
+  u64* d_ue_totals = nullptr;      // [8]
+  u32 ue_injected = 0;             // tracked events already scheduled (each may be injected once)
+  u32 ue_origin[MAX_UEVENTS] = {0};  // origin node of each scheduled event (its shard is the one that stamps the Lamport time)
+  // byzantine injectors (BASELINE configs[4]): allocated by serfsim_set_byzantine
+  u32 byz_n = 0, byz_delta = 2;    // byz_n: injectors of THIS shard
+  bool byz_on = false;             // any injector anywhere (all ranks agree): changes the convergence rule and the drain kernel
+  u8** d_peer_anomaly = nullptr;   // sharded runs: device array of every rank's flag array
+  u32* d_byz_ids = nullptr;        // [byz_n] ascending
+  u8* d_anomaly = nullptr;         // [stride] sender flags
+  u64* d_byz_totals = nullptr;     // [4]
   // host state
   std::vector<HostOp> ops;         // sorted by (tick, seq)
   std::unordered_set<u64> op_keys; // (tick << 32 | node): at most one operation per node per tick
@@ -253,8 +270,32 @@ int launch_ticks(serfsim* h, u32 n) {
       av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
       CU(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av));
     }
+    if (h->ue_table.n) {                       // user-event tick: needs the pre-operation up flags and op bits, so it runs first
+      UeParams u{};
+      u.n_local = h->count; u.first = h->first; u.n_global = h->N; u.R = h->R; u.fanout = h->cfg.fanout; u.tick = t;
+      u.seed_lo = p.seed_lo; u.seed_hi = p.seed_hi; u.limit = h->rules.limit; u.ev_begin = eb; u.ev_end = ee;
+      u.table = h->ue_table; u.state = h->d_ue_state; u.inbox_rd = h->d_ue_inbox[(t & 1) ^ 1]; u.inbox_wr = h->d_ue_inbox[t & 1];
+      u.ltime = h->d_ue_ltime; u.node_state = h->d_node; u.busy = h->d_busy; u.row_ptr = h->d_rowptr; u.col = h->d_col;
+      u.ev_node = h->d_ev_node; u.ev_op = h->d_ev_op; u.ev_slot = h->d_ev_slot;
+      u.row = p.row; u.totals = h->d_ue_totals; u.overflow = h->d_overflow;
+      u.world = (u32)h->cfg.world_size; u.rank = (u32)h->cfg.rank; u.shard_size = h->shard_size; u.win_cap = h->win_cap;
+      u.win_data = h->d_peer_data[h->xepoch & 1]; u.send_count = h->d_send_count;
+      launch_uevent(u, h->cfg.trace != 0, h->stream);
+      h->last_launches++;
+    }
     launch_tick(p, h->cfg.trace != 0, h->grid, h->stream);
     h->last_launches++;
+    if (h->byz_n) {                            // stale entries of this shard's injectors (before the exchange: peers in other shards get window entries)
+      ByzParams b{};
+      b.n_byz = h->byz_n; b.first = h->first; b.R = h->R; b.stride = h->stride; b.fanout = h->cfg.fanout; b.tick = t;
+      b.seed_lo = p.seed_lo; b.seed_hi = p.seed_hi; b.delta = h->byz_delta; b.ids = h->d_byz_ids; b.rec = h->d_rec; b.node_state = h->d_node;
+      b.row_ptr = h->d_rowptr; b.col = h->d_col; b.inbox_wr = h->d_inbox[t & 1]; b.hot_wr = h->d_hot[t & 1]; b.kinds_cur = p.kinds_cur;
+      b.anomaly = h->d_anomaly; b.totals = h->d_byz_totals;
+      b.n_local = h->count; b.world = p.world; b.rank = p.rank; b.shard_size = h->shard_size; b.win_cap = h->win_cap;
+      b.win_data = p.win_data; b.send_count = h->d_send_count; b.overflow = h->d_overflow;
+      launch_byz(b, h->stream);
+      h->last_launches++;
+    }
     if (h->tick_timing && h->cfg.world_size > 1) {
       while (h->mid_ev.size() < (size_t)t + 1) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->mid_ev.push_back(e); }
       CU(cudaEventRecord(h->mid_ev[t], h->stream));
@@ -269,6 +310,8 @@ int launch_ticks(serfsim* h, u32 n) {
       DrainParams d{};
       d.n_local = h->count; d.stride = h->stride; d.R = h->R; d.world = p.world; d.rank = p.rank; d.win_cap = h->win_cap; d.stamp = stamp; d.n_tiles = h->n_tiles; d.kinds_prev = p.kinds_prev;
       d.win_data = h->d_win_data[xpar]; d.ctrl = h->d_ctrl + xpar * 16; d.inbox_wr = h->d_inbox[t & 1]; d.hot_wr = h->d_hot[t & 1]; d.kinds_cur = h->d_kinds + ((size_t)t + 1) * 4; d.overflow = h->d_overflow;
+      d.byz_on = h->byz_on ? 1u : 0u; d.byz_delta = h->byz_delta; d.shard_size = h->shard_size; d.rec = h->d_rec; d.node_state = h->d_node; d.peer_anomaly = h->d_peer_anomaly;
+      d.ue_n = h->ue_table.n; d.ue_inbox_wr = h->ue_table.n ? h->d_ue_inbox[t & 1] : nullptr; d.ue_ltime = h->d_ue_ltime;
       launch_drain(d, h->stream);
       h->last_launches += 2;
       h->xepoch++;
@@ -280,7 +323,19 @@ int launch_ticks(serfsim* h, u32 n) {
       if (!h->d_snap_rec) { CU(cudaMalloc(&h->d_snap_rec, rb)); CU(cudaMalloc(&h->d_snap_node, nb)); }
       CU(cudaMemcpyAsync(h->d_snap_rec, h->d_rec, rb, cudaMemcpyDeviceToDevice, h->stream));
       CU(cudaMemcpyAsync(h->d_snap_node, h->d_node, nb, cudaMemcpyDeviceToDevice, h->stream));
-      launch_pushpull(p, h->d_snap_rec, h->d_snap_node, h->cfg.trace != 0, h->stream);
+      if (h->cfg.world_size > 1) {
+        // partners may live on other GPUs: their snapshots are read through the peer mappings.  Rounds are rare (every
+        // push_pull_interval ticks) and always the first tick of a convergence chunk, so two host barriers are affordable:
+        // every rank has taken its snapshot before anyone reads, everyone has read before anyone moves on.
+        p.snap_rec_peer = h->d_peer_snap_rec; p.snap_node_peer = h->d_peer_snap_node;
+        CU(cudaStreamSynchronize(h->stream));
+        h->barrier(h->comm_user);
+        launch_pushpull(p, h->d_snap_rec, h->d_snap_node, h->cfg.trace != 0, h->stream);
+        CU(cudaStreamSynchronize(h->stream));
+        h->barrier(h->comm_user);
+      } else {
+        launch_pushpull(p, h->d_snap_rec, h->d_snap_node, h->cfg.trace != 0, h->stream);
+      }
       h->last_launches++;
     }
     if (h->tick_timing) CU(cudaEventRecord(h->tick_ev[2 * (size_t)t + 1], h->stream));
@@ -357,6 +412,18 @@ int refresh_watchers(serfsim* h) {
   return 0;
 }
 
+int ue_reset(serfsim* h) {                      // bootstrap event state: clock 1, nothing seen, nothing queued
+  h->ue_injected = 0;
+  if (!h->ue_table.n) return 0;
+  launch_ue_init(h->d_ue_state, h->count, h->stream);
+  CU(cudaMemsetAsync(h->d_ue_inbox[0], 0, (size_t)h->stride * 4, h->stream));
+  CU(cudaMemsetAsync(h->d_ue_inbox[1], 0, (size_t)h->stride * 4, h->stream));
+  CU(cudaMemsetAsync(h->d_ue_ltime, 0, MAX_UEVENTS * 4, h->stream));
+  CU(cudaMemsetAsync(h->d_ue_totals, 0, 8 * 8, h->stream));
+  CU(cudaGetLastError());
+  return 0;
+}
+
 int do_reset(serfsim* h, u64 seed) {
   h->cfg.seed = seed; h->tick = 0; h->ops.clear(); h->op_keys.clear(); h->ops_dirty = false; h->rows.clear();
   h->up_mask = (h->R >= 32) ? 0xffffffffu : ((1u << h->R) - 1);
@@ -375,6 +442,8 @@ int do_reset(serfsim* h, u64 seed) {
     CU(cudaMemsetAsync(h->d_kinds, 0, ((size_t)h->trace_cap + 1) * 4 * sizeof(u32), h->stream));
   }
   if (h->d_send_count) CU(cudaMemsetAsync(h->d_send_count, 0, sizeof(u32) * 8, h->stream));
+  { int rc = ue_reset(h); if (rc) return rc; }
+  if (h->d_anomaly) { CU(cudaMemsetAsync(h->d_anomaly, 0, h->stride, h->stream)); CU(cudaMemsetAsync(h->d_byz_totals, 0, 4 * 8, h->stream)); }
   { int rc = refresh_watchers(h); if (rc) return rc; }
   CU(cudaStreamSynchronize(h->stream));
   return 0;
@@ -383,11 +452,13 @@ int do_reset(serfsim* h, u64 seed) {
 void free_all(serfsim* h) {
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   for (cudaEvent_t e : h->tick_ev) cudaEventDestroy(e);
-  cudaFree(h->d_hot[0]); cudaFree(h->d_hot[1]); cudaFree(h->d_busy); cudaFree(h->d_watch); cudaFree(h->d_snap_rec); cudaFree(h->d_snap_node);
+  cudaFree(h->d_hot[0]); cudaFree(h->d_hot[1]); cudaFree(h->d_busy); cudaFree(h->d_watch); cudaFree(h->d_snap_rec); cudaFree(h->d_snap_node); cudaFree(h->d_peer_snap_rec); cudaFree(h->d_peer_snap_node);
   cudaFree(h->d_qword);
   cudaFree(h->d_rec); cudaFree(h->d_inbox[0]); cudaFree(h->d_inbox[1]); cudaFree(h->d_node); cudaFree(h->d_rowptr); cudaFree(h->d_col);
   cudaFree(h->d_ev_node); cudaFree(h->d_ev_op); cudaFree(h->d_ev_slot); cudaFree(h->d_trace); cudaFree(h->d_kinds); cudaFree(h->d_ones);
   cudaFree(h->d_overflow); cudaFree(h->d_subj); cudaFree(h->d_scratch); cudaFree(h->d_stage);
+  cudaFree(h->d_byz_ids); cudaFree(h->d_anomaly); cudaFree(h->d_byz_totals); cudaFree(h->d_peer_anomaly);
+  cudaFree(h->d_ue_state); cudaFree(h->d_ue_inbox[0]); cudaFree(h->d_ue_inbox[1]); cudaFree(h->d_ue_ltime); cudaFree(h->d_ue_totals);
   for (int par = 0; par < 2; ++par) { cudaFree(h->d_win_data[par]); cudaFree(h->d_peer_data[par]); }
   cudaFree(h->d_ctrl); cudaFree(h->d_send_count); cudaFree(h->d_peer_ctrl);
   if (h->pin_rows) cudaFreeHost(h->pin_rows);
@@ -443,7 +514,6 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
   if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) return fail(SERFSIM_E_INVAL, "bad rank / world_size");
   if (cfg->gossip_interval_ms == 0) return fail(SERFSIM_E_INVAL, "gossip_interval_ms must be > 0");
   if (cfg->push_pull_interval_ticks < 0) return fail(SERFSIM_E_INVAL, "push_pull_interval_ticks must be >= 0");
-  if (cfg->push_pull_interval_ticks > 0 && cfg->world_size > 1) return fail(SERFSIM_E_INVAL, "push-pull rounds are single-GPU in this version (world_size must be 1)");
   if (cfg->suspicion_mult >= 2 && cfg->suspicion_mult - 2 > MAX_K) return fail(SERFSIM_E_INVAL, "suspicion_mult too large");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -527,6 +597,15 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
     CUB(cudaMalloc(&h->d_send_count, 8 * sizeof(u32)));
     CUB(cudaMemset(h->d_send_count, 0, 8 * sizeof(u32)));
     CUB(cudaMalloc(&h->d_peer_ctrl, sizeof(u32*) * 8));
+    CUB(cudaMalloc(&h->d_anomaly, h->stride)); CUB(cudaMemset(h->d_anomaly, 0, h->stride));   // byzantine sender flags: peers' drain kernels raise them
+    CUB(cudaMalloc(&h->d_byz_totals, 4 * 8)); CUB(cudaMemset(h->d_byz_totals, 0, 4 * 8));
+    CUB(cudaMalloc(&h->d_peer_anomaly, sizeof(void*) * 8));
+    if (cfg->push_pull_interval_ticks > 0) {      // the snapshots partners on other GPUs read: allocated now so that they can be exported
+      CUB(cudaMalloc(&h->d_snap_rec, (size_t)h->R * h->stride * 32));
+      CUB(cudaMalloc(&h->d_snap_node, (size_t)h->stride * 8));
+      CUB(cudaMalloc(&h->d_peer_snap_rec, sizeof(void*) * 8));
+      CUB(cudaMalloc(&h->d_peer_snap_node, sizeof(void*) * 8));
+    }
   }
   {
     int rc = ensure_trace(h, 1024);
@@ -622,11 +701,16 @@ int serfsim_reset(serfsim_t* h, uint64_t seed) {
 int serfsim_inject(serfsim_t* h, uint32_t tick, uint32_t op, uint32_t node, uint32_t slot) {
   if (!h) return fail(SERFSIM_E_INVAL, "null handle");
   if (tick < h->tick) return fail(SERFSIM_E_INVAL, "cannot schedule an operation in the past");
-  if (node >= h->N || op < SERFSIM_OP_JOIN || op > SERFSIM_OP_REJOIN) return fail(SERFSIM_E_INVAL, "bad node / op");
+  if (node >= h->N || op < SERFSIM_OP_JOIN || op > SERFSIM_OP_USER_EVENT) return fail(SERFSIM_E_INVAL, "bad node / op");
+  if (op == SERFSIM_OP_USER_EVENT) {
+    if (slot >= h->ue_table.n) return fail(SERFSIM_E_INVAL, "user event index out of range (serfsim_set_user_events)");
+    if ((h->ue_injected >> slot) & 1u) return fail(SERFSIM_E_INVAL, "a tracked user event can be injected once");
+  }
   if (op == SERFSIM_OP_FORCE_LEAVE) { if (slot >= h->R) return fail(SERFSIM_E_INVAL, "slot out of range"); }
   else if ((op == SERFSIM_OP_JOIN || op == SERFSIM_OP_LEAVE) && slot_of(h, node) < 0)
     return fail(SERFSIM_E_INVAL, "join/leave origin must be a tracked subject");
   if (!h->op_keys.insert(((u64)tick << 32) | node).second) return fail(SERFSIM_E_INVAL, "one operation per node per tick");
+  if (op == SERFSIM_OP_USER_EVENT) { h->ue_injected |= 1u << slot; h->ue_origin[slot] = node; }
   h->ops.push_back(HostOp{tick, op, node, slot, h->op_seq++});
   h->ops_dirty = true;
   return 0;
@@ -647,6 +731,7 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
   if (!h) return fail(SERFSIM_E_INVAL, "null handle");
   u32 chunk = 4;
   if (const char* e = getenv("SERFSIM_CHUNK")) chunk = std::max(1, atoi(e));
+  if (h->byz_on) chunk = 1;     // injector ticks are never no-ops, so no tick may be launched past the quiescent one
   const u32 pp = (u32)std::max(0, h->cfg.push_pull_interval_ticks);
   const u32 reap = h->cfg.reap_interval_ticks;
   // Ticks launched beyond the first quiescent one must be no-ops (they are rewound).  Anti-entropy rounds and reaper
@@ -654,7 +739,7 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
   auto boundary = [&](u32 t) { return (pp && (t + 1) % pp == 0) || (reap && (t + 1) % reap == 0); };
   const u32 start = h->tick;
   int rc = 0;
-  if (h->cfg.world_size == 1 && !pp && !reap && getenv("SERFSIM_SPECULATE")) {   // measured: no gain over the synchronous loop (the 8 extra no-op ticks cost what the gaps saved); off by default
+  if (h->cfg.world_size == 1 && !pp && !reap && !h->byz_on && getenv("SERFSIM_SPECULATE")) {   // measured: no gain over the synchronous loop (the 8 extra no-op ticks cost what the gaps saved); off by default
     // Pipelined convergence check (single GPU, no anti-entropy / reaper ticks): chunk k+1 is launched before the rows
     // of chunk k are inspected, so the GPU never waits for the host.  Ticks past the first quiescent one are no-ops on
     // a quiescent cluster and are rewound, exactly as in the synchronous loop below.
@@ -714,7 +799,8 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
       // with anti-entropy on, convergence additionally needs a push-pull round that changed nothing but Lamport times
       // (a Left member is re-sent as "leave at status_ltime + 1", serf/delegate.rs:495-510: status_time creeps by design)
       const bool pp_ok = !pp || (((t + 1) % pp) == 0 && r.changed == 0);
-      if (r.pending == 0 && r.edge_updates == 0 && !future_ops(h, t) && pp_ok) {
+      const bool byz_ok = !h->byz_on || r.changed == 0;       // stale entries stay in flight forever: quiescent = no honest traffic and nothing merged
+      if (r.pending == 0 && r.edge_updates == 0 && !future_ops(h, t) && pp_ok && byz_ok) {
         // ticks after t were no-ops on a quiescent cluster: rewind the logical clock to t + 1
         if (h->tick > t + 1) {
           CU(cudaMemsetAsync(h->d_trace + (size_t)(t + 1) * 8, 0, (size_t)(h->tick - t - 1) * 8 * sizeof(u64), h->stream));
@@ -771,10 +857,13 @@ int serfsim_tick_trace(serfsim_t* h, uint32_t first_tick, uint32_t n, serfsim_ti
 
 int serfsim_state_hash(serfsim_t* h, uint64_t* out) {
   if (!h || !out) return fail(SERFSIM_E_INVAL, "null argument");
-  CU(cudaMemsetAsync(h->d_scratch, 0, 8, h->stream));
+  CU(cudaMemsetAsync(h->d_scratch, 0, 4 * 8, h->stream));
   launch_state_hash(h->d_rec, h->d_qword, h->d_node, h->count, h->stride, h->first, h->N, h->R, h->d_scratch, h->stream);
-  CU(cudaMemcpyAsync(out, h->d_scratch, 8, cudaMemcpyDeviceToHost, h->stream));
+  if (h->ue_table.n) launch_ue_summary(h->d_ue_state, h->count, h->first, h->N, h->R, h->ue_table.n, h->d_scratch + 1, h->stream);
+  u64 parts[4] = {0, 0, 0, 0};
+  CU(cudaMemcpyAsync(parts, h->d_scratch, 4 * 8, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  *out = parts[0] + parts[3];                    // records + node words, plus the event records when user events are on
   if (h->cfg.world_size > 1) {
     if (!h->allreduce) return fail(SERFSIM_E_COMM, "world_size > 1: serfsim_comm_set_hooks was not called");
     h->allreduce(h->comm_user, out, 1);
@@ -807,6 +896,149 @@ int serfsim_stats(serfsim_t* h, serfsim_stats_t* o) {
   return 0;
 }
 
+// ---- byzantine injectors (BASELINE configs[4]; model in byz.cuh) ----
+int serfsim_set_byzantine(serfsim_t* h, uint32_t n, const uint32_t* ids, uint32_t delta) {
+  if (!h) return fail(SERFSIM_E_INVAL, "null handle");
+  if (n && !ids) return fail(SERFSIM_E_INVAL, "null ids");
+  if (h->tick != 0 || !h->ops.empty()) return fail(SERFSIM_E_INVAL, "serfsim_set_byzantine: call before any operation is scheduled (or after serfsim_reset)");
+  if (n && h->cfg.push_pull_interval_ticks > 0) return fail(SERFSIM_E_INVAL, "byzantine injectors cannot be combined with push-pull rounds in this version");
+  if (n && h->cfg.world_size > 1 && h->shard_size >= BYZ_FLAG) return fail(SERFSIM_E_INVAL, "byzantine injectors: shards must hold fewer than 2^25 nodes");
+  std::vector<u32> v(ids, ids + n);
+  std::sort(v.begin(), v.end());
+  for (u32 i = 0; i < n; ++i) if (v[i] >= h->N || (i && v[i] == v[i - 1])) return fail(SERFSIM_E_INVAL, "byzantine ids must be distinct node ids");
+  std::vector<u32> mine;                           // every rank is given the global list and keeps the injectors of its shard
+  for (u32 id : v) if (id - h->first < h->count) mine.push_back(id);
+  cudaFree(h->d_byz_ids); h->d_byz_ids = nullptr;
+  h->byz_n = 0; h->byz_delta = delta; h->byz_on = n != 0;
+  if (n) {
+    if (!h->d_anomaly) { CU(cudaMalloc(&h->d_anomaly, h->stride)); CU(cudaMalloc(&h->d_byz_totals, 4 * 8)); }
+    if (!mine.empty()) {
+      CU(cudaMalloc(&h->d_byz_ids, mine.size() * 4));
+      CU(cudaMemcpy(h->d_byz_ids, mine.data(), mine.size() * 4, cudaMemcpyHostToDevice));
+    }
+    CU(cudaMemset(h->d_anomaly, 0, h->stride));
+    CU(cudaMemset(h->d_byz_totals, 0, 4 * 8));
+    h->byz_n = (u32)mine.size();
+  }
+  return 0;
+}
+
+int serfsim_anomaly_flags(serfsim_t* h, uint8_t* out) {
+  if (!h || !out) return fail(SERFSIM_E_INVAL, "null argument");
+  if (!h->byz_on) return fail(SERFSIM_E_INVAL, "no byzantine injectors set (serfsim_set_byzantine)");
+  CU(cudaStreamSynchronize(h->stream));
+  if (h->cfg.world_size > 1) {                     // peers' drain kernels raise flags in this array: wait until every rank has drained
+    if (!h->barrier) return fail(SERFSIM_E_COMM, "world_size > 1: serfsim_comm_set_hooks was not called");
+    h->barrier(h->comm_user);
+  }
+  CU(cudaMemcpy(out, h->d_anomaly, h->count, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int serfsim_byzantine_stats(serfsim_t* h, serfsim_byz_stats_t* o) {
+  if (!h || !o) return fail(SERFSIM_E_INVAL, "null argument");
+  if (!h->byz_on) return fail(SERFSIM_E_INVAL, "no byzantine injectors set (serfsim_set_byzantine)");
+  u64 t[4] = {0, 0, 0, 0};
+  CU(cudaStreamSynchronize(h->stream));
+  if (h->cfg.world_size > 1) {
+    if (!h->barrier || !h->allreduce) return fail(SERFSIM_E_COMM, "world_size > 1: serfsim_comm_set_hooks was not called");
+    h->barrier(h->comm_user);                      // see serfsim_anomaly_flags
+  }
+  CU(cudaMemcpy(t, h->d_byz_totals, 4 * 8, cudaMemcpyDeviceToHost));
+  std::vector<u8> flags(h->count);
+  CU(cudaMemcpy(flags.data(), h->d_anomaly, h->count, cudaMemcpyDeviceToHost));
+  u64 v[3] = {t[0], t[1], 0};
+  for (u8 f : flags) v[2] += f ? 1 : 0;
+  if (h->cfg.world_size > 1) h->allreduce(h->comm_user, v, 3);
+  o->messages = v[0]; o->edge_updates = v[1]; o->flagged = v[2];
+  return 0;
+}
+
+// ---- user events (rules in uevent.cuh) ----
+int serfsim_set_user_events(serfsim_t* h, uint32_t n_events, const uint32_t* content_ids) {
+  if (!h) return fail(SERFSIM_E_INVAL, "null handle");
+  if (n_events > MAX_UEVENTS) return fail(SERFSIM_E_INVAL, "at most SERFSIM_MAX_USER_EVENTS tracked user events");
+  if (n_events && !content_ids) return fail(SERFSIM_E_INVAL, "null content ids");
+  if (h->tick != 0 || !h->ops.empty()) return fail(SERFSIM_E_INVAL, "serfsim_set_user_events: call before any operation is scheduled (or after serfsim_reset)");
+  if (n_events && h->cfg.push_pull_interval_ticks > 0) return fail(SERFSIM_E_INVAL, "user events cannot be combined with push-pull rounds in this version");
+  if (n_events && !h->d_ue_state) {
+    CU(cudaMalloc(&h->d_ue_state, (size_t)h->stride * 16));
+    CU(cudaMalloc(&h->d_ue_inbox[0], (size_t)h->stride * 4));
+    CU(cudaMalloc(&h->d_ue_inbox[1], (size_t)h->stride * 4));
+    CU(cudaMalloc(&h->d_ue_ltime, MAX_UEVENTS * 4));
+    CU(cudaMalloc(&h->d_ue_totals, 8 * 8));
+  }
+  h->ue_table = UeTable{};
+  h->ue_table.n = n_events;
+  for (u32 e = 0; e < n_events; ++e) h->ue_table.content[e] = content_ids[e];
+  int rc = ue_reset(h);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int serfsim_event_time(serfsim_t* h, uint64_t* out) {
+  if (!h || !out) return fail(SERFSIM_E_INVAL, "null argument");
+  if (!h->ue_table.n) return fail(SERFSIM_E_INVAL, "user events are off (serfsim_set_user_events)");
+  launch_ue_extract(h->d_ue_state, h->count, 0, 0, h->d_stage, h->stream);
+  CU(cudaMemcpyAsync(out, h->d_stage, (size_t)h->count * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int serfsim_user_event_seen(serfsim_t* h, uint32_t event, uint8_t* out) {
+  if (!h || !out) return fail(SERFSIM_E_INVAL, "null argument");
+  if (event >= h->ue_table.n) return fail(SERFSIM_E_INVAL, "user event index out of range");
+  launch_ue_extract(h->d_ue_state, h->count, 1, event, h->d_stage, h->stream);
+  CU(cudaMemcpyAsync(out, h->d_stage, (size_t)h->count, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int serfsim_user_event_ltime(serfsim_t* h, uint32_t event, uint64_t* ltime) {
+  if (!h || !ltime) return fail(SERFSIM_E_INVAL, "null argument");
+  if (event >= h->ue_table.n) return fail(SERFSIM_E_INVAL, "user event index out of range");
+  u32 v = 0;
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpy(&v, h->d_ue_ltime + event, 4, cudaMemcpyDeviceToHost));
+  *ltime = v;
+  if (h->cfg.world_size > 1) {                      // the origin's shard stamped it; the others contribute 0 to the sum
+    if (!h->allreduce) return fail(SERFSIM_E_COMM, "world_size > 1: serfsim_comm_set_hooks was not called");
+    const bool scheduled = (h->ue_injected >> event) & 1u;
+    if (!scheduled || h->ue_origin[event] - h->first >= h->count) *ltime = 0;
+    h->allreduce(h->comm_user, ltime, 1);
+  }
+  return 0;
+}
+
+int serfsim_user_event_records(serfsim_t* h, void* out) {
+  if (!h || !out) return fail(SERFSIM_E_INVAL, "null argument");
+  if (!h->ue_table.n) return fail(SERFSIM_E_INVAL, "user events are off (serfsim_set_user_events)");
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpy(out, h->d_ue_state, (size_t)h->count * 16, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int serfsim_user_event_stats(serfsim_t* h, serfsim_uevent_stats_t* o) {
+  if (!h || !o) return fail(SERFSIM_E_INVAL, "null argument");
+  memset(o, 0, sizeof(*o));
+  if (!h->ue_table.n) return fail(SERFSIM_E_INVAL, "user events are off (serfsim_set_user_events)");
+  u64 tot[8] = {0}, sum[3] = {0, 0, 0};
+  CU(cudaMemsetAsync(h->d_scratch, 0, 3 * 8, h->stream));
+  launch_ue_summary(h->d_ue_state, h->count, h->first, h->N, h->R, h->ue_table.n, h->d_scratch, h->stream);
+  CU(cudaMemcpyAsync(sum, h->d_scratch, 3 * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(tot, h->d_ue_totals, 8 * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  u64 v[6] = {tot[0], tot[1], tot[2], tot[3], tot[4], sum[0]};
+  if (h->cfg.world_size > 1) {                      // counters are sums over shards; event_time (a maximum) stays shard-local
+    if (!h->allreduce) return fail(SERFSIM_E_COMM, "world_size > 1: serfsim_comm_set_hooks was not called");
+    h->allreduce(h->comm_user, v, 6);
+  }
+  o->messages = v[0]; o->edge_updates = v[1]; o->delivered = v[2]; o->duplicates = v[3]; o->too_old = v[4];
+  o->event_queue = v[5]; o->event_time = sum[1];
+  return 0;
+}
+
 int serfsim_set_event_cb(serfsim_t* h, serfsim_event_cb cb, void* user) {
   if (!h) return fail(SERFSIM_E_INVAL, "null handle");
   h->cb = cb; h->cb_user = user;
@@ -835,7 +1067,7 @@ int serfsim_tick_times(serfsim_t* h, uint32_t first_tick, uint32_t n, float* ms_
 }
 
 // ---- multi-GPU: CUDA IPC windows ----------------------------------------------------------
-struct comm_blob { cudaIpcMemHandle_t data[2]; cudaIpcMemHandle_t ctrl; u32 win_cap; u32 rank; };
+struct comm_blob { cudaIpcMemHandle_t data[2]; cudaIpcMemHandle_t ctrl; cudaIpcMemHandle_t snap_rec, snap_node, anomaly; u32 win_cap; u32 rank; u32 has_snap; u32 pad; };
 
 size_t serfsim_comm_blob_size(void) { return sizeof(comm_blob); }
 
@@ -845,7 +1077,12 @@ int serfsim_comm_export(serfsim_t* h, void* blob) {
   comm_blob b{};
   for (int par = 0; par < 2; ++par) CU(cudaIpcGetMemHandle(&b.data[par], h->d_win_data[par]));
   CU(cudaIpcGetMemHandle(&b.ctrl, h->d_ctrl));
+  CU(cudaIpcGetMemHandle(&b.anomaly, h->d_anomaly));
   b.win_cap = h->win_cap; b.rank = (u32)h->cfg.rank;
+  if (h->d_snap_rec) {                              // push-pull rounds are on: partners on other GPUs read these
+    CU(cudaIpcGetMemHandle(&b.snap_rec, h->d_snap_rec)); CU(cudaIpcGetMemHandle(&b.snap_node, h->d_snap_node));
+    b.has_snap = 1;
+  }
   memcpy(blob, &b, sizeof(b));
   return 0;
 }
@@ -858,10 +1095,27 @@ int serfsim_comm_connect(serfsim_t* h, const void* blobs) {
   const comm_blob* bs = (const comm_blob*)blobs;
   std::vector<u32*> pc(8, nullptr);
   std::vector<std::vector<u64*>> pd(2, std::vector<u64*>(8, nullptr));
+  std::vector<const uint4*> psr(8, nullptr);
+  std::vector<const u64*> psn(8, nullptr);
+  std::vector<u8*> pan(8, nullptr);
   for (int r = 0; r < W; ++r) {
     if (bs[r].rank != (u32)r || bs[r].win_cap != h->win_cap) return fail(SERFSIM_E_COMM, "blob order / window size mismatch");
-    if (r == h->cfg.rank) { pd[0][r] = h->d_win_data[0]; pd[1][r] = h->d_win_data[1]; pc[r] = h->d_ctrl; continue; }
+    if ((bs[r].has_snap != 0) != (h->d_snap_rec != nullptr)) return fail(SERFSIM_E_COMM, "push_pull_interval_ticks differs between ranks");
+    if (r == h->cfg.rank) { pd[0][r] = h->d_win_data[0]; pd[1][r] = h->d_win_data[1]; pc[r] = h->d_ctrl; psr[r] = h->d_snap_rec; psn[r] = h->d_snap_node; pan[r] = h->d_anomaly; continue; }
     void* ptr = nullptr;
+    {
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, bs[r].anomaly, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return fail(SERFSIM_E_COMM, std::string("cudaIpcOpenMemHandle(flags): ") + cudaGetErrorString(e));
+      h->ipc_opened.push_back(ptr); pan[r] = (u8*)ptr;
+    }
+    if (bs[r].has_snap) {
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, bs[r].snap_rec, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return fail(SERFSIM_E_COMM, std::string("cudaIpcOpenMemHandle(snapshot): ") + cudaGetErrorString(e));
+      h->ipc_opened.push_back(ptr); psr[r] = (const uint4*)ptr;
+      e = cudaIpcOpenMemHandle(&ptr, bs[r].snap_node, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return fail(SERFSIM_E_COMM, std::string("cudaIpcOpenMemHandle(snapshot): ") + cudaGetErrorString(e));
+      h->ipc_opened.push_back(ptr); psn[r] = (const u64*)ptr;
+    }
     for (int par = 0; par < 2; ++par) {
       cudaError_t e = cudaIpcOpenMemHandle(&ptr, bs[r].data[par], cudaIpcMemLazyEnablePeerAccess);
       if (e != cudaSuccess) return fail(SERFSIM_E_COMM, std::string("cudaIpcOpenMemHandle(window): ") + cudaGetErrorString(e));
@@ -873,6 +1127,11 @@ int serfsim_comm_connect(serfsim_t* h, const void* blobs) {
   }
   for (int par = 0; par < 2; ++par) CU(cudaMemcpy(h->d_peer_data[par], pd[par].data(), sizeof(u64*) * 8, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(h->d_peer_ctrl, pc.data(), sizeof(u32*) * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_peer_anomaly, pan.data(), sizeof(void*) * 8, cudaMemcpyHostToDevice));
+  if (h->d_snap_rec) {
+    CU(cudaMemcpy(h->d_peer_snap_rec, psr.data(), sizeof(void*) * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_peer_snap_node, psn.data(), sizeof(void*) * 8, cudaMemcpyHostToDevice));
+  }
   h->barrier(h->comm_user);          // every rank has mapped every window before the first tick writes into one
   h->connected = true;
   return 0;

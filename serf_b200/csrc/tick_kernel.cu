@@ -24,6 +24,7 @@
 #include <cstdlib>
 
 #include "tick_kernel.cuh"
+#include "byz.cuh"
 
 namespace sfs {
 
@@ -83,8 +84,8 @@ inline u32 ld_u32_stream(const u32* ptr, u64) { return *ptr; }
 inline void st_u32_stream(u32* ptr, u32 v, u64) { *ptr = v; }
 inline void st_u64_stream(u64* ptr, u64 v, u64) { *ptr = v; }
 inline void red_max_resident(u32* ptr, u32 v, u64) { if (v > *ptr) *ptr = v; }
-inline void st_release_sys(u32* ptr, u32 v) { *ptr = v; }
-inline u32 ld_acquire_sys(const u32* ptr) { return *ptr; }
+inline void st_release_sys(u32* ptr, u32 v) { __atomic_store_n(ptr, v, __ATOMIC_RELEASE); }     // peers are other threads of the test process
+inline u32 ld_acquire_sys(const u32* ptr) { return __atomic_load_n(ptr, __ATOMIC_ACQUIRE); }
 #endif
 
 #ifndef SERFSIM_EMU
@@ -725,8 +726,20 @@ __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__
     philox4x32_10(p.tick, v, 0, DOMAIN_PUSHPULL, p.seed_lo, p.seed_hi, w);
     const u32 u = p.col[row0 + (((w[0] & 0xffffu) * deg) >> 16)];
     if (u == v) continue;
-    const u32 ul = u - p.first;                               // single-GPU only (checked by the host)
-    const u64 nu = snap_node[ul];
+    // the partner may live in another shard: its rank's snapshot is read through the peer mapping (the host
+    // separates "every rank has taken its snapshot" and "every rank has finished reading" with barriers)
+    u32 ul = u - p.first;
+    const u64* part_node = snap_node;
+    const uint4* part_rec = snap_rec;
+    u32 part_stride = p.stride;
+    if (p.world > 1) {
+      const u32 shard = u / p.shard_size;
+      ul = u - shard * p.shard_size;
+      part_node = p.snap_node_peer[shard]; part_rec = p.snap_rec_peer[shard];
+      const u32 cnt = min(p.shard_size, p.n_global - shard * p.shard_size);
+      part_stride = ((cnt + BLOCK - 1) / BLOCK) * BLOCK;
+    }
+    const u64 nu = part_node[ul];
     if (!(nu & NS_UP)) continue;
     u32 clock = (u32)ns;
     const u32 sstate = (u32)(ns >> 40) & 3;
@@ -735,14 +748,14 @@ __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__
     bool any_pending = false;
     const u32 wmask = p.watch[vl];
     for (u32 s = 0; s < p.R; ++s) {
-      const size_t iv = (size_t)s * p.stride + vl, iu = (size_t)s * p.stride + ul;
+      const size_t iv = (size_t)s * p.stride + vl, iu = (size_t)s * part_stride + ul;
       const uint4 a0 = p.rec[2 * iv];
       uint4 b0 = p.rec[2 * iv + 1];
       const u32 q0 = p.qword[iv];
       merge_queue_word(b0, q0);
       Rec r, q;
       unpack(a0, b0, r);
-      unpack(snap_rec[2 * iu], snap_rec[2 * iu + 1], q);
+      unpack(part_rec[2 * iu], part_rec[2 * iu + 1], q);
       const bool self = (p.subj[s] == v);
       const bool was = (r.txl | r.txj | r.txm) || r.mlstate == ML_SUSPECT || (p.probe_every && ((p.down_mask >> s) & 1) && !self && ((wmask >> s) & 1) && r.mlstate == ML_ALIVE);
       if (q.flags & 1) {
@@ -820,11 +833,30 @@ __global__ void __launch_bounds__(BLOCK) drain_kernel(const __grid_constant__ Dr
     const u64* w = p.win_data + (size_t)src * p.win_cap;
     for (u32 i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
       const u64 e = __ldcg(w + i);
-      const u32 val1 = (u32)(e >> 32), s = (u32)(e >> 28) & 15, kind = (u32)(e >> 26) & 3, dl = (u32)e & ((1u << 26) - 1);
+      const u32 val1 = (u32)(e >> 32), s = (u32)(e >> 28) & 15, kind = (u32)(e >> 26) & 3;
+      u32 dl = (u32)e & ((1u << 26) - 1);
+      const bool byz = p.byz_on && (dl & BYZ_FLAG);
+      if (byz) dl &= ~BYZ_FLAG;
+      if (byz && kind == 3 && s == BYZ_ANNOT_SLOT) continue;           // third entry of a triple: read by the thread holding the first
       if (dl < p.n_local && s < p.R && kind < 3) {
         atomicMax(p.inbox_wr + ((size_t)(kind * p.R + s)) * p.stride + dl, val1);
         if (mark) p.hot_wr[dl >> TILE_SHIFT] = 1;
         seen |= 1u << kind;
+        if (byz && kind < 2 && i + 2 < n) {                            // first entry of a triple: judge it against MY record, flag the sender in ITS shard
+          const u64 e1 = __ldcg(w + i + 1), e2 = __ldcg(w + i + 2);
+          const u32 src = (u32)(e2 >> 32) - 1u;
+          ByzEntries be{};
+          be.serf_lt = val1 - 1u; be.ml_inc = ((u32)(e1 >> 32) - 1u) >> 6;
+          if (p.node_state[dl] & NS_UP) {
+            const size_t iv = (size_t)s * p.stride + dl;
+            Rec q;
+            unpack(p.rec[2 * iv], p.rec[2 * iv + 1], q);
+            if (byz_anomalous(q, be, p.byz_delta)) { const u32 sh = src / p.shard_size; p.peer_anomaly[sh][src - sh * p.shard_size] = 1; }
+          }
+        }
+      } else if (dl < p.n_local && kind == 3 && s < p.ue_n && val1) {   // user event s arrived: one bit, and the time its origin stamped
+        atomicOr(p.ue_inbox_wr + dl, 1u << s);
+        p.ue_ltime[s] = val1 - 1;                      // every copy carries the same value; this shard learns it no later than the event itself
       }
       else *p.overflow = 3;
     }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "record.cuh"
+#include "uevent.cuh"
 
 // Kernel launch in one spelling for nvcc and for the host build of tests/emu (which defines its own SFS_LAUNCH):
 //   SFS_LAUNCH(grid, block, dynamic_smem_bytes, stream, kernel<template, args>)(kernel arguments);
@@ -11,6 +12,12 @@
 constexpr int SFS_SMS = 148;                 // B200: grid-stride helper kernels are sized in multiples of the SM count
 #else
 constexpr int SFS_SMS = 1;
+#endif
+// Coverage probes of the host build (tests assert that a code path was actually taken); nothing under nvcc.
+#ifdef SERFSIM_EMU
+#define SFS_PROBE(i) (emu::probes[i]++)
+#else
+#define SFS_PROBE(i) ((void)0)
 #endif
 
 namespace sfs {
@@ -50,6 +57,9 @@ struct TickParams {
   u32 world, rank, shard_size, win_cap;
   u64* const* win_data;       // [world] peer windows of this exchange parity; my segment starts at rank·win_cap
   u32* send_count;            // [world] entries written so far into each peer's window (local counters)
+  // sharded push-pull rounds: every rank's end-of-tick snapshot, indexed by shard (null when world == 1).  New members go
+  // at the end: the tick kernels do not read them and keep their parameter offsets (and their SASS) unchanged.
+  const uint4* const* snap_rec_peer; const u64* const* snap_node_peer;
 };
 
 struct PublishParams {        // after the tick kernel: tell every peer how much was written, then raise its flag
@@ -67,6 +77,14 @@ struct DrainParams {
   u8* hot_wr;
   u32* kinds_cur;             // [4] kind counters of this tick (received kinds are added so the next tick reads their planes)
   u32* overflow;
+  // byzantine triples (see ByzParams): judged here against the receiver's end-of-tick record
+  u32 byz_on, byz_delta, shard_size;
+  const uint4* rec; const u64* node_state;
+  u8* const* peer_anomaly;    // [world] every rank's sender-flag array
+  // user-event entries (kind 3: slot = tracked event, value = its Lamport time + 1); null / 0 when user events are off
+  u32 ue_n;
+  u32* ue_inbox_wr;
+  u32* ue_ltime;
 };
 
 void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st);
@@ -82,6 +100,56 @@ void launch_summary(const uint4* rec, const u32* qword, const u64* node_state, u
 int tick_grid_size(u32 n_local, int ctas_per_sm);
 void launch_compute_watch(const u32* row_ptr, const u32* col, const u32* subj_dev, u32 R, u32 first, u32 n_local, u16* watch, cudaStream_t st);
 void launch_apply_watch(const u16* watch, u32 n_local, u8* busy, u8* hot0, u8* hot1, cudaStream_t st);
+
+// User-event tick (uevent_kernel.cu; rules in uevent.cuh)
+struct UeParams {
+  u32 n_local, first, n_global, R, fanout, tick, seed_lo, seed_hi, limit;
+  u32 ev_begin, ev_end;
+  UeTable table;
+  uint4* state;               // [n_local] 16-byte event records
+  u32* inbox_rd;              // [n_local] arrived-event masks written during the previous tick (consumed and cleared)
+  u32* inbox_wr;              // [n_local] masks being filled by this tick's sends
+  u32* ltime;                 // [MAX_UEVENTS] Lamport time of each tracked event, stamped by its origin
+  const u64* node_state;      // membership node words (up flag), pre-operation
+  const u8* busy;             // bit 1: a host operation targets the node this tick
+  const u32* row_ptr; const u32* col;
+  const u32* ev_node; const u32* ev_op; const u32* ev_slot;
+  u64* row;                   // this tick's trace row (shared with the membership kernel)
+  u64* totals;                // run totals: 0 messages, 1 edges, 2 delivered, 3 duplicates, 4 too_old
+  u32* overflow;
+  // sharded runs: a target outside [first, first + n_local) gets one window entry per event (kind 3) over NVLink
+  u32 world, rank, shard_size, win_cap;
+  u64* const* win_data;       // [world] peers' receive windows of this exchange parity
+  u32* send_count;            // [world] entries written into each peer's window this tick (shared with the tick kernel)
+};
+void launch_uevent(const UeParams& p, bool trace, cudaStream_t st);
+void launch_ue_init(uint4* state, u32 n_local, cudaStream_t st);
+void launch_ue_extract(const uint4* state, u32 n_local, int what, u32 e, void* out, cudaStream_t st);
+void launch_ue_summary(const uint4* state, u32 n_local, u32 first, u32 n_global, u32 R, u32 n_events, u64* out, cudaStream_t st);
+
+// Byzantine injectors (byz_kernel.cu; model in byz.cuh)
+struct ByzParams {
+  u32 n_byz, first, R, stride, fanout, tick, seed_lo, seed_hi, delta;
+  const u32* ids;             // [n_byz] byzantine node ids (ascending)
+  const uint4* rec;           // end-of-tick records
+  const u64* node_state;
+  const u32* row_ptr; const u32* col;
+  u32* inbox_wr;              // the planes this tick's membership kernel filled
+  u8* hot_wr;
+  u32* kinds_cur;
+  u8* anomaly;                // [n_local] sender flags
+  u64* totals;                // 0 injected entries, 1 injected (peer, subject) pairs
+  // sharded runs: a peer in another shard gets a TRIPLE of window entries — serf entry and memberlist entry, both with
+  // BYZ_FLAG set in the destination field, then an annotation (kind 3, slot 15) carrying the sender's global id + 1 —
+  // and the receiving shard's drain kernel judges it against ITS record and raises the flag in the sender's shard.
+  u32 n_local, world, rank, shard_size, win_cap;
+  u64* const* win_data;
+  u32* send_count;
+  u32* overflow;
+};
+constexpr u32 BYZ_FLAG = 1u << 25;          // in the 26-bit destination field of a window entry (shards hold < 2^25 nodes when injectors are on)
+constexpr u32 BYZ_ANNOT_SLOT = 15;
+void launch_byz(const ByzParams& p, cudaStream_t st);
 
 enum { EXTRACT_STATUS = 0, EXTRACT_STATUS_LTIME = 1, EXTRACT_CLOCK = 2, EXTRACT_INC = 3, EXTRACT_ML = 4 };
 

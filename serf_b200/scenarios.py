@@ -10,8 +10,11 @@ from .sim import Op, full_mesh_graph, random_regular_graph, small_world_graph
 
 
 class Scenario:
-    def __init__(self, name, n, slots, topology, subjects, ops, cfg=None, max_ticks=2000):
+    def __init__(self, name, n, slots, topology, subjects, ops, cfg=None, max_ticks=2000, user_events=None, byzantine=None, delta=2):
         self.name, self.n, self.slots = name, n, slots
+        self.byzantine = None if byzantine is None else np.asarray(byzantine, dtype=np.uint32)   # stale-record injector ids
+        self.delta = delta
+        self.user_events = None if user_events is None else np.asarray(user_events, dtype=np.uint32)   # content id per tracked user event
         self.row_ptr, self.col = topology
         self.subjects = np.asarray(subjects, dtype=np.uint32)
         self.ops = list(ops)              # (tick, op, node, slot)
@@ -25,6 +28,10 @@ class Scenario:
         sim = factory(self.n, self.slots, **cfg)
         sim.set_topology(self.row_ptr, self.col)
         sim.set_subjects(self.subjects)
+        if self.user_events is not None:
+            sim.set_user_events(self.user_events)
+        if self.byzantine is not None:
+            sim.set_byzantine(self.byzantine, self.delta)
         self.schedule(sim)
         return sim
 
@@ -123,3 +130,52 @@ def fuzz(seed, n=None, slots=None):
         used.add((t, node))
         ops.append((t, int(kind), node, s))
     return Scenario(f"fuzz_{seed}", n, slots, topo, subjects, ops, cfg, max_ticks=6000)
+
+
+def user_event_storm(n=100_000, degree=16, fanout=3, seed=1, graph_seed=7, n_events=4, spacing=3, alias=False, churn=0, with_leave=False):
+    """`n_events` tracked user events fired by different origins `spacing` ticks apart
+    (Serf::user_event, serf/api.rs:241-299).  alias=True gives events 0 and 1 the same (name, payload) and fires them
+    in the same tick from origins with equal event clocks, so they land in the same ring slot with equal content and
+    every node keeps exactly one of the two.  `churn` nodes crash during the storm (some return); with_leave adds a
+    membership leave so both kinds of broadcast share the gossip packets."""
+    rng = np.random.Generator(np.random.Philox(seed + 4242))
+    content = np.arange(1, n_events + 1, dtype=np.uint32) * np.uint32(17)
+    if alias and n_events >= 2:
+        content[1] = content[0]
+    origins = rng.choice(np.arange(2, n), size=n_events, replace=False)
+    ops = []
+    for e in range(n_events):
+        t = 0 if (alias and e < 2) else e * spacing
+        ops.append((t, Op.USER_EVENT, int(origins[e]), e))
+    busy = {(t, node) for (t, _, node, _) in ops}
+    pool = np.setdiff1d(np.arange(2, n), origins)
+    for node in rng.choice(pool, size=min(churn, pool.size), replace=False):
+        t_fail = int(rng.integers(0, max(1, n_events * spacing + 4)))
+        if (t_fail, int(node)) in busy:
+            continue
+        ops.append((t_fail, Op.FAIL, int(node), 0))
+        if rng.random() < 0.5:
+            ops.append((t_fail + 2 + int(rng.integers(0, 6)), Op.REJOIN, int(node), 0))
+    subjects = [0]
+    if with_leave:
+        ops.append((1, Op.LEAVE, 0, 0))
+    return Scenario(f"user_events_{n}_e{n_events}", n, 1, random_regular_graph(n, degree, graph_seed), subjects, ops,
+                    dict(fanout=fanout, seed=seed), max_ticks=3000, user_events=content)
+
+
+def byzantine_injectors(n=100_000, degree=16, fanout=4, frac=0.01, delta=2, seed=1, graph_seed=7, slots=2, churn=True):
+    """BASELINE configs[4] shape: random graph, `frac` of the nodes re-inject stale (status_time - delta,
+    incarnation - delta) copies of their views every tick; the run carries a leave, a crash with probing (so
+    incarnations and Lamport times actually move) and a rejoin."""
+    rng = np.random.Generator(np.random.Philox(seed + 777))
+    subjects = [3, n // 2][:slots]
+    byz = rng.choice(np.arange(8, n), size=max(1, int(n * frac)), replace=False)
+    byz = byz[~np.isin(byz, subjects)]
+    ops = [(0, Op.LEAVE, subjects[0], 0)]
+    if slots > 1 and churn:
+        ops += [(2, Op.FAIL, subjects[1], 0), (30, Op.REJOIN, subjects[1], 0)]
+    cfg = dict(fanout=fanout, seed=seed, init_clock=12)      # Lamport times well above delta, so stale copies beat the bootstrap views
+    if churn:
+        cfg.update(suspicion_mult=2, suspicion_max_timeout_mult=2, probe_interval_ticks=2)
+    return Scenario(f"byzantine_{n}_f{frac}", n, slots, random_regular_graph(n, degree, graph_seed), subjects, ops, cfg,
+                    max_ticks=4000, byzantine=byz, delta=delta)

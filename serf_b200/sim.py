@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class MemberStatus(enum.IntEnum):      # types/member.rs:54-58
@@ -39,6 +39,7 @@ class Op(enum.IntEnum):                # SERFSIM_OP_*
     FORCE_LEAVE = 3
     FAIL = 4
     REJOIN = 5
+    USER_EVENT = 6                     # Serf::user_event, serf/api.rs:241-299
 
 
 class Config(C.Structure):             # serfsim_config_t
@@ -57,6 +58,24 @@ class Stats(C.Structure):              # serfsim_stats_t
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class ByzantineStats(C.Structure):     # serfsim_byz_stats_t
+    _fields_ = [(n, C.c_uint64) for n in ("messages", "edge_updates", "flagged")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class UserEventStats(C.Structure):     # serfsim_uevent_stats_t
+    _fields_ = [(n, C.c_uint64) for n in ("messages", "edge_updates", "delivered", "duplicates", "too_old", "event_queue", "event_time")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+UEVENT_RECORD_DTYPE = np.dtype([("event_clock", "<u4"), ("seen", "u1"), ("first", "u1"), ("pad", "<u2"), ("tx", "u1", (8,))])
+assert UEVENT_RECORD_DTYPE.itemsize == 16
 
 
 class TickRow(C.Structure):            # serfsim_tick_row_t
@@ -100,6 +119,15 @@ SIGNATURES = {
     "stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "tick_trace": (C.c_int, [_vp, _u32, _u32, _vp]),
     "state_hash": (C.c_int, [_vp, C.POINTER(_u64)]),
+    "set_byzantine": (C.c_int, [_vp, _u32, _vp, _u32]),
+    "anomaly_flags": (C.c_int, [_vp, _vp]),
+    "byzantine_stats": (C.c_int, [_vp, C.POINTER(ByzantineStats)]),
+    "set_user_events": (C.c_int, [_vp, _u32, _vp]),
+    "event_time": (C.c_int, [_vp, _vp]),
+    "user_event_seen": (C.c_int, [_vp, _u32, _vp]),
+    "user_event_ltime": (C.c_int, [_vp, _u32, C.POINTER(_u64)]),
+    "user_event_records": (C.c_int, [_vp, _vp]),
+    "user_event_stats": (C.c_int, [_vp, C.POINTER(UserEventStats)]),
 }
 PRODUCT_ONLY = {
     "serfsim_abi_version": (_u32, []),
@@ -258,6 +286,41 @@ class GossipSim:
     def incarnation(self, slot=0): return self._get("incarnation", np.uint32, slot)
     def ml_state(self, slot=0): return self._get("ml_state", np.uint8, slot)
     def records(self, slot=0): return self._get("records", RECORD_DTYPE, slot)
+
+    # -- byzantine stale-record injectors (BASELINE configs[4]) ------------------------------
+    def set_byzantine(self, ids, delta=2):
+        a = np.ascontiguousarray(ids, dtype=np.uint32)
+        self._check(self._fn("set_byzantine")(self._h, int(a.size), a.ctypes.data if a.size else None, int(delta)))
+
+    def anomaly_flags(self): return self._get("anomaly_flags", np.uint8)
+
+    def byzantine_stats(self):
+        s = ByzantineStats()
+        self._check(self._fn("byzantine_stats")(self._h, C.byref(s)))
+        return s.as_dict()
+
+    # -- user events (Serf::user_event, serf/api.rs:241-299) ------------------------------
+    def set_user_events(self, content_ids):
+        a = np.ascontiguousarray(content_ids, dtype=np.uint32)
+        self._ue_keep = a
+        self._check(self._fn("set_user_events")(self._h, int(a.size), a.ctypes.data if a.size else None))
+
+    def user_event(self, node, event, tick=0):
+        self.inject(tick, Op.USER_EVENT, node, event)
+
+    def event_time(self): return self._get("event_time", np.uint64)
+    def user_event_seen(self, event): return self._get("user_event_seen", np.uint8, event)
+    def user_event_records(self): return self._get("user_event_records", UEVENT_RECORD_DTYPE)
+
+    def user_event_ltime(self, event):
+        t = _u64()
+        self._check(self._fn("user_event_ltime")(self._h, int(event), C.byref(t)))
+        return t.value
+
+    def user_event_stats(self):
+        s = UserEventStats()
+        self._check(self._fn("user_event_stats")(self._h, C.byref(s)))
+        return s.as_dict()
 
     def stats(self):                                                                           # Serf::stats
         s = Stats()

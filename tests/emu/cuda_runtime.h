@@ -7,7 +7,8 @@
 // Nothing under serf_b200/ includes or links this; the product library is built by nvcc from the same sources and
 // fails with SERFSIM_E_NO_DEVICE without a GPU.
 //
-// Execution model: one CTA at a time; every CUDA thread of the CTA is a fiber (ucontext) on one OS thread; fibers
+// Execution model (per rank; multi-rank runs give every rank its own OS thread and the engine state is thread-local,
+// peer windows are plain shared host memory with real acquire/release on the flags): one CTA at a time; every CUDA thread of the CTA is a fiber on one OS thread; fibers
 // switch only at collectives (__syncthreads, warp shuffles / votes), where they wait for the other lanes exactly like
 // the hardware does.  __shared__ becomes `static` (CTAs run one after another).  Atomics are plain read-modify-writes.
 #pragma once
@@ -32,7 +33,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __grid_constant__
-#define __shared__ static
+#define __shared__ static thread_local              // one CTA at a time PER RANK THREAD (multi-rank runs: one OS thread per rank)
 #define __align__(n) __attribute__((aligned(n)))
 
 // ---- vector types ----
@@ -45,13 +46,14 @@ inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 // ---- engine ----
 namespace emu {
 struct LaneCtx { uint3 tid, bid, bdim, gdim; };
-extern LaneCtx* cur;
+extern thread_local LaneCtx* cur;
 void run_grid(unsigned grid, unsigned block, const std::function<void()>& body);
 void cta_barrier();
 unsigned long long warp_exchange(unsigned long long v, int src_lane_xor, int src_lane_abs);   // returns the value of lane (abs >= 0 ? abs : lane ^ xor)
 unsigned warp_ballot(bool pred);
 unsigned warp_reduce_or(unsigned v);
 unsigned lane_id();
+extern unsigned long probes[32];                              // coverage probes: SFS_PROBE(i) in the kernels, read by tests through emu_probe()
 
 template <class F>
 struct Bound {
@@ -83,7 +85,10 @@ inline unsigned __shfl_xor_sync(unsigned, unsigned v, int o) { return (unsigned)
 inline int __shfl_xor_sync(unsigned, int v, int o) { return (int)emu::warp_exchange((unsigned)v, o, -1); }
 inline unsigned long __shfl_xor_sync(unsigned, unsigned long v, int o) { return (unsigned long)emu::warp_exchange(v, o, -1); }
 inline unsigned long long __shfl_xor_sync(unsigned, unsigned long long v, int o) { return emu::warp_exchange(v, o, -1); }
-inline unsigned __shfl_sync(unsigned, unsigned v, int src) { return (unsigned)emu::warp_exchange(v, 0, src & 31); }
+inline unsigned __shfl_sync(unsigned mask, unsigned v, int src) {
+  if (mask == (1u << emu::lane_id())) return v;              // the single-lane groups __match_any_sync hands out above
+  return (unsigned)emu::warp_exchange(v, 0, src & 31);
+}
 inline unsigned __ballot_sync(unsigned, int pred) { return emu::warp_ballot(pred != 0); }
 inline int __any_sync(unsigned, int pred) { return emu::warp_ballot(pred != 0) != 0; }
 inline unsigned __reduce_or_sync(unsigned, unsigned v) { return emu::warp_reduce_or(v); }
@@ -95,8 +100,8 @@ inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline T __ldcg(const T* p) { return *p; }
-inline void __threadfence() {}
-inline void __threadfence_system() {}
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
@@ -163,6 +168,7 @@ inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) {
 }
 inline cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
-inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
-inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+// "IPC" between ranks that are threads of one process: the handle is the pointer itself
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void** out, cudaIpcMemHandle_t h, unsigned) { memcpy(out, h.reserved, sizeof(*out)); return cudaSuccess; }
 inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }

@@ -1,5 +1,4 @@
 // tests/emu/emu_engine.cpp — fiber scheduler of the CUDA-on-CPU shim (see cuda_runtime.h).  Test infrastructure only.
-#include <ucontext.h>
 #include <sys/mman.h>
 
 #include <cstdio>
@@ -9,15 +8,46 @@
 #define SERFSIM_EMU 1
 #include "cuda_runtime.h"
 
+#if !defined(__x86_64__)
+#error "tests/emu: the fiber switch below is written for x86-64 (System V ABI)"
+#endif
+// Minimal fiber switch (no signal-mask system call, unlike swapcontext): save the callee-saved registers and the stack
+// pointer of the running fiber, load those of the next one.  A new fiber's stack is primed so that the first switch
+// "returns" into its entry function.
+extern "C" void emu_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size emu_switch,.-emu_switch
+)");
+
 namespace emu {
 
-LaneCtx* cur = nullptr;
+thread_local LaneCtx* cur = nullptr;
+unsigned long probes[32] = {0};
 
 namespace {
 constexpr int MAX_THREADS = 1024;
 constexpr size_t STACK = 256 * 1024;
 struct Lane {
-  ucontext_t ctx;
+  void* sp = nullptr;        // saved stack pointer while the fiber is not running
   LaneCtx lc;
   bool done = false;
   int wait = 0;              // 0 runnable, 1 warp rendezvous, 2 CTA barrier
@@ -30,13 +60,18 @@ struct Warp {
   unsigned long long buf[2][32];
   unsigned votes[2];
 };
-Lane lanes[MAX_THREADS];
-Warp warps[MAX_THREADS / 32];
-int cta_live = 0, cta_arrived = 0;
-unsigned cta_gen = 0;
-ucontext_t sched_ctx;
-Lane* cur_lane = nullptr;
-const std::function<void()>* body = nullptr;
+struct Engine {                     // everything a rank thread needs to run kernels; created on first use
+  Lane lanes[MAX_THREADS];
+  Warp warps[MAX_THREADS / 32];
+};
+thread_local Engine* eng = nullptr;
+#define lanes (eng->lanes)
+#define warps (eng->warps)
+thread_local int cta_live = 0, cta_arrived = 0;
+thread_local unsigned cta_gen = 0;
+thread_local void* sched_sp = nullptr;
+thread_local Lane* cur_lane = nullptr;
+thread_local const std::function<void()>* body = nullptr;
 
 void release_check(Warp& w) { if (w.live > 0 && w.arrived >= w.live) { w.arrived = 0; w.gen++; } }
 void cta_release_check() { if (cta_live > 0 && cta_arrived >= cta_live) { cta_arrived = 0; cta_gen++; } }
@@ -48,7 +83,8 @@ void lane_entry() {
   Warp& w = warps[l->lc.tid.x / 32];
   w.live--; cta_live--;                       // an exited thread no longer takes part in collectives
   release_check(w); cta_release_check();
-  swapcontext(&l->ctx, &sched_ctx);
+  emu_switch(&l->sp, sched_sp);
+  __builtin_unreachable();                    // a finished fiber is never resumed
 }
 
 void warp_rendezvous(Warp& w) {
@@ -56,7 +92,7 @@ void warp_rendezvous(Warp& w) {
   const unsigned g = w.gen;
   if (++w.arrived >= w.live) { w.arrived = 0; w.gen++; return; }
   l->wait = 1; l->wait_gen = g;
-  swapcontext(&l->ctx, &sched_ctx);           // resumed by the scheduler once w.gen has moved on
+  emu_switch(&l->sp, sched_sp);               // resumed by the scheduler once w.gen has moved on
 }
 }  // namespace
 
@@ -67,7 +103,7 @@ void cta_barrier() {
   const unsigned g = cta_gen;
   if (++cta_arrived >= cta_live) { cta_arrived = 0; cta_gen++; return; }
   l->wait = 2; l->wait_gen = g;
-  swapcontext(&l->ctx, &sched_ctx);
+  emu_switch(&l->sp, sched_sp);
 }
 
 // Double-buffered by rendezvous generation: a lane can be at most one collective ahead of the slowest lane of its warp.
@@ -100,6 +136,7 @@ unsigned warp_reduce_or(unsigned v) {
 void run_grid(unsigned grid, unsigned block, const std::function<void()>& fn) {
   if (block == 0 || block > (unsigned)MAX_THREADS) { fprintf(stderr, "emu: bad block size %u\n", block); abort(); }
   if (cur_lane) { fprintf(stderr, "emu: nested kernel launch\n"); abort(); }
+  if (!eng) eng = new Engine();
   body = &fn;
   for (unsigned t = 0; t < block; ++t)
     if (!lanes[t].stack) {
@@ -116,9 +153,13 @@ void run_grid(unsigned grid, unsigned block, const std::function<void()>& fn) {
       l.done = false; l.wait = 0;
       l.lc.tid = uint3{t, 0, 0}; l.lc.bid = uint3{b, 0, 0}; l.lc.bdim = uint3{block, 1, 1}; l.lc.gdim = uint3{grid, 1, 1};
       warps[t / 32].live++;
-      getcontext(&l.ctx);
-      l.ctx.uc_stack.ss_sp = l.stack; l.ctx.uc_stack.ss_size = STACK; l.ctx.uc_link = nullptr;
-      makecontext(&l.ctx, lane_entry, 0);
+      // prime the stack: six callee-saved registers (zero), then lane_entry as the address emu_switch returns to; the
+      // slot above it is the (never used) return address of lane_entry, which puts rsp at 16n + 8 on entry as the ABI asks
+      void** top = reinterpret_cast<void**>(l.stack + STACK);
+      top[-1] = nullptr;
+      top[-2] = reinterpret_cast<void*>(&lane_entry);
+      for (int k = 3; k <= 8; ++k) top[-k] = nullptr;
+      l.sp = &top[-8];
     }
     unsigned remaining = block;
     while (remaining) {
@@ -130,7 +171,7 @@ void run_grid(unsigned grid, unsigned block, const std::function<void()>& fn) {
         if (l.wait == 2 && cta_gen == l.wait_gen) continue;
         l.wait = 0;
         cur_lane = &l; cur = &l.lc;
-        swapcontext(&sched_ctx, &l.ctx);
+        emu_switch(&sched_sp, l.sp);
         progressed = true;
         if (l.done) --remaining;
       }
@@ -141,3 +182,6 @@ void run_grid(unsigned grid, unsigned block, const std::function<void()>& fn) {
 }
 
 }  // namespace emu
+
+extern "C" __attribute__((visibility("default"))) unsigned long emu_probe(int i) { return emu::probes[i & 31]; }
+extern "C" __attribute__((visibility("default"))) void emu_probe_reset() { for (auto& p : emu::probes) p = 0; }
