@@ -157,6 +157,7 @@ struct serfsim {
   size_t l2_persist_max = 0, l2_window_max = 0;
   bool l2_window = false;           // SERFSIM_L2_WINDOW=1: stream access-policy window over the inbox being written
   bool no_skip = false;             // SERFSIM_NO_SKIP=1: process every tile every tick (A/B measurements)
+  bool compact = true;              // SERFSIM_COMPACT=0: tile-by-tile walk in unsaturated ticks too (A/B measurements)
   std::vector<cudaEvent_t> tick_ev;      // 2 per tick when tick_timing
   std::vector<cudaEvent_t> mid_ev;       // after the tick kernel (multi-GPU breakdown, SERFSIM_XTIMING=1)
 };
@@ -253,6 +254,7 @@ int launch_ticks(serfsim* h, u32 n) {
     p.tombstone_ticks = h->cfg.tombstone_timeout_ticks; p.reconnect_ticks = h->cfg.reconnect_timeout_ticks; p.intent_ticks = h->cfg.recent_intent_timeout_ticks;
     p.stride = h->stride; p.n_tiles = h->n_tiles; p.tiles_per_cta = (h->n_tiles + h->grid - 1) / h->grid;
     p.force_all = (h->cfg.trace != 0) || h->no_skip || p.reap_now;
+    p.compact = h->compact ? 1u : 0u;
     const u32 xpar = h->xepoch & 1;
     p.world = (u32)h->cfg.world_size; p.rank = (u32)h->cfg.rank; p.shard_size = h->shard_size; p.win_cap = h->win_cap;
     p.win_data = h->d_peer_data[xpar]; p.send_count = h->d_send_count;
@@ -581,6 +583,7 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
     if (getenv("SERFSIM_VERBOSE")) fprintf(stderr, "serfsim: L2 persisting max %d B, window max %d B, persist %d window %d\n", max_persist, max_window, want, (int)h->l2_window);
   }
   if (const char* e = getenv("SERFSIM_NO_SKIP")) h->no_skip = atoi(e) != 0;
+  if (const char* e = getenv("SERFSIM_COMPACT")) h->compact = atoi(e) != 0;
   if (cfg->world_size > 1) {
     // receive windows: one segment per peer; expected entries per tick and pair ≈ shard · fanout · R · kinds / world
     if (cfg->world_size > 8) return bail(fail(SERFSIM_E_INVAL, "world_size > 8"));

@@ -537,6 +537,69 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
     hot_s[i] = (f || all_hot) ? 1 : 0;
   }
   __syncthreads();
+  // Unsaturated ticks (ramp-up and tail of a dissemination: a few per cent of the nodes have anything to do, spread
+  // one or two per warp): a tile-by-tile walk pays one chain of dependent round trips (state → row → peers) per TILE
+  // for a handful of active lanes.  Instead the CTA scans GROUP hot tiles at once — the 13 "anything to do?" bytes
+  // of every node, all loads in flight together — compacts the active nodes into a shared-memory list and runs the
+  // node logic on dense blocks of 256 list entries: one chain per 256 ACTIVE nodes.  Nodes are independent within a
+  // tick and every cross-node effect is a commutative reduction, so the visiting order changes nothing.
+  constexpr u32 GROUP = SHARDED ? 4 : 8;
+  __shared__ uint4 act_s[GROUP * BLOCK];                   // x: tile-in-group << 8 | lane, busy << 16, any << 24; y, z, w: inbox words
+  __shared__ u32 act_n;
+  __shared__ u8 pend_s[GROUP];
+  __shared__ u16 gt_s[GROUP];
+  const bool compact = !TRACE && !saturated && !p.reap_now && p.compact;
+  if (compact) {
+    u32 i = 0;
+    while (i < ntile) {
+      u32 ng = 0;                                          // the next GROUP hot tiles of this CTA (every thread walks the same flags)
+      while (i < ntile && ng < GROUP) { if (hot_s[i]) { if (threadIdx.x == 0) gt_s[ng] = (u16)i; ++ng; } ++i; }
+      if (!ng) break;
+      if (threadIdx.x == 0) act_n = 0;
+      if (threadIdx.x < GROUP) pend_s[threadIdx.x] = 0;
+      __syncthreads();
+      Pre pr[GROUP];
+#pragma unroll
+      for (u32 g = 0; g < GROUP; ++g) {
+        pr[g] = Pre{};
+        if (g < ng) {
+          const u32 vn = ((tile0 + gt_s[g]) << TILE_SHIFT) + threadIdx.x;
+          if (vn < p.n_local) pr[g] = prefetch_node<R1>(p, vn, kL, kJ, kM, pol_first);
+        }
+      }
+#pragma unroll
+      for (u32 g = 0; g < GROUP; ++g) {
+        const bool act = g < ng && (pr[g].busy != 0 || pr[g].any != 0);
+        const u32 bal = __ballot_sync(0xffffffffu, act);
+        if (bal) {
+          u32 base = 0;
+          if (lane == 0) base = atomicAdd(&act_n, (u32)__popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (act) act_s[base + (u32)__popc(bal & ((1u << lane) - 1u))] =
+              make_uint4((g << 8) | threadIdx.x | (pr[g].busy << 16) | ((pr[g].any ? 1u : 0u) << 24), pr[g].mL, pr[g].mJ, pr[g].mM);
+        }
+      }
+      __syncthreads();
+      const u32 na = act_n;
+      if (threadIdx.x == 0) { SFS_PROBE(0); if (ng > 1) SFS_PROBE(1); if (na > BLOCK) SFS_PROBE(2); }   // groups, multi-tile groups, multi-pass groups
+      for (u32 b0 = 0; b0 < na; b0 += BLOCK) {
+        const u32 e = b0 + threadIdx.x;
+        if (e < na) {
+          const uint4 a = act_s[e];
+          const u32 g = (a.x >> 8) & 0xffu;
+          Pre pre;
+          pre.busy = (a.x >> 16) & 0xffu; pre.any = (a.x >> 24) & 1u; pre.mL = a.y; pre.mJ = a.z; pre.mM = a.w;
+          const u32 vl = ((tile0 + gt_s[g]) << TILE_SHIFT) + (a.x & 0xffu);
+          const bool pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, false, pol_first, pol_last, c);
+          if (mark && pend) pend_s[g] = 1;
+        }
+        if (SHARDED) wrote_remote |= flush_xstage(p, xs);
+      }
+      __syncthreads();
+      if (mark && threadIdx.x < ng && pend_s[threadIdx.x]) p.hot_wr[tile0 + gt_s[threadIdx.x]] = 1;
+      __syncthreads();                                     // gt_s / act_s are rewritten by the next group
+    }
+  } else {
   // Walk the hot tiles of this CTA.  The 13 "is there anything to do" bytes of the NEXT hot tile (busy byte, inbox
   // words) are requested before the current tile is processed, so an idle tile costs no exposed round trip.
   auto prefetch_tile = [&](u32 ti) -> Pre {
@@ -558,6 +621,7 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
     if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + i] = 1;
     if (SHARDED) wrote_remote |= flush_xstage(p, xs);
     i = j;
+  }
   }
   if (SHARDED && wrote_remote) __threadfence_system();   // peer-window stores are performed before the publish kernel raises the flags
   // block reduction (warp shuffles, then shared memory) → one atomic per counter per CTA.

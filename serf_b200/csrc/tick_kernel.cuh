@@ -60,6 +60,7 @@ struct TickParams {
   // sharded push-pull rounds: every rank's end-of-tick snapshot, indexed by shard (null when world == 1).  New members go
   // at the end: the tick kernels do not read them and keep their parameter offsets (and their SASS) unchanged.
   const uint4* const* snap_rec_peer; const u64* const* snap_node_peer;
+  u32 compact;                // 1: unsaturated ticks gather their active nodes across several tiles (SERFSIM_COMPACT=0 switches it off)
 };
 
 struct PublishParams {        // after the tick kernel: tell every peer how much was written, then raise its flag

@@ -148,7 +148,8 @@ _LIB = None
 
 
 def library_path():
-    return os.path.join(_HERE, "libserfsim.so")
+    # SERFSIM_LIB: another nvcc build of the same sources (A/B measurements of kernel variants); same ABI check applies
+    return os.environ.get("SERFSIM_LIB") or os.path.join(_HERE, "libserfsim.so")
 
 
 def load_library():

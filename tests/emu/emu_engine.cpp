@@ -3,6 +3,8 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <utility>
 #include <vector>
 
 #define SERFSIM_EMU 1
@@ -162,9 +164,27 @@ void run_grid(unsigned grid, unsigned block, const std::function<void()>& fn) {
       l.sp = &top[-8];
     }
     unsigned remaining = block;
+    // Lane order of a scheduling pass.  Default: ascending thread index.  SERFSIM_EMU_SCHED=reverse | random:<seed>
+    // visits the lanes in another order (re-drawn every pass for `random`): results must not depend on it, so running
+    // the parity suites under several schedules is a cheap check for order-dependent (racy) kernel logic.
+    static thread_local std::vector<unsigned> order;
+    order.resize(block);
+    for (unsigned t = 0; t < block; ++t) order[t] = t;
+    static const char* sched = getenv("SERFSIM_EMU_SCHED");
+    static thread_local unsigned long long rng = 0;
+    const bool random = sched && !strncmp(sched, "random", 6);
+    if (random && !rng) rng = 0x9E3779B97F4A7C15ull ^ (strlen(sched) > 7 ? strtoull(sched + 7, nullptr, 10) * 0xD1B54A32D192ED03ull : 1);
+    if (sched && !strcmp(sched, "reverse")) for (unsigned t = 0; t < block; ++t) order[t] = block - 1 - t;
     while (remaining) {
       bool progressed = false;
-      for (unsigned t = 0; t < block; ++t) {
+      if (random)
+        for (unsigned t = block - 1; t > 0; --t) {          // Fisher–Yates with xorshift64*
+          rng ^= rng >> 12; rng ^= rng << 25; rng ^= rng >> 27;
+          const unsigned j = (unsigned)(((rng * 0x2545F4914F6CDD1Dull) >> 33) % (t + 1));
+          std::swap(order[t], order[j]);
+        }
+      for (unsigned k = 0; k < block; ++k) {
+        const unsigned t = order[k];
         Lane& l = lanes[t];
         if (l.done) continue;
         if (l.wait == 1 && warps[t / 32].gen == l.wait_gen) continue;

@@ -23,6 +23,8 @@ def sources():
 
 
 def build():
+    if os.environ.get("SERFSIM_EMU_LIB"):          # e.g. a --coverage build of the same sources (tools/emu_coverage.sh)
+        return os.environ["SERFSIM_EMU_LIB"]
     deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     deps += [os.path.join(EMU, "cuda_runtime.h"), os.path.join(EMU, "emu_engine.cpp"), os.path.join(ROOT, "include", "serfsim.h")]
     if os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(d) for d in deps):

@@ -1,0 +1,127 @@
+"""Host-side logic of the C ABI (serf_b200/csrc/serfsim.cu) exercised on the CPU through the host-compiled build of
+tests/emu: stepping API, convergence loop variants, event callback, timing hooks, validation.  Results are compared
+with the oracle where there is something to compare."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from emu_lib import emu_sim, lib
+from oracle_lib import oracle_sim
+from serf_b200 import MemberStatus, scenarios
+from serf_b200.sim import Config, Op, SerfsimError
+from test_emu_parity import assert_same
+
+
+def test_step_by_step_equals_run_until_converged():
+    sc = scenarios.random_graph_leave(2000, 12, 3, seed=2, slots=2)
+    o = sc.build(oracle_sim, trace=1)
+    to, ok = o.run_until_converged(sc.max_ticks)
+    g = sc.build(emu_sim, trace=1)
+    for _ in range(to + 1):
+        g.step(1)
+    assert_same(g, o, sc.slots)
+    h = sc.build(emu_sim, trace=0)
+    h.step(5)
+    h.step(to + 1 - 5)
+    assert_same(h, o, sc.slots, with_hash=False)
+
+
+def test_max_ticks_reached_returns_not_converged():
+    sc = scenarios.random_graph_leave(2000, 12, 3, seed=2)
+    g, o = sc.build(emu_sim, trace=1), sc.build(oracle_sim, trace=1)
+    assert g.run_until_converged(6) == o.run_until_converged(6) == (6, False)
+    assert g.run_until_converged(sc.max_ticks) == o.run_until_converged(sc.max_ticks)      # and both continue from there
+    assert_same(g, o, sc.slots)
+
+
+def test_long_run_grows_the_trace_buffer():
+    """More than 1024 ticks: the device trace / kind-counter arrays are reallocated and copied."""
+    sc = scenarios.random_graph_leave(600, 8, 3, seed=1)
+    g, o = sc.build(emu_sim, trace=1), sc.build(oracle_sim, trace=1)
+    g.run_until_converged(sc.max_ticks), o.run_until_converged(sc.max_ticks)
+    g.inject(1500, Op.JOIN, int(sc.subjects[0]), 0)
+    o.inject(1500, Op.JOIN, int(sc.subjects[0]), 0)
+    assert g.run_until_converged(4000) == o.run_until_converged(4000)
+    assert g.stats()["tick"] > 1500
+    assert_same(g, o, sc.slots)
+
+
+def test_speculative_pipeline_gives_the_same_result(monkeypatch):
+    sc = scenarios.random_graph_leave(3000, 12, 4, seed=3)
+    o = sc.build(oracle_sim, trace=1)
+    to = o.run_until_converged(sc.max_ticks)
+    monkeypatch.setenv("SERFSIM_SPECULATE", "1")
+    for chunk in ("1", "4", "16"):
+        monkeypatch.setenv("SERFSIM_CHUNK", chunk)
+        g = sc.build(emu_sim, trace=0)
+        assert g.run_until_converged(sc.max_ticks) == to
+        assert_same(g, o, sc.slots, with_hash=False)
+    g = sc.build(emu_sim, trace=0)
+    assert g.run_until_converged(7) == (7, False)
+
+
+@pytest.mark.parametrize("chunk", ["1", "3", "9"])
+def test_chunk_size_does_not_change_results(monkeypatch, chunk):
+    monkeypatch.setenv("SERFSIM_CHUNK", chunk)
+    sc = scenarios.fuzz(11)                                # has reaper / push-pull boundary ticks
+    o = sc.build(oracle_sim, trace=1)
+    to = o.run_until_converged(sc.max_ticks)
+    g = sc.build(emu_sim, trace=0)
+    assert g.run_until_converged(sc.max_ticks) == to
+    assert_same(g, o, sc.slots, with_hash=False)
+
+
+def test_event_callback_reports_agreed_status_changes():
+    sc = scenarios.random_graph_fail(1500, 16, 3, seed=2)            # subject 5 crashes, subject n/2 leaves
+    g = sc.build(emu_sim, trace=0, suspicion_mult=2, suspicion_max_timeout_mult=2, probe_interval_ticks=2)
+    seen = []
+    g.set_event_callback(lambda tick, ty, ids: seen.append((ty, tuple(ids))))
+    g.run_until_converged(sc.max_ticks)
+    kinds = {ty for ty, _ in seen}
+    assert 2 in kinds and 1 in kinds                                  # MemberEventType::Failed and ::Leave (event.rs:325-328)
+    assert (2, (5,)) in seen and (1, (750,)) in seen
+    n = len(seen)
+    g.step(3)                                                         # nothing new: no repeated reports
+    assert len(seen) == n
+
+
+def test_timing_hooks():
+    sc = scenarios.random_graph_leave(1000, 8, 3, seed=1)
+    g = sc.build(emu_sim)
+    g.set_tick_timing(True)
+    t, ok = g.run_until_converged(sc.max_ticks)
+    ms = g.tick_times_ms()
+    assert len(ms) == t + 1 and (ms >= 0).all()
+    dev_ms, launches = g.last_step_device_ms()
+    assert launches >= t + 1 and dev_ms >= 0
+    g2 = sc.build(emu_sim)
+    g2.run_until_converged(sc.max_ticks)
+    with pytest.raises(SerfsimError):
+        g2.tick_times_ms(0, 3)                                        # timing was not enabled
+
+
+def test_create_and_inject_validation():
+    L = lib()
+    cfg = Config()
+    L.serfsim_default_config(C.byref(cfg))
+    assert (cfg.fanout, cfg.retransmit_mult, cfg.suspicion_mult, cfg.suspicion_max_timeout_mult, cfg.probe_interval_ticks) == (3, 4, 4, 6, 5)
+    assert cfg.abi_version == L.serfsim_abi_version()
+    for bad in (dict(fanout=0), dict(fanout=9)):
+        with pytest.raises(SerfsimError):
+            emu_sim(100, 1, **bad)
+    with pytest.raises(SerfsimError):
+        emu_sim(100, 17)
+    g = emu_sim(100, 1)
+    with pytest.raises(SerfsimError):
+        g.step(1)                                                     # no topology yet
+    sc = scenarios.random_graph_leave(300, 8, 3, seed=1)
+    g = sc.build(emu_sim)
+    with pytest.raises(SerfsimError):
+        g.inject(0, Op.LEAVE, 17, 0)                                  # join/leave origin must be a tracked subject
+    with pytest.raises(SerfsimError):
+        g.inject(0, Op.FAIL, int(sc.subjects[0]), 0)                  # one operation per node per tick (a LEAVE is scheduled there)
+    g.step(2)
+    with pytest.raises(SerfsimError):
+        g.inject(1, Op.FAIL, 9, 0)                                    # in the past
+    assert g.shard_range() == (0, 300) if hasattr(g, "shard_range") else True

@@ -250,3 +250,19 @@ def test_sharded_byzantine(world):
 
 def test_sharded_byzantine_heavy_three_ranks():
     check_byzantine(scenarios.byzantine_injectors(1501, 12, 3, 0.2, seed=3), 3)
+
+
+def test_sharded_stage_overflow_path():
+    """8 subjects × fan-out 8: a tile produces far more cross-shard entries than the shared-memory stage holds
+    (3072 per CTA), so the write-through path behind the stage is taken — results unchanged."""
+    check(scenarios.random_graph_leave(1500, 12, 8, seed=6, slots=8), 2)
+
+
+def test_window_overflow_is_reported(monkeypatch):
+    """A receive window too small for the traffic must fail loudly (SERFSIM_E_COMM), never drop entries silently."""
+    from serf_b200.sim import SerfsimError
+    monkeypatch.setenv("SERFSIM_WIN_FACTOR", "0.0001")
+    sc = scenarios.random_graph_leave(30000, 12, 8, seed=6, slots=8)
+    with pytest.raises(SerfsimError) as ei:
+        run_sharded(sc, 2, trace=0)
+    assert ei.value.code == -6

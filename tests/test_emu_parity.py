@@ -77,3 +77,43 @@ def test_small_world_churn():
 @pytest.mark.parametrize("seed", range(40))
 def test_fuzz(seed):
     run_both(scenarios.fuzz(seed))
+
+
+def test_compaction_path_is_taken_and_exact():
+    """Unsaturated ticks of a trace-off run gather the active nodes of several tiles (SFS_PROBE 0..2 count the groups,
+    the multi-tile groups and the groups needing more than one dense pass)."""
+    import ctypes as C
+    from emu_lib import lib
+    L = lib()
+    L.emu_probe.restype = C.c_ulong
+    L.emu_probe_reset()
+    sc = scenarios.random_graph_leave(6000, 16, 3, seed=1)
+    o = sc.build(oracle_sim, trace=1)
+    to = o.run_until_converged(sc.max_ticks)
+    f = sc.build(emu_sim, trace=0)
+    assert f.run_until_converged(sc.max_ticks) == to
+    assert L.emu_probe(0) > 0 and L.emu_probe(1) > 0 and L.emu_probe(2) > 0
+    assert_same(f, o, sc.slots, with_hash=False)
+
+
+def test_config1_shape_100k_nodes():
+    """BASELINE configs[1] at full size (100 K-node random graph, fan-out 3) through the host-compiled kernels:
+    391 tiles over 4 CTAs, dense and sparse ticks, production mode (trace off)."""
+    sc = scenarios.random_graph_leave(100_000, 16, 3, seed=1)
+    o = sc.build(oracle_sim, trace=1)
+    to = o.run_until_converged(sc.max_ticks)
+    f = sc.build(emu_sim, trace=0)
+    assert f.run_until_converged(sc.max_ticks) == to
+    assert_same(f, o, sc.slots, with_hash=False)
+
+
+def test_config2_shape_small_world_churn_100k():
+    """BASELINE configs[2] shape (small world, 5 % of the nodes crash / return, 8 tracked subjects, probing on) at
+    100 K nodes, production mode."""
+    sc = scenarios.small_world_churn(100_000, 16, 0.1, 0.05, slots=8, window=60, seed=3)
+    cfg = dict(suspicion_mult=2, suspicion_max_timeout_mult=2, probe_interval_ticks=2)
+    o = sc.build(oracle_sim, trace=1, **cfg)
+    to = o.run_until_converged(sc.max_ticks)
+    f = sc.build(emu_sim, trace=0, **cfg)
+    assert f.run_until_converged(sc.max_ticks) == to
+    assert_same(f, o, sc.slots, with_hash=False)

@@ -23,6 +23,14 @@ CASES = [("full_mesh_leave", dict(n=256, fanout=3, seed=s)) for s in (1, 2, 3)] 
         [("fuzz", dict(seed=s)) for s in range(10)]
 
 
+# user events / byzantine injectors: kept in their own fixture (tests/golden/features.json) and their own test files, so that
+# the device tests of the parts that have not run on hardware yet come after the ones that have
+FEATURE_CASES = [("user_event_storm", dict(n=20_000, degree=16, fanout=3, seed=1, n_events=4, spacing=3)),
+                 ("user_event_storm", dict(n=8_000, degree=12, fanout=4, seed=5, n_events=3, spacing=2, alias=True, churn=40, with_leave=True)),
+                 ("byzantine_injectors", dict(n=20_000, degree=16, fanout=4, frac=0.01, seed=1)),
+                 ("byzantine_injectors", dict(n=6_000, degree=16, fanout=4, frac=0.2, seed=3))]
+
+
 def digest(sim, n):
     tr = sim.tick_trace(0, n)
     return hashlib.sha256(tr.tobytes()).hexdigest()
@@ -34,8 +42,15 @@ def run_case(name, kwargs, factory):
     sim = sc.build(factory, trace=1)
     ticks, ok = sim.run_until_converged(sc.max_ticks)
     st = sim.stats()
-    return {"ticks": int(ticks), "converged": bool(ok), "n_ticks": st["tick"], "edge_updates": st["edge_updates"], "messages": st["messages"],
-            "changed": st["changed"], "state_hash": "%016x" % sim.state_hash(), "trace_sha256": digest(sim, st["tick"])}
+    out = {"ticks": int(ticks), "converged": bool(ok), "n_ticks": st["tick"], "edge_updates": st["edge_updates"], "messages": st["messages"],
+           "changed": st["changed"], "state_hash": "%016x" % sim.state_hash(), "trace_sha256": digest(sim, st["tick"])}
+    if sc.user_events is not None:
+        out["user_events"] = sim.user_event_stats()
+        out["user_event_records_sha256"] = hashlib.sha256(sim.user_event_records().tobytes()).hexdigest()
+    if sc.byzantine is not None:
+        out["byzantine"] = sim.byzantine_stats()
+        out["anomaly_sha256"] = hashlib.sha256(sim.anomaly_flags().tobytes()).hexdigest()
+    return out
 
 
 if __name__ == "__main__":
@@ -45,5 +60,13 @@ if __name__ == "__main__":
         out.append({"scenario": name, "args": kwargs, **r})
         print(name, kwargs, r["ticks"], r["state_hash"])
     path = os.path.join(ROOT, "tests", "golden", "traces.json")
+    json.dump(out, open(path, "w"), indent=1)
+    print("wrote", path)
+    out = []
+    for name, kwargs in FEATURE_CASES:
+        r = run_case(name, kwargs, oracle_sim)
+        out.append({"scenario": name, "args": kwargs, **r})
+        print(name, kwargs, r["ticks"], r["state_hash"])
+    path = os.path.join(ROOT, "tests", "golden", "features.json")
     json.dump(out, open(path, "w"), indent=1)
     print("wrote", path)

@@ -24,6 +24,7 @@ def fingerprints(so):
     for part in re.split(r"\n\s*Function : ", txt)[1:]:
         name, body = part.split("\n", 1)
         body = ANON.sub("ANON", body.split("Fatbin elf code")[0].rstrip())
+        body = re.sub(r"[ \t]+", " ", body)              # cuobjdump pads the comment column to the longest line of the WHOLE listing
         out[ANON.sub("ANON", name.strip())] = hashlib.sha256(body.encode()).hexdigest()[:16]
     return out
 
