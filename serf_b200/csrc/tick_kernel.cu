@@ -590,6 +590,7 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
           Pre pre;
           pre.busy = (a.x >> 16) & 0xffu; pre.any = (a.x >> 24) & 1u; pre.mL = a.y; pre.mJ = a.z; pre.mM = a.w;
           const u32 vl = ((tile0 + gt_s[g]) << TILE_SHIFT) + (a.x & 0xffu);
+          pre.qw = p.qword[vl];                               // not carried through the list: issued here, in flight with the state loads
           const bool pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, false, pol_first, pol_last, c);
           if (mark && pend) pend_s[g] = 1;
         }
