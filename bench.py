@@ -295,7 +295,7 @@ def main():
                 "dtype": "u32", "data": "synthetic", "config": config_dict(args, sc),
                 "ticks_to_convergence": ticks_list[-1], "edge_updates_per_step": eu_per_step, "p_dirty": p_dirty,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "traffic_source": "profiles/r1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per tick launch)" if traffic else None,
+                             "traffic": traffic, "traffic_source": "profiles/r1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per tick launch; captured on the round-1 kernel BEFORE multi-tile compaction of unsaturated ticks — saturated ticks, which carry the traffic, are unchanged)" if traffic else None,
                              "algorithmic_bytes_per_launch": total_eu * be / world / max(1, tick_launches), "peak_source": peak_src, "kernel": "tick_kernel", "bytes_per_edge_update": be,
                              "launches": tick_launches, "avg_launch_us": 1e3 * dev_ms / max(1, tick_launches)},
                 "e2e": {"value": total_eu / wall_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

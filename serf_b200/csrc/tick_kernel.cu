@@ -77,13 +77,15 @@ __device__ __forceinline__ u32 ld_acquire_sys(const u32* ptr) { u32 f; asm volat
 #else   // SERFSIM_EMU: the same accessors as plain C++ (tests/emu compiles this file for the host; cache hints have no meaning there)
 inline u64 policy_evict_first() { return 0; }
 inline u64 policy_evict_last() { return 0; }
-inline Words ld_rec256(const uint4* ptr, u64) { Words r; const u32* q = reinterpret_cast<const u32*>(ptr); for (int i = 0; i < 8; ++i) r.w[i] = q[i]; return r; }
-inline void st_rec256(uint4* ptr, const Words& r, u64) { u32* q = reinterpret_cast<u32*>(ptr); for (int i = 0; i < 8; ++i) q[i] = r.w[i]; }
-inline u64 ld_u64_stream(const u64* ptr, u64) { return *ptr; }
-inline u32 ld_u32_stream(const u32* ptr, u64) { return *ptr; }
-inline void st_u32_stream(u32* ptr, u32 v, u64) { *ptr = v; }
-inline void st_u64_stream(u64* ptr, u64 v, u64) { *ptr = v; }
-inline void red_max_resident(u32* ptr, u32 v, u64) { if (v > *ptr) *ptr = v; }
+// byte counters of the host build (probes 8..14): what the accessors of one run ISSUE, by class — an accounting aid for
+// layout experiments (tools/emu_traffic.py), not a DRAM model
+inline Words ld_rec256(const uint4* ptr, u64) { emu::probes[8] += 32; Words r; const u32* q = reinterpret_cast<const u32*>(ptr); for (int i = 0; i < 8; ++i) r.w[i] = q[i]; return r; }
+inline void st_rec256(uint4* ptr, const Words& r, u64) { emu::probes[9] += 32; u32* q = reinterpret_cast<u32*>(ptr); for (int i = 0; i < 8; ++i) q[i] = r.w[i]; }
+inline u64 ld_u64_stream(const u64* ptr, u64) { emu::probes[10] += 8; return *ptr; }
+inline u32 ld_u32_stream(const u32* ptr, u64) { emu::probes[11] += 4; return *ptr; }
+inline void st_u32_stream(u32* ptr, u32 v, u64) { emu::probes[12] += 4; *ptr = v; }
+inline void st_u64_stream(u64* ptr, u64 v, u64) { emu::probes[13] += 8; *ptr = v; }
+inline void red_max_resident(u32* ptr, u32 v, u64) { emu::probes[14] += 4; if (v > *ptr) *ptr = v; }
 inline void st_release_sys(u32* ptr, u32 v) { __atomic_store_n(ptr, v, __ATOMIC_RELEASE); }     // peers are other threads of the test process
 inline u32 ld_acquire_sys(const u32* ptr) { return __atomic_load_n(ptr, __ATOMIC_ACQUIRE); }
 #endif

@@ -179,3 +179,29 @@ def byzantine_injectors(n=100_000, degree=16, fanout=4, frac=0.01, delta=2, seed
         cfg.update(suspicion_mult=2, suspicion_max_timeout_mult=2, probe_interval_ticks=2)
     return Scenario(f"byzantine_{n}_f{frac}", n, slots, random_regular_graph(n, degree, graph_seed), subjects, ops, cfg,
                     max_ticks=4000, byzantine=byz, delta=delta)
+
+
+def fuzz_features(seed, n=None, slots=None):
+    """fuzz() plus the optional subsystems on top: tracked user events fired at random ticks / origins (possibly with
+    equal content), and a random set of byzantine injectors.  Push-pull is off (not combinable in this version)."""
+    sc = fuzz(seed, n=n, slots=slots)
+    sc.name = f"fuzz_features_{seed}"
+    sc.cfg["push_pull_interval_ticks"] = 0
+    rng = np.random.Generator(np.random.Philox(seed + 90001))
+    used = {(t, node) for (t, _, node, _) in sc.ops}
+    if rng.random() < 0.8:
+        E = int(rng.integers(1, 9))
+        sc.user_events = rng.integers(1, 4, size=E).astype(np.uint32)          # few distinct contents → aliases
+        for e in range(E):
+            for _ in range(8):
+                t, node = int(rng.integers(0, 40)), int(rng.integers(0, sc.n))
+                if (t, node) not in used:
+                    used.add((t, node))
+                    sc.ops.append((t, int(Op.USER_EVENT), node, e))
+                    break
+    if rng.random() < 0.7:
+        k = int(rng.integers(1, max(2, sc.n // 4)))
+        sc.byzantine = rng.choice(sc.n, size=k, replace=False).astype(np.uint32)
+        sc.delta = int(rng.integers(0, 4))
+        sc.cfg["init_clock"] = int(rng.integers(1, 12))
+    return sc

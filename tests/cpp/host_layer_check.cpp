@@ -29,7 +29,22 @@ int main() {
     int left = 0;
     for (auto st : m) left += st == MemberStatus::Left;
     std::printf("converged=%d ticks=%u left=%d leave_events=%d\n", (int)r.second, r.first, left, leaves);
-    return (r.second && left == 255 && leaves == 1) ? 0 : 4;
+    if (!(r.second && left == 255 && leaves == 1)) return 4;
+    // Serf::user_event on a second cluster: two tracked events fired by nodes 7 and 9, every node delivers both
+    Serf u(o);
+    u.set_topology(rp, col);
+    u.track({0, 1});
+    u.track_user_events({11, 22});
+    u.user_event(7, 0, 0);
+    u.user_event(9, 1, 2);
+    auto ru = u.run_until_converged(500);
+    int seen0 = 0, seen1 = 0;
+    for (auto b : u.user_event_seen(0)) seen0 += b;
+    for (auto b : u.user_event_seen(1)) seen1 += b;
+    const auto us = u.user_event_stats();
+    std::printf("user events: converged=%d seen=%d/%d delivered=%llu event_time=%llu\n", (int)ru.second, seen0, seen1,
+                (unsigned long long)us.delivered, (unsigned long long)us.event_time);
+    return (ru.second && seen0 == 256 && seen1 == 256 && us.delivered == 512 && us.event_queue == 0) ? 0 : 6;
   } catch (const Error& e) {
     std::printf("%s\n", e.what());
     return e.code == SERFSIM_E_NO_DEVICE ? 10 : 5;

@@ -98,7 +98,7 @@ inline unsigned __activemask() { return 1u << emu::lane_id(); }
 inline unsigned __match_any_sync(unsigned, unsigned) { return 1u << emu::lane_id(); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
-template <class T> inline T __ldg(const T* p) { return *p; }
+template <class T> inline T __ldg(const T* p) { emu::probes[15] += sizeof(T); return *p; }   // read-only-path loads (row offsets, neighbour gathers)
 template <class T> inline T __ldcg(const T* p) { return *p; }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }

@@ -146,7 +146,20 @@ void run_grid(unsigned grid, unsigned block, const std::function<void()>& fn) {
       if (s == MAP_FAILED) { perror("emu: mmap"); abort(); }
       lanes[t].stack = (char*)s;
     }
-  for (unsigned b = 0; b < grid; ++b) {
+  // CTA order follows SERFSIM_EMU_SCHED too (ascending / reverse / a fresh random permutation per launch): a kernel
+  // whose result depends on which CTA runs first is as wrong as one that depends on the lane order.
+  static const char* sched_env = getenv("SERFSIM_EMU_SCHED");
+  static thread_local std::vector<unsigned> cta_order;
+  static thread_local unsigned long long cta_rng = 0x243F6A8885A308D3ull;
+  cta_order.resize(grid);
+  for (unsigned b = 0; b < grid; ++b) cta_order[b] = (sched_env && !strcmp(sched_env, "reverse")) ? grid - 1 - b : b;
+  if (sched_env && !strncmp(sched_env, "random", 6))
+    for (unsigned b = grid; b > 1; --b) {
+      cta_rng ^= cta_rng >> 12; cta_rng ^= cta_rng << 25; cta_rng ^= cta_rng >> 27;
+      std::swap(cta_order[b - 1], cta_order[(unsigned)(((cta_rng * 0x2545F4914F6CDD1Dull) >> 33) % b)]);
+    }
+  for (unsigned bi = 0; bi < grid; ++bi) {
+    const unsigned b = cta_order[bi];
     const unsigned nw = (block + 31) / 32;
     for (unsigned w = 0; w < nw; ++w) { warps[w].live = 0; warps[w].arrived = 0; warps[w].gen = 0; }
     cta_live = (int)block; cta_arrived = 0; cta_gen = 0;

@@ -125,3 +125,20 @@ def test_create_and_inject_validation():
     with pytest.raises(SerfsimError):
         g.inject(1, Op.FAIL, 9, 0)                                    # in the past
     assert g.shard_range() == (0, 300) if hasattr(g, "shard_range") else True
+
+
+def test_cpp_host_layer_end_to_end(tmp_path):
+    """include/serfsim.hpp (the C++ host layer with the reference's names) driving the host-compiled library: the
+    configs[0] leave scenario with the event callback, then two user events — the program tests/test_abi.py runs on a
+    GPU box, here linked against the emulated build."""
+    import os
+    import subprocess
+    from emu_lib import build
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = build()
+    exe = str(tmp_path / "host_layer_check")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "host_layer_check.cpp"),
+                           so, "-Wl,-rpath," + os.path.dirname(so), "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "left=255 leave_events=1" in r.stdout and "seen=256/256 delivered=512" in r.stdout

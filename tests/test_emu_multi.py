@@ -266,3 +266,58 @@ def test_window_overflow_is_reported(monkeypatch):
     with pytest.raises(SerfsimError) as ei:
         run_sharded(sc, 2, trace=0)
     assert ei.value.code == -6
+
+
+@pytest.mark.parametrize("seed", [1, 4, 6, 8, 13, 21])
+def test_sharded_fuzz_with_user_events_and_injectors(seed):
+    """fuzz_features across 2–3 ranks: operations, reaper, probing, user events and injectors, all crossing shards."""
+    sc = scenarios.fuzz_features(seed, n=400 + 37 * seed, slots=3)
+    sc.max_ticks = 400                     # some injector runs never go quiet (reaper ticks keep merging): both sides stop at the cap
+    world = 2 + seed % 2
+    o = sc.build(oracle_sim, trace=1)
+    to, oko = o.run_until_converged(sc.max_ticks)
+    n = o.stats()["tick"]
+    tro = o.tick_trace(0, n)
+    for trace in (1, 0):
+        comm = ThreadComm(world)
+        res, errs = [None] * world, []
+
+        def worker(rank):
+            try:
+                g = sc.build(emu_sim, rank=rank, world_size=world, trace=trace)
+                g.connect(*comm.hooks(rank))
+                ticks, ok = g.run_until_converged(sc.max_ticks)
+                r = dict(ticks=ticks, ok=ok, trace=g.tick_trace(), hash=g.state_hash(), rec=[g.records(s) for s in range(sc.slots)])
+                if sc.user_events is not None:
+                    r["ue"], r["ue_stats"] = g.user_event_records(), g.user_event_stats()
+                if sc.byzantine is not None:
+                    r["flags"], r["byz_stats"] = g.anomaly_flags(), g.byzantine_stats()
+                res[rank] = r
+                comm.bar.wait()
+            except BaseException as e:                              # noqa: BLE001
+                errs.append(e)
+                comm.bar.abort()
+        th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join(600)
+        if errs:
+            raise errs[0]
+        for r in res:
+            assert (r["ticks"], r["ok"]) == (to, oko)
+            for f in tro.dtype.names:
+                if f == "hash" and not trace:
+                    continue
+                assert (r["trace"][f] == tro[f]).all(), f
+            assert r["hash"] == o.state_hash()
+        for s in range(sc.slots):
+            assert (np.concatenate([r["rec"][s] for r in res]) == o.records(s)).all()
+        if sc.user_events is not None:
+            assert (np.concatenate([r["ue"] for r in res]) == o.user_event_records()).all()
+            so = o.user_event_stats()
+            for r in res:
+                assert {k: v for k, v in r["ue_stats"].items() if k != "event_time"} == {k: v for k, v in so.items() if k != "event_time"}
+        if sc.byzantine is not None:
+            assert (np.concatenate([r["flags"] for r in res]) == o.anomaly_flags()).all()
+            assert all(r["byz_stats"] == o.byzantine_stats() for r in res)

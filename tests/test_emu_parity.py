@@ -117,3 +117,45 @@ def test_config2_shape_small_world_churn_100k():
     f = sc.build(emu_sim, trace=0, **cfg)
     assert f.run_until_converged(sc.max_ticks) == to
     assert_same(f, o, sc.slots, with_hash=False)
+
+
+def _feature_checks(g, o, sc):
+    if sc.user_events is not None:
+        assert g.user_event_stats() == o.user_event_stats()
+        assert (g.user_event_records() == o.user_event_records()).all()
+    if sc.byzantine is not None:
+        assert g.byzantine_stats() == o.byzantine_stats()
+        assert (g.anomaly_flags() == o.anomaly_flags()).all()
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_fuzz_with_user_events_and_injectors(seed):
+    """Every operation kind, reaper, probing, tracked user events (with aliases) and byzantine injectors at once."""
+    sc = scenarios.fuzz_features(seed)
+    o = sc.build(oracle_sim, trace=1)
+    to = o.run_until_converged(sc.max_ticks)
+    for trace in (1, 0):
+        g = sc.build(emu_sim, trace=trace)
+        assert g.run_until_converged(sc.max_ticks) == to
+        assert_same(g, o, sc.slots, with_hash=bool(trace))
+        _feature_checks(g, o, sc)
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("SERFSIM_SLOW"), reason="≈ 2 min and 3 GB: set SERFSIM_SLOW=1 (result recorded in profiles/r1_notes.md)")
+def test_bench_workload_full_10m_nodes():
+    """The bench workload itself — BASELINE configs[3] shape on one device: 10 M-node random graph, fan-out 4, one
+    dissemination to quiescence — through the host-compiled kernel in production mode, against the oracle (8 threads)."""
+    from oracle_lib import lib as olib
+    sc = scenarios.dissemination_storm(10_000_000, 16, 4, slots=1, seed=1)
+    f = sc.build(emu_sim, trace=0)
+    tf = f.run_until_converged(sc.max_ticks)
+    o = sc.build(oracle_sim, trace=0)
+    olib().oracle_sim_set_threads(o._h, 8)
+    o.reset(sc.cfg["seed"])
+    sc.schedule(o)
+    assert o.run_until_converged(sc.max_ticks) == tf
+    assert f.state_hash() == o.state_hash() and f.stats() == o.stats()
+    tr, to = f.tick_trace(), o.tick_trace()
+    for name in tr.dtype.names:
+        if name != "hash":
+            assert (tr[name] == to[name]).all(), name

@@ -89,3 +89,24 @@ def test_user_events_rejected_with_push_pull_or_shards():
     g = GossipSim(1000, 1, push_pull_interval_ticks=10)
     with pytest.raises(SerfsimError):
         g.set_user_events([1, 2])
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_with_user_events_and_injectors(seed):
+    """Every operation kind, reaper, probing, tracked user events (with aliases) and byzantine injectors at once."""
+    sc = scenarios.fuzz_features(seed)
+    o = sc.build(oracle_sim, trace=1)
+    to = o.run_until_converged(sc.max_ticks)
+    for trace in (1, 0):
+        g = sc.build(gpu_sim, trace=trace)
+        assert g.run_until_converged(sc.max_ticks) == to
+        if trace:
+            assert_same(g, o, sc.slots)
+        else:
+            assert g.state_hash() == o.state_hash() and g.stats() == o.stats()
+        if sc.user_events is not None:
+            assert g.user_event_stats() == o.user_event_stats()
+            assert (g.user_event_records() == o.user_event_records()).all()
+        if sc.byzantine is not None:
+            assert g.byzantine_stats() == o.byzantine_stats()
+            assert (g.anomaly_flags() == o.anomaly_flags()).all()

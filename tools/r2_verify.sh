@@ -1,7 +1,7 @@
 #!/bin/bash
-# First GPU call of round 2, on branch r2-integration (= main + queue word + compaction), after `bash tools/build_ab.sh`:
+# First GPU call of round 2, on main, after `bash tools/build_ab.sh` (builds one library per kernel variant):
 #   gpurun --timeout 2700 -- 'bash tools/r2_verify.sh'
-# 1. device parity of everything that was written without a GPU (the integration build is the default library);
+# 1. device parity of everything that was written without a GPU (main's build is the default library);
 # 2. A/B numbers of the kernel variants (one library per branch in serf_b200/ab/), bench + per-tick profile.
 # Everything lands in gpurun_out/r2_*.  Exit code = the test suite's.
 mkdir -p gpurun_out
@@ -11,18 +11,27 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/r2
 timeout 1500 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_multi.py > gpurun_out/r2_tests.log 2>&1
 rc=$?
 tail -5 gpurun_out/r2_tests.log
-if [ $rc -ne 0 ]; then     # localise: the same suites against main's kernels (features only), then compaction off
-  SERFSIM_LIB=$PWD/serf_b200/ab/libserfsim_main.so timeout 900 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_multi.py > gpurun_out/r2_tests_mainlib.log 2>&1
-  tail -3 gpurun_out/r2_tests_mainlib.log
+if [ $rc -ne 0 ]; then     # localise: compaction off
   SERFSIM_COMPACT=0 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x > gpurun_out/r2_tests_nocompact.log 2>&1
   tail -3 gpurun_out/r2_tests_nocompact.log
 fi
-for v in main queue-word compaction integration; do
+for v in main queue-word; do
   lib=$PWD/serf_b200/ab/libserfsim_$v.so
   [ -f "$lib" ] || continue
   SERFSIM_LIB=$lib timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_$v.json 2>> gpurun_out/r2_bench.err
   SERFSIM_LIB=$lib timeout 300 python tools/tick_profile.py --out gpurun_out/r2_ticks_$v.json > gpurun_out/r2_ticks_$v.log 2>&1
   echo "$v: $(python -c "import json;d=json.load(open('gpurun_out/r2_bench_$v.json'));print(d['value'], d['kernel_ms_per_step'], d['roofline']['frac'])" 2>/dev/null)"
 done
-SERFSIM_COMPACT=0 SERFSIM_LIB=$PWD/serf_b200/ab/libserfsim_integration.so timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_integration_nocompact.json 2>> gpurun_out/r2_bench.err
+SERFSIM_COMPACT=0 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_main_nocompact.json 2>> gpurun_out/r2_bench.err
+SERFSIM_COMPACT=0 timeout 300 python tools/tick_profile.py --out gpurun_out/r2_ticks_main_nocompact.json > gpurun_out/r2_ticks_main_nocompact.log 2>&1
+# queue-word parity (its own library against the parity suites) if the main suite is green
+if [ $rc -eq 0 ]; then
+  SERFSIM_LIB=$PWD/serf_b200/ab/libserfsim_queue-word.so timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_golden.py -m gpu -q -x > gpurun_out/r2_tests_queueword.log 2>&1
+  tail -3 gpurun_out/r2_tests_queueword.log
+fi
+# the new features at BASELINE scale (only if their parity passed)
+if [ $rc -eq 0 ]; then
+  timeout 600 python tools/feature_profile.py --what events --out gpurun_out/r2_events.json > gpurun_out/r2_events.log 2>&1; tail -1 gpurun_out/r2_events.log
+  timeout 600 python tools/feature_profile.py --what byzantine --out gpurun_out/r2_byzantine.json > gpurun_out/r2_byzantine.log 2>&1; tail -1 gpurun_out/r2_byzantine.log
+fi
 exit $rc
