@@ -274,6 +274,7 @@ __device__ __forceinline__ Pre prefetch_node(const TickParams& p, u32 vl, bool k
   Pre x;
   x.busy = p.busy[vl];
   x.qw = p.qword[vl];                                   // slot-0 queue word (transmit budgets)
+  SFS_COUNT(6, 4);
   x.mL = kL ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R) * nl + vl, pol_first) : 0u;
   x.mJ = kJ ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R) * nl + vl, pol_first) : 0u;
   x.mM = kM ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R) * nl + vl, pol_first) : 0u;
@@ -375,6 +376,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
         const size_t idn = idx + nl;
         nxt = ld_rec256(p.rec + 2 * idn, pol_first);
         nq = p.qword[idn];
+        SFS_COUNT(6, 4);
         nL = kL ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R + s + 1) * nl + vl, pol_first) : 0;
         nJ = kJ ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R + s + 1) * nl + vl, pol_first) : 0;
         nM = kM ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R + s + 1) * nl + vl, pol_first) : 0;
@@ -489,7 +491,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
       Words o2 = orig, c2 = cur;                           // storage image: record without budgets, budgets in the queue word
       const u32 q_old = split_q(o2), q_new = split_q(c2);
       if (differs(c2, o2)) st_rec256(p.rec + 2 * idx, c2, pol_first);
-      if (q_new != q_old) p.qword[idx] = q_new;
+      if (q_new != q_old) { p.qword[idx] = q_new; SFS_COUNT(7, 4); }
     }
     if (TRACE) c.hash += rec_hash((u64)s * p.n_global + v, make_uint4(cur.w[0], cur.w[1], cur.w[2], cur.w[3]), make_uint4(cur.w[4], cur.w[5], cur.w[6], cur.w[7]));
     if (r.inc >= INC_LIMIT) *p.overflow = 1;
@@ -593,6 +595,7 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
           pre.busy = (a.x >> 16) & 0xffu; pre.any = (a.x >> 24) & 1u; pre.mL = a.y; pre.mJ = a.z; pre.mM = a.w;
           const u32 vl = ((tile0 + gt_s[g]) << TILE_SHIFT) + (a.x & 0xffu);
           pre.qw = p.qword[vl];                               // not carried through the list: issued here, in flight with the state loads
+          SFS_COUNT(6, 4);
           const bool pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, false, pol_first, pol_last, c);
           if (mark && pend) pend_s[g] = 1;
         }

@@ -16,8 +16,10 @@ constexpr int SFS_SMS = 1;
 // Coverage probes of the host build (tests assert that a code path was actually taken); nothing under nvcc.
 #ifdef SERFSIM_EMU
 #define SFS_PROBE(i) (emu::probes[i]++)
+#define SFS_COUNT(i, n) (emu::probes[i] += (n))
 #else
 #define SFS_PROBE(i) ((void)0)
+#define SFS_COUNT(i, n) ((void)0)
 #endif
 
 namespace sfs {

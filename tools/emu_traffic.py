@@ -26,7 +26,7 @@ L = lib()
 L.emu_probe.restype = C.c_ulong
 L.emu_probe_reset()
 ticks, ok = g.run_until_converged(sc.max_ticks)
-names = {8: "record loads", 9: "record stores", 10: "node-word loads", 11: "inbox / stream u32 loads", 12: "inbox clears (u32 stores)",
+names = {6: "queue-word loads (queue-word layout only)", 7: "queue-word stores (queue-word layout only)", 8: "record loads", 9: "record stores", 10: "node-word loads", 11: "inbox / stream u32 loads", 12: "inbox clears (u32 stores)",
          13: "node-word stores", 14: "RED.MAX (4 B each)", 15: "read-only path: row offsets + neighbour gathers"}
 st = g.stats()
 out = {"nodes": a.nodes, "ticks": ticks, "edge_updates": st["edge_updates"], "bytes": {names[k]: int(L.emu_probe(k)) for k in names}}
