@@ -69,6 +69,19 @@ __host__ __device__ inline void pack(const Rec& r, uint4& a, uint4& b) {
   b.w = r.txm | (r.flags << 8) | (r.mask << 16);
 }
 
+// Queue word: the three transmit budgets of a view live in their own 4-byte plane (byte 0 tx_join, 1 tx_leave, 2 tx_ml),
+// so that a sender which only decrements budgets rewrites 4 bytes instead of its whole 32-byte record.  Every external
+// image of a record (records getter, state hash, oracle comparison) is the MERGED one: record | budgets.
+__host__ __device__ inline void merge_queue_word(uint4& b, u32 q) {
+  b.z |= ((q & 0xffu) << 16) | (((q >> 8) & 0xffu) << 24);
+  b.w |= (q >> 16) & 0xffu;
+}
+__host__ __device__ inline u32 split_queue_word(uint4& b) {
+  const u32 q = ((b.z >> 16) & 0xffu) | ((b.z >> 24) << 8) | ((b.w & 0xffu) << 16);
+  b.z &= 0x0000ffffu; b.w &= ~0xffu;
+  return q;
+}
+
 struct Rules {          // per-run constants
   u32 limit;            // memberlist retransmit limit = retransmit_mult * ceil(log10(n+1))
   u32 k;                // max suspicion confirmations

@@ -78,7 +78,8 @@ struct serfsim {
   u32 stride = 0;                  // count rounded up to a whole 256-node tile: stride of every per-slot plane
   Rules rules{};
   // device state
-  uint4* d_rec = nullptr;          // [R][count] × 32 B
+  uint4* d_rec = nullptr;          // [R][stride] × 32 B (transmit-budget bytes zero)
+  u32* d_qword = nullptr;          // [R][stride] queue words (transmit budgets)
   u32* d_inbox[2] = {nullptr, nullptr};   // [3][R][count]
   u64* d_node = nullptr;           // [count]
   u8* d_busy = nullptr;            // [stride] per-node busy byte
@@ -241,7 +242,7 @@ int launch_ticks(serfsim* h, u32 n) {
     p.seed_lo = (u32)h->cfg.seed; p.seed_hi = (u32)(h->cfg.seed >> 32); p.ev_begin = eb; p.ev_end = ee;
     p.rules = h->rules;
     for (u32 s = 0; s < h->R; ++s) p.subj[s] = h->subj[s];
-    p.rec = h->d_rec; p.inbox_rd = h->d_inbox[(t & 1) ^ 1]; p.inbox_wr = h->d_inbox[t & 1];
+    p.rec = h->d_rec; p.qword = h->d_qword; p.inbox_rd = h->d_inbox[(t & 1) ^ 1]; p.inbox_wr = h->d_inbox[t & 1];
     p.node_state = h->d_node; p.busy = h->d_busy; p.watch = h->d_watch; p.row_ptr = h->d_rowptr; p.col = h->d_col;
     p.ev_node = h->d_ev_node; p.ev_op = h->d_ev_op; p.ev_slot = h->d_ev_slot;
     p.row = h->d_trace + (size_t)t * 8;
@@ -385,7 +386,7 @@ int fire_events(serfsim* h) {
   std::vector<u64> init(nout, 0), out(nout);
   for (u32 s = 0; s < h->R; ++s) init[2 + 2 * s] = ~0ull;
   CU(cudaMemcpyAsync(h->d_scratch, init.data(), nout * 8, cudaMemcpyHostToDevice, h->stream));
-  launch_summary(h->d_rec, h->d_node, h->count, h->stride, h->first, h->R, h->d_subj, h->d_scratch, h->stream);
+  launch_summary(h->d_rec, h->d_qword, h->d_node, h->count, h->stride, h->first, h->R, h->d_subj, h->d_scratch, h->stream);
   CU(cudaMemcpyAsync(out.data(), h->d_scratch, nout * 8, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   for (u32 type = 0; type < 3; ++type) {
@@ -436,6 +437,7 @@ int do_reset(serfsim* h, u64 seed) {
   CU(cudaMemsetAsync(h->d_inbox[1], 0, inbox_bytes, h->stream));
   CU(cudaMemsetAsync(h->d_overflow, 0, 4, h->stream));
   CU(cudaMemsetAsync(h->d_busy, 0, h->stride, h->stream));
+  CU(cudaMemsetAsync(h->d_qword, 0, (size_t)h->R * h->stride * 4, h->stream));
   CU(cudaMemsetAsync(h->d_hot[0], 0, h->n_tiles, h->stream));
   CU(cudaMemsetAsync(h->d_hot[1], 0, h->n_tiles, h->stream));
   if (h->d_trace) {
@@ -454,6 +456,7 @@ void free_all(serfsim* h) {
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   for (cudaEvent_t e : h->tick_ev) cudaEventDestroy(e);
   cudaFree(h->d_hot[0]); cudaFree(h->d_hot[1]); cudaFree(h->d_busy); cudaFree(h->d_watch); cudaFree(h->d_snap_rec); cudaFree(h->d_snap_node); cudaFree(h->d_peer_snap_rec); cudaFree(h->d_peer_snap_node);
+  cudaFree(h->d_qword);
   cudaFree(h->d_rec); cudaFree(h->d_inbox[0]); cudaFree(h->d_inbox[1]); cudaFree(h->d_node); cudaFree(h->d_rowptr); cudaFree(h->d_col);
   cudaFree(h->d_ev_node); cudaFree(h->d_ev_op); cudaFree(h->d_ev_slot); cudaFree(h->d_trace); cudaFree(h->d_kinds); cudaFree(h->d_ones);
   cudaFree(h->d_overflow); cudaFree(h->d_subj); cudaFree(h->d_scratch); cudaFree(h->d_stage);
@@ -547,6 +550,8 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
   const size_t inbox_bytes = (size_t)3 * h->R * h->stride * sizeof(u32);
   CUB(cudaMalloc(&h->d_rec, (size_t)h->R * h->stride * 32));
   CUB(cudaMemset(h->d_rec, 0, (size_t)h->R * h->stride * 32));
+  CUB(cudaMalloc(&h->d_qword, (size_t)h->R * h->stride * 4));
+  CUB(cudaMemset(h->d_qword, 0, (size_t)h->R * h->stride * 4));
   CUB(cudaMalloc(&h->d_inbox[0], inbox_bytes)); CUB(cudaMalloc(&h->d_inbox[1], inbox_bytes));
   CUB(cudaMalloc(&h->d_node, (size_t)h->stride * 8));
   CUB(cudaMemset(h->d_node, 0, (size_t)h->stride * 8));
@@ -835,8 +840,13 @@ int serfsim_ml_state(serfsim_t* h, uint32_t slot, uint8_t* out) { return getter(
 int serfsim_records(serfsim_t* h, uint32_t slot, void* out) {
   if (!h || !out) return fail(SERFSIM_E_INVAL, "null argument");
   if (slot >= h->R) return fail(SERFSIM_E_INVAL, "slot out of range");
-  CU(cudaStreamSynchronize(h->stream));
-  CU(cudaMemcpy(out, (const char*)h->d_rec + (size_t)slot * h->stride * 32, (size_t)h->count * 32, cudaMemcpyDeviceToHost));
+  uint4* tmp = nullptr;                          // merged image: record | transmit budgets of the queue word
+  CU(cudaMalloc(&tmp, (size_t)h->count * 32));
+  launch_compose_records(h->d_rec, h->d_qword, h->count, h->stride, slot, tmp, h->stream);
+  cudaError_t e = cudaMemcpyAsync(out, tmp, (size_t)h->count * 32, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(tmp);
+  if (e != cudaSuccess) return fail(SERFSIM_E_CUDA, cudaGetErrorString(e));
   return 0;
 }
 
@@ -853,7 +863,7 @@ int serfsim_tick_trace(serfsim_t* h, uint32_t first_tick, uint32_t n, serfsim_ti
 int serfsim_state_hash(serfsim_t* h, uint64_t* out) {
   if (!h || !out) return fail(SERFSIM_E_INVAL, "null argument");
   CU(cudaMemsetAsync(h->d_scratch, 0, 4 * 8, h->stream));
-  launch_state_hash(h->d_rec, h->d_node, h->count, h->stride, h->first, h->N, h->R, h->d_scratch, h->stream);
+  launch_state_hash(h->d_rec, h->d_qword, h->d_node, h->count, h->stride, h->first, h->N, h->R, h->d_scratch, h->stream);
   if (h->ue_table.n) launch_ue_summary(h->d_ue_state, h->count, h->first, h->N, h->R, h->ue_table.n, h->d_scratch + 1, h->stream);
   u64 parts[4] = {0, 0, 0, 0};
   CU(cudaMemcpyAsync(parts, h->d_scratch, 4 * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -883,7 +893,7 @@ int serfsim_stats(serfsim_t* h, serfsim_stats_t* o) {
   std::vector<u64> init(nout, 0), out(nout);
   for (u32 s = 0; s < h->R; ++s) init[2 + 2 * s] = ~0ull;
   CU(cudaMemcpyAsync(h->d_scratch, init.data(), nout * 8, cudaMemcpyHostToDevice, h->stream));
-  launch_summary(h->d_rec, h->d_node, h->count, h->stride, h->first, h->R, h->d_subj, h->d_scratch, h->stream);
+  launch_summary(h->d_rec, h->d_qword, h->d_node, h->count, h->stride, h->first, h->R, h->d_subj, h->d_scratch, h->stream);
   CU(cudaMemcpyAsync(out.data(), h->d_scratch, nout * 8, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   o->member_time = out[0]; o->intent_queue = out[1];

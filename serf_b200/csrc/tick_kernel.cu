@@ -211,6 +211,12 @@ __device__ __forceinline__ void pack_words(const Rec& r, Words& x) {
   x.w[6] = r.status | (r.mlstate << 8) | (r.qfrom << 10) | (r.txj << 16) | (r.txl << 24);
   x.w[7] = r.txm | (r.flags << 8) | (r.mask << 16);
 }
+__device__ __forceinline__ void merge_q(Words& x, u32 q) { x.w[6] |= ((q & 0xffu) << 16) | (((q >> 8) & 0xffu) << 24); x.w[7] |= (q >> 16) & 0xffu; }
+__device__ __forceinline__ u32 split_q(Words& x) {
+  const u32 q = ((x.w[6] >> 16) & 0xffu) | ((x.w[6] >> 24) << 8) | ((x.w[7] & 0xffu) << 16);
+  x.w[6] &= 0x0000ffffu; x.w[7] &= ~0xffu;
+  return q;
+}
 __device__ __forceinline__ bool differs(const Words& a, const Words& b) {
   return ((a.w[0] ^ b.w[0]) | (a.w[1] ^ b.w[1]) | (a.w[2] ^ b.w[2]) | (a.w[3] ^ b.w[3]) | (a.w[4] ^ b.w[4]) | (a.w[5] ^ b.w[5]) | (a.w[6] ^ b.w[6]) | (a.w[7] ^ b.w[7])) != 0;
 }
@@ -261,12 +267,14 @@ __device__ __forceinline__ u32 pick_targets(const TickParams& p, const StageView
 
 // What decides whether a node has anything to do this tick: its busy byte (pending work / host op) and the inbox
 // words of the previous tick (slot 0 kept, the other slots OR-ed).  13 bytes per node instead of 45.
-struct Pre { u32 busy, mL, mJ, mM, any; };
+struct Pre { u32 busy, mL, mJ, mM, any, qw; };
 template <bool R1>
 __device__ __forceinline__ Pre prefetch_node(const TickParams& p, u32 vl, bool kL, bool kJ, bool kM, u64 pol_first) {
   const u32 nl = p.stride, R = R1 ? 1u : p.R;
   Pre x;
   x.busy = p.busy[vl];
+  x.qw = p.qword[vl];                                   // slot-0 queue word (transmit budgets)
+  SFS_COUNT(6, 4);
   x.mL = kL ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R) * nl + vl, pol_first) : 0u;
   x.mJ = kJ ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R) * nl + vl, pol_first) : 0u;
   x.mM = kM ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R) * nl + vl, pol_first) : 0u;
@@ -311,6 +319,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
     } else {
       cur = ld_rec256(p.rec + 2 * (size_t)vl, pol_first);
     }
+    merge_q(cur, pre.qw);                                  // the record image everything below works on is record | budgets
   };
   if (upfront) load_state();
   const u32 busy = pre.busy;
@@ -357,15 +366,17 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
 
   // multi-slot runs: the record and inbox words of slot s+1 are requested while slot s is being processed
   Words nxt = {};
-  u32 nL = 0, nJ = 0, nM = 0;
+  u32 nL = 0, nJ = 0, nM = 0, nq = 0;
 #pragma unroll 1
   for (u32 s = 0; s < R; ++s) {
     const size_t idx = (size_t)s * nl + vl;
     if (!R1) {
-      if (s) { cur = nxt; mL = nL; mJ = nJ; mM = nM; }
+      if (s) { cur = nxt; merge_q(cur, nq); mL = nL; mJ = nJ; mM = nM; }
       if (s + 1 < R) {
         const size_t idn = idx + nl;
         nxt = ld_rec256(p.rec + 2 * idn, pol_first);
+        nq = p.qword[idn];
+        SFS_COUNT(6, 4);
         nL = kL ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R + s + 1) * nl + vl, pol_first) : 0;
         nJ = kJ ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R + s + 1) * nl + vl, pol_first) : 0;
         nM = kM ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R + s + 1) * nl + vl, pol_first) : 0;
@@ -476,7 +487,12 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
       any_pending |= pend;
     }
     pack_words(r, cur);
-    if (differs(cur, orig)) st_rec256(p.rec + 2 * idx, cur, pol_first);
+    {
+      Words o2 = orig, c2 = cur;                           // storage image: record without budgets, budgets in the queue word
+      const u32 q_old = split_q(o2), q_new = split_q(c2);
+      if (differs(c2, o2)) st_rec256(p.rec + 2 * idx, c2, pol_first);
+      if (q_new != q_old) { p.qword[idx] = q_new; SFS_COUNT(7, 4); }
+    }
     if (TRACE) c.hash += rec_hash((u64)s * p.n_global + v, make_uint4(cur.w[0], cur.w[1], cur.w[2], cur.w[3]), make_uint4(cur.w[4], cur.w[5], cur.w[6], cur.w[7]));
     if (r.inc >= INC_LIMIT) *p.overflow = 1;
   }
@@ -578,6 +594,8 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
           Pre pre;
           pre.busy = (a.x >> 16) & 0xffu; pre.any = (a.x >> 24) & 1u; pre.mL = a.y; pre.mJ = a.z; pre.mM = a.w;
           const u32 vl = ((tile0 + gt_s[g]) << TILE_SHIFT) + (a.x & 0xffu);
+          pre.qw = p.qword[vl];                               // not carried through the list: issued here, in flight with the state loads
+          SFS_COUNT(6, 4);
           const bool pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, false, pol_first, pol_last, c);
           if (mark && pend) pend_s[g] = 1;
         }
@@ -728,6 +746,7 @@ __global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constan
     if (vl < p.n_local) {
       Pre pre = {};
       pre.busy = p.busy[vl];
+      pre.qw = p.qword[vl];          // 4 B per node, read directly (not worth a sixth bulk copy per stage)
       pend = process_node<TRACE, FMAX, false, true, true>(p, sv, nullptr, vl, pre, kL, kJ, kM, mark, true, pol_first, pol_last, c);
     }
     if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + ti] = 1;
@@ -800,7 +819,10 @@ __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__
     const u32 wmask = p.watch[vl];
     for (u32 s = 0; s < p.R; ++s) {
       const size_t iv = (size_t)s * p.stride + vl, iu = (size_t)s * part_stride + ul;
-      const uint4 a0 = p.rec[2 * iv], b0 = p.rec[2 * iv + 1];
+      const uint4 a0 = p.rec[2 * iv];
+      uint4 b0 = p.rec[2 * iv + 1];
+      const u32 q0 = p.qword[iv];
+      merge_queue_word(b0, q0);
       Rec r, q;
       unpack(a0, b0, r);
       unpack(part_rec[2 * iu], part_rec[2 * iu + 1], q);
@@ -819,7 +841,12 @@ __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__
       uint4 a1, b1;
       pack(r, a1, b1);
       const bool ch = (a1.x ^ a0.x) | (a1.y ^ a0.y) | (a1.z ^ a0.z) | (a1.w ^ a0.w) | (b1.x ^ b0.x) | (b1.y ^ b0.y) | (b1.z ^ b0.z) | (b1.w ^ b0.w);
-      if (ch) { p.rec[2 * iv] = a1; p.rec[2 * iv + 1] = b1; }
+      if (ch) {
+        uint4 bs = b1;
+        const u32 q1 = split_queue_word(bs);
+        p.rec[2 * iv] = a1; p.rec[2 * iv + 1] = bs;
+        if (q1 != q0) p.qword[iv] = q1;
+      }
       if ((a1.y ^ a0.y) | (a1.z ^ a0.z) | (a1.w ^ a0.w) | (b1.x ^ b0.x) | (b1.y ^ b0.y) | (b1.z ^ b0.z) | (b1.w ^ b0.w)) d_changed++;   // status_time creep is not a change
       if (TRACE && ch) d_hash += rec_hash((u64)s * p.n_global + v, a1, b1) - rec_hash((u64)s * p.n_global + v, a0, b0);
       const bool now = (r.txl | r.txj | r.txm) || r.mlstate == ML_SUSPECT || (p.probe_every && ((p.down_mask >> s) & 1) && !self && ((wmask >> s) & 1) && r.mlstate == ML_ALIVE);
@@ -972,12 +999,23 @@ __global__ void extract_kernel(const uint4* rec, const u64* node_state, u32 n_lo
   }
 }
 
-__global__ void __launch_bounds__(BLOCK) state_hash_kernel(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 n_global, u32 R, u64* out) {
+__global__ void compose_records_kernel(const uint4* rec, const u32* qword, u32 n_local, u32 stride, u32 slot, uint4* out) {
+  const u32 vl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (vl >= n_local) return;
+  const size_t idx = (size_t)slot * stride + vl;
+  uint4 b = rec[2 * idx + 1];
+  merge_queue_word(b, qword[idx]);
+  out[2 * (size_t)vl] = rec[2 * idx]; out[2 * (size_t)vl + 1] = b;
+}
+
+__global__ void __launch_bounds__(BLOCK) state_hash_kernel(const uint4* rec, const u32* qword, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 n_global, u32 R, u64* out) {
   u64 h = 0;
   for (u32 vl = blockIdx.x * BLOCK + threadIdx.x; vl < n_local; vl += gridDim.x * BLOCK) {
     for (u32 s = 0; s < R; ++s) {
       const size_t idx = (size_t)s * stride + vl;
-      h += rec_hash((u64)s * n_global + first + vl, rec[2 * idx], rec[2 * idx + 1]);
+      uint4 b = rec[2 * idx + 1];
+      merge_queue_word(b, qword[idx]);
+      h += rec_hash((u64)s * n_global + first + vl, rec[2 * idx], b);
     }
     h += node_hash((u64)R * n_global + first + vl, node_state[vl]);
   }
@@ -987,7 +1025,7 @@ __global__ void __launch_bounds__(BLOCK) state_hash_kernel(const uint4* rec, con
 
 // out[0] = max clock, out[1] = queued intents, out[2+2s] = min key, out[3+2s] = max key of slot s over
 // up nodes other than the subject (agreement check for Stats / convergence studies).
-__global__ void __launch_bounds__(BLOCK) summary_kernel(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 R, const u32* subj, u64* out) {
+__global__ void __launch_bounds__(BLOCK) summary_kernel(const uint4* rec, const u32* qword, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 R, const u32* subj, u64* out) {
   u64 maxclock = 0, queued = 0;
   for (u32 s = 0; s < R; ++s) {
     u64 kmin = ~0ull, kmax = 0;
@@ -998,7 +1036,7 @@ __global__ void __launch_bounds__(BLOCK) summary_kernel(const uint4* rec, const 
       const size_t idx = (size_t)s * stride + vl;
       Rec r;
       unpack(rec[2 * idx], rec[2 * idx + 1], r);
-      queued += (r.txj ? 1 : 0) + (r.txl ? 1 : 0);
+      { const u32 q = qword[idx]; queued += ((q & 0xffu) ? 1 : 0) + (((q >> 8) & 0xffu) ? 1 : 0); }
       if ((ns & NS_UP) && sid != first + vl) {
         const bool known = r.flags & 1;
         const u64 key = (((u64)r.st << 32) ^ ((u64)r.inc << 8) ^ ((u64)(known ? r.status : 0) << 4) ^ r.mlstate ^ ((u64)known << 63));
@@ -1101,11 +1139,14 @@ void launch_mark_events(u8* busy, u8* hot_rd, const u32* ev_node, u32 ev_begin, 
 void launch_extract(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 slot, int what, void* out, cudaStream_t st) {
   SFS_LAUNCH((n_local + 255) / 256, 256, 0, st, extract_kernel)(rec, node_state, n_local, stride, slot, what, out);
 }
-void launch_state_hash(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 n_global, u32 R, u64* out, cudaStream_t st) {
-  SFS_LAUNCH(SFS_SMS * 4, BLOCK, 0, st, state_hash_kernel)(rec, node_state, n_local, stride, first, n_global, R, out);
+void launch_compose_records(const uint4* rec, const u32* qword, u32 n_local, u32 stride, u32 slot, uint4* out, cudaStream_t st) {
+  SFS_LAUNCH((n_local + 255) / 256, 256, 0, st, compose_records_kernel)(rec, qword, n_local, stride, slot, out);
 }
-void launch_summary(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 R, const u32* subj_dev, u64* out, cudaStream_t st) {
-  SFS_LAUNCH(SFS_SMS * 4, BLOCK, 0, st, summary_kernel)(rec, node_state, n_local, stride, first, R, subj_dev, out);
+void launch_state_hash(const uint4* rec, const u32* qword, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 n_global, u32 R, u64* out, cudaStream_t st) {
+  SFS_LAUNCH(SFS_SMS * 4, BLOCK, 0, st, state_hash_kernel)(rec, qword, node_state, n_local, stride, first, n_global, R, out);
+}
+void launch_summary(const uint4* rec, const u32* qword, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 R, const u32* subj_dev, u64* out, cudaStream_t st) {
+  SFS_LAUNCH(SFS_SMS * 4, BLOCK, 0, st, summary_kernel)(rec, qword, node_state, n_local, stride, first, R, subj_dev, out);
 }
 
 }  // namespace sfs

@@ -32,7 +32,8 @@ struct TickParams {
   Rules rules;
   u32 subj[MAX_SLOTS];
   // state in HBM
-  uint4* rec;                 // [R][n_local] records, 2 × uint4 each
+  uint4* rec;                 // [R][stride] records, 2 × uint4 each (transmit-budget bytes kept zero: they live in qword)
+  u32* qword;                 // [R][stride] queue words: tx_join | tx_leave << 8 | tx_ml << 16
   u32* inbox_rd;              // [3][R][n_local] reduced inbox filled by the previous tick (value+1, 0 = empty)
   u32* inbox_wr;              // [3][R][n_local] inbox the sends of this tick reduce into
   u64* node_state;            // [n_local]  clock | up | SerfState
@@ -96,8 +97,9 @@ void launch_publish(const PublishParams& p, cudaStream_t st);
 void launch_init_state(uint4* rec, u64* node_state, u32 n_local, u32 stride, u32 R, u32 init_st, u32 init_clock, cudaStream_t st);
 void launch_mark_events(u8* busy, u8* hot_rd, const u32* ev_node, u32 ev_begin, u32 ev_end, u32 first, u32 n_local, cudaStream_t st);
 void launch_extract(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 slot, int what, void* out, cudaStream_t st);
-void launch_state_hash(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 n_global, u32 R, u64* out, cudaStream_t st);
-void launch_summary(const uint4* rec, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 R, const u32* subj_dev, u64* out /*[2 + 2*R + 2]*/, cudaStream_t st);
+void launch_compose_records(const uint4* rec, const u32* qword, u32 n_local, u32 stride, u32 slot, uint4* out, cudaStream_t st);
+void launch_state_hash(const uint4* rec, const u32* qword, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 n_global, u32 R, u64* out, cudaStream_t st);
+void launch_summary(const uint4* rec, const u32* qword, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 R, const u32* subj_dev, u64* out /*[2 + 2*R + 2]*/, cudaStream_t st);
 int tick_grid_size(u32 n_local, int ctas_per_sm);
 void launch_compute_watch(const u32* row_ptr, const u32* col, const u32* subj_dev, u32 R, u32 first, u32 n_local, u16* watch, cudaStream_t st);
 void launch_apply_watch(const u16* watch, u32 n_local, u8* busy, u8* hot0, u8* hot1, cudaStream_t st);
