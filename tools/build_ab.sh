@@ -6,12 +6,12 @@
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 mkdir -p "$ROOT/serf_b200/ab" "$ROOT/.scratch"
-for b in main r2-queue-word; do
+for b in main pre-queue-word; do
   wt="$ROOT/.scratch/wt-$b"
   rm -rf "$wt"; git -C "$ROOT" worktree prune
   git -C "$ROOT" worktree add -q --detach "$wt" "$b"
   (cd "$wt/serf_b200/csrc" && nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden \
-      -shared -o "$ROOT/serf_b200/ab/libserfsim_${b#r2-}.so" *.cu)
+      -shared -o "$ROOT/serf_b200/ab/libserfsim_${b}.so" *.cu)
   git -C "$ROOT" worktree remove --force "$wt"
-  echo "built serf_b200/ab/libserfsim_${b#r2-}.so from $b ($(git -C "$ROOT" rev-parse --short "$b"))"
+  echo "built serf_b200/ab/libserfsim_${b}.so from $b ($(git -C "$ROOT" rev-parse --short "$b"))"
 done

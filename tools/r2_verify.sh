@@ -15,7 +15,7 @@ if [ $rc -ne 0 ]; then     # localise: compaction off
   SERFSIM_COMPACT=0 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x > gpurun_out/r2_tests_nocompact.log 2>&1
   tail -3 gpurun_out/r2_tests_nocompact.log
 fi
-for v in main queue-word; do
+for v in main pre-queue-word; do
   lib=$PWD/serf_b200/ab/libserfsim_$v.so
   [ -f "$lib" ] || continue
   SERFSIM_LIB=$lib timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_$v.json 2>> gpurun_out/r2_bench.err
@@ -24,11 +24,6 @@ for v in main queue-word; do
 done
 SERFSIM_COMPACT=0 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_main_nocompact.json 2>> gpurun_out/r2_bench.err
 SERFSIM_COMPACT=0 timeout 300 python tools/tick_profile.py --out gpurun_out/r2_ticks_main_nocompact.json > gpurun_out/r2_ticks_main_nocompact.log 2>&1
-# queue-word parity (its own library against the parity suites) if the main suite is green
-if [ $rc -eq 0 ]; then
-  SERFSIM_LIB=$PWD/serf_b200/ab/libserfsim_queue-word.so timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_golden.py -m gpu -q -x > gpurun_out/r2_tests_queueword.log 2>&1
-  tail -3 gpurun_out/r2_tests_queueword.log
-fi
 # the new features at BASELINE scale (only if their parity passed)
 if [ $rc -eq 0 ]; then
   timeout 600 python tools/feature_profile.py --what events --out gpurun_out/r2_events.json > gpurun_out/r2_events.log 2>&1; tail -1 gpurun_out/r2_events.log
