@@ -24,6 +24,9 @@ for v in main pre-queue-word; do
 done
 SERFSIM_COMPACT=0 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_main_nocompact.json 2>> gpurun_out/r2_bench.err
 SERFSIM_COMPACT=0 timeout 300 python tools/tick_profile.py --out gpurun_out/r2_ticks_main_nocompact.json > gpurun_out/r2_ticks_main_nocompact.log 2>&1
+# issue-rate micro-benchmarks behind the LSU-bound reading of the plateau (DESIGN "What comes next" item 4)
+[ -x tools/ubench/lsu_red ] || nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o tools/ubench/lsu_red tools/ubench/lsu_red.cu
+timeout 120 tools/ubench/lsu_red > gpurun_out/r2_ubench.txt 2>&1; cat gpurun_out/r2_ubench.txt
 # the new features at BASELINE scale (only if their parity passed)
 if [ $rc -eq 0 ]; then
   timeout 600 python tools/feature_profile.py --what events --out gpurun_out/r2_events.json > gpurun_out/r2_events.log 2>&1; tail -1 gpurun_out/r2_events.log
