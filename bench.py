@@ -283,10 +283,15 @@ def main():
         else:
             peak, peak_src = HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
         tick_launches = launches                       # every kernel this library launched in the timed region (tick kernels ≥ 98 % of them)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if world == 1 and os.path.exists(tpath):       # DRAM bytes per tick launch of this workload from the committed ncu capture
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        traffic, traffic_src = None, None
+        import glob
+        tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))     # newest round's ncu capture of this workload
+        if world == 1 and tfiles:                      # DRAM bytes per tick launch from the committed ncu capture
+            tj = json.load(open(tfiles[-1]))
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_src = f"{os.path.relpath(tfiles[-1], ROOT)} (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per tick launch; {tj.get('source', '')})"
+            if os.path.basename(tfiles[-1]) == "r1_traffic.json":
+                traffic_src += " — captured on the round-1 kernel BEFORE multi-tile compaction and the queue-word layout"
         # per-GPU: each GPU runs its own tick kernel over its shard; algorithmic bytes split evenly
         achieved = (total_eu / world) * be / (dev_ms * 1e-3) / 1e9
         h2d = len(sc.ops) * 12
@@ -295,7 +300,7 @@ def main():
                 "dtype": "u32", "data": "synthetic", "config": config_dict(args, sc),
                 "ticks_to_convergence": ticks_list[-1], "edge_updates_per_step": eu_per_step, "p_dirty": p_dirty,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "traffic_source": "profiles/r1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per tick launch; captured on the round-1 kernel BEFORE multi-tile compaction of unsaturated ticks — saturated ticks, which carry the traffic, are unchanged)" if traffic else None,
+                             "traffic": traffic, "traffic_source": traffic_src,
                              "algorithmic_bytes_per_launch": total_eu * be / world / max(1, tick_launches), "peak_source": peak_src, "kernel": "tick_kernel", "bytes_per_edge_update": be,
                              "launches": tick_launches, "avg_launch_us": 1e3 * dev_ms / max(1, tick_launches)},
                 "e2e": {"value": total_eu / wall_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
