@@ -24,3 +24,11 @@ def test_other_ranks_exit_quietly_under_torchrun_env():
     out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "3",
                                    "--nodes", "20000", "--ref-nodes", "20000"], cwd=ROOT, env=env, timeout=120).decode().strip()
     assert out == ""
+
+
+def test_b200_arm_dry_run_against_the_host_build():
+    """bench.py cannot run here (no GPU); its Python logic can: tests/bench_dry_run.py stubs the torch.cuda calls and points the
+    driver at the host-compiled library, then checks the JSON line against the contract."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "bench_dry_run.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "bench dry run ok" in r.stdout
