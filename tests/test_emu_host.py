@@ -142,3 +142,16 @@ def test_cpp_host_layer_end_to_end(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "left=255 leave_events=1" in r.stdout and "seen=256/256 delivered=512" in r.stdout
+
+
+def test_graft_entry_smoke_logic_runs(monkeypatch):
+    """__graft_entry__.smoke() (the driver's first GPU check) with the library swapped for the host-compiled build: the
+    Python side of the smoke test itself is exercised here, so a typo cannot be what fails on the GPU box."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import __graft_entry__ as ge
+    from serf_b200 import sim
+    monkeypatch.setattr(sim, "_LIB", lib())
+    ge.smoke()
