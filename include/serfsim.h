@@ -214,8 +214,10 @@ int serfsim_set_event_cb (serfsim_t* h, serfsim_event_cb cb, void* user);
  * clock at that tick.  Call before scheduling operations; n_events = 0 switches user events off.
  * Works sharded (an event crossing shards is one 8-byte window entry carrying its Lamport time; call this BEFORE
  * serfsim_comm_export, it resizes the receive windows; counters of
- * serfsim_user_event_stats are global sums, event_time is the local shard's maximum); not together with
- * push-pull rounds in this version. */
+ * serfsim_user_event_stats are global sums, event_time is the local shard's maximum).  With push-pull rounds on,
+ * a round also witnesses the partner's event clock and replays its event ring (`serf/delegate.rs:469-474, 539-552`).
+ * Cluster runs need one Lamport time per ring slot: two tracked events 512·k apart fail the run with SERFSIM_E_INVAL
+ * (the slot-reuse quirk of handle_user_event is kept in the rules and pinned at handler level). */
 int serfsim_set_user_events(serfsim_t* h, uint32_t n_events, const uint32_t* content_ids /*[n_events]*/);
 int serfsim_event_time       (serfsim_t* h, uint64_t* out /*[count]*/);                  /* event_clock.time() per node, `serf.rs:139`              */
 int serfsim_user_event_seen  (serfsim_t* h, uint32_t event, uint8_t* out /*[count]*/);   /* 1: the node delivered the event to its EventSubscriber */

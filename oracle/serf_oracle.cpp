@@ -620,6 +620,7 @@ struct TickSim {
   u64 tot_events = 0;
   // user events
   u32 ue_n = 0; u32 ue_content[8] = {0}; u32 ue_ltime[8] = {0}; u32 ue_injected = 0;
+  u32 ue_stamped = 0; bool ue_alias_error = false;             // events whose origin has fired; two of them in one ring slot with different ltimes
   std::vector<UeNodeB> uen;
   std::vector<std::vector<UeMsg>> ue_mail, ue_mail_next;       // [producer range][consumer range], like `mail`
   u64 ue_tot[5] = {0, 0, 0, 0, 0};                             // messages, edge_updates, delivered, duplicates, too_old
@@ -656,7 +657,7 @@ struct TickSim {
     anomaly.assign(byz_n ? N : 0, 0); for (auto& x : byz_tot) x = 0;
   }
   void ue_reset() {
-    uen.assign(ue_n ? N : 0, UeNodeB{}); ue_mail.clear(); ue_mail_next.clear(); ue_injected = 0;
+    uen.assign(ue_n ? N : 0, UeNodeB{}); ue_mail.clear(); ue_mail_next.clear(); ue_injected = 0; ue_stamped = 0; ue_alias_error = false;
     for (auto& x : ue_ltime) x = 0;
     for (auto& x : ue_tot) x = 0;
   }
@@ -681,7 +682,8 @@ struct TickSim {
   void ue_record(u32 v, u32 out[4]) const {                    // the 16-byte event record the CUDA path keeps
     const UeNodeB& nd = uen[v];
     u32 seen = 0, first = 0;
-    for (auto& kv : nd.ring) { for (u32 e : kv.second.events) seen |= 1u << e; first |= 1u << kv.second.events[0]; }
+    // `first` is a derived field: the lowest-index event of each occupied ring slot — independent of arrival order
+    for (auto& kv : nd.ring) { u32 lo = 0xffffffffu; for (u32 e : kv.second.events) { seen |= 1u << e; lo = std::min(lo, e); } first |= 1u << lo; }
     out[0] = nd.clock; out[1] = seen | (first << 8); out[2] = 0; out[3] = 0;
     for (u32 e = 0; e < 4; ++e) { out[2] |= (u32)nd.tx[e] << (8 * e); out[3] |= (u32)nd.tx[4 + e] << (8 * e); }
   }
@@ -991,7 +993,10 @@ struct TickSim {
     }
     if (ue_n) {
       ue_mail.swap(ue_mail_next);
-      for (auto& st : ue_stamps) ue_ltime[st.first] = st.second;        // visible to receivers from the next tick on
+      for (auto& st : ue_stamps) { ue_ltime[st.first] = st.second; ue_stamped |= 1u << st.first; }   // visible to receivers from the next tick on
+      // cluster runs need one Lamport time per ring slot (the packed record derives the slot's ltime from its events)
+      for (u32 a = 0; a < ue_n; ++a) for (u32 b = a + 1; b < ue_n; ++b)
+        if (((ue_stamped >> a) & 1) && ((ue_stamped >> b) & 1) && ue_ltime[a] % 512 == ue_ltime[b] % 512 && ue_ltime[a] != ue_ltime[b]) ue_alias_error = true;
       for (u32 c = 0; c < T; ++c) for (int i = 0; i < 5; ++i) ue_tot[i] += ue_rows[(size_t)c * 5 + i];
     }
     // ---------------- anti-entropy round: memberlist push-pull + SerfDelegate::merge_remote_state ----------------
@@ -1004,6 +1009,8 @@ struct TickSim {
     if (pp && (t + 1) % pp == 0 && own_count == N) {
       const std::vector<View> srec = rec;
       const std::vector<NodeB> snode = node;
+      const std::vector<UeNodeB> suen = uen;                    // PushPullMessage.event_ltime / .events of every node (delegate.rs:386-425)
+      std::vector<u64> pp_ue((size_t)T * 3, 0);
       auto ppwork = [&](u32 c) {
         serfsim_tick_row_t& row = rows[c];
         const u32 v0 = c * chunk, v1 = std::min<u64>(N, (u64)(c + 1) * chunk);
@@ -1016,6 +1023,16 @@ struct TickSim {
           const u32 u = col[r0 + ((draw16(w, 0) * deg) >> 16)];
           if (u == v || !snode[u].up) continue;
           if (snode[u].clock > 0) witness32(nd.clock, snode[u].clock - 1);            // delegate.rs:466-468
+          if (ue_n) {                                                                  // delegate.rs:469-474 and 539-552
+            UeNodeB& un = uen[v];
+            const UeNodeB& pu = suen[u];
+            if (pu.clock > 0) witness32(un.clock, pu.clock - 1);
+            for (auto& kv : pu.ring)                                                   // the partner's buffer in ring-index order
+              for (u32 e : kv.second.events) {
+                const int oc = ue_handle(un, e, kv.second.ltime);                      // handled, result discarded: nothing is re-queued
+                if (oc == 0) { pp_ue[(size_t)c * 3]++; row.changed++; } else if (oc == 1) pp_ue[(size_t)c * 3 + 1]++; else pp_ue[(size_t)c * 3 + 2]++;
+              }
+          }
           for (u32 s = 0; s < R; ++s) {
             View& r = at(s, v);
             const View before = r;
@@ -1046,6 +1063,7 @@ struct TickSim {
       };
       if (T == 1) ppwork(0);
       else { std::vector<std::thread> th; for (u32 c = 0; c < T; ++c) th.emplace_back(ppwork, c); for (auto& x : th) x.join(); }
+      for (u32 c = 0; c < T; ++c) { ue_tot[2] += pp_ue[(size_t)c * 3]; ue_tot[3] += pp_ue[(size_t)c * 3 + 1]; ue_tot[4] += pp_ue[(size_t)c * 3 + 2]; }
     }
     serfsim_tick_row_t row{};
     for (auto& r : rows) { row.packets += r.packets; row.edge_updates += r.edge_updates; row.messages += r.messages; row.changed += r.changed;
@@ -1197,7 +1215,8 @@ ORC int oracle_sim_inject(void* p, u32 tick, u32 op, u32 node, u32 slot) {
   s->max_event_tick = s->any_event ? std::max(s->max_event_tick, tick) : tick; s->any_event = true;
   return 0;
 }
-ORC int oracle_sim_step(void* p, u32 n) { auto* s = (TickSim*)p; if (s->row_ptr.empty()) { g_err = "no topology"; return SERFSIM_E_INVAL; } for (u32 i = 0; i < n; ++i) s->step_one(); return 0; }
+static int ue_alias_check(TickSim* s) { if (s->ue_alias_error) { g_err = "user events: two tracked events share a ring slot with different Lamport times (not supported in cluster runs)"; return SERFSIM_E_INVAL; } return 0; }
+ORC int oracle_sim_step(void* p, u32 n) { auto* s = (TickSim*)p; if (s->row_ptr.empty()) { g_err = "no topology"; return SERFSIM_E_INVAL; } for (u32 i = 0; i < n; ++i) s->step_one(); return ue_alias_check(s); }
 ORC int oracle_sim_run_until_converged(void* p, u32 max_ticks, u32* ticks_out) {
   auto* s = (TickSim*)p; if (s->row_ptr.empty()) return SERFSIM_E_INVAL;
   for (u32 i = 0; i < max_ticks; ++i) {
@@ -1210,6 +1229,7 @@ ORC int oracle_sim_run_until_converged(void* p, u32 max_ticks, u32* ticks_out) {
     const bool pp_ok = !pp || ((s->tick % pp) == 0 && r.changed == 0);
     // with byzantine injectors stale entries are in flight forever: quiescent = no honest traffic AND nothing merged this tick
     const bool byz_ok = !s->byz_n || r.changed == 0;
+    if (s->ue_alias_error) return ue_alias_check(s);
     if (r.pending == 0 && r.edge_updates == 0 && !s->future_events() && pp_ok && byz_ok) { if (ticks_out) *ticks_out = s->tick - 1; return 0; }
   }
   if (ticks_out) *ticks_out = s->tick;
@@ -1270,7 +1290,7 @@ ORC int oracle_sim_byzantine_stats(void* p, serfsim_byz_stats_t* o) {
 ORC int oracle_sim_set_user_events(void* p, u32 n, const u32* content) {
   auto* s = (TickSim*)p;
   if (n > 8 || (n && !content) || s->tick != 0 || !s->events.empty()) { g_err = "bad set_user_events"; return SERFSIM_E_INVAL; }
-  if (n && (s->own_count != s->N || s->cfg.push_pull_interval_ticks > 0)) { g_err = "user events: single shard, no push-pull"; return SERFSIM_E_INVAL; }
+  if (n && s->own_count != s->N) { g_err = "user events: single oracle instance"; return SERFSIM_E_INVAL; }
   s->ue_n = n; for (u32 e = 0; e < n; ++e) s->ue_content[e] = content[e];
   s->ue_reset();
   return 0;

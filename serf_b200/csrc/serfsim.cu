@@ -110,7 +110,10 @@ struct serfsim {
   u32* d_ue_ltime = nullptr;       // [MAX_UEVENTS]
   u64* d_ue_totals = nullptr;      // [8]
   u32 ue_injected = 0;             // tracked events already scheduled (each may be injected once)
-  u32 ue_origin[MAX_UEVENTS] = {0};  // origin node of each scheduled event (its shard is the one that stamps the Lamport time)
+  uint4* d_ue_snap = nullptr;      // push-pull rounds: snapshot of the event records (partners read it)
+  const uint4** d_peer_ue_snap = nullptr;
+  u32 ue_origin[MAX_UEVENTS] = {0};
+  u32 ue_fire_tick[MAX_UEVENTS] = {0};  // origin node of each scheduled event (its shard is the one that stamps the Lamport time)
   // byzantine injectors (BASELINE configs[4]): allocated by serfsim_set_byzantine
   u32 byz_n = 0, byz_delta = 2;    // byz_n: injectors of THIS shard
   bool byz_on = false;             // any injector anywhere (all ranks agree): changes the convergence rule and the drain kernel
@@ -326,6 +329,11 @@ int launch_ticks(serfsim* h, u32 n) {
       if (!h->d_snap_rec) { CU(cudaMalloc(&h->d_snap_rec, rb)); CU(cudaMalloc(&h->d_snap_node, nb)); }
       CU(cudaMemcpyAsync(h->d_snap_rec, h->d_rec, rb, cudaMemcpyDeviceToDevice, h->stream));
       CU(cudaMemcpyAsync(h->d_snap_node, h->d_node, nb, cudaMemcpyDeviceToDevice, h->stream));
+      if (h->ue_table.n) {
+        CU(cudaMemcpyAsync(h->d_ue_snap, h->d_ue_state, (size_t)h->stride * 16, cudaMemcpyDeviceToDevice, h->stream));
+        p.ue_table = h->ue_table; p.ue_state = h->d_ue_state; p.ue_snap = h->d_ue_snap; p.ue_snap_peer = h->d_peer_ue_snap;
+        p.ue_ltime = h->d_ue_ltime; p.ue_totals = h->d_ue_totals;
+      }
       if (h->cfg.world_size > 1) {
         // partners may live on other GPUs: their snapshots are read through the peer mappings.  Rounds are rare (every
         // push_pull_interval ticks) and always the first tick of a convergence chunk, so two host barriers are affordable:
@@ -359,6 +367,24 @@ int finish_timing(serfsim* h) {
 }
 
 int check_overflow(serfsim* h) {
+  if (h->ue_table.n) {
+    // Cluster runs need one Lamport time per ring slot: the packed event record derives a slot's ltime from the events in it.
+    // (Two tracked events 512·k apart would alias — the quirk itself is kept in ue_handle and pinned by the handler tests.)
+    u32 lt[MAX_UEVENTS];
+    CU(cudaMemcpy(lt, h->d_ue_ltime, sizeof(lt), cudaMemcpyDeviceToHost));
+    if (h->cfg.world_size > 1 && h->allreduce) {           // the origin's shard holds the stamp; the others may not have seen it yet
+      u64 v[MAX_UEVENTS];
+      for (u32 e = 0; e < MAX_UEVENTS; ++e) v[e] = (((h->ue_injected >> e) & 1u) && h->ue_origin[e] - h->first < h->count) ? lt[e] : 0;
+      h->allreduce(h->comm_user, v, MAX_UEVENTS);
+      for (u32 e = 0; e < MAX_UEVENTS; ++e) lt[e] = (u32)v[e];
+    }
+    for (u32 a = 0; a < h->ue_table.n; ++a)
+      for (u32 b = a + 1; b < h->ue_table.n; ++b) {
+        const bool fa = ((h->ue_injected >> a) & 1u) && h->ue_fire_tick[a] < h->tick, fb = ((h->ue_injected >> b) & 1u) && h->ue_fire_tick[b] < h->tick;
+        if (fa && fb && lt[a] % UE_RING == lt[b] % UE_RING && lt[a] != lt[b])
+          return fail(SERFSIM_E_INVAL, "user events: two tracked events share a ring slot with different Lamport times (not supported in cluster runs)");
+      }
+  }
   u32 ov = 0;
   CU(cudaMemcpy(&ov, h->d_overflow, 4, cudaMemcpyDeviceToHost));
   if (ov == 1) return fail(SERFSIM_E_OVERFLOW, "a Lamport time or incarnation left the 32-bit device range");
@@ -461,6 +487,7 @@ void free_all(serfsim* h) {
   cudaFree(h->d_ev_node); cudaFree(h->d_ev_op); cudaFree(h->d_ev_slot); cudaFree(h->d_trace); cudaFree(h->d_kinds); cudaFree(h->d_ones);
   cudaFree(h->d_overflow); cudaFree(h->d_subj); cudaFree(h->d_scratch); cudaFree(h->d_stage);
   cudaFree(h->d_byz_ids); cudaFree(h->d_anomaly); cudaFree(h->d_byz_totals); cudaFree(h->d_peer_anomaly);
+  cudaFree(h->d_ue_snap); cudaFree(h->d_peer_ue_snap);
   cudaFree(h->d_ue_state); cudaFree(h->d_ue_inbox[0]); cudaFree(h->d_ue_inbox[1]); cudaFree(h->d_ue_ltime); cudaFree(h->d_ue_totals);
   for (int par = 0; par < 2; ++par) { cudaFree(h->d_win_data[par]); cudaFree(h->d_peer_data[par]); }
   cudaFree(h->d_ctrl); cudaFree(h->d_send_count); cudaFree(h->d_peer_ctrl);
@@ -715,7 +742,7 @@ int serfsim_inject(serfsim_t* h, uint32_t tick, uint32_t op, uint32_t node, uint
   else if ((op == SERFSIM_OP_JOIN || op == SERFSIM_OP_LEAVE) && slot_of(h, node) < 0)
     return fail(SERFSIM_E_INVAL, "join/leave origin must be a tracked subject");
   if (!h->op_keys.insert(((u64)tick << 32) | node).second) return fail(SERFSIM_E_INVAL, "one operation per node per tick");
-  if (op == SERFSIM_OP_USER_EVENT) { h->ue_injected |= 1u << slot; h->ue_origin[slot] = node; }
+  if (op == SERFSIM_OP_USER_EVENT) { h->ue_injected |= 1u << slot; h->ue_origin[slot] = node; h->ue_fire_tick[slot] = tick; }
   h->ops.push_back(HostOp{tick, op, node, slot, h->op_seq++});
   h->ops_dirty = true;
   return 0;
@@ -965,7 +992,6 @@ int serfsim_set_user_events(serfsim_t* h, uint32_t n_events, const uint32_t* con
   if (n_events > MAX_UEVENTS) return fail(SERFSIM_E_INVAL, "at most SERFSIM_MAX_USER_EVENTS tracked user events");
   if (n_events && !content_ids) return fail(SERFSIM_E_INVAL, "null content ids");
   if (h->tick != 0 || !h->ops.empty()) return fail(SERFSIM_E_INVAL, "serfsim_set_user_events: call before any operation is scheduled (or after serfsim_reset)");
-  if (n_events && h->cfg.push_pull_interval_ticks > 0) return fail(SERFSIM_E_INVAL, "user events cannot be combined with push-pull rounds in this version");
   if (h->cfg.world_size > 1) {
     // every event bit bound for another shard is one window entry: up to fanout · n_events per node and tick on top of the
     // membership entries the windows were sized for.  The windows are exported by serfsim_comm_export, so this must come first.
@@ -988,6 +1014,11 @@ int serfsim_set_user_events(serfsim_t* h, uint32_t n_events, const uint32_t* con
     CU(cudaMalloc(&h->d_ue_inbox[1], (size_t)h->stride * 4));
     CU(cudaMalloc(&h->d_ue_ltime, MAX_UEVENTS * 4));
     CU(cudaMalloc(&h->d_ue_totals, 8 * 8));
+  }
+  if (n_events && h->cfg.push_pull_interval_ticks > 0 && !h->d_ue_snap) {
+    if (h->connected) return fail(SERFSIM_E_INVAL, "serfsim_set_user_events: in sharded runs with push-pull rounds call it before serfsim_comm_export (the event snapshot is exported)");
+    CU(cudaMalloc(&h->d_ue_snap, (size_t)h->stride * 16));
+    CU(cudaMalloc(&h->d_peer_ue_snap, sizeof(void*) * 8));
   }
   h->ue_table = UeTable{};
   h->ue_table.n = n_events;
@@ -1088,7 +1119,7 @@ int serfsim_tick_times(serfsim_t* h, uint32_t first_tick, uint32_t n, float* ms_
 }
 
 // ---- multi-GPU: CUDA IPC windows ----------------------------------------------------------
-struct comm_blob { cudaIpcMemHandle_t data[2]; cudaIpcMemHandle_t ctrl; cudaIpcMemHandle_t snap_rec, snap_node, anomaly; u32 win_cap; u32 rank; u32 has_snap; u32 pad; };
+struct comm_blob { cudaIpcMemHandle_t data[2]; cudaIpcMemHandle_t ctrl; cudaIpcMemHandle_t snap_rec, snap_node, anomaly, ue_snap; u32 win_cap; u32 rank; u32 has_snap; u32 has_ue_snap; };
 
 size_t serfsim_comm_blob_size(void) { return sizeof(comm_blob); }
 
@@ -1099,6 +1130,7 @@ int serfsim_comm_export(serfsim_t* h, void* blob) {
   for (int par = 0; par < 2; ++par) CU(cudaIpcGetMemHandle(&b.data[par], h->d_win_data[par]));
   CU(cudaIpcGetMemHandle(&b.ctrl, h->d_ctrl));
   CU(cudaIpcGetMemHandle(&b.anomaly, h->d_anomaly));
+  if (h->d_ue_snap) { CU(cudaIpcGetMemHandle(&b.ue_snap, h->d_ue_snap)); b.has_ue_snap = 1; }
   b.win_cap = h->win_cap; b.rank = (u32)h->cfg.rank;
   if (h->d_snap_rec) {                              // push-pull rounds are on: partners on other GPUs read these
     CU(cudaIpcGetMemHandle(&b.snap_rec, h->d_snap_rec)); CU(cudaIpcGetMemHandle(&b.snap_node, h->d_snap_node));
@@ -1119,11 +1151,18 @@ int serfsim_comm_connect(serfsim_t* h, const void* blobs) {
   std::vector<const uint4*> psr(8, nullptr);
   std::vector<const u64*> psn(8, nullptr);
   std::vector<u8*> pan(8, nullptr);
+  std::vector<const uint4*> pus(8, nullptr);
   for (int r = 0; r < W; ++r) {
     if (bs[r].rank != (u32)r || bs[r].win_cap != h->win_cap) return fail(SERFSIM_E_COMM, "blob order / window size mismatch");
     if ((bs[r].has_snap != 0) != (h->d_snap_rec != nullptr)) return fail(SERFSIM_E_COMM, "push_pull_interval_ticks differs between ranks");
-    if (r == h->cfg.rank) { pd[0][r] = h->d_win_data[0]; pd[1][r] = h->d_win_data[1]; pc[r] = h->d_ctrl; psr[r] = h->d_snap_rec; psn[r] = h->d_snap_node; pan[r] = h->d_anomaly; continue; }
+    if (r == h->cfg.rank) { pd[0][r] = h->d_win_data[0]; pd[1][r] = h->d_win_data[1]; pc[r] = h->d_ctrl; psr[r] = h->d_snap_rec; psn[r] = h->d_snap_node; pan[r] = h->d_anomaly; pus[r] = h->d_ue_snap; continue; }
     void* ptr = nullptr;
+    if ((bs[r].has_ue_snap != 0) != (h->d_ue_snap != nullptr)) return fail(SERFSIM_E_COMM, "user events / push-pull configuration differs between ranks");
+    if (bs[r].has_ue_snap) {
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, bs[r].ue_snap, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) return fail(SERFSIM_E_COMM, std::string("cudaIpcOpenMemHandle(event snapshot): ") + cudaGetErrorString(e));
+      h->ipc_opened.push_back(ptr); pus[r] = (const uint4*)ptr;
+    }
     {
       cudaError_t e = cudaIpcOpenMemHandle(&ptr, bs[r].anomaly, cudaIpcMemLazyEnablePeerAccess);
       if (e != cudaSuccess) return fail(SERFSIM_E_COMM, std::string("cudaIpcOpenMemHandle(flags): ") + cudaGetErrorString(e));
@@ -1149,6 +1188,7 @@ int serfsim_comm_connect(serfsim_t* h, const void* blobs) {
   for (int par = 0; par < 2; ++par) CU(cudaMemcpy(h->d_peer_data[par], pd[par].data(), sizeof(u64*) * 8, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(h->d_peer_ctrl, pc.data(), sizeof(u32*) * 8, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(h->d_peer_anomaly, pan.data(), sizeof(void*) * 8, cudaMemcpyHostToDevice));
+  if (h->d_ue_snap) CU(cudaMemcpy(h->d_peer_ue_snap, pus.data(), sizeof(void*) * 8, cudaMemcpyHostToDevice));
   if (h->d_snap_rec) {
     CU(cudaMemcpy(h->d_peer_snap_rec, psr.data(), sizeof(void*) * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->d_peer_snap_node, psn.data(), sizeof(void*) * 8, cudaMemcpyHostToDevice));

@@ -854,6 +854,22 @@ __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__
       any_pending |= now;
       if (r.inc >= INC_LIMIT) *p.overflow = 1;
     }
+    if (p.ue_table.n) {                                        // the partner's event clock and ring (a snapshot, like its records)
+      const uint4 pw = (p.world > 1 ? p.ue_snap_peer[u / p.shard_size] : p.ue_snap)[ul];
+      const uint4 w0 = p.ue_state[vl];
+      UeRec er;
+      ue_unpack(w0, er);
+      UeCounts ec = {};
+      ue_replay(er, pw.x, pw.y & 0xffu, p.ue_ltime, p.ue_table, p.rules.limit, ec);
+      const uint4 w1 = ue_pack(er);
+      if ((w1.x ^ w0.x) | (w1.y ^ w0.y) | (w1.z ^ w0.z) | (w1.w ^ w0.w)) p.ue_state[vl] = w1;
+      d_changed += ec.delivered;
+      if (ec.delivered) atomicAdd((unsigned long long*)(p.ue_totals + 2), (unsigned long long)ec.delivered);
+      if (ec.duplicates) atomicAdd((unsigned long long*)(p.ue_totals + 3), (unsigned long long)ec.duplicates);
+      if (ec.too_old) atomicAdd((unsigned long long*)(p.ue_totals + 4), (unsigned long long)ec.too_old);
+      if (TRACE) d_hash += ue_hash((u64)(p.R + 1) * p.n_global + v, w1) - ue_hash((u64)(p.R + 1) * p.n_global + v, w0);
+      if (er.clock >= LTIME_LIMIT) *p.overflow = 1;
+    }
     const u64 ns2 = (ns & ~0xffffffffull) | clock;
     if (ns2 != ns) {
       p.node_state[vl] = ns2;

@@ -62,6 +62,8 @@ struct TickParams {
   // sharded push-pull rounds: every rank's end-of-tick snapshot, indexed by shard (null when world == 1).  New members go
   // at the end: the tick kernels do not read them and keep their parameter offsets (and their SASS) unchanged.
   const uint4* const* snap_rec_peer; const u64* const* snap_node_peer;
+  // push-pull replay of the partner's user-event ring (delegate.rs:469-474, 539-552); ue_table.n == 0: user events off
+  UeTable ue_table; uint4* ue_state; const uint4* ue_snap; const uint4* const* ue_snap_peer; const u32* ue_ltime; u64* ue_totals;
   u32 compact;                // 1: unsaturated ticks gather their active nodes across several tiles (SERFSIM_COMPACT=0 switches it off)
 };
 

@@ -14,8 +14,8 @@
 //
 // Simulation model: E ≤ 8 TRACKED user events.  Tracked event e has a host-given content id (two events with the same
 // id have equal name and payload) and a Lamport time stamped by its origin when it is injected.  A node's whole event
-// state is 16 bytes: event clock, `seen` mask (ring slots it filled, by tracked event), `first` mask (the event that
-// created its ring slot — the slot's ltime, which push-pull would replay), and one transmit budget per event.
+// state is 16 bytes: event clock, `seen` mask (ring slots it filled, by tracked event), `first` mask (the lowest-index seen
+// event of each occupied ring slot — derived, see ue_first_mask), and one transmit budget per event.
 // Gossip entries are single bits OR-ed into the destination's inbox word: an event message carries nothing a receiver
 // does not already know from the table (ltime, content), so "which tracked events arrived" is the complete payload and
 // OR is the order-independent reduction (receiving k copies equals receiving one: copies 2..k are duplicates).
@@ -40,6 +40,7 @@ struct UeTable {                             // per run, by value
   u32 content[MAX_UEVENTS];                  // identity of (name, payload)
 };
 enum : int { UE_ACCEPTED = 0, UE_DUPLICATE = 1, UE_TOO_OLD = 2 };
+struct UeCounts { u32 messages, edges, delivered, duplicates, too_old, pending; };
 
 __host__ __device__ inline void ue_unpack(const uint4& w, UeRec& r) {
   r.clock = w.x; r.seen = w.y & 0xffu; r.first = (w.y >> 8) & 0xffu;
@@ -54,21 +55,42 @@ __host__ __device__ inline uint4 ue_pack(const UeRec& r) {
   return w;
 }
 
-// handle_user_event (serf/base.rs:750-837) for tracked event e stamped L; `ltime[j]` is read only for events in `seen`.
-__host__ __device__ inline int ue_handle(UeRec& r, u32 e, u32 L, const u32* ltime, const UeTable& tb, u32 limit, bool requeue) {
+// `first` is a DERIVED field: bit e is set iff e is the lowest-index seen event of its ring slot (class = ltime % 512).
+// It depends only on the seen set and on the Lamport times of seen events (which are final once an event has been seen),
+// not on the order in which the events arrived — push-pull replays a partner's ring in an order the packed record does
+// not keep.  Cluster runs require that two tracked events that share a ring slot also share their Lamport time (checked
+// by the host after every step; the slot-reuse quirk itself lives on in ue_handle and is pinned by the handler tests), so
+// the slot's own ltime — what a push-pull replay carries — is the ltime of any event in it.
+__host__ __device__ inline u32 ue_first_mask(u32 seen, const u32* ltime, u32 n) {
+  u32 first = 0;
+  for (u32 e = 0; e < n; ++e) {
+    if (!((seen >> e) & 1u)) continue;
+    bool lowest = true;
+    for (u32 j = 0; j < e; ++j) if (((seen >> j) & 1u) && ltime[j] % UE_RING == ltime[e] % UE_RING) lowest = false;
+    if (lowest) first |= 1u << e;
+  }
+  return first;
+}
+
+// handle_user_event (serf/base.rs:750-837) for tracked event e carried with Lamport time L (its own, or — in a push-pull
+// replay — the partner's slot ltime); `ltime[j]` is read only for events in `seen` and for e itself.  `self_L`: the event
+// is being stamped by this very call (the table entry is not written yet).
+__host__ __device__ inline int ue_handle(UeRec& r, u32 e, u32 L, const u32* ltime, const UeTable& tb, u32 limit, bool requeue, bool self_L = false) {
   witness(r.clock, L);                                                   // :763
   // :766-768 `ltime < min_time`: min_time stays 0 here (it only moves on a join with event_join_ignore, delegate.rs:531-537)
   if (r.clock > UE_RING && L < r.clock - UE_RING) return UE_TOO_OLD;     // :771-781
   const u32 idx = L % UE_RING;                                           // :784
-  bool occupied = false;
   for (u32 j = 0; j < tb.n; ++j) {
     if (!((r.seen >> j) & 1u)) continue;
-    if (ltime[j] % UE_RING != idx) continue;
-    occupied = true;                                                     // the slot exists, whatever ltime it was created with (quirk ii)
+    if (ltime[j] % UE_RING != idx) continue;                             // the slot exists, whatever ltime it was created with (quirk ii)
     if (tb.content[j] == tb.content[e]) return UE_DUPLICATE;             // :801-806
   }
   r.seen |= 1u << e;                                                     // :807 push, or :809-813 new slot
-  if (!occupied) r.first |= 1u << e;
+  {                                                                      // re-derive `first` (see ue_first_mask); e's own time may not be in the table yet
+    u32 lt[MAX_UEVENTS];
+    for (u32 j = 0; j < tb.n; ++j) lt[j] = (j == e && self_L) ? L : ltime[j];
+    r.first = ue_first_mask(r.seen, lt, tb.n);
+  }
   if (requeue) r.tx[e] = limit;                                          // → true → re-queued, delegate.rs:293-300
   return UE_ACCEPTED;
 }
@@ -77,9 +99,30 @@ __host__ __device__ inline int ue_handle(UeRec& r, u32 e, u32 L, const u32* ltim
 __host__ __device__ inline u32 ue_originate(UeRec& r, u32 e, const u32* ltime, const UeTable& tb, u32 limit, int& outcome) {
   const u32 L = r.clock;                                                 // :264
   r.clock += 1;                                                          // :285 increment
-  outcome = ue_handle(r, e, L, ltime, tb, limit, false);                 // :288, result ignored
+  outcome = ue_handle(r, e, L, ltime, tb, limit, false, true);           // :288, result ignored
   r.tx[e] = limit;                                                       // :290-297 queued unconditionally
   return L;
+}
+
+// Push-pull replay (SerfDelegate::merge_remote_state, serf/delegate.rs:466-468 and 539-552): witness the partner's event
+// clock − 1, then hand every event of the partner's ring to handle_user_event with the slot's ltime — nothing is re-queued.
+// Replay order: ring index ascending, as the reference walks its buffer (it matters: every replay witnesses its ltime,
+// and a later event can thereby fall out of the 512-wide window); inside a slot the packed record keeps no order and none
+// is needed (one ltime per slot in cluster runs, acceptance per content, `first` derived) — ascending event index.
+__host__ __device__ inline void ue_replay(UeRec& r, u32 partner_clock, u32 partner_seen, const u32* ltime, const UeTable& tb, u32 limit, UeCounts& c) {
+  if (partner_clock > 0) witness(r.clock, partner_clock - 1);
+  u32 todo = partner_seen & ((1u << tb.n) - 1u);
+  while (todo) {
+    u32 best = 0, best_key = 0xffffffffu;
+    for (u32 e = 0; e < tb.n; ++e) {
+      if (!((todo >> e) & 1u)) continue;
+      const u32 key = ((ltime[e] % UE_RING) << 4) | e;
+      if (key < best_key) { best_key = key; best = e; }
+    }
+    todo &= ~(1u << best);
+    const int oc = ue_handle(r, best, ltime[best], ltime, tb, limit, false);
+    if (oc == UE_ACCEPTED) c.delivered++; else if (oc == UE_DUPLICATE) c.duplicates++; else c.too_old++;
+  }
 }
 
 // Gossip send of one node to its `nt` targets (target k gets event e iff its remaining budget exceeds k — one
@@ -132,7 +175,6 @@ __host__ __device__ inline u32 ue_pick_targets(u32 tick, u32 v, u32 row0, u32 de
   return nt;
 }
 
-struct UeCounts { u32 messages, edges, delivered, duplicates, too_old, pending; };
 
 // Phases R and E of one node (pure): arrived events by ascending index, then the node's own injection.
 // Returns the Lamport time stamped by an injection (valid when op == OP_USER_EVENT and the node is up).

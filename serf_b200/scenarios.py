@@ -183,10 +183,10 @@ def byzantine_injectors(n=100_000, degree=16, fanout=4, frac=0.01, delta=2, seed
 
 def fuzz_features(seed, n=None, slots=None):
     """fuzz() plus the optional subsystems on top: tracked user events fired at random ticks / origins (possibly with
-    equal content), and a random set of byzantine injectors.  Push-pull is off (not combinable in this version)."""
+    equal content), and a random set of byzantine injectors.  Push-pull rounds stay on when fuzz() drew them and there are no
+    injectors (injectors and push-pull are not combinable in this version)."""
     sc = fuzz(seed, n=n, slots=slots)
     sc.name = f"fuzz_features_{seed}"
-    sc.cfg["push_pull_interval_ticks"] = 0
     rng = np.random.Generator(np.random.Philox(seed + 90001))
     used = {(t, node) for (t, _, node, _) in sc.ops}
     if rng.random() < 0.8:
@@ -199,7 +199,8 @@ def fuzz_features(seed, n=None, slots=None):
                     used.add((t, node))
                     sc.ops.append((t, int(Op.USER_EVENT), node, e))
                     break
-    if rng.random() < 0.7:
+    if rng.random() < 0.6:
+        sc.cfg["push_pull_interval_ticks"] = 0
         k = int(rng.integers(1, max(2, sc.n // 4)))
         sc.byzantine = rng.choice(sc.n, size=k, replace=False).astype(np.uint32)
         sc.delta = int(rng.integers(0, 4))

@@ -327,3 +327,10 @@ def test_sharded_user_events_need_bigger_windows():
     """5 events × fan-out 3 from every node: more cross-shard entries per tick than the windows serfsim_create sizes for
     membership traffic alone — serfsim_set_user_events must have resized them (it used to overflow at this size)."""
     check_events(scenarios.user_event_storm(20_000, 16, 3, seed=3, n_events=5, spacing=2, churn=50, with_leave=True), 2)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_user_events_with_push_pull(world):
+    """Event replay of a push-pull round when the partner lives in another shard (its event snapshot is peer-mapped)."""
+    check_events(scenarios.user_event_storm(2001, 8, 2, seed=6, n_events=5, spacing=2, churn=30, with_leave=True), world,
+                 push_pull_interval_ticks=5, retransmit_mult=1)

@@ -73,9 +73,6 @@ def test_reset_clears_event_state():
 
 
 def test_host_validation():
-    g = emu_sim(500, 1, push_pull_interval_ticks=10)
-    with pytest.raises(SerfsimError):
-        g.set_user_events([1, 2])                  # not combined with push-pull in this version
     sc = scenarios.user_event_storm(300, 8, 3, seed=1, n_events=2)
     g = sc.build(emu_sim)
     with pytest.raises(SerfsimError):
@@ -84,3 +81,15 @@ def test_host_validation():
         g.user_event(5, 2, tick=9)                 # only 2 tracked events
     with pytest.raises(SerfsimError):
         g.set_user_events([1])                     # operations are already scheduled
+
+
+@pytest.mark.parametrize("pp", [5, 13])
+def test_user_events_with_push_pull_rounds(pp):
+    """retransmit_mult 1 leaves the gossip of the events incomplete; push-pull rounds replay the partner's event ring
+    (delegate.rs:539-552) and witness its event clock until everybody has everything."""
+    sc = scenarios.user_event_storm(2500, 8, 2, seed=6, n_events=5, spacing=2, churn=30, with_leave=True)
+    g, o = run_both(sc, push_pull_interval_ticks=pp, retransmit_mult=1)
+    st = o.user_event_stats()
+    gossip_only = scenarios.user_event_storm(2500, 8, 2, seed=6, n_events=5, spacing=2, churn=30, with_leave=True).build(oracle_sim, trace=1, retransmit_mult=1)
+    gossip_only.run_until_converged(sc.max_ticks)
+    assert st["delivered"] > gossip_only.user_event_stats()["delivered"]        # the rounds did deliver events gossip had missed

@@ -84,12 +84,10 @@ def test_reset_clears_event_state():
     assert g.state_hash() == h1 and g.user_event_stats() == st1
 
 
-def test_user_events_rejected_with_push_pull_or_shards():
-    from serf_b200 import GossipSim
-    from serf_b200.sim import SerfsimError
-    g = GossipSim(1000, 1, push_pull_interval_ticks=10)
-    with pytest.raises(SerfsimError):
-        g.set_user_events([1, 2])
+@pytest.mark.parametrize("pp", [5, 13])
+def test_user_events_with_push_pull_rounds(pp):
+    """retransmit_mult 1 leaves the gossip of the events incomplete; push-pull rounds replay the partner's event ring."""
+    run_both(scenarios.user_event_storm(30_000, 8, 2, seed=6, n_events=5, spacing=2, churn=100, with_leave=True), push_pull_interval_ticks=pp, retransmit_mult=1)
 
 
 @pytest.mark.parametrize("seed", range(12))
