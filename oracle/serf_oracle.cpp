@@ -801,14 +801,6 @@ struct TickSim {
       if (up_s && wmask && cfg.probe_interval_ticks && any_down && ((t + v) % cfg.probe_interval_ticks) == 0)
         have_probe = probe_target(v, t, &ptarget);
       u32 max_tx = 0;
-      // byzantine entries that arrive now are judged against this node's views as they stand, before anything is merged
-      if (byz_n && up_r)
-        for (u32 i = head[v - v0]; i < head[v - v0 + 1]; ++i) {
-          const Msg& m = byd[i];
-          if (!m.byz) continue;
-          const View& q = at(m.slot, v);
-          if (byz_judge(q, m.kind, m.val, byz_delta)) byz_flagged[c].push_back(m.src);
-        }
       for (u32 s = 0; s < R; ++s) {
         View& r = at(s, v);
         const bool self = (subj[s] == v);
@@ -986,6 +978,15 @@ struct TickSim {
     else { std::vector<std::thread> th; for (u32 c = 0; c < T; ++c) th.emplace_back(work, c); for (auto& x : th) x.join(); }
     mail.swap(mail_next);
     if (byz_n) {
+      // Verdicts: every stale entry posted this tick is judged against its receiver's view as it stands when the node loop
+      // of this tick is over — the state the packet meets on arrival, except for what a push-pull round of this very tick
+      // still merges afterwards (the round runs after the verdicts; the device does the same).  A receiver that is down
+      // at that point never sees the packet.  `mail` holds this tick's messages after the swap above.
+      for (auto& box : mail)
+        for (const Msg& m : box) {
+          if (!m.byz || !node[m.dst].up) continue;
+          if (byz_judge(at(m.slot, m.dst), m.kind, m.val, byz_delta)) byz_flagged[0].push_back(m.src);
+        }
       for (u32 c = 0; c < T; ++c) {
         for (u32 src : byz_flagged[c]) if (!anomaly[src]) { anomaly[src] = 1; byz_tot[2]++; }
         byz_tot[0] += byz_rows[(size_t)c * 2]; byz_tot[1] += byz_rows[(size_t)c * 2 + 1];
@@ -1273,7 +1274,7 @@ ORC int oracle_byz_judge(const void* rec32, u32 kind, u32 val, u32 delta) { View
 ORC int oracle_sim_set_byzantine(void* p, u32 n, const u32* ids, u32 delta) {
   auto* s = (TickSim*)p;
   if ((n && !ids) || s->tick != 0 || !s->events.empty()) { g_err = "bad set_byzantine"; return SERFSIM_E_INVAL; }
-  if (n && (s->own_count != s->N || s->cfg.push_pull_interval_ticks > 0)) { g_err = "byzantine injectors: single shard, no push-pull"; return SERFSIM_E_INVAL; }
+  if (n && s->own_count != s->N) { g_err = "byzantine injectors: single oracle instance"; return SERFSIM_E_INVAL; }
   s->byz.assign(n ? s->N : 0, 0); s->byz_n = 0;
   for (u32 i = 0; i < n; ++i) { if (ids[i] >= s->N || s->byz[ids[i]]) { g_err = "bad byzantine id"; return SERFSIM_E_INVAL; } s->byz[ids[i]] = 1; s->byz_n++; }
   s->byz_delta = delta; s->anomaly.assign(n ? s->N : 0, 0); for (auto& x : s->byz_tot) x = 0;

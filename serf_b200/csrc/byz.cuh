@@ -14,8 +14,9 @@
 // accepts and re-gossips them like any other message.
 // Anomaly flag of a SENDER u: set when some receiver v, up at the time the packet arrives, holds a view of that subject
 // that is newer than the injected entry by at least Δ — serf: v knows the member and v.status_time ≥ sent_ltime + Δ;
-// memberlist: v.incarnation ≥ sent_incarnation + Δ — judged on v's view as it stands when the packet arrives (the
-// end-of-tick state of the sending tick, before v merges anything of the next tick).
+// memberlist: v.incarnation ≥ sent_incarnation + Δ — judged on v's view at the end of the sending tick's node pass (what the
+// packet meets on arrival, except for what a push-pull round of that very tick merges afterwards: the round runs after
+// the verdicts, on the device as in the oracle).
 #pragma once
 #include "record.cuh"
 

@@ -933,7 +933,6 @@ int serfsim_set_byzantine(serfsim_t* h, uint32_t n, const uint32_t* ids, uint32_
   if (!h) return fail(SERFSIM_E_INVAL, "null handle");
   if (n && !ids) return fail(SERFSIM_E_INVAL, "null ids");
   if (h->tick != 0 || !h->ops.empty()) return fail(SERFSIM_E_INVAL, "serfsim_set_byzantine: call before any operation is scheduled (or after serfsim_reset)");
-  if (n && h->cfg.push_pull_interval_ticks > 0) return fail(SERFSIM_E_INVAL, "byzantine injectors cannot be combined with push-pull rounds in this version");
   if (n && h->cfg.world_size > 1 && h->shard_size >= BYZ_FLAG) return fail(SERFSIM_E_INVAL, "byzantine injectors: shards must hold fewer than 2^25 nodes");
   std::vector<u32> v(ids, ids + n);
   std::sort(v.begin(), v.end());

@@ -183,8 +183,7 @@ def byzantine_injectors(n=100_000, degree=16, fanout=4, frac=0.01, delta=2, seed
 
 def fuzz_features(seed, n=None, slots=None):
     """fuzz() plus the optional subsystems on top: tracked user events fired at random ticks / origins (possibly with
-    equal content), and a random set of byzantine injectors.  Push-pull rounds stay on when fuzz() drew them and there are no
-    injectors (injectors and push-pull are not combinable in this version)."""
+    equal content), and a random set of byzantine injectors — on top of whatever fuzz() drew (push-pull rounds, reaper, probing)."""
     sc = fuzz(seed, n=n, slots=slots)
     sc.name = f"fuzz_features_{seed}"
     rng = np.random.Generator(np.random.Philox(seed + 90001))
@@ -200,7 +199,6 @@ def fuzz_features(seed, n=None, slots=None):
                     sc.ops.append((t, int(Op.USER_EVENT), node, e))
                     break
     if rng.random() < 0.6:
-        sc.cfg["push_pull_interval_ticks"] = 0
         k = int(rng.integers(1, max(2, sc.n // 4)))
         sc.byzantine = rng.choice(sc.n, size=k, replace=False).astype(np.uint32)
         sc.delta = int(rng.integers(0, 4))

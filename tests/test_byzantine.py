@@ -141,6 +141,3 @@ def test_set_byzantine_validation():
         o.set_byzantine([5, 5])
     with pytest.raises(SerfsimError):
         o.set_byzantine([100])
-    pp = oracle_sim(100, 1, push_pull_interval_ticks=5)
-    with pytest.raises(SerfsimError):
-        pp.set_byzantine([1])

@@ -57,3 +57,9 @@ def test_injectors_and_user_events_together():
     g, o = run_both(sc)
     assert g.user_event_stats() == o.user_event_stats()
     assert (g.user_event_records() == o.user_event_records()).all()
+
+
+@pytest.mark.parametrize("pp", [6, 15])
+def test_injectors_with_push_pull_rounds(pp):
+    """Verdicts of a tick are taken before that tick's push-pull round, on the device as in the oracle."""
+    run_both(scenarios.byzantine_injectors(2500, 12, 3, 0.05, seed=5), push_pull_interval_ticks=pp)

@@ -334,3 +334,7 @@ def test_sharded_user_events_with_push_pull(world):
     """Event replay of a push-pull round when the partner lives in another shard (its event snapshot is peer-mapped)."""
     check_events(scenarios.user_event_storm(2001, 8, 2, seed=6, n_events=5, spacing=2, churn=30, with_leave=True), world,
                  push_pull_interval_ticks=5, retransmit_mult=1)
+
+
+def test_sharded_byzantine_with_push_pull():
+    check_byzantine(scenarios.byzantine_injectors(2400, 12, 3, 0.05, seed=5), 3, push_pull_interval_ticks=6)

@@ -132,6 +132,7 @@ def _feature_checks(g, o, sc):
 def test_fuzz_with_user_events_and_injectors(seed):
     """Every operation kind, reaper, probing, tracked user events (with aliases) and byzantine injectors at once."""
     sc = scenarios.fuzz_features(seed)
+    sc.max_ticks = 1200                    # injector runs with push-pull / reaper rounds may never go quiet: both sides stop at the cap
     o = sc.build(oracle_sim, trace=1)
     to = o.run_until_converged(sc.max_ticks)
     for trace in (1, 0):

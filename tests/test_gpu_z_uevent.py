@@ -94,6 +94,7 @@ def test_user_events_with_push_pull_rounds(pp):
 def test_fuzz_with_user_events_and_injectors(seed):
     """Every operation kind, reaper, probing, tracked user events (with aliases) and byzantine injectors at once."""
     sc = scenarios.fuzz_features(seed)
+    sc.max_ticks = 1200
     o = sc.build(oracle_sim, trace=1)
     to = o.run_until_converged(sc.max_ticks)
     for trace in (1, 0):
