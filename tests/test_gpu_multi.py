@@ -68,6 +68,7 @@ WORLDS = [int(x) for x in os.environ.get("SERFSIM_TEST_WORLDS", "2,4").split(","
     ("fuzz", dict(seed=11, n=3000, slots=3), {}),                                   # push-pull rounds across shards (fuzz 11 has them on)
     ("fuzz_features", dict(seed=6, n=3000, slots=3), {}),
     ("user_event_storm", dict(n=20_000, degree=8, fanout=2, seed=6, n_events=5, spacing=2, churn=100, with_leave=True), dict(push_pull_interval_ticks=5, retransmit_mult=1)),
+    ("byzantine_injectors", dict(n=20_000, degree=12, fanout=3, frac=0.05, seed=5), dict(push_pull_interval_ticks=6)),
 ])
 def test_sharded_equals_oracle(world, scen, tmp_path):
     if torch.cuda.device_count() < world:
