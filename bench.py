@@ -6,7 +6,8 @@ state, schedule the host operations, run gossip ticks until the cluster is quies
 (serfsim_run_until_converged).  `value` = edge-updates of all ranks ÷ device time (CUDA events on
 the launch stream, max over ranks), inputs resident in HBM.  `e2e` = the same study driven through
 the C ABI with HOST buffers: the operation schedule goes host→device and the member-status,
-status-time and Lamport-clock vectors come back device→host inside the timed region.
+status-time and Lamport-clock vectors come back device→host inside the timed region (the two Lamport vectors through the
+compact u32 getters: the device keeps them in 32 bits and fails loudly rather than wrap).
 
     python bench.py --gpus 1 --steps 5 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
@@ -217,8 +218,8 @@ def main():
 
     # pinned host buffers for the results a caller reads back (the C ABI copies into caller-owned memory)
     pin_status = [torch.empty(g.count, dtype=torch.uint8).pin_memory() for _ in range(sc.slots)]
-    pin_ltime = [torch.empty(g.count, dtype=torch.int64).pin_memory() for _ in range(sc.slots)]
-    pin_clock = torch.empty(g.count, dtype=torch.int64).pin_memory()
+    pin_ltime = [torch.empty(g.count, dtype=torch.int32).pin_memory() for _ in range(sc.slots)]     # Lamport times cross PCIe as u32 (serfsim_*_u32)
+    pin_clock = torch.empty(g.count, dtype=torch.int32).pin_memory()
 
     def one_step(read_back):
         g.reset(1)
@@ -229,8 +230,8 @@ def main():
         if read_back:                                  # device→host: the step's result vectors
             for s in range(sc.slots):
                 out_bytes += g.member_status(s, out=pin_status[s].numpy()).nbytes
-                out_bytes += g.status_ltime(s, out=pin_ltime[s].numpy().view(np.uint64)).nbytes
-            out_bytes += g.lamport_time(out=pin_clock.numpy().view(np.uint64)).nbytes
+                out_bytes += g.status_ltime_u32(s, out=pin_ltime[s].numpy().view(np.uint32)).nbytes
+            out_bytes += g.lamport_time_u32(out=pin_clock.numpy().view(np.uint32)).nbytes
         return ticks, ok, ms, launches, out_bytes
 
     sampler = ClockSampler(local_rank)

@@ -198,6 +198,10 @@ int serfsim_shard_range(serfsim_t* h, uint32_t* first, uint32_t* count);
 int serfsim_member_status(serfsim_t* h, uint32_t slot, uint8_t*  out /*[count]*/);  /* Serf::members → Member.status, `serf/api.rs:136-146` */
 int serfsim_status_ltime (serfsim_t* h, uint32_t slot, uint64_t* out /*[count]*/);  /* MemberState.status_time, `types/member.rs:23`         */
 int serfsim_lamport_time (serfsim_t* h, uint64_t* out /*[count]*/);                 /* LamportClock::time, `types/clock.rs:142`              */
+/* The same two vectors at half the size: the device keeps Lamport times in 32 bits (a run that would leave that range fails with
+ * SERFSIM_E_OVERFLOW instead of wrapping), so a caller that reads them every step can take them as u32 and widen lazily. */
+int serfsim_status_ltime_u32(serfsim_t* h, uint32_t slot, uint32_t* out /*[count]*/);
+int serfsim_lamport_time_u32(serfsim_t* h, uint32_t* out /*[count]*/);
 int serfsim_incarnation  (serfsim_t* h, uint32_t slot, uint32_t* out /*[count]*/);  /* memberlist incarnation of the subject as seen         */
 int serfsim_ml_state     (serfsim_t* h, uint32_t slot, uint8_t*  out /*[count]*/);  /* SERFSIM_ML_*                                          */
 int serfsim_records      (serfsim_t* h, uint32_t slot, void* out /*[count][32]*/);  /* raw 32-byte member records (layout: DESIGN.md)        */

@@ -134,6 +134,9 @@ class Serf {
     return out;
   }
   std::vector<LamportTime> status_ltime(uint32_t slot = 0) const { std::vector<LamportTime> v(n_); check(serfsim_status_ltime(h_, slot, v.data())); return v; }
+  // the same vector as the device keeps it (u32; a run that would leave that range fails with SERFSIM_E_OVERFLOW): half the bytes over PCIe
+  std::vector<uint32_t> status_ltime_u32(uint32_t slot = 0) const { std::vector<uint32_t> v(n_); check(serfsim_status_ltime_u32(h_, slot, v.data())); return v; }
+  std::vector<uint32_t> lamport_time_u32() const { std::vector<uint32_t> v(n_); check(serfsim_lamport_time_u32(h_, v.data())); return v; }
   // LamportClock::time of every node (types/clock.rs:142)
   std::vector<LamportTime> lamport_time() const { std::vector<LamportTime> v(n_); check(serfsim_lamport_time(h_, v.data())); return v; }
   // Serf::stats (serf/api.rs:150-183)

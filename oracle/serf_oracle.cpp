@@ -1238,6 +1238,8 @@ ORC int oracle_sim_run_until_converged(void* p, u32 max_ticks, u32* ticks_out) {
 }
 ORC int oracle_sim_member_status(void* p, u32 slot, u8* out) { auto* s = (TickSim*)p; if (slot >= s->R) return SERFSIM_E_INVAL; for (u32 v = 0; v < s->N; ++v) { View& r = s->at(slot, v); out[v] = known(r) ? r.status : (u8)ST_NONE; } return 0; }
 ORC int oracle_sim_status_ltime(void* p, u32 slot, u64* out) { auto* s = (TickSim*)p; if (slot >= s->R) return SERFSIM_E_INVAL; for (u32 v = 0; v < s->N; ++v) { View& r = s->at(slot, v); out[v] = known(r) ? r.st : 0; } return 0; }
+ORC int oracle_sim_status_ltime_u32(void* p, u32 slot, u32* out) { auto* s = (TickSim*)p; if (slot >= s->R) return SERFSIM_E_INVAL; for (u32 v = 0; v < s->N; ++v) { View& r = s->at(slot, v); out[v] = known(r) ? r.st : 0; } return 0; }
+ORC int oracle_sim_lamport_time_u32(void* p, u32* out) { auto* s = (TickSim*)p; for (u32 v = 0; v < s->N; ++v) out[v] = s->node[v].clock; return 0; }
 ORC int oracle_sim_lamport_time(void* p, u64* out) { auto* s = (TickSim*)p; for (u32 v = 0; v < s->N; ++v) out[v] = s->node[v].clock; return 0; }
 ORC int oracle_sim_incarnation(void* p, u32 slot, u32* out) { auto* s = (TickSim*)p; if (slot >= s->R) return SERFSIM_E_INVAL; for (u32 v = 0; v < s->N; ++v) out[v] = s->at(slot, v).inc; return 0; }
 ORC int oracle_sim_ml_state(void* p, u32 slot, u8* out) { auto* s = (TickSim*)p; if (slot >= s->R) return SERFSIM_E_INVAL; for (u32 v = 0; v < s->N; ++v) out[v] = ml_state(s->at(slot, v)); return 0; }

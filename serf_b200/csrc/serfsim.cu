@@ -500,7 +500,7 @@ void free_all(serfsim* h) {
 
 int getter(serfsim* h, u32 slot, int what, void* out, size_t elem) {
   if (!h || !out) return fail(SERFSIM_E_INVAL, "null argument");
-  if (what != EXTRACT_CLOCK && slot >= h->R) return fail(SERFSIM_E_INVAL, "slot out of range");
+  if (what != EXTRACT_CLOCK && what != EXTRACT_CLOCK32 && slot >= h->R) return fail(SERFSIM_E_INVAL, "slot out of range");
   launch_extract(h->d_rec, h->d_node, h->count, h->stride, slot, what, h->d_stage, h->stream);
   CU(cudaMemcpyAsync(out, h->d_stage, (size_t)h->count * elem, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -861,6 +861,10 @@ int serfsim_shard_range(serfsim_t* h, uint32_t* first, uint32_t* count) {
 int serfsim_member_status(serfsim_t* h, uint32_t slot, uint8_t* out) { return getter(h, slot, EXTRACT_STATUS, out, 1); }
 int serfsim_status_ltime(serfsim_t* h, uint32_t slot, uint64_t* out) { return getter(h, slot, EXTRACT_STATUS_LTIME, out, 8); }
 int serfsim_lamport_time(serfsim_t* h, uint64_t* out) { return getter(h, 0, EXTRACT_CLOCK, out, 8); }
+// compact variants: the device keeps Lamport times in 32 bits (a run that would leave that range fails with SERFSIM_E_OVERFLOW), so
+// the same values can cross PCIe at half the size
+int serfsim_status_ltime_u32(serfsim_t* h, uint32_t slot, uint32_t* out) { return getter(h, slot, EXTRACT_STATUS_LTIME32, out, 4); }
+int serfsim_lamport_time_u32(serfsim_t* h, uint32_t* out) { return getter(h, 0, EXTRACT_CLOCK32, out, 4); }
 int serfsim_incarnation(serfsim_t* h, uint32_t slot, uint32_t* out) { return getter(h, slot, EXTRACT_INC, out, 4); }
 int serfsim_ml_state(serfsim_t* h, uint32_t slot, uint8_t* out) { return getter(h, slot, EXTRACT_ML, out, 1); }
 

@@ -1003,6 +1003,7 @@ __global__ void extract_kernel(const uint4* rec, const u64* node_state, u32 n_lo
   const u32 vl = blockIdx.x * blockDim.x + threadIdx.x;
   if (vl >= n_local) return;
   if (what == EXTRACT_CLOCK) { ((u64*)out)[vl] = node_state[vl] & 0xffffffffull; return; }
+  if (what == EXTRACT_CLOCK32) { ((u32*)out)[vl] = (u32)node_state[vl]; return; }
   const size_t idx = (size_t)slot * stride + vl;
   Rec r;
   unpack(rec[2 * idx], rec[2 * idx + 1], r);
@@ -1010,6 +1011,7 @@ __global__ void extract_kernel(const uint4* rec, const u64* node_state, u32 n_lo
   switch (what) {
     case EXTRACT_STATUS: ((u8*)out)[vl] = known ? (u8)r.status : (u8)ST_NONE; break;
     case EXTRACT_STATUS_LTIME: ((u64*)out)[vl] = known ? r.st : 0; break;
+    case EXTRACT_STATUS_LTIME32: ((u32*)out)[vl] = known ? r.st : 0; break;
     case EXTRACT_INC: ((u32*)out)[vl] = r.inc; break;
     case EXTRACT_ML: ((u8*)out)[vl] = (u8)r.mlstate; break;
   }

@@ -156,6 +156,6 @@ constexpr u32 BYZ_FLAG = 1u << 25;          // in the 26-bit destination field o
 constexpr u32 BYZ_ANNOT_SLOT = 15;
 void launch_byz(const ByzParams& p, cudaStream_t st);
 
-enum { EXTRACT_STATUS = 0, EXTRACT_STATUS_LTIME = 1, EXTRACT_CLOCK = 2, EXTRACT_INC = 3, EXTRACT_ML = 4 };
+enum { EXTRACT_STATUS = 0, EXTRACT_STATUS_LTIME = 1, EXTRACT_CLOCK = 2, EXTRACT_INC = 3, EXTRACT_ML = 4, EXTRACT_STATUS_LTIME32 = 5, EXTRACT_CLOCK32 = 6 };
 
 }  // namespace sfs

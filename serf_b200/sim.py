@@ -113,6 +113,8 @@ SIGNATURES = {
     "member_status": (C.c_int, [_vp, _u32, _vp]),
     "status_ltime": (C.c_int, [_vp, _u32, _vp]),
     "lamport_time": (C.c_int, [_vp, _vp]),
+    "status_ltime_u32": (C.c_int, [_vp, _u32, _vp]),
+    "lamport_time_u32": (C.c_int, [_vp, _vp]),
     "incarnation": (C.c_int, [_vp, _u32, _vp]),
     "ml_state": (C.c_int, [_vp, _u32, _vp]),
     "records": (C.c_int, [_vp, _u32, _vp]),
@@ -286,6 +288,8 @@ class GossipSim:
     def member_status(self, slot=0, out=None): return self._get("member_status", np.uint8, slot, out)        # Serf::members
     def status_ltime(self, slot=0, out=None): return self._get("status_ltime", np.uint64, slot, out)
     def lamport_time(self, out=None): return self._get("lamport_time", np.uint64, None, out)
+    def status_ltime_u32(self, slot=0, out=None): return self._get("status_ltime_u32", np.uint32, slot, out)       # same values, half the bytes
+    def lamport_time_u32(self, out=None): return self._get("lamport_time_u32", np.uint32, None, out)
     def incarnation(self, slot=0): return self._get("incarnation", np.uint32, slot)
     def ml_state(self, slot=0): return self._get("ml_state", np.uint8, slot)
     def records(self, slot=0): return self._get("records", RECORD_DTYPE, slot)

@@ -27,12 +27,14 @@ def assert_same(g, o, slots):
         bad = np.nonzero(tg[f] != to[f])[0]
         assert bad.size == 0, f"trace field {f} first differs at tick {bad[0]}: gpu {tg[f][bad[0]]} oracle {to[f][bad[0]]}"
     assert (g.lamport_time() == o.lamport_time()).all()
+    assert (g.lamport_time_u32() == o.lamport_time()).all()
     for s in range(slots):
         rg, ro = g.records(s), o.records(s)
         bad = np.nonzero(rg != ro)[0]
         assert bad.size == 0, f"slot {s}: record of node {bad[0]} differs: gpu {rg[bad[0]]} oracle {ro[bad[0]]}"
         assert (g.member_status(s) == o.member_status(s)).all()
         assert (g.status_ltime(s) == o.status_ltime(s)).all()
+        assert (g.status_ltime_u32(s) == o.status_ltime(s)).all()                 # compact getters: same values, half the bytes
         assert (g.incarnation(s) == o.incarnation(s)).all()
         assert (g.ml_state(s) == o.ml_state(s)).all()
     assert g.state_hash() == o.state_hash()
