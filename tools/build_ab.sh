@@ -6,7 +6,7 @@
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 mkdir -p "$ROOT/serf_b200/ab" "$ROOT/.scratch"
-for b in main pre-queue-word; do
+for b in main ab-no-queue-word; do
   wt="$ROOT/.scratch/wt-$b"
   rm -rf "$wt"; git -C "$ROOT" worktree prune
   git -C "$ROOT" worktree add -q --detach "$wt" "$b"

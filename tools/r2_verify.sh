@@ -15,7 +15,7 @@ if [ $rc -ne 0 ]; then     # localise: compaction off
   SERFSIM_COMPACT=0 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x > gpurun_out/r2_tests_nocompact.log 2>&1
   tail -3 gpurun_out/r2_tests_nocompact.log
 fi
-for v in main pre-queue-word; do
+for v in main ab-no-queue-word; do
   lib=$PWD/serf_b200/ab/libserfsim_$v.so
   [ -f "$lib" ] || continue
   SERFSIM_LIB=$lib timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_$v.json 2>> gpurun_out/r2_bench.err
