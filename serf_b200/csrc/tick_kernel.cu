@@ -87,7 +87,13 @@ inline void st_u32_stream(u32* ptr, u32 v, u64) { emu::probes[12] += 4; *ptr = v
 inline void st_u64_stream(u64* ptr, u64 v, u64) { emu::probes[13] += 8; *ptr = v; }
 inline void red_max_resident(u32* ptr, u32 v, u64) { emu::probes[14] += 4; if (v > *ptr) *ptr = v; }
 inline void st_release_sys(u32* ptr, u32 v) { __atomic_store_n(ptr, v, __ATOMIC_RELEASE); }     // peers are other threads of the test process
-inline u32 ld_acquire_sys(const u32* ptr) { return __atomic_load_n(ptr, __ATOMIC_ACQUIRE); }
+inline u32 ld_acquire_sys(const u32* ptr) {                 // polled in a loop by the drain kernel: be polite to the peer threads, and never hang a test run
+  static thread_local const u32* last = nullptr;
+  static thread_local unsigned long spins = 0;
+  if (ptr != last) { last = ptr; spins = 0; }
+  if (++spins > 64) emu::polite_wait(spins);
+  return __atomic_load_n(ptr, __ATOMIC_ACQUIRE);
+}
 #endif
 
 #ifndef SERFSIM_EMU

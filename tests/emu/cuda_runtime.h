@@ -53,6 +53,7 @@ unsigned long long warp_exchange(unsigned long long v, int src_lane_xor, int src
 unsigned warp_ballot(bool pred);
 unsigned warp_reduce_or(unsigned v);
 unsigned lane_id();
+void polite_wait(unsigned long spins);                          // yields the OS thread; aborts the process after ~120 s of fruitless polling (a peer rank died)
 extern unsigned long probes[32];                              // coverage probes: SFS_PROBE(i) in the kernels, read by tests through emu_probe()
 
 template <class F>

@@ -1,5 +1,7 @@
 // tests/emu/emu_engine.cpp — fiber scheduler of the CUDA-on-CPU shim (see cuda_runtime.h).  Test infrastructure only.
+#include <sched.h>
 #include <sys/mman.h>
+#include <ctime>
 
 #include <cstdio>
 #include <cstdlib>
@@ -99,6 +101,17 @@ void warp_rendezvous(Warp& w) {
 }  // namespace
 
 unsigned lane_id() { return cur_lane->lc.tid.x & 31u; }
+
+void polite_wait(unsigned long spins) {
+  sched_yield();
+  if (spins > 64 && (spins & 0xfff) == 0) {
+    static thread_local time_t t0 = 0;
+    static thread_local unsigned long base = 0;
+    if (spins < base || !t0) { t0 = time(nullptr); }          // a new wait
+    base = spins;
+    if (time(nullptr) - t0 > 120) { fprintf(stderr, "emu: a rank has been polling a peer's flag for 120 s — the peer is gone; aborting instead of hanging\n"); abort(); }
+  }
+}
 
 void cta_barrier() {
   Lane* l = cur_lane;
