@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/r2_gpu.txt 2>&1
 
-timeout 1500 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_multi.py > gpurun_out/r2_tests.log 2>&1
+timeout 2000 python -m pytest tests -m gpu -q --maxfail=12 --deselect tests/test_gpu_multi.py > gpurun_out/r2_tests.log 2>&1
 rc=$?
 tail -5 gpurun_out/r2_tests.log
 if [ $rc -ne 0 ]; then     # localise: compaction off
