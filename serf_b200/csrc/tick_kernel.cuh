@@ -7,6 +7,9 @@
 
 // Kernel launch in one spelling for nvcc and for the host build of tests/emu (which defines its own SFS_LAUNCH):
 //   SFS_LAUNCH(grid, block, dynamic_smem_bytes, stream, kernel<template, args>)(kernel arguments);
+#if defined(SERFSIM_EMU) && defined(__CUDACC__)
+#error "SERFSIM_EMU is the host-only test build of tests/emu (g++); the product is built by nvcc without it"
+#endif
 #ifndef SERFSIM_EMU
 #define SFS_LAUNCH(grid, block, smem, stream, ...) __VA_ARGS__<<<(grid), (block), (smem), (stream)>>>
 constexpr int SFS_SMS = 148;                 // B200: grid-stride helper kernels are sized in multiples of the SM count
