@@ -341,6 +341,18 @@ int launch_ticks(serfsim* h, u32 n) {
         p.snap_rec_peer = h->d_peer_snap_rec; p.snap_node_peer = h->d_peer_snap_node;
         CU(cudaStreamSynchronize(h->stream));
         h->barrier(h->comm_user);
+        if (h->ue_table.n) {
+          // A partner in another shard may hold events this shard has never received, so their Lamport times are not in the
+          // local table yet (a shard learns them from the first window entry of the event).  The replay needs them: the
+          // origin's shard contributes its stamp, the others 0, and every rank installs the sum before the round.
+          u32 lt[MAX_UEVENTS];
+          u64 v[MAX_UEVENTS];
+          CU(cudaMemcpy(lt, h->d_ue_ltime, sizeof(lt), cudaMemcpyDeviceToHost));
+          for (u32 e = 0; e < MAX_UEVENTS; ++e) v[e] = (((h->ue_injected >> e) & 1u) && h->ue_origin[e] - h->first < h->count) ? lt[e] : 0;
+          h->allreduce(h->comm_user, v, MAX_UEVENTS);
+          for (u32 e = 0; e < MAX_UEVENTS; ++e) lt[e] = (u32)v[e];
+          CU(cudaMemcpy(h->d_ue_ltime, lt, sizeof(lt), cudaMemcpyHostToDevice));
+        }
         launch_pushpull(p, h->d_snap_rec, h->d_snap_node, h->cfg.trace != 0, h->stream);
         CU(cudaStreamSynchronize(h->stream));
         h->barrier(h->comm_user);
