@@ -453,6 +453,22 @@ int refresh_watchers(serfsim* h) {
   return 0;
 }
 
+// The convergence loops launch ticks past the first quiescent one; those were no-ops on a quiescent cluster and the logical
+// clock is rewound to `next`.  Two things they did touch: their (all-zero) trace rows, and the hot-tile flags — which are
+// double-buffered by tick parity and consumed by the tick that reads them.  On a quiescent cluster only watcher tiles are
+// hot, and each no-op tick moves their flags to the other parity; after an ODD number of rewound ticks the parity the next
+// tick reads is the consumed one, so the watcher flags are re-applied to both parities (the watchers' SWIM
+// probe of the first tick after a converge → inject → continue was lost).
+int rewind_to(serfsim* h, u32 next) {
+  if (h->tick <= next) return 0;
+  const u32 k = h->tick - next;
+  CU(cudaMemsetAsync(h->d_trace + (size_t)next * 8, 0, (size_t)k * 8 * sizeof(u64), h->stream));
+  CU(cudaMemsetAsync(h->d_kinds + ((size_t)next + 1) * 4, 0, (size_t)k * 4 * sizeof(u32), h->stream));
+  h->tick = next; h->rows.resize(next);
+  if (k & 1) return refresh_watchers(h);
+  return 0;
+}
+
 int ue_reset(serfsim* h) {                      // bootstrap event state: clock 1, nothing seen, nothing queued
   h->ue_injected = 0;
   if (!h->ue_table.n) return 0;
@@ -715,6 +731,7 @@ int serfsim_set_topology_csr(serfsim_t* h, const uint64_t* row_ptr, const uint32
     if (use && h->R == 1 && need <= 48u * 1024u) h->stage_col_bytes = (need + 127u) & ~127u;
   }
   h->grid = tick_grid_size(h->count, h->stage_col_bytes ? 3 : h->ctas_per_sm);
+  if (getenv("SERFSIM_VERBOSE")) fprintf(stderr, "serfsim: tick kernel = %s (stage_col_bytes %u, grid %d)\n", h->stage_col_bytes ? "tick_kernel_tma" : "tick_kernel", h->stage_col_bytes, h->grid);
   h->has_topo = true;
   h->watch_dirty = true;
   return refresh_watchers(h);
@@ -813,10 +830,7 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
         const serfsim_tick_row_t& r = h->rows[t];
         if (r.pending == 0 && r.edge_updates == 0 && !future_ops(h, t)) {
           CU(cudaStreamSynchronize(h->stream));                 // the speculative chunk (no-ops) has drained
-          if (h->tick > t + 1) {
-            CU(cudaMemsetAsync(h->d_trace + (size_t)(t + 1) * 8, 0, (size_t)(h->tick - t - 1) * 8 * sizeof(u64), h->stream));
-            h->tick = t + 1; h->rows.resize(t + 1);
-          }
+          if ((rc = rewind_to(h, t + 1))) return rc;
           if ((rc = finish_timing(h))) return rc;
           if ((rc = check_overflow(h))) return rc;
           if (ticks_out) *ticks_out = t;
@@ -846,10 +860,7 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
       const bool byz_ok = !h->byz_on || r.changed == 0;       // stale entries stay in flight forever: quiescent = no honest traffic and nothing merged
       if (r.pending == 0 && r.edge_updates == 0 && !future_ops(h, t) && pp_ok && byz_ok) {
         // ticks after t were no-ops on a quiescent cluster: rewind the logical clock to t + 1
-        if (h->tick > t + 1) {
-          CU(cudaMemsetAsync(h->d_trace + (size_t)(t + 1) * 8, 0, (size_t)(h->tick - t - 1) * 8 * sizeof(u64), h->stream));
-          h->tick = t + 1; h->rows.resize(t + 1);
-        }
+        if ((rc = rewind_to(h, t + 1))) return rc;
         if ((rc = finish_timing(h))) return rc;
         if ((rc = check_overflow(h))) return rc;
         if (ticks_out) *ticks_out = t;

@@ -155,3 +155,28 @@ def test_graft_entry_smoke_logic_runs(monkeypatch):
     from serf_b200 import sim
     monkeypatch.setattr(sim, "_LIB", lib())
     ge.smoke()
+
+
+@pytest.mark.parametrize("seed", range(1, 9))
+@pytest.mark.parametrize("chunk", ["4", "3"])
+def test_multi_phase_production_mode_rewind(monkeypatch, seed, chunk):
+    """trace=0 (tile skipping, lazy loads, compaction): converge → inject at the CURRENT tick → continue.  The convergence
+    loop rewinds the ticks it launched past the quiescent one; the hot-tile flags are double-buffered by tick parity, so
+    an odd rewind used to leave the watcher tiles unscheduled for the next tick (their SWIM probe of that tick was lost)."""
+    monkeypatch.setenv("SERFSIM_CHUNK", chunk)
+    n = 1500
+    sc = scenarios.random_graph_leave(n, 12, 3, seed=seed, slots=2, graph_seed=seed + 20)
+    cfg = dict(suspicion_mult=2, suspicion_max_timeout_mult=2, probe_interval_ticks=2)
+    sc.ops = [(0, Op.JOIN, int(sc.subjects[0]), 0)]
+    g, o = sc.build(emu_sim, trace=0, **cfg), sc.build(oracle_sim, trace=1, **cfg)
+    assert g.run_until_converged(sc.max_ticks) == o.run_until_converged(sc.max_ticks)
+    for sim in (g, o):
+        sim.inject(sim.stats()["tick"], Op.FAIL, int(sc.subjects[1]), 0)
+    assert g.run_until_converged(5000) == o.run_until_converged(5000)
+    assert_same(g, o, sc.slots, with_hash=False)
+    for sim in (g, o):                                               # and once more: the subject returns, a force-leave follows later
+        t = sim.stats()["tick"]
+        sim.inject(t, Op.REJOIN, int(sc.subjects[1]), 0)
+        sim.inject(t + 3, Op.FORCE_LEAVE, 7, 0)
+    assert g.run_until_converged(5000) == o.run_until_converged(5000)
+    assert_same(g, o, sc.slots, with_hash=False)
