@@ -14,6 +14,7 @@ namespace sfs {
 namespace {
 
 __global__ void __launch_bounds__(128) byz_kernel(const __grid_constant__ ByzParams p) {
+  if (p.gate && *p.gate) return;                               // the run is over (convergence gate): this tick does not exist
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   u32 n_msgs = 0, n_edges = 0, kL = 0, kJ = 0, kM = 0;
   bool wrote_remote = false;

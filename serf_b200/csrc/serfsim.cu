@@ -132,9 +132,15 @@ struct serfsim {
   bool has_topo = false;
   u32 stage_col_bytes = 0;         // 0: direct-load kernel; else bytes of CSR per TMA stage
   u32 max_tile_edges = 0;          // largest 16-byte-aligned CSR span of one 256-node tile (sizes the TMA stage)
-  std::vector<serfsim_tick_row_t> rows;   // rows pulled from the device so far
-  serfsim_tick_row_t* pin_rows = nullptr;  // pinned staging for the convergence loop (2 chunks)
-  cudaEvent_t chunk_ev[2] = {nullptr, nullptr};
+  std::vector<serfsim_tick_row_t> rows;   // rows pulled from the device so far (global sums when sharded)
+  // device-side convergence gate (tick_kernel.cuh: Gate)
+  u32* d_runctl = nullptr;         // [0] done flag, [1] first quiescent tick
+  u32* pin_ctl = nullptr;          // pinned host copy, read once per chunk
+  u64* d_grow = nullptr;           // sharded runs: [trace_cap][8] global trace rows, summed on the device by the drain kernel
+  bool gate_on = false;
+  u32 gate_first = 0;              // first tick of the current run_until_converged call (it always runs)
+  std::vector<u32> launch_log;     // kernels launched per tick since the timing window opened (ticks past the quiescent one do not count)
+  u32 launch_log_first = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timing_open = false;
@@ -162,6 +168,7 @@ struct serfsim {
   bool l2_window = false;           // SERFSIM_L2_WINDOW=1: stream access-policy window over the inbox being written
   bool no_skip = false;             // SERFSIM_NO_SKIP=1: process every tile every tick (A/B measurements)
   bool compact = true;              // SERFSIM_COMPACT=0: tile-by-tile walk in unsaturated ticks too (A/B measurements)
+  bool wstage = true;               // SERFSIM_WSTAGE=0: saturated ticks gather their neighbour picks from global memory instead of a staged CSR span
   std::vector<cudaEvent_t> tick_ev;      // 2 per tick when tick_timing
   std::vector<cudaEvent_t> mid_ev;       // after the tick kernel (multi-GPU breakdown, SERFSIM_XTIMING=1)
 };
@@ -177,18 +184,21 @@ int ensure_trace(serfsim* h, u32 need) {
   if (need <= h->trace_cap) return 0;
   u32 cap = std::max<u32>(1024, h->trace_cap);
   while (cap < need) cap *= 2;
-  u64* nt = nullptr; u32* nk = nullptr;
+  u64* nt = nullptr; u32* nk = nullptr; u64* ng = nullptr;
+  const bool sharded = h->cfg.world_size > 1;
   CU(cudaMalloc(&nt, (size_t)cap * 8 * sizeof(u64)));
   CU(cudaMalloc(&nk, ((size_t)cap + 1) * 4 * sizeof(u32)));
   CU(cudaMemsetAsync(nt, 0, (size_t)cap * 8 * sizeof(u64), h->stream));
   CU(cudaMemsetAsync(nk, 0, ((size_t)cap + 1) * 4 * sizeof(u32), h->stream));
+  if (sharded) { CU(cudaMalloc(&ng, (size_t)cap * 8 * sizeof(u64))); CU(cudaMemsetAsync(ng, 0, (size_t)cap * 8 * sizeof(u64), h->stream)); }
   if (h->d_trace) {
     CU(cudaMemcpyAsync(nt, h->d_trace, (size_t)h->trace_cap * 8 * sizeof(u64), cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaMemcpyAsync(nk, h->d_kinds, ((size_t)h->trace_cap + 1) * 4 * sizeof(u32), cudaMemcpyDeviceToDevice, h->stream));
+    if (sharded) CU(cudaMemcpyAsync(ng, h->d_grow, (size_t)h->trace_cap * 8 * sizeof(u64), cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    cudaFree(h->d_trace); cudaFree(h->d_kinds);
+    cudaFree(h->d_trace); cudaFree(h->d_kinds); cudaFree(h->d_grow);
   }
-  h->d_trace = nt; h->d_kinds = nk; h->trace_cap = cap;
+  h->d_trace = nt; h->d_kinds = nk; h->d_grow = ng; h->trace_cap = cap;
   return 0;
 }
 
@@ -227,9 +237,12 @@ int launch_ticks(serfsim* h, u32 n) {
   if (rc) return rc;
   rc = ensure_trace(h, h->tick + n + 1);
   if (rc) return rc;
-  if (!h->timing_open) { CU(cudaEventRecord(h->ev0, h->stream)); h->timing_open = true; h->last_launches = 0; }
+  if (!h->timing_open) { CU(cudaEventRecord(h->ev0, h->stream)); h->timing_open = true; h->last_launches = 0; h->launch_log.clear(); h->launch_log_first = h->tick; }
+  const bool sharded = h->cfg.world_size > 1;
+  const u64* grow = sharded ? h->d_grow : h->d_trace;            // global rows: the device sums them when sharded
   for (u32 i = 0; i < n; ++i) {
     const u32 t = h->tick;
+    const u64 launches_before = h->last_launches;
     auto lo = std::lower_bound(h->ops.begin(), h->ops.end(), t, [](const HostOp& o, u32 tt) { return o.tick < tt; });
     auto hi = std::upper_bound(h->ops.begin(), h->ops.end(), t, [](u32 tt, const HostOp& o) { return tt < o.tick; });
     const u32 eb = (u32)(lo - h->ops.begin()), ee = (u32)(hi - h->ops.begin());
@@ -259,9 +272,18 @@ int launch_ticks(serfsim* h, u32 n) {
     p.stride = h->stride; p.n_tiles = h->n_tiles; p.tiles_per_cta = (h->n_tiles + h->grid - 1) / h->grid;
     p.force_all = (h->cfg.trace != 0) || h->no_skip || p.reap_now;
     p.compact = h->compact ? 1u : 0u;
+    p.wstage = h->wstage ? 1u : 0u;
     const u32 xpar = h->xepoch & 1;
     p.world = (u32)h->cfg.world_size; p.rank = (u32)h->cfg.rank; p.shard_size = h->shard_size; p.win_cap = h->win_cap;
     p.win_data = h->d_peer_data[xpar]; p.send_count = h->d_send_count;
+    Gate gate{};                                   // convergence gate: the first kernel of the tick evaluates the row of tick t-1
+    if (h->gate_on) {
+      gate.ctl = h->d_runctl; gate.prev_row = t > h->gate_first ? grow + (size_t)(t - 1) * 8 : nullptr; gate.tick = t;
+      gate.future_ops = (t > 0 && future_ops(h, t - 1)) ? 1u : 0u;
+      gate.pp = (u32)std::max(0, h->cfg.push_pull_interval_ticks); gate.byz_on = h->byz_on ? 1u : 0u;
+    }
+    const u32* gate_word = h->gate_on ? h->d_runctl : nullptr;
+    p.gate = gate; p.gate.evaluate = h->ue_table.n ? 0u : 1u;
     if (h->tick_timing) {
       while (h->tick_ev.size() < 2 * ((size_t)t + 1)) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->tick_ev.push_back(e); }
       CU(cudaEventRecord(h->tick_ev[2 * (size_t)t], h->stream));
@@ -286,6 +308,7 @@ int launch_ticks(serfsim* h, u32 n) {
       u.row = p.row; u.totals = h->d_ue_totals; u.overflow = h->d_overflow;
       u.world = (u32)h->cfg.world_size; u.rank = (u32)h->cfg.rank; u.shard_size = h->shard_size; u.win_cap = h->win_cap;
       u.win_data = h->d_peer_data[h->xepoch & 1]; u.send_count = h->d_send_count;
+      u.gate = gate; u.gate.evaluate = 1u;
       launch_uevent(u, h->cfg.trace != 0, h->stream);
       h->last_launches++;
     }
@@ -298,7 +321,7 @@ int launch_ticks(serfsim* h, u32 n) {
       b.row_ptr = h->d_rowptr; b.col = h->d_col; b.inbox_wr = h->d_inbox[t & 1]; b.hot_wr = h->d_hot[t & 1]; b.kinds_cur = p.kinds_cur;
       b.anomaly = h->d_anomaly; b.totals = h->d_byz_totals;
       b.n_local = h->count; b.world = p.world; b.rank = p.rank; b.shard_size = h->shard_size; b.win_cap = h->win_cap;
-      b.win_data = p.win_data; b.send_count = h->d_send_count; b.overflow = h->d_overflow;
+      b.win_data = p.win_data; b.send_count = h->d_send_count; b.overflow = h->d_overflow; b.gate = gate_word;
       launch_byz(b, h->stream);
       h->last_launches++;
     }
@@ -312,12 +335,15 @@ int launch_ticks(serfsim* h, u32 n) {
       const u32 stamp = h->xepoch + 1;
       PublishParams pb{};
       pb.world = p.world; pb.rank = p.rank; pb.stamp = stamp; pb.xpar = xpar; pb.send_count = h->d_send_count; pb.peer_ctrl = h->d_peer_ctrl;
+      pb.row = p.row; pb.gate = gate_word;
       launch_publish(pb, h->stream);
       DrainParams d{};
       d.n_local = h->count; d.stride = h->stride; d.R = h->R; d.world = p.world; d.rank = p.rank; d.win_cap = h->win_cap; d.stamp = stamp; d.n_tiles = h->n_tiles; d.kinds_prev = p.kinds_prev;
       d.win_data = h->d_win_data[xpar]; d.ctrl = h->d_ctrl + xpar * 16; d.inbox_wr = h->d_inbox[t & 1]; d.hot_wr = h->d_hot[t & 1]; d.kinds_cur = h->d_kinds + ((size_t)t + 1) * 4; d.overflow = h->d_overflow;
       d.byz_on = h->byz_on ? 1u : 0u; d.byz_delta = h->byz_delta; d.shard_size = h->shard_size; d.rec = h->d_rec; d.node_state = h->d_node; d.peer_anomaly = h->d_peer_anomaly;
       d.ue_n = h->ue_table.n; d.ue_inbox_wr = h->ue_table.n ? h->d_ue_inbox[t & 1] : nullptr; d.ue_ltime = h->d_ue_ltime;
+      d.my_row = p.row; d.grow = h->d_grow + (size_t)t * 8; d.gate = gate_word;
+      d.sums = reinterpret_cast<const u64*>(reinterpret_cast<const unsigned char*>(h->d_ctrl) + CTRL_SUMS_OFF) + (size_t)xpar * 8 * 8;
       launch_drain(d, h->stream);
       h->last_launches += 2;
       h->xepoch++;
@@ -356,12 +382,19 @@ int launch_ticks(serfsim* h, u32 n) {
         launch_pushpull(p, h->d_snap_rec, h->d_snap_node, h->cfg.trace != 0, h->stream);
         CU(cudaStreamSynchronize(h->stream));
         h->barrier(h->comm_user);
+        // the round changed this rank's row (changed / pending / hash) after the drain kernel summed the rows: redo the sum through
+        // the host hook — the host is in the loop here anyway (two barriers), and rounds are rare
+        u64 row[8];
+        CU(cudaMemcpy(row, h->d_trace + (size_t)t * 8, sizeof(row), cudaMemcpyDeviceToHost));
+        h->allreduce(h->comm_user, row, 8);
+        CU(cudaMemcpy(h->d_grow + (size_t)t * 8, row, sizeof(row), cudaMemcpyHostToDevice));
       } else {
         launch_pushpull(p, h->d_snap_rec, h->d_snap_node, h->cfg.trace != 0, h->stream);
       }
       h->last_launches++;
     }
     if (h->tick_timing) CU(cudaEventRecord(h->tick_ev[2 * (size_t)t + 1], h->stream));
+    h->launch_log.push_back((u32)(h->last_launches - launches_before));
     h->tick++;
   }
   CU(cudaGetLastError());
@@ -410,11 +443,9 @@ int pull_rows(serfsim* h) {                     // bring rows [rows.size(), tick
   if (have >= h->tick) return 0;
   const u32 n = h->tick - have;
   h->rows.resize(h->tick);
-  CU(cudaMemcpy(h->rows.data() + have, h->d_trace + (size_t)have * 8, (size_t)n * sizeof(serfsim_tick_row_t), cudaMemcpyDeviceToHost));
-  if (h->cfg.world_size > 1) {
-    if (!h->allreduce) return fail(SERFSIM_E_COMM, "world_size > 1: serfsim_comm_set_hooks was not called");
-    h->allreduce(h->comm_user, (uint64_t*)(h->rows.data() + have), n * 8);
-  }
+  // sharded runs: the drain kernel of every tick has already summed the ranks' rows on the device (d_grow), no host collective
+  const u64* src = h->cfg.world_size > 1 ? h->d_grow : h->d_trace;
+  CU(cudaMemcpy(h->rows.data() + have, src + (size_t)have * 8, (size_t)n * sizeof(serfsim_tick_row_t), cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -453,22 +484,6 @@ int refresh_watchers(serfsim* h) {
   return 0;
 }
 
-// The convergence loops launch ticks past the first quiescent one; those were no-ops on a quiescent cluster and the logical
-// clock is rewound to `next`.  Two things they did touch: their (all-zero) trace rows, and the hot-tile flags — which are
-// double-buffered by tick parity and consumed by the tick that reads them.  On a quiescent cluster only watcher tiles are
-// hot, and each no-op tick moves their flags to the other parity; after an ODD number of rewound ticks the parity the next
-// tick reads is the consumed one, so the watcher flags are re-applied to both parities (the watchers' SWIM
-// probe of the first tick after a converge → inject → continue was lost).
-int rewind_to(serfsim* h, u32 next) {
-  if (h->tick <= next) return 0;
-  const u32 k = h->tick - next;
-  CU(cudaMemsetAsync(h->d_trace + (size_t)next * 8, 0, (size_t)k * 8 * sizeof(u64), h->stream));
-  CU(cudaMemsetAsync(h->d_kinds + ((size_t)next + 1) * 4, 0, (size_t)k * 4 * sizeof(u32), h->stream));
-  h->tick = next; h->rows.resize(next);
-  if (k & 1) return refresh_watchers(h);
-  return 0;
-}
-
 int ue_reset(serfsim* h) {                      // bootstrap event state: clock 1, nothing seen, nothing queued
   h->ue_injected = 0;
   if (!h->ue_table.n) return 0;
@@ -498,6 +513,8 @@ int do_reset(serfsim* h, u64 seed) {
     CU(cudaMemsetAsync(h->d_trace, 0, (size_t)h->trace_cap * 8 * sizeof(u64), h->stream));
     CU(cudaMemsetAsync(h->d_kinds, 0, ((size_t)h->trace_cap + 1) * 4 * sizeof(u32), h->stream));
   }
+  if (h->d_grow) CU(cudaMemsetAsync(h->d_grow, 0, (size_t)h->trace_cap * 8 * sizeof(u64), h->stream));
+  CU(cudaMemsetAsync(h->d_runctl, 0, 2 * sizeof(u32), h->stream));
   if (h->d_send_count) CU(cudaMemsetAsync(h->d_send_count, 0, sizeof(u32) * 8, h->stream));
   { int rc = ue_reset(h); if (rc) return rc; }
   if (h->d_anomaly) { CU(cudaMemsetAsync(h->d_anomaly, 0, h->stride, h->stream)); CU(cudaMemsetAsync(h->d_byz_totals, 0, 4 * 8, h->stream)); }
@@ -519,8 +536,8 @@ void free_all(serfsim* h) {
   cudaFree(h->d_ue_state); cudaFree(h->d_ue_inbox[0]); cudaFree(h->d_ue_inbox[1]); cudaFree(h->d_ue_ltime); cudaFree(h->d_ue_totals);
   for (int par = 0; par < 2; ++par) { cudaFree(h->d_win_data[par]); cudaFree(h->d_peer_data[par]); }
   cudaFree(h->d_ctrl); cudaFree(h->d_send_count); cudaFree(h->d_peer_ctrl);
-  if (h->pin_rows) cudaFreeHost(h->pin_rows);
-  for (int i = 0; i < 2; ++i) if (h->chunk_ev[i]) cudaEventDestroy(h->chunk_ev[i]);
+  if (h->pin_ctl) cudaFreeHost(h->pin_ctl);
+  cudaFree(h->d_runctl); cudaFree(h->d_grow);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -617,6 +634,9 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
   CUB(cudaMalloc(&h->d_hot[0], h->n_tiles)); CUB(cudaMalloc(&h->d_hot[1], h->n_tiles));
   CUB(cudaMalloc(&h->d_overflow, 4)); CUB(cudaMalloc(&h->d_subj, MAX_SLOTS * 4)); CUB(cudaMalloc(&h->d_scratch, 64 * 8));
   CUB(cudaMalloc(&h->d_stage, (size_t)h->count * 8));
+  CUB(cudaMalloc(&h->d_runctl, 2 * sizeof(u32)));
+  CUB(cudaMemset(h->d_runctl, 0, 2 * sizeof(u32)));
+  CUB(cudaMallocHost(&h->pin_ctl, 2 * sizeof(u32)));
   CUB(cudaMalloc(&h->d_ones, 16));
   const u32 ones[4] = {0x40000000u, 0x40000000u, 0x40000000u, 1u};   // multi-GPU: every inbox plane may hold entries, every tick is dense
   CUB(cudaMemcpy(h->d_ones, ones, 16, cudaMemcpyHostToDevice));
@@ -640,6 +660,7 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
   }
   if (const char* e = getenv("SERFSIM_NO_SKIP")) h->no_skip = atoi(e) != 0;
   if (const char* e = getenv("SERFSIM_COMPACT")) h->compact = atoi(e) != 0;
+  if (const char* e = getenv("SERFSIM_WSTAGE")) h->wstage = atoi(e) != 0;
   if (cfg->world_size > 1) {
     // receive windows: one segment per peer; expected entries per tick and pair ≈ shard · fanout · R · kinds / world
     if (cfg->world_size > 8) return bail(fail(SERFSIM_E_INVAL, "world_size > 8"));
@@ -652,8 +673,8 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
       CUB(cudaMalloc(&h->d_win_data[par], (size_t)cfg->world_size * h->win_cap * 8));
       CUB(cudaMalloc(&h->d_peer_data[par], sizeof(u64*) * 8));
     }
-    CUB(cudaMalloc(&h->d_ctrl, 2 * 16 * sizeof(u32)));
-    CUB(cudaMemset(h->d_ctrl, 0, 2 * 16 * sizeof(u32)));
+    CUB(cudaMalloc(&h->d_ctrl, CTRL_BYTES));
+    CUB(cudaMemset(h->d_ctrl, 0, CTRL_BYTES));
     CUB(cudaMalloc(&h->d_send_count, 8 * sizeof(u32)));
     CUB(cudaMemset(h->d_send_count, 0, 8 * sizeof(u32)));
     CUB(cudaMalloc(&h->d_peer_ctrl, sizeof(u32*) * 8));
@@ -790,89 +811,53 @@ int serfsim_step(serfsim_t* h, uint32_t n_ticks) {
 
 int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* ticks_out) {
   if (!h) return fail(SERFSIM_E_INVAL, "null handle");
-  u32 chunk = 4;
-  if (const char* e = getenv("SERFSIM_CHUNK")) chunk = std::max(1, atoi(e));
-  if (h->byz_on) chunk = 1;     // injector ticks are never no-ops, so no tick may be launched past the quiescent one
+  // Ticks are launched in chunks WITHOUT looking at their rows: the first kernel of every tick evaluates the quiescence rule
+  // on the previous tick's (global) row on the device and, once the run is over, it and every later kernel return at once
+  // (tick_kernel.cuh: Gate).  The host reads two words per chunk; ranks of a sharded run reach the same verdict from the same
+  // device-summed rows, so there is no host collective in the loop.  Ticks launched past the first quiescent one never
+  // execute: nothing to rewind on the device, the logical clock (and the exchange epoch) is simply set back.
+  u32 chunk = 16;
+  if (const char* e = getenv("SERFSIM_CHUNK")) chunk = (u32)std::max(1, atoi(e));
   const u32 pp = (u32)std::max(0, h->cfg.push_pull_interval_ticks);
-  const u32 reap = h->cfg.reap_interval_ticks;
-  // Ticks launched beyond the first quiescent one must be no-ops (they are rewound).  Anti-entropy rounds and reaper
-  // ticks are not — they act on a quiescent cluster too — so such a tick is only ever the FIRST tick of a chunk.
-  auto boundary = [&](u32 t) { return (pp && (t + 1) % pp == 0) || (reap && (t + 1) % reap == 0); };
   const u32 start = h->tick;
   int rc = 0;
-  if (h->cfg.world_size == 1 && !pp && !reap && !h->byz_on && getenv("SERFSIM_SPECULATE")) {   // measured: no gain over the synchronous loop (the 8 extra no-op ticks cost what the gaps saved); off by default
-    // Pipelined convergence check (single GPU, no anti-entropy / reaper ticks): chunk k+1 is launched before the rows
-    // of chunk k are inspected, so the GPU never waits for the host.  Ticks past the first quiescent one are no-ops on
-    // a quiescent cluster and are rewound, exactly as in the synchronous loop below.
-    constexpr u32 MAXC = 16;
-    chunk = std::min(chunk, MAXC);
-    if (!h->pin_rows) { CU(cudaMallocHost(&h->pin_rows, 2 * MAXC * sizeof(serfsim_tick_row_t))); CU(cudaEventCreate(&h->chunk_ev[0])); CU(cudaEventCreate(&h->chunk_ev[1])); }
-    if ((rc = pull_rows(h))) return rc;                       // rows of earlier steps
-    struct Chunk { u32 from, n; };
-    Chunk cur{0, 0}, nxt{0, 0};
-    int slot = 0;
-    auto launch = [&](Chunk& c, int sl) -> int {
-      c.from = h->tick; c.n = std::min(chunk, max_ticks - (h->tick - start));
-      if (!c.n) return 0;
-      int r = launch_ticks(h, c.n);
-      if (r) return r;
-      CU(cudaMemcpyAsync(h->pin_rows + (size_t)sl * MAXC, h->d_trace + (size_t)c.from * 8, (size_t)c.n * sizeof(serfsim_tick_row_t), cudaMemcpyDeviceToHost, h->stream));
-      CU(cudaEventRecord(h->chunk_ev[sl], h->stream));
-      return 0;
-    };
-    if ((rc = launch(cur, slot))) return rc;
-    while (cur.n) {
-      if ((rc = launch(nxt, slot ^ 1))) return rc;              // speculative: may turn out to be all no-ops
-      CU(cudaEventSynchronize(h->chunk_ev[slot]));
-      h->rows.resize(cur.from + cur.n);
-      memcpy(h->rows.data() + cur.from, h->pin_rows + (size_t)slot * MAXC, (size_t)cur.n * sizeof(serfsim_tick_row_t));
-      for (u32 t = cur.from; t < cur.from + cur.n; ++t) {
-        const serfsim_tick_row_t& r = h->rows[t];
-        if (r.pending == 0 && r.edge_updates == 0 && !future_ops(h, t)) {
-          CU(cudaStreamSynchronize(h->stream));                 // the speculative chunk (no-ops) has drained
-          if ((rc = rewind_to(h, t + 1))) return rc;
-          if ((rc = finish_timing(h))) return rc;
-          if ((rc = check_overflow(h))) return rc;
-          if (ticks_out) *ticks_out = t;
-          return fire_events(h);
-        }
-      }
-      cur = nxt; nxt = Chunk{0, 0}; slot ^= 1;
-    }
+  CU(cudaMemsetAsync(h->d_runctl, 0, 2 * sizeof(u32), h->stream));
+  h->gate_on = true; h->gate_first = start;
+  struct GateOff { serfsim* h; ~GateOff() { h->gate_on = false; } } gate_off{h};
+  auto finish = [&](u32 converged_at, bool converged) -> int {
     if ((rc = finish_timing(h))) return rc;
     if ((rc = check_overflow(h))) return rc;
-    if (ticks_out) *ticks_out = h->tick;
+    if (ticks_out) *ticks_out = converged_at;
     if ((rc = fire_events(h))) return rc;
-    return 1;
-  }
+    return converged ? 0 : 1;
+  };
+  auto stop_at = [&](u32 t) {                         // tick t is the first quiescent one: later launches did not execute
+    const u32 skipped = h->tick - (t + 1);
+    if (h->cfg.world_size > 1) h->xepoch -= skipped;   // skipped ticks exchanged nothing
+    h->tick = t + 1;
+    if (h->rows.size() > h->tick) h->rows.resize(h->tick);
+    u64 executed = 0;                                  // kernels of the ticks that did run (launch_log starts at launch_log_first)
+    for (u32 k = 0; k < h->launch_log.size() && h->launch_log_first + k <= t; ++k) executed += h->launch_log[k];
+    h->last_launches = executed;
+  };
   while (h->tick - start < max_ticks) {
-    u32 n = std::min(chunk, max_ticks - (h->tick - start));
-    for (u32 k = 1; k < n; ++k) if (boundary(h->tick + k)) { n = k; break; }
-    const u32 from = h->tick;
+    const u32 n = std::min(chunk, max_ticks - (h->tick - start));
     if ((rc = launch_ticks(h, n))) return rc;
+    CU(cudaMemcpyAsync(h->pin_ctl, h->d_runctl, 2 * sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    if ((rc = pull_rows(h))) return rc;
-    for (u32 t = from; t < h->tick; ++t) {
-      const serfsim_tick_row_t& r = h->rows[t];
-      // with anti-entropy on, convergence additionally needs a push-pull round that changed nothing but Lamport times
-      // (a Left member is re-sent as "leave at status_ltime + 1", serf/delegate.rs:495-510: status_time creeps by design)
-      const bool pp_ok = !pp || (((t + 1) % pp) == 0 && r.changed == 0);
-      const bool byz_ok = !h->byz_on || r.changed == 0;       // stale entries stay in flight forever: quiescent = no honest traffic and nothing merged
-      if (r.pending == 0 && r.edge_updates == 0 && !future_ops(h, t) && pp_ok && byz_ok) {
-        // ticks after t were no-ops on a quiescent cluster: rewind the logical clock to t + 1
-        if ((rc = rewind_to(h, t + 1))) return rc;
-        if ((rc = finish_timing(h))) return rc;
-        if ((rc = check_overflow(h))) return rc;
-        if (ticks_out) *ticks_out = t;
-        return fire_events(h);
-      }
+    if (h->pin_ctl[0]) {
+      const u32 t = h->pin_ctl[1];
+      stop_at(t);
+      return finish(t, true);
     }
   }
-  if ((rc = finish_timing(h))) return rc;
-  if ((rc = check_overflow(h))) return rc;
-  if (ticks_out) *ticks_out = h->tick;
-  if ((rc = fire_events(h))) return rc;
-  return 1;
+  // max_ticks reached: the last tick's row has not been judged by any kernel yet — apply the same rule here
+  if (h->tick > start) {
+    if ((rc = pull_rows(h))) return rc;
+    const u32 t = h->tick - 1;
+    if (quiescent_row((const u64*)&h->rows[t], t, future_ops(h, t), pp, h->byz_on)) return finish(t, true);
+  }
+  return finish(h->tick, false);
 }
 
 int serfsim_shard_range(serfsim_t* h, uint32_t* first, uint32_t* count) {

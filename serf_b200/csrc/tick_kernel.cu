@@ -116,6 +116,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, 
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
+#else   // host build: a bulk copy is a memcpy that has completed when it returns; barriers have nothing to wait for
+inline void mbar_init(u64*, u32) {}
+inline void mbar_arrive_expect_tx(u64*, u32) {}
+inline void mbar_wait(u64*, u32) {}
+inline void fence_proxy_async() {}
+inline void bulk_g2s(void* dst, const void* src, u32 bytes, u64*, u64) { emu::probes[16] += bytes; memcpy(dst, src, bytes); }
 #endif
 
 // Shared-memory image of one tile (single-slot runs): everything the 256 nodes of the tile read this tick.
@@ -125,6 +131,7 @@ struct StageView {
   const Words* rec; const u64* node; const u32* inL; const u32* inJ; const u32* inM; const u32* rowptr; const u32* col;
   u32 col_base;                            // first CSR element held in `col`
   bool col_staged;                         // false: the tile's CSR span exceeds the stage; gather from global memory
+  u64* wbar; u32 wphase;                   // warp-level stage (tick_kernel): the mbarrier its bulk copy completes on, and the phase to wait for
 };
 
 struct Counters {          // per-thread, reduced once per CTA; rare counters (events, suspects) go straight to the trace row
@@ -137,6 +144,11 @@ __device__ __forceinline__ u32 warp_sum(u32 v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+__device__ __forceinline__ u32 warp_max(u32 v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
 __device__ __forceinline__ u64 warp_sum64(u64 v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -146,12 +158,15 @@ __device__ __forceinline__ u64 warp_sum64(u64 v) {
 // Deliver one entry to `dst` (global id): local → RED.MAX into this shard's inbox plane `plane`
 // (= inbox_wr + (kind·R + slot)·n_local) and mark the destination tile hot for the next tick;
 // cross-shard → append to the peer's receive window over NVLink.
-// Cross-shard staging area of a CTA: entries are grouped by destination shard in shared memory and flushed
-// once per tile with coalesced 8-byte stores into the peer's window (one counter atomic per shard per tile).
-constexpr u32 XTOTAL = 3072;               // staged entries per CTA (24 KB), split evenly over the world-1 peers
+// Cross-shard staging: every WARP owns one small buffer per destination shard in shared memory; entries are appended
+// with a warp-aggregated shared-memory atomic and a buffer that holds at least 32 entries is copied into the peer's
+// window by its own warp — 256+ contiguous bytes over NVLink, one global counter atomic per flush, no CTA barrier
+// anywhere (a per-tile CTA-wide flush cost four barriers per tile and made every warp wait for the slowest one).
 constexpr u32 MAX_WORLD = 8;
-struct XStage { u64 buf[XTOTAL]; u32 cnt[MAX_WORLD]; u32 base[MAX_WORLD]; };
-__device__ __forceinline__ u32 xcap(const TickParams& p) { return XTOTAL / (p.world - 1); }
+constexpr u32 XW_TOTAL = 392;              // staged entries per warp (3 KB), split evenly over the world-1 peers (world 8: 56 each)
+constexpr u32 XW_FLUSH = 32;               // flush threshold: a full warp-wide store
+struct XStage { u64 buf[(BLOCK / 32) * XW_TOTAL]; u32 cnt[BLOCK / 32][MAX_WORLD]; };
+__device__ __forceinline__ u32 xcap(const TickParams& p) { return XW_TOTAL / (p.world - 1); }
 __device__ __forceinline__ u32 xseg(const TickParams& p, u32 shard) { return (shard < p.rank ? shard : shard - 1) * xcap(p); }
 
 template <bool SHARDED>
@@ -165,16 +180,16 @@ __device__ __forceinline__ void deliver(const TickParams& p, XStage* xs, u32* pl
     const u32 dloc = dst - shard * p.shard_size;
     const u64 e = ((u64)val1 << 32) | ((u64)s << 28) | ((u64)kind << 26) | dloc;
     // warp-aggregated append: the lanes of this call that target the same shard reserve their slots with ONE
-    // shared-memory atomic (a per-message atomic on the same counter serialises the whole tile)
+    // shared-memory atomic on the warp's own counter (divergent callers of the same warp may interleave: keep it atomic)
     const u32 peers = __match_any_sync(__activemask(), shard);
-    const u32 lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5, leader = __ffs(peers) - 1;
     u32 base = 0;
-    if (lane == leader) base = atomicAdd(&xs->cnt[shard], (u32)__popc(peers));
+    if (lane == leader) base = atomicAdd(&xs->cnt[wid][shard], (u32)__popc(peers));
     base = __shfl_sync(peers, base, leader);
     const u32 pos = base + (u32)__popc(peers & ((1u << lane) - 1u));
     if (pos < xcap(p)) {
-      xs->buf[xseg(p, shard) + pos] = e;
-    } else {                                   // stage full: write this one straight through
+      xs->buf[wid * XW_TOTAL + xseg(p, shard) + pos] = e;
+    } else {                                   // buffer full: write this one straight through
       const u32 g = atomicAdd(p.send_count + shard, 1u);
       if (g < p.win_cap) p.win_data[shard][(size_t)p.rank * p.win_cap + g] = e;
       else *p.overflow = 2;
@@ -182,28 +197,31 @@ __device__ __forceinline__ void deliver(const TickParams& p, XStage* xs, u32* pl
   }
 }
 
-// Flush the staged cross-shard entries of a tile (whole CTA).
-__device__ __forceinline__ bool flush_xstage(const TickParams& p, XStage* xs) {
-  __syncthreads();
-  if (threadIdx.x < p.world && threadIdx.x != p.rank) {
-    const u32 n = min(xs->cnt[threadIdx.x], xcap(p));
-    xs->base[threadIdx.x] = n ? atomicAdd(p.send_count + threadIdx.x, n) : 0u;
-  }
-  __syncthreads();
+// Copy the warp's staged entries into the peers' windows (whole warp, convergent).  force = false: only buffers that make
+// a full warp-wide store; force = true (end of the kernel): everything.
+__device__ __forceinline__ bool flush_xwarp(const TickParams& p, XStage* xs, bool force) {
+  const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncwarp();
   bool wrote = false;
   for (u32 sh = 0; sh < p.world; ++sh) {
     if (sh == p.rank) continue;
-    const u32 n = min(xs->cnt[sh], xcap(p)), base = xs->base[sh];
-    const u64* src = xs->buf + xseg(p, sh);
+    const u32 staged = xs->cnt[wid][sh];       // uniform over the warp
+    if (staged == 0 || (!force && staged < XW_FLUSH)) continue;
+    if (staged > xcap(p)) wrote = true;        // the excess went straight through
+    const u32 n = min(staged, xcap(p));
+    u32 base = 0;
+    if (lane == 0) base = atomicAdd(p.send_count + sh, n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const u64* src = xs->buf + wid * XW_TOTAL + xseg(p, sh);
     u64* dst = p.win_data[sh] + (size_t)p.rank * p.win_cap;
-    for (u32 i = threadIdx.x; i < n; i += BLOCK) {
+    for (u32 i = lane; i < n; i += 32) {
       if (base + i < p.win_cap) { dst[base + i] = src[i]; wrote = true; }
       else *p.overflow = 2;
     }
+    __syncwarp();
+    if (lane == 0) xs->cnt[wid][sh] = 0;
   }
-  __syncthreads();
-  if (threadIdx.x < MAX_WORLD) xs->cnt[threadIdx.x] = 0;
-  __syncthreads();
+  __syncwarp();
   return wrote;
 }
 
@@ -273,11 +291,13 @@ __device__ __forceinline__ u32 pick_targets(const TickParams& p, const StageView
 
 // What decides whether a node has anything to do this tick: its busy byte (pending work / host op) and the inbox
 // words of the previous tick (slot 0 kept, the other slots OR-ed).  13 bytes per node instead of 45.
-struct Pre { u32 busy, mL, mJ, mM, any, qw; };
+struct Pre { u32 busy, mL, mJ, mM, any, qw, row0, row1; };
 template <bool R1>
-__device__ __forceinline__ Pre prefetch_node(const TickParams& p, u32 vl, bool kL, bool kJ, bool kM, u64 pol_first) {
+__device__ __forceinline__ Pre prefetch_node(const TickParams& p, u32 vl, bool kL, bool kJ, bool kM, u64 pol_first, bool with_rows = false) {
   const u32 nl = p.stride, R = R1 ? 1u : p.R;
   Pre x;
+  x.row0 = x.row1 = 0;
+  if (with_rows) { x.row0 = __ldg(p.row_ptr + vl); x.row1 = __ldg(p.row_ptr + vl + 1); }   // saturated ticks: the warp stages its CSR span (bulk copy) as soon as these arrive
   x.busy = p.busy[vl];
   x.qw = p.qword[vl];                                   // slot-0 queue word (transmit budgets)
   SFS_COUNT(6, 4);
@@ -296,7 +316,7 @@ __device__ __forceinline__ Pre prefetch_node(const TickParams& p, u32 vl, bool k
 }
 
 // Returns true when the node still holds pending work (keeps its tile hot for the next tick).
-template <bool TRACE, int FMAX, bool SHARDED, bool R1, bool STAGED>
+template <bool TRACE, int FMAX, bool SHARDED, bool R1, bool STAGED, bool WSTAGE = false>
 __device__ __forceinline__ bool process_node(const TickParams& p, const StageView& sv, XStage* xs, const u32 vl, const Pre& pre, const bool kL, const bool kJ, const bool kM, const bool mark, const bool saturated,
                                              const u64 pol_first, const u64 pol_last, Counters& c) {
   static_assert(!STAGED || R1, "the staged path is the single-slot path");
@@ -317,8 +337,8 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   Words cur;
   auto load_state = [&]() {
     ns = STAGED ? sv.node[lt] : ld_u64_stream(p.node_state + vl, pol_first);
-    row0 = STAGED ? sv.rowptr[lt] : __ldg(p.row_ptr + vl);
-    row1 = STAGED ? sv.rowptr[lt + 1] : __ldg(p.row_ptr + vl + 1);
+    row0 = STAGED ? sv.rowptr[lt] : (WSTAGE ? pre.row0 : __ldg(p.row_ptr + vl));
+    row1 = STAGED ? sv.rowptr[lt + 1] : (WSTAGE ? pre.row1 : __ldg(p.row_ptr + vl + 1));
     if (STAGED) {
       const uint4 a = reinterpret_cast<const uint4*>(sv.rec + lt)[0], b = reinterpret_cast<const uint4*>(sv.rec + lt)[1];
       cur.w[0] = a.x; cur.w[1] = a.y; cur.w[2] = a.z; cur.w[3] = a.w; cur.w[4] = b.x; cur.w[5] = b.y; cur.w[6] = b.z; cur.w[7] = b.w;
@@ -466,7 +486,11 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
       // ---------------- Phase S ----------------
       const u32 mx = max(r.txl, max(r.txj, r.txm));
       if (mx) {
-        if (!have_targets) { nt = pick_targets<FMAX, STAGED>(p, sv, v, row0, deg, tg); have_targets = true; }
+        if (!have_targets) {
+          if (WSTAGE && sv.col_staged) mbar_wait(sv.wbar, sv.wphase);       // the warp's CSR span has landed in shared memory
+          nt = pick_targets<FMAX, STAGED || WSTAGE>(p, sv, v, row0, deg, tg);
+          have_targets = true;
+        }
         u32* const planeL = p.inbox_wr + (size_t)(KIND_LEAVE * R + s) * nl;
         u32* const planeJ = p.inbox_wr + (size_t)(KIND_JOIN * R + s) * nl;
         u32* const planeM = p.inbox_wr + (size_t)(KIND_ML * R + s) * nl;
@@ -521,11 +545,12 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
   __shared__ u64 red[8][BLOCK / 32];
   __shared__ __align__(16) unsigned char xs_mem[SHARDED ? sizeof(XStage) : 16];
   XStage* xs = reinterpret_cast<XStage*>(xs_mem);
+  if (gate_closed(p.gate, blockIdx.x == 0 && threadIdx.x == 0)) return;   // the run is over (uniform over the grid): this tick does not exist
   Counters c = {};
   const bool kL = p.kinds_prev[KIND_LEAVE] != 0, kJ = p.kinds_prev[KIND_JOIN] != 0, kM = p.kinds_prev[KIND_ML] != 0;
   const u64 pol_first = policy_evict_first(), pol_last = policy_evict_last();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (SHARDED && threadIdx.x < MAX_WORLD) xs->cnt[threadIdx.x] = 0;
+  if (SHARDED && threadIdx.x < (BLOCK / 32) * MAX_WORLD) xs->cnt[threadIdx.x / MAX_WORLD][threadIdx.x % MAX_WORLD] = 0;
   bool wrote_remote = false;
 
   // Dense / sparse ticks.  While the gossip front is wide (the previous tick sent at least one message per
@@ -554,7 +579,18 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
   // node logic on dense blocks of 256 list entries: one chain per 256 ACTIVE nodes.  Nodes are independent within a
   // tick and every cross-node effect is a commutative reduction, so the visiting order changes nothing.
   constexpr u32 GROUP = SHARDED ? 4 : 8;
-  __shared__ uint4 act_s[GROUP * BLOCK];                   // x: tile-in-group << 8 | lane, busy << 16, any << 24; y, z, w: inbox words
+  // One shared-memory region, two uses (a launch takes one path or the other): the active-node list of the compaction
+  // path, or — tile-by-tile walk of saturated ticks — one CSR stage per warp: the neighbour lists of the warp's 32 nodes are
+  // one contiguous span of `col`, bulk-copied (cp.async.bulk → UBLKCP, completion on the warp's own mbarrier) into shared
+  // memory by lane 0 as soon as the row offsets are known.  The four neighbour picks of a node then read shared memory
+  // instead of issuing four scattered 4-byte gathers: at out-degree 16 that is 16 L1 tag requests per warp less per pick
+  // instruction (the plateau tick is bound by the L1 request rate: 40 M RED + 20 M gather tags of 64 M per tick).
+  constexpr u32 WCAP = SHARDED ? 576 : 1024;               // CSR entries per warp stage (degree ≤ 16 / ≤ 32 on average); larger spans gather from global memory
+  constexpr u32 UBYTES = (GROUP * BLOCK * 16 > (BLOCK / 32) * WCAP * 4) ? GROUP * BLOCK * 16 : (BLOCK / 32) * WCAP * 4;
+  __shared__ __align__(128) unsigned char u_mem[UBYTES];
+  uint4* const act_s = reinterpret_cast<uint4*>(u_mem);    // x: tile-in-group << 8 | lane, busy << 16, any << 24; y, z, w: inbox words
+  u32* const wstage_s = reinterpret_cast<u32*>(u_mem);
+  __shared__ __align__(8) u64 wbar_s[BLOCK / 32];
   __shared__ u32 act_n;
   __shared__ u8 pend_s[GROUP];
   __shared__ u16 gt_s[GROUP];
@@ -605,7 +641,7 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
           const bool pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, false, pol_first, pol_last, c);
           if (mark && pend) pend_s[g] = 1;
         }
-        if (SHARDED) wrote_remote |= flush_xstage(p, xs);
+        if (SHARDED) wrote_remote |= flush_xwarp(p, xs, false);
       }
       __syncthreads();
       if (mark && threadIdx.x < ng && pend_s[threadIdx.x]) p.hot_wr[tile0 + gt_s[threadIdx.x]] = 1;
@@ -614,9 +650,17 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
   } else {
   // Walk the hot tiles of this CTA.  The 13 "is there anything to do" bytes of the NEXT hot tile (busy byte, inbox
   // words) are requested before the current tile is processed, so an idle tile costs no exposed round trip.
+  const bool wstage = saturated && p.wstage;             // uniform over the grid
+  if (wstage) {
+    if (lane == 0) mbar_init(&wbar_s[wid], 1);
+    fence_proxy_async();
+    __syncwarp();
+  }
+  u32 wphase = 0;
+  bool armed = false;
   auto prefetch_tile = [&](u32 ti) -> Pre {
     const u32 vn = ((tile0 + ti) << TILE_SHIFT) + threadIdx.x;
-    return vn < p.n_local ? prefetch_node<R1>(p, vn, kL, kJ, kM, pol_first) : Pre{};
+    return vn < p.n_local ? prefetch_node<R1>(p, vn, kL, kJ, kM, pol_first, true) : Pre{};
   };
   u32 i = 0;
   while (i < ntile && !hot_s[i]) ++i;
@@ -629,13 +673,39 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
     if (j < ntile) pre_next = prefetch_tile(j);
     const u32 vl = ((tile0 + i) << TILE_SHIFT) + threadIdx.x;
     bool pend = false;
-    if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, saturated, pol_first, pol_last, c);
+    StageView sv{};
+    if (wstage) {
+      // the warp's CSR span [s0, s1) (16-byte granules; `col` is padded) — worth staging when enough of its nodes hold queued transmits
+      const u32 s0 = __shfl_sync(0xffffffffu, pre.row0, 0) & ~3u;
+      const u32 s1 = (warp_max(pre.row1) + 3u) & ~3u;
+      const u32 senders = (u32)__popc(__ballot_sync(0xffffffffu, (pre.busy & 1u) != 0));
+      if (armed) { mbar_wait(&wbar_s[wid], wphase); wphase ^= 1u; armed = false; }      // the previous copy has landed (nobody may have waited for it)
+      if (senders >= 4 && s1 > s0 && s1 - s0 <= WCAP) {
+        __syncwarp();                                      // every lane is done reading the previous tile's span
+        if (lane == 0) {
+          fence_proxy_async();
+          mbar_arrive_expect_tx(&wbar_s[wid], (s1 - s0) * 4u);
+          bulk_g2s(wstage_s + wid * WCAP, p.col + s0, (s1 - s0) * 4u, &wbar_s[wid], pol_first);
+        }
+#ifdef SERFSIM_EMU
+        __syncwarp();                                      // host build: the copy is lane 0's memcpy and mbar_wait is a no-op — order it before the other lanes' reads
+#endif
+        armed = true;
+        sv.col = wstage_s + wid * WCAP; sv.col_base = s0; sv.col_staged = true; sv.wbar = &wbar_s[wid]; sv.wphase = wphase;
+        SFS_PROBE(3);
+      }
+    }
+    if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, R1, false, true>(p, sv, xs, vl, pre, kL, kJ, kM, mark, saturated, pol_first, pol_last, c);
     if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + i] = 1;
-    if (SHARDED) wrote_remote |= flush_xstage(p, xs);
+    if (SHARDED) wrote_remote |= flush_xwarp(p, xs, false);
     i = j;
   }
+  if (armed) mbar_wait(&wbar_s[wid], wphase);            // no bulk copy may be in flight into this CTA's shared memory when it exits
   }
-  if (SHARDED && wrote_remote) __threadfence_system();   // peer-window stores are performed before the publish kernel raises the flags
+  if (SHARDED) {
+    wrote_remote |= flush_xwarp(p, xs, true);
+    if (wrote_remote) __threadfence_system();            // peer-window stores are performed before the publish kernel raises the flags
+  }
   // block reduction (warp shuffles, then shared memory) → one atomic per counter per CTA.
   // trace row: 0 packets, 1 edge_updates, 2 messages, 3 changed, 4 pending, (5 events, 6 suspects: direct), 7 hash
   const u64 vals[8] = {c.packets, c.edges, (u64)c.kL + c.kJ + c.kM, c.changed, c.pending, c.kL, c.kJ, c.kM};
@@ -674,6 +744,7 @@ __global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constan
   __shared__ u64 red[8][BLOCK / 32];
   __shared__ __align__(8) u64 full_bar[2], empty_bar[2];
   __shared__ u32 col_base_s[2], col_ok_s[2];
+  if (gate_closed(p.gate, blockIdx.x == 0 && threadIdx.x == 0)) return;
   Counters c = {};
   const bool kL = p.kinds_prev[KIND_LEAVE] != 0, kJ = p.kinds_prev[KIND_JOIN] != 0, kM = p.kinds_prev[KIND_ML] != 0;
   const u64 pol_first = policy_evict_first(), pol_last = policy_evict_last();
@@ -790,6 +861,7 @@ __global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constan
 // handlers' results discarded: nothing is re-queued (delegate.rs:495-523).  A node writes only its own records.
 template <bool TRACE>
 __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__ TickParams p, const uint4* __restrict__ snap_rec, const u64* __restrict__ snap_node) {
+  if (p.gate.ctl && p.gate.ctl[0]) return;
   long long d_changed = 0, d_pending = 0;
   u64 d_hash = 0;
   for (u32 vl = blockIdx.x * BLOCK + threadIdx.x; vl < p.n_local; vl += gridDim.x * BLOCK) {
@@ -895,10 +967,14 @@ __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__
 // After the tick kernel: publish, to every peer, how many entries this rank wrote into its window, then raise
 // the peer's flag for this exchange (system-scope release).  One warp.
 __global__ void publish_kernel(const __grid_constant__ PublishParams p) {
+  if (p.gate && *p.gate) return;
   const u32 r = threadIdx.x;
   if (r < p.world && r != p.rank) {
     u32* ctrl = p.peer_ctrl[r] + p.xpar * 16;
     ctrl[p.rank] = p.send_count[r];
+    u64* sums = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(p.peer_ctrl[r]) + CTRL_SUMS_OFF) + ((size_t)p.xpar * 8 + p.rank) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sums[i] = p.row[i];          // this rank's counters of the tick: every rank sums them on the device
     __threadfence_system();
     st_release_sys(ctrl + 8 + p.rank, p.stamp);
     p.send_count[r] = 0;
@@ -909,11 +985,18 @@ __global__ void publish_kernel(const __grid_constant__ PublishParams p) {
 // this exchange's flag — the peers' publish kernels precede their own drains in stream order, so the wait
 // cannot deadlock — then reduces the entries exactly like local deliveries.
 __global__ void __launch_bounds__(BLOCK) drain_kernel(const __grid_constant__ DrainParams p) {
+  if (p.gate && *p.gate) return;
   if (threadIdx.x < p.world && threadIdx.x != p.rank) {
     u32 f;
     do { f = ld_acquire_sys(p.ctrl + 8 + threadIdx.x); } while (f != p.stamp);
   }
   __syncthreads();
+  // global trace row of this tick: my counters + the rows the peers published with their flags (acquired above)
+  if (blockIdx.x == 0 && threadIdx.x < 8) {
+    u64 s = p.my_row[threadIdx.x];
+    for (u32 src = 0; src < p.world; ++src) if (src != p.rank) s += __ldcg(p.sums + (size_t)src * 8 + threadIdx.x);
+    p.grow[threadIdx.x] = s;
+  }
   // same dense / sparse decision as the tick kernel of this tick: in a dense tick the next tick processes every
   // tile anyway, so per-entry tile marking (millions of byte stores onto a few thousand flags) is skipped
   const u32 prev_msgs = p.kinds_prev[KIND_LEAVE] + p.kinds_prev[KIND_JOIN] + p.kinds_prev[KIND_ML];

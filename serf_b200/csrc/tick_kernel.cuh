@@ -27,6 +27,39 @@ constexpr int SFS_SMS = 1;
 
 namespace sfs {
 
+// Device-side convergence gate (serfsim_run_until_converged).  The host launches ticks in large chunks without looking at
+// their rows; the FIRST kernel of tick t evaluates the quiescence rule on the (global) row of tick t-1 and, when the run is
+// over, sets a sticky word — that kernel and every later kernel of the call then return at once, so ticks launched past the
+// first quiescent one cost a few microseconds of launch latency and touch no state at all (no rewind, no consumed tile
+// flags, no exchange epoch).  Every rank evaluates the same global row with the same parameters, so all ranks stop at the
+// same tick without a host collective.  ctl[0]: done flag, ctl[1]: index of the first quiescent tick.
+struct Gate {
+  u32* ctl;                   // null: gating off (serfsim_step)
+  const u64* prev_row;        // global trace row of tick-1 (8 × u64); null for the first tick of a call (it always runs)
+  u32 tick;                   // this tick
+  u32 evaluate;               // 1: this kernel is the first of the tick's launch sequence and evaluates the rule
+  u32 future_ops;             // a host operation is scheduled at a tick > tick-1
+  u32 pp, byz_on;             // push-pull interval (0 = off), byzantine injectors on
+};
+// The quiescence rule — one definition for the device gate and the host (max_ticks boundary, serfsim.cu):
+// nothing pending, nothing delivered, no operation still to come; with anti-entropy on additionally a push-pull round that
+// changed nothing but Lamport times (serf/delegate.rs:495-510: status_time creeps by design); with injectors on nothing merged
+// (stale entries stay in flight forever).
+__host__ __device__ inline bool quiescent_row(const u64* row, u32 t, bool future_ops, u32 pp, bool byz_on) {
+  const u64 edges = row[1], changed = row[3], pending = row[4];
+  const bool pp_ok = !pp || (((t + 1) % pp) == 0 && changed == 0);
+  const bool byz_ok = !byz_on || changed == 0;
+  return pending == 0 && edges == 0 && !future_ops && pp_ok && byz_ok;
+}
+__device__ __forceinline__ bool gate_closed(const Gate& g, bool leader) {
+  if (!g.ctl) return false;
+  if (g.ctl[0]) return true;
+  if (!g.evaluate || !g.prev_row) return false;
+  if (!quiescent_row(g.prev_row, g.tick - 1, g.future_ops != 0, g.pp, g.byz_on != 0)) return false;
+  if (leader) { g.ctl[1] = g.tick - 1; g.ctl[0] = 1; }      // every CTA of this kernel reaches the same verdict from the row itself
+  return true;
+}
+
 struct TickParams {
   // geometry / run constants
   u32 n_local, first, n_global, R;
@@ -68,12 +101,21 @@ struct TickParams {
   // push-pull replay of the partner's user-event ring (delegate.rs:469-474, 539-552); ue_table.n == 0: user events off
   UeTable ue_table; uint4* ue_state; const uint4* ue_snap; const uint4* const* ue_snap_peer; const u32* ue_ltime; u64* ue_totals;
   u32 compact;                // 1: unsaturated ticks gather their active nodes across several tiles (SERFSIM_COMPACT=0 switches it off)
+  Gate gate;
+  u32 wstage;                 // 1: saturated ticks stage each warp's CSR span in shared memory with a bulk copy (SERFSIM_WSTAGE=0 switches it off)
 };
 
-struct PublishParams {        // after the tick kernel: tell every peer how much was written, then raise its flag
+// Control block of a rank (one allocation, mapped into every peer): per exchange parity the entry counts and epoch flags
+// the peers write, then the peers' trace rows of that tick (the device-side sum of the per-tick counters).
+constexpr u32 CTRL_U32 = 2 * 16;                        // [parity][ counts[8] | flags[8] ]
+constexpr u32 CTRL_SUMS_OFF = CTRL_U32 * 4;             // byte offset of u64 sums[2][8][8]  ([parity][source rank][field])
+constexpr size_t CTRL_BYTES = CTRL_SUMS_OFF + 2 * 8 * 8 * sizeof(u64);
+struct PublishParams {        // after the tick kernel: tell every peer how much was written and this rank's row, then raise its flag
   u32 world, rank, stamp, xpar;
   u32* send_count;            // [world] local, reset here
-  u32* const* peer_ctrl;      // [world] peers' control blocks: [parity][ counts[8] | flags[8] ]
+  u32* const* peer_ctrl;      // [world] peers' control blocks
+  const u64* row;             // this rank's trace row of the tick (complete: the tick kernels precede the publish kernel)
+  const u32* gate;            // sticky done word of the convergence gate (null: off)
 };
 
 struct DrainParams {
@@ -93,6 +135,9 @@ struct DrainParams {
   u32 ue_n;
   u32* ue_inbox_wr;
   u32* ue_ltime;
+  // device-side sum of the tick's trace row over all ranks: grow[i] = my_row[i] + Σ peers' published rows
+  const u64* my_row; const u64* sums; u64* grow;
+  const u32* gate;
 };
 
 void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st);
@@ -125,6 +170,7 @@ struct UeParams {
   u64* row;                   // this tick's trace row (shared with the membership kernel)
   u64* totals;                // run totals: 0 messages, 1 edges, 2 delivered, 3 duplicates, 4 too_old
   u32* overflow;
+  Gate gate;                  // the user-event kernel is the first kernel of a tick when user events are on
   // sharded runs: a target outside [first, first + n_local) gets one window entry per event (kind 3) over NVLink
   u32 world, rank, shard_size, win_cap;
   u64* const* win_data;       // [world] peers' receive windows of this exchange parity
@@ -154,6 +200,7 @@ struct ByzParams {
   u64* const* win_data;
   u32* send_count;
   u32* overflow;
+  const u32* gate;
 };
 constexpr u32 BYZ_FLAG = 1u << 25;          // in the 26-bit destination field of a window entry (shards hold < 2^25 nodes when injectors are on)
 constexpr u32 BYZ_ANNOT_SLOT = 15;

@@ -27,6 +27,7 @@ __device__ __forceinline__ u64 ue_warp_sum64(u64 v) {
 
 template <bool TRACE>
 __global__ void __launch_bounds__(UE_BLOCK) uevent_kernel(const __grid_constant__ UeParams p) {
+  if (gate_closed(p.gate, blockIdx.x == 0 && threadIdx.x == 0)) return;   // the run is over: this tick does not exist
   UeCounts c = {};
   u32 changed = 0;
   u64 hash = 0;
