@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SERFSIM_ABI_VERSION 3u
+#define SERFSIM_ABI_VERSION 4u
 
 /* ---- error codes ------------------------------------------------------------------ */
 #define SERFSIM_OK            0
@@ -202,6 +202,11 @@ int serfsim_lamport_time (serfsim_t* h, uint64_t* out /*[count]*/);             
  * SERFSIM_E_OVERFLOW instead of wrapping), so a caller that reads them every step can take them as u32 and widen lazily. */
 int serfsim_status_ltime_u32(serfsim_t* h, uint32_t slot, uint32_t* out /*[count]*/);
 int serfsim_lamport_time_u32(serfsim_t* h, uint32_t* out /*[count]*/);
+/* The same three vectors without stalling the caller (any pointer may be NULL): the extraction is ordered after the ticks on the
+ * library's launch stream, the device→host copies run on a second stream and overlap whatever the caller does next (e.g. the
+ * ticks of its next study).  The buffers (pinned, ideally) must stay valid until serfsim_results_wait returns. */
+int serfsim_results_async(serfsim_t* h, uint32_t slot, uint8_t* status /*[count]*/, uint32_t* status_ltime /*[count]*/, uint32_t* lamport /*[count]*/);
+int serfsim_results_wait (serfsim_t* h);
 int serfsim_incarnation  (serfsim_t* h, uint32_t slot, uint32_t* out /*[count]*/);  /* memberlist incarnation of the subject as seen         */
 int serfsim_ml_state     (serfsim_t* h, uint32_t slot, uint8_t*  out /*[count]*/);  /* SERFSIM_ML_*                                          */
 int serfsim_records      (serfsim_t* h, uint32_t slot, void* out /*[count][32]*/);  /* raw 32-byte member records (layout: DESIGN.md)        */

@@ -37,6 +37,8 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <pthread.h>
+#include <sched.h>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -630,7 +632,13 @@ struct TickSim {
   std::vector<u8> anomaly;                                     // per node: sender flag
   u64 byz_tot[3] = {0, 0, 0};                                  // injected entries, injected (peer, subject) pairs, senders flagged
   int threads = 1;
+  std::vector<int> pin;                                        // optional: worker c of the tick loop runs on logical CPU pin[c % size] (stable timings)
   std::string err;
+  void pin_worker(u32 c) const {
+    if (pin.empty()) return;
+    cpu_set_t set; CPU_ZERO(&set); CPU_SET(pin[c % pin.size()], &set);
+    pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+  }
 
   View& at(u32 s, u32 v) { return rec[(size_t)s * N + v]; }
 
@@ -975,7 +983,7 @@ struct TickSim {
     }
     };
     if (T == 1) work(0);
-    else { std::vector<std::thread> th; for (u32 c = 0; c < T; ++c) th.emplace_back(work, c); for (auto& x : th) x.join(); }
+    else { std::vector<std::thread> th; for (u32 c = 0; c < T; ++c) th.emplace_back([&, c] { pin_worker(c); work(c); }); for (auto& x : th) x.join(); }
     mail.swap(mail_next);
     if (byz_n) {
       // Verdicts: every stale entry posted this tick is judged against its receiver's view as it stands when the node loop
@@ -1063,7 +1071,7 @@ struct TickSim {
         }
       };
       if (T == 1) ppwork(0);
-      else { std::vector<std::thread> th; for (u32 c = 0; c < T; ++c) th.emplace_back(ppwork, c); for (auto& x : th) x.join(); }
+      else { std::vector<std::thread> th; for (u32 c = 0; c < T; ++c) th.emplace_back([&, c] { pin_worker(c); ppwork(c); }); for (auto& x : th) x.join(); }
       for (u32 c = 0; c < T; ++c) { ue_tot[2] += pp_ue[(size_t)c * 3]; ue_tot[3] += pp_ue[(size_t)c * 3 + 1]; ue_tot[4] += pp_ue[(size_t)c * 3 + 2]; }
     }
     serfsim_tick_row_t row{};
@@ -1457,6 +1465,14 @@ ORC int oracle_sim_import(void* p, const void* in, u32 n) {
 }
 ORC u32 oracle_msg_size(void) { return (u32)sizeof(Msg); }
 
+// Pin worker c of the tick loop to logical CPU cpus[c % n] (n = 0: no pinning).  Timing aid for bench.py's CPU arm: unpinned
+// workers migrate between NUMA nodes and the same run varied 5x between two boxes.  Results do not depend on it.
+ORC int oracle_sim_set_affinity(void* p, const int* cpus, int n) {
+  auto* s = (TickSim*)p;
+  if (n < 0 || (n && !cpus)) return SERFSIM_E_INVAL;
+  s->pin.assign(cpus, cpus + n);
+  return 0;
+}
 // Number of host threads the tick loop uses (results are independent of it).  Takes effect at the next reset.
 ORC int oracle_sim_set_threads(void* p, int n) {
   auto* s = (TickSim*)p;

@@ -132,6 +132,7 @@ struct serfsim {
   bool has_topo = false;
   u32 stage_col_bytes = 0;         // 0: direct-load kernel; else bytes of CSR per TMA stage
   u32 max_tile_edges = 0;          // largest 16-byte-aligned CSR span of one 256-node tile (sizes the TMA stage)
+  u32 udeg = 0;                    // uniform out-degree of the shard's rows (0: degrees differ)
   std::vector<serfsim_tick_row_t> rows;   // rows pulled from the device so far (global sums when sharded)
   // device-side convergence gate (tick_kernel.cuh: Gate)
   u32* d_runctl = nullptr;         // [0] done flag, [1] first quiescent tick
@@ -168,7 +169,13 @@ struct serfsim {
   bool l2_window = false;           // SERFSIM_L2_WINDOW=1: stream access-policy window over the inbox being written
   bool no_skip = false;             // SERFSIM_NO_SKIP=1: process every tile every tick (A/B measurements)
   bool compact = true;              // SERFSIM_COMPACT=0: tile-by-tile walk in unsaturated ticks too (A/B measurements)
-  bool wstage = true;               // SERFSIM_WSTAGE=0: saturated ticks gather their neighbour picks from global memory instead of a staged CSR span
+  // asynchronous result read-back (serfsim_results_async): extraction into a ring of staging buffers on the launch stream,
+  // device→host copies on a second stream so that they overlap the ticks of the caller's next step
+  struct ResBuf { unsigned char* d = nullptr; cudaEvent_t copied = nullptr; bool used = false; };
+  ResBuf res[4];
+  u32 res_next = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_extracted = nullptr;
   std::vector<cudaEvent_t> tick_ev;      // 2 per tick when tick_timing
   std::vector<cudaEvent_t> mid_ev;       // after the tick kernel (multi-GPU breakdown, SERFSIM_XTIMING=1)
 };
@@ -272,7 +279,7 @@ int launch_ticks(serfsim* h, u32 n) {
     p.stride = h->stride; p.n_tiles = h->n_tiles; p.tiles_per_cta = (h->n_tiles + h->grid - 1) / h->grid;
     p.force_all = (h->cfg.trace != 0) || h->no_skip || p.reap_now;
     p.compact = h->compact ? 1u : 0u;
-    p.wstage = h->wstage ? 1u : 0u;
+    p.udeg = h->udeg;
     const u32 xpar = h->xepoch & 1;
     p.world = (u32)h->cfg.world_size; p.rank = (u32)h->cfg.rank; p.shard_size = h->shard_size; p.win_cap = h->win_cap;
     p.win_data = h->d_peer_data[xpar]; p.send_count = h->d_send_count;
@@ -536,6 +543,9 @@ void free_all(serfsim* h) {
   cudaFree(h->d_ue_state); cudaFree(h->d_ue_inbox[0]); cudaFree(h->d_ue_inbox[1]); cudaFree(h->d_ue_ltime); cudaFree(h->d_ue_totals);
   for (int par = 0; par < 2; ++par) { cudaFree(h->d_win_data[par]); cudaFree(h->d_peer_data[par]); }
   cudaFree(h->d_ctrl); cudaFree(h->d_send_count); cudaFree(h->d_peer_ctrl);
+  for (auto& b : h->res) { cudaFree(b.d); if (b.copied) cudaEventDestroy(b.copied); }
+  if (h->ev_extracted) cudaEventDestroy(h->ev_extracted);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->pin_ctl) cudaFreeHost(h->pin_ctl);
   cudaFree(h->d_runctl); cudaFree(h->d_grow);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -643,7 +653,7 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
   CUB(cudaMemcpy(h->d_subj, h->subj.data(), h->R * 4, cudaMemcpyHostToDevice));
   {
     const char* e = getenv("SERFSIM_MINB");
-    h->ctas_per_sm = (h->R == 1) ? ((e && atoi(e) == 5) ? 5 : 4) : 3;
+    h->ctas_per_sm = (h->R == 1) ? ((e && atoi(e) == 5) ? 5 : tick_ctas_per_sm_r1()) : 3;
   }
   h->grid = tick_grid_size(h->count, h->ctas_per_sm);
   {
@@ -660,7 +670,6 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
   }
   if (const char* e = getenv("SERFSIM_NO_SKIP")) h->no_skip = atoi(e) != 0;
   if (const char* e = getenv("SERFSIM_COMPACT")) h->compact = atoi(e) != 0;
-  if (const char* e = getenv("SERFSIM_WSTAGE")) h->wstage = atoi(e) != 0;
   if (cfg->world_size > 1) {
     // receive windows: one segment per peer; expected entries per tick and pair ≈ shard · fanout · R · kinds / world
     if (cfg->world_size > 8) return bail(fail(SERFSIM_E_INVAL, "world_size > 8"));
@@ -730,6 +739,9 @@ int serfsim_set_topology_csr(serfsim_t* h, const uint64_t* row_ptr, const uint32
     rp[i] = (u32)(r - e0);
   }
   const u64 ne = e1 - e0;
+  h->udeg = (h->count && ne % h->count == 0) ? (u32)(ne / h->count) : 0u;
+  for (u32 i = 0; i <= h->count && h->udeg; ++i) if (rp[i] != (u64)i * h->udeg) h->udeg = 0;
+  if (const char* e = getenv("SERFSIM_UDEG")) { if (!atoi(e)) h->udeg = 0; }   // A/B: force the general path
   for (size_t i = h->count + 1; i < rp.size(); ++i) rp[i] = (u32)ne;      // padding rows: degree 0
   h->max_tile_edges = 0;
   for (u32 b = 0; b < h->count; b += 256) {
@@ -875,6 +887,35 @@ int serfsim_status_ltime_u32(serfsim_t* h, uint32_t slot, uint32_t* out) { retur
 int serfsim_lamport_time_u32(serfsim_t* h, uint32_t* out) { return getter(h, 0, EXTRACT_CLOCK32, out, 4); }
 int serfsim_incarnation(serfsim_t* h, uint32_t slot, uint32_t* out) { return getter(h, slot, EXTRACT_INC, out, 4); }
 int serfsim_ml_state(serfsim_t* h, uint32_t slot, uint8_t* out) { return getter(h, slot, EXTRACT_ML, out, 1); }
+
+// The step's result vectors without stalling the launch stream: the three extractions run on the launch stream (in order after
+// the ticks), the device→host copies on a second stream.  The caller may start its next step at once; the copies overlap its
+// ticks.  Host buffers must stay valid (and should be pinned) until serfsim_results_wait returns.
+int serfsim_results_async(serfsim_t* h, uint32_t slot, uint8_t* status, uint32_t* status_ltime, uint32_t* lamport) {
+  if (!h) return fail(SERFSIM_E_INVAL, "null handle");
+  if (slot >= h->R) return fail(SERFSIM_E_INVAL, "slot out of range");
+  if (!h->copy_stream) { CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)); CU(cudaEventCreate(&h->ev_extracted)); }
+  serfsim::ResBuf& b = h->res[h->res_next++ & 3u];
+  const size_t n = h->count, n4 = ((n * 4 + 255) / 256) * 256;
+  if (!b.d) { CU(cudaMalloc(&b.d, 2 * n4 + n)); CU(cudaEventCreate(&b.copied)); }
+  if (b.used) CU(cudaStreamWaitEvent(h->stream, b.copied, 0));            // the copy that last read this staging buffer has finished
+  if (status_ltime) launch_extract(h->d_rec, h->d_node, h->count, h->stride, slot, EXTRACT_STATUS_LTIME32, b.d, h->stream);
+  if (lamport) launch_extract(h->d_rec, h->d_node, h->count, h->stride, slot, EXTRACT_CLOCK32, b.d + n4, h->stream);
+  if (status) launch_extract(h->d_rec, h->d_node, h->count, h->stride, slot, EXTRACT_STATUS, b.d + 2 * n4, h->stream);
+  CU(cudaEventRecord(h->ev_extracted, h->stream));
+  CU(cudaStreamWaitEvent(h->copy_stream, h->ev_extracted, 0));
+  if (status_ltime) CU(cudaMemcpyAsync(status_ltime, b.d, n * 4, cudaMemcpyDeviceToHost, h->copy_stream));
+  if (lamport) CU(cudaMemcpyAsync(lamport, b.d + n4, n * 4, cudaMemcpyDeviceToHost, h->copy_stream));
+  if (status) CU(cudaMemcpyAsync(status, b.d + 2 * n4, n, cudaMemcpyDeviceToHost, h->copy_stream));
+  CU(cudaEventRecord(b.copied, h->copy_stream));
+  b.used = true;
+  return 0;
+}
+int serfsim_results_wait(serfsim_t* h) {
+  if (!h) return fail(SERFSIM_E_INVAL, "null handle");
+  if (h->copy_stream) CU(cudaStreamSynchronize(h->copy_stream));
+  return 0;
+}
 
 int serfsim_records(serfsim_t* h, uint32_t slot, void* out) {
   if (!h || !out) return fail(SERFSIM_E_INVAL, "null argument");

@@ -31,6 +31,9 @@ namespace sfs {
 namespace {
 
 constexpr int BLOCK = 256;
+#ifndef SFS_MB_R1
+#define SFS_MB_R1 4                         // resident CTAs per SM of the single-slot kernels (64 registers per thread)
+#endif
 constexpr u32 TILE_SHIFT = 8;              // one tile = one CTA pass = 256 nodes
 constexpr u32 MAX_TILES_PER_CTA = 1024;
 static_assert((1u << TILE_SHIFT) == BLOCK, "tile = block");
@@ -116,12 +119,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, 
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
-#else   // host build: a bulk copy is a memcpy that has completed when it returns; barriers have nothing to wait for
-inline void mbar_init(u64*, u32) {}
-inline void mbar_arrive_expect_tx(u64*, u32) {}
-inline void mbar_wait(u64*, u32) {}
-inline void fence_proxy_async() {}
-inline void bulk_g2s(void* dst, const void* src, u32 bytes, u64*, u64) { emu::probes[16] += bytes; memcpy(dst, src, bytes); }
 #endif
 
 // Shared-memory image of one tile (single-slot runs): everything the 256 nodes of the tile read this tick.
@@ -131,7 +128,6 @@ struct StageView {
   const Words* rec; const u64* node; const u32* inL; const u32* inJ; const u32* inM; const u32* rowptr; const u32* col;
   u32 col_base;                            // first CSR element held in `col`
   bool col_staged;                         // false: the tile's CSR span exceeds the stage; gather from global memory
-  u64* wbar; u32 wphase;                   // warp-level stage (tick_kernel): the mbarrier its bulk copy completes on, and the phase to wait for
 };
 
 struct Counters {          // per-thread, reduced once per CTA; rare counters (events, suspects) go straight to the trace row
@@ -142,11 +138,6 @@ struct Counters {          // per-thread, reduced once per CTA; rare counters (e
 __device__ __forceinline__ u32 warp_sum(u32 v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ u32 warp_max(u32 v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
 __device__ __forceinline__ u64 warp_sum64(u64 v) {
@@ -252,13 +243,14 @@ __device__ __forceinline__ bool differs(const Words& a, const Words& b) {
 // node itself are dropped; peers are used in draw order.  No rejection loop, no divergence, m gathers.
 constexpr u32 NO_TARGET = 0xffffffffu;
 __device__ __forceinline__ u32 draw16(const u32 (&w)[4], int i) { const u32 x = w[(i >> 1) & 3]; return (i & 1) ? (x >> 16) : (x & 0xffffu); }
+// pick_issue draws the slots and requests the neighbour ids (cand[]: loads in flight), pick_finish drops self slots and packs the targets.
+#define SFS_LD_COL(ptr, pol) __ldg(ptr)     // read-only path WITH L1 allocation: the four picks of a node fall into its two CSR sectors, later picks hit L1 (an evict_first / no-allocate gather was 6 % slower in plateau ticks)
 template <int FMAX, bool STAGED>
-__device__ __forceinline__ u32 pick_targets(const TickParams& p, const StageView& sv, u32 v, u32 row0, u32 deg, u32 (&tg)[FMAX]) {
+__device__ __forceinline__ void pick_issue(const TickParams& p, const StageView& sv, u32 v, u32 row0, u32 deg, u64 pol_first, u32 (&cand)[FMAX]) {
   const u32 m = min(p.fanout, deg);
   u32 w[4];
   philox4x32_10(p.tick, v, 0, DOMAIN_GOSSIP, p.seed_lo, p.seed_hi, w);
   u32 srt[FMAX];                                           // chosen slots so far, ascending; unused entries = NO_TARGET (sort last)
-  u32 cand[FMAX];
 #pragma unroll
   for (int k = 0; k < FMAX; ++k) srt[k] = NO_TARGET;
 #pragma unroll
@@ -268,13 +260,16 @@ __device__ __forceinline__ u32 pick_targets(const TickParams& p, const StageView
     for (int i = 0; i < k; ++i) j += (j >= srt[i]) ? 1u : 0u;         // rank → slot: skip the slots already taken
     const bool use = (u32)k < m;
     const u32 e = row0 + (use ? j : 0u);
-    cand[k] = use ? ((STAGED && sv.col_staged) ? sv.col[e - sv.col_base] : __ldg(p.col + e)) : v;
+    cand[k] = use ? ((STAGED && sv.col_staged) ? sv.col[e - sv.col_base] : SFS_LD_COL(p.col + e, pol_first)) : v;
     // insert j into the ascending list (only if used): bubble it down from position k
     u32 x = use ? j : NO_TARGET;
 #pragma unroll
     for (int i = 0; i < k; ++i) { const u32 lo = min(srt[i], x), hi = max(srt[i], x); srt[i] = lo; x = hi; }
     srt[k] = x;
   }
+}
+template <int FMAX>
+__device__ __forceinline__ u32 pick_finish(u32 v, const u32 (&cand)[FMAX], u32 (&tg)[FMAX]) {
   u32 nt = 0;
 #pragma unroll
   for (int k = 0; k < FMAX; ++k) tg[k] = NO_TARGET;
@@ -291,13 +286,11 @@ __device__ __forceinline__ u32 pick_targets(const TickParams& p, const StageView
 
 // What decides whether a node has anything to do this tick: its busy byte (pending work / host op) and the inbox
 // words of the previous tick (slot 0 kept, the other slots OR-ed).  13 bytes per node instead of 45.
-struct Pre { u32 busy, mL, mJ, mM, any, qw, row0, row1; };
+struct Pre { u32 busy, mL, mJ, mM, any, qw; };
 template <bool R1>
-__device__ __forceinline__ Pre prefetch_node(const TickParams& p, u32 vl, bool kL, bool kJ, bool kM, u64 pol_first, bool with_rows = false) {
+__device__ __forceinline__ Pre prefetch_node(const TickParams& p, u32 vl, bool kL, bool kJ, bool kM, u64 pol_first) {
   const u32 nl = p.stride, R = R1 ? 1u : p.R;
   Pre x;
-  x.row0 = x.row1 = 0;
-  if (with_rows) { x.row0 = __ldg(p.row_ptr + vl); x.row1 = __ldg(p.row_ptr + vl + 1); }   // saturated ticks: the warp stages its CSR span (bulk copy) as soon as these arrive
   x.busy = p.busy[vl];
   x.qw = p.qword[vl];                                   // slot-0 queue word (transmit budgets)
   SFS_COUNT(6, 4);
@@ -316,7 +309,7 @@ __device__ __forceinline__ Pre prefetch_node(const TickParams& p, u32 vl, bool k
 }
 
 // Returns true when the node still holds pending work (keeps its tile hot for the next tick).
-template <bool TRACE, int FMAX, bool SHARDED, bool R1, bool STAGED, bool WSTAGE = false>
+template <bool TRACE, int FMAX, bool SHARDED, bool R1, bool STAGED>
 __device__ __forceinline__ bool process_node(const TickParams& p, const StageView& sv, XStage* xs, const u32 vl, const Pre& pre, const bool kL, const bool kJ, const bool kM, const bool mark, const bool saturated,
                                              const u64 pol_first, const u64 pol_last, Counters& c) {
   static_assert(!STAGED || R1, "the staged path is the single-slot path");
@@ -337,8 +330,9 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   Words cur;
   auto load_state = [&]() {
     ns = STAGED ? sv.node[lt] : ld_u64_stream(p.node_state + vl, pol_first);
-    row0 = STAGED ? sv.rowptr[lt] : (WSTAGE ? pre.row0 : __ldg(p.row_ptr + vl));
-    row1 = STAGED ? sv.rowptr[lt + 1] : (WSTAGE ? pre.row1 : __ldg(p.row_ptr + vl + 1));
+    if (STAGED) { row0 = sv.rowptr[lt]; row1 = sv.rowptr[lt + 1]; }
+    else if (p.udeg) { row0 = vl * p.udeg; row1 = row0 + p.udeg; }     // uniform out-degree: the row offsets are arithmetic
+    else { row0 = __ldg(p.row_ptr + vl); row1 = __ldg(p.row_ptr + vl + 1); }
     if (STAGED) {
       const uint4 a = reinterpret_cast<const uint4*>(sv.rec + lt)[0], b = reinterpret_cast<const uint4*>(sv.rec + lt)[1];
       cur.w[0] = a.x; cur.w[1] = a.y; cur.w[2] = a.z; cur.w[3] = a.w; cur.w[4] = b.x; cur.w[5] = b.y; cur.w[6] = b.z; cur.w[7] = b.w;
@@ -380,7 +374,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
     u32 w[4];
     philox4x32_10(t, v, 0, DOMAIN_PROBE, p.seed_lo, p.seed_hi, w);
     const u32 e = row0 + (((w[0] & 0xffffu) * deg) >> 16);
-    ptarget = (STAGED && sv.col_staged) ? sv.col[e - sv.col_base] : __ldg(p.col + e);
+    ptarget = (STAGED && sv.col_staged) ? sv.col[e - sv.col_base] : SFS_LD_COL(p.col + e, pol_first);
     have_probe = true;
   }
 
@@ -487,8 +481,9 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
       const u32 mx = max(r.txl, max(r.txj, r.txm));
       if (mx) {
         if (!have_targets) {
-          if (WSTAGE && sv.col_staged) mbar_wait(sv.wbar, sv.wphase);       // the warp's CSR span has landed in shared memory
-          nt = pick_targets<FMAX, STAGED || WSTAGE>(p, sv, v, row0, deg, tg);
+          u32 cand[FMAX];
+          pick_issue<FMAX, STAGED>(p, sv, v, row0, deg, pol_first, cand);
+          nt = pick_finish<FMAX>(v, cand, tg);
           have_targets = true;
         }
         u32* const planeL = p.inbox_wr + (size_t)(KIND_LEAVE * R + s) * nl;
@@ -579,18 +574,7 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
   // node logic on dense blocks of 256 list entries: one chain per 256 ACTIVE nodes.  Nodes are independent within a
   // tick and every cross-node effect is a commutative reduction, so the visiting order changes nothing.
   constexpr u32 GROUP = SHARDED ? 4 : 8;
-  // One shared-memory region, two uses (a launch takes one path or the other): the active-node list of the compaction
-  // path, or — tile-by-tile walk of saturated ticks — one CSR stage per warp: the neighbour lists of the warp's 32 nodes are
-  // one contiguous span of `col`, bulk-copied (cp.async.bulk → UBLKCP, completion on the warp's own mbarrier) into shared
-  // memory by lane 0 as soon as the row offsets are known.  The four neighbour picks of a node then read shared memory
-  // instead of issuing four scattered 4-byte gathers: at out-degree 16 that is 16 L1 tag requests per warp less per pick
-  // instruction (the plateau tick is bound by the L1 request rate: 40 M RED + 20 M gather tags of 64 M per tick).
-  constexpr u32 WCAP = SHARDED ? 576 : 1024;               // CSR entries per warp stage (degree ≤ 16 / ≤ 32 on average); larger spans gather from global memory
-  constexpr u32 UBYTES = (GROUP * BLOCK * 16 > (BLOCK / 32) * WCAP * 4) ? GROUP * BLOCK * 16 : (BLOCK / 32) * WCAP * 4;
-  __shared__ __align__(128) unsigned char u_mem[UBYTES];
-  uint4* const act_s = reinterpret_cast<uint4*>(u_mem);    // x: tile-in-group << 8 | lane, busy << 16, any << 24; y, z, w: inbox words
-  u32* const wstage_s = reinterpret_cast<u32*>(u_mem);
-  __shared__ __align__(8) u64 wbar_s[BLOCK / 32];
+  __shared__ uint4 act_s[GROUP * BLOCK];                   // x: tile-in-group << 8 | lane, busy << 16, any << 24; y, z, w: inbox words
   __shared__ u32 act_n;
   __shared__ u8 pend_s[GROUP];
   __shared__ u16 gt_s[GROUP];
@@ -650,17 +634,9 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
   } else {
   // Walk the hot tiles of this CTA.  The 13 "is there anything to do" bytes of the NEXT hot tile (busy byte, inbox
   // words) are requested before the current tile is processed, so an idle tile costs no exposed round trip.
-  const bool wstage = saturated && p.wstage;             // uniform over the grid
-  if (wstage) {
-    if (lane == 0) mbar_init(&wbar_s[wid], 1);
-    fence_proxy_async();
-    __syncwarp();
-  }
-  u32 wphase = 0;
-  bool armed = false;
   auto prefetch_tile = [&](u32 ti) -> Pre {
     const u32 vn = ((tile0 + ti) << TILE_SHIFT) + threadIdx.x;
-    return vn < p.n_local ? prefetch_node<R1>(p, vn, kL, kJ, kM, pol_first, true) : Pre{};
+    return vn < p.n_local ? prefetch_node<R1>(p, vn, kL, kJ, kM, pol_first) : Pre{};
   };
   u32 i = 0;
   while (i < ntile && !hot_s[i]) ++i;
@@ -673,34 +649,11 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
     if (j < ntile) pre_next = prefetch_tile(j);
     const u32 vl = ((tile0 + i) << TILE_SHIFT) + threadIdx.x;
     bool pend = false;
-    StageView sv{};
-    if (wstage) {
-      // the warp's CSR span [s0, s1) (16-byte granules; `col` is padded) — worth staging when enough of its nodes hold queued transmits
-      const u32 s0 = __shfl_sync(0xffffffffu, pre.row0, 0) & ~3u;
-      const u32 s1 = (warp_max(pre.row1) + 3u) & ~3u;
-      const u32 senders = (u32)__popc(__ballot_sync(0xffffffffu, (pre.busy & 1u) != 0));
-      if (armed) { mbar_wait(&wbar_s[wid], wphase); wphase ^= 1u; armed = false; }      // the previous copy has landed (nobody may have waited for it)
-      if (senders >= 4 && s1 > s0 && s1 - s0 <= WCAP) {
-        __syncwarp();                                      // every lane is done reading the previous tile's span
-        if (lane == 0) {
-          fence_proxy_async();
-          mbar_arrive_expect_tx(&wbar_s[wid], (s1 - s0) * 4u);
-          bulk_g2s(wstage_s + wid * WCAP, p.col + s0, (s1 - s0) * 4u, &wbar_s[wid], pol_first);
-        }
-#ifdef SERFSIM_EMU
-        __syncwarp();                                      // host build: the copy is lane 0's memcpy and mbar_wait is a no-op — order it before the other lanes' reads
-#endif
-        armed = true;
-        sv.col = wstage_s + wid * WCAP; sv.col_base = s0; sv.col_staged = true; sv.wbar = &wbar_s[wid]; sv.wphase = wphase;
-        SFS_PROBE(3);
-      }
-    }
-    if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, R1, false, true>(p, sv, xs, vl, pre, kL, kJ, kM, mark, saturated, pol_first, pol_last, c);
+    if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, saturated, pol_first, pol_last, c);
     if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + i] = 1;
     if (SHARDED) wrote_remote |= flush_xwarp(p, xs, false);
     i = j;
   }
-  if (armed) mbar_wait(&wbar_s[wid], wphase);            // no bulk copy may be in flight into this CTA's shared memory when it exits
   }
   if (SHARDED) {
     wrote_remote |= flush_xwarp(p, xs, true);
@@ -1171,6 +1124,7 @@ __global__ void __launch_bounds__(BLOCK) summary_kernel(const uint4* rec, const 
 
 }  // namespace
 
+int tick_ctas_per_sm_r1() { return SFS_MB_R1; }
 int tick_grid_size(u32 n_local, int ctas_per_sm) {
   static int sms = 0;
   if (!sms) {
@@ -1180,7 +1134,9 @@ int tick_grid_size(u32 n_local, int ctas_per_sm) {
     if (sms <= 0) sms = 148;
   }
   const u32 tiles = (n_local + BLOCK - 1) / BLOCK;
-  u32 grid = (u32)sms * (u32)ctas_per_sm * 2;    // persistent: SM count × resident CTAs × 2 (two waves for balance)
+  static int mul = 0;
+  if (!mul) { const char* e = getenv("SERFSIM_GRIDMUL"); mul = e ? atoi(e) : 2; if (mul < 1) mul = 2; }
+  u32 grid = (u32)sms * (u32)ctas_per_sm * (u32)mul;    // persistent: SM count × resident CTAs × 2 (two waves for balance)
   if (tiles < grid) grid = tiles ? tiles : 1;
   while ((tiles + grid - 1) / grid > MAX_TILES_PER_CTA) grid += (u32)sms * (u32)ctas_per_sm;
   return (int)grid;
@@ -1214,8 +1170,8 @@ static void launch_tick_v(const TickParams& p, int grid, cudaStream_t st) {
 #endif
   static int mb5 = -1;
   if (mb5 < 0) { const char* e = getenv("SERFSIM_MINB"); mb5 = (e && atoi(e) == 5) ? 1 : 0; }
-  if (sharded) { if (r1) SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, true, true, 4>)(p); else SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, true, false, 3>)(p); }
-  else if (r1) { if (mb5) SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, false, true, 5>)(p); else SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, false, true, 4>)(p); }
+  if (sharded) { if (r1) SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, true, true, SFS_MB_R1>)(p); else SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, true, false, 3>)(p); }
+  else if (r1) { if (mb5) SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, false, true, 5>)(p); else SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, false, true, SFS_MB_R1>)(p); }
   else SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, false, false, 3>)(p);
 }
 void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st) {

@@ -102,7 +102,7 @@ struct TickParams {
   UeTable ue_table; uint4* ue_state; const uint4* ue_snap; const uint4* const* ue_snap_peer; const u32* ue_ltime; u64* ue_totals;
   u32 compact;                // 1: unsaturated ticks gather their active nodes across several tiles (SERFSIM_COMPACT=0 switches it off)
   Gate gate;
-  u32 wstage;                 // 1: saturated ticks stage each warp's CSR span in shared memory with a bulk copy (SERFSIM_WSTAGE=0 switches it off)
+  u32 udeg;                   // > 0: every node of the shard has this out-degree (row v starts at v·udeg): row offsets are not loaded and senders draw their peers early
 };
 
 // Control block of a rank (one allocation, mapped into every peer): per exchange parity the entry counts and epoch flags
@@ -151,6 +151,7 @@ void launch_compose_records(const uint4* rec, const u32* qword, u32 n_local, u32
 void launch_state_hash(const uint4* rec, const u32* qword, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 n_global, u32 R, u64* out, cudaStream_t st);
 void launch_summary(const uint4* rec, const u32* qword, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 R, const u32* subj_dev, u64* out /*[2 + 2*R + 2]*/, cudaStream_t st);
 int tick_grid_size(u32 n_local, int ctas_per_sm);
+int tick_ctas_per_sm_r1();
 void launch_compute_watch(const u32* row_ptr, const u32* col, const u32* subj_dev, u32 R, u32 first, u32 n_local, u16* watch, cudaStream_t st);
 void launch_apply_watch(const u16* watch, u32 n_local, u8* busy, u8* hot0, u8* hot1, cudaStream_t st);
 

@@ -80,19 +80,25 @@ def small_world_churn(n=1_000_000, k=16, beta=0.1, churn_frac=0.05, slots=8, win
                     dict(fanout=fanout, seed=seed), max_ticks=20000)
 
 
-def dissemination_storm(n=10_000_000, degree=16, fanout=4, slots=1, seed=1, graph_seed=7, waves=1, spacing=8):
+def dissemination_storm(n=10_000_000, degree=16, fanout=4, slots=1, seed=1, graph_seed=7, waves=1, spacing=8, with_fail=False):
     """configs[3] on one GPU / sharded: 10 M-node random graph, fanout 4.  Every tracked subject leaves at tick
     0; with `waves` > 1 further force-leave / join operations follow every `spacing` ticks so the gossip front
-    never drains (sustained activity for throughput measurements)."""
+    never drains (sustained activity for throughput measurements).
+    with_fail=True is SURVEY §8d item 4 verbatim — "one leave-intent + one fail at tick 0": the last tracked subject crashes
+    instead of leaving, so the run also carries the SWIM probe → suspect (Lifeguard confirmations) → suspicion timeout →
+    dead → Failed cycle with the memberlist LAN timers (three dissemination waves and a timer wait instead of one wave)."""
     subjects = (np.arange(slots, dtype=np.uint64) * np.uint64(max(1, n // max(1, slots))) + np.uint64(3)).astype(np.uint32)
     ops = [(0, Op.LEAVE, int(subjects[s]), 0) for s in range(slots)]
+    if with_fail:
+        assert slots >= 2, "leave + fail needs two tracked subjects"
+        ops[-1] = (0, Op.FAIL, int(subjects[-1]), 0)
     for w in range(1, waves):
         for s in range(slots):
             origin = int((int(subjects[s]) + 1 + 7919 * w) % n)
             if origin in set(int(x) for x in subjects):
                 origin = (origin + 1) % n
             ops.append((w * spacing, Op.FORCE_LEAVE, origin, s))
-    return Scenario(f"storm_{n}_d{degree}_f{fanout}_r{slots}_w{waves}", n, slots, random_regular_graph(n, degree, graph_seed), subjects, ops,
+    return Scenario(f"storm_{n}_d{degree}_f{fanout}_r{slots}_w{waves}" + ("_fail" if with_fail else ""), n, slots, random_regular_graph(n, degree, graph_seed), subjects, ops,
                     dict(fanout=fanout, seed=seed), max_ticks=4000)
 
 

@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class MemberStatus(enum.IntEnum):      # types/member.rs:54-58
@@ -137,6 +137,8 @@ PRODUCT_ONLY = {
     "serfsim_last_error": (C.c_char_p, []),
     "serfsim_shard_range": (C.c_int, [_vp, C.POINTER(_u32), C.POINTER(_u32)]),
     "serfsim_set_event_cb": (C.c_int, [_vp, EVENT_CB, _vp]),
+    "serfsim_results_async": (C.c_int, [_vp, _u32, _vp, _vp, _vp]),
+    "serfsim_results_wait": (C.c_int, [_vp]),
     "serfsim_last_step_device_ms": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(_u64)]),
     "serfsim_set_tick_timing": (C.c_int, [_vp, C.c_int]),
     "serfsim_tick_times": (C.c_int, [_vp, _u32, _u32, _vp]),
@@ -290,6 +292,15 @@ class GossipSim:
     def lamport_time(self, out=None): return self._get("lamport_time", np.uint64, None, out)
     def status_ltime_u32(self, slot=0, out=None): return self._get("status_ltime_u32", np.uint32, slot, out)       # same values, half the bytes
     def lamport_time_u32(self, out=None): return self._get("lamport_time_u32", np.uint32, None, out)
+    def results_async(self, slot=0, status=None, status_ltime=None, lamport=None):
+        """Queue the read-back of the step's result vectors into caller-owned (pinned) numpy arrays; returns the bytes queued."""
+        ptr = lambda a: a.ctypes.data if a is not None else None
+        self._check(self._lib.serfsim_results_async(self._h, int(slot), ptr(status), ptr(status_ltime), ptr(lamport)))
+        return sum(a.nbytes for a in (status, status_ltime, lamport) if a is not None)
+
+    def results_wait(self):
+        self._check(self._lib.serfsim_results_wait(self._h))
+
     def incarnation(self, slot=0): return self._get("incarnation", np.uint32, slot)
     def ml_state(self, slot=0): return self._get("ml_state", np.uint8, slot)
     def records(self, slot=0): return self._get("records", RECORD_DTYPE, slot)

@@ -45,7 +45,7 @@ def test_struct_layouts_match_header():
 
 def test_create_fails_loudly_without_gpu():
     lib = sim.load_library()
-    assert lib.serfsim_abi_version() == sim.ABI_VERSION == 3
+    assert lib.serfsim_abi_version() == sim.ABI_VERSION == 4
     import torch
     if torch.cuda.is_available():
         pytest.skip("GPU present: covered by the gpu tests")

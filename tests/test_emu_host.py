@@ -180,3 +180,23 @@ def test_multi_phase_production_mode_rewind(monkeypatch, seed, chunk):
         sim.inject(t + 3, Op.FORCE_LEAVE, 7, 0)
     assert g.run_until_converged(5000) == o.run_until_converged(5000)
     assert_same(g, o, sc.slots, with_hash=False)
+
+
+def test_results_async_returns_the_getters_values():
+    """serfsim_results_async / _wait (ABI v4): the three result vectors of a slot through the staging ring, several calls in
+    flight (more than the ring holds), partial requests (NULL pointers)."""
+    sc = scenarios.random_graph_leave(3000, 12, 3, seed=2, slots=3)
+    g = sc.build(emu_sim, trace=0)
+    g.run_until_converged(sc.max_ticks)
+    bufs = []
+    for rep in range(2):
+        for s in range(3):
+            st, lt, ck = np.zeros(g.count, np.uint8), np.zeros(g.count, np.uint32), np.zeros(g.count, np.uint32)
+            n = g.results_async(s, status=st, status_ltime=lt, lamport=ck if s == 0 else None)
+            assert n == g.count * (1 + 4 + (4 if s == 0 else 0))
+            bufs.append((s, st, lt, ck))
+    g.results_wait()
+    for s, st, lt, ck in bufs:
+        assert (st == g.member_status(s)).all() and (lt == g.status_ltime_u32(s)).all()
+        if s == 0:
+            assert (ck == g.lamport_time_u32()).all()

@@ -17,11 +17,14 @@ ap.add_argument("--degree", type=int, default=16)
 ap.add_argument("--waves", type=int, default=1)
 ap.add_argument("--runs", type=int, default=2)
 ap.add_argument("--out", default=None)
-ap.add_argument("--scenario", default="storm", choices=["storm", "churn"])
+ap.add_argument("--scenario", default="storm", choices=["storm", "storm_fail", "churn"])
 a = ap.parse_args()
 if a.scenario == "churn":      # BASELINE configs[2]: small-world graph, 5 % of the nodes fail / rejoin, 8 tracked subjects
     sc = scenarios.small_world_churn(a.nodes, a.degree, 0.1, 0.05, slots=a.slots, window=200, seed=1, fanout=a.fanout)
     extra = dict(suspicion_mult=2, suspicion_max_timeout_mult=2, probe_interval_ticks=2)
+elif a.scenario == "storm_fail":   # bench.py's default workload: one subject leaves, one crashes
+    sc = scenarios.dissemination_storm(a.nodes, a.degree, a.fanout, slots=max(2, a.slots), seed=1, waves=a.waves, with_fail=True)
+    extra = {}
 else:
     sc = scenarios.dissemination_storm(a.nodes, a.degree, a.fanout, slots=a.slots, seed=1, waves=a.waves)
     extra = {}
