@@ -90,6 +90,9 @@ struct serfsim {
   const uint4** d_peer_snap_rec = nullptr;   // sharded push-pull: device arrays of every rank's snapshot pointers
   const u64** d_peer_snap_node = nullptr;
   u8* d_hot[2] = {nullptr, nullptr};      // [n_tiles] per tick parity
+  u8* d_hot_static = nullptr;             // [n_tiles] tiles that hold a watcher (never consumed)
+  u32* d_tile_due = nullptr;              // [n_tiles] earliest suspicion deadline of a tile's nodes (the timer wheel)
+  u32* d_sched = nullptr;                 // scheduler words (tick_kernel.cuh: SCHED_*)
   u32 n_tiles = 0;
   u32* d_rowptr = nullptr;         // [count+1]
   u32* d_col = nullptr;
@@ -280,6 +283,9 @@ int launch_ticks(serfsim* h, u32 n) {
     p.force_all = (h->cfg.trace != 0) || h->no_skip || p.reap_now;
     p.compact = h->compact ? 1u : 0u;
     p.udeg = h->udeg;
+    p.tile_due = h->d_tile_due; p.hot_static = h->d_hot_static; p.sched = h->d_sched;
+    p.sleep_on = (h->no_skip || h->byz_on) ? 0u : 1u;          // injectors send every tick: the cluster never sleeps
+    p.pp_every = (u32)std::max(0, h->cfg.push_pull_interval_ticks); p.reap_every = h->cfg.reap_interval_ticks;
     const u32 xpar = h->xepoch & 1;
     p.world = (u32)h->cfg.world_size; p.rank = (u32)h->cfg.rank; p.shard_size = h->shard_size; p.win_cap = h->win_cap;
     p.win_data = h->d_peer_data[xpar]; p.send_count = h->d_send_count;
@@ -312,7 +318,7 @@ int launch_ticks(serfsim* h, u32 n) {
       u.table = h->ue_table; u.state = h->d_ue_state; u.inbox_rd = h->d_ue_inbox[(t & 1) ^ 1]; u.inbox_wr = h->d_ue_inbox[t & 1];
       u.ltime = h->d_ue_ltime; u.node_state = h->d_node; u.busy = h->d_busy; u.row_ptr = h->d_rowptr; u.col = h->d_col;
       u.ev_node = h->d_ev_node; u.ev_op = h->d_ev_op; u.ev_slot = h->d_ev_slot;
-      u.row = p.row; u.totals = h->d_ue_totals; u.overflow = h->d_overflow;
+      u.row = p.row; u.totals = h->d_ue_totals; u.overflow = h->d_overflow; u.sched = h->d_sched;
       u.world = (u32)h->cfg.world_size; u.rank = (u32)h->cfg.rank; u.shard_size = h->shard_size; u.win_cap = h->win_cap;
       u.win_data = h->d_peer_data[h->xepoch & 1]; u.send_count = h->d_send_count;
       u.gate = gate; u.gate.evaluate = 1u;
@@ -486,7 +492,8 @@ int refresh_watchers(serfsim* h) {
     launch_compute_watch(h->d_rowptr, h->d_col, h->d_subj, h->R, h->first, h->count, h->d_watch, h->stream);
     h->watch_dirty = false;
   }
-  launch_apply_watch(h->d_watch, h->count, h->d_busy, h->d_hot[0], h->d_hot[1], h->stream);
+  CU(cudaMemsetAsync(h->d_hot_static, 0, h->n_tiles, h->stream));
+  launch_apply_watch(h->d_watch, h->count, h->d_busy, h->d_hot_static, h->stream);
   CU(cudaGetLastError());
   return 0;
 }
@@ -516,6 +523,8 @@ int do_reset(serfsim* h, u64 seed) {
   CU(cudaMemsetAsync(h->d_qword, 0, (size_t)h->R * h->stride * 4, h->stream));
   CU(cudaMemsetAsync(h->d_hot[0], 0, h->n_tiles, h->stream));
   CU(cudaMemsetAsync(h->d_hot[1], 0, h->n_tiles, h->stream));
+  CU(cudaMemsetAsync(h->d_tile_due, 0xff, (size_t)h->n_tiles * sizeof(u32), h->stream));      // no timer runs
+  CU(cudaMemsetAsync(h->d_sched, 0, SCHED_WORDS * sizeof(u32), h->stream));
   if (h->d_trace) {
     CU(cudaMemsetAsync(h->d_trace, 0, (size_t)h->trace_cap * 8 * sizeof(u64), h->stream));
     CU(cudaMemsetAsync(h->d_kinds, 0, ((size_t)h->trace_cap + 1) * 4 * sizeof(u32), h->stream));
@@ -533,6 +542,7 @@ int do_reset(serfsim* h, u64 seed) {
 void free_all(serfsim* h) {
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   for (cudaEvent_t e : h->tick_ev) cudaEventDestroy(e);
+  cudaFree(h->d_hot_static); cudaFree(h->d_tile_due); cudaFree(h->d_sched);
   cudaFree(h->d_hot[0]); cudaFree(h->d_hot[1]); cudaFree(h->d_busy); cudaFree(h->d_watch); cudaFree(h->d_snap_rec); cudaFree(h->d_snap_node); cudaFree(h->d_peer_snap_rec); cudaFree(h->d_peer_snap_node);
   cudaFree(h->d_qword);
   cudaFree(h->d_rec); cudaFree(h->d_inbox[0]); cudaFree(h->d_inbox[1]); cudaFree(h->d_node); cudaFree(h->d_rowptr); cudaFree(h->d_col);
@@ -642,6 +652,8 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
   CUB(cudaMalloc(&h->d_watch, (size_t)h->stride * 2));
   CUB(cudaMemset(h->d_watch, 0, (size_t)h->stride * 2));
   CUB(cudaMalloc(&h->d_hot[0], h->n_tiles)); CUB(cudaMalloc(&h->d_hot[1], h->n_tiles));
+  CUB(cudaMalloc(&h->d_hot_static, h->n_tiles)); CUB(cudaMalloc(&h->d_tile_due, (size_t)h->n_tiles * sizeof(u32))); CUB(cudaMalloc(&h->d_sched, SCHED_WORDS * sizeof(u32)));
+  CUB(cudaMemset(h->d_hot_static, 0, h->n_tiles));
   CUB(cudaMalloc(&h->d_overflow, 4)); CUB(cudaMalloc(&h->d_subj, MAX_SLOTS * 4)); CUB(cudaMalloc(&h->d_scratch, 64 * 8));
   CUB(cudaMalloc(&h->d_stage, (size_t)h->count * 8));
   CUB(cudaMalloc(&h->d_runctl, 2 * sizeof(u32)));

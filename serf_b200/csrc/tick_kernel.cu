@@ -132,6 +132,8 @@ struct StageView {
 
 struct Counters {          // per-thread, reduced once per CTA; rare counters (events, suspects) go straight to the trace row
   u32 packets, edges, changed, pending, kL, kJ, kM;
+  u32 awake;               // nodes that stay awake (the scheduler's "can the next tick do anything" input)
+  int dsusp;               // net change of the number of Suspect views at up nodes (persistent counter, tick_kernel.cuh)
   u64 hash;
 };
 
@@ -284,9 +286,12 @@ __device__ __forceinline__ u32 pick_finish(u32 v, const u32 (&cand)[FMAX], u32 (
   return nt;
 }
 
-// What decides whether a node has anything to do this tick: its busy byte (pending work / host op) and the inbox
-// words of the previous tick (slot 0 kept, the other slots OR-ed).  13 bytes per node instead of 45.
-struct Pre { u32 busy, mL, mJ, mM, any, qw; };
+// What decides whether a node has anything to do this tick: its busy byte and the inbox words of the previous tick
+// (slot 0 kept; per slot one "has mail" bit), plus — multi-slot runs — one "has queued transmits" bit per slot from the
+// queue words.  13 bytes per node instead of 45 (single slot).
+// busy byte: bit 0 awake (queued transmits / probe duty), bit 1 host operation this tick, bit 2 watcher (static),
+// bit 3 some view of the node runs a suspicion timer (it sleeps until its tile comes due, tick_kernel.cuh).
+struct Pre { u32 busy, mL, mJ, mM, any, qw, mailmask, qmask; };
 template <bool R1>
 __device__ __forceinline__ Pre prefetch_node(const TickParams& p, u32 vl, bool kL, bool kJ, bool kM, u64 pol_first) {
   const u32 nl = p.stride, R = R1 ? 1u : p.R;
@@ -298,20 +303,34 @@ __device__ __forceinline__ Pre prefetch_node(const TickParams& p, u32 vl, bool k
   x.mJ = kJ ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R) * nl + vl, pol_first) : 0u;
   x.mM = kM ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R) * nl + vl, pol_first) : 0u;
   x.any = x.mL | x.mJ | x.mM;
+  x.mailmask = x.any ? 1u : 0u;
+  x.qmask = x.qw ? 1u : 0u;
   if (!R1) {
     for (u32 s2 = 1; s2 < R; ++s2) {
-      if (kL) x.any |= ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R + s2) * nl + vl, pol_first);
-      if (kJ) x.any |= ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R + s2) * nl + vl, pol_first);
-      if (kM) x.any |= ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R + s2) * nl + vl, pol_first);
+      u32 m = 0;
+      if (kL) m |= ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R + s2) * nl + vl, pol_first);
+      if (kJ) m |= ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R + s2) * nl + vl, pol_first);
+      if (kM) m |= ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R + s2) * nl + vl, pol_first);
+      x.any |= m;
+      x.mailmask |= (m ? 1u : 0u) << s2;
+      x.qmask |= (p.qword[(size_t)s2 * nl + vl] ? 1u : 0u) << s2;
+      SFS_COUNT(6, 4);
     }
   }
   return x;
 }
+// Has the node anything to do this tick?  (due: its tile's earliest suspicion deadline has been reached.)
+__device__ __forceinline__ bool node_active(const TickParams& p, const Pre& x, bool due) {
+  return (x.busy & 7u) != 0 || x.any != 0 || p.reap_now != 0 || (due && (x.busy & 8u));
+}
 
-// Returns true when the node still holds pending work (keeps its tile hot for the next tick).
+// Returns true when the node stays awake (queued transmits, probe duty): that keeps its tile hot for the next tick.
+// A view whose only business is a running suspicion timer does not: its deadline goes to `mind` (the caller registers the
+// minimum in tile_due) and the view sleeps until its tile comes due.  `due`: this tile's earliest deadline has been reached —
+// every node of it that carries a timer (busy bit 3) visits all its views.
 template <bool TRACE, int FMAX, bool SHARDED, bool R1, bool STAGED>
 __device__ __forceinline__ bool process_node(const TickParams& p, const StageView& sv, XStage* xs, const u32 vl, const Pre& pre, const bool kL, const bool kJ, const bool kM, const bool mark, const bool saturated,
-                                             const u64 pol_first, const u64 pol_last, Counters& c) {
+                                             const bool due, const u64 pol_first, const u64 pol_last, Counters& c, u32& mind) {
   static_assert(!STAGED || R1, "the staged path is the single-slot path");
   const u32 lt = threadIdx.x;              // index inside the staged tile
   const u32 v = p.first + vl;
@@ -322,17 +341,19 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
 
   // ---- loads.  Saturated ticks (the previous tick delivered to at least half of the nodes): everything a node
   // needs is requested up front, independent loads in flight together.  Otherwise most nodes are idle: read only
-  // the busy byte (pending work / host op) and the inbox words, and fetch the 8-byte node word and the 32-byte
-  // record just for the nodes that have something to do. ----
-  const bool upfront = saturated || TRACE || STAGED;
+  // the busy byte and the inbox words, and fetch the 8-byte node word and the 32-byte record just for the nodes
+  // that have something to do.  Multi-slot runs fetch the records of the views that have something to do. ----
+  const bool upfront = R1 && (saturated || TRACE || STAGED);
   u64 ns = 0;
   u32 row0 = 0, row1 = 0;
   Words cur;
-  auto load_state = [&]() {
+  auto load_node = [&]() {
     ns = STAGED ? sv.node[lt] : ld_u64_stream(p.node_state + vl, pol_first);
     if (STAGED) { row0 = sv.rowptr[lt]; row1 = sv.rowptr[lt + 1]; }
     else if (p.udeg) { row0 = vl * p.udeg; row1 = row0 + p.udeg; }     // uniform out-degree: the row offsets are arithmetic
     else { row0 = __ldg(p.row_ptr + vl); row1 = __ldg(p.row_ptr + vl + 1); }
+  };
+  auto load_rec0 = [&]() {
     if (STAGED) {
       const uint4 a = reinterpret_cast<const uint4*>(sv.rec + lt)[0], b = reinterpret_cast<const uint4*>(sv.rec + lt)[1];
       cur.w[0] = a.x; cur.w[1] = a.y; cur.w[2] = a.z; cur.w[3] = a.w; cur.w[4] = b.x; cur.w[5] = b.y; cur.w[6] = b.z; cur.w[7] = b.w;
@@ -341,15 +362,17 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
     }
     merge_q(cur, pre.qw);                                  // the record image everything below works on is record | budgets
   };
-  if (upfront) load_state();
+  if (upfront) { load_node(); load_rec0(); }
   const u32 busy = pre.busy;
   u32 mL = pre.mL, mJ = pre.mJ, mM = pre.mM;
   if (STAGED) { mL = kL ? sv.inL[lt] : 0u; mJ = kJ ? sv.inJ[lt] : 0u; mM = kM ? sv.inM[lt] : 0u; }
 
-  // ---- idle exit: nothing received (any slot), nothing queued, no timer, no host operation, no probe duty ----
-  if (!TRACE && !STAGED && busy == 0 && !pre.any && !p.reap_now) return false;
+  // ---- idle exit: nothing received (any slot), nothing queued, no host operation, no probe duty, no timer due ----
+  const bool timers_due = due && (busy & 8u);
+  if (!TRACE && !STAGED && !node_active(p, pre, due)) return false;
+  if (STAGED && !TRACE && !((busy & 7u) || (mL | mJ | mM) || p.reap_now || timers_due)) return false;
   const u32 wmask = (busy & 4) ? (u32)p.watch[vl] : 0u;     // subjects this node can probe (it has them as neighbours)
-  if (!upfront) load_state();
+  if (!upfront) { load_node(); if (R1) load_rec0(); }
 
   u32 clock = (u32)ns;
   const bool up_r = (ns & NS_UP) != 0;
@@ -382,26 +405,39 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   u32 nt = 0;
   bool have_targets = false;
   u32 max_tx = 0;
-  bool any_pending = false;
+  bool awake = false, has_timer = false;
 
-  // multi-slot runs: the record and inbox words of slot s+1 are requested while slot s is being processed
+  // Views to visit: all of them when the node as a whole has business (trace, reaper round, host operation, timers due);
+  // otherwise those with mail, queued transmits or probe duty (a watcher's view of a subject that is down).
+  const u32 all_views = (R >= 32u) ? 0xffffffffu : ((1u << R) - 1u);
+  const bool visit_all = R1 || TRACE || p.reap_now || (busy & 2u) || timers_due || !p.sleep_on;
+  u32 todo = visit_all ? all_views : ((pre.mailmask | pre.qmask | (p.probe_every ? (wmask & p.down_mask) : 0u)) & all_views);
+  if (!R1) SFS_COUNT(5, R - (u32)__popc(todo));             // views left asleep by a visited node
+
+  // multi-slot runs: the record and inbox words of the next view to visit are requested while the current one is processed
   Words nxt = {};
   u32 nL = 0, nJ = 0, nM = 0, nq = 0;
+  auto load_view = [&](u32 s2, Words& w, u32& q, u32& iL, u32& iJ, u32& iM) {
+    const size_t idn = (size_t)s2 * nl + vl;
+    w = ld_rec256(p.rec + 2 * idn, pol_first);
+    if (s2 == 0) { q = pre.qw; iL = pre.mL; iJ = pre.mJ; iM = pre.mM; return; }
+    q = p.qword[idn];
+    SFS_COUNT(6, 4);
+    iL = kL ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R + s2) * nl + vl, pol_first) : 0;
+    iJ = kJ ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R + s2) * nl + vl, pol_first) : 0;
+    iM = kM ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R + s2) * nl + vl, pol_first) : 0;
+  };
+  u32 s = R;
+  if (R1) { s = 0; todo = 0; }
+  else if (todo) {
+    s = (u32)__ffs((int)todo) - 1u; todo &= todo - 1u;
+    u32 q0; load_view(s, cur, q0, mL, mJ, mM); merge_q(cur, q0);
+  }
 #pragma unroll 1
-  for (u32 s = 0; s < R; ++s) {
+  while (s < R) {
     const size_t idx = (size_t)s * nl + vl;
-    if (!R1) {
-      if (s) { cur = nxt; merge_q(cur, nq); mL = nL; mJ = nJ; mM = nM; }
-      if (s + 1 < R) {
-        const size_t idn = idx + nl;
-        nxt = ld_rec256(p.rec + 2 * idn, pol_first);
-        nq = p.qword[idn];
-        SFS_COUNT(6, 4);
-        nL = kL ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R + s + 1) * nl + vl, pol_first) : 0;
-        nJ = kJ ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R + s + 1) * nl + vl, pol_first) : 0;
-        nM = kM ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R + s + 1) * nl + vl, pol_first) : 0;
-      }
-    }
+    u32 s_next = R;
+    if (!R1 && todo) { s_next = (u32)__ffs((int)todo) - 1u; todo &= todo - 1u; load_view(s_next, nxt, nq, nL, nJ, nM); }
     if (mL) st_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R + s) * nl + vl, 0u, pol_first);   // consume: clear for reuse in two ticks
     if (mJ) st_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R + s) * nl + vl, 0u, pol_first);
     if (mM) st_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R + s) * nl + vl, 0u, pol_first);
@@ -409,6 +445,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
     Rec r;
     unpack_words(cur, r);
     const bool self = (p.subj[s] == v);
+    const bool susp_before = up_r && r.mlstate == ML_SUSPECT;
 
     // ---------------- Phase R ----------------
     if (up_r && (mL | mJ | mM)) {
@@ -506,11 +543,19 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
       if (self && sstate == SS_LEAVING && r.txl == 0 && r.mlstate == ML_ALIVE) {
         r.mlstate = ML_LEFT; r.qfrom = 0; r.txm = limit; sstate = SS_LEFT;
       }
-      const bool pend = (r.txl | r.txj | r.txm) || r.mlstate == ML_SUSPECT ||
-                        (p.probe_every && ((p.down_mask >> s) & 1) && !self && ((wmask >> s) & 1) && r.mlstate == ML_ALIVE);   // a watcher that has not noticed yet
-      c.pending += pend ? 1 : 0;
-      any_pending |= pend;
+      // The trace's `pending` counts the views with queued transmits, a running suspicion timer, or a watcher that has not
+      // noticed yet.  Suspect views are counted by the persistent counter (they sleep), the others here.  A watcher's view of
+      // a down subject stays awake while it is Alive or Suspect: its own failed probe may still start or confirm the suspicion.
+      const bool queued = (r.txl | r.txj | r.txm) != 0;
+      const bool watching = p.probe_every && ((p.down_mask >> s) & 1) && !self && ((wmask >> s) & 1);
+      const bool suspect = r.mlstate == ML_SUSPECT;
+      c.pending += (!suspect && (queued || (watching && r.mlstate == ML_ALIVE))) ? 1 : 0;
+      // (its own failed probe is a confirmation only while its bucket is not in the confirmer set and the set is not full)
+      const bool can_confirm = suspect && (u32)__popc(r.mask) - 1u < p.rules.k && !(r.mask & (1u << from_bucket(v)));
+      awake |= queued || (watching && (r.mlstate == ML_ALIVE || can_confirm));
+      if (suspect && r.deadline != 0) { has_timer = true; mind = min(mind, r.deadline); }
     }
+    c.dsusp += ((up_s && r.mlstate == ML_SUSPECT) ? 1 : 0) - (susp_before ? 1 : 0);
     pack_words(r, cur);
     {
       Words o2 = orig, c2 = cur;                           // storage image: record without budgets, budgets in the queue word
@@ -520,20 +565,124 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
     }
     if (TRACE) c.hash += rec_hash((u64)s * p.n_global + v, make_uint4(cur.w[0], cur.w[1], cur.w[2], cur.w[3]), make_uint4(cur.w[4], cur.w[5], cur.w[6], cur.w[7]));
     if (r.inc >= INC_LIMIT) *p.overflow = 1;
+    if (!R1) { cur = nxt; merge_q(cur, nq); mL = nL; mJ = nJ; mM = nM; }
+    s = s_next;
   }
   const u64 ns2 = (u64)clock | (up_s ? NS_UP : 0) | ((u64)sstate << 40);
   if (ns2 != ns) st_u64_stream(p.node_state + vl, ns2, pol_first);
   if (TRACE) c.hash += node_hash((u64)R * p.n_global + v, ns2);
   if (clock >= LTIME_LIMIT) *p.overflow = 1;
   c.packets += min(nt, max_tx);
-  const u32 busy2 = (any_pending ? 1u : 0u) | (busy & 4u);   // the op bit is consumed, the watcher bit is static
+  // busy byte: the op bit is consumed, the watcher bit is static; the timer bit is exact after a visit of every view and
+  // sticky otherwise (a view that was not visited may run a timer: it is found when its tile comes due)
+  const u32 busy2 = (awake ? 1u : 0u) | (busy & 4u) | ((has_timer || (!visit_all && (busy & 8u))) ? 8u : 0u);
   if (busy2 != busy) p.busy[vl] = (u8)busy2;
-  return any_pending || (busy & 4u);                        // watchers keep their tile hot
+  c.awake += awake ? 1 : 0;
+  return awake;
+}
+
+__device__ __forceinline__ u32 warp_min(u32 v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// A skipped tick (tick_is_idle): nothing can happen, so the only trace it leaves is its row — nothing delivered, nothing
+// changed, `pending` = the sleeping Suspect views, and (trace runs) the state hash of the previous tick.
+template <bool TRACE>
+__device__ __forceinline__ void write_idle_row(const TickParams& p) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    SFS_PROBE(3);                                          // skipped ticks
+    p.row[4] += *reinterpret_cast<const u64*>(p.sched + SCHED_SUSPECTS);
+    if (TRACE && p.tick > 0) p.row[7] = *(p.row - 8 + 7);
+  }
+}
+
+// Scan of the CTA's tile flags.  hot_s[i]: bit 0 = process the tile, bit 1 = its earliest suspicion deadline has been reached
+// (the entry is reset here, by the tile's owner, before any of its nodes runs: the timers that are still running re-register).
+__device__ __forceinline__ void scan_tiles(const TickParams& p, u8* hot_s, u32 tile0, u32 ntile, bool all_hot) {
+  for (u32 i = threadIdx.x; i < ntile; i += BLOCK) {
+    const u8 f = p.hot_rd[tile0 + i];
+    if (f) p.hot_rd[tile0 + i] = 0;                      // consumed; this parity is written again two ticks from now
+    const bool due = p.tile_due[tile0 + i] <= p.tick;
+    if (due) { p.tile_due[tile0 + i] = NO_DEADLINE; SFS_PROBE(4); }     // tiles woken by the timer wheel
+    hot_s[i] = (u8)(((f || all_hot || due || p.hot_static[tile0 + i]) ? 1u : 0u) | (due ? 2u : 0u));
+  }
+}
+
+// End of a tick: block reduction of the counters (warp shuffles, then shared memory) → one atomic per counter per CTA; the
+// LAST CTA to finish (ticket) completes the row and decides how long the cluster can sleep.
+// trace row: 0 packets, 1 edge_updates, 2 messages, 3 changed, 4 pending, (5 events, 6 suspects: direct), 7 hash
+template <bool TRACE>
+__device__ __forceinline__ void finish_tick(const TickParams& p, const Counters& c, u64 (*red)[BLOCK / 32]) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __shared__ u32 last_s, due_min_s[BLOCK / 32];
+  const u64 vals[8] = {c.packets, c.edges, (u64)c.kL + c.kJ + c.kM, c.changed, c.pending, c.kL, c.kJ, c.kM};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const u32 s = warp_sum((u32)vals[i]);
+    if (lane == 0) red[i][wid] = s;
+  }
+  u64 hs = 0;
+  if (TRACE) hs = warp_sum64(c.hash);
+  const u32 aw = warp_sum(c.awake);
+  const u32 ds = warp_sum((u32)c.dsusp);                  // two's complement: the sum of the lanes' signed changes
+  if (lane == 0) {
+    if (aw) atomicAdd(p.sched + SCHED_AWAKE, aw);
+    if (ds) atomicAdd(reinterpret_cast<unsigned long long*>(p.sched + SCHED_SUSPECTS), (unsigned long long)(long long)(int)ds);
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    u64 s = 0;
+#pragma unroll
+    for (int w = 0; w < BLOCK / 32; ++w) s += red[threadIdx.x][w];
+    if (s) {
+      if (threadIdx.x < 5) atomicAdd((unsigned long long*)(p.row + threadIdx.x), (unsigned long long)s);
+      else atomicAdd(p.kinds_cur + (threadIdx.x - 5), (u32)min(s, (u64)0xffffffffu));
+    }
+  }
+  if (TRACE && lane == 0 && hs) atomicAdd((unsigned long long*)(p.row + 7), (unsigned long long)hs);
+  // ---- ticket: every CTA's counters are in the row before the last one reads it ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last_s = (atomicAdd(p.sched + SCHED_TICKET, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!last_s) return;
+  __threadfence();
+  volatile u32* sched = p.sched;
+  volatile u64* row = p.row;
+  const u64 suspects = *reinterpret_cast<volatile u64*>(p.sched + SCHED_SUSPECTS);
+  // Can the next ticks do anything?  Not if nothing was sent (no mail), nobody stays awake (no queued transmit, no probe duty),
+  // the user-event kernel reported nothing queued or sent (with injectors sleep_on is off): then the cluster sleeps until the earliest
+  // suspicion deadline or the next anti-entropy / reaper round (host operations are checked at launch).  Sharded runs never
+  // skip (the ranks would have to agree on the deadline).
+  const bool quiet = p.sleep_on && p.world == 1 && row[1] == 0 && row[2] == 0 && sched[SCHED_AWAKE] == 0 && sched[SCHED_UE_ACTIVITY] == 0;
+  u32 until = p.tick + 1;
+  if (quiet) {                                             // uniform over the CTA
+    u32 m = NO_DEADLINE;
+    for (u32 i = threadIdx.x; i < p.n_tiles; i += BLOCK) m = min(m, __ldcg(p.tile_due + i));
+    m = warp_min(m);
+    if (lane == 0) due_min_s[wid] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 0; w < BLOCK / 32; ++w) m = min(m, due_min_s[w]);
+      // a round runs in tick u when (u + 1) % period == 0; the first such u > tick:
+      if (p.pp_every) m = min(m, ((p.tick + 1) / p.pp_every + 1) * p.pp_every - 1);
+      if (p.reap_every) m = min(m, ((p.tick + 1) / p.reap_every + 1) * p.reap_every - 1);
+      until = max(m, p.tick + 1);
+    }
+  }
+  if (threadIdx.x == 0) {
+    row[4] = row[4] + suspects;                            // pending = awake views counted above + sleeping Suspect views
+    sched[SCHED_IDLE_UNTIL] = until;
+    sched[SCHED_AWAKE] = 0; sched[SCHED_UE_ACTIVITY] = 0; sched[SCHED_TICKET] = 0;
+  }
 }
 
 // Persistent CTAs; each owns a contiguous range of 256-node tiles.  A tile is processed only if it is
-// "hot": somebody delivered into it during the previous tick, it kept pending work (queued transmits,
-// suspicion timers), or a host operation targets it — otherwise not a single byte of it is touched.
+// "hot": somebody delivered into it during the previous tick, it holds a node that stays awake (queued transmits,
+// probe duty), a host operation targets it, or a suspicion timer of one of its nodes has come due — otherwise not a
+// single byte of it is touched.
 template <bool TRACE, int FMAX, bool SHARDED, bool R1, int MB>
 __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__ TickParams p) {
   __shared__ u8 hot_s[MAX_TILES_PER_CTA];
@@ -541,10 +690,11 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
   __shared__ __align__(16) unsigned char xs_mem[SHARDED ? sizeof(XStage) : 16];
   XStage* xs = reinterpret_cast<XStage*>(xs_mem);
   if (gate_closed(p.gate, blockIdx.x == 0 && threadIdx.x == 0)) return;   // the run is over (uniform over the grid): this tick does not exist
+  if (tick_is_idle(p.sched, p.tick, p.ev_begin, p.ev_end)) { write_idle_row<TRACE>(p); return; }   // nothing can happen in this tick (uniform)
   Counters c = {};
   const bool kL = p.kinds_prev[KIND_LEAVE] != 0, kJ = p.kinds_prev[KIND_JOIN] != 0, kM = p.kinds_prev[KIND_ML] != 0;
   const u64 pol_first = policy_evict_first(), pol_last = policy_evict_last();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   if (SHARDED && threadIdx.x < (BLOCK / 32) * MAX_WORLD) xs->cnt[threadIdx.x / MAX_WORLD][threadIdx.x % MAX_WORLD] = 0;
   bool wrote_remote = false;
 
@@ -561,11 +711,7 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
 
   const u32 tile0 = blockIdx.x * p.tiles_per_cta;
   const u32 ntile = tile0 < p.n_tiles ? min(p.tiles_per_cta, p.n_tiles - tile0) : 0;
-  for (u32 i = threadIdx.x; i < ntile; i += BLOCK) {
-    const u8 f = p.hot_rd[tile0 + i];
-    if (f) p.hot_rd[tile0 + i] = 0;                      // consumed; this parity is written again two ticks from now
-    hot_s[i] = (f || all_hot) ? 1 : 0;
-  }
+  scan_tiles(p, hot_s, tile0, ntile, all_hot);
   __syncthreads();
   // Unsaturated ticks (ramp-up and tail of a dissemination: a few per cent of the nodes have anything to do, spread
   // one or two per warp): a tile-by-tile walk pays one chain of dependent round trips (state → row → peers) per TILE
@@ -599,7 +745,7 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
       }
 #pragma unroll
       for (u32 g = 0; g < GROUP; ++g) {
-        const bool act = g < ng && (pr[g].busy != 0 || pr[g].any != 0);
+        const bool act = g < ng && node_active(p, pr[g], (hot_s[gt_s[g]] & 2u) != 0);   // lanes past n_local hold an empty Pre
         const u32 bal = __ballot_sync(0xffffffffu, act);
         if (bal) {
           u32 base = 0;
@@ -617,13 +763,21 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
         if (e < na) {
           const uint4 a = act_s[e];
           const u32 g = (a.x >> 8) & 0xffu;
+          const u32 ti = gt_s[g];
+          const u32 vl = ((tile0 + ti) << TILE_SHIFT) + (a.x & 0xffu);
           Pre pre;
-          pre.busy = (a.x >> 16) & 0xffu; pre.any = (a.x >> 24) & 1u; pre.mL = a.y; pre.mJ = a.z; pre.mM = a.w;
-          const u32 vl = ((tile0 + gt_s[g]) << TILE_SHIFT) + (a.x & 0xffu);
-          pre.qw = p.qword[vl];                               // not carried through the list: issued here, in flight with the state loads
-          SFS_COUNT(6, 4);
-          const bool pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, false, pol_first, pol_last, c);
+          if (R1) {
+            pre.busy = (a.x >> 16) & 0xffu; pre.any = (a.x >> 24) & 1u; pre.mL = a.y; pre.mJ = a.z; pre.mM = a.w;
+            pre.qw = p.qword[vl];                             // not carried through the list: issued here, in flight with the state loads
+            pre.mailmask = pre.any ? 1u : 0u; pre.qmask = pre.qw ? 1u : 0u;
+            SFS_COUNT(6, 4);
+          } else {
+            pre = prefetch_node<R1>(p, vl, kL, kJ, kM, pol_first);   // per-view masks are not carried through the list: the few active nodes read them again
+          }
+          u32 mind = NO_DEADLINE;
+          const bool pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, false, (hot_s[ti] & 2u) != 0, pol_first, pol_last, c, mind);
           if (mark && pend) pend_s[g] = 1;
+          if (mind != NO_DEADLINE) atomicMin(p.tile_due + tile0 + ti, mind);
         }
         if (SHARDED) wrote_remote |= flush_xwarp(p, xs, false);
       }
@@ -649,8 +803,13 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
     if (j < ntile) pre_next = prefetch_tile(j);
     const u32 vl = ((tile0 + i) << TILE_SHIFT) + threadIdx.x;
     bool pend = false;
-    if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, saturated, pol_first, pol_last, c);
+    u32 mind = NO_DEADLINE;
+    if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, saturated, (hot_s[i] & 2u) != 0, pol_first, pol_last, c, mind);
     if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + i] = 1;
+    if (__any_sync(0xffffffffu, mind != NO_DEADLINE)) {      // running timers of this warp's nodes: one registration per warp
+      const u32 wm = warp_min(mind);
+      if (lane == 0) atomicMin(p.tile_due + tile0 + i, wm);
+    }
     if (SHARDED) wrote_remote |= flush_xwarp(p, xs, false);
     i = j;
   }
@@ -659,27 +818,7 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
     wrote_remote |= flush_xwarp(p, xs, true);
     if (wrote_remote) __threadfence_system();            // peer-window stores are performed before the publish kernel raises the flags
   }
-  // block reduction (warp shuffles, then shared memory) → one atomic per counter per CTA.
-  // trace row: 0 packets, 1 edge_updates, 2 messages, 3 changed, 4 pending, (5 events, 6 suspects: direct), 7 hash
-  const u64 vals[8] = {c.packets, c.edges, (u64)c.kL + c.kJ + c.kM, c.changed, c.pending, c.kL, c.kJ, c.kM};
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const u32 s = warp_sum((u32)vals[i]);
-    if (lane == 0) red[i][wid] = s;
-  }
-  u64 hs = 0;
-  if (TRACE) hs = warp_sum64(c.hash);
-  __syncthreads();
-  if (threadIdx.x < 8) {
-    u64 s = 0;
-#pragma unroll
-    for (int w = 0; w < BLOCK / 32; ++w) s += red[threadIdx.x][w];
-    if (s) {
-      if (threadIdx.x < 5) atomicAdd((unsigned long long*)(p.row + threadIdx.x), (unsigned long long)s);
-      else atomicAdd(p.kinds_cur + (threadIdx.x - 5), (u32)min(s, (u64)0xffffffffu));
-    }
-  }
-  if (TRACE && lane == 0 && hs) atomicAdd((unsigned long long*)(p.row + 7), (unsigned long long)hs);
+  finish_tick<TRACE>(p, c, red);
 }
 
 #ifndef SERFSIM_EMU   // the TMA pipeline is device-only (bulk copies, mbarriers); the host build of tests/emu uses the direct-load kernel
@@ -698,10 +837,11 @@ __global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constan
   __shared__ __align__(8) u64 full_bar[2], empty_bar[2];
   __shared__ u32 col_base_s[2], col_ok_s[2];
   if (gate_closed(p.gate, blockIdx.x == 0 && threadIdx.x == 0)) return;
+  if (tick_is_idle(p.sched, p.tick, p.ev_begin, p.ev_end)) { write_idle_row<TRACE>(p); return; }
   Counters c = {};
   const bool kL = p.kinds_prev[KIND_LEAVE] != 0, kJ = p.kinds_prev[KIND_JOIN] != 0, kM = p.kinds_prev[KIND_ML] != 0;
   const u64 pol_first = policy_evict_first(), pol_last = policy_evict_last();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
 
   const u32 prev_msgs = p.kinds_prev[KIND_LEAVE] + p.kinds_prev[KIND_JOIN] + p.kinds_prev[KIND_ML];
   const bool dense_now = prev_msgs >= (p.n_tiles >> 1) + 1;
@@ -711,11 +851,7 @@ __global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constan
 
   const u32 tile0 = blockIdx.x * p.tiles_per_cta;
   const u32 ntile = tile0 < p.n_tiles ? min(p.tiles_per_cta, p.n_tiles - tile0) : 0;
-  for (u32 i = threadIdx.x; i < ntile; i += BLOCK) {
-    const u8 f = p.hot_rd[tile0 + i];
-    if (f) p.hot_rd[tile0 + i] = 0;
-    hot_s[i] = (f || all_hot) ? 1 : 0;
-  }
+  scan_tiles(p, hot_s, tile0, ntile, all_hot);
   if (threadIdx.x == 0) {
     mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1);
     mbar_init(&empty_bar[0], BLOCK / 32); mbar_init(&empty_bar[1], BLOCK / 32);     // one arrival per consumer warp
@@ -773,36 +909,23 @@ __global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constan
     const u32 ti = hot_list[j];
     const u32 vl = ((tile0 + ti) << TILE_SHIFT) + threadIdx.x;
     bool pend = false;
+    u32 mind = NO_DEADLINE;
     if (vl < p.n_local) {
       Pre pre = {};
       pre.busy = p.busy[vl];
       pre.qw = p.qword[vl];          // 4 B per node, read directly (not worth a sixth bulk copy per stage)
-      pend = process_node<TRACE, FMAX, false, true, true>(p, sv, nullptr, vl, pre, kL, kJ, kM, mark, true, pol_first, pol_last, c);
+      pend = process_node<TRACE, FMAX, false, true, true>(p, sv, nullptr, vl, pre, kL, kJ, kM, mark, true, (hot_s[ti] & 2u) != 0, pol_first, pol_last, c, mind);
     }
     if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + ti] = 1;
+    if (__any_sync(0xffffffffu, mind != NO_DEADLINE)) {
+      const u32 wm = warp_min(mind);
+      if (lane == 0) atomicMin(p.tile_due + tile0 + ti, wm);
+    }
     if (BARSYNC) __syncthreads();
     else { __syncwarp(); if (lane == 0) mbar_arrive(&empty_bar[st]); }     // this warp is done reading stage `st`
   }
 
-  const u64 vals[8] = {c.packets, c.edges, (u64)c.kL + c.kJ + c.kM, c.changed, c.pending, c.kL, c.kJ, c.kM};
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const u32 s = warp_sum((u32)vals[i]);
-    if (lane == 0) red[i][wid] = s;
-  }
-  u64 hs = 0;
-  if (TRACE) hs = warp_sum64(c.hash);
-  __syncthreads();
-  if (threadIdx.x < 8) {
-    u64 s = 0;
-#pragma unroll
-    for (int w = 0; w < BLOCK / 32; ++w) s += red[threadIdx.x][w];
-    if (s) {
-      if (threadIdx.x < 5) atomicAdd((unsigned long long*)(p.row + threadIdx.x), (unsigned long long)s);
-      else atomicAdd(p.kinds_cur + (threadIdx.x - 5), (u32)min(s, (u64)0xffffffffu));
-    }
-  }
-  if (TRACE && lane == 0 && hs) atomicAdd((unsigned long long*)(p.row + 7), (unsigned long long)hs);
+  finish_tick<TRACE>(p, c, red);
 }
 #endif
 
@@ -815,7 +938,9 @@ __global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constan
 template <bool TRACE>
 __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__ TickParams p, const uint4* __restrict__ snap_rec, const u64* __restrict__ snap_node) {
   if (p.gate.ctl && p.gate.ctl[0]) return;
-  long long d_changed = 0, d_pending = 0;
+  // a round can queue transmits and start timers after the tick kernel has decided how long the cluster may sleep: take the decision back
+  if (blockIdx.x == 0 && threadIdx.x == 0) p.sched[SCHED_IDLE_UNTIL] = 0;
+  long long d_changed = 0, d_pending = 0, d_susp = 0;
   u64 d_hash = 0;
   for (u32 vl = blockIdx.x * BLOCK + threadIdx.x; vl < p.n_local; vl += gridDim.x * BLOCK) {
     const u32 v = p.first + vl;
@@ -846,7 +971,8 @@ __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__
     const u32 sstate = (u32)(ns >> 40) & 3;
     const u32 cu = (u32)nu;
     if (cu > 0) witness(clock, cu - 1);
-    bool any_pending = false;
+    bool awake = false, has_timer = false;
+    u32 mind = NO_DEADLINE;
     const u32 wmask = p.watch[vl];
     for (u32 s = 0; s < p.R; ++s) {
       const size_t iv = (size_t)s * p.stride + vl, iu = (size_t)s * part_stride + ul;
@@ -880,9 +1006,13 @@ __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__
       }
       if ((a1.y ^ a0.y) | (a1.z ^ a0.z) | (a1.w ^ a0.w) | (b1.x ^ b0.x) | (b1.y ^ b0.y) | (b1.z ^ b0.z) | (b1.w ^ b0.w)) d_changed++;   // status_time creep is not a change
       if (TRACE && ch) d_hash += rec_hash((u64)s * p.n_global + v, a1, b1) - rec_hash((u64)s * p.n_global + v, a0, b0);
-      const bool now = (r.txl | r.txj | r.txm) || r.mlstate == ML_SUSPECT || (p.probe_every && ((p.down_mask >> s) & 1) && !self && ((wmask >> s) & 1) && r.mlstate == ML_ALIVE);
+      const bool watching = p.probe_every && ((p.down_mask >> s) & 1) && !self && ((wmask >> s) & 1);
+      const bool now = (r.txl | r.txj | r.txm) || r.mlstate == ML_SUSPECT || (watching && r.mlstate == ML_ALIVE);
       d_pending += (now ? 1 : 0) - (was ? 1 : 0);
-      any_pending |= now;
+      d_susp += (r.mlstate == ML_SUSPECT ? 1 : 0) - (((b0.z >> 8) & 3u) == ML_SUSPECT ? 1 : 0);     // the node is up: counted views
+      awake |= (r.txl | r.txj | r.txm) != 0 || (watching && (r.mlstate == ML_ALIVE ||
+               (r.mlstate == ML_SUSPECT && (u32)__popc(r.mask) - 1u < p.rules.k && !(r.mask & (1u << from_bucket(v))))));
+      if (r.mlstate == ML_SUSPECT && r.deadline != 0) { has_timer = true; mind = min(mind, r.deadline); }
       if (r.inc >= INC_LIMIT) *p.overflow = 1;
     }
     if (p.ue_table.n) {                                        // the partner's event clock and ring (a snapshot, like its records)
@@ -907,12 +1037,16 @@ __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__
       if (TRACE) d_hash += node_hash((u64)p.R * p.n_global + v, ns2) - node_hash((u64)p.R * p.n_global + v, ns);
     }
     if (clock >= LTIME_LIMIT) *p.overflow = 1;
-    if (any_pending) { p.busy[vl] = (u8)(1u | (wmask ? 4u : 0u)); p.hot_wr[vl >> TILE_SHIFT] = 1; }
+    // every view of the node was visited: its busy byte is exact (bit 0 awake, bit 2 watcher, bit 3 running timer)
+    p.busy[vl] = (u8)((awake ? 1u : 0u) | (wmask ? 4u : 0u) | (has_timer ? 8u : 0u));
+    if (awake) p.hot_wr[vl >> TILE_SHIFT] = 1;
+    if (has_timer) atomicMin(p.tile_due + (vl >> TILE_SHIFT), mind);
   }
-  const u64 c = warp_sum64((u64)d_changed), q = warp_sum64((u64)d_pending), h = TRACE ? warp_sum64(d_hash) : 0;
+  const u64 c = warp_sum64((u64)d_changed), q = warp_sum64((u64)d_pending), ds = warp_sum64((u64)d_susp), h = TRACE ? warp_sum64(d_hash) : 0;
   if ((threadIdx.x & 31) == 0) {
     if (c) atomicAdd((unsigned long long*)(p.row + 3), (unsigned long long)c);
     if (q) atomicAdd((unsigned long long*)(p.row + 4), (unsigned long long)q);
+    if (ds) atomicAdd(reinterpret_cast<unsigned long long*>(p.sched + SCHED_SUSPECTS), (unsigned long long)ds);
     if (TRACE && h) atomicAdd((unsigned long long*)(p.row + 7), (unsigned long long)h);
   }
 }
@@ -1010,11 +1144,11 @@ __global__ void compute_watch_kernel(const u32* __restrict__ row_ptr, const u32*
   }
   watch[vl] = (u16)m;
 }
-__global__ void apply_watch_kernel(const u16* __restrict__ watch, u32 n_local, u8* busy, u8* hot0, u8* hot1) {
+__global__ void apply_watch_kernel(const u16* __restrict__ watch, u32 n_local, u8* busy, u8* hot_static) {
   const u32 vl = blockIdx.x * blockDim.x + threadIdx.x;
   if (vl >= n_local || watch[vl] == 0) return;
   busy[vl] |= 4;
-  hot0[vl >> TILE_SHIFT] = 1; hot1[vl >> TILE_SHIFT] = 1;
+  hot_static[vl >> TILE_SHIFT] = 1;              // a watcher's tile is scheduled every tick (static flags: never consumed)
 }
 
 __global__ void init_state_kernel(uint4* rec, u64* node_state, u32 n_local, u32 stride, u32 R, u32 init_st, u32 init_clock) {
@@ -1186,8 +1320,8 @@ void launch_pushpull(const TickParams& p, const uint4* snap_rec, const u64* snap
 void launch_compute_watch(const u32* row_ptr, const u32* col, const u32* subj_dev, u32 R, u32 first, u32 n_local, u16* watch, cudaStream_t st) {
   SFS_LAUNCH((n_local + 255) / 256, 256, 0, st, compute_watch_kernel)(row_ptr, col, subj_dev, R, first, n_local, watch);
 }
-void launch_apply_watch(const u16* watch, u32 n_local, u8* busy, u8* hot0, u8* hot1, cudaStream_t st) {
-  SFS_LAUNCH((n_local + 255) / 256, 256, 0, st, apply_watch_kernel)(watch, n_local, busy, hot0, hot1);
+void launch_apply_watch(const u16* watch, u32 n_local, u8* busy, u8* hot_static, cudaStream_t st) {
+  SFS_LAUNCH((n_local + 255) / 256, 256, 0, st, apply_watch_kernel)(watch, n_local, busy, hot_static);
 }
 void launch_drain(const DrainParams& p, cudaStream_t st) { SFS_LAUNCH(SFS_SMS * 8, BLOCK, 0, st, drain_kernel)(p); }
 void launch_publish(const PublishParams& p, cudaStream_t st) { SFS_LAUNCH(1, 32, 0, st, publish_kernel)(p); }

@@ -103,7 +103,24 @@ struct TickParams {
   u32 compact;                // 1: unsaturated ticks gather their active nodes across several tiles (SERFSIM_COMPACT=0 switches it off)
   Gate gate;
   u32 udeg;                   // > 0: every node of the shard has this out-degree (row v starts at v·udeg): row offsets are not loaded and senders draw their peers early
+  // Sleeping views (the suspicion timer wheel).  A view whose only business is a running suspicion timer is not visited tick after
+  // tick: its deadline is registered in tile_due (a lower bound of the earliest deadline of the tile's 256 nodes, reset and
+  // re-registered whenever it comes due), its node carries busy bit 3, and the number of such views lives in a persistent counter
+  // instead of being recounted every tick.  Ticks in which provably nothing can happen (no mail, no queued transmit, no probe
+  // duty, no timer due, no host operation, no anti-entropy / reaper round) return at once (sched[SCHED_IDLE_UNTIL]).
+  u32* tile_due;              // [n_tiles]
+  const u8* hot_static;       // [n_tiles] tiles that hold a watcher (static; never consumed)
+  u32* sched;                 // scheduler words (SCHED_*), u64 suspect-view counter at sched + SCHED_SUSPECTS
+  u32 sleep_on;               // 0: SERFSIM_NO_SKIP — every tile, every view, every tick
+  u32 pp_every, reap_every;   // push-pull / reaper periods in ticks (0 = off): such ticks are never skipped
 };
+constexpr u32 SCHED_TICKET = 0, SCHED_IDLE_UNTIL = 1, SCHED_UE_ACTIVITY = 2, SCHED_AWAKE = 3, SCHED_SUSPECTS = 4 /* u64 */, SCHED_WORDS = 8;
+constexpr u32 NO_DEADLINE = 0xffffffffu;
+// A tick is skipped (grid-uniform decision of its first instruction) when the last executed tick proved that nothing can happen
+// before SCHED_IDLE_UNTIL and the host scheduled no operation for it.
+__device__ __forceinline__ bool tick_is_idle(const u32* sched, u32 tick, u32 ev_begin, u32 ev_end) {
+  return sched && ev_begin == ev_end && tick < sched[SCHED_IDLE_UNTIL];
+}
 
 // Control block of a rank (one allocation, mapped into every peer): per exchange parity the entry counts and epoch flags
 // the peers write, then the peers' trace rows of that tick (the device-side sum of the per-tick counters).
@@ -153,7 +170,7 @@ void launch_summary(const uint4* rec, const u32* qword, const u64* node_state, u
 int tick_grid_size(u32 n_local, int ctas_per_sm);
 int tick_ctas_per_sm_r1();
 void launch_compute_watch(const u32* row_ptr, const u32* col, const u32* subj_dev, u32 R, u32 first, u32 n_local, u16* watch, cudaStream_t st);
-void launch_apply_watch(const u16* watch, u32 n_local, u8* busy, u8* hot0, u8* hot1, cudaStream_t st);
+void launch_apply_watch(const u16* watch, u32 n_local, u8* busy, u8* hot_static, cudaStream_t st);
 
 // User-event tick (uevent_kernel.cu; rules in uevent.cuh)
 struct UeParams {
@@ -171,6 +188,7 @@ struct UeParams {
   u64* row;                   // this tick's trace row (shared with the membership kernel)
   u64* totals;                // run totals: 0 messages, 1 edges, 2 delivered, 3 duplicates, 4 too_old
   u32* overflow;
+  u32* sched;                 // scheduler words of the membership kernel (idle-tick skipping): this kernel reports its activity there
   Gate gate;                  // the user-event kernel is the first kernel of a tick when user events are on
   // sharded runs: a target outside [first, first + n_local) gets one window entry per event (kind 3) over NVLink
   u32 world, rank, shard_size, win_cap;

@@ -28,6 +28,7 @@ __device__ __forceinline__ u64 ue_warp_sum64(u64 v) {
 template <bool TRACE>
 __global__ void __launch_bounds__(UE_BLOCK) uevent_kernel(const __grid_constant__ UeParams p) {
   if (gate_closed(p.gate, blockIdx.x == 0 && threadIdx.x == 0)) return;   // the run is over: this tick does not exist
+  if (tick_is_idle(p.sched, p.tick, p.ev_begin, p.ev_end)) return;          // nothing can happen in this tick (the membership kernel writes its row)
   UeCounts c = {};
   u32 changed = 0;
   u64 hash = 0;
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(UE_BLOCK) uevent_kernel(const __grid_constant_
     if (s_msgs) { atomicAdd((ull*)(p.row + 2), (ull)s_msgs); atomicAdd((ull*)(p.totals + 0), (ull)s_msgs); }
     if (s_chg) atomicAdd((ull*)(p.row + 3), (ull)s_chg);
     if (s_pend) atomicAdd((ull*)(p.row + 4), (ull)s_pend);
+    if (s_pend | s_msgs) atomicAdd(p.sched + SCHED_UE_ACTIVITY, 1u);      // queued or sent events: the next tick cannot be skipped
     if (s_deliv) atomicAdd((ull*)(p.totals + 2), (ull)s_deliv);
     if (s_dup) atomicAdd((ull*)(p.totals + 3), (ull)s_dup);
     if (s_old) atomicAdd((ull*)(p.totals + 4), (ull)s_old);

@@ -139,3 +139,34 @@ def oracle_sim(n_nodes, slots=1, **cfg_kw):
         f = getattr(L, "oracle_sim_" + name)
         f.restype, f.argtypes = res, args
     return _sim.GossipSim(n_nodes, slots, _lib=L, _prefix="oracle_sim_", _errfn="oracle_last_error", **cfg_kw)
+
+
+def physical_cpus():
+    """One logical CPU per physical core this process may use, alternating between packages (NUMA nodes)."""
+    allowed = sorted(os.sched_getaffinity(0))
+    by_pkg = {}
+    for c in allowed:
+        try:
+            core = int(open(f"/sys/devices/system/cpu/cpu{c}/topology/core_id").read())
+            pkg = int(open(f"/sys/devices/system/cpu/cpu{c}/topology/physical_package_id").read())
+        except (OSError, ValueError):
+            core, pkg = c, 0
+        by_pkg.setdefault(pkg, {}).setdefault(core, c)
+    lists = [list(v.values()) for _, v in sorted(by_pkg.items())]
+    out = []
+    for i in range(max(len(x) for x in lists)):
+        out += [x[i] for x in lists if i < len(x)]
+    return out
+
+
+def oracle_sim_threaded(n_nodes, slots=1, **cfg_kw):
+    """oracle_sim with one pinned worker per physical core (results do not depend on the thread count): the checker of the
+    full-size parity tests, where a single-threaded run would take minutes."""
+    o = oracle_sim(n_nodes, slots, **cfg_kw)
+    L = lib()
+    L.oracle_sim_set_threads.restype, L.oracle_sim_set_threads.argtypes = C.c_int, [C.c_void_p, C.c_int]
+    L.oracle_sim_set_affinity.restype, L.oracle_sim_set_affinity.argtypes = C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int]
+    cpus = physical_cpus()
+    assert L.oracle_sim_set_threads(o._h, len(cpus)) == 0
+    assert L.oracle_sim_set_affinity(o._h, (C.c_int * len(cpus))(*cpus), len(cpus)) == 0
+    return o

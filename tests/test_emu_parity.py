@@ -98,6 +98,36 @@ def test_compaction_path_is_taken_and_exact():
     assert_same(f, o, sc.slots, with_hash=False)
 
 
+def test_sleeping_views_timer_wheel_and_idle_ticks():
+    """A crash with the memberlist LAN timers: the suspicion timers run for ~100 ticks in which nothing else happens.  Views that
+    only wait for their timer sleep (SFS_PROBE 5 counts the views a visited node left asleep), their tiles are woken by the
+    timer wheel (probe 4) and the ticks in which nothing can happen are skipped (probe 3) — with every trace row, `pending`
+    included, the records and the clocks still equal to the oracle's, which visits every view in every tick."""
+    import ctypes as C
+    from emu_lib import lib
+    L = lib()
+    L.emu_probe.restype = C.c_ulong
+    sc = scenarios.dissemination_storm(3000, 12, 3, slots=2, seed=3, with_fail=True)
+    o = sc.build(oracle_sim, trace=1)
+    to = o.run_until_converged(sc.max_ticks)
+    assert to[0] > 60
+    for trace in (0, 1):
+        L.emu_probe_reset()
+        f = sc.build(emu_sim, trace=trace)
+        assert f.run_until_converged(sc.max_ticks) == to
+        assert L.emu_probe(3) > 20 and L.emu_probe(4) > 0, (L.emu_probe(3), L.emu_probe(4))
+        if not trace:
+            assert L.emu_probe(5) > 0
+        assert_same(f, o, sc.slots, with_hash=bool(trace))
+    # stepping one tick at a time takes the same decisions (the scheduler words live on the device, not in the call)
+    f = sc.build(emu_sim, trace=1)
+    for _ in range(to[0] + 1):
+        f.step(1)
+    o2 = sc.build(oracle_sim, trace=1)
+    o2.step(to[0] + 1)
+    assert_same(f, o2, sc.slots)
+
+
 def test_config1_shape_100k_nodes():
     """BASELINE configs[1] at full size (100 K-node random graph, fan-out 3) through the host-compiled kernels:
     391 tiles over 4 CTAs, dense and sparse ticks, production mode (trace off)."""
