@@ -102,7 +102,8 @@ struct serfsim {
   u32* d_kinds = nullptr;          // [trace_cap+1][4]; row t+1 = messages by kind sent in tick t
   u32* d_ones = nullptr;           // [4] non-zero (multi-GPU: never skip an inbox plane)
   u32 trace_cap = 0;
-  u32* d_overflow = nullptr;
+  u32* d_overflow = nullptr;       // device address of pin_overflow (mapped pinned host memory: written by kernels on the rare error paths, read by the host without a copy)
+  u32* pin_overflow = nullptr;
   u32* d_subj = nullptr;
   u64* d_scratch = nullptr;        // summary / hash output
   void* d_stage = nullptr;         // getter staging, count × 8 B
@@ -139,7 +140,8 @@ struct serfsim {
   std::vector<serfsim_tick_row_t> rows;   // rows pulled from the device so far (global sums when sharded)
   // device-side convergence gate (tick_kernel.cuh: Gate)
   u32* d_runctl = nullptr;         // [0] done flag, [1] first quiescent tick
-  u32* pin_ctl = nullptr;          // pinned host copy, read once per chunk
+  u32* pin_ctl = nullptr;          // the verdict in mapped pinned host memory (written by the gate's leader thread), read once per chunk
+  u32* d_pin_ctl = nullptr;        // its device address
   u64* d_grow = nullptr;           // sharded runs: [trace_cap][8] global trace rows, summed on the device by the drain kernel
   bool gate_on = false;
   u32 gate_first = 0;              // first tick of the current run_until_converged call (it always runs)
@@ -286,12 +288,13 @@ int launch_ticks(serfsim* h, u32 n) {
     p.tile_due = h->d_tile_due; p.hot_static = h->d_hot_static; p.sched = h->d_sched;
     p.sleep_on = (h->no_skip || h->byz_on) ? 0u : 1u;          // injectors send every tick: the cluster never sleeps
     p.pp_every = (u32)std::max(0, h->cfg.push_pull_interval_ticks); p.reap_every = h->cfg.reap_interval_ticks;
+    p.host_idle_until = h->d_pin_ctl + 2;
     const u32 xpar = h->xepoch & 1;
     p.world = (u32)h->cfg.world_size; p.rank = (u32)h->cfg.rank; p.shard_size = h->shard_size; p.win_cap = h->win_cap;
     p.win_data = h->d_peer_data[xpar]; p.send_count = h->d_send_count;
     Gate gate{};                                   // convergence gate: the first kernel of the tick evaluates the row of tick t-1
     if (h->gate_on) {
-      gate.ctl = h->d_runctl; gate.prev_row = t > h->gate_first ? grow + (size_t)(t - 1) * 8 : nullptr; gate.tick = t;
+      gate.ctl = h->d_runctl; gate.host_ctl = h->d_pin_ctl; gate.prev_row = t > h->gate_first ? grow + (size_t)(t - 1) * 8 : nullptr; gate.tick = t;
       gate.future_ops = (t > 0 && future_ops(h, t - 1)) ? 1u : 0u;
       gate.pp = (u32)std::max(0, h->cfg.push_pull_interval_ticks); gate.byz_on = h->byz_on ? 1u : 0u;
     }
@@ -443,8 +446,8 @@ int check_overflow(serfsim* h) {
           return fail(SERFSIM_E_INVAL, "user events: two tracked events share a ring slot with different Lamport times (not supported in cluster runs)");
       }
   }
-  u32 ov = 0;
-  CU(cudaMemcpy(&ov, h->d_overflow, 4, cudaMemcpyDeviceToHost));
+  CU(cudaStreamSynchronize(h->stream));
+  const u32 ov = *(volatile u32*)h->pin_overflow;
   if (ov == 1) return fail(SERFSIM_E_OVERFLOW, "a Lamport time or incarnation left the 32-bit device range");
   if (ov == 2) return fail(SERFSIM_E_COMM, "cross-shard window overflow (raise SERFSIM_WIN_FACTOR)");
   if (ov) return fail(SERFSIM_E_COMM, "corrupt cross-shard window entry");
@@ -518,7 +521,9 @@ int do_reset(serfsim* h, u64 seed) {
   launch_init_state(h->d_rec, h->d_node, h->count, h->stride, h->R, h->cfg.init_status_ltime, h->cfg.init_clock, h->stream);
   CU(cudaMemsetAsync(h->d_inbox[0], 0, inbox_bytes, h->stream));
   CU(cudaMemsetAsync(h->d_inbox[1], 0, inbox_bytes, h->stream));
-  CU(cudaMemsetAsync(h->d_overflow, 0, 4, h->stream));
+  CU(cudaStreamSynchronize(h->stream));                   // no kernel of an earlier run is still writing the error word
+  *(volatile u32*)h->pin_overflow = 0;
+  ((volatile u32*)h->pin_ctl)[2] = 0;                     // the scheduler's "sleep until" word (mirrors d_sched, cleared below)
   CU(cudaMemsetAsync(h->d_busy, 0, h->stride, h->stream));
   CU(cudaMemsetAsync(h->d_qword, 0, (size_t)h->R * h->stride * 4, h->stream));
   CU(cudaMemsetAsync(h->d_hot[0], 0, h->n_tiles, h->stream));
@@ -547,7 +552,8 @@ void free_all(serfsim* h) {
   cudaFree(h->d_qword);
   cudaFree(h->d_rec); cudaFree(h->d_inbox[0]); cudaFree(h->d_inbox[1]); cudaFree(h->d_node); cudaFree(h->d_rowptr); cudaFree(h->d_col);
   cudaFree(h->d_ev_node); cudaFree(h->d_ev_op); cudaFree(h->d_ev_slot); cudaFree(h->d_trace); cudaFree(h->d_kinds); cudaFree(h->d_ones);
-  cudaFree(h->d_overflow); cudaFree(h->d_subj); cudaFree(h->d_scratch); cudaFree(h->d_stage);
+  if (h->pin_overflow) cudaFreeHost(h->pin_overflow);
+  cudaFree(h->d_subj); cudaFree(h->d_scratch); cudaFree(h->d_stage);
   cudaFree(h->d_byz_ids); cudaFree(h->d_anomaly); cudaFree(h->d_byz_totals); cudaFree(h->d_peer_anomaly);
   cudaFree(h->d_ue_snap); cudaFree(h->d_peer_ue_snap);
   cudaFree(h->d_ue_state); cudaFree(h->d_ue_inbox[0]); cudaFree(h->d_ue_inbox[1]); cudaFree(h->d_ue_ltime); cudaFree(h->d_ue_totals);
@@ -654,11 +660,16 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
   CUB(cudaMalloc(&h->d_hot[0], h->n_tiles)); CUB(cudaMalloc(&h->d_hot[1], h->n_tiles));
   CUB(cudaMalloc(&h->d_hot_static, h->n_tiles)); CUB(cudaMalloc(&h->d_tile_due, (size_t)h->n_tiles * sizeof(u32))); CUB(cudaMalloc(&h->d_sched, SCHED_WORDS * sizeof(u32)));
   CUB(cudaMemset(h->d_hot_static, 0, h->n_tiles));
-  CUB(cudaMalloc(&h->d_overflow, 4)); CUB(cudaMalloc(&h->d_subj, MAX_SLOTS * 4)); CUB(cudaMalloc(&h->d_scratch, 64 * 8));
+  CUB(cudaHostAlloc(&h->pin_overflow, sizeof(u32), cudaHostAllocMapped));
+  CUB(cudaHostGetDevicePointer(&h->d_overflow, h->pin_overflow, 0));
+  *h->pin_overflow = 0;
+  CUB(cudaMalloc(&h->d_subj, MAX_SLOTS * 4)); CUB(cudaMalloc(&h->d_scratch, 64 * 8));
   CUB(cudaMalloc(&h->d_stage, (size_t)h->count * 8));
   CUB(cudaMalloc(&h->d_runctl, 2 * sizeof(u32)));
   CUB(cudaMemset(h->d_runctl, 0, 2 * sizeof(u32)));
-  CUB(cudaMallocHost(&h->pin_ctl, 2 * sizeof(u32)));
+  CUB(cudaHostAlloc(&h->pin_ctl, 4 * sizeof(u32), cudaHostAllocMapped));
+  CUB(cudaHostGetDevicePointer(&h->d_pin_ctl, h->pin_ctl, 0));
+  h->pin_ctl[0] = h->pin_ctl[1] = h->pin_ctl[2] = h->pin_ctl[3] = 0;
   CUB(cudaMalloc(&h->d_ones, 16));
   const u32 ones[4] = {0x40000000u, 0x40000000u, 0x40000000u, 1u};   // multi-GPU: every inbox plane may hold entries, every tick is dense
   CUB(cudaMemcpy(h->d_ones, ones, 16, cudaMemcpyHostToDevice));
@@ -840,12 +851,15 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
   // (tick_kernel.cuh: Gate).  The host reads two words per chunk; ranks of a sharded run reach the same verdict from the same
   // device-summed rows, so there is no host collective in the loop.  Ticks launched past the first quiescent one never
   // execute: nothing to rewind on the device, the logical clock (and the exchange epoch) is simply set back.
-  u32 chunk = 16;
-  if (const char* e = getenv("SERFSIM_CHUNK")) chunk = (u32)std::max(1, atoi(e));
+  // Chunks grow (16, 32, 64, 128): short runs overshoot by a few gated launches, long ones synchronise rarely.
+  u32 chunk = 16, chunk_max = 128;
+  if (const char* e = getenv("SERFSIM_CHUNK")) chunk = chunk_max = (u32)std::max(1, atoi(e));
+  const bool host_jump = !getenv("SERFSIM_NO_JUMP");
   const u32 pp = (u32)std::max(0, h->cfg.push_pull_interval_ticks);
   const u32 start = h->tick;
   int rc = 0;
   CU(cudaMemsetAsync(h->d_runctl, 0, 2 * sizeof(u32), h->stream));
+  h->pin_ctl[0] = h->pin_ctl[1] = 0;                   // nothing of an earlier call is in flight: every call ends synchronised
   h->gate_on = true; h->gate_first = start;
   struct GateOff { serfsim* h; ~GateOff() { h->gate_on = false; } } gate_off{h};
   auto finish = [&](u32 converged_at, bool converged) -> int {
@@ -864,15 +878,46 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
     for (u32 k = 0; k < h->launch_log.size() && h->launch_log_first + k <= t; ++k) executed += h->launch_log[k];
     h->last_launches = executed;
   };
+  bool probe = false;                                  // the next launch is the single tick whose gate judges the row the jump starts from
   while (h->tick - start < max_ticks) {
-    const u32 n = std::min(chunk, max_ticks - (h->tick - start));
+    const u32 n = probe ? 1u : std::min(chunk, max_ticks - (h->tick - start));
     if ((rc = launch_ticks(h, n))) return rc;
-    CU(cudaMemcpyAsync(h->pin_ctl, h->d_runctl, 2 * sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    if (h->pin_ctl[0]) {
-      const u32 t = h->pin_ctl[1];
+    if (*(volatile u32*)h->pin_ctl) {
+      const u32 t = ((volatile u32*)h->pin_ctl)[1];
       stop_at(t);
       return finish(t, true);
+    }
+    if (!probe) chunk = std::min(chunk * 2, chunk_max);
+    // The last executed tick proved that nothing can happen before tick `until` (tick_kernel.cu: finish_tick): the ticks up to
+    // there — and up to the next host operation — are not even launched; one small kernel writes their rows.  The rows a jump
+    // produces equal the row before it, and that one must have been judged "not quiescent" by a gate first: a jump is
+    // preceded by one single-tick launch (`probe`).
+    const u32 until = ((volatile u32*)h->pin_ctl)[2];
+    const bool sleeping = host_jump && h->cfg.world_size == 1 && until > h->tick && h->tick - start < max_ticks;
+    if (sleeping && probe) {
+      u32 stop = until;
+      auto nxt = std::lower_bound(h->ops.begin(), h->ops.end(), h->tick, [](const HostOp& o, u32 tt) { return o.tick < tt; });
+      if (nxt != h->ops.end()) stop = std::min(stop, nxt->tick);
+      const u32 n_skip = std::min(stop > h->tick ? stop - h->tick : 0u, max_ticks - (h->tick - start));
+      if (n_skip) {
+        if ((rc = ensure_trace(h, h->tick + n_skip + 1))) return rc;
+        launch_fill_idle_rows(h->d_trace + (size_t)h->tick * 8, n_skip, h->d_sched, h->cfg.trace != 0, h->stream);
+        h->last_launches++;
+        SFS_COUNT(17, n_skip);                           // ticks the host jumped over
+        for (u32 k = 0; k < n_skip; ++k) {
+          if (h->tick_timing) {
+            const u32 t = h->tick + k;
+            while (h->tick_ev.size() < 2 * ((size_t)t + 1)) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->tick_ev.push_back(e); }
+            CU(cudaEventRecord(h->tick_ev[2 * (size_t)t], h->stream)); CU(cudaEventRecord(h->tick_ev[2 * (size_t)t + 1], h->stream));
+          }
+          h->launch_log.push_back(k == 0 ? 1u : 0u);
+        }
+        h->tick += n_skip;
+      }
+      probe = false;
+    } else {
+      probe = sleeping;
     }
   }
   // max_ticks reached: the last tick's row has not been judged by any kernel yet — apply the same rule here

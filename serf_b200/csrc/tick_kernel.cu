@@ -675,6 +675,7 @@ __device__ __forceinline__ void finish_tick(const TickParams& p, const Counters&
   if (threadIdx.x == 0) {
     row[4] = row[4] + suspects;                            // pending = awake views counted above + sleeping Suspect views
     sched[SCHED_IDLE_UNTIL] = until;
+    if (p.host_idle_until) *p.host_idle_until = until;
     sched[SCHED_AWAKE] = 0; sched[SCHED_UE_ACTIVITY] = 0; sched[SCHED_TICKET] = 0;
   }
 }
@@ -939,7 +940,7 @@ template <bool TRACE>
 __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__ TickParams p, const uint4* __restrict__ snap_rec, const u64* __restrict__ snap_node) {
   if (p.gate.ctl && p.gate.ctl[0]) return;
   // a round can queue transmits and start timers after the tick kernel has decided how long the cluster may sleep: take the decision back
-  if (blockIdx.x == 0 && threadIdx.x == 0) p.sched[SCHED_IDLE_UNTIL] = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { p.sched[SCHED_IDLE_UNTIL] = 0; if (p.host_idle_until) *p.host_idle_until = 0; }
   long long d_changed = 0, d_pending = 0, d_susp = 0;
   u64 d_hash = 0;
   for (u32 vl = blockIdx.x * BLOCK + threadIdx.x; vl < p.n_local; vl += gridDim.x * BLOCK) {
@@ -1130,6 +1131,15 @@ __global__ void __launch_bounds__(BLOCK) drain_kernel(const __grid_constant__ Dr
   }
 }
 
+// Rows of ticks the host did not launch because the cluster sleeps through them (serfsim_run_until_converged): what
+// write_idle_row would have written.  rows = first of the n rows; the row before it belongs to the last executed / skipped tick.
+__global__ void fill_idle_rows_kernel(u64* rows, u32 n, const u32* sched, int trace) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rows[(size_t)i * 8 + 4] = *reinterpret_cast<const u64*>(sched + SCHED_SUSPECTS);
+  if (trace) rows[(size_t)i * 8 + 7] = *(rows - 8 + 7);
+}
+
 // watch[v]: bit s set iff subject s appears in node v's neighbour list — only such nodes can ever pick it as a probe
 // target, so they alone evaluate the SWIM probe (and stay scheduled while it is down).
 __global__ void compute_watch_kernel(const u32* __restrict__ row_ptr, const u32* __restrict__ col, const u32* __restrict__ subj, u32 R, u32 first, u32 n_local, u16* watch) {
@@ -1312,6 +1322,9 @@ void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st) {
   const bool small = p.fanout <= 4;          // the common fan-outs (3, 4) get the 4-wide target array
   if (trace) { if (small) launch_tick_v<true, 4>(p, grid, st); else launch_tick_v<true, 8>(p, grid, st); }
   else { if (small) launch_tick_v<false, 4>(p, grid, st); else launch_tick_v<false, 8>(p, grid, st); }
+}
+void launch_fill_idle_rows(u64* rows, u32 n, const u32* sched, bool trace, cudaStream_t st) {
+  if (n) SFS_LAUNCH((n + 127) / 128, 128, 0, st, fill_idle_rows_kernel)(rows, n, sched, trace ? 1 : 0);
 }
 void launch_pushpull(const TickParams& p, const uint4* snap_rec, const u64* snap_node, bool trace, cudaStream_t st) {
   if (trace) SFS_LAUNCH(SFS_SMS * 8, BLOCK, 0, st, pushpull_kernel<true>)(p, snap_rec, snap_node);

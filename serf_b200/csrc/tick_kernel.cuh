@@ -35,6 +35,8 @@ namespace sfs {
 // same tick without a host collective.  ctl[0]: done flag, ctl[1]: index of the first quiescent tick.
 struct Gate {
   u32* ctl;                   // null: gating off (serfsim_step)
+  u32* host_ctl;              // the same two words in mapped pinned host memory: the host reads the verdict without a device→host copy
+                              // (a copy would queue behind the result vectors of the previous run on the copy engine)
   const u64* prev_row;        // global trace row of tick-1 (8 × u64); null for the first tick of a call (it always runs)
   u32 tick;                   // this tick
   u32 evaluate;               // 1: this kernel is the first of the tick's launch sequence and evaluates the rule
@@ -56,7 +58,10 @@ __device__ __forceinline__ bool gate_closed(const Gate& g, bool leader) {
   if (g.ctl[0]) return true;
   if (!g.evaluate || !g.prev_row) return false;
   if (!quiescent_row(g.prev_row, g.tick - 1, g.future_ops != 0, g.pp, g.byz_on != 0)) return false;
-  if (leader) { g.ctl[1] = g.tick - 1; g.ctl[0] = 1; }      // every CTA of this kernel reaches the same verdict from the row itself
+  if (leader) {                                            // every CTA of this kernel reaches the same verdict from the row itself
+    g.ctl[1] = g.tick - 1; g.ctl[0] = 1;
+    if (g.host_ctl) { g.host_ctl[1] = g.tick - 1; g.host_ctl[0] = 1; }   // visible to the host once the kernel has completed
+  }
   return true;
 }
 
@@ -113,6 +118,7 @@ struct TickParams {
   u32* sched;                 // scheduler words (SCHED_*), u64 suspect-view counter at sched + SCHED_SUSPECTS
   u32 sleep_on;               // 0: SERFSIM_NO_SKIP — every tile, every view, every tick
   u32 pp_every, reap_every;   // push-pull / reaper periods in ticks (0 = off): such ticks are never skipped
+  u32* host_idle_until;       // SCHED_IDLE_UNTIL mirrored into mapped pinned host memory: serfsim_run_until_converged does not even launch the ticks the cluster sleeps through
 };
 constexpr u32 SCHED_TICKET = 0, SCHED_IDLE_UNTIL = 1, SCHED_UE_ACTIVITY = 2, SCHED_AWAKE = 3, SCHED_SUSPECTS = 4 /* u64 */, SCHED_WORDS = 8;
 constexpr u32 NO_DEADLINE = 0xffffffffu;
@@ -158,6 +164,7 @@ struct DrainParams {
 };
 
 void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st);
+void launch_fill_idle_rows(u64* rows, u32 n, const u32* sched, bool trace, cudaStream_t st);
 void launch_pushpull(const TickParams& p, const uint4* snap_rec, const u64* snap_node, bool trace, cudaStream_t st);
 void launch_drain(const DrainParams& p, cudaStream_t st);
 void launch_publish(const PublishParams& p, cudaStream_t st);

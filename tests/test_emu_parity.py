@@ -111,11 +111,20 @@ def test_sleeping_views_timer_wheel_and_idle_ticks():
     o = sc.build(oracle_sim, trace=1)
     to = o.run_until_converged(sc.max_ticks)
     assert to[0] > 60
-    for trace in (0, 1):
+    import os
+    for trace, chunk in ((0, None), (1, None), (0, "4"), (1, "5")):
         L.emu_probe_reset()
         f = sc.build(emu_sim, trace=trace)
-        assert f.run_until_converged(sc.max_ticks) == to
-        assert L.emu_probe(3) > 20 and L.emu_probe(4) > 0, (L.emu_probe(3), L.emu_probe(4))
+        if chunk:
+            os.environ["SERFSIM_CHUNK"] = chunk            # small launch chunks: the host learns early that the cluster sleeps
+        try:
+            assert f.run_until_converged(sc.max_ticks) == to
+        finally:
+            os.environ.pop("SERFSIM_CHUNK", None)
+        # skipped on the device (launched before the host learnt that the cluster sleeps, probe 3) or not launched at all (probe 17)
+        assert L.emu_probe(3) + L.emu_probe(17) > 20 and L.emu_probe(4) > 0, (L.emu_probe(3), L.emu_probe(17), L.emu_probe(4))
+        if chunk:
+            assert L.emu_probe(17) > 10
         if not trace:
             assert L.emu_probe(5) > 0
         assert_same(f, o, sc.slots, with_hash=bool(trace))
