@@ -74,6 +74,8 @@ extern "C" {
 #define SERFSIM_OP_FAIL         4u  /* process crash: node stops sending/receiving (fault injection, cf. MessageDropper `serf/delegate.rs:42-45`) */
 #define SERFSIM_OP_REJOIN       5u  /* crashed node returns: memberlist alive(inc+1) + Serf::join                        */
 #define SERFSIM_OP_USER_EVENT   6u  /* Serf::user_event                   `serf/api.rs:241-299`; `slot` = tracked user event */
+#define SERFSIM_OP_FORCE_LEAVE_PRUNE 7u /* Serf::remove_failed_node_prune `serf/api.rs:513`, `serf/base.rs:454-480` with LeaveMessage.prune
+                                           (`types/leave.rs:39-44`): receivers erase the member (handle_prune, `serf/base.rs:1628-1653`) */
 
 #define SERFSIM_MAX_USER_EVENTS 8u
 
@@ -274,6 +276,12 @@ int    serfsim_comm_connect(serfsim_t* h, const void* blobs /*[world_size][blob_
 typedef void (*serfsim_barrier_fn)(void* user);
 typedef void (*serfsim_allreduce_u64_fn)(void* user, uint64_t* buf, uint32_t n);
 int    serfsim_comm_set_hooks(serfsim_t* h, serfsim_barrier_fn barrier, serfsim_allreduce_u64_fn allreduce, void* user);
+/* PROFILING AID (tools/loopback_profile.py): a handle created with world_size = W exchanges with ITSELF — every "peer window"
+ * is a segment of its own receive window, so the cross-shard entries of its ticks come back as deliveries into its own shard.
+ * One GPU then carries exactly the per-GPU work of a W-rank run (the sharded tick kernel with (W-1)/W of its sends staged and
+ * stored into windows, the publish kernel, the drain kernel folding W-1 windows), which makes that path measurable and
+ * profilable with ncu on a single GPU.  The simulation results of such a handle are meaningless.  No hooks are needed. */
+int    serfsim_comm_loopback(serfsim_t* h);
 
 #ifdef __cplusplus
 }

@@ -104,6 +104,8 @@ class Serf {
   void leave(uint32_t node, uint32_t tick = 0) { check(serfsim_inject(h_, tick, SERFSIM_OP_LEAVE, node, 0)); }
   // Serf::remove_failed_node (serf/api.rs:505-515 → force_leave, serf/base.rs:454-480): `origin` asks the cluster to forget subject `slot`
   void remove_failed_node(uint32_t origin, uint32_t slot, uint32_t tick = 0) { check(serfsim_inject(h_, tick, SERFSIM_OP_FORCE_LEAVE, origin, slot)); }
+  /// Serf::remove_failed_node_prune (serf/api.rs:513): the leave intent carries `prune`, receivers erase the member
+  void remove_failed_node_prune(uint32_t origin, uint32_t slot, uint32_t tick = 0) { check(serfsim_inject(h_, tick, SERFSIM_OP_FORCE_LEAVE_PRUNE, origin, slot)); }
   // fault injection (cf. MessageDropper, serf/delegate.rs:42-45)
   void fail(uint32_t node, uint32_t tick = 0) { check(serfsim_inject(h_, tick, SERFSIM_OP_FAIL, node, 0)); }
   void rejoin(uint32_t node, uint32_t tick = 0) { check(serfsim_inject(h_, tick, SERFSIM_OP_REJOIN, node, 0)); }

@@ -393,7 +393,7 @@ struct RefNode {
   // (ties: longer message, then newer), each pick increments transmits, entries reaching
   // retransmit_limit(mult, NumMembers = states.len()) are dropped (finished()).
   // serf.rs:109-131 (NumMembers), serf/delegate.rs:317-344.
-  u32 get_broadcasts(u32 byte_limit, u32 overhead, u8* ty_out, u64* lt_out, u64* id_out, u32 cap) {
+  u32 get_broadcasts(u32 byte_limit, u32 overhead, u8* ty_out, u64* lt_out, u64* id_out, u32 cap, u8* prune_out = nullptr) {
     u32 limit = retransmit_limit(retransmit_mult, states.size());
     std::vector<size_t> order(broadcasts.size());
     for (size_t i = 0; i < order.size(); ++i) order[i] = i;
@@ -409,7 +409,7 @@ struct RefNode {
       QueuedA& q = broadcasts[i];
       if (used + overhead + q.len > byte_limit) continue;
       used += overhead + q.len;
-      if (n < cap) { ty_out[n] = q.ty; lt_out[n] = q.ltime; id_out[n] = q.id; }
+      if (n < cap) { ty_out[n] = q.ty; lt_out[n] = q.ltime; id_out[n] = q.id; if (prune_out) prune_out[n] = q.prune ? 1 : 0; }
       ++n;
       if (++q.transmits >= limit) done.push_back(i);
     }
@@ -496,7 +496,7 @@ static bool v_join_intent(View& r, u32 lt, const RuleCtx& cx, bool requeue = tru
   if (acc && requeue) { r.qjoin = lt; r.txj = (u8)cx.limit; }                // serf/delegate.rs:294-300 re-queue (push-pull discards the result, :495-523)
   return acc;
 }
-static bool v_leave_intent(View& r, u32 lt, bool self, u8 sstate, bool* refute, const RuleCtx& cx, bool requeue = true) {   // base.rs:1442-1572
+static bool v_leave_intent(View& r, u32 lt, bool self, u8 sstate, bool* refute, const RuleCtx& cx, bool requeue = true, bool prune = false) {   // base.rs:1442-1572
   bool acc;
   if (!known(r)) {
     if (r.status == TY_NONE || lt > r.st) { r.status = TY_LEAVE; r.st = lt; acc = true; } else acc = false;
@@ -511,8 +511,12 @@ static bool v_leave_intent(View& r, u32 lt, bool self, u8 sstate, bool* refute, 
       case ST_FAILED: r.status = ST_LEFT; acc = true; break;
       default: r.status = ST_LEAVING; acc = true; break;
     }
+    // msg.prune → handle_prune (base.rs:1504-1570, 1628-1653): the member is erased from the table (erase_node!, :499-519).  The
+    // reference first sleeps broadcast_timeout + leave_propagate_delay when the member is Leaving (holding the member lock); the
+    // tick model erases at once, like RefNode::handle_prune above.
+    if (acc && prune) { r.flags &= (u8)~1u; r.status = TY_NONE; r.st = 0; r.leave_tick = 0; }
   }
-  if (acc && requeue) { r.qleave = lt; r.txl = (u8)cx.limit; }
+  if (acc && requeue) { r.qleave = lt; r.txl = (u8)cx.limit; r.flags = (u8)((r.flags & ~2u) | (prune ? 2u : 0u)); }   // flags bit 1: the queued leave intent carries prune
   return acc;
 }
 static void v_node_join(View& r) {                                           // base.rs:1206-1334
@@ -583,7 +587,7 @@ static bool byz_judge(const View& q, u8 kind, u32 val, u32 delta) {             
   return (kind == 2) ? (q.inc >= (val >> 6) + delta) : (known(q) && q.st >= val + delta);
 }
 
-struct Msg { u32 dst, src, val; u8 slot, kind, byz = 0; };   // kind 0 leave, 1 join, 2 memberlist; byz: a stale entry injected by a byzantine node
+struct Msg { u32 dst, src, val; u8 slot, kind, byz = 0, prune = 0; };   // prune: LeaveMessage.prune (types/leave.rs:39-44), leave intents only   // kind 0 leave, 1 join, 2 memberlist; byz: a stale entry injected by a byzantine node
 
 // ---- user events: literal per-node state ----
 // EventCore.buffer is `Vec<Option<UserEvents>>` of event_buffer_size = 512 entries (serf/base.rs:193, options.rs:516);
@@ -822,7 +826,9 @@ struct TickSim {
               if (a.slot != b.slot) return a.slot < b.slot;
               const int ka = a.kind == 2 ? 0 : a.kind == 0 ? 1 : 2, kb = b.kind == 2 ? 0 : b.kind == 0 ? 1 : 2;
               if (ka != kb) return ka < kb;
-              return a.val != b.val ? a.val < b.val : a.src < b.src;
+              if (a.val != b.val) return a.val < b.val;
+              if (a.kind == 0 && a.prune != b.prune) return a.prune > b.prune;   // leave intents of equal Lamport time: the pruning one first (DESIGN rule P-1)
+              return a.src < b.src;
             });
           u32 i0 = head[v - v0];
           const u32 i1 = head[v - v0 + 1];
@@ -840,7 +846,22 @@ struct TickSim {
           }
           // serf intents, one message at a time
           bool refute = false;
-          for (; i0 < i1 && byd[i0].slot == s && byd[i0].kind == 0; ++i0) { witness32(nd.clock, byd[i0].val); v_leave_intent(r, byd[i0].val, self, nd.sstate, &refute, cx); }
+          {
+            // rule P-1: of the leave intents of one tick only the greatest (ltime, then non-pruning over pruning) keeps its prune
+            // flag — every copy of it does (gossip delivers the same intent from several peers; the first copy is accepted)
+            u32 j = i0;
+            while (j < i1 && byd[j].slot == s && byd[j].kind == 0) ++j;
+            for (u32 i = i0; i < j; ++i) {
+              // rule P-2: further copies of one intent within a tick are dropped.  Without prune a second copy is rejected anyway
+              // (ltime <= status_time, or no newer than the buffered intent); after a pruning one the member is unknown again
+              // and the reference would buffer the second copy as a fresh intent — the reduced inbox cannot count copies.
+              if (i > i0 && byd[i].val == byd[i - 1].val && byd[i].prune == byd[i - 1].prune) continue;
+              const bool greatest = byd[i].val == byd[j - 1].val && byd[i].prune == byd[j - 1].prune;
+              witness32(nd.clock, byd[i].val);
+              v_leave_intent(r, byd[i].val, self, nd.sstate, &refute, cx, true, greatest && byd[i].prune);
+            }
+            i0 = j;
+          }
           for (; i0 < i1 && byd[i0].slot == s && byd[i0].kind == 1; ++i0) { witness32(nd.clock, byd[i0].val); v_join_intent(r, byd[i0].val, cx); }
           if (refute) {                                   // base.rs:1470-1480 → broadcast_join(clock.time()), base.rs:381-397
             u32 T = nd.clock; witness32(nd.clock, T);
@@ -869,13 +890,14 @@ struct TickSim {
             u32 T = nd.clock; nd.clock += 1;
             bool refute = false;
             v_leave_intent(r, T, true, nd.sstate, &refute, cx);
-            r.qleave = T; r.txl = (u8)cx.limit;
+            r.qleave = T; r.txl = (u8)cx.limit; r.flags &= (u8)~2u;
           }
-          if (op == SERFSIM_OP_FORCE_LEAVE && up_r && ev->slot == s) {                            // base.rs:454-480
+          if ((op == SERFSIM_OP_FORCE_LEAVE || op == SERFSIM_OP_FORCE_LEAVE_PRUNE) && up_r && ev->slot == s) {   // base.rs:454-480; api.rs:500-515
+            const bool prune = op == SERFSIM_OP_FORCE_LEAVE_PRUNE;
             u32 T = nd.clock; witness32(nd.clock, T);
             bool refute = false;
-            v_leave_intent(r, T, self, nd.sstate, &refute, cx);
-            r.qleave = T; r.txl = (u8)cx.limit;
+            v_leave_intent(r, T, self, nd.sstate, &refute, cx, true, prune);
+            r.qleave = T; r.txl = (u8)cx.limit; r.flags = (u8)((r.flags & ~2u) | (prune ? 2u : 0u));   // queued whatever the handler said (base.rs:466-476)
             if (refute) { u32 T2 = nd.clock; witness32(nd.clock, T2); v_join_intent(r, T2, cx); r.qjoin = T2; r.txj = (u8)cx.limit; }
           }
         }
@@ -905,7 +927,7 @@ struct TickSim {
             if (!have_targets) { nt = gossip_targets(v, t, targets); have_targets = true; }
             for (u32 k = 0; k < nt; ++k) {
               u32 cnt = 0;
-              if (r.txl > k) { post(Msg{targets[k], v, r.qleave, (u8)s, 0}); ++cnt; }
+              if (r.txl > k) { post(Msg{targets[k], v, r.qleave, (u8)s, 0, 0, (u8)((r.flags >> 1) & 1u)}); ++cnt; }
               if (r.txj > k) { post(Msg{targets[k], v, r.qjoin, (u8)s, 1}); ++cnt; }
               if (r.txm > k) { post(Msg{targets[k], v, ml_key(r), (u8)s, 2}); ++cnt; }
               if (cnt) { row.edge_updates++; row.messages += cnt; }
@@ -1211,12 +1233,12 @@ ORC int oracle_sim_set_subjects(void* p, const u32* subjects) {
 ORC int oracle_sim_reset(void* p, u64 seed) { ((TickSim*)p)->reset(seed); return 0; }
 ORC int oracle_sim_inject(void* p, u32 tick, u32 op, u32 node, u32 slot) {
   auto* s = (TickSim*)p;
-  if (tick < s->tick || node >= s->N || op < 1 || op > 6) { g_err = "bad inject"; return SERFSIM_E_INVAL; }
+  if (tick < s->tick || node >= s->N || op < 1 || op > SERFSIM_OP_FORCE_LEAVE_PRUNE) { g_err = "bad inject"; return SERFSIM_E_INVAL; }
   if (op == SERFSIM_OP_USER_EVENT) {
     if (slot >= s->ue_n) { g_err = "user event index out of range"; return SERFSIM_E_INVAL; }
     if ((s->ue_injected >> slot) & 1u) { g_err = "a tracked user event can be injected once"; return SERFSIM_E_INVAL; }
   }
-  if (op == SERFSIM_OP_FORCE_LEAVE) { if (slot >= s->R) return SERFSIM_E_INVAL; }
+  if (op == SERFSIM_OP_FORCE_LEAVE || op == SERFSIM_OP_FORCE_LEAVE_PRUNE) { if (slot >= s->R) return SERFSIM_E_INVAL; }
   else if ((op == SERFSIM_OP_JOIN || op == SERFSIM_OP_LEAVE) && s->slot_of(node) < 0) { g_err = "join/leave origin must be a tracked subject"; return SERFSIM_E_INVAL; }
   if (!s->event_keys.insert(((u64)tick << 32) | node).second) { g_err = "one operation per node per tick"; return SERFSIM_E_INVAL; }
   if (op == SERFSIM_OP_USER_EVENT) s->ue_injected |= 1u << slot;
@@ -1344,7 +1366,7 @@ struct FaithfulSim {
   std::vector<u64> row_ptr; std::vector<u32> col;
   struct Op { u32 tick, op, node; u64 subject; };
   std::vector<Op> ops;
-  struct M { u32 dst, src; u8 ty; u64 ltime, id; };
+  struct M { u32 dst, src; u8 ty; u64 ltime, id; bool prune; };
   std::vector<M> inflight;
   std::vector<u64> subjects;      // processing order of subjects at a receiver (slot order of Part B)
 
@@ -1387,6 +1409,7 @@ struct FaithfulSim {
       if (oa != ob) return oa < ob;
       if (a.ty != b.ty) return a.ty < b.ty;            // TY_LEAVE (1) before TY_JOIN (2)
       if (a.ltime != b.ltime) return a.ltime < b.ltime;
+      if (a.prune != b.prune) return a.prune > b.prune;   // equal Lamport time: the pruning intent first (Part B's canonical order)
       return a.src < b.src;
     });
     // Per node, per subject in slot order: Phase R (that subject's messages, leaves then joins), the refutation task,
@@ -1403,13 +1426,13 @@ struct FaithfulSim {
       for (size_t sl = 0; sl <= subjects.size(); ++sl) {           // the last round takes untracked subjects (none in the tests)
         while (i < end && order_of(inflight[i].id) == (int)sl) {
           const M& m = inflight[i++];
-          const bool rb = (m.ty == TY_JOIN) ? nd.handle_node_join_intent(m.ltime, m.id) : nd.handle_node_leave_intent(m.ltime, m.id, false);
-          if (rb) nd.queue(m.ty, m.ltime, m.id, false, false);           // serf/delegate.rs:294-300
+          const bool rb = (m.ty == TY_JOIN) ? nd.handle_node_join_intent(m.ltime, m.id) : nd.handle_node_leave_intent(m.ltime, m.id, m.prune);
+          if (rb) nd.queue(m.ty, m.ltime, m.id, m.prune, false);         // serf/delegate.rs:294-300: the raw message is re-queued, prune flag included
         }
         nd.run_detached();                                               // the refutation task of this subject, if any
         if (op && sl < subjects.size()) {
           if (op->op == SERFSIM_OP_JOIN && subjects[sl] == d) nd.api_join();
-          else if (op->op == SERFSIM_OP_FORCE_LEAVE && subjects[sl] == op->subject) { nd.api_force_leave(op->subject, false); nd.run_detached(); }
+          else if ((op->op == SERFSIM_OP_FORCE_LEAVE || op->op == SERFSIM_OP_FORCE_LEAVE_PRUNE) && subjects[sl] == op->subject) { nd.api_force_leave(op->subject, op->op == SERFSIM_OP_FORCE_LEAVE_PRUNE); nd.run_detached(); }
         }
       }
       i = end;
@@ -1421,9 +1444,9 @@ struct FaithfulSim {
       if (nd.broadcasts.empty()) continue;
       u32 tg[8]; const u32 nt = targets(v, t, tg);
       for (u32 k = 0; k < nt && !nd.broadcasts.empty(); ++k) {
-        u8 ty[64]; u64 lt[64], id[64];
-        const u32 n = nd.get_broadcasts(1u << 20, 2, ty, lt, id, 64);
-        for (u32 q = 0; q < n && q < 64; ++q) inflight.push_back(M{tg[k], v, ty[q], lt[q], id[q]});
+        u8 ty[64], pr[64]; u64 lt[64], id[64];
+        const u32 n = nd.get_broadcasts(1u << 20, 2, ty, lt, id, 64, pr);
+        for (u32 q = 0; q < n && q < 64; ++q) inflight.push_back(M{tg[k], v, ty[q], lt[q], id[q], pr[q] != 0});
       }
     }
     ++tick;

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(128) byz_kernel(const __grid_constant__ ByzPar
         const ByzEntries e = byz_entries(r, p.delta);
         if (!e.any) continue;
         u32* const planeS = p.inbox_wr + (size_t)(e.serf_kind * p.R + s) * p.stride;
+        const u32 serf_val1 = (e.serf_kind == KIND_LEAVE ? leave_key(e.serf_lt, false) : e.serf_lt) + 1u;   // the word an honest sender would post
         u32* const planeM = p.inbox_wr + (size_t)(KIND_ML * p.R + s) * p.stride;
         for (u32 k = 0; k < nt; ++k) {
           const u32 dl = tg[k] - p.first;
@@ -43,7 +44,7 @@ __global__ void __launch_bounds__(128) byz_kernel(const __grid_constant__ ByzPar
             const u32 g = atomicAdd(p.send_count + shard, 3u);
             if (g + 3 <= p.win_cap) {
               u64* w = p.win_data[shard] + (size_t)p.rank * p.win_cap + g;
-              w[0] = ((u64)(e.serf_lt + 1u) << 32) | ((u64)s << 28) | ((u64)e.serf_kind << 26) | dloc;
+              w[0] = ((u64)serf_val1 << 32) | ((u64)s << 28) | ((u64)e.serf_kind << 26) | dloc;
               w[1] = ((u64)(e.ml_key + 1u) << 32) | ((u64)s << 28) | ((u64)KIND_ML << 26) | dloc;
               w[2] = ((u64)(u + 1u) << 32) | ((u64)BYZ_ANNOT_SLOT << 28) | (3ull << 26) | dloc;
             } else {
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(128) byz_kernel(const __grid_constant__ ByzPar
             wrote_remote = true;
             continue;                                          // kinds / tile flags / verdict are the receiving shard's business
           }
-          atomicMax(planeS + dl, e.serf_lt + 1u);
+          atomicMax(planeS + dl, serf_val1);
           atomicMax(planeM + dl, e.ml_key + 1u);
           p.hot_wr[dl >> 8] = 1;                               // TILE_SHIFT = 8: the destination tile must run next tick
           if (e.serf_kind == KIND_LEAVE) ++kL; else ++kJ;

@@ -21,7 +21,8 @@
 //   26 u8  tx_join        remaining transmits of the queued join intent (TransmitLimitedQueue)
 //   27 u8  tx_leave       remaining transmits of the queued leave intent
 //   28 u8  tx_ml          remaining transmits of the queued alive/suspect/dead message
-//   29 u8  flags          bit 0: known (member present in Members.states, types/member.rs:37)
+//   29 u8  flags          bit 0: known (member present in Members.states, types/member.rs:37); bit 1: the queued leave intent carries
+//                         LeaveMessage.prune (types/leave.rs:39-44)
 //   30 u16 conf_mask      suspicion confirmer buckets (Lifeguard)
 #pragma once
 #include <cstdint>
@@ -37,14 +38,15 @@ enum : u32 { ST_NONE = 0, ST_ALIVE = 1, ST_LEAVING = 2, ST_LEFT = 3, ST_FAILED =
 enum : u32 { TY_NONE = 0, TY_LEAVE = 1, TY_JOIN = 2 };                                   // types/message.rs:17-18
 enum : u32 { ML_ALIVE = 0, ML_SUSPECT = 1, ML_DEAD = 2, ML_LEFT = 3 };
 enum : u32 { SS_ALIVE = 0, SS_LEAVING = 1, SS_LEFT = 2 };                                // SerfState
-enum : u32 { OP_JOIN = 1, OP_LEAVE = 2, OP_FORCE_LEAVE = 3, OP_FAIL = 4, OP_REJOIN = 5 };
+enum : u32 { OP_JOIN = 1, OP_LEAVE = 2, OP_FORCE_LEAVE = 3, OP_FAIL = 4, OP_REJOIN = 5, /* 6: OP_USER_EVENT, uevent.cuh */ OP_FORCE_LEAVE_PRUNE = 7 };
 enum : u32 { DOMAIN_GOSSIP = 0, DOMAIN_PROBE = 1, DOMAIN_PUSHPULL = 2 };
 enum : u32 { KIND_LEAVE = 0, KIND_JOIN = 1, KIND_ML = 2 };
 
 constexpr u32 MAX_SLOTS = 16;
 constexpr u32 MAX_FANOUT = 8;
 constexpr u32 MAX_K = 7;            // suspicion_mult - 2
-constexpr u32 LTIME_LIMIT = 0xFFFFFFF0u;
+constexpr u32 LTIME_LIMIT = 0x7FFFFFF0u;     // a leave intent travels as (ltime << 1 | !prune) + 1 in 32 bits
+constexpr u32 FLAG_KNOWN = 1u, FLAG_QPRUNE = 2u;
 constexpr u32 INC_LIMIT = (1u << 26) - 16;
 
 // node_state word: bits 0-31 LamportClock (types/clock.rs:125), 32 up, 40-41 SerfState
@@ -108,8 +110,16 @@ __host__ __device__ inline void join_intent(Rec& r, u32 lt, u32 limit, bool requ
   if (acc && requeue) { r.qjoin = lt; r.txj = limit; }   // push-pull discards the handler's result (serf/delegate.rs:495-523)
 }
 
-// handle_node_leave_intent — serf/base.rs:1442-1572
-__host__ __device__ inline void leave_intent(Rec& r, u32 lt, bool self, u32 sstate, bool& refute, u32 limit, bool requeue = true) {
+// Leave intents on the wire (inbox words, window entries): key = ltime << 1 | !prune.  Of the leave intents a view receives in
+// one tick only the greatest key is applied (DESIGN.md reduction lemma); rule P-1: a prune flag carried by any other one is
+// dropped — and at equal Lamport time the intent WITHOUT prune is the greater one, so that applying the greatest alone equals
+// applying all of them in ascending order with the lesser ones' flags dropped.
+__host__ __device__ inline u32 leave_key(u32 lt, bool prune) { return (lt << 1) | (prune ? 0u : 1u); }
+
+// handle_node_leave_intent — serf/base.rs:1442-1572; prune → handle_prune, :1504-1570, 1628-1653: the member is erased from the
+// view (erase_node!, :499-519).  The reference sleeps broadcast_timeout + leave_propagate_delay first when the member is Leaving,
+// holding the node's member lock; the tick model erases at once (as the literal oracle node does).
+__host__ __device__ inline void leave_intent(Rec& r, u32 lt, bool prune, bool self, u32 sstate, bool& refute, u32 limit, bool requeue = true) {
   bool acc;
   if (!(r.flags & 1)) {                                   // :1450-1458
     acc = (r.status == TY_NONE) || (lt > r.st);
@@ -125,8 +135,9 @@ __host__ __device__ inline void leave_intent(Rec& r, u32 lt, bool self, u32 ssta
       case ST_FAILED: r.status = ST_LEFT; acc = true; break;      // :1520-1559
       default: r.status = ST_LEAVING; acc = true; break;          // :1560-1570
     }
+    if (acc && prune) { r.flags &= ~FLAG_KNOWN; r.status = TY_NONE; r.st = 0; r.leave_tick = 0; }   // handle_prune → erase_node!
   }
-  if (acc && requeue) { r.qleave = lt; r.txl = limit; }
+  if (acc && requeue) { r.qleave = lt; r.txl = limit; r.flags = (r.flags & ~FLAG_QPRUNE) | (prune ? FLAG_QPRUNE : 0u); }
 }
 
 // handle_node_join — serf/base.rs:1206-1334

@@ -167,6 +167,7 @@ struct serfsim {
   u32 win_cap = 0;
   u32 win_cap_base = 0;                        // capacity sized for the membership entries alone (serfsim_create)
   bool connected = false;
+  bool loopback = false;                       // serfsim_comm_loopback: profiling aid, the handle exchanges with itself
   serfsim_barrier_fn barrier = nullptr; serfsim_allreduce_u64_fn allreduce = nullptr; void* comm_user = nullptr;
   std::vector<void*> ipc_opened;
   bool tick_timing = false;
@@ -351,7 +352,7 @@ int launch_ticks(serfsim* h, u32 n) {
       const u32 stamp = h->xepoch + 1;
       PublishParams pb{};
       pb.world = p.world; pb.rank = p.rank; pb.stamp = stamp; pb.xpar = xpar; pb.send_count = h->d_send_count; pb.peer_ctrl = h->d_peer_ctrl;
-      pb.row = p.row; pb.gate = gate_word;
+      pb.row = p.row; pb.gate = gate_word; pb.sched = h->d_sched; pb.loopback = h->loopback ? 1u : 0u;
       launch_publish(pb, h->stream);
       DrainParams d{};
       d.n_local = h->count; d.stride = h->stride; d.R = h->R; d.world = p.world; d.rank = p.rank; d.win_cap = h->win_cap; d.stamp = stamp; d.n_tiles = h->n_tiles; d.kinds_prev = p.kinds_prev;
@@ -359,7 +360,8 @@ int launch_ticks(serfsim* h, u32 n) {
       d.byz_on = h->byz_on ? 1u : 0u; d.byz_delta = h->byz_delta; d.shard_size = h->shard_size; d.rec = h->d_rec; d.node_state = h->d_node; d.peer_anomaly = h->d_peer_anomaly;
       d.ue_n = h->ue_table.n; d.ue_inbox_wr = h->ue_table.n ? h->d_ue_inbox[t & 1] : nullptr; d.ue_ltime = h->d_ue_ltime;
       d.my_row = p.row; d.grow = h->d_grow + (size_t)t * 8; d.gate = gate_word;
-      d.sums = reinterpret_cast<const u64*>(reinterpret_cast<const unsigned char*>(h->d_ctrl) + CTRL_SUMS_OFF) + (size_t)xpar * 8 * 8;
+      d.sums = reinterpret_cast<const u64*>(reinterpret_cast<const unsigned char*>(h->d_ctrl) + CTRL_SUMS_OFF) + (size_t)xpar * 8 * CTRL_FIELDS;
+      d.sched = h->d_sched; d.host_idle_until = h->d_pin_ctl + 2; d.tick = t; d.sleep_on = p.sleep_on;
       launch_drain(d, h->stream);
       h->last_launches += 2;
       h->xepoch++;
@@ -818,12 +820,12 @@ int serfsim_reset(serfsim_t* h, uint64_t seed) {
 int serfsim_inject(serfsim_t* h, uint32_t tick, uint32_t op, uint32_t node, uint32_t slot) {
   if (!h) return fail(SERFSIM_E_INVAL, "null handle");
   if (tick < h->tick) return fail(SERFSIM_E_INVAL, "cannot schedule an operation in the past");
-  if (node >= h->N || op < SERFSIM_OP_JOIN || op > SERFSIM_OP_USER_EVENT) return fail(SERFSIM_E_INVAL, "bad node / op");
+  if (node >= h->N || op < SERFSIM_OP_JOIN || op > SERFSIM_OP_FORCE_LEAVE_PRUNE) return fail(SERFSIM_E_INVAL, "bad node / op");
   if (op == SERFSIM_OP_USER_EVENT) {
     if (slot >= h->ue_table.n) return fail(SERFSIM_E_INVAL, "user event index out of range (serfsim_set_user_events)");
     if ((h->ue_injected >> slot) & 1u) return fail(SERFSIM_E_INVAL, "a tracked user event can be injected once");
   }
-  if (op == SERFSIM_OP_FORCE_LEAVE) { if (slot >= h->R) return fail(SERFSIM_E_INVAL, "slot out of range"); }
+  if (op == SERFSIM_OP_FORCE_LEAVE || op == SERFSIM_OP_FORCE_LEAVE_PRUNE) { if (slot >= h->R) return fail(SERFSIM_E_INVAL, "slot out of range"); }
   else if ((op == SERFSIM_OP_JOIN || op == SERFSIM_OP_LEAVE) && slot_of(h, node) < 0)
     return fail(SERFSIM_E_INVAL, "join/leave origin must be a tracked subject");
   if (!h->op_keys.insert(((u64)tick << 32) | node).second) return fail(SERFSIM_E_INVAL, "one operation per node per tick");
@@ -852,7 +854,7 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
   // device-summed rows, so there is no host collective in the loop.  Ticks launched past the first quiescent one never
   // execute: nothing to rewind on the device, the logical clock (and the exchange epoch) is simply set back.
   // Chunks grow (16, 32, 64, 128): short runs overshoot by a few gated launches, long ones synchronise rarely.
-  u32 chunk = 16, chunk_max = 128;
+  u32 chunk = 16, chunk_max = h->cfg.world_size > 1 ? 32 : 128;    // sharded: ticks launched into a sleeping cluster still execute
   if (const char* e = getenv("SERFSIM_CHUNK")) chunk = chunk_max = (u32)std::max(1, atoi(e));
   const bool host_jump = !getenv("SERFSIM_NO_JUMP");
   const u32 pp = (u32)std::max(0, h->cfg.push_pull_interval_ticks);
@@ -894,7 +896,7 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
     // produces equal the row before it, and that one must have been judged "not quiescent" by a gate first: a jump is
     // preceded by one single-tick launch (`probe`).
     const u32 until = ((volatile u32*)h->pin_ctl)[2];
-    const bool sleeping = host_jump && h->cfg.world_size == 1 && until > h->tick && h->tick - start < max_ticks;
+    const bool sleeping = host_jump && until > h->tick && h->tick - start < max_ticks;      // sharded runs: every rank reads the same word
     if (sleeping && probe) {
       u32 stop = until;
       auto nxt = std::lower_bound(h->ops.begin(), h->ops.end(), h->tick, [](const HostOp& o, u32 tt) { return o.tick < tt; });
@@ -902,7 +904,7 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
       const u32 n_skip = std::min(stop > h->tick ? stop - h->tick : 0u, max_ticks - (h->tick - start));
       if (n_skip) {
         if ((rc = ensure_trace(h, h->tick + n_skip + 1))) return rc;
-        launch_fill_idle_rows(h->d_trace + (size_t)h->tick * 8, n_skip, h->d_sched, h->cfg.trace != 0, h->stream);
+        launch_fill_idle_rows(h->d_trace + (size_t)h->tick * 8, h->cfg.world_size > 1 ? h->d_grow + (size_t)h->tick * 8 : nullptr, n_skip, h->d_sched, h->cfg.trace != 0, h->stream);
         h->last_launches++;
         SFS_COUNT(17, n_skip);                           // ticks the host jumped over
         for (u32 k = 0; k < n_skip; ++k) {
@@ -1304,6 +1306,29 @@ int serfsim_comm_connect(serfsim_t* h, const void* blobs) {
   }
   h->barrier(h->comm_user);          // every rank has mapped every window before the first tick writes into one
   h->connected = true;
+  return 0;
+}
+
+int serfsim_comm_loopback(serfsim_t* h) {
+  if (!h) return fail(SERFSIM_E_INVAL, "null handle");
+  const int W = h->cfg.world_size;
+  if (W < 2) return fail(SERFSIM_E_INVAL, "world_size == 1");
+  if (h->cfg.rank != 0) return fail(SERFSIM_E_INVAL, "loopback: create the handle as rank 0");
+  if (h->cfg.push_pull_interval_ticks > 0 || h->byz_on || h->ue_table.n) return fail(SERFSIM_E_INVAL, "loopback profiles the membership path only");
+  // entries for shard s are written at win_data[s][rank·win_cap + g]: with rank 0 the window of "peer" s is my own segment s
+  std::vector<u32*> pc(8, nullptr);
+  std::vector<std::vector<u64*>> pd(2, std::vector<u64*>(8, nullptr));
+  std::vector<u8*> pan(8, nullptr);
+  for (int r = 0; r < W; ++r) {
+    pc[r] = h->d_ctrl; pan[r] = h->d_anomaly;
+    for (int par = 0; par < 2; ++par) pd[par][r] = h->d_win_data[par] + (size_t)r * h->win_cap;
+  }
+  for (int par = 0; par < 2; ++par) CU(cudaMemcpy(h->d_peer_data[par], pd[par].data(), sizeof(u64*) * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_peer_ctrl, pc.data(), sizeof(u32*) * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->d_peer_anomaly, pan.data(), sizeof(void*) * 8, cudaMemcpyHostToDevice));
+  h->barrier = [](void*) {};
+  h->allreduce = [](void*, uint64_t*, uint32_t) {};
+  h->connected = true; h->loopback = true;
   return 0;
 }
 

@@ -132,8 +132,6 @@ struct StageView {
 
 struct Counters {          // per-thread, reduced once per CTA; rare counters (events, suspects) go straight to the trace row
   u32 packets, edges, changed, pending, kL, kJ, kM;
-  u32 awake;               // nodes that stay awake (the scheduler's "can the next tick do anything" input)
-  int dsusp;               // net change of the number of Suspect views at up nodes (persistent counter, tick_kernel.cuh)
   u64 hash;
 };
 
@@ -324,13 +322,89 @@ __device__ __forceinline__ bool node_active(const TickParams& p, const Pre& x, b
   return (x.busy & 7u) != 0 || x.any != 0 || p.reap_now != 0 || (due && (x.busy & 8u));
 }
 
+// ---- cold paths of a node's tick, kept out of line: host operations, the reaper round and the SWIM probe run for a handful of
+// nodes per tick (or for all of them once in a long while); inlined, their temporaries (a second Philox block, the operation
+// scan) raise the register demand of the path every node takes and make it spill.
+#ifdef SERFSIM_EMU
+#define SFS_COLD __attribute__((noinline))
+#else
+#define SFS_COLD __noinline__
+#endif
+// Phase E — what the API call does at its origin: Serf::join / leave / remove_failed_node[_prune], crash, restart.
+__device__ SFS_COLD void cold_host_op(Rec& r, u32& clock, u32& sstate, u32 op, bool op_here, bool self, bool up_r, u32 limit) {
+  if (op == OP_REJOIN && self && !up_r) {
+    r.inc += 1; r.mlstate = ML_ALIVE; r.qfrom = 0; r.txm = limit; r.deadline = 0; r.mask = 0;
+    sstate = SS_ALIVE;
+    node_join(r);
+  }
+  if (((op == OP_JOIN && up_r) || (op == OP_REJOIN && !up_r)) && self) {     // serf/api.rs:339-342 → serf/base.rs:381-397
+    const u32 T = clock; witness(clock, T);
+    join_intent(r, T, limit);
+    r.qjoin = T; r.txj = limit;
+  }
+  if (op == OP_LEAVE && up_r && self && sstate == SS_ALIVE) {                // serf/api.rs:422-449
+    sstate = SS_LEAVING;
+    const u32 T = clock; clock += 1;
+    bool rf = false;
+    leave_intent(r, T, false, true, sstate, rf, limit);
+    r.qleave = T; r.txl = limit; r.flags &= ~FLAG_QPRUNE;
+  }
+  if ((op == OP_FORCE_LEAVE || op == OP_FORCE_LEAVE_PRUNE) && up_r && op_here) {   // serf/base.rs:454-480 (remove_failed_node[_prune], serf/api.rs:500-515)
+    const u32 T = clock; witness(clock, T);
+    const bool prune = op == OP_FORCE_LEAVE_PRUNE;
+    bool rf = false;
+    leave_intent(r, T, prune, self, sstate, rf, limit);
+    r.qleave = T; r.txl = limit; r.flags = (r.flags & ~FLAG_QPRUNE) | (prune ? FLAG_QPRUNE : 0u);   // queued whatever the handler said
+    if (rf) { const u32 T2 = clock; witness(clock, T2); join_intent(r, T2, limit); r.qjoin = T2; r.txj = limit; }
+  }
+}
+// Which host operation targets node v this tick (the mark kernel set bit 1 of its busy byte)?
+__device__ SFS_COLD u32 cold_find_op(const TickParams& p, u32 v, u32& op_slot) {
+  atomicAdd((unsigned long long*)(p.row + 5), 1ull);
+  for (u32 e = p.ev_begin; e < p.ev_end; ++e)
+    if (p.ev_node[e] == v) { op_slot = p.ev_slot[e]; return p.ev_op[e]; }
+  return 0;
+}
+// Reaper round (serf/base.rs:483-610): Left / Failed members past their timeouts are erased, stale buffered intents dropped.
+__device__ SFS_COLD void cold_reap(Rec& r, u32 t, u32 tombstone, u32 reconnect, u32 intent) {
+  const u32 age = r.leave_tick ? (t + 1 - r.leave_tick) : 0;
+  if ((r.flags & 1) && r.leave_tick && ((r.status == ST_LEFT && age > tombstone) || (r.status == ST_FAILED && age > reconnect))) {
+    r.flags &= ~1u; r.status = TY_NONE; r.st = 0; r.leave_tick = 0;           // erase_node! :499-519
+  } else if (!(r.flags & 1) && r.status != TY_NONE && r.leave_tick && age > intent) {
+    r.status = TY_NONE; r.st = 0; r.leave_tick = 0;                           // reap_intents :1817-1822
+  }
+}
+// SWIM probe target of a watcher's round: a uniformly random neighbour (memberlist walks a shuffled list).
+__device__ SFS_COLD u32 cold_probe_target(const TickParams& p, u32 v, u32 row0, u32 deg) {
+  u32 w[4];
+  philox4x32_10(p.tick, v, 0, DOMAIN_PROBE, p.seed_lo, p.seed_hi, w);
+  return __ldg(p.col + row0 + (((w[0] & 0xffffu) * deg) >> 16));
+}
+// The probe found the subject down: suspect it (or confirm with this node's bucket).
+__device__ SFS_COLD void cold_probe_hit(const TickParams& p, Rec& r, u32 v) {
+  if (r.mlstate == ML_ALIVE || r.mlstate == ML_SUSPECT) {
+    if (r.mlstate == ML_ALIVE) atomicAdd((unsigned long long*)(p.row + 6), 1ull);
+    ml_suspect(r, r.inc, from_bucket(v), p.tick, false, p.rules);
+  }
+}
+// Refutation of a leave intent about ourselves: serf/base.rs:1470-1480 → broadcast_join(clock.time()), :381-397
+__device__ SFS_COLD void cold_refute(Rec& r, u32& clock, u32 limit) {
+  const u32 T = clock; witness(clock, T);
+  join_intent(r, T, limit);
+  r.qjoin = T; r.txj = limit;
+}
+// Is a watcher's own failed probe still a confirmation (its bucket not in the confirmer set, the set not full)?
+__device__ SFS_COLD bool cold_can_confirm(const TickParams& p, const Rec& r, u32 v) {
+  return (u32)__popc(r.mask) - 1u < p.rules.k && !(r.mask & (1u << from_bucket(v)));
+}
+
 // Returns true when the node stays awake (queued transmits, probe duty): that keeps its tile hot for the next tick.
 // A view whose only business is a running suspicion timer does not: its deadline goes to `mind` (the caller registers the
 // minimum in tile_due) and the view sleeps until its tile comes due.  `due`: this tile's earliest deadline has been reached —
 // every node of it that carries a timer (busy bit 3) visits all its views.
 template <bool TRACE, int FMAX, bool SHARDED, bool R1, bool STAGED>
 __device__ __forceinline__ bool process_node(const TickParams& p, const StageView& sv, XStage* xs, const u32 vl, const Pre& pre, const bool kL, const bool kJ, const bool kM, const bool mark, const bool saturated,
-                                             const bool due, const u64 pol_first, const u64 pol_last, Counters& c, u32& mind) {
+                                             const bool due, const u64 pol_first, const u64 pol_last, Counters& c, u32& mind, int& dsusp) {
   static_assert(!STAGED || R1, "the staged path is the single-slot path");
   const u32 lt = threadIdx.x;              // index inside the staged tile
   const u32 v = p.first + vl;
@@ -381,11 +455,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
 
   // host operation for this node (at most one per tick; the mark kernel set bit 1 of the busy byte)
   u32 op = 0, op_slot = 0;
-  if (busy & 2) {
-    for (u32 e = p.ev_begin; e < p.ev_end; ++e)
-      if (p.ev_node[e] == v) { op = p.ev_op[e]; op_slot = p.ev_slot[e]; break; }
-    atomicAdd((unsigned long long*)(p.row + 5), 1ull);
-  }
+  if (busy & 2) op = cold_find_op(p, v, op_slot);
   bool up_s = up_r;
   if (op == OP_FAIL) up_s = false;
   if (op == OP_REJOIN) up_s = true;
@@ -394,10 +464,12 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   bool have_probe = false;
   u32 ptarget = 0;
   if (up_s && wmask && p.probe_every && p.down_mask && ((t + v) % p.probe_every) == 0 && deg) {
-    u32 w[4];
-    philox4x32_10(t, v, 0, DOMAIN_PROBE, p.seed_lo, p.seed_hi, w);
-    const u32 e = row0 + (((w[0] & 0xffffu) * deg) >> 16);
-    ptarget = (STAGED && sv.col_staged) ? sv.col[e - sv.col_base] : SFS_LD_COL(p.col + e, pol_first);
+    ptarget = (STAGED && sv.col_staged) ? 0u : cold_probe_target(p, v, row0, deg);
+    if (STAGED && sv.col_staged) {
+      u32 w[4];
+      philox4x32_10(t, v, 0, DOMAIN_PROBE, p.seed_lo, p.seed_hi, w);
+      ptarget = sv.col[row0 + (((w[0] & 0xffffu) * deg) >> 16) - sv.col_base];
+    }
     have_probe = true;
   }
 
@@ -427,6 +499,9 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
     iJ = kJ ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R + s2) * nl + vl, pol_first) : 0;
     iM = kM ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R + s2) * nl + vl, pol_first) : 0;
   };
+#ifndef SFS_VIEW_PREFETCH
+#define SFS_VIEW_PREFETCH 1                  // 0: a view's record is requested when its turn comes (12 registers less, one exposed round trip per further view)
+#endif
   u32 s = R;
   if (R1) { s = 0; todo = 0; }
   else if (todo) {
@@ -437,7 +512,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   while (s < R) {
     const size_t idx = (size_t)s * nl + vl;
     u32 s_next = R;
-    if (!R1 && todo) { s_next = (u32)__ffs((int)todo) - 1u; todo &= todo - 1u; load_view(s_next, nxt, nq, nL, nJ, nM); }
+    if (!R1 && todo) { s_next = (u32)__ffs((int)todo) - 1u; todo &= todo - 1u; if (SFS_VIEW_PREFETCH) load_view(s_next, nxt, nq, nL, nJ, nM); }
     if (mL) st_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R + s) * nl + vl, 0u, pol_first);   // consume: clear for reuse in two ticks
     if (mJ) st_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R + s) * nl + vl, 0u, pol_first);
     if (mM) st_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R + s) * nl + vl, 0u, pol_first);
@@ -456,64 +531,22 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
         else ml_dead(r, inc, kind == ML_LEFT, t, self, limit);
       }
       bool refute = false;
-      if (mL) { const u32 lt = mL - 1; witness(clock, lt); leave_intent(r, lt, self, sstate, refute, limit); }
+      if (mL) { const u32 key = mL - 1, lt = key >> 1; witness(clock, lt); leave_intent(r, lt, !(key & 1u), self, sstate, refute, limit); }
       if (mJ) { const u32 lt = mJ - 1; witness(clock, lt); join_intent(r, lt, limit); }
-      if (refute) {                                       // serf/base.rs:1470-1480 → broadcast_join(clock.time()), :381-397
-        const u32 T = clock; witness(clock, T);
-        join_intent(r, T, limit);
-        r.qjoin = T; r.txj = limit;
-      }
+      if (refute) cold_refute(r, clock, limit);
       if (!(r.flags & 1) && r.status != TY_NONE && (r.status != (orig.w[6] & 0xff) || r.st != orig.w[0])) r.leave_tick = t + 1;   // NodeIntent.wall_time (types/member.rs:32)
       Words mid;
       pack_words(r, mid);
       c.changed += differs(mid, orig) ? 1 : 0;
     }
     // ---------------- Phase E ----------------
-    if (op) {
-      if (op == OP_REJOIN && self && !up_r) {
-        r.inc += 1; r.mlstate = ML_ALIVE; r.qfrom = 0; r.txm = limit; r.deadline = 0; r.mask = 0;
-        sstate = SS_ALIVE;
-        node_join(r);
-      }
-      if (((op == OP_JOIN && up_r) || (op == OP_REJOIN && !up_r)) && self) {     // serf/api.rs:339-342 → serf/base.rs:381-397
-        const u32 T = clock; witness(clock, T);
-        join_intent(r, T, limit);
-        r.qjoin = T; r.txj = limit;
-      }
-      if (op == OP_LEAVE && up_r && self && sstate == SS_ALIVE) {                // serf/api.rs:422-449
-        sstate = SS_LEAVING;
-        const u32 T = clock; clock += 1;
-        bool rf = false;
-        leave_intent(r, T, true, sstate, rf, limit);
-        r.qleave = T; r.txl = limit;
-      }
-      if (op == OP_FORCE_LEAVE && up_r && op_slot == s) {                        // serf/base.rs:454-480
-        const u32 T = clock; witness(clock, T);
-        bool rf = false;
-        leave_intent(r, T, self, sstate, rf, limit);
-        r.qleave = T; r.txl = limit;
-        if (rf) { const u32 T2 = clock; witness(clock, T2); join_intent(r, T2, limit); r.qjoin = T2; r.txj = limit; }
-      }
-    }
+    if (op) cold_host_op(r, clock, sstate, op, op_slot == s, self, up_r, limit);
     if (op && !(r.flags & 1) && r.status != TY_NONE && r.leave_tick == 0) r.leave_tick = t + 1;
     if (up_s) {
       // ---------------- Phase T: reaper (serf/base.rs:483-610), suspicion timer, probe ----------------
-      if (p.reap_now) {
-        const u32 age = r.leave_tick ? (t + 1 - r.leave_tick) : 0;
-        if ((r.flags & 1) && r.leave_tick &&
-            ((r.status == ST_LEFT && age > p.tombstone_ticks) || (r.status == ST_FAILED && age > p.reconnect_ticks))) {
-          r.flags &= ~1u; r.status = TY_NONE; r.st = 0; r.leave_tick = 0;           // erase_node! :499-519
-        } else if (!(r.flags & 1) && r.status != TY_NONE && r.leave_tick && age > p.intent_ticks) {
-          r.status = TY_NONE; r.st = 0; r.leave_tick = 0;                           // reap_intents :1817-1822
-        }
-      }
+      if (p.reap_now) cold_reap(r, t, p.tombstone_ticks, p.reconnect_ticks, p.intent_ticks);
       if (r.mlstate == ML_SUSPECT && r.deadline != 0 && t >= r.deadline) ml_dead(r, r.inc, false, t, false, limit);
-      if (have_probe && !self && ptarget == p.subj[s] && ((p.down_mask >> s) & 1)) {
-        if (r.mlstate == ML_ALIVE || r.mlstate == ML_SUSPECT) {
-          if (r.mlstate == ML_ALIVE) atomicAdd((unsigned long long*)(p.row + 6), 1ull);
-          ml_suspect(r, r.inc, from_bucket(v), t, false, p.rules);
-        }
-      }
+      if (have_probe && !self && ptarget == p.subj[s] && ((p.down_mask >> s) & 1)) cold_probe_hit(p, r, v);
       // ---------------- Phase S ----------------
       const u32 mx = max(r.txl, max(r.txj, r.txm));
       if (mx) {
@@ -526,7 +559,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
         u32* const planeL = p.inbox_wr + (size_t)(KIND_LEAVE * R + s) * nl;
         u32* const planeJ = p.inbox_wr + (size_t)(KIND_JOIN * R + s) * nl;
         u32* const planeM = p.inbox_wr + (size_t)(KIND_ML * R + s) * nl;
-        const u32 vL = r.qleave + 1, vJ = r.qjoin + 1, vM = ml_key(r) + 1;
+        const u32 vL = leave_key(r.qleave, (r.flags & FLAG_QPRUNE) != 0) + 1, vJ = r.qjoin + 1, vM = ml_key(r) + 1;
         const u32 sL = min(r.txl, nt), sJ = min(r.txj, nt), sM = min(r.txm, nt);     // entry e goes to targets 0 .. min(tx_e, nt)-1
 #pragma unroll
         for (int k = 0; k < FMAX; ++k) {
@@ -551,11 +584,10 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
       const bool suspect = r.mlstate == ML_SUSPECT;
       c.pending += (!suspect && (queued || (watching && r.mlstate == ML_ALIVE))) ? 1 : 0;
       // (its own failed probe is a confirmation only while its bucket is not in the confirmer set and the set is not full)
-      const bool can_confirm = suspect && (u32)__popc(r.mask) - 1u < p.rules.k && !(r.mask & (1u << from_bucket(v)));
-      awake |= queued || (watching && (r.mlstate == ML_ALIVE || can_confirm));
+      awake |= queued || (watching && (r.mlstate == ML_ALIVE || (suspect && cold_can_confirm(p, r, v))));
       if (suspect && r.deadline != 0) { has_timer = true; mind = min(mind, r.deadline); }
     }
-    c.dsusp += ((up_s && r.mlstate == ML_SUSPECT) ? 1 : 0) - (susp_before ? 1 : 0);
+    dsusp += ((up_s && r.mlstate == ML_SUSPECT) ? 1 : 0) - (susp_before ? 1 : 0);
     pack_words(r, cur);
     {
       Words o2 = orig, c2 = cur;                           // storage image: record without budgets, budgets in the queue word
@@ -565,7 +597,10 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
     }
     if (TRACE) c.hash += rec_hash((u64)s * p.n_global + v, make_uint4(cur.w[0], cur.w[1], cur.w[2], cur.w[3]), make_uint4(cur.w[4], cur.w[5], cur.w[6], cur.w[7]));
     if (r.inc >= INC_LIMIT) *p.overflow = 1;
-    if (!R1) { cur = nxt; merge_q(cur, nq); mL = nL; mJ = nJ; mM = nM; }
+    if (!R1) {
+      if (!SFS_VIEW_PREFETCH && s_next < R) load_view(s_next, nxt, nq, nL, nJ, nM);
+      cur = nxt; merge_q(cur, nq); mL = nL; mJ = nJ; mM = nM;
+    }
     s = s_next;
   }
   const u64 ns2 = (u64)clock | (up_s ? NS_UP : 0) | ((u64)sstate << 40);
@@ -577,7 +612,9 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   // sticky otherwise (a view that was not visited may run a timer: it is found when its tile comes due)
   const u32 busy2 = (awake ? 1u : 0u) | (busy & 4u) | ((has_timer || (!visit_all && (busy & 8u))) ? 8u : 0u);
   if (busy2 != busy) p.busy[vl] = (u8)busy2;
-  c.awake += awake ? 1 : 0;
+  // The scheduler must know whether anybody stays awake.  A node that sent a packet this tick shows in the row's message count;
+  // the others (a watcher on probe duty, a queue that has no peer to go to, a transmit queued after the send phase) are rare.
+  if (awake && min(nt, max_tx) == 0) atomicAdd(p.sched + SCHED_AWAKE, 1u);
   return awake;
 }
 
@@ -585,6 +622,19 @@ __device__ __forceinline__ u32 warp_min(u32 v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// After a warp has processed its nodes of one tile: register the earliest running suspicion deadline in the timer wheel and add
+// the warp's net change of Suspect views to the CTA's shared counter (both rare outside suspicion waves: one vote each).
+__device__ __forceinline__ void note_timers(const TickParams& p, u32 tile, u32 mind, int dsusp, int* dsusp_s) {
+  if (__any_sync(0xffffffffu, mind != NO_DEADLINE)) {
+    const u32 wm = warp_min(mind);
+    if ((threadIdx.x & 31) == 0) atomicMin(p.tile_due + tile, wm);
+  }
+  if (__any_sync(0xffffffffu, dsusp != 0)) {
+    const u32 ws = warp_sum((u32)dsusp);                   // two's complement: the sum of the lanes' signed changes
+    if ((threadIdx.x & 31) == 0) atomicAdd(dsusp_s, (int)ws);
+  }
 }
 
 // A skipped tick (tick_is_idle): nothing can happen, so the only trace it leaves is its row — nothing delivered, nothing
@@ -614,7 +664,7 @@ __device__ __forceinline__ void scan_tiles(const TickParams& p, u8* hot_s, u32 t
 // LAST CTA to finish (ticket) completes the row and decides how long the cluster can sleep.
 // trace row: 0 packets, 1 edge_updates, 2 messages, 3 changed, 4 pending, (5 events, 6 suspects: direct), 7 hash
 template <bool TRACE>
-__device__ __forceinline__ void finish_tick(const TickParams& p, const Counters& c, u64 (*red)[BLOCK / 32]) {
+__device__ __forceinline__ void finish_tick(const TickParams& p, const Counters& c, u64 (*red)[BLOCK / 32], int dsusp_cta) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   __shared__ u32 last_s, due_min_s[BLOCK / 32];
   const u64 vals[8] = {c.packets, c.edges, (u64)c.kL + c.kJ + c.kM, c.changed, c.pending, c.kL, c.kJ, c.kM};
@@ -625,13 +675,8 @@ __device__ __forceinline__ void finish_tick(const TickParams& p, const Counters&
   }
   u64 hs = 0;
   if (TRACE) hs = warp_sum64(c.hash);
-  const u32 aw = warp_sum(c.awake);
-  const u32 ds = warp_sum((u32)c.dsusp);                  // two's complement: the sum of the lanes' signed changes
-  if (lane == 0) {
-    if (aw) atomicAdd(p.sched + SCHED_AWAKE, aw);
-    if (ds) atomicAdd(reinterpret_cast<unsigned long long*>(p.sched + SCHED_SUSPECTS), (unsigned long long)(long long)(int)ds);
-  }
-  __syncthreads();
+  __syncthreads();                                         // dsusp_cta is complete
+  if (threadIdx.x == 0 && dsusp_cta) atomicAdd(reinterpret_cast<unsigned long long*>(p.sched + SCHED_SUSPECTS), (unsigned long long)(long long)dsusp_cta);
   if (threadIdx.x < 8) {
     u64 s = 0;
 #pragma unroll
@@ -654,9 +699,9 @@ __device__ __forceinline__ void finish_tick(const TickParams& p, const Counters&
   const u64 suspects = *reinterpret_cast<volatile u64*>(p.sched + SCHED_SUSPECTS);
   // Can the next ticks do anything?  Not if nothing was sent (no mail), nobody stays awake (no queued transmit, no probe duty),
   // the user-event kernel reported nothing queued or sent (with injectors sleep_on is off): then the cluster sleeps until the earliest
-  // suspicion deadline or the next anti-entropy / reaper round (host operations are checked at launch).  Sharded runs never
-  // skip (the ranks would have to agree on the deadline).
-  const bool quiet = p.sleep_on && p.world == 1 && row[1] == 0 && row[2] == 0 && sched[SCHED_AWAKE] == 0 && sched[SCHED_UE_ACTIVITY] == 0;
+  // suspicion deadline or the next anti-entropy / reaper round (host operations are checked at launch).  Sharded runs: this is
+  // the rank's verdict; it travels with the row and the drain kernel combines the ranks' (all quiet, earliest deadline).
+  const bool quiet = p.sleep_on && row[1] == 0 && row[2] == 0 && sched[SCHED_AWAKE] == 0 && sched[SCHED_UE_ACTIVITY] == 0;
   u32 until = p.tick + 1;
   if (quiet) {                                             // uniform over the CTA
     u32 m = NO_DEADLINE;
@@ -674,8 +719,12 @@ __device__ __forceinline__ void finish_tick(const TickParams& p, const Counters&
   }
   if (threadIdx.x == 0) {
     row[4] = row[4] + suspects;                            // pending = awake views counted above + sleeping Suspect views
-    sched[SCHED_IDLE_UNTIL] = until;
-    if (p.host_idle_until) *p.host_idle_until = until;
+    if (p.world == 1) {
+      sched[SCHED_IDLE_UNTIL] = until;
+      if (p.host_idle_until) *p.host_idle_until = until;
+    } else {
+      sched[SCHED_LOCAL_QUIET] = quiet ? 1u : 0u; sched[SCHED_LOCAL_UNTIL] = until;
+    }
     sched[SCHED_AWAKE] = 0; sched[SCHED_UE_ACTIVITY] = 0; sched[SCHED_TICKET] = 0;
   }
 }
@@ -688,10 +737,12 @@ template <bool TRACE, int FMAX, bool SHARDED, bool R1, int MB>
 __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__ TickParams p) {
   __shared__ u8 hot_s[MAX_TILES_PER_CTA];
   __shared__ u64 red[8][BLOCK / 32];
+  __shared__ int dsusp_s;                                  // net change of the number of Suspect views at up nodes, this CTA
   __shared__ __align__(16) unsigned char xs_mem[SHARDED ? sizeof(XStage) : 16];
   XStage* xs = reinterpret_cast<XStage*>(xs_mem);
   if (gate_closed(p.gate, blockIdx.x == 0 && threadIdx.x == 0)) return;   // the run is over (uniform over the grid): this tick does not exist
   if (tick_is_idle(p.sched, p.tick, p.ev_begin, p.ev_end)) { write_idle_row<TRACE>(p); return; }   // nothing can happen in this tick (uniform)
+  if (threadIdx.x == 0) dsusp_s = 0;                       // ordered before its first use by the barrier after the tile scan
   Counters c = {};
   const bool kL = p.kinds_prev[KIND_LEAVE] != 0, kJ = p.kinds_prev[KIND_JOIN] != 0, kM = p.kinds_prev[KIND_ML] != 0;
   const u64 pol_first = policy_evict_first(), pol_last = policy_evict_last();
@@ -776,9 +827,11 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
             pre = prefetch_node<R1>(p, vl, kL, kJ, kM, pol_first);   // per-view masks are not carried through the list: the few active nodes read them again
           }
           u32 mind = NO_DEADLINE;
-          const bool pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, false, (hot_s[ti] & 2u) != 0, pol_first, pol_last, c, mind);
+          int dsusp = 0;
+          const bool pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, false, (hot_s[ti] & 2u) != 0, pol_first, pol_last, c, mind, dsusp);
           if (mark && pend) pend_s[g] = 1;
-          if (mind != NO_DEADLINE) atomicMin(p.tile_due + tile0 + ti, mind);
+          if (mind != NO_DEADLINE) atomicMin(p.tile_due + tile0 + ti, mind);      // the list mixes tiles: per-lane registration (few active nodes)
+          if (dsusp) atomicAdd(&dsusp_s, dsusp);
         }
         if (SHARDED) wrote_remote |= flush_xwarp(p, xs, false);
       }
@@ -805,12 +858,10 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
     const u32 vl = ((tile0 + i) << TILE_SHIFT) + threadIdx.x;
     bool pend = false;
     u32 mind = NO_DEADLINE;
-    if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, saturated, (hot_s[i] & 2u) != 0, pol_first, pol_last, c, mind);
+    int dsusp = 0;
+    if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, saturated, (hot_s[i] & 2u) != 0, pol_first, pol_last, c, mind, dsusp);
     if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + i] = 1;
-    if (__any_sync(0xffffffffu, mind != NO_DEADLINE)) {      // running timers of this warp's nodes: one registration per warp
-      const u32 wm = warp_min(mind);
-      if (lane == 0) atomicMin(p.tile_due + tile0 + i, wm);
-    }
+    note_timers(p, tile0 + i, mind, dsusp, &dsusp_s);
     if (SHARDED) wrote_remote |= flush_xwarp(p, xs, false);
     i = j;
   }
@@ -819,7 +870,8 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
     wrote_remote |= flush_xwarp(p, xs, true);
     if (wrote_remote) __threadfence_system();            // peer-window stores are performed before the publish kernel raises the flags
   }
-  finish_tick<TRACE>(p, c, red);
+  __syncthreads();
+  finish_tick<TRACE>(p, c, red, dsusp_s);
 }
 
 #ifndef SERFSIM_EMU   // the TMA pipeline is device-only (bulk copies, mbarriers); the host build of tests/emu uses the direct-load kernel
@@ -837,6 +889,7 @@ __global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constan
   __shared__ u64 red[8][BLOCK / 32];
   __shared__ __align__(8) u64 full_bar[2], empty_bar[2];
   __shared__ u32 col_base_s[2], col_ok_s[2];
+  __shared__ int dsusp_s;
   if (gate_closed(p.gate, blockIdx.x == 0 && threadIdx.x == 0)) return;
   if (tick_is_idle(p.sched, p.tick, p.ev_begin, p.ev_end)) { write_idle_row<TRACE>(p); return; }
   Counters c = {};
@@ -854,6 +907,7 @@ __global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constan
   const u32 ntile = tile0 < p.n_tiles ? min(p.tiles_per_cta, p.n_tiles - tile0) : 0;
   scan_tiles(p, hot_s, tile0, ntile, all_hot);
   if (threadIdx.x == 0) {
+    dsusp_s = 0;
     mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1);
     mbar_init(&empty_bar[0], BLOCK / 32); mbar_init(&empty_bar[1], BLOCK / 32);     // one arrival per consumer warp
     fence_proxy_async();
@@ -911,22 +965,21 @@ __global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constan
     const u32 vl = ((tile0 + ti) << TILE_SHIFT) + threadIdx.x;
     bool pend = false;
     u32 mind = NO_DEADLINE;
+    int dsusp = 0;
     if (vl < p.n_local) {
       Pre pre = {};
       pre.busy = p.busy[vl];
       pre.qw = p.qword[vl];          // 4 B per node, read directly (not worth a sixth bulk copy per stage)
-      pend = process_node<TRACE, FMAX, false, true, true>(p, sv, nullptr, vl, pre, kL, kJ, kM, mark, true, (hot_s[ti] & 2u) != 0, pol_first, pol_last, c, mind);
+      pend = process_node<TRACE, FMAX, false, true, true>(p, sv, nullptr, vl, pre, kL, kJ, kM, mark, true, (hot_s[ti] & 2u) != 0, pol_first, pol_last, c, mind, dsusp);
     }
     if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + ti] = 1;
-    if (__any_sync(0xffffffffu, mind != NO_DEADLINE)) {
-      const u32 wm = warp_min(mind);
-      if (lane == 0) atomicMin(p.tile_due + tile0 + ti, wm);
-    }
+    note_timers(p, tile0 + ti, mind, dsusp, &dsusp_s);
     if (BARSYNC) __syncthreads();
     else { __syncwarp(); if (lane == 0) mbar_arrive(&empty_bar[st]); }     // this warp is done reading stage `st`
   }
 
-  finish_tick<TRACE>(p, c, red);
+  __syncthreads();
+  finish_tick<TRACE>(p, c, red, dsusp_s);
 }
 #endif
 
@@ -991,7 +1044,7 @@ __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__
         else if (q.mlstate == ML_LEFT) ml_dead(r, q.inc, true, p.tick, self, p.rules.limit);
         else ml_suspect(r, q.inc, from_bucket(v), p.tick, self, p.rules);
         bool refute = false;
-        if (q.status == ST_LEFT) { witness(clock, q.st + 1); leave_intent(r, q.st + 1, self, sstate, refute, p.rules.limit, false); }
+        if (q.status == ST_LEFT) { witness(clock, q.st + 1); leave_intent(r, q.st + 1, false, self, sstate, refute, p.rules.limit, false); }
         else { witness(clock, q.st); join_intent(r, q.st, p.rules.limit, false); }
         if (refute) { const u32 T = clock; witness(clock, T); join_intent(r, T, p.rules.limit); r.qjoin = T; r.txj = p.rules.limit; }
         if (!(r.flags & 1) && r.status != TY_NONE && (r.status != (b0.z & 0xff) || r.st != a0.x)) r.leave_tick = p.tick + 1;
@@ -1058,13 +1111,15 @@ __global__ void publish_kernel(const __grid_constant__ PublishParams p) {
   if (p.gate && *p.gate) return;
   const u32 r = threadIdx.x;
   if (r < p.world && r != p.rank) {
+    const u32 me = p.loopback ? r : p.rank;                 // the slot this rank owns in the peer's control block
     u32* ctrl = p.peer_ctrl[r] + p.xpar * 16;
-    ctrl[p.rank] = p.send_count[r];
-    u64* sums = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(p.peer_ctrl[r]) + CTRL_SUMS_OFF) + ((size_t)p.xpar * 8 + p.rank) * 8;
+    ctrl[me] = p.send_count[r];
+    u64* sums = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(p.peer_ctrl[r]) + CTRL_SUMS_OFF) + ((size_t)p.xpar * 8 + me) * CTRL_FIELDS;
 #pragma unroll
     for (int i = 0; i < 8; ++i) sums[i] = p.row[i];          // this rank's counters of the tick: every rank sums them on the device
+    sums[8] = p.sched[SCHED_LOCAL_QUIET]; sums[9] = p.sched[SCHED_LOCAL_UNTIL];
     __threadfence_system();
-    st_release_sys(ctrl + 8 + p.rank, p.stamp);
+    st_release_sys(ctrl + 8 + me, p.stamp);
     p.send_count[r] = 0;
   }
 }
@@ -1082,8 +1137,22 @@ __global__ void __launch_bounds__(BLOCK) drain_kernel(const __grid_constant__ Dr
   // global trace row of this tick: my counters + the rows the peers published with their flags (acquired above)
   if (blockIdx.x == 0 && threadIdx.x < 8) {
     u64 s = p.my_row[threadIdx.x];
-    for (u32 src = 0; src < p.world; ++src) if (src != p.rank) s += __ldcg(p.sums + (size_t)src * 8 + threadIdx.x);
+    for (u32 src = 0; src < p.world; ++src) if (src != p.rank) s += __ldcg(p.sums + (size_t)src * CTRL_FIELDS + threadIdx.x);
     p.grow[threadIdx.x] = s;
+  }
+  // The ranks' scheduler verdicts: the cluster sleeps iff every rank is quiet, until the earliest of their deadlines.  Every rank
+  // computes the same value from the same published words and hands it to its HOST only (mapped memory): in sharded runs the
+  // device never skips a launched tick — a skipped exchange would let a fast rank reuse a window parity its peer is still
+  // draining — the hosts simply do not launch the ticks the cluster sleeps through (serfsim_run_until_converged), all alike.
+  if (blockIdx.x == 0 && threadIdx.x == 0 && p.sched) {
+    bool quiet = p.sleep_on && p.sched[SCHED_LOCAL_QUIET] != 0;
+    u32 until = p.sched[SCHED_LOCAL_UNTIL];
+    for (u32 src = 0; src < p.world; ++src) {
+      if (src == p.rank) continue;
+      quiet = quiet && __ldcg(p.sums + (size_t)src * CTRL_FIELDS + 8) != 0;
+      until = min(until, (u32)__ldcg(p.sums + (size_t)src * CTRL_FIELDS + 9));
+    }
+    if (p.host_idle_until) *p.host_idle_until = quiet ? max(until, p.tick + 1) : p.tick + 1;
   }
   // same dense / sparse decision as the tick kernel of this tick: in a dense tick the next tick processes every
   // tile anyway, so per-entry tile marking (millions of byte stores onto a few thousand flags) is skipped
@@ -1109,7 +1178,7 @@ __global__ void __launch_bounds__(BLOCK) drain_kernel(const __grid_constant__ Dr
           const u64 e1 = __ldcg(w + i + 1), e2 = __ldcg(w + i + 2);
           const u32 src = (u32)(e2 >> 32) - 1u;
           ByzEntries be{};
-          be.serf_lt = val1 - 1u; be.ml_inc = ((u32)(e1 >> 32) - 1u) >> 6;
+          be.serf_lt = kind == KIND_LEAVE ? (val1 - 1u) >> 1 : val1 - 1u; be.ml_inc = ((u32)(e1 >> 32) - 1u) >> 6;
           if (p.node_state[dl] & NS_UP) {
             const size_t iv = (size_t)s * p.stride + dl;
             Rec q;
@@ -1133,11 +1202,15 @@ __global__ void __launch_bounds__(BLOCK) drain_kernel(const __grid_constant__ Dr
 
 // Rows of ticks the host did not launch because the cluster sleeps through them (serfsim_run_until_converged): what
 // write_idle_row would have written.  rows = first of the n rows; the row before it belongs to the last executed / skipped tick.
-__global__ void fill_idle_rows_kernel(u64* rows, u32 n, const u32* sched, int trace) {
+__global__ void fill_idle_rows_kernel(u64* rows, u64* grow_rows, u32 n, const u32* sched, int trace) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   rows[(size_t)i * 8 + 4] = *reinterpret_cast<const u64*>(sched + SCHED_SUSPECTS);
   if (trace) rows[(size_t)i * 8 + 7] = *(rows - 8 + 7);
+  if (grow_rows) {                                         // sharded: the global rows repeat the global pending count / hash
+    grow_rows[(size_t)i * 8 + 4] = *(grow_rows - 8 + 4);
+    if (trace) grow_rows[(size_t)i * 8 + 7] = *(grow_rows - 8 + 7);
+  }
 }
 
 // watch[v]: bit s set iff subject s appears in node v's neighbour list — only such nodes can ever pick it as a probe
@@ -1323,8 +1396,8 @@ void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st) {
   if (trace) { if (small) launch_tick_v<true, 4>(p, grid, st); else launch_tick_v<true, 8>(p, grid, st); }
   else { if (small) launch_tick_v<false, 4>(p, grid, st); else launch_tick_v<false, 8>(p, grid, st); }
 }
-void launch_fill_idle_rows(u64* rows, u32 n, const u32* sched, bool trace, cudaStream_t st) {
-  if (n) SFS_LAUNCH((n + 127) / 128, 128, 0, st, fill_idle_rows_kernel)(rows, n, sched, trace ? 1 : 0);
+void launch_fill_idle_rows(u64* rows, u64* grow_rows, u32 n, const u32* sched, bool trace, cudaStream_t st) {
+  if (n) SFS_LAUNCH((n + 127) / 128, 128, 0, st, fill_idle_rows_kernel)(rows, grow_rows, n, sched, trace ? 1 : 0);
 }
 void launch_pushpull(const TickParams& p, const uint4* snap_rec, const u64* snap_node, bool trace, cudaStream_t st) {
   if (trace) SFS_LAUNCH(SFS_SMS * 8, BLOCK, 0, st, pushpull_kernel<true>)(p, snap_rec, snap_node);

@@ -120,7 +120,8 @@ struct TickParams {
   u32 pp_every, reap_every;   // push-pull / reaper periods in ticks (0 = off): such ticks are never skipped
   u32* host_idle_until;       // SCHED_IDLE_UNTIL mirrored into mapped pinned host memory: serfsim_run_until_converged does not even launch the ticks the cluster sleeps through
 };
-constexpr u32 SCHED_TICKET = 0, SCHED_IDLE_UNTIL = 1, SCHED_UE_ACTIVITY = 2, SCHED_AWAKE = 3, SCHED_SUSPECTS = 4 /* u64 */, SCHED_WORDS = 8;
+constexpr u32 SCHED_TICKET = 0, SCHED_IDLE_UNTIL = 1, SCHED_UE_ACTIVITY = 2, SCHED_AWAKE = 3, SCHED_SUSPECTS = 4 /* u64 */,
+              SCHED_LOCAL_QUIET = 6, SCHED_LOCAL_UNTIL = 7 /* sharded runs: this rank's verdict; the drain kernel combines the ranks' */, SCHED_WORDS = 8;
 constexpr u32 NO_DEADLINE = 0xffffffffu;
 // A tick is skipped (grid-uniform decision of its first instruction) when the last executed tick proved that nothing can happen
 // before SCHED_IDLE_UNTIL and the host scheduled no operation for it.
@@ -131,14 +132,18 @@ __device__ __forceinline__ bool tick_is_idle(const u32* sched, u32 tick, u32 ev_
 // Control block of a rank (one allocation, mapped into every peer): per exchange parity the entry counts and epoch flags
 // the peers write, then the peers' trace rows of that tick (the device-side sum of the per-tick counters).
 constexpr u32 CTRL_U32 = 2 * 16;                        // [parity][ counts[8] | flags[8] ]
-constexpr u32 CTRL_SUMS_OFF = CTRL_U32 * 4;             // byte offset of u64 sums[2][8][8]  ([parity][source rank][field])
-constexpr size_t CTRL_BYTES = CTRL_SUMS_OFF + 2 * 8 * 8 * sizeof(u64);
+constexpr u32 CTRL_SUMS_OFF = CTRL_U32 * 4;             // byte offset of u64 sums[2][8][CTRL_FIELDS]  ([parity][source rank][field])
+constexpr u32 CTRL_FIELDS = 10;                         // the 8 trace-row fields, then the rank's scheduler verdict: 8 = quiet (0 / 1), 9 = sleep until
+constexpr size_t CTRL_BYTES = CTRL_SUMS_OFF + 2 * 8 * CTRL_FIELDS * sizeof(u64);
 struct PublishParams {        // after the tick kernel: tell every peer how much was written and this rank's row, then raise its flag
   u32 world, rank, stamp, xpar;
   u32* send_count;            // [world] local, reset here
   u32* const* peer_ctrl;      // [world] peers' control blocks
   const u64* row;             // this rank's trace row of the tick (complete: the tick kernels precede the publish kernel)
   const u32* gate;            // sticky done word of the convergence gate (null: off)
+  const u32* sched;           // scheduler words: the rank's verdict (quiet, sleep until) goes out with its row
+  u32 loopback;               // profiling aid (serfsim_comm_loopback): every peer is this rank itself; counts / rows / flags go to the slot of the
+                              // "peer" they are addressed to instead of this rank's own slot
 };
 
 struct DrainParams {
@@ -161,10 +166,12 @@ struct DrainParams {
   // device-side sum of the tick's trace row over all ranks: grow[i] = my_row[i] + Σ peers' published rows
   const u64* my_row; const u64* sums; u64* grow;
   const u32* gate;
+  const u32* sched; u32* host_idle_until;   // the ranks' verdicts combined: every rank hands the same "sleep until" tick to its host
+  u32 tick, sleep_on;
 };
 
 void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st);
-void launch_fill_idle_rows(u64* rows, u32 n, const u32* sched, bool trace, cudaStream_t st);
+void launch_fill_idle_rows(u64* rows, u64* grow_rows, u32 n, const u32* sched, bool trace, cudaStream_t st);
 void launch_pushpull(const TickParams& p, const uint4* snap_rec, const u64* snap_node, bool trace, cudaStream_t st);
 void launch_drain(const DrainParams& p, cudaStream_t st);
 void launch_publish(const PublishParams& p, cudaStream_t st);

@@ -187,6 +187,30 @@ def byzantine_injectors(n=100_000, degree=16, fanout=4, frac=0.01, delta=2, seed
                     max_ticks=4000, byzantine=byz, delta=delta)
 
 
+def remove_failed_node_prune(n=3, seed=1, at=40):
+    """The reference's `serf_remove_failed_node_prune` (serf/base/tests/serf/remove.rs:95-165) as a scenario: node 1 crashes, is
+    detected Failed (short timers), then node 0 calls remove_failed_node_prune(node 1): the leave intent carries `prune` and every
+    node that accepts it erases the member — the survivors end with n - 1 members."""
+    return Scenario(f"prune_{n}", n, 1, full_mesh_graph(n) if n <= 512 else random_regular_graph(n, 16, 7), [1],
+                    [(0, Op.FAIL, 1, 0), (at, Op.FORCE_LEAVE_PRUNE, 0, 0)],
+                    dict(fanout=min(3, n - 1), seed=seed, suspicion_mult=2, suspicion_max_timeout_mult=2, probe_interval_ticks=1), max_ticks=2000)
+
+
+def fuzz_prune(seed, n=None, slots=None):
+    """fuzz() with most force-leave operations pruning (Serf::remove_failed_node_prune) and a few more of them."""
+    sc = fuzz(seed, n=n, slots=slots)
+    sc.name = f"fuzz_prune_{seed}"
+    rng = np.random.Generator(np.random.Philox(seed + 424242))
+    used = {(t, node) for (t, _, node, _) in sc.ops}
+    sc.ops = [(t, int(Op.FORCE_LEAVE_PRUNE) if (op == Op.FORCE_LEAVE and rng.random() < 0.7) else op, node, s) for (t, op, node, s) in sc.ops]
+    for _ in range(int(rng.integers(1, 6))):
+        t, node, s = int(rng.integers(0, 60)), int(rng.integers(0, sc.n)), int(rng.integers(0, sc.slots))
+        if (t, node) not in used:
+            used.add((t, node))
+            sc.ops.append((t, int(Op.FORCE_LEAVE_PRUNE), node, s))
+    return sc
+
+
 def fuzz_features(seed, n=None, slots=None):
     """fuzz() plus the optional subsystems on top: tracked user events fired at random ticks / origins (possibly with
     equal content), and a random set of byzantine injectors — on top of whatever fuzz() drew (push-pull rounds, reaper, probing)."""

@@ -40,6 +40,7 @@ class Op(enum.IntEnum):                # SERFSIM_OP_*
     FAIL = 4
     REJOIN = 5
     USER_EVENT = 6                     # Serf::user_event, serf/api.rs:241-299
+    FORCE_LEAVE_PRUNE = 7              # Serf::remove_failed_node_prune, serf/api.rs:513 (LeaveMessage.prune: receivers erase the member)
 
 
 class Config(C.Structure):             # serfsim_config_t
@@ -146,6 +147,7 @@ PRODUCT_ONLY = {
     "serfsim_comm_export": (C.c_int, [_vp, _vp]),
     "serfsim_comm_connect": (C.c_int, [_vp, _vp]),
     "serfsim_comm_set_hooks": (C.c_int, [_vp, BARRIER_FN, ALLREDUCE_FN, _vp]),
+    "serfsim_comm_loopback": (C.c_int, [_vp]),
 }
 
 _LIB = None
@@ -260,6 +262,9 @@ class GossipSim:
 
     def remove_failed_node(self, origin, slot, tick=0):   # Serf::remove_failed_node (force_leave)
         self.inject(tick, Op.FORCE_LEAVE, origin, slot)
+
+    def remove_failed_node_prune(self, origin, slot, tick=0):   # Serf::remove_failed_node_prune
+        self.inject(tick, Op.FORCE_LEAVE_PRUNE, origin, slot)
 
     def fail(self, node, tick=0):
         self.inject(tick, Op.FAIL, node)
@@ -401,6 +406,12 @@ class GossipSim:
         blobs = b"".join(all_gather_bytes(blob.raw))
         assert len(blobs) == size * self.cfg.world_size
         self._check(self._lib.serfsim_comm_connect(self._h, blobs))
+
+
+    def connect_loopback(self):
+        """Profiling aid: a world_size = W handle (rank 0) that exchanges with itself — the per-GPU work of a W-rank run on
+        one GPU (tools/loopback_profile.py).  Its simulation results are meaningless."""
+        self._check(self._lib.serfsim_comm_loopback(self._h))
 
 
 # ---- synthetic topologies (BASELINE.json configs) -------------------------------------

@@ -107,6 +107,21 @@ def test_sharded_failure_detection():
     check(scenarios.random_graph_fail(2000, 16, 3, seed=2), 2, suspicion_mult=2, suspicion_max_timeout_mult=2, probe_interval_ticks=2)
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_cluster_sleeps_through_the_suspicion_timers(world, monkeypatch):
+    """LAN timers: ~30 ticks in which every shard only waits for suspicion deadlines.  The ranks publish their scheduler verdicts
+    with their rows, every rank derives the same "sleep until" tick, and the hosts do not launch those ticks (probe 17 counts
+    them) — rows, records and clocks still equal the oracle's."""
+    import ctypes as C
+    from emu_lib import lib
+    L = lib()
+    L.emu_probe.restype = C.c_ulong
+    L.emu_probe_reset()
+    monkeypatch.setenv("SERFSIM_CHUNK", "4")
+    check(scenarios.dissemination_storm(3000, 12, 3, slots=2, seed=3, with_fail=True), world)
+    assert L.emu_probe(17) > 20 * world            # both trace modes, every rank
+
+
 @pytest.mark.parametrize("seed", [7, 9, 12])
 def test_sharded_fuzz(seed):
     check(scenarios.fuzz(seed, n=600, slots=4), 2, push_pull_interval_ticks=0)
@@ -340,3 +355,13 @@ def test_sharded_user_events_with_push_pull(world):
 
 def test_sharded_byzantine_with_push_pull():
     check_byzantine(scenarios.byzantine_injectors(2400, 12, 3, 0.05, seed=5), 3, push_pull_interval_ticks=6)
+
+
+def test_loopback_profiling_aid_runs():
+    """serfsim_comm_loopback: a world-4 handle exchanging with itself (tools/loopback_profile.py).  Its results are meaningless by
+    construction; what is checked is that the sharded kernels run to quiescence through the windows without an error."""
+    sc = scenarios.random_graph_leave(4000, 12, 3, seed=2, slots=1)
+    g = sc.build(emu_sim, rank=0, world_size=4, trace=0)
+    g.connect_loopback()
+    ticks, ok = g.run_until_converged(400)
+    assert ok and g.stats()["edge_updates"] > 0

@@ -98,6 +98,23 @@ def test_compaction_path_is_taken_and_exact():
     assert_same(f, o, sc.slots, with_hash=False)
 
 
+def test_remove_failed_node_prune_reference_scenario():
+    """serf_remove_failed_node_prune (serf/base/tests/serf/remove.rs:95-165): after the pruning force-leave the survivors no
+    longer list the failed node (`wait_until_num_nodes(2, ..)` in the reference)."""
+    for n in (3, 40):
+        sc = scenarios.remove_failed_node_prune(n)
+        f, o = run_both(sc)
+        st = f.member_status(0)
+        assert (np.delete(st, 1) == MemberStatus.NONE).all(), st          # erased from every survivor's member table
+        tr = o.tick_trace()
+        assert tr["pending"][sc.ops[1][0] - 1] == 0                       # the failure had been detected and had settled before the prune
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_prune(seed):
+    run_both(scenarios.fuzz_prune(seed))
+
+
 def test_sleeping_views_timer_wheel_and_idle_ticks():
     """A crash with the memberlist LAN timers: the suspicion timers run for ~100 ticks in which nothing else happens.  Views that
     only wait for their timer sleep (SFS_PROBE 5 counts the views a visited node left asleep), their tiles are woken by the

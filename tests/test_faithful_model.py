@@ -29,7 +29,7 @@ def _faithful():
     return L
 
 
-def _run(seed, overlap):
+def _run(seed, overlap, prune=False):
     rng = np.random.default_rng(seed)
     n, deg, fan, rm = int(rng.integers(60, 200)), int(rng.integers(4, 10)), int(rng.integers(2, 5)), int(rng.integers(2, 5))
     row_ptr, col = random_regular_graph(n, deg, seed + 3)
@@ -41,6 +41,8 @@ def _run(seed, overlap):
         t = int(rng.integers(0, 5))
         for _ in range(int(rng.integers(1, 4))):
             kind = Op.JOIN if rng.random() < 0.4 else Op.FORCE_LEAVE
+            if prune and kind == Op.FORCE_LEAVE and rng.random() < 0.6:
+                kind = Op.FORCE_LEAVE_PRUNE                # Serf::remove_failed_node_prune: receivers erase the member
             node = int(subjects[s]) if kind == Op.JOIN else int(rng.integers(0, n))
             if (t, node) not in used:
                 used.add((t, node)); ops.append((t, int(kind), node, s))
@@ -70,7 +72,9 @@ def _run(seed, overlap):
         st_b, lt_b = o.member_status(s), o.status_ltime(s)
         for v in range(n):
             st, lt = C.c_uint8(), C.c_uint64()
-            assert L.faithful_view(f, v, int(subjects[s]), C.byref(st), C.byref(lt))
+            if not L.faithful_view(f, v, int(subjects[s]), C.byref(st), C.byref(lt)):
+                assert prune                               # the member is not in this node's table: erased by a pruning leave intent
+                st.value, lt.value = 0, 0                  # the tick model reports MemberStatus::None, status time 0 for an unknown member
             diffs += int((st.value, lt.value) != (int(st_b[v]), int(lt_b[v])))
     diffs += sum(int(L.faithful_clock(f, v) != int(clk[v])) for v in range(n))
     L.faithful_free(f)
@@ -81,6 +85,21 @@ def _run(seed, overlap):
 def test_tick_model_equals_literal_nodes_when_intents_do_not_overlap(seed):
     diffs, total = _run(seed, overlap=False)
     assert diffs == 0, f"{diffs} of {total} (status, status_time, clock) values differ from the literal multi-node run"
+
+
+def test_prune_against_literal_nodes():
+    """remove_failed_node_prune (serf/api.rs:513): LeaveMessage.prune travels with the intent and every receiver that accepts it
+    erases the member (handle_prune, serf/base.rs:1628-1653).  Operations far enough apart that no two different leave intents
+    about one subject meet.  One modelling deviation remains and is measured here (DESIGN rules P-1 / P-2): in the reference an
+    erased member is unknown again, so the NEXT copy of the same pruning intent is buffered as a fresh intent and re-queued with a
+    fresh budget.  The tick model delivers one reduced inbox word per (node, subject, tick): when two copies reach a node in the
+    tick of its first reception it sees the second one a tick later than the literal node does (or never, if no further copy
+    comes), so a few re-queues start a tick later."""
+    tot_d = tot = exact = 0
+    for seed in range(12):
+        d, t = _run(200 + seed, overlap=False, prune=True)
+        tot_d += d; tot += t; exact += d == 0
+    assert exact >= 6 and tot_d <= 0.002 * tot, (exact, tot_d, tot)       # measured: 8 of 12 scenarios exact, 4 of 5532 values differ (0.07 %)
 
 
 def test_overlapping_same_kind_intents_deviation_is_small():

@@ -117,6 +117,22 @@ def test_fuzz(seed):
     run_both(sc)
 
 
+def test_remove_failed_node_prune_reference_scenario():
+    """serf_remove_failed_node_prune (serf/base/tests/serf/remove.rs:95-165) and the same on a 20 K-node random graph: after the
+    pruning force-leave no survivor lists the failed node any more."""
+    for n in (3, 40, 20_000):
+        g, o, ticks = run_both(scenarios.remove_failed_node_prune(n, at=40 if n < 1000 else 120))
+        st = g.member_status(0)
+        assert (np.delete(st, 1) != MemberStatus.NONE).sum() <= (0 if n < 1000 else 3)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_prune(seed):
+    sc = scenarios.fuzz_prune(seed)
+    sc.max_ticks = 1500
+    run_both(sc)
+
+
 def test_stepwise_equals_batched_and_inject_midway():
     sc = scenarios.random_graph_leave(30_000, 16, 3, seed=8, slots=2)
     g, o = sc.build(gpu_sim, trace=1), sc.build(oracle_sim, trace=1)
