@@ -678,7 +678,7 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
   CUB(cudaMemcpy(h->d_subj, h->subj.data(), h->R * 4, cudaMemcpyHostToDevice));
   {
     const char* e = getenv("SERFSIM_MINB");
-    h->ctas_per_sm = (h->R == 1) ? ((e && atoi(e) == 5) ? 5 : tick_ctas_per_sm_r1()) : 3;
+    h->ctas_per_sm = (h->R == 1) ? ((e && atoi(e) == 5) ? 5 : tick_ctas_per_sm_r1()) : tick_ctas_per_sm_rn();
   }
   h->grid = tick_grid_size(h->count, h->ctas_per_sm);
   {

@@ -34,6 +34,9 @@ constexpr int BLOCK = 256;
 #ifndef SFS_MB_R1
 #define SFS_MB_R1 4                         // resident CTAs per SM of the single-slot kernels (64 registers per thread)
 #endif
+#ifndef SFS_MB_RN
+#define SFS_MB_RN 3                         // resident CTAs per SM of the multi-slot kernels (80 registers per thread)
+#endif
 constexpr u32 TILE_SHIFT = 8;              // one tile = one CTA pass = 256 nodes
 constexpr u32 MAX_TILES_PER_CTA = 1024;
 static_assert((1u << TILE_SHIFT) == BLOCK, "tile = block");
@@ -1342,6 +1345,7 @@ __global__ void __launch_bounds__(BLOCK) summary_kernel(const uint4* rec, const 
 }  // namespace
 
 int tick_ctas_per_sm_r1() { return SFS_MB_R1; }
+int tick_ctas_per_sm_rn() { return SFS_MB_RN; }
 int tick_grid_size(u32 n_local, int ctas_per_sm) {
   static int sms = 0;
   if (!sms) {
@@ -1387,9 +1391,9 @@ static void launch_tick_v(const TickParams& p, int grid, cudaStream_t st) {
 #endif
   static int mb5 = -1;
   if (mb5 < 0) { const char* e = getenv("SERFSIM_MINB"); mb5 = (e && atoi(e) == 5) ? 1 : 0; }
-  if (sharded) { if (r1) SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, true, true, SFS_MB_R1>)(p); else SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, true, false, 3>)(p); }
+  if (sharded) { if (r1) SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, true, true, SFS_MB_R1>)(p); else SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, true, false, SFS_MB_RN>)(p); }
   else if (r1) { if (mb5) SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, false, true, 5>)(p); else SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, false, true, SFS_MB_R1>)(p); }
-  else SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, false, false, 3>)(p);
+  else SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, false, false, SFS_MB_RN>)(p);
 }
 void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st) {
   const bool small = p.fanout <= 4;          // the common fan-outs (3, 4) get the 4-wide target array

@@ -183,6 +183,7 @@ void launch_state_hash(const uint4* rec, const u32* qword, const u64* node_state
 void launch_summary(const uint4* rec, const u32* qword, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 R, const u32* subj_dev, u64* out /*[2 + 2*R + 2]*/, cudaStream_t st);
 int tick_grid_size(u32 n_local, int ctas_per_sm);
 int tick_ctas_per_sm_r1();
+int tick_ctas_per_sm_rn();
 void launch_compute_watch(const u32* row_ptr, const u32* col, const u32* subj_dev, u32 R, u32 first, u32 n_local, u16* watch, cudaStream_t st);
 void launch_apply_watch(const u16* watch, u32 n_local, u8* busy, u8* hot_static, cudaStream_t st);
 
