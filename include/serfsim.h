@@ -283,6 +283,38 @@ int    serfsim_comm_set_hooks(serfsim_t* h, serfsim_barrier_fn barrier, serfsim_
  * profilable with ncu on a single GPU.  The simulation results of such a handle are meaningless.  No hooks are needed. */
 int    serfsim_comm_loopback(serfsim_t* h);
 
+/* ---- wire codec: serf's TLV encoding of the messages of this path ----------------------------------
+ * Join / Leave / PushPull exactly as `types/join.rs:107-158`, `types/leave.rs:121-195`, `types/push_pull.rs:319-450` and the
+ * envelope of `types/message.rs:397-428, 507-692` lay them out, ids being u64 (`JoinMessageU64` .. of `types/tests.rs:49-62`).
+ * The primitives those files import from the external crate memberlist_core::proto (tag byte, varint, wire types) are restated
+ * in serf_b200/csrc/wire.cuh and are UNPINNED at byte level: the crate is not in the reference tree and the tree holds no golden
+ * bytes, only the round-trip property (`types/tests.rs:8-25`), which tests/test_wire.py restates. */
+#define SERFSIM_WIRE_LEAVE     1u  /* MessageType tags, `types/message.rs:17-19` */
+#define SERFSIM_WIRE_JOIN      2u
+#define SERFSIM_WIRE_PUSH_PULL 3u
+typedef struct { uint32_t type /* SERFSIM_WIRE_JOIN | _LEAVE */, prune /* LeaveMessage.prune */; uint64_t ltime, id; } serfsim_wire_intent_t;
+typedef struct {
+  uint64_t ltime, event_ltime, query_ltime;         /* `types/push_pull.rs:24-80` */
+  uint32_t n_status, n_left;                         /* encode: entries; decode: in = capacity of the arrays, out = entries */
+  uint32_t n_events_skipped, pad;                    /* decode: `events` entries present in the message (skipped: not on this path) */
+  uint64_t* status_ids; uint64_t* status_ltimes;     /* status_ltimes: IndexMap<Id, LamportTime> in insertion order */
+  uint64_t* left_ids;                                /* left_members: IndexSet<Id> */
+} serfsim_wire_push_pull_t;
+size_t serfsim_wire_encoded_len_intent(const serfsim_wire_intent_t* m);                   /* encoded_message_len, `types/message.rs:484-491` */
+int serfsim_wire_encode_intent(const serfsim_wire_intent_t* m, uint8_t* buf, size_t cap, size_t* len);         /* encode_message; *len = needed size even on failure */
+int serfsim_wire_encode_push_pull(const serfsim_wire_push_pull_t* m, uint8_t* buf, size_t cap, size_t* len);
+int serfsim_wire_message_type(const uint8_t* buf, size_t len, uint32_t* type);            /* decode_message's dispatch, `types/message.rs:507-692` */
+int serfsim_wire_decode_intent(const uint8_t* buf, size_t len, serfsim_wire_intent_t* out);
+int serfsim_wire_decode_push_pull(const uint8_t* buf, size_t len, serfsim_wire_push_pull_t* out);
+/* SerfDelegate::local_state (`serf/delegate.rs:386-425`) of EVERY node of the shard, encoded on the device: message i occupies
+ * out[offsets[i] .. offsets[i + 1]).  offsets has count + 1 entries and is always filled; if out is NULL or cap < *total the call
+ * fails after setting *total.  A virtual node's member table holds the tracked subjects it knows. */
+int serfsim_wire_local_state_batch(serfsim_t* h, uint8_t* out, size_t cap, uint64_t* offsets, size_t* total);
+/* The inverse batch on the device: n concatenated push-pull messages → per message the Lamport clock and up to `cap`
+ * (id, status_time) entries (arrays [n][cap]) with their count. */
+int serfsim_wire_decode_batch(serfsim_t* h, const uint8_t* buf, const uint64_t* offsets, uint32_t n, uint32_t cap,
+                              uint64_t* ltime, uint64_t* ids, uint64_t* status_ltimes, uint32_t* n_status);
+
 #ifdef __cplusplus
 }
 #endif

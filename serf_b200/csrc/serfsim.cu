@@ -582,6 +582,17 @@ int getter(serfsim* h, u32 slot, int what, void* out, size_t elem) {
 
 }  // namespace
 
+// hooks for wire_codec.cu (the other translation unit behind the C ABI)
+namespace sfs {
+struct WireView { const uint4* rec; const u32* qword; const u64* node_state; const uint4* ue_state; const u32* subj; u32 n_local, stride, R; cudaStream_t stream; };
+int serfsim_fail(int code, const char* msg) { return fail(code, msg); }
+int serfsim_wire_view(const serfsim* h, WireView* out) {
+  if (!h) return fail(SERFSIM_E_INVAL, "null handle");
+  *out = WireView{h->d_rec, h->d_qword, h->d_node, h->ue_table.n ? h->d_ue_state : nullptr, h->d_subj, h->count, h->stride, h->R, h->stream};
+  return 0;
+}
+}  // namespace sfs
+
 // =====================================================================================
 // C ABI
 // =====================================================================================
@@ -700,11 +711,14 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
     if (cfg->world_size > 8) return bail(fail(SERFSIM_E_INVAL, "world_size > 8"));
     double factor = 1.25;
     if (const char* e = getenv("SERFSIM_WIN_FACTOR")) factor = atof(e);
-    double cap = (double)h->shard_size * cfg->fanout * h->R * 3.0 * factor / cfg->world_size + 4096.0;
+    // … plus the blocks the warps of the tick kernel reserve and do not fill (flush_xwarp: up to two 32-entry blocks per warp and peer)
+    const double pad = (double)tick_grid_size(h->count, h->ctas_per_sm) * 8.0 * 64.0;
+    double cap = (double)h->shard_size * cfg->fanout * h->R * 3.0 * factor / cfg->world_size + 4096.0 + pad;
     h->win_cap = (u32)std::min(cap, 4.0e9);
     h->win_cap_base = h->win_cap;
     for (int par = 0; par < 2; ++par) {
       CUB(cudaMalloc(&h->d_win_data[par], (size_t)cfg->world_size * h->win_cap * 8));
+      CUB(cudaMemset(h->d_win_data[par], 0, (size_t)cfg->world_size * h->win_cap * 8));      // windows read as zeros wherever nothing was written
       CUB(cudaMalloc(&h->d_peer_data[par], sizeof(u64*) * 8));
     }
     CUB(cudaMalloc(&h->d_ctrl, CTRL_BYTES));
@@ -1115,6 +1129,7 @@ int serfsim_set_user_events(serfsim_t* h, uint32_t n_events, const uint32_t* con
       for (int par = 0; par < 2; ++par) {
         cudaFree(h->d_win_data[par]); h->d_win_data[par] = nullptr;
         CU(cudaMalloc(&h->d_win_data[par], (size_t)h->cfg.world_size * want * 8));
+        CU(cudaMemset(h->d_win_data[par], 0, (size_t)h->cfg.world_size * want * 8));
       }
       h->win_cap = want;
     }

@@ -191,9 +191,17 @@ __device__ __forceinline__ void deliver(const TickParams& p, XStage* xs, u32* pl
   }
 }
 
-// Copy the warp's staged entries into the peers' windows (whole warp, convergent).  force = false: only buffers that make
-// a full warp-wide store; force = true (end of the kernel): everything.
-__device__ __forceinline__ bool flush_xwarp(const TickParams& p, XStage* xs, bool force) {
+// Copy the warp's staged entries into the peers' windows (whole warp, convergent), one 32-entry BLOCK (256 contiguous bytes over
+// NVLink) at a time.  A block is reserved in the peer's window with one atomic on this rank's per-peer counter — and the
+// reservation for the NEXT block is issued right after a block has been written, by the lane whose index is the peer's rank,
+// which keeps the result in its own register (`resv`): the atomic's round trip is off the critical path, the next flush finds
+// the address waiting.  (Reserving at flush time stalled every flush for the atomic's latency on a counter the whole grid
+// hammers: 17 % of the sharded kernel's stall samples, profiles/r2g_hot_loop8_tick13.txt.)  Blocks that stay partly or wholly
+// unwritten — the last one of a warp, a reservation nobody used — read as zeros at the receiver: the drain kernel skips zero
+// entries and clears every entry it consumes, so a window is all zeros again before it is written next.
+// force = false: full blocks only; force = true (end of the kernel): everything.
+constexpr u32 NO_BLOCK = 0xffffffffu;
+__device__ __forceinline__ bool flush_xwarp(const TickParams& p, XStage* xs, bool force, u32& resv) {
   const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   __syncwarp();
   bool wrote = false;
@@ -203,17 +211,30 @@ __device__ __forceinline__ bool flush_xwarp(const TickParams& p, XStage* xs, boo
     if (staged == 0 || (!force && staged < XW_FLUSH)) continue;
     if (staged > xcap(p)) wrote = true;        // the excess went straight through
     const u32 n = min(staged, xcap(p));
-    u32 base = 0;
-    if (lane == 0) base = atomicAdd(p.send_count + sh, n);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    const u64* src = xs->buf + wid * XW_TOTAL + xseg(p, sh);
+    u64* src = xs->buf + wid * XW_TOTAL + xseg(p, sh);
     u64* dst = p.win_data[sh] + (size_t)p.rank * p.win_cap;
-    for (u32 i = lane; i < n; i += 32) {
-      if (base + i < p.win_cap) { dst[base + i] = src[i]; wrote = true; }
-      else *p.overflow = 2;
+    u32 done = 0;
+    while (n - done >= XW_FLUSH || (force && done < n)) {
+      const u32 chunk = min(XW_FLUSH, n - done);
+      u32 base = __shfl_sync(0xffffffffu, resv, sh);
+      if (base == NO_BLOCK) {                  // first block for this peer: reserve now
+        if (lane == sh) base = atomicAdd(p.send_count + sh, XW_FLUSH);
+        base = __shfl_sync(0xffffffffu, base, sh);
+      }
+      if (lane < chunk) {
+        if (base + lane < p.win_cap) dst[base + lane] = src[done + lane];
+        else *p.overflow = 2;
+      }
+      wrote = true;
+      done += chunk;
+      if (lane == sh) resv = force ? NO_BLOCK : atomicAdd(p.send_count + sh, XW_FLUSH);   // not waited for here
     }
+    const u32 rem = n - done;                  // < 32 entries stay staged: move them to the front
+    u64 keep = 0;
+    if (lane < rem) keep = src[done + lane];
     __syncwarp();
-    if (lane == 0) xs->cnt[wid][sh] = 0;
+    if (lane < rem) src[lane] = keep;
+    if (lane == 0) xs->cnt[wid][sh] = rem;
   }
   __syncwarp();
   return wrote;
@@ -327,8 +348,12 @@ __device__ __forceinline__ bool node_active(const TickParams& p, const Pre& x, b
 
 // ---- cold paths of a node's tick, kept out of line: host operations, the reaper round and the SWIM probe run for a handful of
 // nodes per tick (or for all of them once in a long while); inlined, their temporaries (a second Philox block, the operation
-// scan) raise the register demand of the path every node takes and make it spill.
-#ifdef SERFSIM_EMU
+// scan) raise the register demand of the path every node takes and make it spill.  They are called on COPIES of the view and
+// the node's scalars: a variable whose address is passed to a call lives in local memory for its whole lifetime, and the
+// hot path's record must stay in registers (measured: 4.6 extra L2 sectors per node and +25 % per plateau tick otherwise).
+#if defined(SFS_COLD_INLINE)
+#define SFS_COLD __forceinline__               // A/B: everything inline again
+#elif defined(SERFSIM_EMU)
 #define SFS_COLD __attribute__((noinline))
 #else
 #define SFS_COLD __noinline__
@@ -397,8 +422,8 @@ __device__ SFS_COLD void cold_refute(Rec& r, u32& clock, u32 limit) {
   r.qjoin = T; r.txj = limit;
 }
 // Is a watcher's own failed probe still a confirmation (its bucket not in the confirmer set, the set not full)?
-__device__ SFS_COLD bool cold_can_confirm(const TickParams& p, const Rec& r, u32 v) {
-  return (u32)__popc(r.mask) - 1u < p.rules.k && !(r.mask & (1u << from_bucket(v)));
+__device__ SFS_COLD bool cold_can_confirm(u32 k, u32 mask, u32 v) {
+  return (u32)__popc(mask) - 1u < k && !(mask & (1u << from_bucket(v)));
 }
 
 // Returns true when the node stays awake (queued transmits, probe duty): that keeps its tile hot for the next tick.
@@ -448,7 +473,8 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   const bool timers_due = due && (busy & 8u);
   if (!TRACE && !STAGED && !node_active(p, pre, due)) return false;
   if (STAGED && !TRACE && !((busy & 7u) || (mL | mJ | mM) || p.reap_now || timers_due)) return false;
-  const u32 wmask = (busy & 4) ? (u32)p.watch[vl] : 0u;     // subjects this node can probe (it has them as neighbours)
+  // (the watcher mask — subjects this node can probe, it has them as neighbours — is re-read where a watcher needs it: a handful of nodes)
+#define SFS_WMASK() ((busy & 4u) ? (u32)p.watch[vl] : 0u)
   if (!upfront) { load_node(); if (R1) load_rec0(); }
 
   u32 clock = (u32)ns;
@@ -458,7 +484,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
 
   // host operation for this node (at most one per tick; the mark kernel set bit 1 of the busy byte)
   u32 op = 0, op_slot = 0;
-  if (busy & 2) op = cold_find_op(p, v, op_slot);
+  if (busy & 2) { u32 slot_tmp = 0; op = cold_find_op(p, v, slot_tmp); op_slot = slot_tmp; }
   bool up_s = up_r;
   if (op == OP_FAIL) up_s = false;
   if (op == OP_REJOIN) up_s = true;
@@ -466,7 +492,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   // SWIM probe target of this round (only matters while some tracked subject is down)
   bool have_probe = false;
   u32 ptarget = 0;
-  if (up_s && wmask && p.probe_every && p.down_mask && ((t + v) % p.probe_every) == 0 && deg) {
+  if (up_s && (busy & 4u) && p.probe_every && p.down_mask && ((t + v) % p.probe_every) == 0 && deg) {
     ptarget = (STAGED && sv.col_staged) ? 0u : cold_probe_target(p, v, row0, deg);
     if (STAGED && sv.col_staged) {
       u32 w[4];
@@ -486,7 +512,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   // otherwise those with mail, queued transmits or probe duty (a watcher's view of a subject that is down).
   const u32 all_views = (R >= 32u) ? 0xffffffffu : ((1u << R) - 1u);
   const bool visit_all = R1 || TRACE || p.reap_now || (busy & 2u) || timers_due || !p.sleep_on;
-  u32 todo = visit_all ? all_views : ((pre.mailmask | pre.qmask | (p.probe_every ? (wmask & p.down_mask) : 0u)) & all_views);
+  u32 todo = visit_all ? all_views : ((pre.mailmask | pre.qmask | (p.probe_every ? (SFS_WMASK() & p.down_mask) : 0u)) & all_views);
   if (!R1) SFS_COUNT(5, R - (u32)__popc(todo));             // views left asleep by a visited node
 
   // multi-slot runs: the record and inbox words of the next view to visit are requested while the current one is processed
@@ -536,20 +562,20 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
       bool refute = false;
       if (mL) { const u32 key = mL - 1, lt = key >> 1; witness(clock, lt); leave_intent(r, lt, !(key & 1u), self, sstate, refute, limit); }
       if (mJ) { const u32 lt = mJ - 1; witness(clock, lt); join_intent(r, lt, limit); }
-      if (refute) cold_refute(r, clock, limit);
+      if (refute) { Rec tr = r; u32 ck = clock; cold_refute(tr, ck, limit); r = tr; clock = ck; }
       if (!(r.flags & 1) && r.status != TY_NONE && (r.status != (orig.w[6] & 0xff) || r.st != orig.w[0])) r.leave_tick = t + 1;   // NodeIntent.wall_time (types/member.rs:32)
       Words mid;
       pack_words(r, mid);
       c.changed += differs(mid, orig) ? 1 : 0;
     }
     // ---------------- Phase E ----------------
-    if (op) cold_host_op(r, clock, sstate, op, op_slot == s, self, up_r, limit);
+    if (op) { Rec tr = r; u32 ck = clock, ss = sstate; cold_host_op(tr, ck, ss, op, op_slot == s, self, up_r, limit); r = tr; clock = ck; sstate = ss; }
     if (op && !(r.flags & 1) && r.status != TY_NONE && r.leave_tick == 0) r.leave_tick = t + 1;
     if (up_s) {
       // ---------------- Phase T: reaper (serf/base.rs:483-610), suspicion timer, probe ----------------
-      if (p.reap_now) cold_reap(r, t, p.tombstone_ticks, p.reconnect_ticks, p.intent_ticks);
+      if (p.reap_now) { Rec tr = r; cold_reap(tr, t, p.tombstone_ticks, p.reconnect_ticks, p.intent_ticks); r = tr; }
       if (r.mlstate == ML_SUSPECT && r.deadline != 0 && t >= r.deadline) ml_dead(r, r.inc, false, t, false, limit);
-      if (have_probe && !self && ptarget == p.subj[s] && ((p.down_mask >> s) & 1)) cold_probe_hit(p, r, v);
+      if (have_probe && !self && ptarget == p.subj[s] && ((p.down_mask >> s) & 1)) { Rec tr = r; cold_probe_hit(p, tr, v); r = tr; }
       // ---------------- Phase S ----------------
       const u32 mx = max(r.txl, max(r.txj, r.txm));
       if (mx) {
@@ -583,11 +609,11 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
       // noticed yet.  Suspect views are counted by the persistent counter (they sleep), the others here.  A watcher's view of
       // a down subject stays awake while it is Alive or Suspect: its own failed probe may still start or confirm the suspicion.
       const bool queued = (r.txl | r.txj | r.txm) != 0;
-      const bool watching = p.probe_every && ((p.down_mask >> s) & 1) && !self && ((wmask >> s) & 1);
+      const bool watching = (busy & 4u) && p.probe_every && ((p.down_mask >> s) & 1) && !self && ((SFS_WMASK() >> s) & 1);
       const bool suspect = r.mlstate == ML_SUSPECT;
       c.pending += (!suspect && (queued || (watching && r.mlstate == ML_ALIVE))) ? 1 : 0;
       // (its own failed probe is a confirmation only while its bucket is not in the confirmer set and the set is not full)
-      awake |= queued || (watching && (r.mlstate == ML_ALIVE || (suspect && cold_can_confirm(p, r, v))));
+      awake |= queued || (watching && (r.mlstate == ML_ALIVE || (suspect && cold_can_confirm(p.rules.k, r.mask, v))));
       if (suspect && r.deadline != 0) { has_timer = true; mind = min(mind, r.deadline); }
     }
     dsusp += ((up_s && r.mlstate == ML_SUSPECT) ? 1 : 0) - (susp_before ? 1 : 0);
@@ -752,6 +778,7 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
   const int lane = threadIdx.x & 31;
   if (SHARDED && threadIdx.x < (BLOCK / 32) * MAX_WORLD) xs->cnt[threadIdx.x / MAX_WORLD][threadIdx.x % MAX_WORLD] = 0;
   bool wrote_remote = false;
+  u32 resv = NO_BLOCK;                                     // lane s: the block this warp holds in peer s's window (flush_xwarp)
 
   // Dense / sparse ticks.  While the gossip front is wide (the previous tick sent at least one message per
   // two tiles) every tile will be hot anyway: senders skip the per-message tile marking and the next tick
@@ -836,7 +863,7 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
           if (mind != NO_DEADLINE) atomicMin(p.tile_due + tile0 + ti, mind);      // the list mixes tiles: per-lane registration (few active nodes)
           if (dsusp) atomicAdd(&dsusp_s, dsusp);
         }
-        if (SHARDED) wrote_remote |= flush_xwarp(p, xs, false);
+        if (SHARDED) wrote_remote |= flush_xwarp(p, xs, false, resv);
       }
       __syncthreads();
       if (mark && threadIdx.x < ng && pend_s[threadIdx.x]) p.hot_wr[tile0 + gt_s[threadIdx.x]] = 1;
@@ -865,12 +892,12 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
     if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, saturated, (hot_s[i] & 2u) != 0, pol_first, pol_last, c, mind, dsusp);
     if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + i] = 1;
     note_timers(p, tile0 + i, mind, dsusp, &dsusp_s);
-    if (SHARDED) wrote_remote |= flush_xwarp(p, xs, false);
+    if (SHARDED) wrote_remote |= flush_xwarp(p, xs, false, resv);
     i = j;
   }
   }
   if (SHARDED) {
-    wrote_remote |= flush_xwarp(p, xs, true);
+    wrote_remote |= flush_xwarp(p, xs, true, resv);
     if (wrote_remote) __threadfence_system();            // peer-window stores are performed before the publish kernel raises the flags
   }
   __syncthreads();
@@ -1165,9 +1192,12 @@ __global__ void __launch_bounds__(BLOCK) drain_kernel(const __grid_constant__ Dr
   for (u32 src = 0; src < p.world; ++src) {
     if (src == p.rank) continue;
     const u32 n = min(p.ctrl[src], p.win_cap);
-    const u64* w = p.win_data + (size_t)src * p.win_cap;
+    u64* w = p.win_data + (size_t)src * p.win_cap;
     for (u32 i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
       const u64 e = __ldcg(w + i);
+      if (e == 0) continue;                          // padding of a partly filled block (a real entry has value + 1 > 0 in its high word)
+      if (!p.byz_on) w[i] = 0;                       // consumed: the window reads as zeros when it is written next (injector triples are
+                                                     // read by a neighbouring thread too: those runs clear the windows in a kernel of their own)
       const u32 val1 = (u32)(e >> 32), s = (u32)(e >> 28) & 15, kind = (u32)(e >> 26) & 3;
       u32 dl = (u32)e & ((1u << 26) - 1);
       const bool byz = p.byz_on && (dl & BYZ_FLAG);
@@ -1213,6 +1243,17 @@ __global__ void fill_idle_rows_kernel(u64* rows, u64* grow_rows, u32 n, const u3
   if (grow_rows) {                                         // sharded: the global rows repeat the global pending count / hash
     grow_rows[(size_t)i * 8 + 4] = *(grow_rows - 8 + 4);
     if (trace) grow_rows[(size_t)i * 8 + 7] = *(grow_rows - 8 + 7);
+  }
+}
+
+// Injector runs: the drain kernel leaves its windows as they are (a triple is read by two threads); this clears what it consumed.
+__global__ void __launch_bounds__(BLOCK) clear_windows_kernel(const __grid_constant__ DrainParams p) {
+  if (p.gate && *p.gate) return;
+  for (u32 src = 0; src < p.world; ++src) {
+    if (src == p.rank) continue;
+    const u32 n = min(p.ctrl[src], p.win_cap);
+    u64* w = p.win_data + (size_t)src * p.win_cap;
+    for (u32 i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) w[i] = 0;
   }
 }
 
@@ -1413,7 +1454,10 @@ void launch_compute_watch(const u32* row_ptr, const u32* col, const u32* subj_de
 void launch_apply_watch(const u16* watch, u32 n_local, u8* busy, u8* hot_static, cudaStream_t st) {
   SFS_LAUNCH((n_local + 255) / 256, 256, 0, st, apply_watch_kernel)(watch, n_local, busy, hot_static);
 }
-void launch_drain(const DrainParams& p, cudaStream_t st) { SFS_LAUNCH(SFS_SMS * 8, BLOCK, 0, st, drain_kernel)(p); }
+void launch_drain(const DrainParams& p, cudaStream_t st) {
+  SFS_LAUNCH(SFS_SMS * 8, BLOCK, 0, st, drain_kernel)(p);
+  if (p.byz_on) SFS_LAUNCH(SFS_SMS * 2, BLOCK, 0, st, clear_windows_kernel)(p);
+}
 void launch_publish(const PublishParams& p, cudaStream_t st) { SFS_LAUNCH(1, 32, 0, st, publish_kernel)(p); }
 void launch_init_state(uint4* rec, u64* node_state, u32 n_local, u32 stride, u32 R, u32 init_st, u32 init_clock, cudaStream_t st) {
   SFS_LAUNCH((n_local + 255) / 256, 256, 0, st, init_state_kernel)(rec, node_state, n_local, stride, R, init_st, init_clock);

@@ -149,7 +149,7 @@ struct PublishParams {        // after the tick kernel: tell every peer how much
 struct DrainParams {
   u32 n_local, stride, R, world, rank, win_cap, stamp, n_tiles;
   const u32* kinds_prev;      // [4] the kind counters the tick kernel of this tick based its dense/sparse decision on
-  const u64* win_data;        // my window of this exchange parity: [world][win_cap]
+  u64* win_data;              // my window of this exchange parity: [world][win_cap]; entries are cleared as they are consumed
   const u32* ctrl;            // my control block of this parity: counts[8] | flags[8], written by the peers
   u32* inbox_wr;
   u8* hot_wr;

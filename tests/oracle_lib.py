@@ -16,9 +16,8 @@ u8p, u32p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uin
 
 def build():
     so = os.path.join(ORACLE_DIR, "liboracle.so")
-    src = os.path.join(ORACLE_DIR, "serf_oracle.cpp")
-    hdr = os.path.join(ROOT, "include", "serfsim.h")
-    if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    srcs = [os.path.join(ORACLE_DIR, "serf_oracle.cpp"), os.path.join(ORACLE_DIR, "wire_oracle.cpp"), os.path.join(ROOT, "include", "serfsim.h")]
+    if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
     return so
 
