@@ -35,8 +35,8 @@ constexpr int BLOCK = 256;
 #define SFS_MB_R1 4                         // resident CTAs per SM of the single-slot kernels (64 registers per thread)
 #endif
 #ifndef SFS_MB_RN
-#define SFS_MB_RN 3                         // resident CTAs per SM of the multi-slot kernels (80 registers per thread)
-#endif
+#define SFS_MB_RN 2                         // resident CTAs per SM of the multi-slot kernels (128 registers per thread: at 3 CTAs / 80 registers the
+#endif                                      // view loop spills, and local-memory traffic goes through the LSU the kernel is bound by: −7 % per run, profiles/r2_notes.md)
 constexpr u32 TILE_SHIFT = 8;              // one tile = one CTA pass = 256 nodes
 constexpr u32 MAX_TILES_PER_CTA = 1024;
 static_assert((1u << TILE_SHIFT) == BLOCK, "tile = block");
@@ -191,51 +191,57 @@ __device__ __forceinline__ void deliver(const TickParams& p, XStage* xs, u32* pl
   }
 }
 
-// Copy the warp's staged entries into the peers' windows (whole warp, convergent), one 32-entry BLOCK (256 contiguous bytes over
-// NVLink) at a time.  A block is reserved in the peer's window with one atomic on this rank's per-peer counter — and the
-// reservation for the NEXT block is issued right after a block has been written, by the lane whose index is the peer's rank,
-// which keeps the result in its own register (`resv`): the atomic's round trip is off the critical path, the next flush finds
-// the address waiting.  (Reserving at flush time stalled every flush for the atomic's latency on a counter the whole grid
-// hammers: 17 % of the sharded kernel's stall samples, profiles/r2g_hot_loop8_tick13.txt.)  Blocks that stay partly or wholly
-// unwritten — the last one of a warp, a reservation nobody used — read as zeros at the receiver: the drain kernel skips zero
-// entries and clears every entry it consumes, so a window is all zeros again before it is written next.
-// force = false: full blocks only; force = true (end of the kernel): everything.
-constexpr u32 NO_BLOCK = 0xffffffffu;
-__device__ __forceinline__ bool flush_xwarp(const TickParams& p, XStage* xs, bool force, u32& resv) {
+// Copy the warp's staged entries into the peers' windows (whole warp, convergent) in runs of whole 32-entry blocks (256+
+// contiguous bytes over NVLink).  Space in a peer's window is reserved with an atomic on this rank's per-peer counter — one
+// flush AHEAD: after its blocks have been written, the lane whose index is the peer's rank reserves as many entries as this
+// flush used and keeps base and length in its own registers (`resv`, `rlen`); nothing reads them before the next flush, so the
+// atomic's round trip on a counter the whole grid hammers is off the critical path (reserving at flush time cost 17 % of the
+// sharded kernel's stall samples, profiles/r2g_hot_loop8_tick13.txt; so did a reservation issued inside the per-peer loop,
+// whose next warp shuffle had to wait for it, profiles/r2h_hot_loop8_tick13.txt).  In saturated ticks the first reservation is
+// made when the kernel starts.  A flush that needs more than it holds takes the rest synchronously.  Reserved entries that stay
+// unwritten read as zeros at the receiver: the drain kernel skips zero entries and clears every entry it consumes, so a window
+// is all zeros again before it is written next.  force = false: whole blocks only; force = true (end of the kernel): everything.
+constexpr u32 XW_RESERVE_MAX = 128;        // entries reserved ahead per warp and peer, at most (bounds the padding, serfsim_create)
+__device__ __forceinline__ bool flush_xwarp(const TickParams& p, XStage* xs, bool force, u32& resv, u32& rlen) {
   const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   __syncwarp();
   bool wrote = false;
+  u32 want = 0;                                // this lane's peer: entries to reserve for the next flush
   for (u32 sh = 0; sh < p.world; ++sh) {
     if (sh == p.rank) continue;
     const u32 staged = xs->cnt[wid][sh];       // uniform over the warp
     if (staged == 0 || (!force && staged < XW_FLUSH)) continue;
     if (staged > xcap(p)) wrote = true;        // the excess went straight through
     const u32 n = min(staged, xcap(p));
+    const u32 m = force ? n : (n & ~(XW_FLUSH - 1u));          // entries to write now
     u64* src = xs->buf + wid * XW_TOTAL + xseg(p, sh);
     u64* dst = p.win_data[sh] + (size_t)p.rank * p.win_cap;
-    u32 done = 0;
-    while (n - done >= XW_FLUSH || (force && done < n)) {
-      const u32 chunk = min(XW_FLUSH, n - done);
-      u32 base = __shfl_sync(0xffffffffu, resv, sh);
-      if (base == NO_BLOCK) {                  // first block for this peer: reserve now
-        if (lane == sh) base = atomicAdd(p.send_count + sh, XW_FLUSH);
-        base = __shfl_sync(0xffffffffu, base, sh);
-      }
-      if (lane < chunk) {
-        if (base + lane < p.win_cap) dst[base + lane] = src[done + lane];
+    const u32 base = __shfl_sync(0xffffffffu, resv, sh), avail = __shfl_sync(0xffffffffu, rlen, sh);
+    const u32 take = min(m, avail);
+    for (u32 i = lane; i < take; i += 32) {
+      if (base + i < p.win_cap) dst[base + i] = src[i];
+      else *p.overflow = 2;
+    }
+    if (m > take) {                            // not (enough) reserved ahead: take the rest now
+      u32 b2 = 0;
+      if (lane == sh) b2 = atomicAdd(p.send_count + sh, m - take);
+      b2 = __shfl_sync(0xffffffffu, b2, sh);
+      for (u32 i = lane; i < m - take; i += 32) {
+        if (b2 + i < p.win_cap) dst[b2 + i] = src[take + i];
         else *p.overflow = 2;
       }
-      wrote = true;
-      done += chunk;
-      if (lane == sh) resv = force ? NO_BLOCK : atomicAdd(p.send_count + sh, XW_FLUSH);   // not waited for here
     }
-    const u32 rem = n - done;                  // < 32 entries stay staged: move them to the front
+    if (lane == sh) { resv += take; rlen -= take; want = min(m, XW_RESERVE_MAX); }
+    wrote = true;
+    const u32 rem = n - m;                     // < 32 entries stay staged: move them to the front
     u64 keep = 0;
-    if (lane < rem) keep = src[done + lane];
+    if (lane < rem) keep = src[m + lane];
     __syncwarp();
     if (lane < rem) src[lane] = keep;
     if (lane == 0) xs->cnt[wid][sh] = rem;
   }
+  // reservations for the next flush: issued last, consumed by the shuffles of the NEXT call
+  if (!force && want && rlen == 0) { resv = atomicAdd(p.send_count + lane, want); rlen = want; }
   __syncwarp();
   return wrote;
 }
@@ -529,7 +535,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
     iM = kM ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R + s2) * nl + vl, pol_first) : 0;
   };
 #ifndef SFS_VIEW_PREFETCH
-#define SFS_VIEW_PREFETCH 1                  // 0: a view's record is requested when its turn comes (12 registers less, one exposed round trip per further view)
+#define SFS_VIEW_PREFETCH 0                  // 1: the next view's record is requested while the current one is processed (12 more live registers; measured slower)
 #endif
   u32 s = R;
   if (R1) { s = 0; todo = 0; }
@@ -778,7 +784,7 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
   const int lane = threadIdx.x & 31;
   if (SHARDED && threadIdx.x < (BLOCK / 32) * MAX_WORLD) xs->cnt[threadIdx.x / MAX_WORLD][threadIdx.x % MAX_WORLD] = 0;
   bool wrote_remote = false;
-  u32 resv = NO_BLOCK;                                     // lane s: the block this warp holds in peer s's window (flush_xwarp)
+  u32 resv = 0, rlen = 0;                                  // lane s: the entries this warp holds reserved in peer s's window (flush_xwarp)
 
   // Dense / sparse ticks.  While the gossip front is wide (the previous tick sent at least one message per
   // two tiles) every tile will be hot anyway: senders skip the per-message tile marking and the next tick
@@ -793,6 +799,7 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
 
   const u32 tile0 = blockIdx.x * p.tiles_per_cta;
   const u32 ntile = tile0 < p.n_tiles ? min(p.tiles_per_cta, p.n_tiles - tile0) : 0;
+  if (SHARDED && saturated && ntile && (u32)lane < p.world && (u32)lane != p.rank) { resv = atomicAdd(p.send_count + lane, XW_FLUSH); rlen = XW_FLUSH; }   // every warp will send to every peer
   scan_tiles(p, hot_s, tile0, ntile, all_hot);
   __syncthreads();
   // Unsaturated ticks (ramp-up and tail of a dissemination: a few per cent of the nodes have anything to do, spread
@@ -863,7 +870,7 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
           if (mind != NO_DEADLINE) atomicMin(p.tile_due + tile0 + ti, mind);      // the list mixes tiles: per-lane registration (few active nodes)
           if (dsusp) atomicAdd(&dsusp_s, dsusp);
         }
-        if (SHARDED) wrote_remote |= flush_xwarp(p, xs, false, resv);
+        if (SHARDED) wrote_remote |= flush_xwarp(p, xs, false, resv, rlen);
       }
       __syncthreads();
       if (mark && threadIdx.x < ng && pend_s[threadIdx.x]) p.hot_wr[tile0 + gt_s[threadIdx.x]] = 1;
@@ -892,12 +899,12 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
     if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, saturated, (hot_s[i] & 2u) != 0, pol_first, pol_last, c, mind, dsusp);
     if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + i] = 1;
     note_timers(p, tile0 + i, mind, dsusp, &dsusp_s);
-    if (SHARDED) wrote_remote |= flush_xwarp(p, xs, false, resv);
+    if (SHARDED) wrote_remote |= flush_xwarp(p, xs, false, resv, rlen);
     i = j;
   }
   }
   if (SHARDED) {
-    wrote_remote |= flush_xwarp(p, xs, true, resv);
+    wrote_remote |= flush_xwarp(p, xs, true, resv, rlen);
     if (wrote_remote) __threadfence_system();            // peer-window stores are performed before the publish kernel raises the flags
   }
   __syncthreads();
