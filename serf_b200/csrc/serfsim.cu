@@ -293,6 +293,9 @@ int launch_ticks(serfsim* h, u32 n) {
     const u32 xpar = h->xepoch & 1;
     p.world = (u32)h->cfg.world_size; p.rank = (u32)h->cfg.rank; p.shard_size = h->shard_size; p.win_cap = h->win_cap;
     p.win_data = h->d_peer_data[xpar]; p.send_count = h->d_send_count;
+    p.peer_ctrl = h->d_peer_ctrl; p.stamp = h->xepoch + 1; p.xpar = xpar; p.loopback = h->loopback ? 1u : 0u;
+    p.fuse_publish = (sharded && !h->byz_on && !getenv("SERFSIM_NO_FUSE")) ? 1u : 0u;
+    p.shard_inv = (u32)(0x100000000ull / h->shard_size); p.xcap = p.world > 1 ? 392u / (p.world - 1) : 0u;     // XW_TOTAL = 392 (tick_kernel.cu)
     Gate gate{};                                   // convergence gate: the first kernel of the tick evaluates the row of tick t-1
     if (h->gate_on) {
       gate.ctl = h->d_runctl; gate.host_ctl = h->d_pin_ctl; gate.prev_row = t > h->gate_first ? grow + (size_t)(t - 1) * 8 : nullptr; gate.tick = t;
@@ -353,7 +356,7 @@ int launch_ticks(serfsim* h, u32 n) {
       PublishParams pb{};
       pb.world = p.world; pb.rank = p.rank; pb.stamp = stamp; pb.xpar = xpar; pb.send_count = h->d_send_count; pb.peer_ctrl = h->d_peer_ctrl;
       pb.row = p.row; pb.gate = gate_word; pb.sched = h->d_sched; pb.loopback = h->loopback ? 1u : 0u;
-      launch_publish(pb, h->stream);
+      if (!p.fuse_publish) { launch_publish(pb, h->stream); h->last_launches++; }
       DrainParams d{};
       d.n_local = h->count; d.stride = h->stride; d.R = h->R; d.world = p.world; d.rank = p.rank; d.win_cap = h->win_cap; d.stamp = stamp; d.n_tiles = h->n_tiles; d.kinds_prev = p.kinds_prev;
       d.win_data = h->d_win_data[xpar]; d.ctrl = h->d_ctrl + xpar * 16; d.inbox_wr = h->d_inbox[t & 1]; d.hot_wr = h->d_hot[t & 1]; d.kinds_cur = h->d_kinds + ((size_t)t + 1) * 4; d.overflow = h->d_overflow;
@@ -363,7 +366,7 @@ int launch_ticks(serfsim* h, u32 n) {
       d.sums = reinterpret_cast<const u64*>(reinterpret_cast<const unsigned char*>(h->d_ctrl) + CTRL_SUMS_OFF) + (size_t)xpar * 8 * CTRL_FIELDS;
       d.sched = h->d_sched; d.host_idle_until = h->d_pin_ctl + 2; d.tick = t; d.sleep_on = p.sleep_on;
       launch_drain(d, h->stream);
-      h->last_launches += 2;
+      h->last_launches += 1;
       h->xepoch++;
     }
     const u32 pp = (u32)std::max(0, h->cfg.push_pull_interval_ticks);
@@ -689,7 +692,7 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
   CUB(cudaMemcpy(h->d_subj, h->subj.data(), h->R * 4, cudaMemcpyHostToDevice));
   {
     const char* e = getenv("SERFSIM_MINB");
-    h->ctas_per_sm = (h->R == 1) ? ((e && atoi(e) == 5) ? 5 : tick_ctas_per_sm_r1()) : tick_ctas_per_sm_rn();
+    h->ctas_per_sm = (h->R == 1) ? ((e && atoi(e) == 5) ? 5 : (cfg->world_size > 1 ? tick_ctas_per_sm_r1s() : tick_ctas_per_sm_r1())) : tick_ctas_per_sm_rn();
   }
   h->grid = tick_grid_size(h->count, h->ctas_per_sm);
   {

@@ -34,6 +34,9 @@ constexpr int BLOCK = 256;
 #ifndef SFS_MB_R1
 #define SFS_MB_R1 4                         // resident CTAs per SM of the single-slot kernels (64 registers per thread)
 #endif
+#ifndef SFS_MB_R1S
+#define SFS_MB_R1S SFS_MB_R1                // … of the sharded single-slot kernel (its send path needs more registers: A/B in profiles/r2_notes.md)
+#endif
 #ifndef SFS_MB_RN
 #define SFS_MB_RN 2                         // resident CTAs per SM of the multi-slot kernels (128 registers per thread: at 3 CTAs / 80 registers the
 #endif                                      // view loop spills, and local-memory traffic goes through the LSU the kernel is bound by: −7 % per run, profiles/r2_notes.md)
@@ -160,8 +163,17 @@ constexpr u32 MAX_WORLD = 8;
 constexpr u32 XW_TOTAL = 392;              // staged entries per warp (3 KB), split evenly over the world-1 peers (world 8: 56 each)
 constexpr u32 XW_FLUSH = 32;               // flush threshold: a full warp-wide store
 struct XStage { u64 buf[(BLOCK / 32) * XW_TOTAL]; u32 cnt[BLOCK / 32][MAX_WORLD]; };
-__device__ __forceinline__ u32 xcap(const TickParams& p) { return XW_TOTAL / (p.world - 1); }
-__device__ __forceinline__ u32 xseg(const TickParams& p, u32 shard) { return (shard < p.rank ? shard : shard - 1) * xcap(p); }
+// (no integer division on the send path: the sharded kernel issues on every cycle it can — 2.4× the instructions of the unsharded one —
+// and `x / runtime value` is ≈ 25 of them; capacity and reciprocal come with the parameters)
+__device__ __forceinline__ u32 xcap(const TickParams& p) { return p.xcap; }
+__device__ __forceinline__ u32 xseg(const TickParams& p, u32 shard) { return (shard - (shard > p.rank ? 1u : 0u)) * p.xcap; }
+__device__ __forceinline__ u32 shard_of(const TickParams& p, u32 dst, u32& dloc) {
+  u32 q = mulhi32(dst, p.shard_inv);           // floor(dst / shard_size) or one less
+  u32 r = dst - q * p.shard_size;
+  if (r >= p.shard_size) { ++q; r -= p.shard_size; }
+  dloc = r;
+  return q;
+}
 
 template <bool SHARDED>
 __device__ __forceinline__ void deliver(const TickParams& p, XStage* xs, u32* plane, u32 dst, u32 kind, u32 s, u32 val1, u64 pol_last, bool mark) {
@@ -170,8 +182,8 @@ __device__ __forceinline__ void deliver(const TickParams& p, XStage* xs, u32* pl
     red_max_resident(plane + dl, val1, pol_last);
     if (mark) p.hot_wr[dl >> TILE_SHIFT] = 1;  // sparse ticks only: tell the next tick which tiles received something
   } else {
-    const u32 shard = dst / p.shard_size;
-    const u32 dloc = dst - shard * p.shard_size;
+    u32 dloc;
+    const u32 shard = shard_of(p, dst, dloc);
     const u64 e = ((u64)val1 << 32) | ((u64)s << 28) | ((u64)kind << 26) | dloc;
     // warp-aggregated append: the lanes of this call that target the same shard reserve their slots with ONE
     // shared-memory atomic on the warp's own counter (divergent callers of the same warp may interleave: keep it atomic)
@@ -207,10 +219,13 @@ __device__ __forceinline__ bool flush_xwarp(const TickParams& p, XStage* xs, boo
   __syncwarp();
   bool wrote = false;
   u32 want = 0;                                // this lane's peer: entries to reserve for the next flush
-  for (u32 sh = 0; sh < p.world; ++sh) {
-    if (sh == p.rank) continue;
-    const u32 staged = xs->cnt[wid][sh];       // uniform over the warp
-    if (staged == 0 || (!force && staged < XW_FLUSH)) continue;
+  // peers whose buffer holds a whole block (anything, when forced): lane s looks at peer s, one vote, then only those are visited
+  const u32 mine = lane < p.world ? xs->cnt[wid][lane] : 0u;
+  u32 ready = __ballot_sync(0xffffffffu, lane != p.rank && (force ? mine != 0 : mine >= XW_FLUSH));
+  while (ready) {
+    const u32 sh = (u32)__ffs((int)ready) - 1u;
+    ready &= ready - 1u;
+    const u32 staged = __shfl_sync(0xffffffffu, mine, sh);
     if (staged > xcap(p)) wrote = true;        // the excess went straight through
     const u32 n = min(staged, xcap(p));
     const u32 m = force ? n : (n & ~(XW_FLUSH - 1u));          // entries to write now
@@ -662,13 +677,12 @@ __device__ __forceinline__ u32 warp_min(u32 v) {
 // After a warp has processed its nodes of one tile: register the earliest running suspicion deadline in the timer wheel and add
 // the warp's net change of Suspect views to the CTA's shared counter (both rare outside suspicion waves: one vote each).
 __device__ __forceinline__ void note_timers(const TickParams& p, u32 tile, u32 mind, int dsusp, int* dsusp_s) {
-  if (__any_sync(0xffffffffu, mind != NO_DEADLINE)) {
-    const u32 wm = warp_min(mind);
-    if ((threadIdx.x & 31) == 0) atomicMin(p.tile_due + tile, wm);
-  }
-  if (__any_sync(0xffffffffu, dsusp != 0)) {
-    const u32 ws = warp_sum((u32)dsusp);                   // two's complement: the sum of the lanes' signed changes
-    if ((threadIdx.x & 31) == 0) atomicAdd(dsusp_s, (int)ws);
+  if (!__any_sync(0xffffffffu, (mind != NO_DEADLINE) | (dsusp != 0))) return;      // one vote on the common path
+  const u32 wm = warp_min(mind);
+  const u32 ws = warp_sum((u32)dsusp);                     // two's complement: the sum of the lanes' signed changes
+  if ((threadIdx.x & 31) == 0) {
+    if (wm != NO_DEADLINE) atomicMin(p.tile_due + tile, wm);
+    if (ws) atomicAdd(dsusp_s, (int)ws);
   }
 }
 
@@ -693,6 +707,23 @@ __device__ __forceinline__ void scan_tiles(const TickParams& p, u8* hot_s, u32 t
     if (due) { p.tile_due[tile0 + i] = NO_DEADLINE; SFS_PROBE(4); }     // tiles woken by the timer wheel
     hot_s[i] = (u8)(((f || all_hot || due || p.hot_static[tile0 + i]) ? 1u : 0u) | (due ? 2u : 0u));
   }
+}
+
+// What publish_kernel does, for one peer per calling thread (threads 0 .. world-1 of one CTA): entry count, this rank's trace row and
+// scheduler verdict into the peer's control block, then the release flag of this exchange.
+__device__ __forceinline__ void publish_to_peer(u32 r, u32 world, u32 rank, u32 xpar, u32 stamp, u32 loopback, u32* const* peer_ctrl, u32* send_count,
+                                                const volatile u64* row, const volatile u32* sched) {
+  if (r >= world || r == rank) return;
+  const u32 me = loopback ? r : rank;                       // the slot this rank owns in the peer's control block
+  u32* ctrl = peer_ctrl[r] + xpar * 16;
+  ctrl[me] = send_count[r];
+  u64* sums = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(peer_ctrl[r]) + CTRL_SUMS_OFF) + ((size_t)xpar * 8 + me) * CTRL_FIELDS;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sums[i] = row[i];              // this rank's counters of the tick: every rank sums them on the device
+  sums[8] = sched[SCHED_LOCAL_QUIET]; sums[9] = sched[SCHED_LOCAL_UNTIL];
+  __threadfence_system();
+  st_release_sys(ctrl + 8 + me, stamp);
+  send_count[r] = 0;
 }
 
 // End of a tick: block reduction of the counters (warp shuffles, then shared memory) → one atomic per counter per CTA; the
@@ -736,7 +767,12 @@ __device__ __forceinline__ void finish_tick(const TickParams& p, const Counters&
   // the user-event kernel reported nothing queued or sent (with injectors sleep_on is off): then the cluster sleeps until the earliest
   // suspicion deadline or the next anti-entropy / reaper round (host operations are checked at launch).  Sharded runs: this is
   // the rank's verdict; it travels with the row and the drain kernel combines the ranks' (all quiet, earliest deadline).
-  const bool quiet = p.sleep_on && row[1] == 0 && row[2] == 0 && sched[SCHED_AWAKE] == 0 && sched[SCHED_UE_ACTIVITY] == 0;
+  // (decided by ONE thread and broadcast: the words it reads are cleared below by thread 0, and a warp that evaluated them later than
+  // thread 0 cleared them would take the other side of a branch that contains a barrier)
+  __shared__ u32 quiet_s;
+  if (threadIdx.x == 0) quiet_s = (p.sleep_on && row[1] == 0 && row[2] == 0 && sched[SCHED_AWAKE] == 0 && sched[SCHED_UE_ACTIVITY] == 0) ? 1u : 0u;
+  __syncthreads();
+  const bool quiet = quiet_s != 0;
   u32 until = p.tick + 1;
   if (quiet) {                                             // uniform over the CTA
     u32 m = NO_DEADLINE;
@@ -761,6 +797,12 @@ __device__ __forceinline__ void finish_tick(const TickParams& p, const Counters&
       sched[SCHED_LOCAL_QUIET] = quiet ? 1u : 0u; sched[SCHED_LOCAL_UNTIL] = until;
     }
     sched[SCHED_AWAKE] = 0; sched[SCHED_UE_ACTIVITY] = 0; sched[SCHED_TICKET] = 0;
+  }
+  if (p.world > 1 && p.fuse_publish) {
+    // every CTA fenced its peer-window stores (system scope) before it took its ticket; this one saw all tickets
+    __syncthreads();
+    __threadfence();
+    publish_to_peer(threadIdx.x, p.world, p.rank, p.xpar, p.stamp, p.loopback, p.peer_ctrl, p.send_count, row, sched);
   }
 }
 
@@ -1146,19 +1188,7 @@ __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__
 // the peer's flag for this exchange (system-scope release).  One warp.
 __global__ void publish_kernel(const __grid_constant__ PublishParams p) {
   if (p.gate && *p.gate) return;
-  const u32 r = threadIdx.x;
-  if (r < p.world && r != p.rank) {
-    const u32 me = p.loopback ? r : p.rank;                 // the slot this rank owns in the peer's control block
-    u32* ctrl = p.peer_ctrl[r] + p.xpar * 16;
-    ctrl[me] = p.send_count[r];
-    u64* sums = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(p.peer_ctrl[r]) + CTRL_SUMS_OFF) + ((size_t)p.xpar * 8 + me) * CTRL_FIELDS;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sums[i] = p.row[i];          // this rank's counters of the tick: every rank sums them on the device
-    sums[8] = p.sched[SCHED_LOCAL_QUIET]; sums[9] = p.sched[SCHED_LOCAL_UNTIL];
-    __threadfence_system();
-    st_release_sys(ctrl + 8 + me, p.stamp);
-    p.send_count[r] = 0;
-  }
+  publish_to_peer(threadIdx.x, p.world, p.rank, p.xpar, p.stamp, p.loopback, p.peer_ctrl, p.send_count, p.row, p.sched);
 }
 
 // Fold the cross-shard windows into the inbox.  Waits (system-scope acquire) until every peer has raised
@@ -1393,6 +1423,7 @@ __global__ void __launch_bounds__(BLOCK) summary_kernel(const uint4* rec, const 
 }  // namespace
 
 int tick_ctas_per_sm_r1() { return SFS_MB_R1; }
+int tick_ctas_per_sm_r1s() { return SFS_MB_R1S; }
 int tick_ctas_per_sm_rn() { return SFS_MB_RN; }
 int tick_grid_size(u32 n_local, int ctas_per_sm) {
   static int sms = 0;
@@ -1439,7 +1470,7 @@ static void launch_tick_v(const TickParams& p, int grid, cudaStream_t st) {
 #endif
   static int mb5 = -1;
   if (mb5 < 0) { const char* e = getenv("SERFSIM_MINB"); mb5 = (e && atoi(e) == 5) ? 1 : 0; }
-  if (sharded) { if (r1) SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, true, true, SFS_MB_R1>)(p); else SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, true, false, SFS_MB_RN>)(p); }
+  if (sharded) { if (r1) SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, true, true, SFS_MB_R1S>)(p); else SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, true, false, SFS_MB_RN>)(p); }
   else if (r1) { if (mb5) SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, false, true, 5>)(p); else SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, false, true, SFS_MB_R1>)(p); }
   else SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<TRACE, FMAX, false, false, SFS_MB_RN>)(p);
 }

@@ -118,6 +118,10 @@ struct TickParams {
   u32* sched;                 // scheduler words (SCHED_*), u64 suspect-view counter at sched + SCHED_SUSPECTS
   u32 sleep_on;               // 0: SERFSIM_NO_SKIP — every tile, every view, every tick
   u32 pp_every, reap_every;   // push-pull / reaper periods in ticks (0 = off): such ticks are never skipped
+  // sharded runs without injectors: the tick's LAST CTA also publishes (counts, row, verdict, release flag → every peer's control
+  // block): one launch less per tick.  With injectors their kernel still writes windows after this one, and publish_kernel follows it.
+  u32* const* peer_ctrl; u32 stamp, xpar, loopback, fuse_publish;
+  u32 shard_inv, xcap;        // floor(2^32 / shard_size) (a remote target's shard without a division); staged entries per warp and peer
   u32* host_idle_until;       // SCHED_IDLE_UNTIL mirrored into mapped pinned host memory: serfsim_run_until_converged does not even launch the ticks the cluster sleeps through
 };
 constexpr u32 SCHED_TICKET = 0, SCHED_IDLE_UNTIL = 1, SCHED_UE_ACTIVITY = 2, SCHED_AWAKE = 3, SCHED_SUSPECTS = 4 /* u64 */,
@@ -183,6 +187,7 @@ void launch_state_hash(const uint4* rec, const u32* qword, const u64* node_state
 void launch_summary(const uint4* rec, const u32* qword, const u64* node_state, u32 n_local, u32 stride, u32 first, u32 R, const u32* subj_dev, u64* out /*[2 + 2*R + 2]*/, cudaStream_t st);
 int tick_grid_size(u32 n_local, int ctas_per_sm);
 int tick_ctas_per_sm_r1();
+int tick_ctas_per_sm_r1s();
 int tick_ctas_per_sm_rn();
 void launch_compute_watch(const u32* row_ptr, const u32* col, const u32* subj_dev, u32 R, u32 first, u32 n_local, u16* watch, cudaStream_t st);
 void launch_apply_watch(const u16* watch, u32 n_local, u8* busy, u8* hot_static, cudaStream_t st);
