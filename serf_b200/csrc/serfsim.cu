@@ -91,6 +91,7 @@ struct serfsim {
   const u64** d_peer_snap_node = nullptr;
   u8* d_hot[2] = {nullptr, nullptr};      // [n_tiles] per tick parity
   u8* d_hot_static = nullptr;             // [n_tiles] tiles that hold a watcher (never consumed)
+  u32* d_node_due = nullptr;              // [stride] per-node earliest suspicion deadline (tick_kernel.cuh)
   u32* d_tile_due = nullptr;              // [n_tiles] earliest suspicion deadline of a tile's nodes (the timer wheel)
   u32* d_sched = nullptr;                 // scheduler words (tick_kernel.cuh: SCHED_*)
   u32 n_tiles = 0;
@@ -136,6 +137,7 @@ struct serfsim {
   bool has_topo = false;
   u32 stage_col_bytes = 0;         // 0: direct-load kernel; else bytes of CSR per TMA stage
   u32 max_tile_edges = 0;          // largest 16-byte-aligned CSR span of one 256-node tile (sizes the TMA stage)
+  u32 ahead = 1;                   // multi-slot tick kernel: software pipelining of saturated ticks (SERFSIM_AHEAD=0 / 1 / 2, tick_kernel.cuh)
   u32 udeg = 0;                    // uniform out-degree of the shard's rows (0: degrees differ)
   std::vector<serfsim_tick_row_t> rows;   // rows pulled from the device so far (global sums when sharded)
   // device-side convergence gate (tick_kernel.cuh: Gate)
@@ -285,8 +287,8 @@ int launch_ticks(serfsim* h, u32 n) {
     p.stride = h->stride; p.n_tiles = h->n_tiles; p.tiles_per_cta = (h->n_tiles + h->grid - 1) / h->grid;
     p.force_all = (h->cfg.trace != 0) || h->no_skip || p.reap_now;
     p.compact = h->compact ? 1u : 0u;
-    p.udeg = h->udeg;
-    p.tile_due = h->d_tile_due; p.hot_static = h->d_hot_static; p.sched = h->d_sched;
+    p.udeg = h->udeg; p.ahead = h->ahead;
+    p.tile_due = h->d_tile_due; p.node_due = h->d_node_due; p.hot_static = h->d_hot_static; p.sched = h->d_sched;
     p.sleep_on = (h->no_skip || h->byz_on) ? 0u : 1u;          // injectors send every tick: the cluster never sleeps
     p.pp_every = (u32)std::max(0, h->cfg.push_pull_interval_ticks); p.reap_every = h->cfg.reap_interval_ticks;
     p.host_idle_until = h->d_pin_ctl + 2;
@@ -534,6 +536,7 @@ int do_reset(serfsim* h, u64 seed) {
   CU(cudaMemsetAsync(h->d_hot[0], 0, h->n_tiles, h->stream));
   CU(cudaMemsetAsync(h->d_hot[1], 0, h->n_tiles, h->stream));
   CU(cudaMemsetAsync(h->d_tile_due, 0xff, (size_t)h->n_tiles * sizeof(u32), h->stream));      // no timer runs
+  CU(cudaMemsetAsync(h->d_node_due, 0xff, (size_t)h->stride * sizeof(u32), h->stream));
   CU(cudaMemsetAsync(h->d_sched, 0, SCHED_WORDS * sizeof(u32), h->stream));
   if (h->d_trace) {
     CU(cudaMemsetAsync(h->d_trace, 0, (size_t)h->trace_cap * 8 * sizeof(u64), h->stream));
@@ -552,7 +555,7 @@ int do_reset(serfsim* h, u64 seed) {
 void free_all(serfsim* h) {
   for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   for (cudaEvent_t e : h->tick_ev) cudaEventDestroy(e);
-  cudaFree(h->d_hot_static); cudaFree(h->d_tile_due); cudaFree(h->d_sched);
+  cudaFree(h->d_hot_static); cudaFree(h->d_tile_due); cudaFree(h->d_node_due); cudaFree(h->d_sched);
   cudaFree(h->d_hot[0]); cudaFree(h->d_hot[1]); cudaFree(h->d_busy); cudaFree(h->d_watch); cudaFree(h->d_snap_rec); cudaFree(h->d_snap_node); cudaFree(h->d_peer_snap_rec); cudaFree(h->d_peer_snap_node);
   cudaFree(h->d_qword);
   cudaFree(h->d_rec); cudaFree(h->d_inbox[0]); cudaFree(h->d_inbox[1]); cudaFree(h->d_node); cudaFree(h->d_rowptr); cudaFree(h->d_col);
@@ -674,7 +677,7 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
   CUB(cudaMalloc(&h->d_watch, (size_t)h->stride * 2));
   CUB(cudaMemset(h->d_watch, 0, (size_t)h->stride * 2));
   CUB(cudaMalloc(&h->d_hot[0], h->n_tiles)); CUB(cudaMalloc(&h->d_hot[1], h->n_tiles));
-  CUB(cudaMalloc(&h->d_hot_static, h->n_tiles)); CUB(cudaMalloc(&h->d_tile_due, (size_t)h->n_tiles * sizeof(u32))); CUB(cudaMalloc(&h->d_sched, SCHED_WORDS * sizeof(u32)));
+  CUB(cudaMalloc(&h->d_hot_static, h->n_tiles)); CUB(cudaMalloc(&h->d_tile_due, (size_t)h->n_tiles * sizeof(u32))); CUB(cudaMalloc(&h->d_node_due, (size_t)h->stride * sizeof(u32))); CUB(cudaMalloc(&h->d_sched, SCHED_WORDS * sizeof(u32)));
   CUB(cudaMemset(h->d_hot_static, 0, h->n_tiles));
   CUB(cudaHostAlloc(&h->pin_overflow, sizeof(u32), cudaHostAllocMapped));
   CUB(cudaHostGetDevicePointer(&h->d_overflow, h->pin_overflow, 0));
@@ -709,6 +712,7 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
   }
   if (const char* e = getenv("SERFSIM_NO_SKIP")) h->no_skip = atoi(e) != 0;
   if (const char* e = getenv("SERFSIM_COMPACT")) h->compact = atoi(e) != 0;
+  if (const char* e = getenv("SERFSIM_AHEAD")) h->ahead = (u32)std::min(2, std::max(0, atoi(e)));
   if (cfg->world_size > 1) {
     // receive windows: one segment per peer; expected entries per tick and pair ≈ shard · fanout · R · kinds / world
     if (cfg->world_size > 8) return bail(fail(SERFSIM_E_INVAL, "world_size > 8"));

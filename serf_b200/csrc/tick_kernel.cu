@@ -334,38 +334,46 @@ __device__ __forceinline__ u32 pick_finish(u32 v, const u32 (&cand)[FMAX], u32 (
 // queue words.  13 bytes per node instead of 45 (single slot).
 // busy byte: bit 0 awake (queued transmits / probe duty), bit 1 host operation this tick, bit 2 watcher (static),
 // bit 3 some view of the node runs a suspicion timer (it sleeps until its tile comes due, tick_kernel.cuh).
-struct Pre { u32 busy, mL, mJ, mM, any, qw, mailmask, qmask; };
+// nd: the node's own earliest suspicion deadline (node_due), read only in tiles that have come due
+struct Pre { u32 busy, mL, mJ, mM, any, qw, mailmask, qmask, keep, nd; };   // mL, mJ, mM, qw: the words of view `keep` (0 in single-slot runs)
 template <bool R1>
-__device__ __forceinline__ Pre prefetch_node(const TickParams& p, u32 vl, bool kL, bool kJ, bool kM, u64 pol_first) {
+__device__ __forceinline__ Pre prefetch_node(const TickParams& p, u32 vl, bool kL, bool kJ, bool kM, u64 pol_first, bool due, u32 keep = 0) {
   const u32 nl = p.stride, R = R1 ? 1u : p.R;
   Pre x;
   x.busy = p.busy[vl];
-  x.qw = p.qword[vl];                                   // slot-0 queue word (transmit budgets)
-  SFS_COUNT(6, 4);
-  x.mL = kL ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R) * nl + vl, pol_first) : 0u;
-  x.mJ = kJ ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R) * nl + vl, pol_first) : 0u;
-  x.mM = kM ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R) * nl + vl, pol_first) : 0u;
-  x.any = x.mL | x.mJ | x.mM;
-  x.mailmask = x.any ? 1u : 0u;
-  x.qmask = x.qw ? 1u : 0u;
-  if (!R1) {
-    for (u32 s2 = 1; s2 < R; ++s2) {
-      u32 m = 0;
-      if (kL) m |= ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R + s2) * nl + vl, pol_first);
-      if (kJ) m |= ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R + s2) * nl + vl, pol_first);
-      if (kM) m |= ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R + s2) * nl + vl, pol_first);
-      x.any |= m;
-      x.mailmask |= (m ? 1u : 0u) << s2;
-      x.qmask |= (p.qword[(size_t)s2 * nl + vl] ? 1u : 0u) << s2;
-      SFS_COUNT(6, 4);
-    }
+  x.nd = due ? p.node_due[vl] : NO_DEADLINE;
+  x.keep = R1 ? 0u : keep;
+  x.mL = x.mJ = x.mM = x.qw = 0; x.any = 0; x.mailmask = 0; x.qmask = 0;
+  for (u32 s2 = 0; s2 < R; ++s2) {
+    const u32 l = kL ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R + s2) * nl + vl, pol_first) : 0u;
+    const u32 j = kJ ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R + s2) * nl + vl, pol_first) : 0u;
+    const u32 m = kM ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R + s2) * nl + vl, pol_first) : 0u;
+    const u32 q = p.qword[(size_t)s2 * nl + vl];        // queue word (transmit budgets)
+    SFS_COUNT(6, 4);
+    if (R1 || s2 == x.keep) { x.mL = l; x.mJ = j; x.mM = m; x.qw = q; }
+    x.any |= l | j | m;
+    x.mailmask |= ((l | j | m) ? 1u : 0u) << s2;
+    x.qmask |= (q ? 1u : 0u) << s2;
   }
   return x;
 }
-// Has the node anything to do this tick?  (due: its tile's earliest suspicion deadline has been reached.)
+// Has the node anything to do this tick?  (due: its tile's earliest suspicion deadline has been reached — then a node that runs timers
+// looks at its OWN earliest deadline: only if that has been reached too does it visit its views; otherwise it hands the deadline back
+// to the timer wheel, sleeping_deadline(), without touching a record.)
 __device__ __forceinline__ bool node_active(const TickParams& p, const Pre& x, bool due) {
-  return (x.busy & 7u) != 0 || x.any != 0 || p.reap_now != 0 || (due && (x.busy & 8u));
+  return (x.busy & 7u) != 0 || x.any != 0 || p.reap_now != 0 || (due && (x.busy & 8u) && x.nd <= p.tick);
 }
+
+// Multi-slot runs, saturated ticks: what a node needs beyond its `Pre` words, requested ONE TILE AHEAD together with them — the node
+// word, the neighbour ids of its gossip peers (uniform out-degree: the row offset is arithmetic, the draw needs only tick and id) and the
+// record of the view it will most probably visit first (`keep`: the first view this thread visited in its previous tile; in a
+// dissemination wave nearly every node has the same views active).  The multi-slot kernel holds 16 warps per SM (128 registers per
+// thread): without this every tile pays three dependent round trips (Pre → node word + record → neighbour ids) with too few warps to
+// hide them.  A guess that turns out wrong costs one unused 32-byte load; results never depend on it.
+template <int FMAX>
+struct Ahead { u64 ns; Words rec; u32 cand[FMAX]; u32 valid; };
+
+__device__ __forceinline__ u32 sleeping_deadline(const Pre& x, bool due) { return (due && (x.busy & 8u)) ? x.nd : NO_DEADLINE; }
 
 // ---- cold paths of a node's tick, kept out of line: host operations, the reaper round and the SWIM probe run for a handful of
 // nodes per tick (or for all of them once in a long while); inlined, their temporaries (a second Philox block, the operation
@@ -453,7 +461,7 @@ __device__ SFS_COLD bool cold_can_confirm(u32 k, u32 mask, u32 v) {
 // every node of it that carries a timer (busy bit 3) visits all its views.
 template <bool TRACE, int FMAX, bool SHARDED, bool R1, bool STAGED>
 __device__ __forceinline__ bool process_node(const TickParams& p, const StageView& sv, XStage* xs, const u32 vl, const Pre& pre, const bool kL, const bool kJ, const bool kM, const bool mark, const bool saturated,
-                                             const bool due, const u64 pol_first, const u64 pol_last, Counters& c, u32& mind, int& dsusp) {
+                                             const bool due, const u64 pol_first, const u64 pol_last, Counters& c, u32& mind, int& dsusp, const Ahead<FMAX>& ah, u32& first_view) {
   static_assert(!STAGED || R1, "the staged path is the single-slot path");
   const u32 lt = threadIdx.x;              // index inside the staged tile
   const u32 v = p.first + vl;
@@ -491,12 +499,14 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   if (STAGED) { mL = kL ? sv.inL[lt] : 0u; mJ = kJ ? sv.inJ[lt] : 0u; mM = kM ? sv.inM[lt] : 0u; }
 
   // ---- idle exit: nothing received (any slot), nothing queued, no host operation, no probe duty, no timer due ----
-  const bool timers_due = due && (busy & 8u);
-  if (!TRACE && !STAGED && !node_active(p, pre, due)) return false;
-  if (STAGED && !TRACE && !((busy & 7u) || (mL | mJ | mM) || p.reap_now || timers_due)) return false;
+  const bool timers_due = due && (busy & 8u) && pre.nd <= p.tick;
+  if (!TRACE && !STAGED && !node_active(p, pre, due)) { mind = min(mind, sleeping_deadline(pre, due)); if (due && (busy & 8u)) SFS_PROBE(20); return false; }
+  if (STAGED && !TRACE && !((busy & 7u) || (mL | mJ | mM) || p.reap_now || timers_due)) { mind = min(mind, sleeping_deadline(pre, due)); return false; }
   // (the watcher mask — subjects this node can probe, it has them as neighbours — is re-read where a watcher needs it: a handful of nodes)
 #define SFS_WMASK() ((busy & 4u) ? (u32)p.watch[vl] : 0u)
-  if (!upfront) { load_node(); if (R1) load_rec0(); }
+  const bool ahead = !R1 && !STAGED && ah.valid;       // node word, peers' ids and the record of view pre.keep were requested a tile ago
+  if (ahead) { ns = ah.ns; row0 = vl * p.udeg; row1 = row0 + p.udeg; }
+  else if (!upfront) { load_node(); if (R1) load_rec0(); }
 
   u32 clock = (u32)ns;
   const bool up_r = (ns & NS_UP) != 0;
@@ -527,7 +537,8 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   u32 nt = 0;
   bool have_targets = false;
   u32 max_tx = 0;
-  bool awake = false, has_timer = false;
+  bool awake = false, has_timer = false, dl_moved = false;
+  u32 mind_node = NO_DEADLINE;             // earliest running suspicion deadline among the views visited
 
   // Views to visit: all of them when the node as a whole has business (trace, reaper round, host operation, timers due);
   // otherwise those with mail, queued transmits or probe duty (a watcher's view of a subject that is down).
@@ -542,7 +553,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   auto load_view = [&](u32 s2, Words& w, u32& q, u32& iL, u32& iJ, u32& iM) {
     const size_t idn = (size_t)s2 * nl + vl;
     w = ld_rec256(p.rec + 2 * idn, pol_first);
-    if (s2 == 0) { q = pre.qw; iL = pre.mL; iJ = pre.mJ; iM = pre.mM; return; }
+    if (s2 == pre.keep) { q = pre.qw; iL = pre.mL; iJ = pre.mJ; iM = pre.mM; return; }
     q = p.qword[idn];
     SFS_COUNT(6, 4);
     iL = kL ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R + s2) * nl + vl, pol_first) : 0;
@@ -556,7 +567,11 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   if (R1) { s = 0; todo = 0; }
   else if (todo) {
     s = (u32)__ffs((int)todo) - 1u; todo &= todo - 1u;
-    u32 q0; load_view(s, cur, q0, mL, mJ, mM); merge_q(cur, q0);
+    u32 q0;
+    if (ahead && s == pre.keep) { cur = ah.rec; q0 = pre.qw; mL = pre.mL; mJ = pre.mJ; mM = pre.mM; SFS_PROBE(18); }
+    else load_view(s, cur, q0, mL, mJ, mM);
+    merge_q(cur, q0);
+    first_view = s;
   }
 #pragma unroll 1
   while (s < R) {
@@ -601,9 +616,12 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
       const u32 mx = max(r.txl, max(r.txj, r.txm));
       if (mx) {
         if (!have_targets) {
-          u32 cand[FMAX];
-          pick_issue<FMAX, STAGED>(p, sv, v, row0, deg, pol_first, cand);
-          nt = pick_finish<FMAX>(v, cand, tg);
+          if (ahead) nt = pick_finish<FMAX>(v, ah.cand, tg);
+          else {
+            u32 cand[FMAX];
+            pick_issue<FMAX, STAGED>(p, sv, v, row0, deg, pol_first, cand);
+            nt = pick_finish<FMAX>(v, cand, tg);
+          }
           have_targets = true;
         }
         u32* const planeL = p.inbox_wr + (size_t)(KIND_LEAVE * R + s) * nl;
@@ -635,7 +653,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
       c.pending += (!suspect && (queued || (watching && r.mlstate == ML_ALIVE))) ? 1 : 0;
       // (its own failed probe is a confirmation only while its bucket is not in the confirmer set and the set is not full)
       awake |= queued || (watching && (r.mlstate == ML_ALIVE || (suspect && cold_can_confirm(p.rules.k, r.mask, v))));
-      if (suspect && r.deadline != 0) { has_timer = true; mind = min(mind, r.deadline); }
+      if (suspect && r.deadline != 0) { has_timer = true; mind_node = min(mind_node, r.deadline); dl_moved |= r.deadline != orig.w[4]; }
     }
     dsusp += ((up_s && r.mlstate == ML_SUSPECT) ? 1 : 0) - (susp_before ? 1 : 0);
     pack_words(r, cur);
@@ -662,6 +680,14 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   // sticky otherwise (a view that was not visited may run a timer: it is found when its tile comes due)
   const u32 busy2 = (awake ? 1u : 0u) | (busy & 4u) | ((has_timer || (!visit_all && (busy & 8u))) ? 8u : 0u);
   if (busy2 != busy) p.busy[vl] = (u8)busy2;
+  // node_due: a lower bound of the node's earliest running deadline, exact after a visit of every view.  A view's deadline only moves
+  // while the view is visited, so views that were not visited are still covered by the word as it stands.
+  if (has_timer) {
+    if (visit_all || !(busy & 8u)) p.node_due[vl] = mind_node;
+    else if (dl_moved) atomicMin(p.node_due + vl, mind_node);
+  }
+  mind = min(mind, mind_node);
+  if (!visit_all) mind = min(mind, sleeping_deadline(pre, due));   // its tile's entry was reset: timers of the views not visited go back with the node's word
   // The scheduler must know whether anybody stays awake.  A node that sent a packet this tick shows in the row's message count;
   // the others (a watcher on probe duty, a queue that has no peer to go to, a transmit queued after the send phase) are rare.
   if (awake && min(nt, max_tx) == 0) atomicAdd(p.sched + SCHED_AWAKE, 1u);
@@ -871,12 +897,18 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
         pr[g] = Pre{};
         if (g < ng) {
           const u32 vn = ((tile0 + gt_s[g]) << TILE_SHIFT) + threadIdx.x;
-          if (vn < p.n_local) pr[g] = prefetch_node<R1>(p, vn, kL, kJ, kM, pol_first);
+          if (vn < p.n_local) pr[g] = prefetch_node<R1>(p, vn, kL, kJ, kM, pol_first, (hot_s[gt_s[g]] & 2u) != 0);
         }
       }
 #pragma unroll
       for (u32 g = 0; g < GROUP; ++g) {
-        const bool act = g < ng && node_active(p, pr[g], (hot_s[gt_s[g]] & 2u) != 0);   // lanes past n_local hold an empty Pre
+        const bool due_g = g < ng && (hot_s[gt_s[g]] & 2u) != 0;
+        const bool act = g < ng && node_active(p, pr[g], due_g);   // lanes past n_local hold an empty Pre
+        if (due_g) {                                         // (warp-uniform) nodes whose own timers run later hand their deadline back to the wheel
+          const u32 wm = warp_min(act ? NO_DEADLINE : sleeping_deadline(pr[g], true));
+          if (lane == 0 && wm != NO_DEADLINE) atomicMin(p.tile_due + tile0 + gt_s[g], wm);
+          if (!act && (pr[g].busy & 8u)) SFS_PROBE(20);
+        }
         const u32 bal = __ballot_sync(0xffffffffu, act);
         if (bal) {
           u32 base = 0;
@@ -898,16 +930,17 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
           const u32 vl = ((tile0 + ti) << TILE_SHIFT) + (a.x & 0xffu);
           Pre pre;
           if (R1) {
-            pre.busy = (a.x >> 16) & 0xffu; pre.any = (a.x >> 24) & 1u; pre.mL = a.y; pre.mJ = a.z; pre.mM = a.w;
+            pre.busy = (a.x >> 16) & 0xffu; pre.any = (a.x >> 24) & 1u; pre.mL = a.y; pre.mJ = a.z; pre.mM = a.w; pre.keep = 0;
+            pre.nd = (hot_s[ti] & 2u) ? p.node_due[vl] : NO_DEADLINE;
             pre.qw = p.qword[vl];                             // not carried through the list: issued here, in flight with the state loads
             pre.mailmask = pre.any ? 1u : 0u; pre.qmask = pre.qw ? 1u : 0u;
             SFS_COUNT(6, 4);
           } else {
-            pre = prefetch_node<R1>(p, vl, kL, kJ, kM, pol_first);   // per-view masks are not carried through the list: the few active nodes read them again
+            pre = prefetch_node<R1>(p, vl, kL, kJ, kM, pol_first, (hot_s[ti] & 2u) != 0);   // per-view masks are not carried through the list: the few active nodes read them again
           }
-          u32 mind = NO_DEADLINE;
+          u32 mind = NO_DEADLINE, fv_unused = 0;
           int dsusp = 0;
-          const bool pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, false, (hot_s[ti] & 2u) != 0, pol_first, pol_last, c, mind, dsusp);
+          const bool pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, false, (hot_s[ti] & 2u) != 0, pol_first, pol_last, c, mind, dsusp, Ahead<FMAX>{}, fv_unused);
           if (mark && pend) pend_s[g] = 1;
           if (mind != NO_DEADLINE) atomicMin(p.tile_due + tile0 + ti, mind);      // the list mixes tiles: per-lane registration (few active nodes)
           if (dsusp) atomicAdd(&dsusp_s, dsusp);
@@ -921,24 +954,41 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
   } else {
   // Walk the hot tiles of this CTA.  The 13 "is there anything to do" bytes of the NEXT hot tile (busy byte, inbox
   // words) are requested before the current tile is processed, so an idle tile costs no exposed round trip.
+  // Multi-slot runs, saturated ticks: node word, peers' ids and the probable first view's record travel one tile ahead too (Ahead).
+  const bool ahead_on = !R1 && p.udeg != 0 && (p.ahead == 2u || (p.ahead == 1u && saturated));
+  u32 first_view = 0;                                      // the first view this thread visited in its last tile
   auto prefetch_tile = [&](u32 ti) -> Pre {
     const u32 vn = ((tile0 + ti) << TILE_SHIFT) + threadIdx.x;
-    return vn < p.n_local ? prefetch_node<R1>(p, vn, kL, kJ, kM, pol_first) : Pre{};
+    return vn < p.n_local ? prefetch_node<R1>(p, vn, kL, kJ, kM, pol_first, (hot_s[ti] & 2u) != 0, first_view) : Pre{};
+  };
+  auto ahead_tile = [&](u32 ti, u32 keep) -> Ahead<FMAX> {
+    Ahead<FMAX> a = {};
+    const u32 vn = ((tile0 + ti) << TILE_SHIFT) + threadIdx.x;
+    if (!R1 && ahead_on && vn < p.n_local) {
+      a.ns = ld_u64_stream(p.node_state + vn, pol_first);
+      a.rec = ld_rec256(p.rec + 2 * ((size_t)keep * p.stride + vn), pol_first);
+      pick_issue<FMAX, false>(p, StageView{}, p.first + vn, vn * p.udeg, p.udeg, pol_first, a.cand);
+      a.valid = 1;
+      SFS_PROBE(19);
+    }
+    return a;
   };
   u32 i = 0;
   while (i < ntile && !hot_s[i]) ++i;
   Pre pre_next = {};
-  if (i < ntile) pre_next = prefetch_tile(i);
+  Ahead<FMAX> ah_next = {};
+  if (i < ntile) { pre_next = prefetch_tile(i); ah_next = ahead_tile(i, pre_next.keep); }
   while (i < ntile) {
     const Pre pre = pre_next;
+    const Ahead<FMAX> ah = ah_next;
     u32 j = i + 1;
     while (j < ntile && !hot_s[j]) ++j;
-    if (j < ntile) pre_next = prefetch_tile(j);
+    if (j < ntile) { pre_next = prefetch_tile(j); ah_next = ahead_tile(j, pre_next.keep); }
     const u32 vl = ((tile0 + i) << TILE_SHIFT) + threadIdx.x;
     bool pend = false;
     u32 mind = NO_DEADLINE;
     int dsusp = 0;
-    if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, saturated, (hot_s[i] & 2u) != 0, pol_first, pol_last, c, mind, dsusp);
+    if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, saturated, (hot_s[i] & 2u) != 0, pol_first, pol_last, c, mind, dsusp, ah, first_view);
     if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + i] = 1;
     note_timers(p, tile0 + i, mind, dsusp, &dsusp_s);
     if (SHARDED) wrote_remote |= flush_xwarp(p, xs, false, resv, rlen);
@@ -1049,7 +1099,9 @@ __global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constan
       Pre pre = {};
       pre.busy = p.busy[vl];
       pre.qw = p.qword[vl];          // 4 B per node, read directly (not worth a sixth bulk copy per stage)
-      pend = process_node<TRACE, FMAX, false, true, true>(p, sv, nullptr, vl, pre, kL, kJ, kM, mark, true, (hot_s[ti] & 2u) != 0, pol_first, pol_last, c, mind, dsusp);
+      pre.nd = (hot_s[ti] & 2u) ? p.node_due[vl] : NO_DEADLINE;
+      u32 fv_unused = 0;
+      pend = process_node<TRACE, FMAX, false, true, true>(p, sv, nullptr, vl, pre, kL, kJ, kM, mark, true, (hot_s[ti] & 2u) != 0, pol_first, pol_last, c, mind, dsusp, Ahead<FMAX>{}, fv_unused);
     }
     if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + ti] = 1;
     note_timers(p, tile0 + ti, mind, dsusp, &dsusp_s);
@@ -1173,7 +1225,7 @@ __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__
     // every view of the node was visited: its busy byte is exact (bit 0 awake, bit 2 watcher, bit 3 running timer)
     p.busy[vl] = (u8)((awake ? 1u : 0u) | (wmask ? 4u : 0u) | (has_timer ? 8u : 0u));
     if (awake) p.hot_wr[vl >> TILE_SHIFT] = 1;
-    if (has_timer) atomicMin(p.tile_due + (vl >> TILE_SHIFT), mind);
+    if (has_timer) { atomicMin(p.tile_due + (vl >> TILE_SHIFT), mind); p.node_due[vl] = mind; }
   }
   const u64 c = warp_sum64((u64)d_changed), q = warp_sum64((u64)d_pending), ds = warp_sum64((u64)d_susp), h = TRACE ? warp_sum64(d_hash) : 0;
   if ((threadIdx.x & 31) == 0) {

@@ -114,6 +114,8 @@ struct TickParams {
   // instead of being recounted every tick.  Ticks in which provably nothing can happen (no mail, no queued transmit, no probe
   // duty, no timer due, no host operation, no anti-entropy / reaper round) return at once (sched[SCHED_IDLE_UNTIL]).
   u32* tile_due;              // [n_tiles]
+  u32* node_due;              // [n_local] lower bound of the node's own earliest running deadline (exact after a visit of all its views; meaningful while busy bit 3 is set):
+                              // when a tile comes due only the nodes whose own deadline has been reached visit their views, the others re-register this word
   const u8* hot_static;       // [n_tiles] tiles that hold a watcher (static; never consumed)
   u32* sched;                 // scheduler words (SCHED_*), u64 suspect-view counter at sched + SCHED_SUSPECTS
   u32 sleep_on;               // 0: SERFSIM_NO_SKIP — every tile, every view, every tick
@@ -122,6 +124,7 @@ struct TickParams {
   // block): one launch less per tick.  With injectors their kernel still writes windows after this one, and publish_kernel follows it.
   u32* const* peer_ctrl; u32 stamp, xpar, loopback, fuse_publish;
   u32 shard_inv, xcap;        // floor(2^32 / shard_size) (a remote target's shard without a division); staged entries per warp and peer
+  u32 ahead;                  // multi-slot runs: 1 = saturated ticks request node word, peers and the probable first view's record one tile ahead; 2 = every tick (tests); 0 = off (SERFSIM_AHEAD)
   u32* host_idle_until;       // SCHED_IDLE_UNTIL mirrored into mapped pinned host memory: serfsim_run_until_converged does not even launch the ticks the cluster sleeps through
 };
 constexpr u32 SCHED_TICKET = 0, SCHED_IDLE_UNTIL = 1, SCHED_UE_ACTIVITY = 2, SCHED_AWAKE = 3, SCHED_SUSPECTS = 4 /* u64 */,

@@ -144,6 +144,7 @@ def test_sleeping_views_timer_wheel_and_idle_ticks():
             assert L.emu_probe(17) > 10
         if not trace:
             assert L.emu_probe(5) > 0
+            assert L.emu_probe(20) > 0             # nodes of a due tile whose own deadline (node_due) lies later: no view visited
         assert_same(f, o, sc.slots, with_hash=bool(trace))
     # stepping one tick at a time takes the same decisions (the scheduler words live on the device, not in the call)
     f = sc.build(emu_sim, trace=1)
@@ -152,6 +153,27 @@ def test_sleeping_views_timer_wheel_and_idle_ticks():
     o2 = sc.build(oracle_sim, trace=1)
     o2.step(to[0] + 1)
     assert_same(f, o2, sc.slots)
+
+
+@pytest.mark.parametrize("ahead", ["0", "2"])
+def test_multi_slot_requests_one_tile_ahead(ahead, monkeypatch):
+    """Multi-slot runs request node word, gossip peers and the probable first view's record one tile ahead in saturated ticks
+    (SERFSIM_AHEAD, tick_kernel.cu `Ahead`); 2 forces the path in every tick of the tile walk, 0 switches it off.  Probe 19 counts the
+    nodes requested ahead, probe 18 the records that were used (the guess of the first view was right)."""
+    import ctypes as C
+    from emu_lib import lib
+    L = lib()
+    L.emu_probe.restype = C.c_ulong
+    monkeypatch.setenv("SERFSIM_AHEAD", ahead)
+    monkeypatch.setenv("SERFSIM_COMPACT", "0")             # every tick walks its tiles
+    L.emu_probe_reset()
+    for sc in (scenarios.dissemination_storm(3000, 12, 3, slots=2, seed=3, with_fail=True), scenarios.random_graph_leave(5000, 16, 4, seed=2, slots=3),
+               scenarios.fuzz(3), scenarios.fuzz(11), scenarios.fuzz_prune(5)):
+        run_both(sc)
+    if ahead == "2":
+        assert L.emu_probe(19) > 1000 and L.emu_probe(18) > 100, (L.emu_probe(19), L.emu_probe(18))
+    else:
+        assert L.emu_probe(19) == 0
 
 
 def test_config1_shape_100k_nodes():
