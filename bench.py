@@ -120,9 +120,14 @@ def b_edge(fanout, p_dirty):
 
 
 # ---- the CPU oracle (test infrastructure): the checker of every step and the timed CPU baseline ----------------------
+_ALL_CPUS = None                                         # taken before the driver thread is bound to the GPU's NUMA node
+
+
 def physical_cpus():
     """One logical CPU per physical core of the cores this process may use, alternating between packages (NUMA nodes) so
     that consecutive oracle workers — which own consecutive id ranges — land on alternating memory controllers."""
+    if _ALL_CPUS is not None:
+        return _ALL_CPUS
     allowed = sorted(os.sched_getaffinity(0))
     by_pkg = {}
     for c in allowed:
@@ -225,6 +230,7 @@ def main():
                     help="leave_fail: SURVEY §8d item 4 (one subject leaves, one crashes; 2 tracked subjects); leave: the round-1 workload (1 subject leaves)")
     ap.add_argument("--ref-nodes", type=int, default=0, help="size of the bounded CPU sample (0: 1 M nodes inside the b200 arm, 2 M in the reference arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="A/B: leave the driver thread where the OS scheduler puts it")
     ap.add_argument("--no-check", action="store_true", help="skip the full-size oracle run every step is checked against")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -243,6 +249,10 @@ def main():
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
+    global _ALL_CPUS
+    _ALL_CPUS = physical_cpus()                          # the oracle's workers keep the whole machine (they pin themselves, one per physical core)
+    from serf_b200 import bind_thread_near_gpu
+    near = None if args.no_numa_bind else bind_thread_near_gpu(local_rank)   # the driver thread and its pinned buffers: the GPU's own NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -310,8 +320,9 @@ def main():
         t, ok, *_ = one_step()
         check_step(t, ok)
     time.sleep(1.2)                                      # let nvidia-smi come up before the timed regions (all ranks: steps are collective)
-    for _ in range(2):
-        one_step()
+    for k in range(4):                                   # … and the read-back path: staging buffers, copy stream and events are created on first use,
+        one_step(pins[k & 1])                            # all four ring entries once (device allocations inside the timed region cost up to 15 ms per step)
+    g.results_wait()
 
     # ---- device-timed region: K steps ----
     sync_all()
@@ -390,7 +401,8 @@ def main():
                              "note": "achieved = algorithmic bytes of the step / device time of the step (CUDA events on the launch stream around all its tick launches, idle timer-wait ticks included)"},
                 "e2e": {"value": total_eu / wall_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": 1e3 * wall_e2e / args.steps},
-                "gpu_launches": launches, "clocks": clocks}
+                "gpu_launches": launches, "clocks": clocks,
+                "host": {"driver_thread_cpus": (f"{len(near)} CPUs of the GPU's NUMA node" if near else "unbound")}}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = {k: v for k, v in time_oracle(args, args.ref_nodes or 1_000_000).items() if k not in ("seconds", "ticks")}
         print(json.dumps(line))

@@ -133,6 +133,9 @@ struct serfsim {
   u64 op_seq = 0;
   std::vector<u32> subj;
   u32 up_mask = 0;
+  u32 ever_down = 0;               // subjects that have been down at some tick since the reset (only those are probed, suspected, run timers)
+  u32 sv = 1;                      // single-view ticks of multi-slot runs: 1 = dual launch, 2 = check mode, 0 = off (SERFSIM_SV, tick_kernel.cuh)
+  int grid_sv = 0;                 // grid of the single-view kernel
   u32 tick = 0;
   bool has_topo = false;
   u32 stage_col_bytes = 0;         // 0: direct-load kernel; else bytes of CSR per TMA stage
@@ -270,6 +273,7 @@ int launch_ticks(serfsim* h, u32 n) {
     p.n_local = h->count; p.first = h->first; p.n_global = h->N; p.R = h->R;
     p.fanout = h->cfg.fanout; p.probe_every = h->cfg.probe_interval_ticks; p.tick = t;
     p.down_mask = (~h->up_mask) & ((1u << h->R) - 1);
+    h->ever_down |= p.down_mask;
     p.seed_lo = (u32)h->cfg.seed; p.seed_hi = (u32)(h->cfg.seed >> 32); p.ev_begin = eb; p.ev_end = ee;
     p.rules = h->rules;
     for (u32 s = 0; s < h->R; ++s) p.subj[s] = h->subj[s];
@@ -334,8 +338,27 @@ int launch_ticks(serfsim* h, u32 n) {
       launch_uevent(u, h->cfg.trace != 0, h->stream);
       h->last_launches++;
     }
+    // Multi-slot runs in production mode: the general kernel and the single-view kernel are both launched, the device decides (SV_*)
+    const bool sv_ok = h->sv && h->R > 1 && h->R < 32 && !h->cfg.trace && p.sleep_on && !h->byz_on && __builtin_popcount(h->ever_down) == 1;
+    if (sv_ok) {
+      const bool all = ee > eb || p.reap_now;                 // a host operation or a reaper round visits every view
+      p.views_host = all ? 0xffffffffu : h->ever_down;
+      p.sv_mode = h->sv == 2 ? SV_CHECK : SV_GENERAL;
+      p.sv_slot = (u32)__builtin_ctz(h->ever_down); p.sv_R = h->R;
+    }
     launch_tick(p, h->cfg.trace != 0, h->grid, h->stream);
     h->last_launches++;
+    if (sv_ok && h->sv == 1) {
+      TickParams q = p;                                    // the planes as the single-slot kernel sees them: they start at view sv_slot
+      const u32 s0 = p.sv_slot;
+      q.sv_mode = SV_SINGLE; q.gate.evaluate = 0u; q.sv_wshift = s0;
+      q.rec = p.rec + 2 * (size_t)s0 * h->stride; q.qword = p.qword + (size_t)s0 * h->stride;
+      q.inbox_rd = p.inbox_rd + (size_t)s0 * h->stride; q.inbox_wr = p.inbox_wr + (size_t)s0 * h->stride;
+      q.subj[0] = p.subj[s0]; q.down_mask = (p.down_mask >> s0) & 1u;
+      q.tiles_per_cta = (h->n_tiles + h->grid_sv - 1) / h->grid_sv;
+      launch_tick_single_view(q, h->grid_sv, h->stream);
+      h->last_launches++;
+    }
     if (h->byz_n) {                            // stale entries of this shard's injectors (before the exchange: peers in other shards get window entries)
       ByzParams b{};
       b.n_byz = h->byz_n; b.first = h->first; b.R = h->R; b.stride = h->stride; b.fanout = h->cfg.fanout; b.tick = t;
@@ -366,7 +389,7 @@ int launch_ticks(serfsim* h, u32 n) {
       d.ue_n = h->ue_table.n; d.ue_inbox_wr = h->ue_table.n ? h->d_ue_inbox[t & 1] : nullptr; d.ue_ltime = h->d_ue_ltime;
       d.my_row = p.row; d.grow = h->d_grow + (size_t)t * 8; d.gate = gate_word;
       d.sums = reinterpret_cast<const u64*>(reinterpret_cast<const unsigned char*>(h->d_ctrl) + CTRL_SUMS_OFF) + (size_t)xpar * 8 * CTRL_FIELDS;
-      d.sched = h->d_sched; d.host_idle_until = h->d_pin_ctl + 2; d.tick = t; d.sleep_on = p.sleep_on;
+      d.sched = h->d_sched; d.sched_rw = h->d_sched; d.host_idle_until = h->d_pin_ctl + 2; d.tick = t; d.sleep_on = p.sleep_on;
       launch_drain(d, h->stream);
       h->last_launches += 1;
       h->xepoch++;
@@ -457,6 +480,7 @@ int check_overflow(serfsim* h) {
   const u32 ov = *(volatile u32*)h->pin_overflow;
   if (ov == 1) return fail(SERFSIM_E_OVERFLOW, "a Lamport time or incarnation left the 32-bit device range");
   if (ov == 2) return fail(SERFSIM_E_COMM, "cross-shard window overflow (raise SERFSIM_WIN_FACTOR)");
+  if (ov == 4) return fail(SERFSIM_E_INVAL, "single-view check (SERFSIM_SV=2): a view outside the set of views with business had business");
   if (ov) return fail(SERFSIM_E_COMM, "corrupt cross-shard window entry");
   return 0;
 }
@@ -523,6 +547,7 @@ int ue_reset(serfsim* h) {                      // bootstrap event state: clock 
 int do_reset(serfsim* h, u64 seed) {
   h->cfg.seed = seed; h->tick = 0; h->ops.clear(); h->op_keys.clear(); h->ops_dirty = false; h->rows.clear();
   h->up_mask = (h->R >= 32) ? 0xffffffffu : ((1u << h->R) - 1);
+  h->ever_down = 0;
   h->reported.assign(h->R, (u8)ST_ALIVE);
   const size_t inbox_bytes = (size_t)3 * h->R * h->stride * sizeof(u32);
   launch_init_state(h->d_rec, h->d_node, h->count, h->stride, h->R, h->cfg.init_status_ltime, h->cfg.init_clock, h->stream);
@@ -698,6 +723,7 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
     h->ctas_per_sm = (h->R == 1) ? ((e && atoi(e) == 5) ? 5 : (cfg->world_size > 1 ? tick_ctas_per_sm_r1s() : tick_ctas_per_sm_r1())) : tick_ctas_per_sm_rn();
   }
   h->grid = tick_grid_size(h->count, h->ctas_per_sm);
+  h->grid_sv = tick_grid_size(h->count, cfg->world_size > 1 ? tick_ctas_per_sm_r1s() : tick_ctas_per_sm_r1());
   {
     // L2 set-aside for persisting (evict_last) lines: the randomly addressed inbox planes live there
     int max_persist = 0, max_window = 0;
@@ -713,6 +739,7 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
   if (const char* e = getenv("SERFSIM_NO_SKIP")) h->no_skip = atoi(e) != 0;
   if (const char* e = getenv("SERFSIM_COMPACT")) h->compact = atoi(e) != 0;
   if (const char* e = getenv("SERFSIM_AHEAD")) h->ahead = (u32)std::min(2, std::max(0, atoi(e)));
+  if (const char* e = getenv("SERFSIM_SV")) h->sv = (u32)std::min(2, std::max(0, atoi(e)));
   if (cfg->world_size > 1) {
     // receive windows: one segment per peer; expected entries per tick and pair ≈ shard · fanout · R · kinds / world
     if (cfg->world_size > 8) return bail(fail(SERFSIM_E_INVAL, "world_size > 8"));

@@ -137,7 +137,10 @@ struct StageView {
 };
 
 struct Counters {          // per-thread, reduced once per CTA; rare counters (events, suspects) go straight to the trace row
-  u32 packets, edges, changed, pending, kL, kJ, kM;
+  u32 packets, edges, changed, pending, kL, kJ, kM, views;
+  // single-view kernels (64 registers per thread, on the edge of spilling) keep six of them in three: a thread visits at most
+  // MAX_TILES_PER_CTA = 1024 nodes, each adds at most MAX_FANOUT = 8 to a counter — 16 bits hold that
+  u32 pe /* packets | edges << 16 */, cp /* changed | pending << 16 */, kLJ /* kL | kJ << 16 */;
   u64 hash;
 };
 
@@ -184,7 +187,7 @@ __device__ __forceinline__ void deliver(const TickParams& p, XStage* xs, u32* pl
   } else {
     u32 dloc;
     const u32 shard = shard_of(p, dst, dloc);
-    const u64 e = ((u64)val1 << 32) | ((u64)s << 28) | ((u64)kind << 26) | dloc;
+    const u64 e = ((u64)val1 << 32) | ((u64)(s + p.sv_wshift) << 28) | ((u64)kind << 26) | dloc;   // (a single-view launch numbers its view 0: the entry carries the real one)
     // warp-aggregated append: the lanes of this call that target the same shard reserve their slots with ONE
     // shared-memory atomic on the warp's own counter (divergent callers of the same warp may interleave: keep it atomic)
     const u32 peers = __match_any_sync(__activemask(), shard);
@@ -338,13 +341,15 @@ __device__ __forceinline__ u32 pick_finish(u32 v, const u32 (&cand)[FMAX], u32 (
 struct Pre { u32 busy, mL, mJ, mM, any, qw, mailmask, qmask, keep, nd; };   // mL, mJ, mM, qw: the words of view `keep` (0 in single-slot runs)
 template <bool R1>
 __device__ __forceinline__ Pre prefetch_node(const TickParams& p, u32 vl, bool kL, bool kJ, bool kM, u64 pol_first, bool due, u32 keep = 0) {
-  const u32 nl = p.stride, R = R1 ? 1u : p.R;
+  // R1: the kernel visits exactly one view, the one its planes start with (single-slot runs; single-view ticks of multi-slot runs, whose
+  // parameter block points at the active view — the distance between the planes of two kinds is p.R views either way)
+  const u32 nl = p.stride, R = p.R, s_hi = R1 ? 1u : R;
   Pre x;
   x.busy = p.busy[vl];
-  x.nd = due ? p.node_due[vl] : NO_DEADLINE;
+  x.nd = (!R1 && due) ? p.node_due[vl] : NO_DEADLINE;    // single-view kernels (64 registers) read it where it is needed instead: one register less across the tile loop
   x.keep = R1 ? 0u : keep;
   x.mL = x.mJ = x.mM = x.qw = 0; x.any = 0; x.mailmask = 0; x.qmask = 0;
-  for (u32 s2 = 0; s2 < R; ++s2) {
+  for (u32 s2 = 0; s2 < s_hi; ++s2) {
     const u32 l = kL ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_LEAVE * R + s2) * nl + vl, pol_first) : 0u;
     const u32 j = kJ ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_JOIN * R + s2) * nl + vl, pol_first) : 0u;
     const u32 m = kM ? ld_u32_stream(p.inbox_rd + (size_t)(KIND_ML * R + s2) * nl + vl, pol_first) : 0u;
@@ -461,14 +466,14 @@ __device__ SFS_COLD bool cold_can_confirm(u32 k, u32 mask, u32 v) {
 // every node of it that carries a timer (busy bit 3) visits all its views.
 template <bool TRACE, int FMAX, bool SHARDED, bool R1, bool STAGED>
 __device__ __forceinline__ bool process_node(const TickParams& p, const StageView& sv, XStage* xs, const u32 vl, const Pre& pre, const bool kL, const bool kJ, const bool kM, const bool mark, const bool saturated,
-                                             const bool due, const u64 pol_first, const u64 pol_last, Counters& c, u32& mind, int& dsusp, const Ahead<FMAX>& ah, u32& first_view) {
+                                             const bool due, const u64 pol_first, const u64 pol_last, Counters& c, u32& mind, int& dsusp, const Ahead<FMAX>& ah, u32& first_view, const u32 sv_views = 0xffffffffu) {
   static_assert(!STAGED || R1, "the staged path is the single-slot path");
   const u32 lt = threadIdx.x;              // index inside the staged tile
   const u32 v = p.first + vl;
   const u32 t = p.tick;
   const u32 limit = p.rules.limit;
   const u32 nl = p.stride;               // plane stride (n_local rounded up to a whole tile)
-  const u32 R = R1 ? 1u : p.R;
+  const u32 R = p.R;                     // R1: one view is visited, the first of the planes as this launch sees them (they keep the distance of p.R views between kinds)
 
   // ---- loads.  Saturated ticks (the previous tick delivered to at least half of the nodes): everything a node
   // needs is requested up front, independent loads in flight together.  Otherwise most nodes are idle: read only
@@ -499,11 +504,14 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   if (STAGED) { mL = kL ? sv.inL[lt] : 0u; mJ = kJ ? sv.inJ[lt] : 0u; mM = kM ? sv.inM[lt] : 0u; }
 
   // ---- idle exit: nothing received (any slot), nothing queued, no host operation, no probe duty, no timer due ----
-  const bool timers_due = due && (busy & 8u) && pre.nd <= p.tick;
-  if (!TRACE && !STAGED && !node_active(p, pre, due)) { mind = min(mind, sleeping_deadline(pre, due)); if (due && (busy & 8u)) SFS_PROBE(20); return false; }
-  if (STAGED && !TRACE && !((busy & 7u) || (mL | mJ | mM) || p.reap_now || timers_due)) { mind = min(mind, sleeping_deadline(pre, due)); return false; }
+  u32 nd = pre.nd;                                       // the node's own earliest deadline: matters in due tiles, for nodes that run timers
+  if (R1 && due && (busy & 8u)) nd = p.node_due[vl];
+  const u32 sleeping = (due && (busy & 8u)) ? nd : NO_DEADLINE;
+  const bool timers_due = sleeping <= p.tick;
+  if (!TRACE && !STAGED && !((busy & 7u) != 0 || pre.any != 0 || p.reap_now != 0 || timers_due)) { mind = min(mind, sleeping); if (due && (busy & 8u)) SFS_PROBE(20); return false; }
+  if (STAGED && !TRACE && !((busy & 7u) || (mL | mJ | mM) || p.reap_now || timers_due)) { mind = min(mind, sleeping); return false; }
   // (the watcher mask — subjects this node can probe, it has them as neighbours — is re-read where a watcher needs it: a handful of nodes)
-#define SFS_WMASK() ((busy & 4u) ? (u32)p.watch[vl] : 0u)
+#define SFS_WMASK() ((busy & 4u) ? ((u32)p.watch[vl] >> p.sv_wshift) : 0u)   /* sv_wshift: the view a single-view launch works on (0 in every other launch) */
   const bool ahead = !R1 && !STAGED && ah.valid;       // node word, peers' ids and the record of view pre.keep were requested a tile ago
   if (ahead) { ns = ah.ns; row0 = vl * p.udeg; row1 = row0 + p.udeg; }
   else if (!upfront) { load_node(); if (R1) load_rec0(); }
@@ -538,7 +546,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   bool have_targets = false;
   u32 max_tx = 0;
   bool awake = false, has_timer = false, dl_moved = false;
-  u32 mind_node = NO_DEADLINE;             // earliest running suspicion deadline among the views visited
+  // (`mind`, NO_DEADLINE on entry: the earliest running suspicion deadline among the views visited)
 
   // Views to visit: all of them when the node as a whole has business (trace, reaper round, host operation, timers due);
   // otherwise those with mail, queued transmits or probe duty (a watcher's view of a subject that is down).
@@ -586,6 +594,8 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
     unpack_words(cur, r);
     const bool self = (p.subj[s] == v);
     const bool susp_before = up_r && r.mlstate == ML_SUSPECT;
+    if (!R1 && p.sv_mode == SV_CHECK && !((sv_views >> s) & 1u) && up_r &&
+        ((mL | mJ | mM) || (r.txl | r.txj | r.txm) || r.mlstate == ML_SUSPECT)) *p.overflow = 4;     // SERFSIM_SV=2: the set of views with business was not a superset
 
     // ---------------- Phase R ----------------
     if (up_r && (mL | mJ | mM)) {
@@ -602,7 +612,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
       if (!(r.flags & 1) && r.status != TY_NONE && (r.status != (orig.w[6] & 0xff) || r.st != orig.w[0])) r.leave_tick = t + 1;   // NodeIntent.wall_time (types/member.rs:32)
       Words mid;
       pack_words(r, mid);
-      c.changed += differs(mid, orig) ? 1 : 0;
+      if (R1) c.cp += differs(mid, orig) ? 1u : 0u; else c.changed += differs(mid, orig) ? 1 : 0;
     }
     // ---------------- Phase E ----------------
     if (op) { Rec tr = r; u32 ck = clock, ss = sstate; cold_host_op(tr, ck, ss, op, op_slot == s, self, up_r, limit); r = tr; clock = ck; sstate = ss; }
@@ -635,8 +645,8 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
           if ((u32)k < sJ) deliver<SHARDED>(p, xs, planeJ, tg[k], KIND_JOIN, s, vJ, pol_last, mark);
           if ((u32)k < sM) deliver<SHARDED>(p, xs, planeM, tg[k], KIND_ML, s, vM, pol_last, mark);
         }
-        c.kL += sL; c.kJ += sJ; c.kM += sM;
-        c.edges += min(mx, nt);
+        if (R1) { c.kLJ += sL | (sJ << 16); c.kM += sM; c.pe += min(mx, nt) << 16; }
+        else { c.kL += sL; c.kJ += sJ; c.kM += sM; c.edges += min(mx, nt); }
         max_tx = max(max_tx, mx);
         r.txl -= sL; r.txj -= sJ; r.txm -= sM;
       }
@@ -648,12 +658,13 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
       // noticed yet.  Suspect views are counted by the persistent counter (they sleep), the others here.  A watcher's view of
       // a down subject stays awake while it is Alive or Suspect: its own failed probe may still start or confirm the suspicion.
       const bool queued = (r.txl | r.txj | r.txm) != 0;
+      if (!R1 && (queued || mx)) c.views |= 1u << s;                  // the view sent mail or keeps a queue: it has business in the next tick (single-view ticks)
       const bool watching = (busy & 4u) && p.probe_every && ((p.down_mask >> s) & 1) && !self && ((SFS_WMASK() >> s) & 1);
       const bool suspect = r.mlstate == ML_SUSPECT;
-      c.pending += (!suspect && (queued || (watching && r.mlstate == ML_ALIVE))) ? 1 : 0;
+      { const u32 pnd = (!suspect && (queued || (watching && r.mlstate == ML_ALIVE))) ? 1u : 0u; if (R1) c.cp += pnd << 16; else c.pending += pnd; }
       // (its own failed probe is a confirmation only while its bucket is not in the confirmer set and the set is not full)
       awake |= queued || (watching && (r.mlstate == ML_ALIVE || (suspect && cold_can_confirm(p.rules.k, r.mask, v))));
-      if (suspect && r.deadline != 0) { has_timer = true; mind_node = min(mind_node, r.deadline); dl_moved |= r.deadline != orig.w[4]; }
+      if (suspect && r.deadline != 0) { has_timer = true; mind = min(mind, r.deadline); dl_moved |= r.deadline != orig.w[4]; }
     }
     dsusp += ((up_s && r.mlstate == ML_SUSPECT) ? 1 : 0) - (susp_before ? 1 : 0);
     pack_words(r, cur);
@@ -675,7 +686,7 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   if (ns2 != ns) st_u64_stream(p.node_state + vl, ns2, pol_first);
   if (TRACE) c.hash += node_hash((u64)R * p.n_global + v, ns2);
   if (clock >= LTIME_LIMIT) *p.overflow = 1;
-  c.packets += min(nt, max_tx);
+  if (R1) c.pe += min(nt, max_tx); else c.packets += min(nt, max_tx);
   // busy byte: the op bit is consumed, the watcher bit is static; the timer bit is exact after a visit of every view and
   // sticky otherwise (a view that was not visited may run a timer: it is found when its tile comes due)
   const u32 busy2 = (awake ? 1u : 0u) | (busy & 4u) | ((has_timer || (!visit_all && (busy & 8u))) ? 8u : 0u);
@@ -683,11 +694,10 @@ __device__ __forceinline__ bool process_node(const TickParams& p, const StageVie
   // node_due: a lower bound of the node's earliest running deadline, exact after a visit of every view.  A view's deadline only moves
   // while the view is visited, so views that were not visited are still covered by the word as it stands.
   if (has_timer) {
-    if (visit_all || !(busy & 8u)) p.node_due[vl] = mind_node;
-    else if (dl_moved) atomicMin(p.node_due + vl, mind_node);
+    if (visit_all || !(busy & 8u)) p.node_due[vl] = mind;
+    else if (dl_moved) atomicMin(p.node_due + vl, mind);
   }
-  mind = min(mind, mind_node);
-  if (!visit_all) mind = min(mind, sleeping_deadline(pre, due));   // its tile's entry was reset: timers of the views not visited go back with the node's word
+  if (!visit_all) mind = min(mind, sleeping);   // its tile's entry was reset: timers of the views not visited go back with the node's word
   // The scheduler must know whether anybody stays awake.  A node that sent a packet this tick shows in the row's message count;
   // the others (a watcher on probe duty, a queue that has no peer to go to, a transmit queued after the send phase) are rare.
   if (awake && min(nt, max_tx) == 0) atomicAdd(p.sched + SCHED_AWAKE, 1u);
@@ -746,7 +756,7 @@ __device__ __forceinline__ void publish_to_peer(u32 r, u32 world, u32 rank, u32 
   u64* sums = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(peer_ctrl[r]) + CTRL_SUMS_OFF) + ((size_t)xpar * 8 + me) * CTRL_FIELDS;
 #pragma unroll
   for (int i = 0; i < 8; ++i) sums[i] = row[i];              // this rank's counters of the tick: every rank sums them on the device
-  sums[8] = sched[SCHED_LOCAL_QUIET]; sums[9] = sched[SCHED_LOCAL_UNTIL];
+  sums[8] = sched[SCHED_LOCAL_QUIET]; sums[9] = sched[SCHED_LOCAL_UNTIL]; sums[10] = sched[SCHED_VIEWS_NEW];
   __threadfence_system();
   st_release_sys(ctrl + 8 + me, stamp);
   send_count[r] = 0;
@@ -755,11 +765,13 @@ __device__ __forceinline__ void publish_to_peer(u32 r, u32 world, u32 rank, u32 
 // End of a tick: block reduction of the counters (warp shuffles, then shared memory) → one atomic per counter per CTA; the
 // LAST CTA to finish (ticket) completes the row and decides how long the cluster can sleep.
 // trace row: 0 packets, 1 edge_updates, 2 messages, 3 changed, 4 pending, (5 events, 6 suspects: direct), 7 hash
-template <bool TRACE>
+template <bool TRACE, bool PACKED>
 __device__ __forceinline__ void finish_tick(const TickParams& p, const Counters& c, u64 (*red)[BLOCK / 32], int dsusp_cta) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   __shared__ u32 last_s, due_min_s[BLOCK / 32];
-  const u64 vals[8] = {c.packets, c.edges, (u64)c.kL + c.kJ + c.kM, c.changed, c.pending, c.kL, c.kJ, c.kM};
+  const u32 kL = PACKED ? (c.kLJ & 0xffffu) : c.kL, kJ = PACKED ? (c.kLJ >> 16) : c.kJ;
+  const u64 vals[8] = {PACKED ? (c.pe & 0xffffu) : c.packets, PACKED ? (c.pe >> 16) : c.edges, (u64)kL + kJ + c.kM, PACKED ? (c.cp & 0xffffu) : c.changed,
+                       PACKED ? (c.cp >> 16) : c.pending, kL, kJ, c.kM};
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const u32 s = warp_sum((u32)vals[i]);
@@ -779,6 +791,7 @@ __device__ __forceinline__ void finish_tick(const TickParams& p, const Counters&
     }
   }
   if (TRACE && lane == 0 && hs) atomicAdd((unsigned long long*)(p.row + 7), (unsigned long long)hs);
+  { const u32 vw = __reduce_or_sync(0xffffffffu, c.views); if (lane == 0 && vw) atomicOr(p.sched + SCHED_VIEWS_NEXT, vw); }
   // ---- ticket: every CTA's counters are in the row before the last one reads it ----
   __threadfence();
   __syncthreads();
@@ -822,7 +835,13 @@ __device__ __forceinline__ void finish_tick(const TickParams& p, const Counters&
     } else {
       sched[SCHED_LOCAL_QUIET] = quiet ? 1u : 0u; sched[SCHED_LOCAL_UNTIL] = until;
     }
+    const u32 awake_n = sched[SCHED_AWAKE];
     sched[SCHED_AWAKE] = 0; sched[SCHED_UE_ACTIVITY] = 0; sched[SCHED_TICKET] = 0;
+    // (the single-view kernel keeps no per-thread set: its view has business again iff anything was sent or anybody stays awake)
+    const u32 sv_next = (p.sv_mode == SV_SINGLE && (row[2] != 0 || awake_n != 0)) ? (1u << p.sv_slot) : 0u;
+    // this tick's set stays readable (OLD) for the kernel of this tick that is launched after this one and must return
+    const u32 sv_base = p.tick >= sched[SCHED_VIEWS_FROM] ? sched[SCHED_VIEWS_NEW] : sched[SCHED_VIEWS_OLD];   // what this kernel's CTAs read when they started (nobody else writes these words)
+    sched[SCHED_VIEWS_OLD] = sv_base; sched[SCHED_VIEWS_NEW] = sched[SCHED_VIEWS_NEXT] | sv_next; sched[SCHED_VIEWS_FROM] = p.tick + 1; sched[SCHED_VIEWS_NEXT] = 0;   // the views with business in the next tick (kernels that follow in this tick — anti-entropy, drain — add to it)
   }
   if (p.world > 1 && p.fuse_publish) {
     // every CTA fenced its peer-window stores (system scope) before it took its ticket; this one saw all tickets
@@ -844,7 +863,19 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
   __shared__ __align__(16) unsigned char xs_mem[SHARDED ? sizeof(XStage) : 16];
   XStage* xs = reinterpret_cast<XStage*>(xs_mem);
   if (gate_closed(p.gate, blockIdx.x == 0 && threadIdx.x == 0)) return;   // the run is over (uniform over the grid): this tick does not exist
-  if (tick_is_idle(p.sched, p.tick, p.ev_begin, p.ev_end)) { write_idle_row<TRACE>(p); return; }   // nothing can happen in this tick (uniform)
+  if (tick_is_idle(p.sched, p.tick, p.ev_begin, p.ev_end)) { if (p.sv_mode != SV_SINGLE) write_idle_row<TRACE>(p); return; }   // nothing can happen in this tick (uniform)
+  // Single-view ticks of multi-slot runs (tick_kernel.cuh, SV_*): the general kernel and the single-view kernel are both launched; the
+  // set of views that can have business in this tick — known on the device since the end of the previous tick — decides which one runs.
+  u32 sv_views = 0xffffffffu;
+  if (p.sv_mode != SV_OFF) {
+    // (the kernel of this tick that ran before this one, if any, has already published the NEXT tick's set: SCHED_VIEWS_FROM says since when it holds)
+    const u32 sv_base = p.tick >= p.sched[SCHED_VIEWS_FROM] ? p.sched[SCHED_VIEWS_NEW] : p.sched[SCHED_VIEWS_OLD];
+    const u32 views = (sv_base | p.views_host) & ((1u << p.sv_R) - 1u);
+    const bool single = views == (1u << p.sv_slot);        // exactly the one view the single-view launch was set up for
+    if (p.sv_mode == SV_SINGLE) { if (!single) return; SFS_PROBE(21); }
+    else if (p.sv_mode == SV_GENERAL && single) return;
+    if (p.sv_mode == SV_CHECK && single) sv_views = views;   // checked only where the single-view kernel would have run
+  }
   if (threadIdx.x == 0) dsusp_s = 0;                       // ordered before its first use by the barrier after the tile scan
   Counters c = {};
   const bool kL = p.kinds_prev[KIND_LEAVE] != 0, kJ = p.kinds_prev[KIND_JOIN] != 0, kM = p.kinds_prev[KIND_ML] != 0;
@@ -897,17 +928,19 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
         pr[g] = Pre{};
         if (g < ng) {
           const u32 vn = ((tile0 + gt_s[g]) << TILE_SHIFT) + threadIdx.x;
-          if (vn < p.n_local) pr[g] = prefetch_node<R1>(p, vn, kL, kJ, kM, pol_first, (hot_s[gt_s[g]] & 2u) != 0);
+          if (vn < p.n_local) pr[g] = prefetch_node<R1>(p, vn, kL, kJ, kM, pol_first, false);   // (a node's own deadline is read below, in due tiles only: eight more live registers otherwise)
         }
       }
 #pragma unroll
       for (u32 g = 0; g < GROUP; ++g) {
         const bool due_g = g < ng && (hot_s[gt_s[g]] & 2u) != 0;
-        const bool act = g < ng && node_active(p, pr[g], due_g);   // lanes past n_local hold an empty Pre
+        Pre prg = pr[g];
+        if (due_g && (prg.busy & 8u)) prg.nd = p.node_due[((tile0 + gt_s[g]) << TILE_SHIFT) + threadIdx.x];
+        const bool act = g < ng && node_active(p, prg, due_g);   // lanes past n_local hold an empty Pre
         if (due_g) {                                         // (warp-uniform) nodes whose own timers run later hand their deadline back to the wheel
-          const u32 wm = warp_min(act ? NO_DEADLINE : sleeping_deadline(pr[g], true));
+          const u32 wm = warp_min(act ? NO_DEADLINE : sleeping_deadline(prg, true));
           if (lane == 0 && wm != NO_DEADLINE) atomicMin(p.tile_due + tile0 + gt_s[g], wm);
-          if (!act && (pr[g].busy & 8u)) SFS_PROBE(20);
+          if (!act && (prg.busy & 8u)) SFS_PROBE(20);
         }
         const u32 bal = __ballot_sync(0xffffffffu, act);
         if (bal) {
@@ -931,7 +964,7 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
           Pre pre;
           if (R1) {
             pre.busy = (a.x >> 16) & 0xffu; pre.any = (a.x >> 24) & 1u; pre.mL = a.y; pre.mJ = a.z; pre.mM = a.w; pre.keep = 0;
-            pre.nd = (hot_s[ti] & 2u) ? p.node_due[vl] : NO_DEADLINE;
+            pre.nd = NO_DEADLINE;
             pre.qw = p.qword[vl];                             // not carried through the list: issued here, in flight with the state loads
             pre.mailmask = pre.any ? 1u : 0u; pre.qmask = pre.qw ? 1u : 0u;
             SFS_COUNT(6, 4);
@@ -940,7 +973,7 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
           }
           u32 mind = NO_DEADLINE, fv_unused = 0;
           int dsusp = 0;
-          const bool pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, false, (hot_s[ti] & 2u) != 0, pol_first, pol_last, c, mind, dsusp, Ahead<FMAX>{}, fv_unused);
+          const bool pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, false, (hot_s[ti] & 2u) != 0, pol_first, pol_last, c, mind, dsusp, Ahead<FMAX>{}, fv_unused, sv_views);
           if (mark && pend) pend_s[g] = 1;
           if (mind != NO_DEADLINE) atomicMin(p.tile_due + tile0 + ti, mind);      // the list mixes tiles: per-lane registration (few active nodes)
           if (dsusp) atomicAdd(&dsusp_s, dsusp);
@@ -988,7 +1021,7 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
     bool pend = false;
     u32 mind = NO_DEADLINE;
     int dsusp = 0;
-    if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, saturated, (hot_s[i] & 2u) != 0, pol_first, pol_last, c, mind, dsusp, ah, first_view);
+    if (vl < p.n_local) pend = process_node<TRACE, FMAX, SHARDED, R1, false>(p, StageView{}, xs, vl, pre, kL, kJ, kM, mark, saturated, (hot_s[i] & 2u) != 0, pol_first, pol_last, c, mind, dsusp, ah, first_view, sv_views);
     if (mark && __any_sync(0xffffffffu, pend) && lane == 0) p.hot_wr[tile0 + i] = 1;
     note_timers(p, tile0 + i, mind, dsusp, &dsusp_s);
     if (SHARDED) wrote_remote |= flush_xwarp(p, xs, false, resv, rlen);
@@ -1000,7 +1033,7 @@ __global__ void __launch_bounds__(BLOCK, MB) tick_kernel(const __grid_constant__
     if (wrote_remote) __threadfence_system();            // peer-window stores are performed before the publish kernel raises the flags
   }
   __syncthreads();
-  finish_tick<TRACE>(p, c, red, dsusp_s);
+  finish_tick<TRACE, R1>(p, c, red, dsusp_s);
 }
 
 #ifndef SERFSIM_EMU   // the TMA pipeline is device-only (bulk copies, mbarriers); the host build of tests/emu uses the direct-load kernel
@@ -1099,7 +1132,7 @@ __global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constan
       Pre pre = {};
       pre.busy = p.busy[vl];
       pre.qw = p.qword[vl];          // 4 B per node, read directly (not worth a sixth bulk copy per stage)
-      pre.nd = (hot_s[ti] & 2u) ? p.node_due[vl] : NO_DEADLINE;
+      pre.nd = NO_DEADLINE;
       u32 fv_unused = 0;
       pend = process_node<TRACE, FMAX, false, true, true>(p, sv, nullptr, vl, pre, kL, kJ, kM, mark, true, (hot_s[ti] & 2u) != 0, pol_first, pol_last, c, mind, dsusp, Ahead<FMAX>{}, fv_unused);
     }
@@ -1110,7 +1143,7 @@ __global__ void __launch_bounds__(BLOCK, 3) tick_kernel_tma(const __grid_constan
   }
 
   __syncthreads();
-  finish_tick<TRACE>(p, c, red, dsusp_s);
+  finish_tick<TRACE, true>(p, c, red, dsusp_s);
 }
 #endif
 
@@ -1127,6 +1160,7 @@ __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__
   if (blockIdx.x == 0 && threadIdx.x == 0) { p.sched[SCHED_IDLE_UNTIL] = 0; if (p.host_idle_until) *p.host_idle_until = 0; }
   long long d_changed = 0, d_pending = 0, d_susp = 0;
   u64 d_hash = 0;
+  u32 d_views = 0;                                         // views left with queued transmits: they have business in the next tick
   for (u32 vl = blockIdx.x * BLOCK + threadIdx.x; vl < p.n_local; vl += gridDim.x * BLOCK) {
     const u32 v = p.first + vl;
     const u64 ns = snap_node[vl];
@@ -1198,6 +1232,7 @@ __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__
       awake |= (r.txl | r.txj | r.txm) != 0 || (watching && (r.mlstate == ML_ALIVE ||
                (r.mlstate == ML_SUSPECT && (u32)__popc(r.mask) - 1u < p.rules.k && !(r.mask & (1u << from_bucket(v))))));
       if (r.mlstate == ML_SUSPECT && r.deadline != 0) { has_timer = true; mind = min(mind, r.deadline); }
+      if (r.txl | r.txj | r.txm) d_views |= 1u << s;
       if (r.inc >= INC_LIMIT) *p.overflow = 1;
     }
     if (p.ue_table.n) {                                        // the partner's event clock and ring (a snapshot, like its records)
@@ -1228,7 +1263,9 @@ __global__ void __launch_bounds__(BLOCK) pushpull_kernel(const __grid_constant__
     if (has_timer) { atomicMin(p.tile_due + (vl >> TILE_SHIFT), mind); p.node_due[vl] = mind; }
   }
   const u64 c = warp_sum64((u64)d_changed), q = warp_sum64((u64)d_pending), ds = warp_sum64((u64)d_susp), h = TRACE ? warp_sum64(d_hash) : 0;
+  d_views = __reduce_or_sync(0xffffffffu, d_views);
   if ((threadIdx.x & 31) == 0) {
+    if (d_views) atomicOr(p.sched + SCHED_VIEWS_NEW, d_views);
     if (c) atomicAdd((unsigned long long*)(p.row + 3), (unsigned long long)c);
     if (q) atomicAdd((unsigned long long*)(p.row + 4), (unsigned long long)q);
     if (ds) atomicAdd(reinterpret_cast<unsigned long long*>(p.sched + SCHED_SUSPECTS), (unsigned long long)ds);
@@ -1272,6 +1309,9 @@ __global__ void __launch_bounds__(BLOCK) drain_kernel(const __grid_constant__ Dr
       until = min(until, (u32)__ldcg(p.sums + (size_t)src * CTRL_FIELDS + 9));
     }
     if (p.host_idle_until) *p.host_idle_until = quiet ? max(until, p.tick + 1) : p.tick + 1;
+    u32 views = 0;                                        // views with business in the next tick: anywhere in the cluster (their mail crosses shards)
+    for (u32 src = 0; src < p.world; ++src) if (src != p.rank) views |= (u32)__ldcg(p.sums + (size_t)src * CTRL_FIELDS + 10);
+    if (views) atomicOr(p.sched_rw + SCHED_VIEWS_NEW, views);
   }
   // same dense / sparse decision as the tick kernel of this tick: in a dense tick the next tick processes every
   // tile anyway, so per-entry tile marking (millions of byte stores onto a few thousand flags) is skipped
@@ -1530,6 +1570,17 @@ void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st) {
   const bool small = p.fanout <= 4;          // the common fan-outs (3, 4) get the 4-wide target array
   if (trace) { if (small) launch_tick_v<true, 4>(p, grid, st); else launch_tick_v<true, 8>(p, grid, st); }
   else { if (small) launch_tick_v<false, 4>(p, grid, st); else launch_tick_v<false, 8>(p, grid, st); }
+}
+// The single-view kernel of a dual launch (SV_SINGLE): the single-slot kernel on the one view that has business (multi-slot plane layout).
+void launch_tick_single_view(const TickParams& p, int grid, cudaStream_t st) {
+  const bool sharded = p.world > 1;
+  if (p.fanout <= 4) {
+    if (sharded) SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<false, 4, true, true, SFS_MB_R1S>)(p);
+    else SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<false, 4, false, true, SFS_MB_R1>)(p);
+  } else {
+    if (sharded) SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<false, 8, true, true, SFS_MB_R1S>)(p);
+    else SFS_LAUNCH(grid, BLOCK, 0, st, tick_kernel<false, 8, false, true, SFS_MB_R1>)(p);
+  }
 }
 void launch_fill_idle_rows(u64* rows, u64* grow_rows, u32 n, const u32* sched, bool trace, cudaStream_t st) {
   if (n) SFS_LAUNCH((n + 127) / 128, 128, 0, st, fill_idle_rows_kernel)(rows, grow_rows, n, sched, trace ? 1 : 0);

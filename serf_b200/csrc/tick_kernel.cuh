@@ -124,11 +124,26 @@ struct TickParams {
   // block): one launch less per tick.  With injectors their kernel still writes windows after this one, and publish_kernel follows it.
   u32* const* peer_ctrl; u32 stamp, xpar, loopback, fuse_publish;
   u32 shard_inv, xcap;        // floor(2^32 / shard_size) (a remote target's shard without a division); staged entries per warp and peer
+  u32 sv_wshift;              // single-view launch: its view's bit in the watch masks (0 in every other launch)
+  u32 sv_mode, views_host, sv_slot, sv_R;    // single-view ticks (SV_*, below): sv_slot = the view the single-view launch works on, sv_R = number of views of the run
   u32 ahead;                  // multi-slot runs: 1 = saturated ticks request node word, peers and the probable first view's record one tile ahead; 2 = every tick (tests); 0 = off (SERFSIM_AHEAD)
   u32* host_idle_until;       // SCHED_IDLE_UNTIL mirrored into mapped pinned host memory: serfsim_run_until_converged does not even launch the ticks the cluster sleeps through
 };
 constexpr u32 SCHED_TICKET = 0, SCHED_IDLE_UNTIL = 1, SCHED_UE_ACTIVITY = 2, SCHED_AWAKE = 3, SCHED_SUSPECTS = 4 /* u64 */,
-              SCHED_LOCAL_QUIET = 6, SCHED_LOCAL_UNTIL = 7 /* sharded runs: this rank's verdict; the drain kernel combines the ranks' */, SCHED_WORDS = 8;
+              SCHED_LOCAL_QUIET = 6, SCHED_LOCAL_UNTIL = 7 /* sharded runs: this rank's verdict; the drain kernel combines the ranks' */,
+              SCHED_VIEWS_NEW = 8 /* single-view ticks: bit s = view s can have business, in the ticks from SCHED_VIEWS_FROM on */, SCHED_VIEWS_NEXT = 9 /* being collected */,
+              SCHED_VIEWS_OLD = 10 /* the set of the tick before SCHED_VIEWS_FROM */, SCHED_VIEWS_FROM = 11, SCHED_WORDS = 12;
+// Single-view ticks (multi-slot runs).  In long stretches of a study exactly one tracked subject is in motion (the suspicion and dead waves
+// of a crash after the leave wave has died down): every node visits the same single view, and the lean single-slot kernel (64 registers,
+// 32 warps per SM, every load requested up front) does that tick in half the time of the multi-slot kernel (128 registers, 16 warps).
+// Which views can have business in tick t+1 is known at the end of tick t: views that sent mail or keep a queue (collected by the tick
+// kernel, the anti-entropy kernel and — across shards — the drain kernel in SCHED_VIEWS_*), plus what the host knows (views_host: every
+// subject that has ever been down — only those are probed, suspected and run timers; all views when the tick carries a host operation or a
+// reaper round).  While exactly ONE subject has ever been down (sv_slot) the host launches BOTH kernels — the single-view one with a
+// parameter block whose planes start at that view and whose subject / down flag are that view's — each looks at the set and one of them
+// returns at once.  SV_CHECK (SERFSIM_SV=2) runs the
+// general kernel alone and raises error 4 if a view outside a one-element set turns out to have business (the set must be a superset).
+constexpr u32 SV_OFF = 0, SV_GENERAL = 1, SV_SINGLE = 2, SV_CHECK = 3;
 constexpr u32 NO_DEADLINE = 0xffffffffu;
 // A tick is skipped (grid-uniform decision of its first instruction) when the last executed tick proved that nothing can happen
 // before SCHED_IDLE_UNTIL and the host scheduled no operation for it.
@@ -140,7 +155,7 @@ __device__ __forceinline__ bool tick_is_idle(const u32* sched, u32 tick, u32 ev_
 // the peers write, then the peers' trace rows of that tick (the device-side sum of the per-tick counters).
 constexpr u32 CTRL_U32 = 2 * 16;                        // [parity][ counts[8] | flags[8] ]
 constexpr u32 CTRL_SUMS_OFF = CTRL_U32 * 4;             // byte offset of u64 sums[2][8][CTRL_FIELDS]  ([parity][source rank][field])
-constexpr u32 CTRL_FIELDS = 10;                         // the 8 trace-row fields, then the rank's scheduler verdict: 8 = quiet (0 / 1), 9 = sleep until
+constexpr u32 CTRL_FIELDS = 11;                         // the 8 trace-row fields, then the rank's scheduler verdict: 8 = quiet (0 / 1), 9 = sleep until, 10 = views with business in the next tick
 constexpr size_t CTRL_BYTES = CTRL_SUMS_OFF + 2 * 8 * CTRL_FIELDS * sizeof(u64);
 struct PublishParams {        // after the tick kernel: tell every peer how much was written and this rank's row, then raise its flag
   u32 world, rank, stamp, xpar;
@@ -173,11 +188,13 @@ struct DrainParams {
   // device-side sum of the tick's trace row over all ranks: grow[i] = my_row[i] + Σ peers' published rows
   const u64* my_row; const u64* sums; u64* grow;
   const u32* gate;
+  u32* sched_rw;              // the same words, writable: the peers' views with business are added to SCHED_VIEWS_CUR
   const u32* sched; u32* host_idle_until;   // the ranks' verdicts combined: every rank hands the same "sleep until" tick to its host
   u32 tick, sleep_on;
 };
 
 void launch_tick(const TickParams& p, bool trace, int grid, cudaStream_t st);
+void launch_tick_single_view(const TickParams& p, int grid, cudaStream_t st);
 void launch_fill_idle_rows(u64* rows, u64* grow_rows, u32 n, const u32* sched, bool trace, cudaStream_t st);
 void launch_pushpull(const TickParams& p, const uint4* snap_rec, const u64* snap_node, bool trace, cudaStream_t st);
 void launch_drain(const DrainParams& p, cudaStream_t st);

@@ -415,6 +415,32 @@ class GossipSim:
 
 
 # ---- synthetic topologies (BASELINE.json configs) -------------------------------------
+def bind_thread_near_gpu(cuda_index):
+    """Pin the calling thread (and the threads it creates afterwards: the CUDA runtime's workers, torch's pinned-memory
+    allocations by first touch) to the CPUs that share a NUMA node with GPU `cuda_index`.  A driver thread on the other socket
+    pays the inter-socket hop on every launch and lands its pinned result buffers in far memory; two runs of the same bench
+    differed by 15 % end to end depending on where the scheduler had put the process.  Returns the CPU set, or None when NVML
+    (nvidia-ml-py) or the affinity call is not available — nothing is changed then."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(cuda_index).uuid)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1} & os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def full_mesh_graph(n):
     """Every node may gossip with every other node (config 1: 256-node full mesh)."""
     col = np.empty((n, n - 1), dtype=np.uint32)

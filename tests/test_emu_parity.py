@@ -176,6 +176,32 @@ def test_multi_slot_requests_one_tile_ahead(ahead, monkeypatch):
         assert L.emu_probe(19) == 0
 
 
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def test_single_view_ticks(mode, monkeypatch):
+    """Multi-slot runs in production mode, exactly one subject ever down: ticks in which only that subject's view has business run the
+    single-slot kernel on it (SERFSIM_SV=1: both kernels launched, the device picks; probe 21 counts the CTAs of single-view kernels
+    that ran).  SERFSIM_SV=2 runs the general kernel alone and fails with error 4 if a view outside a one-element set had business;
+    0 switches the dispatch off.  All three equal the oracle."""
+    import ctypes as C
+    from emu_lib import lib
+    L = lib()
+    L.emu_probe.restype = C.c_ulong
+    monkeypatch.setenv("SERFSIM_SV", mode)
+    L.emu_probe_reset()
+    scs = [scenarios.dissemination_storm(3000, 12, 3, slots=2, seed=3, with_fail=True), scenarios.dissemination_storm(2500, 10, 4, slots=3, seed=5, with_fail=True)]
+    scs += [scenarios.fuzz(k) for k in range(12)] + [scenarios.fuzz_prune(k) for k in range(6)]
+    for sc in scs:
+        o = sc.build(oracle_sim, trace=1)
+        to = o.run_until_converged(sc.max_ticks)
+        f = sc.build(emu_sim, trace=0)
+        assert f.run_until_converged(sc.max_ticks) == to, sc.name
+        assert_same(f, o, sc.slots, with_hash=False)
+    if mode == "1":
+        assert L.emu_probe(21) > 20, L.emu_probe(21)
+    else:
+        assert L.emu_probe(21) == 0
+
+
 def test_config1_shape_100k_nodes():
     """BASELINE configs[1] at full size (100 K-node random graph, fan-out 3) through the host-compiled kernels:
     391 tiles over 4 CTAs, dense and sparse ticks, production mode (trace off)."""
