@@ -382,8 +382,10 @@ def main():
         tpath = os.path.join(ROOT, "profiles", f"r2_traffic_{args.workload}.json")      # ncu capture of THIS workload with the shipped kernel
         if world == 1 and os.path.exists(tpath):
             tj = json.load(open(tpath))
-            traffic = tj.get("dram_bytes_per_launch")
-            traffic_src = f"{os.path.relpath(tpath, ROOT)} (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per tick_kernel launch; {tj.get('source', '')})"
+            # DRAM bytes of ONE run of this workload (every tick_kernel launch of the capture) over the launches of one bench step: the same
+            # denominator as algorithmic_bytes_per_launch (launches that return at once — gated ticks, the idle half of a dual launch — count in both)
+            traffic = (tj.get("dram_bytes_read", 0.0) + tj.get("dram_bytes_write", 0.0)) / max(1.0, launches / args.steps)
+            traffic_src = f"{os.path.relpath(tpath, ROOT)} (ncu dram__bytes_read.sum + dram__bytes_write.sum over all tick_kernel launches of one run, per launch of a bench step; {tj.get('source', '')})"
         # per-GPU: each GPU runs its own tick kernel over its shard; algorithmic bytes split evenly
         achieved = (total_eu / world) * be / (dev_ms * 1e-3) / 1e9
         h2d = len(sc.ops) * 12

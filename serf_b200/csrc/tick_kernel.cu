@@ -190,12 +190,17 @@ __device__ __forceinline__ void deliver(const TickParams& p, XStage* xs, u32* pl
     const u64 e = ((u64)val1 << 32) | ((u64)(s + p.sv_wshift) << 28) | ((u64)kind << 26) | dloc;   // (a single-view launch numbers its view 0: the entry carries the real one)
     // warp-aggregated append: the lanes of this call that target the same shard reserve their slots with ONE
     // shared-memory atomic on the warp's own counter (divergent callers of the same warp may interleave: keep it atomic)
+#ifdef SFS_XSTAGE_MATCH                           // A/B: one shared atomic per distinct shard of the call (match_any + leader + shuffle)
     const u32 peers = __match_any_sync(__activemask(), shard);
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5, leader = __ffs(peers) - 1;
     u32 base = 0;
     if (lane == leader) base = atomicAdd(&xs->cnt[wid][shard], (u32)__popc(peers));
     base = __shfl_sync(peers, base, leader);
     const u32 pos = base + (u32)__popc(peers & ((1u << lane) - 1u));
+#else                                             // one shared atomic per lane: the hardware serialises the lanes that hit the same counter
+    const u32 wid = threadIdx.x >> 5;
+    const u32 pos = atomicAdd(&xs->cnt[wid][shard], 1u);
+#endif
     if (pos < xcap(p)) {
       xs->buf[wid * XW_TOTAL + xseg(p, shard) + pos] = e;
     } else {                                   // buffer full: write this one straight through
