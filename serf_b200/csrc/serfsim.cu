@@ -1279,7 +1279,7 @@ int serfsim_tick_times(serfsim_t* h, uint32_t first_tick, uint32_t n, float* ms_
 }
 
 // ---- multi-GPU: CUDA IPC windows ----------------------------------------------------------
-struct comm_blob { cudaIpcMemHandle_t data[2]; cudaIpcMemHandle_t ctrl; cudaIpcMemHandle_t snap_rec, snap_node, anomaly, ue_snap; u32 win_cap; u32 rank; u32 has_snap; u32 has_ue_snap; };
+struct comm_blob { cudaIpcMemHandle_t data[2]; cudaIpcMemHandle_t ctrl; cudaIpcMemHandle_t snap_rec, snap_node, anomaly, ue_snap; u32 win_cap; u32 rank; u32 has_snap; u32 has_ue_snap; unsigned char dev_uuid[16]; };
 
 size_t serfsim_comm_blob_size(void) { return sizeof(comm_blob); }
 
@@ -1292,6 +1292,9 @@ int serfsim_comm_export(serfsim_t* h, void* blob) {
   CU(cudaIpcGetMemHandle(&b.anomaly, h->d_anomaly));
   if (h->d_ue_snap) { CU(cudaIpcGetMemHandle(&b.ue_snap, h->d_ue_snap)); b.has_ue_snap = 1; }
   b.win_cap = h->win_cap; b.rank = (u32)h->cfg.rank;
+#ifndef SERFSIM_EMU
+  { int dev = 0; cudaDeviceProp pr{}; CU(cudaGetDevice(&dev)); CU(cudaGetDeviceProperties(&pr, dev)); memcpy(b.dev_uuid, pr.uuid.bytes, 16); }
+#endif
   if (h->d_snap_rec) {                              // push-pull rounds are on: partners on other GPUs read these
     CU(cudaIpcGetMemHandle(&b.snap_rec, h->d_snap_rec)); CU(cudaIpcGetMemHandle(&b.snap_node, h->d_snap_node));
     b.has_snap = 1;
@@ -1314,6 +1317,10 @@ int serfsim_comm_connect(serfsim_t* h, const void* blobs) {
   std::vector<const uint4*> pus(8, nullptr);
   for (int r = 0; r < W; ++r) {
     if (bs[r].rank != (u32)r || bs[r].win_cap != h->win_cap) return fail(SERFSIM_E_COMM, "blob order / window size mismatch");
+#ifndef SERFSIM_EMU
+    // one rank per GPU: the drain kernel spins on its peers' flags, and a peer that shares this GPU may never get an SM to raise them
+    for (int r2 = 0; r2 < r; ++r2) if (!h->loopback && memcmp(bs[r].dev_uuid, bs[r2].dev_uuid, 16) == 0) return fail(SERFSIM_E_COMM, "two ranks share one GPU (one process per GPU is required)");
+#endif
     if ((bs[r].has_snap != 0) != (h->d_snap_rec != nullptr)) return fail(SERFSIM_E_COMM, "push_pull_interval_ticks differs between ranks");
     if (r == h->cfg.rank) { pd[0][r] = h->d_win_data[0]; pd[1][r] = h->d_win_data[1]; pc[r] = h->d_ctrl; psr[r] = h->d_snap_rec; psn[r] = h->d_snap_node; pan[r] = h->d_anomaly; pus[r] = h->d_ue_snap; continue; }
     void* ptr = nullptr;
