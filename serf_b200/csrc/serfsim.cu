@@ -901,8 +901,11 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
   // (tick_kernel.cuh: Gate).  The host reads two words per chunk; ranks of a sharded run reach the same verdict from the same
   // device-summed rows, so there is no host collective in the loop.  Ticks launched past the first quiescent one never
   // execute: nothing to rewind on the device, the logical clock (and the exchange epoch) is simply set back.
-  // Chunks grow (16, 32, 64, 128): short runs overshoot by a few gated launches, long ones synchronise rarely.
-  u32 chunk = 16, chunk_max = h->cfg.world_size > 1 ? 32 : 128;    // sharded: ticks launched into a sleeping cluster still execute
+  // Chunks start small and grow (8, 16, 32) — and start small again after every jump over a sleeping stretch: a tick launched into a
+  // cluster that has just gone to sleep (or has just finished) still costs its launches (5 – 11 µs: two kernels per tick in multi-slot
+  // runs; in sharded runs it even executes), a synchronisation costs less than two of them.  The leave + fail study (877 ticks, ≈ 70 of
+  // them busy) launched 382 ticks per run with chunks of up to 128.
+  u32 chunk = 8, chunk_max = 32;
   if (const char* e = getenv("SERFSIM_CHUNK")) chunk = chunk_max = (u32)std::max(1, atoi(e));
   const bool host_jump = !getenv("SERFSIM_NO_JUMP");
   const u32 pp = (u32)std::max(0, h->cfg.push_pull_interval_ticks);
@@ -964,6 +967,7 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
           h->launch_log.push_back(k == 0 ? 1u : 0u);
         }
         h->tick += n_skip;
+        if (!getenv("SERFSIM_CHUNK")) chunk = 8;            // the busy stretch after a sleep is short as a rule
       }
       probe = false;
     } else {
