@@ -936,6 +936,7 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
     const u32 n = probe ? 1u : std::min(chunk, max_ticks - (h->tick - start));
     if ((rc = launch_ticks(h, n))) return rc;
     CU(cudaStreamSynchronize(h->stream));
+    if (getenv("SERFSIM_DEBUG_LOOP")) fprintf(stderr, "loop: launched %u ticks -> tick %u, ctl %u %u until %u probe %d chunk %u\n", n, h->tick, h->pin_ctl[0], h->pin_ctl[1], h->pin_ctl[2], (int)probe, chunk);
     if (*(volatile u32*)h->pin_ctl) {
       const u32 t = ((volatile u32*)h->pin_ctl)[1];
       stop_at(t);
@@ -948,7 +949,15 @@ int serfsim_run_until_converged(serfsim_t* h, uint32_t max_ticks, uint32_t* tick
     // preceded by one single-tick launch (`probe`).
     const u32 until = ((volatile u32*)h->pin_ctl)[2];
     const bool sleeping = host_jump && until > h->tick && h->tick - start < max_ticks;      // sharded runs: every rank reads the same word
-    if (sleeping && probe) {
+    // … and the probe tick itself must have been an idle one: with a host operation in it (which may well change nothing) its row is a new
+    // one that no gate has judged yet — the next launch is another single tick (found by fuzz scenario 16 once the launch chunks ended
+    // on the tick before a no-op operation: the run was reported quiescent at the end of the jump instead of at the operation's tick)
+    bool probe_was_idle = true;
+    if (probe && h->tick > 0) {
+      auto it = std::lower_bound(h->ops.begin(), h->ops.end(), h->tick - 1, [](const HostOp& o, u32 tt) { return o.tick < tt; });
+      probe_was_idle = it == h->ops.end() || it->tick != h->tick - 1;
+    }
+    if (sleeping && probe && probe_was_idle) {
       u32 stop = until;
       auto nxt = std::lower_bound(h->ops.begin(), h->ops.end(), h->tick, [](const HostOp& o, u32 tt) { return o.tick < tt; });
       if (nxt != h->ops.end()) stop = std::min(stop, nxt->tick);

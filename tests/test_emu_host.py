@@ -200,3 +200,17 @@ def test_results_async_returns_the_getters_values():
         assert (st == g.member_status(s)).all() and (lt == g.status_ltime_u32(s)).all()
         if s == 0:
             assert (ck == g.lamport_time_u32()).all()
+
+
+def test_jump_after_a_probe_tick_with_a_host_operation():
+    """The host jumps over a sleeping stretch after ONE single-tick launch whose gate has judged the row before it.  If that probe tick
+    carries a host operation (here one that changes nothing), its own row is new and unjudged: the jump must wait for one more single tick.
+    Fuzz scenario 16 with the default launch chunks (8, 16, 32, 32 → the chunk ends on tick 87, the no-op operation sits at tick 88, the
+    reaper at 99): the run was reported quiescent at tick 98 instead of 88."""
+    sc = scenarios.fuzz(16)
+    sc.max_ticks = 1500
+    o = sc.build(oracle_sim, trace=1)
+    to = o.run_until_converged(sc.max_ticks)
+    for trace in (1, 0):
+        g = sc.build(emu_sim, trace=trace)
+        assert g.run_until_converged(sc.max_ticks) == to
