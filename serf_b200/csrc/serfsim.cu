@@ -746,7 +746,7 @@ int serfsim_create(const serfsim_config_t* cfg, serfsim_t** out) {
     double factor = 1.25;
     if (const char* e = getenv("SERFSIM_WIN_FACTOR")) factor = atof(e);
     // … plus the entries the warps of the tick kernel reserve ahead and do not fill (flush_xwarp: at most XW_RESERVE_MAX = 128 per warp and peer)
-    const double pad = (double)tick_grid_size(h->count, h->ctas_per_sm) * 8.0 * 160.0;
+    const double pad = (double)std::max(tick_grid_size(h->count, h->ctas_per_sm), h->grid_sv) * 8.0 * 160.0;   // (the single-view kernel of a multi-slot run has the larger grid)
     double cap = (double)h->shard_size * cfg->fanout * h->R * 3.0 * factor / cfg->world_size + 4096.0 + pad;
     h->win_cap = (u32)std::min(cap, 4.0e9);
     h->win_cap_base = h->win_cap;
