@@ -77,3 +77,15 @@ def test_product_loader_refuses_the_host_compiled_test_build():
     env = dict(os.environ, SERFSIM_LIB=emu_lib.build())
     r = subprocess.run([sys.executable, "-c", "from serf_b200 import sim; sim.load_library()"], cwd=ROOT, env=env, capture_output=True, text=True)
     assert r.returncode != 0 and "refusing to use it as the product" in r.stderr
+
+
+def test_bind_thread_near_gpu_without_a_gpu_changes_nothing():
+    """The NUMA helper of the Python driver: without a GPU / NVML it returns None and leaves the thread's affinity alone."""
+    import os
+    from serf_b200 import bind_thread_near_gpu
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: covered by bench.py")
+    before = os.sched_getaffinity(0)
+    assert bind_thread_near_gpu(0) is None
+    assert os.sched_getaffinity(0) == before
