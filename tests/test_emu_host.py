@@ -214,3 +214,26 @@ def test_jump_after_a_probe_tick_with_a_host_operation():
     for trace in (1, 0):
         g = sc.build(emu_sim, trace=trace)
         assert g.run_until_converged(sc.max_ticks) == to
+
+
+@pytest.mark.parametrize("seed", range(1000, 1012))
+def test_late_operations_in_sleeping_stretches(seed, monkeypatch):
+    """Fuzz scenarios with extra (mostly no-op) host operations scattered over the 300 ticks after the busy part — the convergence loop's
+    probe / jump / gate rules with the default launch chunks, in trace mode, and with a small fixed chunk (a sample of
+    tools/campaigns/late_ops.py)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("late_ops_gen", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "campaigns", "late_ops_gen.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    sc = gen.late(seed)
+    o = sc.build(oracle_sim, trace=1)
+    to = o.run_until_converged(sc.max_ticks)
+    for trace, chunk in ((0, None), (1, None), (0, str(2 + seed % 11))):
+        if chunk:
+            monkeypatch.setenv("SERFSIM_CHUNK", chunk)
+        else:
+            monkeypatch.delenv("SERFSIM_CHUNK", raising=False)
+        g = sc.build(emu_sim, trace=trace)
+        assert g.run_until_converged(sc.max_ticks) == to
+        assert_same(g, o, sc.slots, with_hash=bool(trace))

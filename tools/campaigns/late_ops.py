@@ -11,21 +11,9 @@ from serf_b200 import scenarios
 from serf_b200.sim import Op
 import test_emu_parity as P
 import test_emu_multi as M
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
-def late(seed):
-    sc = scenarios.fuzz(seed)
-    rng = np.random.Generator(np.random.Philox(seed + 777))
-    used = {(t, node) for (t, _, node, _) in sc.ops}
-    t0 = max([t for (t, *_) in sc.ops] + [0])
-    for _ in range(int(rng.integers(1, 7))):
-        t = t0 + int(rng.integers(1, 300))
-        kind = rng.choice([Op.JOIN, Op.FORCE_LEAVE, Op.FORCE_LEAVE, Op.REJOIN, Op.FAIL, Op.LEAVE])
-        s = int(rng.integers(0, sc.slots))
-        node = int(rng.integers(0, sc.n)) if kind == Op.FORCE_LEAVE else int(sc.subjects[s])
-        if (t, node) not in used:
-            used.add((t, node)); sc.ops.append((t, int(kind), node, s))
-    sc.name = f"late_{seed}"; sc.max_ticks = 3000
-    return sc
+from late_ops_gen import late
 
 bad = []; t_start = time.time()
 for seed in range(1000, 1400):
