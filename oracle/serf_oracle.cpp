@@ -29,6 +29,9 @@
 // Build: see oracle/Makefile (g++ -O2 -shared -fPIC).  Plain C ABI at the bottom (ctypes).
 
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <memory>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -601,6 +604,48 @@ struct UeNodeB {
 struct UeMsg { u32 dst, e; };
 struct EventB { u32 tick, op, node, slot; };
 
+// Persistent workers of the threaded tick loop (test infrastructure: the timed CPU baseline and the full-size checks).  A tick used to create and
+// join one thread per worker — twice with anti-entropy on —, i.e. 64 thread creations and affinity calls per tick on the bench hosts: for a study
+// whose ticks are mostly idle that was most of the run time, and it made the timings depend on the box (round-1 review: "not a stable anchor").
+// The workers are now created once per instance, pinned once and parked on a condition variable between ticks.
+struct WorkerPool {
+  std::vector<std::thread> th;
+  std::mutex m;
+  std::condition_variable cv_go, cv_done;
+  const std::function<void(u32)>* job = nullptr;
+  unsigned long long gen = 0;
+  u32 left = 0;
+  bool stop = false;
+  WorkerPool(u32 T, const std::vector<int>& pin) {
+    for (u32 c = 0; c < T; ++c) th.emplace_back([this, c, pin] {
+      if (!pin.empty()) { cpu_set_t set; CPU_ZERO(&set); CPU_SET(pin[c % pin.size()], &set); pthread_setaffinity_np(pthread_self(), sizeof(set), &set); }
+      unsigned long long seen = 0;
+      std::unique_lock<std::mutex> lk(m);
+      for (;;) {
+        cv_go.wait(lk, [&] { return stop || gen != seen; });
+        if (stop) return;
+        seen = gen;
+        const std::function<void(u32)>* f = job;
+        lk.unlock();
+        (*f)(c);
+        lk.lock();
+        if (--left == 0) cv_done.notify_one();
+      }
+    });
+  }
+  void run(const std::function<void(u32)>& f) {              // f(c) on every worker c; returns when all are done
+    std::unique_lock<std::mutex> lk(m);
+    job = &f; left = (u32)th.size(); ++gen;
+    cv_go.notify_all();
+    cv_done.wait(lk, [&] { return left == 0; });
+  }
+  ~WorkerPool() {
+    { std::lock_guard<std::mutex> lk(m); stop = true; }
+    cv_go.notify_all();
+    for (auto& t : th) t.join();
+  }
+};
+
 struct TickSim {
   serfsim_config_t cfg;
   u32 N, R, tick = 0;
@@ -636,6 +681,11 @@ struct TickSim {
   std::vector<u8> anomaly;                                     // per node: sender flag
   u64 byz_tot[3] = {0, 0, 0};                                  // injected entries, injected (peer, subject) pairs, senders flagged
   int threads = 1;
+  std::unique_ptr<WorkerPool> pool; std::vector<int> pool_pin;   // workers of the threaded tick loop (created on first use, re-created when threads / pin change)
+  void run_workers(u32 T, const std::function<void(u32)>& f) {
+    if (!pool || pool->th.size() != T || pool_pin != pin) { pool.reset(); pool.reset(new WorkerPool(T, pin)); pool_pin = pin; }
+    pool->run(f);
+  }
   std::vector<int> pin;                                        // optional: worker c of the tick loop runs on logical CPU pin[c % size] (stable timings)
   std::string err;
   void pin_worker(u32 c) const {
@@ -1005,7 +1055,7 @@ struct TickSim {
     }
     };
     if (T == 1) work(0);
-    else { std::vector<std::thread> th; for (u32 c = 0; c < T; ++c) th.emplace_back([&, c] { pin_worker(c); work(c); }); for (auto& x : th) x.join(); }
+    else run_workers(T, work);
     mail.swap(mail_next);
     if (byz_n) {
       // Verdicts: every stale entry posted this tick is judged against its receiver's view as it stands when the node loop
@@ -1093,7 +1143,7 @@ struct TickSim {
         }
       };
       if (T == 1) ppwork(0);
-      else { std::vector<std::thread> th; for (u32 c = 0; c < T; ++c) th.emplace_back([&, c] { pin_worker(c); ppwork(c); }); for (auto& x : th) x.join(); }
+      else run_workers(T, ppwork);
       for (u32 c = 0; c < T; ++c) { ue_tot[2] += pp_ue[(size_t)c * 3]; ue_tot[3] += pp_ue[(size_t)c * 3 + 1]; ue_tot[4] += pp_ue[(size_t)c * 3 + 2]; }
     }
     serfsim_tick_row_t row{};
